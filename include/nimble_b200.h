@@ -1,0 +1,202 @@
+/* nimble_b200.h — C ABI of the B200-native replacement for nimble-aligner's read-alignment hot path.
+ *
+ * The reference (BimberLab/nimble-aligner, pure Rust) has no FFI of its own; its boundary is the Rust library API.
+ * Every entry point below names the reference interface it stands in for (paths under /root/reference).  A Rust (or
+ * C++) host binds these with `extern "C"`; INTEGRATION.md shows the binding.  Conventions: plain pointers and sizes,
+ * POD structs, no C++/torch types, no exceptions across the boundary; every call returns 0 or a negative nb_status
+ * and nb_last_error() holds the message (the reference panics with a message instead — src/bin/main.rs:37,46,90,128).
+ * The caller owns all host buffers; the library owns device memory.  An nb_index is immutable after build and may be
+ * shared by several nb_ctx on the same device (the reference shares Arc<Vec<PseudoAligner>>, src/process/bam.rs:152-154).
+ * There is NO CPU fallback: every compute entry point fails with NB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef NIMBLE_B200_H
+#define NIMBLE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum nb_status {
+  NB_OK = 0,
+  NB_ERR_INVALID = -1,      /* bad argument */
+  NB_ERR_IO = -2,           /* file could not be read / written */
+  NB_ERR_PARSE = -3,        /* library JSON malformed or a config value has the wrong type (reference: expect() panics) */
+  NB_ERR_CONFIG = -4,       /* sanity_check_align_config failed (src/reference_library.rs:209-226) */
+  NB_ERR_UNSUPPORTED = -5,  /* input outside what the device path represents; message says what */
+  NB_ERR_CUDA = -6,         /* CUDA runtime error, or no usable device */
+  NB_ERR_OVERFLOW = -7,     /* a device scratch arena overflowed; message says which knob to raise */
+  NB_ERR_FEATURE_NOT_FOUND = -8 /* unmap() would panic "Feature not found in reference columns" (src/align.rs:861) */
+} nb_status;
+
+/* LibraryChemistry, src/align.rs:97-103; strings of src/bin/main.rs:40-47 */
+enum { NB_CHEM_UNSTRANDED = 0, NB_CHEM_FIVEPRIME = 1, NB_CHEM_THREEPRIME = 2, NB_CHEM_NONE = 3 };
+
+/* FilterReason, src/align.rs:32-51, same order (Display strings: nb_reason_str) */
+enum {
+  NB_R_SCORE_BELOW_THRESHOLD = 0, NB_R_DISCARDED_MULTIPLE_MATCH, NB_R_DISCARDED_NONZERO_MISMATCH, NB_R_NO_MATCH,
+  NB_R_NO_MATCH_AND_SCORE_BELOW_THRESHOLD, NB_R_DIFFERENT_FILTER_REASONS, NB_R_NOT_MATCHING_PAIR,
+  NB_R_FORCE_INTERSECT_FAILURE, NB_R_SHORT_READ, NB_R_MAX_HITS_EXCEEDED, NB_R_HIGH_ENTROPY, NB_R_SUCCESSFUL_MATCH,
+  NB_R_STRAND_WAS_WRONG, NB_R_TRIAGE_EMPTY_EQUIVALENCE_CLASS, NB_R_ABOVE_MISMATCH_THRESHOLD,
+  NB_R_SKIPPED_ALIGN_DUE_TO_UNPAIRED_DUMMY, NB_R_NONE
+};
+
+/* AlignFilterConfig, src/align.rs:80-95 (field meaning identical; bools as int32) */
+typedef struct nb_config {
+  uint64_t reference_genome_size;
+  double score_percent;
+  uint64_t score_threshold;
+  uint64_t num_mismatches;
+  int32_t discard_nonzero_mismatch;
+  int32_t discard_multiple_matches;
+  int32_t score_filter;
+  int32_t intersect_level;       /* 0 NoIntersect, 1 IntersectWithFallback, 2 ForceIntersect */
+  int32_t require_valid_pair;
+  int32_t strand_filter;         /* NB_CHEM_* */
+  uint64_t discard_multi_hits;
+  uint64_t max_hits_to_report;
+  double trim_strictness;
+  uint64_t trim_target_length;
+} nb_config;
+
+typedef struct nb_library nb_library;  /* Reference + AlignFilterConfig, src/reference_library.rs:11-17 */
+typedef struct nb_index nb_index;      /* PseudoAligner = Pseudoaligner<Kmer30>, src/align.rs:21 */
+typedef struct nb_ctx nb_ctx;          /* one (GPU, stream) execution context holding the aggregation state */
+
+const char* nb_last_error(void);                 /* thread-local message of the last failing call */
+const char* nb_reason_str(int reason);           /* Display for FilterReason, src/align.rs:53-77 */
+const char* nb_version(void);
+
+/* ---- reference_library::get_reference_library(path, strand_filter) -> (AlignFilterConfig, Reference)
+ *      src/reference_library.rs:20-174: parses the 2-object JSON, U->T, appends the "name§rev" row after every row. */
+int nb_library_load_json(const char* path, int strand_filter, nb_library** out);
+int nb_library_parse_json(const char* text, size_t len, int strand_filter, nb_library** out);
+/* Build a Reference directly (what the reference's tests do by constructing the struct, src/align.rs:1029-1040):
+ * column-major strings, rows already final (no §rev rows are added). */
+int nb_library_from_columns(const char* const* headers, uint32_t n_headers, const char* const* const* columns,
+                            uint32_t n_rows, uint32_t group_on, uint32_t sequence_name_idx, uint32_t sequence_idx,
+                            const nb_config* cfg, nb_library** out);
+void nb_library_free(nb_library*);
+int nb_library_get_config(const nb_library*, nb_config* out);
+int nb_library_set_config(nb_library*, const nb_config* cfg);      /* e.g. --trim override, src/bin/main.rs:109-114 */
+uint32_t nb_library_n_rows(const nb_library*);                     /* rows incl. §rev rows */
+uint32_t nb_library_n_headers(const nb_library*);
+const char* nb_library_header(const nb_library*, uint32_t col);
+const char* nb_library_value(const nb_library*, uint32_t col, uint32_t row);
+uint32_t nb_library_group_on(const nb_library*);
+uint32_t nb_library_sequence_name_idx(const nb_library*);
+uint32_t nb_library_sequence_idx(const nb_library*);
+/* tests/basic-cases.rs:29-36 mutate the Reference: push a column and point group_on at it */
+int nb_library_push_column(nb_library*, const char* header, const char* const* values, uint32_t n_rows, int set_group_on);
+
+/* ---- utils::get_reference_sequence_data + debruijn_mapping::build_index::build_index::<Kmer30>(seqs, names, {}, cores)
+ *      src/utils.rs:7-24, src/bin/main.rs:117-128.  Host build of the coloured compacted stranded de Bruijn graph
+ *      (k = 30) into the flat GPU layout (DESIGN.md "Index layout"); the device copy is made by nb_ctx_create. */
+int nb_index_build(const nb_library* lib, int n_threads, nb_index** out);
+int nb_index_build_from_sequences(const uint8_t* seq_ascii, const uint64_t* seq_off, uint32_t n_seqs, int n_threads,
+                                  nb_index** out);
+void nb_index_free(nb_index*);
+/* out[0..7] = n_kmers, n_nodes, n_colours, colour_elems, unitig_bases, table_slots, device_bytes, n_sequences */
+int nb_index_stats(const nb_index*, uint64_t* out8);
+/* canonical text dump (one line per unitig, sorted) used by the parity tests; returns bytes needed */
+uint64_t nb_index_dump(const nb_index*, char* buf, uint64_t cap);
+
+/* ---- execution context */
+int nb_device_count(void);
+int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void* cuda_stream /* NULL: own stream */,
+                  nb_ctx** out);
+void nb_ctx_free(nb_ctx*);
+int nb_ctx_set_config(nb_ctx*, const nb_config* cfg);   /* config is read by pseudoalign / filter_and_coerce per call */
+int nb_ctx_sync(nb_ctx*);
+/* tuning knobs: "max_batch_pairs", "ec_arena_entries", "callset_slots", "key_slots", "agg_slots", "count_work" */
+int nb_ctx_set_option(nb_ctx*, const char* name, uint64_t value);
+
+/* pinned host memory for the caller's double-buffered batches (src/parse readers feed these) */
+void* nb_host_alloc(size_t bytes);
+void nb_host_free(void*);
+
+enum { NB_MEM_HOST = 0, NB_MEM_DEVICE = 1 };
+enum { NB_FLAG_SKIP_ALIGN = 1 /* metadata[37]=="TRUE", src/align.rs:527 */, NB_FLAG_REVCOMP = 2 /* REVERSE, src/process/bam.rs:407-415 */ };
+
+/* One batch of read pairs = the iterators score::call receives (src/score.rs:14-31).  Sequences are ASCII bases
+ * (DnaString::from_acgt_bytes semantics: ACGT either case, anything else -> A), concatenated, with n_pairs+1 offsets.
+ * r2 == NULL: single-end (mate_sequences = None).  q1/q2: raw Phred bytes (BAM record.qual(), no -33) laid out with
+ * the same offsets; NULL = no metadata (FASTQ mode: no trimming, src/align.rs:521-525).  flags1/flags2: NB_FLAG_*
+ * per pair side or NULL.  scope_id: aggregation scope per pair (the (UMI,CB) group of src/process/bam.rs:200-221),
+ * non-decreasing; NULL = one whole-run scope (src/process/fastq.rs:15-29).  Every scope must be complete within one
+ * call: a scoped batch is de-duplicated and folded into the (cell, callset) count table before the call returns. */
+typedef struct nb_batch {
+  uint64_t n_pairs;
+  int32_t location;            /* NB_MEM_HOST (pinned recommended) or NB_MEM_DEVICE */
+  uint32_t max_read_len;       /* longest read in the batch; 0 = let the library scan the offsets (host batches only) */
+  const uint8_t* r1; const uint64_t* r1_off;
+  const uint8_t* r2; const uint64_t* r2_off;
+  const uint8_t* q1; const uint8_t* q2;
+  const uint8_t* flags1; const uint8_t* flags2;
+  const uint32_t* scope_id;
+  const uint32_t* cell_id;     /* optional with scope_id: row key of the count table (e.g. the cell barcode); NULL = scope_id */
+} nb_batch;
+
+/* Per-read outcome of align::pseudoalign (src/align.rs:945-989): reason is SuccessfulMatch when the read passed;
+ * score / mismatches are map_read_with_mismatch's coverage and mismatch totals (0 when it returned None). */
+typedef struct nb_read_result {
+  uint8_t reason; uint8_t pass; uint16_t score; uint16_t mismatches; uint16_t trimmed_len; uint32_t ec_len; uint32_t ec_hash;
+} nb_read_result;
+/* Per-pair outcome: filter reasons as score_sequences records them (src/align.rs:586-600), triage as
+ * filter_and_coerce_sequence_call_orientations records it (233-241), callset = id into nb_counts of this ctx
+ * (0xFFFFFFFF none).  `insertable`: the pair reached score_map.insert (src/align.rs:685). */
+typedef struct nb_pair_result {
+  uint32_t callset; uint8_t triage; uint8_t fr1; uint8_t fr2; uint8_t insertable; uint64_t key_lo; uint64_t key_hi;
+} nb_pair_result;
+
+/* score::call on one batch (src/score.rs:14-46 -> align::get_calls src/align.rs:392-467): maps every read, applies
+ * thresholds, pair / strand / orientation logic and folds the pairs into the context's per-scope de-duplicated
+ * callset counts.  reads_out (2*n_pairs entries when paired, else n_pairs; side-major per pair: [2p]=sequence,
+ * [2p+1]=mate) and pairs_out may be NULL.  Output buffers follow batch->location.  Asynchronous on the context's
+ * stream: host buffers may be reused after nb_ctx_sync() or after the second following nb_align_batch() returns. */
+int nb_align_batch(nb_ctx*, const nb_batch* batch, nb_read_result* reads_out, nb_pair_result* pairs_out);
+/* Debug / parity: full equivalence class of every read of the LAST batch: ec_off (n_reads+1) and ids. Host buffers. */
+int nb_last_batch_ecs(nb_ctx*, uint64_t* ec_off, uint32_t* ec_ids, uint64_t ec_cap, uint64_t* ec_total);
+
+/* Result of get_calls for the scopes seen since the last nb_counts_reset: rows (scope, callset, count) with the
+ * callset dictionary.  Callset c = group indices callset_items[callset_off[c] .. callset_off[c+1]) into the library's
+ * group-name table (nb_library_group_name); rows are sorted by scope then by Vec<String> Ord of the callset
+ * (utils::sort_score_vector, src/utils.rs:54-59).  Pointers stay valid until the next finalize/reset/free. */
+typedef struct nb_counts {
+  uint64_t n_rows; const uint32_t* row_scope; const uint32_t* row_callset; const int64_t* row_count;
+  uint64_t n_callsets; const uint64_t* callset_off; const uint32_t* callset_items;
+  uint64_t n_pairs_seen; uint64_t n_unique_keys;
+  uint64_t n_slots; const uint32_t* slot_to_callset;   /* nb_pair_result.callset (dictionary slot) -> callset id here */
+} nb_counts;
+int nb_counts_finalize(nb_ctx*, nb_counts* out);
+int nb_counts_reset(nb_ctx*);
+uint32_t nb_library_n_groups(const nb_library*);
+const char* nb_library_group_name(const nb_library*, uint32_t group);
+
+/* multi-GPU merge of the whole-run scope.  Reads shard over ranks with the index replicated; counts
+ * are over unique read_keys of the whole run, so ranks exchange their de-duplication records by key range
+ * (all-to-all over NCCL, driven by the host), re-import the partition they own and finalize; the per-callset counts
+ * are then summed across ranks (all-reduce).  Records are 32 bytes {key_lo, key_hi, order = global pair index,
+ * callset_tag}; dev_records are device pointers.  Callset dictionaries travel as (tag, len, items[gcap]) rows. */
+int nb_keys_export_count(nb_ctx*, uint64_t* n);
+int nb_keys_export(nb_ctx*, void* dev_records, uint64_t cap, uint64_t pair_index_base);
+int nb_keys_import(nb_ctx*, const void* dev_records, uint64_t n);
+int nb_callsets_export(nb_ctx*, uint64_t* tags, uint32_t* lens, uint32_t* items, uint64_t cap, uint64_t* n_out, uint32_t* gcap_out);
+int nb_callsets_import(nb_ctx*, const uint64_t* tags, const uint32_t* lens, const uint32_t* items, uint64_t n);
+
+/* timing of the dominant kernel (seed_walk_map), CUDA events on the launching stream: out[0]=launches, out[1]=total ms,
+ * out[2]=reads processed, out[3]=all kernels launched by this ctx since reset */
+int nb_ctx_kernel_stats(nb_ctx*, double* out4, int reset);
+/* work counters of k_map when option "count_work" is 1: out[0..3] = hash probes, unitigs visited, bases compared,
+ * colour ids touched (the terms of the algorithmic-bytes formula, DESIGN.md "Roofline") */
+int nb_ctx_work_counters(nb_ctx*, uint64_t* out4);
+
+/* ---- drivers: process::fastq::process (src/process/fastq.rs:7-30) and utils::write_to_tsv (src/utils.rs:27-51) */
+int nb_write_fastq_tsv(const char* path, const nb_library* lib, const nb_counts* counts);
+int nb_process_fastq(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,
+                     uint32_t n_refs, int strand_filter, int num_cores, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

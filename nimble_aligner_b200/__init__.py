@@ -1,0 +1,395 @@
+"""nimble_aligner_b200 — B200-native replacement for nimble-aligner's read-alignment hot path.
+
+Python is only the test / bench harness here: everything below is a thin ctypes binding of the C ABI declared in
+``include/nimble_b200.h`` (built by ``nimble_aligner_b200/build.py`` into ``libnimble_b200.so``).  Names mirror the
+reference's library entry points (paths under /root/reference):
+
+  get_reference_library        src/reference_library.rs:20
+  get_reference_sequence_data  src/utils.rs:7
+  build_index                  debruijn_mapping::build_index::build_index::<Kmer30>  (src/bin/main.rs:121-128)
+  get_calls / call             src/align.rs:392 / src/score.rs:14
+  process_fastq                src/process/fastq.rs:7
+
+There is no CPU fallback: if the shared library is missing or no sm_100 device is present, calls raise NbError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libnimble_b200.so")
+
+CHEM = {"unstranded": 0, "fiveprime": 1, "threeprime": 2, "none": 3}
+REASONS = ["ScoreBelowThreshold", "DiscardedMultipleMatch", "DiscardedNonzeroMismatch", "NoMatch", "NoMatchAndScoreBelowThreshold",
+           "DifferentFilterReasons", "NotMatchingPair", "ForceIntersectFailure", "ShortRead", "MaxHitsExceeded", "HighEntropy",
+           "SuccessfulMatch", "StrandWasWrong", "TriageEmptyEquivalenceClass", "AboveMismatchThreshold",
+           "SkippedAlignDueToUnpairedDummy", "None"]
+R = {n: i for i, n in enumerate(REASONS)}
+NB_MEM_HOST, NB_MEM_DEVICE = 0, 1
+FLAG_SKIP_ALIGN, FLAG_REVCOMP = 1, 2
+
+
+class NbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("nimble_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):  # nb_config == AlignFilterConfig (src/align.rs:80-95)
+    _fields_ = [("reference_genome_size", C.c_uint64), ("score_percent", C.c_double), ("score_threshold", C.c_uint64),
+                ("num_mismatches", C.c_uint64), ("discard_nonzero_mismatch", C.c_int32), ("discard_multiple_matches", C.c_int32),
+                ("score_filter", C.c_int32), ("intersect_level", C.c_int32), ("require_valid_pair", C.c_int32),
+                ("strand_filter", C.c_int32), ("discard_multi_hits", C.c_uint64), ("max_hits_to_report", C.c_uint64),
+                ("trim_strictness", C.c_double), ("trim_target_length", C.c_uint64)]
+
+    def copy(self, **kw):
+        c = Config.from_buffer_copy(bytes(self))
+        for k, v in kw.items():
+            if k == "strand_filter" and isinstance(v, str):
+                v = CHEM[v]
+            setattr(c, k, v)
+        return c
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("location", C.c_int32), ("max_read_len", C.c_uint32),
+                ("r1", C.c_void_p), ("r1_off", C.c_void_p), ("r2", C.c_void_p), ("r2_off", C.c_void_p),
+                ("q1", C.c_void_p), ("q2", C.c_void_p), ("flags1", C.c_void_p), ("flags2", C.c_void_p),
+                ("scope_id", C.c_void_p), ("cell_id", C.c_void_p)]
+
+
+class Counts(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("row_scope", C.POINTER(C.c_uint32)), ("row_callset", C.POINTER(C.c_uint32)),
+                ("row_count", C.POINTER(C.c_int64)), ("n_callsets", C.c_uint64), ("callset_off", C.POINTER(C.c_uint64)),
+                ("callset_items", C.POINTER(C.c_uint32)), ("n_pairs_seen", C.c_uint64), ("n_unique_keys", C.c_uint64),
+                ("n_slots", C.c_uint64), ("slot_to_callset", C.POINTER(C.c_uint32))]
+
+
+READ_DT = np.dtype([("reason", "u1"), ("pass", "u1"), ("score", "<u2"), ("mismatches", "<u2"), ("trimmed_len", "<u2"),
+                    ("ec_len", "<u4"), ("ec_hash", "<u4")])
+PAIR_DT = np.dtype([("callset", "<u4"), ("triage", "u1"), ("fr1", "u1"), ("fr2", "u1"), ("insertable", "u1"),
+                    ("key_lo", "<u8"), ("key_hi", "<u8")])
+
+_lib = None
+
+_SIGS = {
+    "nb_last_error": (C.c_char_p, []), "nb_reason_str": (C.c_char_p, [C.c_int]), "nb_version": (C.c_char_p, []),
+    "nb_library_load_json": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "nb_library_parse_json": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "nb_library_from_columns": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "nb_library_free": (None, [C.c_void_p]),
+    "nb_library_get_config": (C.c_int, [C.c_void_p, C.POINTER(Config)]), "nb_library_set_config": (C.c_int, [C.c_void_p, C.POINTER(Config)]),
+    "nb_library_n_rows": (C.c_uint32, [C.c_void_p]), "nb_library_n_headers": (C.c_uint32, [C.c_void_p]),
+    "nb_library_header": (C.c_char_p, [C.c_void_p, C.c_uint32]), "nb_library_value": (C.c_char_p, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "nb_library_group_on": (C.c_uint32, [C.c_void_p]), "nb_library_sequence_name_idx": (C.c_uint32, [C.c_void_p]),
+    "nb_library_sequence_idx": (C.c_uint32, [C.c_void_p]),
+    "nb_library_push_column": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint32, C.c_int]),
+    "nb_library_n_groups": (C.c_uint32, [C.c_void_p]), "nb_library_group_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),
+    "nb_index_build": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "nb_index_build_from_sequences": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]),
+    "nb_index_free": (None, [C.c_void_p]), "nb_index_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nb_index_dump": (C.c_uint64, [C.c_void_p, C.c_char_p, C.c_uint64]),
+    "nb_device_count": (C.c_int, []),
+    "nb_ctx_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "nb_ctx_free": (None, [C.c_void_p]), "nb_ctx_set_config": (C.c_int, [C.c_void_p, C.POINTER(Config)]),
+    "nb_ctx_sync": (C.c_int, [C.c_void_p]), "nb_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
+    "nb_host_alloc": (C.c_void_p, [C.c_size_t]), "nb_host_free": (None, [C.c_void_p]),
+    "nb_align_batch": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
+    "nb_last_batch_ecs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "nb_counts_finalize": (C.c_int, [C.c_void_p, C.POINTER(Counts)]), "nb_counts_reset": (C.c_int, [C.c_void_p]),
+    "nb_keys_export_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "nb_keys_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "nb_keys_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "nb_callsets_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "nb_callsets_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "nb_ctx_kernel_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "nb_ctx_work_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),
+    "nb_process_fastq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]),
+}
+
+
+def lib():
+    """Loads libnimble_b200.so.  Fails loudly when it has not been built: there is no other implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise NbError(-6, "libnimble_b200.so is missing (run `python nimble_aligner_b200/build.py`); there is no CPU fallback")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in _SIGS.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise NbError(rc, lib().nb_last_error().decode("utf-8", "replace"))
+
+
+def _strs(strs):
+    arr = (C.c_char_p * len(strs))(*[s.encode("utf-8") for s in strs])
+    return arr
+
+
+class Library:
+    """Reference + AlignFilterConfig (src/reference_library.rs:11-17, src/align.rs:80-95)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def from_json(cls, path, strand_filter="unstranded"):
+        h = C.c_void_p()
+        _ck(lib().nb_library_load_json(str(path).encode(), CHEM[strand_filter] if isinstance(strand_filter, str) else strand_filter, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_text(cls, text, strand_filter="unstranded"):
+        h = C.c_void_p()
+        b = text.encode() if isinstance(text, str) else text
+        _ck(lib().nb_library_parse_json(b, len(b), CHEM[strand_filter], C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_columns(cls, headers, columns, group_on, sequence_name_idx, sequence_idx, cfg):
+        hs = _strs(headers)
+        cols = [_strs(c) for c in columns]
+        colptr = (C.c_void_p * len(cols))(*[C.cast(c, C.c_void_p) for c in cols])
+        h = C.c_void_p()
+        _ck(lib().nb_library_from_columns(hs, len(headers), colptr, len(columns[0]), group_on, sequence_name_idx, sequence_idx, C.byref(cfg), C.byref(h)))
+        return cls(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().nb_library_free(self.h)
+            self.h = None
+
+    @property
+    def config(self):
+        c = Config()
+        _ck(lib().nb_library_get_config(self.h, C.byref(c)))
+        return c
+
+    def set_config(self, cfg):
+        _ck(lib().nb_library_set_config(self.h, C.byref(cfg)))
+
+    @property
+    def n_rows(self):
+        return lib().nb_library_n_rows(self.h)
+
+    @property
+    def headers(self):
+        return [lib().nb_library_header(self.h, i).decode() for i in range(lib().nb_library_n_headers(self.h))]
+
+    def column(self, c):
+        return [lib().nb_library_value(self.h, c, r).decode() for r in range(self.n_rows)]
+
+    @property
+    def group_on(self):
+        return lib().nb_library_group_on(self.h)
+
+    @property
+    def sequence_name_idx(self):
+        return lib().nb_library_sequence_name_idx(self.h)
+
+    @property
+    def sequence_idx(self):
+        return lib().nb_library_sequence_idx(self.h)
+
+    def push_column(self, header, values, set_group_on=True):
+        _ck(lib().nb_library_push_column(self.h, header.encode(), _strs(values), len(values), int(set_group_on)))
+
+    def group_names(self):
+        return [lib().nb_library_group_name(self.h, g).decode() for g in range(lib().nb_library_n_groups(self.h))]
+
+
+def get_reference_library(path, strand_filter="unstranded"):
+    """reference_library::get_reference_library -> (AlignFilterConfig, Reference)."""
+    l = Library.from_json(path, strand_filter)
+    return l.config, l
+
+
+def get_reference_sequence_data(reference):
+    """utils::get_reference_sequence_data -> (sequences, names) (src/utils.rs:7-24)."""
+    return reference.column(reference.sequence_idx), reference.column(reference.sequence_name_idx)
+
+
+class Index:
+    """PseudoAligner (src/align.rs:21): coloured compacted de Bruijn index in the flat GPU layout."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def build(cls, library, threads=1):
+        h = C.c_void_p()
+        _ck(lib().nb_index_build(library.h, threads, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_sequences(cls, seqs, threads=1):
+        data, off = pack_reads(seqs)
+        h = C.c_void_p()
+        _ck(lib().nb_index_build_from_sequences(data.ctypes.data, off.ctypes.data, len(seqs), threads, C.byref(h)))
+        return cls(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().nb_index_free(self.h)
+            self.h = None
+
+    def stats(self):
+        o = np.zeros(8, dtype=np.uint64)
+        _ck(lib().nb_index_stats(self.h, o.ctypes.data))
+        return dict(zip(["n_kmers", "n_nodes", "n_colours", "colour_elems", "unitig_bases", "table_slots", "device_bytes", "n_sequences"], o.tolist()))
+
+    def dump(self):
+        n = lib().nb_index_dump(self.h, None, 0)
+        buf = C.create_string_buffer(max(n, 1))
+        lib().nb_index_dump(self.h, buf, n)
+        return buf.raw[:n].decode()
+
+
+def build_index(library, threads=1):
+    return Index.build(library, threads)
+
+
+def pack_reads(reads):
+    """list of str/bytes -> (uint8 array, uint64 offsets[n+1])."""
+    bs = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+    off = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    data = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs and off[-1] else np.zeros(1, dtype=np.uint8)
+    return data, off
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return a.data_ptr()
+    return int(a)
+
+
+class Context:
+    """One (GPU, stream) execution context: device index copy + aggregation state."""
+
+    def __init__(self, index, library, device=0, stream=None, **options):
+        self.index, self.library = index, library
+        h = C.c_void_p()
+        _ck(lib().nb_ctx_create(index.h, library.h, device, stream, C.byref(h)))
+        self.h = h
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().nb_ctx_free(self.h)
+            self.h = None
+
+    def set_config(self, cfg):
+        _ck(lib().nb_ctx_set_config(self.h, C.byref(cfg)))
+
+    def set_option(self, name, value):
+        _ck(lib().nb_ctx_set_option(self.h, name.encode(), int(value)))
+
+    def sync(self):
+        _ck(lib().nb_ctx_sync(self.h))
+
+    def align_batch(self, r1, r1_off, r2=None, r2_off=None, q1=None, q2=None, flags1=None, flags2=None, scope_id=None, cell_id=None,
+                    n_pairs=None, max_read_len=0, location=NB_MEM_HOST, reads_out=None, pairs_out=None, want_reads=False, want_pairs=False):
+        """nb_align_batch.  Host arrays are numpy; device arrays may be torch tensors or raw pointers (then pass n_pairs)."""
+        keep = [np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a for a in (r1, r1_off, r2, r2_off, q1, q2, flags1, flags2, scope_id, cell_id)]
+        if n_pairs is None:
+            n_pairs = len(keep[1]) - 1
+        b = Batch(n_pairs, location, max_read_len, *[_ptr(a) for a in keep])
+        sides = 2 if r2 is not None else 1
+        if want_reads and reads_out is None:
+            reads_out = np.zeros(n_pairs * sides, dtype=READ_DT)
+        if want_pairs and pairs_out is None:
+            pairs_out = np.zeros(n_pairs, dtype=PAIR_DT)
+        _ck(lib().nb_align_batch(self.h, C.byref(b), _ptr(reads_out), _ptr(pairs_out)))
+        if location == NB_MEM_HOST:
+            self.sync()   # keeps the numpy temporaries alive until the copies have run
+        return reads_out, pairs_out
+
+    def last_batch_ecs(self, n_reads):
+        off = np.zeros(n_reads + 1, dtype=np.uint64)
+        tot = C.c_uint64(0)
+        _ck(lib().nb_last_batch_ecs(self.h, off.ctypes.data, None, 0, C.byref(tot)))
+        ids = np.zeros(max(tot.value, 1), dtype=np.uint32)
+        _ck(lib().nb_last_batch_ecs(self.h, off.ctypes.data, ids.ctypes.data, len(ids), C.byref(tot)))
+        return off, ids[:tot.value]
+
+    def counts(self):
+        """nb_counts_finalize -> dict(rows=[(scope, [group names], count)], callsets=[[names]], n_pairs_seen, n_unique_keys)."""
+        c = Counts()
+        _ck(lib().nb_counts_finalize(self.h, C.byref(c)))
+        names = self.library.group_names()
+        callsets = []
+        for i in range(c.n_callsets):
+            callsets.append([names[c.callset_items[k]] for k in range(c.callset_off[i], c.callset_off[i + 1])])
+        rows = [(c.row_scope[r], callsets[c.row_callset[r]], c.row_count[r]) for r in range(c.n_rows)]
+        return dict(rows=rows, callsets=callsets, n_pairs_seen=c.n_pairs_seen, n_unique_keys=c.n_unique_keys,
+                    row_scope=np.ctypeslib.as_array(c.row_scope, (c.n_rows,)).copy() if c.n_rows else np.zeros(0, np.uint32),
+                    row_callset=np.ctypeslib.as_array(c.row_callset, (c.n_rows,)).copy() if c.n_rows else np.zeros(0, np.uint32),
+                    row_count=np.ctypeslib.as_array(c.row_count, (c.n_rows,)).copy() if c.n_rows else np.zeros(0, np.int64),
+                    slot_to_callset=np.ctypeslib.as_array(c.slot_to_callset, (c.n_slots,)).copy() if c.n_slots else np.zeros(0, np.uint32))
+
+    def write_tsv(self, path):
+        c = Counts()
+        _ck(lib().nb_counts_finalize(self.h, C.byref(c)))
+        _ck(lib().nb_write_fastq_tsv(str(path).encode(), self.library.h, C.byref(c)))
+
+    def reset(self):
+        _ck(lib().nb_counts_reset(self.h))
+
+    def kernel_stats(self, reset=False):
+        o = np.zeros(4, dtype=np.float64)
+        _ck(lib().nb_ctx_kernel_stats(self.h, o.ctypes.data, int(reset)))
+        return dict(map_launches=int(o[0]), map_ms=float(o[1]), map_reads=int(o[2]), launches=int(o[3]))
+
+    def work_counters(self):
+        o = np.zeros(4, dtype=np.uint64)
+        _ck(lib().nb_ctx_work_counters(self.h, o.ctypes.data))
+        return dict(zip(["probes", "nodes", "bases", "colour_elems"], o.tolist()))
+
+
+def get_calls(sequences, mate_sequences, sequence_metadata, index, reference, aligner_config, device=0):
+    """align::get_calls (src/align.rs:392-467) for one aggregation scope.  `sequences` / `mate_sequences`: lists of
+    strings; `sequence_metadata`: None/[] (FASTQ mode) or per-pair dict(q1, q2, skip1, skip2) arrays.
+    Returns (sorted [(callset, count)], per-read records, per-pair records)."""
+    ctx = Context(index, reference, device)
+    try:
+        ctx.set_config(aligner_config)
+        r1, o1 = pack_reads(sequences)
+        r2 = o2 = None
+        if mate_sequences is not None:
+            r2, o2 = pack_reads(mate_sequences)
+        md = sequence_metadata or {}
+        reads, pairs = ctx.align_batch(r1, o1, r2, o2, q1=md.get("q1"), q2=md.get("q2"), flags1=md.get("flags1"), flags2=md.get("flags2"),
+                                       want_reads=True, want_pairs=True)
+        res = ctx.counts()
+        return [(cs, n) for _, cs, n in res["rows"]], reads, pairs
+    finally:
+        ctx.close()
+
+
+def call(sequences, mate_sequences, per_sequence_metadata, reference_index, reference, aligner_config, device=0):
+    """score::call (src/score.rs:14-46): get_calls + sort_score_vector (rows already come back sorted)."""
+    return get_calls(sequences, mate_sequences, per_sequence_metadata, reference_index, reference, aligner_config, device)
+
+
+def process_fastq(input_files, reference_json_paths, output_paths, strand_filter="unstranded", num_cores=1, device=0):
+    """process::fastq::process behind main.rs's library loop (src/process/fastq.rs:7-30, src/bin/main.rs:95-147)."""
+    _ck(lib().nb_process_fastq(_strs(input_files), len(input_files), _strs(reference_json_paths), _strs(output_paths),
+                               len(reference_json_paths), CHEM[strand_filter], num_cores, device))

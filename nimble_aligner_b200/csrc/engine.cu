@@ -1,0 +1,492 @@
+// engine.cu — execution context behind the C ABI: device copies of the index / library tables, per-batch staging,
+// the K0..K4 launch sequence on one CUDA stream, and result read-back.  No CPU fallback: every entry point fails
+// with NB_ERR_CUDA when the device cannot be used.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "host.hpp"
+#include "kernels.cuh"
+
+using namespace nb;
+using nbk::BatchDev; using nbk::Counters; using nbk::DevCfg; using nbk::DevIndex; using nbk::DevLib; using nbk::Tables;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(NB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+namespace {
+
+struct DBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes, cudaStream_t s, bool zero = false) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) return e; cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want); if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = want;
+    if (zero) return cudaMemsetAsync(p, 0, want, s);
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T> cudaError_t upload(DBuf& d, const std::vector<T>& v, cudaStream_t s, size_t pad_bytes = 0) {
+  size_t bytes = v.size() * sizeof(T);
+  cudaError_t e = d.ensure(bytes + pad_bytes + 16, s); if (e != cudaSuccess) return e;
+  if (bytes) e = cudaMemcpyAsync(d.p, v.data(), bytes, cudaMemcpyHostToDevice, s);
+  return e;
+}
+
+// maxinfo tables, src/align.rs:873-897 (built once per config on the host with the same libm as the CPU reference)
+i64 f64_as_i64(double v) { if (std::isnan(v)) return 0; if (v >= 9223372036854775807.0) return INT64_MAX; if (v <= -9223372036854775808.0) return INT64_MIN; return (i64)v; }
+void build_maxinfo_tables(u64 target, double strictness, std::vector<i64>& ls, std::vector<i64>& qp) {
+  const int LONGEST = 1000, MAXQ = 60;
+  std::vector<double> l(LONGEST), q(MAXQ + 1);
+  for (int i = 0; i < LONGEST; i++) { double pow1 = std::exp((double)target - (double)i - 1.0); l[i] = std::log(1.0 / (1.0 + pow1)) + std::log((double)(i + 1)) * (1.0 - strictness); }
+  for (int i = 0; i <= MAXQ; i++) { double pc = 1.0 - std::pow(10.0, -((0.5 + (double)i) / 10.0)); q[i] = std::log(pc) * strictness; }
+  auto ratio = [](const std::vector<double>& a) { double mx = std::fabs(a[0]); for (size_t i = 1; i < a.size(); i++) { double v = std::fabs(a[i]); if (v > mx) mx = v; } return 9223372036854775807.0 / (mx * 2000.0); };
+  double r = std::fmax(ratio(l), ratio(q));
+  ls.resize(LONGEST); qp.resize(MAXQ + 1);
+  for (int i = 0; i < LONGEST; i++) ls[i] = f64_as_i64(l[i] * r);
+  for (int i = 0; i <= MAXQ; i++) qp[i] = f64_as_i64(q[i] * r);
+}
+
+}  // namespace
+
+struct nb_ctx {
+  int device = 0; cudaStream_t stream = nullptr; bool own_stream = false;
+  const nb_index* hix = nullptr; const nb_library* lib = nullptr;
+  nb_config hcfg; DevCfg dcfg; DevIndex dix; DevLib dlib;
+  // index + library device copies
+  DBuf d_tkey, d_tval, d_unitig, d_node, d_redge, d_ledge, d_coloff, d_colids, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp;
+  // options
+  u64 max_batch_pairs = 1u << 20, arena_entries = 1u << 24, cs_slots = 1u << 18, key_slots = 1u << 22, agg_slots = 1u << 20;
+  int count_work = 0; u32 min_read_len = 40;  // MIN_READ_LENGTH, src/align.rs:18 (tests pass 12, src/align.rs:1066)
+  // persistent tables
+  DBuf d_cstag, d_cslen, d_csitems, d_key, d_kval, d_aggkey, d_aggcnt, d_arena, d_ctr, d_scratch, d_nout;
+  u32 gcap = 16;
+  bool tables_ready = false;
+  // staging + per-batch buffers
+  DBuf s_a[2], s_off[2], s_q[2], s_f[2], s_scope, s_cell, d_pk, d_lenfull, d_lentrim, d_rres, d_pres, d_rout;
+  // state
+  int mode = -1;  // -1 unset, 0 whole-run scope (keys persist), 1 scoped (keys live for one batch)
+  bool folded = false;
+  u64 pairs_seen = 0, keys_upper = 0, last_unique = 0;
+  BatchDev last_b; bool have_last = false;
+  // timing
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+  double map_ms = 0; u64 map_launches = 0, map_reads = 0, all_launches = 0;
+  // results
+  std::vector<u32> row_scope, row_callset, cs_items, slot_dense; std::vector<i64> row_count; std::vector<u64> cs_off;
+};
+
+static Tables make_tables(nb_ctx* c) {
+  Tables t;
+  t.cs_tag = (u64*)c->d_cstag.p; t.cs_len = (u32*)c->d_cslen.p; t.cs_items = (u32*)c->d_csitems.p; t.cs_mask = (u32)c->cs_slots - 1; t.gcap = c->gcap;
+  t.key = (ulonglong2*)c->d_key.p; t.kval = (unsigned long long*)c->d_kval.p; t.key_mask = c->key_slots - 1;
+  t.agg_key = (unsigned long long*)c->d_aggkey.p; t.agg_cnt = (unsigned long long*)c->d_aggcnt.p; t.agg_mask = c->agg_slots - 1;
+  t.arena = (u32*)c->d_arena.p; t.arena_cap = c->arena_entries; t.ctr = (Counters*)c->d_ctr.p;
+  t.ent = (const double*)c->d_ent.p; t.ls = (const i64*)c->d_ls.p; t.qp = (const i64*)c->d_qp.p;
+  return t;
+}
+
+static int apply_config(nb_ctx* c, const nb_config& cfg) {
+  if (cfg.intersect_level < 0 || cfg.intersect_level > 2 || cfg.strand_filter < 0 || cfg.strand_filter > 3) return fail(NB_ERR_INVALID, "invalid intersect_level / strand_filter");
+  u64 T = std::max<u64>(cfg.discard_multi_hits, cfg.max_hits_to_report);
+  if (T + 1 > (u64)nbk::GL_MAX) return fail(NB_ERR_UNSUPPORTED, "max(discard_multi_hits, max_hits_to_report) must be < 64 on the device path");
+  if (cfg.score_threshold > 0xFFFFFFFFull || cfg.num_mismatches > 0xFFFFull) return fail(NB_ERR_UNSUPPORTED, "score_threshold / num_mismatches out of range");
+  u32 need_gcap = (u32)std::max<u64>(1, cfg.max_hits_to_report);
+  if (c->tables_ready && need_gcap > c->gcap) return fail(NB_ERR_UNSUPPORTED, "max_hits_to_report grew beyond the callset stride chosen at context creation; create a new context");
+  c->hcfg = cfg;
+  DevCfg& d = c->dcfg;
+  d.score_percent = cfg.score_percent; d.score_threshold = (u32)cfg.score_threshold; d.num_mismatches = (u32)cfg.num_mismatches;
+  d.discard_nonzero_mismatch = cfg.discard_nonzero_mismatch; d.discard_multiple_matches = cfg.discard_multiple_matches; d.require_valid_pair = cfg.require_valid_pair;
+  d.intersect_level = cfg.intersect_level; d.strand_filter = cfg.strand_filter; d.no_dedup = c->lib->no_dedup;
+  d.discard_multi_hits = (u32)cfg.discard_multi_hits; d.max_hits = (u32)cfg.max_hits_to_report; d.gcap = c->gcap; d.min_read_len = c->min_read_len;
+  std::vector<i64> ls, qp; build_maxinfo_tables(cfg.trim_target_length, cfg.trim_strictness, ls, qp);
+  CK(upload(c->d_ls, ls, c->stream)); CK(upload(c->d_qp, qp, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return NB_OK;
+}
+
+static int alloc_tables(nb_ctx* c) {
+  cudaStream_t s = c->stream;
+  c->gcap = std::max<u32>(16, (u32)c->hcfg.max_hits_to_report);
+  c->dcfg.gcap = c->gcap;
+  CK(c->d_cstag.ensure(c->cs_slots * 8, s)); CK(c->d_cslen.ensure(c->cs_slots * 4, s)); CK(c->d_csitems.ensure(c->cs_slots * (size_t)c->gcap * 4, s));
+  CK(c->d_key.ensure(c->key_slots * 16, s)); CK(c->d_kval.ensure(c->key_slots * 8, s));
+  CK(c->d_aggkey.ensure(c->agg_slots * 8, s)); CK(c->d_aggcnt.ensure(c->agg_slots * 8, s));
+  CK(c->d_arena.ensure(c->arena_entries * 4, s)); CK(c->d_ctr.ensure(sizeof(Counters), s)); CK(c->d_nout.ensure(64, s));
+  CK(cudaMemsetAsync(c->d_cstag.p, 0, c->cs_slots * 8, s)); CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s));
+  CK(cudaMemsetAsync(c->d_aggkey.p, 0, c->agg_slots * 8, s)); CK(cudaMemsetAsync(c->d_aggcnt.p, 0, c->agg_slots * 8, s)); CK(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), s));
+  c->tables_ready = true; c->mode = -1; c->folded = false; c->pairs_seen = 0; c->keys_upper = 0; c->have_last = false;
+  return NB_OK;
+}
+
+static int check_device_errors(nb_ctx* c, Counters* out = nullptr) {
+  Counters h;
+  CK(cudaMemcpyAsync(&h, c->d_ctr.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (out) *out = h;
+  if (h.err & nbk::E_FEATURE) return fail(NB_ERR_FEATURE_NOT_FOUND, "Feature not found in reference columns");
+  if (h.err & nbk::E_ARENA) return fail(NB_ERR_OVERFLOW, "equivalence-class arena overflow: raise option ec_arena_entries or lower max_batch_pairs");
+  if (h.err & nbk::E_CS_FULL) return fail(NB_ERR_OVERFLOW, "callset dictionary full: raise option callset_slots");
+  if (h.err & nbk::E_KEY_FULL) return fail(NB_ERR_OVERFLOW, "read-key table full: raise option key_slots");
+  if (h.err & nbk::E_AGG_FULL) return fail(NB_ERR_OVERFLOW, "count table full: raise option agg_slots");
+  return NB_OK;
+}
+
+extern "C" {
+
+int nb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+void* nb_host_alloc(size_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void nb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void* cuda_stream, nb_ctx** out) {
+  if (!index || !lib || !out) return fail(NB_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(NB_ERR_CUDA, "no CUDA device available: nimble_b200 has no CPU path"); }
+  if (device < 0 || device >= ndev) return fail(NB_ERR_INVALID, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(NB_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) + "; this library is built for sm_100a only");
+  nb_library* mlib = const_cast<nb_library*>(lib);
+  if (!mlib->derived) mlib->finalize();
+  if (index->n_sequences != lib->n_rows()) return fail(NB_ERR_INVALID, "index was not built from this library (row count differs)");
+  nb_ctx* c = new nb_ctx();
+  c->device = device; c->hix = index; c->lib = lib;
+  if (cuda_stream) c->stream = (cudaStream_t)cuda_stream; else { if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(NB_ERR_CUDA, "cudaStreamCreate failed"); } c->own_stream = true; }
+  cudaStream_t s = c->stream;
+  int rc = NB_OK;
+  auto up = [&](cudaError_t e) { if (e != cudaSuccess && rc == NB_OK) rc = fail(NB_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e)); };
+  up(upload(c->d_tkey, index->table_key, s)); up(upload(c->d_tval, index->table_val, s)); up(upload(c->d_unitig, index->unitig, s));
+  up(upload(c->d_node, index->node, s)); up(upload(c->d_redge, index->redge, s)); up(upload(c->d_ledge, index->ledge, s));
+  up(upload(c->d_coloff, index->col_off, s)); up(upload(c->d_colids, index->col_ids, s));
+  up(upload(c->d_rowfid, lib->row_fid, s)); up(upload(c->d_rowrev, lib->row_rev, s)); up(upload(c->d_rowof, lib->row_of, s)); up(upload(c->d_featgroup, lib->feat_group, s));
+  {  // entropy terms f*log2(f), f = c/n, for every read length n <= ENT_NMAX (src/utils.rs:96-119)
+    const int N = nbk::ENT_NMAX;
+    std::vector<double> ent((size_t)(N + 1) * (N + 2) / 2, 0.0);
+    for (int n = 1; n <= N; n++) for (int k = 1; k <= n; k++) { double f = (double)k / (double)n; ent[(size_t)n * (n + 1) / 2 + k] = f * std::log2(f); }
+    up(upload(c->d_ent, ent, s));
+  }
+  if (rc == NB_OK) { cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) rc = fail(NB_ERR_CUDA, cudaGetErrorString(e)); }
+  if (rc != NB_OK) { nb_ctx_free(c); return rc; }
+  c->dix.tkey = (const u64*)c->d_tkey.p; c->dix.tval = (const u64*)c->d_tval.p; c->dix.tmask = index->table_mask; c->dix.unitig = (const u64*)c->d_unitig.p;
+  c->dix.node = (const uint4*)c->d_node.p; c->dix.redge = (const uint4*)c->d_redge.p; c->dix.ledge = (const uint4*)c->d_ledge.p;
+  c->dix.col_off = (const u32*)c->d_coloff.p; c->dix.col_ids = (const u32*)c->d_colids.p;
+  c->dlib.row_fid = (const u32*)c->d_rowfid.p; c->dlib.row_rev = (const u8*)c->d_rowrev.p; c->dlib.row_of = (const u32*)c->d_rowof.p; c->dlib.feat_group = (const u32*)c->d_featgroup.p; c->dlib.n_rows = lib->n_rows();
+  rc = apply_config(c, lib->cfg);
+  if (rc != NB_OK) { nb_ctx_free(c); return rc; }
+  *out = c;
+  return NB_OK;
+}
+
+void nb_ctx_free(nb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_unitig, &c->d_node, &c->d_redge, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
+                 &c->d_ent, &c->d_ls, &c->d_qp, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
+                 &c->s_a[0], &c->s_a[1], &c->s_off[0], &c->s_off[1], &c->s_q[0], &c->s_q[1], &c->s_f[0], &c->s_f[1], &c->s_scope, &c->s_cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout};
+  for (DBuf* b : all) b->release();
+  for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (auto& e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int nb_ctx_set_config(nb_ctx* c, const nb_config* cfg) { if (!c || !cfg) return fail(NB_ERR_INVALID, "null argument"); CK(cudaSetDevice(c->device)); return apply_config(c, *cfg); }
+int nb_ctx_sync(nb_ctx* c) { if (!c) return fail(NB_ERR_INVALID, "null argument"); CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return NB_OK; }
+
+int nb_ctx_set_option(nb_ctx* c, const char* name, uint64_t value) {
+  if (!c || !name) return fail(NB_ERR_INVALID, "null argument");
+  auto pow2 = [](u64 v) { u64 p = 16; while (p < v) p <<= 1; return p; };
+  std::string n(name);
+  if (n == "count_work") { c->count_work = value != 0; return NB_OK; }
+  if (n == "min_read_length") { c->min_read_len = (u32)value; c->dcfg.min_read_len = (u32)value; return NB_OK; }
+  if (c->tables_ready) return fail(NB_ERR_INVALID, "options must be set before the first nb_align_batch (or after nb_counts_reset)");
+  if (n == "max_batch_pairs") c->max_batch_pairs = std::max<u64>(1, value);
+  else if (n == "ec_arena_entries") c->arena_entries = std::max<u64>(1024, value);
+  else if (n == "callset_slots") { c->cs_slots = pow2(value); if (c->cs_slots > (1u << 23)) return fail(NB_ERR_INVALID, "callset_slots must be <= 2^23"); }
+  else if (n == "key_slots") c->key_slots = pow2(value);
+  else if (n == "agg_slots") c->agg_slots = pow2(value);
+  else return fail(NB_ERR_INVALID, "unknown option " + n);
+  return NB_OK;
+}
+
+static int grow_keys(nb_ctx* c, u64 need_slots) {
+  u64 ns = c->key_slots; while (ns < need_slots) ns <<= 1;
+  DBuf nk, nv; cudaStream_t s = c->stream;
+  CK(nk.ensure(ns * 16, s)); CK(nv.ensure(ns * 8, s));
+  CK(cudaMemsetAsync(nk.p, 0, ns * 16, s)); CK(cudaMemsetAsync(nv.p, 0, ns * 8, s));
+  Tables o = make_tables(c); Tables n = o; n.key = (ulonglong2*)nk.p; n.kval = (unsigned long long*)nv.p; n.key_mask = ns - 1;
+  // n_keys is re-counted by the inserts of the rehash
+  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
+  nbk::launch_rehash_keys(o, n, s); c->all_launches++;
+  CK(cudaStreamSynchronize(s));
+  c->d_key.release(); c->d_kval.release(); c->d_key = nk; c->d_kval = nv; c->key_slots = ns;
+  return NB_OK;
+}
+
+static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len, nb_read_result* reads_out, nb_pair_result* pairs_out) {
+  cudaStream_t s = c->stream;
+  u64 np = p1 - p0; u32 sides = bt->r2 ? 2 : 1; u64 nr = np * sides;
+  bool host = bt->location == NB_MEM_HOST;
+  cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  BatchDev b; memset(&b, 0, sizeof b);
+  b.n_pairs = np; b.sides = sides; b.n_reads = (u32)nr; b.W = (max_len + 31) / 32 + 1; b.order_base = c->pairs_seen;
+  const u8* src_a[2] = {bt->r1, bt->r2}; const u64* src_off[2] = {bt->r1_off, bt->r2_off}; const u8* src_q[2] = {bt->q1, bt->q2}; const u8* src_f[2] = {bt->flags1, bt->flags2};
+  for (u32 sd = 0; sd < sides; sd++) {
+    if (host) {
+      u64 a0 = src_off[sd][p0], a1 = src_off[sd][p1];
+      CK(c->s_a[sd].ensure(a1 - a0 + 64, s)); CK(c->s_off[sd].ensure((np + 1) * 8, s));
+      if (a1 > a0) CK(cudaMemcpyAsync(c->s_a[sd].p, src_a[sd] + a0, a1 - a0, kind, s));
+      CK(cudaMemcpyAsync(c->s_off[sd].p, src_off[sd] + p0, (np + 1) * 8, kind, s));
+      b.a[sd] = (const u8*)c->s_a[sd].p - a0; b.off[sd] = (const u64*)c->s_off[sd].p;
+      if (src_q[sd]) { CK(c->s_q[sd].ensure(a1 - a0 + 64, s)); if (a1 > a0) CK(cudaMemcpyAsync(c->s_q[sd].p, src_q[sd] + a0, a1 - a0, kind, s)); b.q[sd] = (const u8*)c->s_q[sd].p - a0; }
+      if (src_f[sd]) { CK(c->s_f[sd].ensure(np, s)); CK(cudaMemcpyAsync(c->s_f[sd].p, src_f[sd] + p0, np, kind, s)); b.flags[sd] = (const u8*)c->s_f[sd].p; }
+    } else {
+      b.a[sd] = src_a[sd]; b.off[sd] = src_off[sd] + p0; b.q[sd] = src_q[sd]; b.flags[sd] = src_f[sd] ? src_f[sd] + p0 : nullptr;
+    }
+  }
+  if (bt->scope_id) {
+    if (host) { CK(c->s_scope.ensure(np * 4, s)); CK(cudaMemcpyAsync(c->s_scope.p, bt->scope_id + p0, np * 4, kind, s)); b.scope = (const u32*)c->s_scope.p; }
+    else b.scope = bt->scope_id + p0;
+    b.cell = b.scope;
+    if (bt->cell_id) {
+      if (host) { CK(c->s_cell.ensure(np * 4, s)); CK(cudaMemcpyAsync(c->s_cell.p, bt->cell_id + p0, np * 4, kind, s)); b.cell = (const u32*)c->s_cell.p; }
+      else b.cell = bt->cell_id + p0;
+    }
+  }
+  CK(c->d_pk.ensure((size_t)b.W * nr * 8, s)); CK(c->d_lenfull.ensure(nr * 4, s)); CK(c->d_lentrim.ensure(nr * 4, s));
+  CK(c->d_rres.ensure(nr * sizeof(nbk::ReadRes), s)); CK(c->d_pres.ensure(np * sizeof(nbk::PairRes), s));
+  b.pk = (u64*)c->d_pk.p; b.len_full = (u32*)c->d_lenfull.p; b.len_trim = (u32*)c->d_lentrim.p; b.rres = (nbk::ReadRes*)c->d_rres.p; b.pres = (nbk::PairRes*)c->d_pres.p;
+  // key-table capacity
+  if (c->mode == 0) {
+    if (2 * (c->keys_upper + np) > c->key_slots) {
+      Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
+      c->keys_upper = h.n_keys;
+      if (2 * (c->keys_upper + np) > c->key_slots) { rc = grow_keys(c, 2 * (c->keys_upper + np)); if (rc) return rc; }
+    }
+    c->keys_upper += np;
+  } else if (2 * np > c->key_slots) { int rc = grow_keys(c, 2 * np); if (rc) return rc; }
+  Tables t = make_tables(c);
+  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->arena_top, 0, 8, s));
+  nbk::launch_pack(b, s); c->all_launches++;
+  if (b.q[0] || b.q[1]) { nbk::launch_trim(b, t, s); c->all_launches++; }
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (!c->ev_free.empty()) { ev = c->ev_free.back(); c->ev_free.pop_back(); } else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
+  CK(cudaEventRecord(ev.first, s));
+  nbk::launch_map(b, c->dix, c->dcfg, t, c->count_work, s); c->all_launches++;
+  CK(cudaEventRecord(ev.second, s));
+  c->ev_pending.push_back(ev); c->map_launches++; c->map_reads += nr;
+  nbk::launch_pair(b, c->dix, c->dlib, c->dcfg, t, s); c->all_launches++;
+  if (c->mode == 1) {
+    nbk::launch_fold(t, b.cell, b.order_base, s); c->all_launches++;
+    CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s));
+  }
+  cudaMemcpyKind okind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (reads_out) {
+    CK(c->d_rout.ensure(nr * sizeof(nb_read_result), s));
+    nbk::launch_export_reads(b, c->dix, t, c->d_rout.p, s); c->all_launches++;
+    CK(cudaMemcpyAsync(reads_out + p0 * sides, c->d_rout.p, nr * sizeof(nb_read_result), okind, s));
+  }
+  if (pairs_out) CK(cudaMemcpyAsync(pairs_out + p0, c->d_pres.p, np * sizeof(nb_pair_result), okind, s));
+  CK(cudaGetLastError());
+  c->pairs_seen += np; c->last_b = b; c->have_last = true;
+  return NB_OK;
+}
+
+int nb_align_batch(nb_ctx* c, const nb_batch* bt, nb_read_result* reads_out, nb_pair_result* pairs_out) {
+  if (!c || !bt) return fail(NB_ERR_INVALID, "null argument");
+  static_assert(sizeof(nb_read_result) == 16 && sizeof(nb_pair_result) == 24, "ABI struct size");
+  static_assert(sizeof(nbk::PairRes) == sizeof(nb_pair_result), "PairRes layout");
+  CK(cudaSetDevice(c->device));
+  if (bt->n_pairs && (!bt->r1 || !bt->r1_off || (bt->r2 && !bt->r2_off))) return fail(NB_ERR_INVALID, "batch needs r1/r1_off (and r2_off with r2)");
+  if (bt->location != NB_MEM_HOST && bt->location != NB_MEM_DEVICE) return fail(NB_ERR_INVALID, "batch location must be NB_MEM_HOST or NB_MEM_DEVICE");
+  if (!c->lib->injective) return fail(NB_ERR_UNSUPPORTED, "reference library not representable on the device pair stage: " + c->lib->irregular_reason);
+  if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
+  if (c->folded) return fail(NB_ERR_INVALID, "counts were finalized; call nb_counts_reset before aligning more batches");
+  int mode = bt->scope_id ? 1 : 0;
+  if (c->mode == -1) c->mode = mode;
+  else if (c->mode != mode) return fail(NB_ERR_INVALID, "cannot mix scoped and whole-run batches in one context without nb_counts_reset");
+  if (bt->n_pairs == 0) return NB_OK;
+  u32 max_len = bt->max_read_len;
+  if (!max_len) {
+    if (bt->location != NB_MEM_HOST) return fail(NB_ERR_INVALID, "device-resident batches must state max_read_len");
+    for (u64 p = 0; p < bt->n_pairs; p++) { max_len = std::max<u32>(max_len, (u32)(bt->r1_off[p + 1] - bt->r1_off[p])); if (bt->r2) max_len = std::max<u32>(max_len, (u32)(bt->r2_off[p + 1] - bt->r2_off[p])); }
+  }
+  if (max_len > (u32)nbk::ENT_NMAX) return fail(NB_ERR_UNSUPPORTED, "reads longer than 1024 bases are not supported by the device path");
+  if (max_len == 0) max_len = 1;
+  u64 chunk = c->max_batch_pairs;
+  for (u64 p0 = 0; p0 < bt->n_pairs; p0 += chunk) {
+    u64 p1 = std::min(bt->n_pairs, p0 + chunk);
+    if (c->mode == 1 && p1 < bt->n_pairs) {  // never split a scope across chunks
+      while (p1 > p0 + 1 && bt->location == NB_MEM_HOST && bt->scope_id[p1] == bt->scope_id[p1 - 1]) p1--;
+      if (bt->location != NB_MEM_HOST) return fail(NB_ERR_INVALID, "scoped device-resident batches must fit max_batch_pairs");
+      chunk = p1 - p0;
+    }
+    int rc = run_chunk(c, bt, p0, p1, max_len, reads_out, pairs_out);
+    if (rc) return rc;
+    chunk = c->max_batch_pairs;
+  }
+  return NB_OK;
+}
+
+int nb_last_batch_ecs(nb_ctx* c, uint64_t* ec_off, uint32_t* ec_ids, uint64_t ec_cap, uint64_t* ec_total) {
+  if (!c || !ec_off || !ec_total) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->have_last) return fail(NB_ERR_INVALID, "no batch has been aligned");
+  CK(cudaSetDevice(c->device));
+  const BatchDev& b = c->last_b;
+  std::vector<nbk::ReadRes> rr(b.n_reads);
+  CK(cudaMemcpyAsync(rr.data(), b.rres, rr.size() * sizeof(nbk::ReadRes), cudaMemcpyDeviceToHost, c->stream));
+  Counters h; CK(cudaMemcpyAsync(&h, c->d_ctr.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  std::vector<u32> arena(std::min<u64>(h.arena_top, c->arena_entries));
+  if (!arena.empty()) { CK(cudaMemcpy(arena.data(), c->d_arena.p, arena.size() * 4, cudaMemcpyDeviceToHost)); }
+  u64 tot = 0;
+  for (u32 i = 0; i < b.n_reads; i++) {
+    ec_off[i] = tot;
+    const nbk::ReadRes& r = rr[i];
+    if (!r.ec_len) continue;
+    bool big = (r.hdr >> 9) & 1;
+    if (big) { for (u32 k = 0; k < r.bsize; k++) { if (ec_ids && tot < ec_cap) ec_ids[tot] = arena[r.ref + k]; tot++; } }
+    else { for (u32 k = 0; k < r.bsize; k++) if ((r.mask >> k) & 1) { if (ec_ids && tot < ec_cap) ec_ids[tot] = c->hix->col_ids[r.ref + k]; tot++; } }
+  }
+  ec_off[b.n_reads] = tot; *ec_total = tot;
+  return NB_OK;
+}
+
+int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
+  if (!c || !out) return fail(NB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  memset(out, 0, sizeof *out);
+  c->row_scope.clear(); c->row_callset.clear(); c->row_count.clear(); c->cs_items.clear(); c->cs_off.assign(1, 0);
+  if (!c->tables_ready) { out->callset_off = c->cs_off.data(); return NB_OK; }
+  cudaStream_t s = c->stream;
+  Tables t = make_tables(c);
+  if (c->mode == 0 && !c->folded) { nbk::launch_fold(t, nullptr, 0, s); c->all_launches++; c->folded = true; }
+  Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
+  c->last_unique = h.n_keys;
+  // read back the (cell, callset) table and the callset dictionary
+  std::vector<u64> ak(c->agg_slots), ac(c->agg_slots);
+  CK(cudaMemcpyAsync(ak.data(), c->d_aggkey.p, c->agg_slots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(ac.data(), c->d_aggcnt.p, c->agg_slots * 8, cudaMemcpyDeviceToHost, s));
+  std::vector<u64> tag(c->cs_slots); std::vector<u32> len(c->cs_slots), items((size_t)c->cs_slots * c->gcap);
+  CK(cudaMemcpyAsync(tag.data(), c->d_cstag.p, c->cs_slots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(len.data(), c->d_cslen.p, c->cs_slots * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(items.data(), c->d_csitems.p, items.size() * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  // callsets sorted by Vec<String> Ord (utils::sort_score_vector, src/utils.rs:54-59): bytewise on the group names
+  const std::vector<std::string>& gn = c->lib->group_names;
+  std::vector<u32> slots; for (u32 i = 0; i < c->cs_slots; i++) if (tag[i]) slots.push_back(i);
+  auto cs_less = [&](u32 a, u32 b) {
+    u32 la = len[a], lb = len[b];
+    for (u32 i = 0; i < std::min(la, lb); i++) { u32 ga = items[(size_t)a * c->gcap + i], gb = items[(size_t)b * c->gcap + i]; if (ga != gb) { int cmp = gn[ga].compare(gn[gb]); if (cmp) return cmp < 0; } }
+    return la < lb;
+  };
+  std::sort(slots.begin(), slots.end(), cs_less);
+  std::vector<u32>& dense = c->slot_dense; dense.assign(c->cs_slots, NONE32);
+  for (u32 i = 0; i < slots.size(); i++) { dense[slots[i]] = i; for (u32 k = 0; k < len[slots[i]]; k++) c->cs_items.push_back(items[(size_t)slots[i] * c->gcap + k]); c->cs_off.push_back(c->cs_items.size()); }
+  struct Row { u32 cell, cs; i64 n; };
+  std::vector<Row> rows;
+  for (u64 i = 0; i < c->agg_slots; i++) if (ak[i]) { u64 k = ak[i] - 1; rows.push_back(Row{(u32)(k >> 24), dense[(u32)(k & 0xFFFFFF)], (i64)ac[i]}); }
+  std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.cell != b.cell ? a.cell < b.cell : a.cs < b.cs; });
+  for (auto& r : rows) { c->row_scope.push_back(r.cell); c->row_callset.push_back(r.cs); c->row_count.push_back(r.n); }
+  out->n_rows = rows.size(); out->row_scope = c->row_scope.data(); out->row_callset = c->row_callset.data(); out->row_count = c->row_count.data();
+  out->n_callsets = slots.size(); out->callset_off = c->cs_off.data(); out->callset_items = c->cs_items.data();
+  out->n_pairs_seen = c->pairs_seen; out->n_unique_keys = h.n_keys; out->n_slots = c->cs_slots; out->slot_to_callset = c->slot_dense.data();
+  return NB_OK;
+}
+
+int nb_counts_reset(nb_ctx* c) {
+  if (!c) return fail(NB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  if (c->tables_ready) { CK(cudaStreamSynchronize(c->stream)); c->tables_ready = false; }
+  c->mode = -1; c->folded = false; c->pairs_seen = 0; c->keys_upper = 0; c->have_last = false;
+  return NB_OK;
+}
+
+int nb_ctx_work_counters(nb_ctx* c, uint64_t* out4) {
+  if (!c || !out4) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->tables_ready) { out4[0] = out4[1] = out4[2] = out4[3] = 0; return NB_OK; }
+  Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
+  out4[0] = h.probes; out4[1] = h.nodes; out4[2] = h.bases; out4[3] = h.colour_elems;
+  return NB_OK;
+}
+
+int nb_ctx_kernel_stats(nb_ctx* c, double* o, int reset) {
+  if (!c || !o) return fail(NB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+  for (auto& e : c->ev_pending) { float ms = 0; CK(cudaEventElapsedTime(&ms, e.first, e.second)); c->map_ms += ms; c->ev_free.push_back(e); }
+  c->ev_pending.clear();
+  o[0] = (double)c->map_launches; o[1] = c->map_ms; o[2] = (double)c->map_reads; o[3] = (double)c->all_launches;
+  if (reset) { c->map_launches = 0; c->map_ms = 0; c->map_reads = 0; c->all_launches = 0; }
+  return NB_OK;
+}
+
+int nb_keys_export_count(nb_ctx* c, uint64_t* n) {
+  if (!c || !n) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->tables_ready) { *n = 0; return NB_OK; }
+  Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
+  *n = h.n_keys; return NB_OK;
+}
+int nb_keys_export(nb_ctx* c, void* dev_records, uint64_t cap, uint64_t pair_index_base) {
+  if (!c || (!dev_records && cap)) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->tables_ready) return NB_OK;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(c->d_nout.p, 0, 8, c->stream));
+  nbk::launch_keys_export(make_tables(c), dev_records, (unsigned long long*)c->d_nout.p, cap, pair_index_base, c->stream); c->all_launches++;
+  CK(cudaStreamSynchronize(c->stream));
+  return NB_OK;
+}
+// callset dictionary entries as (tag, len, items[gcap]) rows so that ranks can merge dictionaries on the host
+int nb_callsets_export(nb_ctx* c, uint64_t* tags, uint32_t* lens, uint32_t* items, uint64_t cap, uint64_t* n_out, uint32_t* gcap_out) {
+  if (!c || !n_out) return fail(NB_ERR_INVALID, "null argument");
+  *n_out = 0; if (gcap_out) *gcap_out = c->gcap;
+  if (!c->tables_ready) return NB_OK;
+  CK(cudaSetDevice(c->device));
+  std::vector<u64> tag(c->cs_slots); std::vector<u32> len(c->cs_slots), it((size_t)c->cs_slots * c->gcap);
+  CK(cudaMemcpyAsync(tag.data(), c->d_cstag.p, c->cs_slots * 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaMemcpyAsync(len.data(), c->d_cslen.p, c->cs_slots * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(it.data(), c->d_csitems.p, it.size() * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+  u64 n = 0;
+  for (u32 i = 0; i < c->cs_slots; i++) if (tag[i]) { if (tags && n < cap) { tags[n] = tag[i]; lens[n] = len[i]; memcpy(items + n * c->gcap, &it[(size_t)i * c->gcap], c->gcap * 4); } n++; }
+  *n_out = n;
+  return NB_OK;
+}
+// insert callsets received from other ranks (same tag function as the device uses) so that imported key records resolve
+int nb_callsets_import(nb_ctx* c, const uint64_t* tags, const uint32_t* lens, const uint32_t* items, uint64_t n) {
+  if (!c || (n && (!tags || !lens || !items))) return fail(NB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
+  std::vector<u64> tag(c->cs_slots); std::vector<u32> len(c->cs_slots), it((size_t)c->cs_slots * c->gcap);
+  CK(cudaMemcpyAsync(tag.data(), c->d_cstag.p, c->cs_slots * 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaMemcpyAsync(len.data(), c->d_cslen.p, c->cs_slots * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(it.data(), c->d_csitems.p, it.size() * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+  u32 mask = (u32)c->cs_slots - 1;
+  for (u64 i = 0; i < n; i++) {
+    u32 h = (u32)(tags[i] >> 24) & mask; bool done = false;
+    for (u64 pr = 0; pr <= mask; pr++) { if (tag[h] == tags[i]) { done = true; break; } if (!tag[h]) { tag[h] = tags[i]; len[h] = lens[i]; memcpy(&it[(size_t)h * c->gcap], items + i * c->gcap, c->gcap * 4); done = true; break; } h = (h + 1) & mask; }
+    if (!done) return fail(NB_ERR_OVERFLOW, "callset dictionary full: raise option callset_slots");
+  }
+  CK(cudaMemcpyAsync(c->d_cstag.p, tag.data(), c->cs_slots * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaMemcpyAsync(c->d_cslen.p, len.data(), c->cs_slots * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_csitems.p, it.data(), it.size() * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
+  return NB_OK;
+}
+// replace this context's whole-run key table by the received partition (records from all ranks whose keys fall in
+// this rank's range) so that nb_counts_finalize counts each unique read_key of the partition once
+int nb_keys_import(nb_ctx* c, const void* dev_records, uint64_t n) {
+  if (!c || (n && !dev_records)) return fail(NB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
+  if (c->mode == 1) return fail(NB_ERR_INVALID, "key exchange applies to the whole-run scope only");
+  c->mode = 0;
+  cudaStream_t s = c->stream;
+  if (2 * n > c->key_slots) { c->d_key.release(); c->d_kval.release(); u64 ns = c->key_slots; while (ns < 2 * n) ns <<= 1; c->key_slots = ns; CK(c->d_key.ensure(ns * 16, s)); CK(c->d_kval.ensure(ns * 8, s)); }
+  CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s));
+  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
+  nbk::launch_keys_import(make_tables(c), dev_records, n, s); c->all_launches++;
+  c->folded = false;
+  return check_device_errors(c);
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+// index_build.cpp — host build of the coloured, compacted, stranded de Bruijn graph (k = 30) into the flat GPU layout.
+//
+// Replaces debruijn_mapping::build_index::build_index::<Kmer30>(seqs, names, {}, cores)
+// (call sites /root/reference/src/bin/main.rs:121-128, tests/utils.rs:48-51; the crate itself is an un-vendored git
+// dependency, Cargo.toml:23).  Semantics: every 30-mer of every sequence, stranded; colour =
+// sorted set of sequence ids containing the k-mer; exts = bases observed before / after any occurrence; unitigs join
+// x -> y iff |R(x)| == 1, |L(y)| == 1 and colour(x) == colour(y); a pure cycle starts at its smallest k-mer.
+// Method here (not the upstream's minimizer shards + MPHF): enumerate occurrences, bucketed parallel sort, group,
+// open-addressed table (linear probing, load <= 0.5) over the distinct k-mers, chain walk by list ranking on threads.
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <unordered_map>
+
+#include "host.hpp"
+
+using namespace nb;
+
+namespace {
+
+struct Occ { u64 kmer; u32 id; u32 lr; };  // kmer big-endian (first base most significant => lexicographic order); lr = l | r<<4, 4 = none
+
+inline u64 mix64(u64 x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
+
+// big-endian 60-bit k-mer -> device form (base i at bits 2i)
+inline u64 to_device_form(u64 be) { u64 v = 0; for (int i = 0; i < K; i++) { v |= ((be >> (2 * (K - 1 - i))) & 3) << (2 * i); } return v; }
+
+void parallel_for(int n_threads, u64 n, const std::function<void(u64, u64, int)>& fn) {
+  if (n_threads <= 1 || n < 4096) { fn(0, n, 0); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; t++) { u64 a = n * (u64)t / (u64)n_threads, b = n * (u64)(t + 1) / (u64)n_threads; th.emplace_back(fn, a, b, t); }
+  for (auto& x : th) x.join();
+}
+
+struct Table {
+  std::vector<u64>& key; std::vector<u64>& val; u64 mask;
+  // returns slot of kmer (device form) or ~0
+  u64 find(u64 dk) const { u64 h = mix64(dk) & mask; for (;;) { u64 k = key[h]; if (!(k >> 63)) return ~0ULL; if ((k & KMASK) == dk) return h; h = (h + 1) & mask; } }
+};
+
+}  // namespace
+
+int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads, nb_index** out) {
+  if (n_threads < 1) n_threads = 1;
+  if (seqs.size() >= 0xFFFFFFFFull) return fail(NB_ERR_UNSUPPORTED, "too many reference sequences");
+  nb_index* ix = new nb_index();
+  ix->n_sequences = seqs.size();
+  // ---- 1. enumerate occurrences
+  std::vector<u64> occ_off(seqs.size() + 1, 0);
+  for (size_t s = 0; s < seqs.size(); s++) occ_off[s + 1] = occ_off[s] + (seqs[s].size() >= (size_t)K ? seqs[s].size() - K + 1 : 0);
+  u64 n_occ = occ_off.back();
+  std::vector<Occ> occ(n_occ);
+  parallel_for(n_threads, seqs.size(), [&](u64 a, u64 b, int) {
+    for (u64 s = a; s < b; s++) {
+      const std::vector<u8>& d = seqs[s];
+      if (d.size() < (size_t)K) continue;
+      u64 km = 0; Occ* o = &occ[occ_off[s]];
+      for (size_t p = 0; p < d.size(); p++) {
+        km = ((km << 2) | d[p]) & KMASK;
+        if (p + 1 >= (size_t)K) {
+          size_t st = p + 1 - K;
+          o->kmer = km; o->id = (u32)s; o->lr = (st > 0 ? d[st - 1] : 4u) | ((p + 1 < d.size() ? d[p + 1] : 4u) << 4);
+          o++;
+        }
+      }
+    }
+  });
+  // ---- 2. bucketed parallel sort by (kmer, id): bucket = top 10 bits (first 5 bases)
+  const int NB = 1024;
+  std::vector<Occ> sorted(n_occ);
+  std::vector<u64> bstart(NB + 1, 0);
+  {
+    std::vector<std::vector<u64>> cnt(n_threads, std::vector<u64>(NB, 0));
+    parallel_for(n_threads, n_occ, [&](u64 a, u64 b, int t) { for (u64 i = a; i < b; i++) cnt[t][occ[i].kmer >> 50]++; });
+    bool used_threads = !(n_threads <= 1 || n_occ < 4096);
+    int T = used_threads ? n_threads : 1;
+    std::vector<std::vector<u64>> pos(T, std::vector<u64>(NB, 0));
+    u64 run = 0;
+    for (int bkt = 0; bkt < NB; bkt++) { bstart[bkt] = run; for (int t = 0; t < T; t++) { pos[t][bkt] = run; run += cnt[t][bkt]; } }
+    bstart[NB] = run;
+    parallel_for(n_threads, n_occ, [&](u64 a, u64 b, int t) { for (u64 i = a; i < b; i++) sorted[pos[t][occ[i].kmer >> 50]++] = occ[i]; });
+    std::atomic<int> next(0);
+    auto work = [&]() { for (;;) { int bkt = next.fetch_add(1); if (bkt >= NB) break; std::sort(sorted.begin() + bstart[bkt], sorted.begin() + bstart[bkt + 1], [](const Occ& x, const Occ& y) { return x.kmer != y.kmer ? x.kmer < y.kmer : x.id < y.id; }); } };
+    std::vector<std::thread> th; for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+    work(); for (auto& x : th) x.join();
+  }
+  std::vector<Occ>().swap(occ);
+  // ---- 3. group into distinct k-mers (sorted order): exts, colour signature; intern colours
+  std::vector<u64> gstart;  // start offset of each distinct k-mer in `sorted`
+  {
+    std::vector<std::vector<u64>> parts(NB);
+    std::atomic<int> next(0);
+    auto work = [&]() { for (;;) { int bkt = next.fetch_add(1); if (bkt >= NB) break; auto& v = parts[bkt]; for (u64 i = bstart[bkt]; i < bstart[bkt + 1]; i++) if (i == bstart[bkt] || sorted[i].kmer != sorted[i - 1].kmer) v.push_back(i); } };
+    std::vector<std::thread> th; for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+    work(); for (auto& x : th) x.join();
+    u64 tot = 0; for (auto& v : parts) tot += v.size();
+    gstart.reserve(tot + 1);
+    for (auto& v : parts) gstart.insert(gstart.end(), v.begin(), v.end());
+    gstart.push_back(n_occ);
+  }
+  u64 n = gstart.size() - 1;
+  ix->n_kmers = n;
+  std::vector<u64> kmers(n); std::vector<u8> L(n), R(n); std::vector<u32> col(n);
+  std::vector<u64> sig_a(n), sig_b(n);
+  parallel_for(n_threads, n, [&](u64 a, u64 b, int) {
+    for (u64 g = a; g < b; g++) {
+      u8 l = 0, r = 0; u64 ha = 0x9E3779B97F4A7C15ULL, hb = 0xC2B2AE3D27D4EB4FULL; u32 last = NONE32;
+      for (u64 i = gstart[g]; i < gstart[g + 1]; i++) {
+        u32 lr = sorted[i].lr;
+        if ((lr & 15) < 4) l |= (u8)(1u << (lr & 15));
+        if ((lr >> 4) < 4) r |= (u8)(1u << (lr >> 4));
+        if (sorted[i].id != last) { last = sorted[i].id; ha = mix64(ha ^ last) + 0x632BE59BD9B4E019ULL; hb = mix64(hb + last * 0x9FB21C651E98DF25ULL); }
+      }
+      kmers[g] = sorted[gstart[g]].kmer; L[g] = l; R[g] = r; sig_a[g] = ha; sig_b[g] = hb;
+    }
+  });
+  {
+    struct Sig { u64 a, b; bool operator==(const Sig& o) const { return a == o.a && b == o.b; } };
+    struct SigHash { size_t operator()(const Sig& s) const { return (size_t)(s.a ^ (s.b * 0x9E3779B97F4A7C15ULL)); } };
+    std::unordered_map<Sig, u32, SigHash> intern;
+    ix->col_off.push_back(0);
+    u64 prev_a = 0, prev_b = 0; u32 prev_c = NONE32;
+    for (u64 g = 0; g < n; g++) {
+      if (prev_c != NONE32 && sig_a[g] == prev_a && sig_b[g] == prev_b) { col[g] = prev_c; continue; }
+      auto it = intern.find(Sig{sig_a[g], sig_b[g]});
+      u32 c;
+      if (it == intern.end()) {
+        c = (u32)ix->col_off.size() - 1; intern.emplace(Sig{sig_a[g], sig_b[g]}, c);
+        u32 last = NONE32;
+        for (u64 i = gstart[g]; i < gstart[g + 1]; i++) if (sorted[i].id != last) { last = sorted[i].id; ix->col_ids.push_back(last); }
+        if (ix->col_ids.size() >= 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "colour table exceeds 2^32 entries"); }
+        ix->col_off.push_back((u32)ix->col_ids.size());
+      } else c = it->second;
+      col[g] = c; prev_a = sig_a[g]; prev_b = sig_b[g]; prev_c = c;
+    }
+  }
+  std::vector<Occ>().swap(sorted); std::vector<u64>().swap(gstart); std::vector<u64>().swap(sig_a); std::vector<u64>().swap(sig_b);
+  // ---- 4. open-addressed table over distinct k-mers (value = distinct index for now)
+  u64 slots = 16; while (slots < 2 * n) slots <<= 1;
+  ix->table_mask = slots - 1;
+  ix->table_key.assign(slots, 0); ix->table_val.assign(slots, 0);
+  {
+    std::atomic<u64>* keys = reinterpret_cast<std::atomic<u64>*>(ix->table_key.data());
+    parallel_for(n_threads, n, [&](u64 a, u64 b, int) {
+      for (u64 g = a; g < b; g++) {
+        u64 dk = to_device_form(kmers[g]) | (1ULL << 63); u64 h = mix64(dk & KMASK) & ix->table_mask;
+        for (;;) { u64 expect = 0; if (keys[h].compare_exchange_strong(expect, dk, std::memory_order_relaxed)) { ix->table_val[h] = g; break; } h = (h + 1) & ix->table_mask; }
+      }
+    });
+  }
+  Table tab{ix->table_key, ix->table_val, ix->table_mask};
+  auto index_of = [&](u64 be) -> u64 { u64 s = tab.find(to_device_form(be)); return s == ~0ULL ? ~0ULL : ix->table_val[s]; };
+  // ---- 5. join relation
+  std::vector<u32> succ(n, NONE32), pred(n, NONE32);
+  if (n >= 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "more than 2^32 distinct k-mers"); }
+  parallel_for(n_threads, n, [&](u64 a, u64 b, int) {
+    for (u64 g = a; g < b; g++) {
+      if (__builtin_popcount(R[g]) != 1) continue;
+      u64 y = ((kmers[g] << 2) | (u64)__builtin_ctz(R[g])) & KMASK;
+      u64 j = index_of(y);
+      if (j != ~0ULL && __builtin_popcount(L[j]) == 1 && col[g] == col[j]) { succ[g] = (u32)j; pred[j] = (u32)g; }  // pred[j] has a single writer: |L(j)| == 1
+    }
+  });
+  // ---- 6. unitigs: starts = k-mers without a joining predecessor; pure cycles start at their smallest k-mer
+  std::vector<u64> starts;
+  for (u64 g = 0; g < n; g++) if (pred[g] == NONE32) starts.push_back(g);
+  std::vector<u32> node_of(n, NONE32), off_of(n, 0);
+  std::vector<u32> node_len;  // in k-mers
+  std::vector<u64> node_first, node_last;
+  auto walk = [&](u64 s, u32 id) { u64 cur = s; u32 o = 0; for (;;) { node_of[cur] = id; off_of[cur] = o; u32 nx = succ[cur]; if (nx == NONE32 || node_of[nx] != NONE32) break; cur = nx; o++; } return std::make_pair(cur, o + 1); };
+  node_len.resize(starts.size()); node_first.resize(starts.size()); node_last.resize(starts.size());
+  parallel_for(n_threads, starts.size(), [&](u64 a, u64 b, int) { for (u64 i = a; i < b; i++) { auto r = walk(starts[i], (u32)i); node_first[i] = starts[i]; node_last[i] = r.first; node_len[i] = r.second; } });
+  for (u64 g = 0; g < n; g++) if (node_of[g] == NONE32) {  // cycles (rare), ascending k-mer order
+    u32 id = (u32)node_len.size(); auto r = walk(g, id); node_first.push_back(g); node_last.push_back(r.first); node_len.push_back(r.second);
+  }
+  u64 n_nodes = node_len.size();
+  std::vector<u64> base_start(n_nodes + 1, 0);
+  for (u64 i = 0; i < n_nodes; i++) base_start[i + 1] = base_start[i] + node_len[i] + K - 1;
+  ix->unitig_bases = base_start[n_nodes];
+  if (ix->unitig_bases >> 40) { delete ix; return fail(NB_ERR_UNSUPPORTED, "unitig store exceeds 2^40 bases"); }
+  ix->unitig.assign((ix->unitig_bases + 31) / 32 + 2, 0);
+  ix->node.resize(n_nodes); ix->redge.assign(4 * n_nodes, NONE32); ix->ledge.assign(4 * n_nodes, NONE32);
+  parallel_for(n_threads, n_nodes, [&](u64 a, u64 b, int) {
+    for (u64 i = a; i < b; i++) {
+      u64 pos = base_start[i];
+      auto put = [&](u64 base) { __atomic_fetch_or(&ix->unitig[pos >> 5], base << (2 * (pos & 31)), __ATOMIC_RELAXED); pos++; };
+      u64 first = kmers[node_first[i]];
+      for (int k = K - 1; k >= 0; k--) put((first >> (2 * k)) & 3);
+      u64 cur = node_first[i];
+      for (u32 o = 1; o < node_len[i]; o++) { cur = succ[cur]; put(kmers[cur] & 3); }
+      NodeRec& nr = ix->node[i];
+      nr.start_lo = (u32)base_start[i]; nr.len = node_len[i] + K - 1; nr.colour = col[node_first[i]];
+      nr.exts_hi = (u32)L[node_first[i]] | ((u32)R[node_last[i]] << 4) | ((u32)(base_start[i] >> 32) << 8);
+    }
+  });
+  // table values -> (node, offset)
+  parallel_for(n_threads, slots, [&](u64 a, u64 b, int) { for (u64 h = a; h < b; h++) if (ix->table_key[h] >> 63) { u64 g = ix->table_val[h]; ix->table_val[h] = (u64)node_of[g] | ((u64)off_of[g] << 32); } });
+  // distinct index of a k-mer is gone from the table now; edges need start/end node of neighbouring k-mers, which the
+  // table gives directly: right edge target must sit at offset 0, left edge target at its node's last k-mer.
+  int bad = 0;
+  parallel_for(n_threads, n_nodes, [&](u64 a, u64 b, int) {
+    for (u64 i = a; i < b; i++) {
+      u64 first = kmers[node_first[i]], last = kmers[node_last[i]];
+      u8 l = L[node_first[i]], r = R[node_last[i]];
+      for (int bb = 0; bb < 4; bb++) {
+        if (r >> bb & 1) { u64 y = ((last << 2) | (u64)bb) & KMASK; u64 s = tab.find(to_device_form(y)); if (s == ~0ULL || (ix->table_val[s] >> 32) != 0) { bad = 1; continue; } ix->redge[4 * i + bb] = (u32)ix->table_val[s]; }
+        if (l >> bb & 1) { u64 x = (first >> 2) | ((u64)bb << 58); u64 s = tab.find(to_device_form(x)); if (s == ~0ULL) { bad = 1; continue; } u32 nd = (u32)ix->table_val[s]; if ((u32)(ix->table_val[s] >> 32) != node_len[nd] - 1) { bad = 1; continue; } ix->ledge[4 * i + bb] = nd; }
+      }
+    }
+  });
+  if (bad) { delete ix; return fail(NB_ERR_INVALID, "internal: de Bruijn edge does not land on a unitig boundary"); }
+  *out = ix;
+  return NB_OK;
+}
+
+extern "C" {
+
+int nb_index_build_from_sequences(const uint8_t* seq_ascii, const uint64_t* seq_off, uint32_t n_seqs, int n_threads, nb_index** out) {
+  if (!seq_off || !out || (!seq_ascii && n_seqs)) return fail(NB_ERR_INVALID, "null argument");
+  std::vector<std::vector<u8>> seqs(n_seqs);
+  for (u32 s = 0; s < n_seqs; s++) { u64 a = seq_off[s], b = seq_off[s + 1]; seqs[s].resize(b - a); for (u64 i = a; i < b; i++) seqs[s][i - a] = base_code(seq_ascii[i]); }
+  return nb_build_index_impl(seqs, n_threads, out);
+}
+// utils::get_reference_sequence_data (src/utils.rs:7-24): DnaString::from_acgt_bytes over the sequence column, then build_index
+int nb_index_build(const nb_library* lib, int n_threads, nb_index** out) {
+  if (!lib || !out) return fail(NB_ERR_INVALID, "null argument");
+  const std::vector<std::string>& col = lib->columns[lib->seq_idx];
+  std::vector<std::vector<u8>> seqs(col.size());
+  for (size_t s = 0; s < col.size(); s++) { seqs[s].resize(col[s].size()); for (size_t i = 0; i < col[s].size(); i++) seqs[s][i] = base_code((u8)col[s][i]); }
+  return nb_build_index_impl(seqs, n_threads, out);
+}
+void nb_index_free(nb_index* ix) { delete ix; }
+int nb_index_stats(const nb_index* ix, uint64_t* o) {
+  if (!ix || !o) return fail(NB_ERR_INVALID, "null argument");
+  o[0] = ix->n_kmers; o[1] = ix->node.size(); o[2] = ix->col_off.size() - 1; o[3] = ix->col_ids.size(); o[4] = ix->unitig_bases;
+  o[5] = ix->table_key.size(); o[6] = ix->device_bytes(); o[7] = ix->n_sequences;
+  return NB_OK;
+}
+uint64_t nb_index_dump(const nb_index* ix, char* buf, uint64_t cap) {
+  std::vector<std::string> lines(ix->node.size());
+  for (size_t i = 0; i < ix->node.size(); i++) {
+    const NodeRec& nr = ix->node[i]; u64 st = (u64)nr.start_lo | ((u64)(nr.exts_hi >> 8) << 32);
+    std::string l(nr.len, 'A');
+    for (u32 p = 0; p < nr.len; p++) { u64 pos = st + p; l[p] = "ACGT"[(ix->unitig[pos >> 5] >> (2 * (pos & 31))) & 3]; }
+    l += "\t";
+    for (u32 c = ix->col_off[nr.colour]; c < ix->col_off[nr.colour + 1]; c++) { if (c != ix->col_off[nr.colour]) l += ","; l += std::to_string(ix->col_ids[c]); }
+    l += "\t" + std::to_string(nr.exts_hi & 15) + "\t" + std::to_string((nr.exts_hi >> 4) & 15) + "\n";
+    lines[i] = l;
+  }
+  std::sort(lines.begin(), lines.end());
+  u64 tot = 0; for (auto& l : lines) tot += l.size();
+  if (buf && cap >= tot) { u64 p = 0; for (auto& l : lines) { memcpy(buf + p, l.data(), l.size()); p += l.size(); } }
+  return tot;
+}
+
+}  // extern "C"

@@ -1,0 +1,558 @@
+// kernels.cu — hand-written sm_100a kernels (see kernels.cuh for the map to the reference functions).
+#include <float.h>
+
+#include "kernels.cuh"
+
+namespace nbk {
+
+// FilterReason values used on the device (src/align.rs:32-51 order)
+enum { R_SCORE_BELOW = 0, R_MULTI = 1, R_NONZERO_MM = 2, R_NO_MATCH = 3, R_NOT_MATCHING_PAIR = 6, R_SHORT = 8, R_MAX_HITS = 9,
+       R_ENTROPY = 10, R_SUCCESS = 11, R_TRIAGE_EMPTY = 13, R_ABOVE_MM = 14, R_SKIPPED = 15, R_NONE = 16 };
+
+__host__ __device__ __forceinline__ u64 mix64(u64 x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
+}
+
+// ------------------------------------------------------------------------------------------------ K0 pack
+// One thread per (read, 32-base word).  The 32 source bytes are fetched as aligned 32-bit words and realigned with
+// funnel shifts; 4 bases are classified per SIMD-in-register compare (non-ACGT -> A like DnaString::from_acgt_bytes).
+__device__ __forceinline__ u32 codes4(u32 v) {
+  u32 u = v & 0xDFDFDFDFu;
+  u32 c4 = (__vcmpeq4(u, 0x43434343u) & 0x01010101u) | (__vcmpeq4(u, 0x47474747u) & 0x02020202u) | (__vcmpeq4(u, 0x54545454u) & 0x03030303u);
+  c4 = (c4 | (c4 >> 6)) & 0x000F000Fu;
+  return (c4 | (c4 >> 12)) & 0xFFu;
+}
+__device__ __forceinline__ u64 rev2(u64 x) {  // reverse the order of the 32 2-bit groups
+  x = __brevll(x);
+  return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+}
+
+__global__ void __launch_bounds__(256) k_pack(BatchDev b) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx >= (u64)b.n_reads * b.W) return;
+  u32 ri = (u32)(idx / b.W), w = (u32)(idx % b.W);
+  u32 side = ri % b.sides; u64 p = ri / b.sides;
+  u64 o0 = b.off[side][p]; u32 len = (u32)(b.off[side][p + 1] - o0);
+  bool rc = b.flags[side] != nullptr && (b.flags[side][p] & 2);
+  if (w == 0) { b.len_full[ri] = len; b.len_trim[ri] = len; }
+  u64 word = 0; u32 s = w * 32;
+  if (s < len) {
+    u32 cnt = min(32u, len - s);
+    u64 src = rc ? (o0 + len - s - cnt) : (o0 + s);
+    const u8* addr = b.a[side] + src;
+    const u32* al = (const u32*)((uintptr_t)addr & ~(uintptr_t)3);
+    u32 sh = (u32)((uintptr_t)addr & 3);
+    u32 nwords = (sh + cnt + 3) >> 2;  // <= 9
+    u32 wv[10];
+#pragma unroll
+    for (int j = 0; j < 9; j++) wv[j] = j < (int)nwords ? __ldg(al + j) : 0u;
+    wv[9] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      u32 v = __funnelshift_r(wv[j], wv[j + 1], sh * 8);
+      word |= (u64)codes4(v) << (8 * j);
+    }
+    if (cnt < 32) word &= (1ULL << (2 * cnt)) - 1;
+    if (rc) { word = rev2(word) >> (64 - 2 * cnt); word ^= cnt < 32 ? ((1ULL << (2 * cnt)) - 1) : ~0ULL; }
+  }
+  b.pk[(u64)w * b.n_reads + ri] = word;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 trim (maxinfo)
+__global__ void __launch_bounds__(256) k_trim(BatchDev b, Tables t) {
+  u32 ri = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ri >= b.n_reads) return;
+  u32 side = ri % b.sides; u64 p = ri / b.sides;
+  if (b.q[side] == nullptr) return;
+  u64 o0 = b.off[side][p]; u32 len = (u32)(b.off[side][p + 1] - o0);
+  bool rc = b.flags[side] != nullptr && (b.flags[side][p] & 2);
+  const u8* q = b.q[side] + o0;
+  i64 acc = 0; double max_score = -DBL_MAX; u32 pos = 0;
+  for (u32 i = 0; i < len; i++) {
+    u32 qq = rc ? q[len - 1 - i] : q[i];
+    if (qq > 60) qq = 60;
+    acc += t.qp[qq];
+    i64 score = (i < 1000 ? t.ls[i] : 0) + acc;
+    if ((double)score >= max_score) { max_score = (double)score; pos = i + 1; }
+  }
+  u32 r = (pos < 1 || max_score == 0.0) ? 0u : min(pos, len);
+  b.len_trim[ri] = r;
+}
+
+// ------------------------------------------------------------------------------------------------ K2 map
+struct ReadView {
+  const u64* p; u32 stride;
+  __device__ __forceinline__ u64 word(u32 w) const { return __ldg(p + (u64)w * stride); }
+  __device__ __forceinline__ u64 win(u32 pos) const {
+    u32 w = pos >> 5, sh = (pos & 31) * 2; u64 lo = word(w);
+    if (!sh) return lo;
+    return (lo >> sh) | (word(w + 1) << (64 - sh));
+  }
+  __device__ __forceinline__ u32 base(u32 pos) const { return (u32)(word(pos >> 5) >> ((pos & 31) * 2)) & 3u; }
+};
+__device__ __forceinline__ u64 uwin(const u64* U, u64 pos) {
+  u64 w = pos >> 5; u32 sh = (u32)(pos & 31) * 2; u64 lo = __ldg(U + w);
+  if (!sh) return lo;
+  return (lo >> sh) | (__ldg(U + w + 1) << (64 - sh));
+}
+__device__ __forceinline__ bool bsearch32(const u32* a, u32 n, u32 x, u32& idx) {
+  u32 lo = 0, hi = n;
+  while (lo < hi) { u32 mid = (lo + hi) >> 1; if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid; }
+  idx = lo; return lo < n && __ldg(a + lo) == x;
+}
+
+struct WorkCnt { u32 probes, nodes, bases, colour_elems; };
+
+// Running intersection of the colours of the visited unitigs.  "mask mode": survivors are a 64-bit mask over the
+// smallest-so-far colour list (<= 64 ids); "big mode": a private copy in the arena that shrinks in place.
+struct EcAcc {
+  const u32* col_off; const u32* col_ids; u32* arena; Counters* ctr; u64 arena_cap;
+  bool any, big; u32 last, base, bsize, alen; u64 boff, aoff, mask;
+  __device__ void init(const DevIndex& ix, const Tables& t) { col_off = ix.col_off; col_ids = ix.col_ids; arena = t.arena; ctr = t.ctr; arena_cap = t.arena_cap; any = big = false; last = NONE32; base = NONE32; bsize = alen = 0; boff = aoff = 0; mask = 0; }
+  __device__ void add(u32 cid, WorkCnt& wc) {
+    if (cid == last) { return; }
+    last = cid;
+    u32 o = __ldg(col_off + cid), s = __ldg(col_off + cid + 1) - o;
+    wc.colour_elems += s;
+    if (!any) {
+      any = true; base = cid; boff = o; bsize = s;
+      if (s <= 64) mask = s == 64 ? ~0ULL : ((1ULL << s) - 1);
+      else {
+        big = true; alen = s;
+        aoff = atomicAdd(&ctr->arena_top, (unsigned long long)s);
+        if (aoff + s > arena_cap) { atomicOr(&ctr->err, (unsigned)E_ARENA); alen = 0; aoff = 0; return; }
+        for (u32 i = 0; i < s; i++) arena[aoff + i] = __ldg(col_ids + o + i);
+      }
+      return;
+    }
+    if (!big) {
+      if (cid == base) return;
+      u64 m = mask;
+      while (m) { int i = __ffsll((long long)m) - 1; m &= m - 1; u32 idx; if (!bsearch32(col_ids + o, s, __ldg(col_ids + boff + i), idx)) mask &= ~(1ULL << i); }
+    } else if (s <= 64) {
+      u64 nm = 0;
+      for (u32 i = 0; i < s; i++) { u32 e = __ldg(col_ids + o + i); u32 lo = 0, hi = alen; while (lo < hi) { u32 mid = (lo + hi) >> 1; if (arena[aoff + mid] < e) lo = mid + 1; else hi = mid; } if (lo < alen && arena[aoff + lo] == e) nm |= 1ULL << i; }
+      big = false; base = cid; boff = o; bsize = s; mask = nm;
+    } else {
+      u32 j = 0;
+      for (u32 i = 0; i < alen; i++) { u32 e = arena[aoff + i], idx; if (bsearch32(col_ids + o, s, e, idx)) arena[aoff + j++] = e; }
+      alen = j;
+    }
+  }
+  __device__ u32 ec_len() const { return !any ? 0u : (big ? alen : (u32)__popcll(mask)); }
+};
+
+// forward compare of m bases: unitig [upos, upos+m) vs read [rpos, rpos+m); the (allowed+1)-th mismatch trips the
+// per-node budget: it is counted in snp (-> mismatches) but not in mb (-> coverage)   [App. B]
+__device__ __forceinline__ void cmp_fwd(const u64* U, u64 upos, const ReadView& rd, u32 rpos, u32 m, u32 allowed, u32& mb, u32& snp, bool& brk) {
+  mb = 0; snp = 0; brk = false;
+  while (mb < m) {
+    u32 c = min(32u, m - mb);
+    u64 x = uwin(U, upos + mb) ^ rd.win(rpos + mb);
+    u64 d = (x | (x >> 1)) & 0x5555555555555555ULL;
+    if (c < 32) d &= (1ULL << (2 * c)) - 1;
+    u32 cnt = (u32)__popcll(d);
+    if (snp + cnt <= allowed) { snp += cnt; mb += c; continue; }
+    u32 need = allowed - snp;
+    for (u32 i = 0; i < need; i++) d &= d - 1;
+    mb += (u32)(__ffsll((long long)d) - 1) >> 1;
+    snp = allowed + 1; brk = true; break;
+  }
+}
+// backward compare: unitig positions uhi-i vs read positions rhi-i, i in [0, m)
+__device__ __forceinline__ void cmp_bwd(const u64* U, u64 uhi, const ReadView& rd, u32 rhi, u32 m, u32 allowed, u32& mb, u32& snp, bool& brk) {
+  mb = 0; snp = 0; brk = false;
+  while (mb < m) {
+    u32 c = min(32u, m - mb);
+    u64 x = uwin(U, uhi - mb - (c - 1)) ^ rd.win(rhi - mb - (c - 1));
+    u64 d = (x | (x >> 1)) & 0x5555555555555555ULL;
+    if (c < 32) d &= (1ULL << (2 * c)) - 1;
+    u32 cnt = (u32)__popcll(d);
+    if (snp + cnt <= allowed) { snp += cnt; mb += c; continue; }
+    u32 need = allowed - snp;
+    for (u32 i = 0; i < need; i++) d &= ~(1ULL << (63 - __clzll((long long)d)));
+    u32 j = (u32)(63 - __clzll((long long)d)) >> 1;
+    mb += c - 1 - j;
+    snp = allowed + 1; brk = true; break;
+  }
+}
+
+__device__ __forceinline__ bool find_seed(const DevIndex& ix, const ReadView& rd, u32& kp, u32 last_kpos, u32& node, u32& off, WorkCnt& wc) {
+  while (kp <= last_kpos) {  // seeds at stride 3 [App. B]
+    u64 km = rd.win(kp) & KMASK;
+    u64 h = mix64(km) & ix.tmask;
+    wc.probes++;
+    for (;;) {
+      u64 k = __ldg(ix.tkey + h);
+      if (!(k >> 63)) break;
+      if ((k & KMASK) == km) { u64 v = __ldg(ix.tval + h); node = (u32)v; off = (u32)(v >> 32); return true; }
+      h = (h + 1) & ix.tmask;
+    }
+    kp += 3;
+  }
+  return false;
+}
+
+template <int COUNT_WORK>
+__global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg, Tables t) {
+  u32 ri = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ri >= b.n_reads) return;
+  u32 side = ri % b.sides; u64 p = ri / b.sides;
+  ReadRes rr; rr.hdr = R_SUCCESS; rr.score = 0; rr.mm = 0; rr.ec_len = 0; rr.bsize = 0; rr.ref = 0; rr.mask = 0;
+  WorkCnt wc = {0, 0, 0, 0};
+  u32 n = b.len_trim[ri];
+  bool skip = b.flags[side] != nullptr && (b.flags[side][p] & 1);
+  ReadView rd{b.pk + ri, b.n_reads};
+  if (skip) { rr.hdr = R_SKIPPED | (1u << 10); }                                        // src/align.rs:527-528
+  else if (n < cfg.min_read_len) { rr.hdr = R_SHORT; }                                               // src/align.rs:955-957
+  else {
+    // shannon_entropy on the (trimmed) read, src/utils.rs:96-119; terms come from a host-built table of
+    // f*log2(f) (same libm as the CPU reference), summed in the reference's A,T,C,G order.
+    u32 cA = 0, cC = 0, cG = 0, cT = 0;
+    for (u32 w = 0; w * 32 < n; w++) {
+      u64 x = rd.word(w); u32 c = min(32u, n - w * 32);
+      u64 lo = x & 0x5555555555555555ULL, hi = (x >> 1) & 0x5555555555555555ULL;
+      u64 valid = c < 32 ? ((1ULL << (2 * c)) - 1) & 0x5555555555555555ULL : 0x5555555555555555ULL;
+      cC += __popcll(lo & ~hi & valid); cG += __popcll(hi & ~lo & valid); cT += __popcll(hi & lo & valid);
+    }
+    cA = n - cC - cG - cT;
+    const double* et = t.ent + (size_t)n * (n + 1) / 2;
+    double e = 0.0;
+    if (cA) e += et[cA];
+    if (cT) e += et[cT];
+    if (cC) e += et[cC];
+    if (cG) e += et[cG];
+    if (-e < 1.75) { rr.hdr = R_ENTROPY; }                                              // src/align.rs:960-962
+    else {
+      EcAcc acc; acc.init(ix, t);
+      u32 cov = 0, mm = 0, allowed = cfg.num_mismatches;
+      u32 last_kpos = n - K, kp = n < (u32)K ? 1u : 0u, node = 0, off = 0;  // n < k: map_read returns None
+      if (n < (u32)K) last_kpos = 0;
+      const u32* redge = (const u32*)ix.redge; const u32* ledge = (const u32*)ix.ledge;
+      bool found = find_seed(ix, rd, kp, last_kpos, node, off, wc);
+      if (found) {
+        u32 lthr = (u32)(0.2 * (double)n);
+        if (kp >= lthr) {  // left extension [App. B]
+          u32 lp = kp - 1, pn = node, po = off > 0 ? off - 1 : 0;
+          for (;;) {
+            uint4 nd = __ldg(ix.node + pn);
+            u64 start = (u64)nd.x | ((u64)(nd.w >> 8) << 32);
+            u32 m = min(lp + 1, po + 1), mb, snp; bool brk;
+            cmp_bwd(ix.unitig, start + po, rd, lp, m, allowed, mb, snp, brk);
+            mm += snp; cov += mb; wc.bases += mb + (brk ? 1 : 0);
+            if (lp + 1 - mb == 0 || brk) break;
+            lp -= mb;
+            u32 bs = rd.base(lp);
+            if ((nd.w >> bs) & 1) {
+              pn = __ldg(ledge + 4 * (u64)pn + bs);
+              uint4 n2 = __ldg(ix.node + pn);
+              po = n2.y - K; acc.add(n2.z, wc); wc.nodes++;
+            } else break;
+          }
+        }
+        for (;;) {  // forward walk
+          uint4 nd = __ldg(ix.node + node);
+          u64 start = (u64)nd.x | ((u64)(nd.w >> 8) << 32);
+          kp += K; cov += K; acc.add(nd.z, wc); wc.nodes++;
+          u32 ro = off + K, m = min(n - kp, nd.y - ro), mb, snp; bool brk;
+          cmp_fwd(ix.unitig, start + ro, rd, kp, m, allowed, mb, snp, brk);
+          mm += snp; cov += mb; kp += mb; wc.bases += mb + (brk ? 1 : 0);
+          if (kp >= n) break;
+          u32 bs = rd.base(kp);
+          if (!brk && ((nd.w >> (4 + bs)) & 1)) { node = __ldg(redge + 4 * (u64)node + bs); off = 0; kp -= K - 1; cov -= K - 1; }
+          else { if (kp > last_kpos) break; if (!find_seed(ix, rd, kp, last_kpos, node, off, wc)) break; }
+        }
+      }
+      if (!acc.any) rr.hdr = R_NO_MATCH;                                               // src/align.rs:987
+      else {
+        u32 ecl = acc.ec_len();
+        rr.score = (u16)cov; rr.mm = (u16)mm; rr.ec_len = ecl; rr.bsize = acc.big ? acc.alen : acc.bsize;
+        rr.ref = acc.big ? acc.aoff : acc.boff; rr.mask = acc.mask;
+        double norm = (double)cov / (double)n;
+        u32 reason;
+        if (cfg.discard_nonzero_mismatch && mm != 0) reason = R_NONZERO_MM;             // src/align.rs:971-973
+        else if (cov >= cfg.score_threshold && norm >= cfg.score_percent && ecl != 0) {  // src/filter/align.rs:17-45
+          if (cfg.discard_multiple_matches && ecl > 1) reason = R_MULTI;
+          else if (mm > cfg.num_mismatches) reason = R_ABOVE_MM;
+          else reason = R_SUCCESS | (1u << 8);
+        } else reason = R_SCORE_BELOW;
+        rr.hdr = reason | (acc.big ? (1u << 9) : 0u);
+      }
+    }
+  }
+  b.rres[ri] = rr;
+  if (COUNT_WORK) {
+    atomicAdd(&t.ctr->probes, (unsigned long long)wc.probes); atomicAdd(&t.ctr->nodes, (unsigned long long)wc.nodes);
+    atomicAdd(&t.ctr->bases, (unsigned long long)wc.bases); atomicAdd(&t.ctr->colour_elems, (unsigned long long)wc.colour_elems);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K3 pair
+struct EcView { const u32* list; u64 mask; u32 lsize; u32 n; bool big; };
+__device__ __forceinline__ EcView make_view(const ReadRes& r, const DevIndex& ix, const Tables& t) {
+  EcView e; e.n = 0; e.list = nullptr; e.mask = 0; e.lsize = 0; e.big = false;
+  if (!((r.hdr >> 8) & 1)) return e;   // only passing alignments contribute an equivalence class (src/align.rs:561-572)
+  e.big = (r.hdr >> 9) & 1; e.n = r.ec_len; e.lsize = r.bsize; e.mask = r.mask;
+  e.list = e.big ? (t.arena + r.ref) : (ix.col_ids + r.ref);
+  return e;
+}
+__device__ __forceinline__ bool ec_has(const EcView& e, u32 x) {
+  if (e.n == 0 || x == NONE32) return false;
+  u32 lo = 0, hi = e.lsize;
+  while (lo < hi) { u32 mid = (lo + hi) >> 1; if (e.list[mid] < x) lo = mid + 1; else hi = mid; }
+  if (lo >= e.lsize || e.list[lo] != x) return false;
+  return e.big ? true : ((e.mask >> lo) & 1);
+}
+template <class F> __device__ __forceinline__ void ec_each(const EcView& e, F f) {
+  if (e.n == 0) return;
+  if (e.big) { for (u32 i = 0; i < e.lsize; i++) if (!f(e.list[i])) return; }
+  else { u64 m = e.mask; while (m) { int i = __ffsll((long long)m) - 1; m &= m - 1; if (!f(e.list[i])) return; } }
+}
+// membership after filter_read_calls_with_orientation (src/align.rs:144-171): a feature called in both orientations
+// by one mate is dropped from that mate's list
+__device__ __forceinline__ bool in_side(const EcView& e, const DevLib& L, u32 row) {
+  if (row == NONE32 || !ec_has(e, row)) return false;
+  u32 other = L.row_of[2 * (u64)L.row_fid[row] + (1 - L.row_rev[row])];
+  return !ec_has(e, other);
+}
+
+struct GroupList {
+  u32 g[GL_MAX]; u32 n; u32 limit; bool dedup; bool sat;
+  __device__ void add(u32 x) {
+    if (sat) return;
+    u32 i = 0;
+    while (i < n && g[i] < x) i++;
+    if (dedup && i < n && g[i] == x) return;
+    if (n >= limit) { sat = true; return; }
+    for (u32 j = n; j > i; j--) g[j] = g[j - 1];
+    g[i] = x; n++;
+  }
+};
+
+__device__ __forceinline__ void cas128(ulonglong2* addr, u64 n0, u64 n1, u64& o0, u64& o1) {
+  asm volatile("{\n\t.reg .b128 c, n, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\tatom.global.cas.b128 o, [%6], c, n;\n\tmov.b128 {%0, %1}, o;\n\t}\n"
+               : "=l"(o0), "=l"(o1) : "l"(0ULL), "l"(0ULL), "l"(n0), "l"(n1), "l"(addr) : "memory");
+}
+// insert-or-find a 128-bit key; returns slot or ~0 when the table is full
+__device__ __forceinline__ u64 key_insert(const Tables& t, u64 k0, u64 k1) {
+  u64 h = (k0 ^ (k1 >> 17)) & t.key_mask;
+  for (u64 probes = 0; probes <= t.key_mask; probes++) {
+    // the 128-bit CAS is also the (atomic) read: a plain 16-byte load could be torn against a concurrent insert
+    u64 o0, o1; cas128(t.key + h, k0, k1, o0, o1);
+    if (o0 == 0 && o1 == 0) { atomicAdd(&t.ctr->n_keys, 1ULL); return h; }
+    if (o0 == k0 && o1 == k1) return h;
+    h = (h + 1) & t.key_mask;
+  }
+  return ~0ULL;
+}
+__device__ __forceinline__ u32 callset_intern(const Tables& t, const u32* g, u32 n) {
+  u64 tag = 0x9E3779B97F4A7C15ULL ^ n;
+  for (u32 i = 0; i < n; i++) tag = mix64(tag ^ g[i]) + 0x632BE59BD9B4E019ULL;
+  tag = mix64(tag) | 1ULL;
+  u32 h = (u32)(tag >> 24) & t.cs_mask;
+  for (u32 probes = 0; probes <= t.cs_mask; probes++) {
+    unsigned long long old = atomicCAS((unsigned long long*)(t.cs_tag + h), 0ULL, (unsigned long long)tag);
+    if (old == 0ULL) {
+      t.cs_len[h] = n;
+      for (u32 i = 0; i < n; i++) t.cs_items[(u64)h * t.gcap + i] = g[i];
+      atomicAdd(&t.ctr->n_callsets, 1ULL);
+      return h;
+    }
+    if (old == tag) return h;
+    h = (h + 1) & t.cs_mask;
+  }
+  return NONE32;
+}
+
+__global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L, DevCfg cfg, Tables t) {
+  u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (p >= b.n_pairs) return;
+  bool paired = b.sides == 2;
+  u32 ri1 = (u32)(p * b.sides);
+  ReadRes r1 = b.rres[ri1], r2;
+  if (paired) r2 = b.rres[ri1 + 1]; else { r2.hdr = R_SUCCESS; r2.ec_len = 0; r2.bsize = 0; r2.ref = 0; r2.mask = 0; r2.score = r2.mm = 0; }
+  EcView e1 = make_view(r1, ix, t), e2 = make_view(r2, ix, t);
+  PairRes out; out.callset = NONE32; out.triage = R_NONE; out.insertable = 0; out.fr1 = (u8)(r1.hdr & 0xFF); out.fr2 = (u8)(r2.hdr & 0xFF);
+  // ---- read_key = R1 string + R2 string (untrimmed, after revcomp), src/align.rs:576-579 — hashed to 128 bits over
+  // the concatenated 2-bit stream so that, like the reference's string concatenation, only the joined bases matter.
+  u32 n1 = b.len_full[ri1], n2 = paired ? b.len_full[ri1 + 1] : 0, tot = n1 + n2;
+  ReadView rd1{b.pk + ri1, b.n_reads}, rd2{b.pk + ri1 + 1, b.n_reads};
+  u64 h0 = 0x243F6A8885A308D3ULL, h1 = 0x13198A2E03707344ULL;
+  for (u32 s = 0; s < tot; s += 32) {
+    u64 w;
+    if (s + 32 <= n1) w = rd1.win(s);
+    else if (s >= n1) w = rd2.win(s - n1);
+    else { u32 c1 = n1 - s; w = rd1.win(s) & ((1ULL << (2 * c1)) - 1); if (n2) w |= rd2.win(0) << (2 * c1); }
+    h0 = mix64(h0 ^ w); h1 = mix64(h1 + w * 0x9FB21C651E98DF25ULL);
+  }
+  u32 scope = b.scope ? b.scope[p] : 0u;
+  h0 = mix64(h0 ^ tot ^ ((u64)scope << 32)); h1 = mix64(h1 + (u64)tot * 0xD6E8FEB86659FD93ULL + scope);
+  if ((h0 | h1) == 0) h0 = 1;
+  out.key_lo = h0; out.key_hi = h1;
+  // ---- require_valid_pair, src/align.rs:582-588 + filter_pair 732-760
+  if (paired && cfg.require_valid_pair) {
+    bool bad = e1.n == 0 || e2.n == 0 || e1.n != e2.n;
+    if (!bad) ec_each(e1, [&](u32 x) { if (!ec_has(e2, x)) { bad = true; return false; } return true; });
+    if (bad) { out.fr1 = out.fr2 = R_NOT_MATCHING_PAIR; b.pres[p] = out; return; }
+  }
+  if (e1.n == 0 && e2.n == 0) { b.pres[p] = out; return; }   // failed alignment: bookkeeping only (src/align.rs:686-725)
+  out.insertable = 1;
+  // ---- filter_and_coerce_sequence_call_orientations, src/align.rs:178-252, on integer ids
+  int chem = cfg.strand_filter;
+  auto in_ua = [&](u32 row) { return in_side(e1, L, row) && !in_side(e2, L, row); };
+  auto qual_a = [&](u32 row) -> bool {   // row comes from e1
+    if (!in_side(e1, L, row)) return false;
+    if (chem == 3) return true;
+    if (in_side(e2, L, row)) return false;
+    if (chem == 0) return true;
+    bool rev = L.row_rev[row];
+    return chem == 1 ? !rev : rev;
+  };
+  auto qual_b = [&](u32 row) -> bool {   // row comes from e2
+    if (!in_side(e2, L, row)) return false;
+    if (chem == 3) return true;
+    if (in_side(e1, L, row)) return false;
+    if (chem == 0) return true;
+    u32 f = L.row_fid[row]; bool rev = L.row_rev[row];
+    u32 rf = L.row_of[2 * (u64)f], rr_ = L.row_of[2 * (u64)f + 1];
+    if (chem == 1) { if (in_ua(rr_)) return false; return rev || in_ua(rf); }        // filter_five_prime 311-342
+    if (in_ua(rf)) return false; return !rev || in_ua(rr_);                           // filter_three_prime 344-375
+  };
+  auto feat_in_b = [&](u32 f) -> bool {
+    u32 rf = L.row_of[2 * (u64)f], rr_ = L.row_of[2 * (u64)f + 1];
+    return (ec_has(e2, rf) && qual_b(rf)) || (ec_has(e2, rr_) && qual_b(rr_));
+  };
+  u32 T = max(cfg.discard_multi_hits, cfg.max_hits);
+  GroupList gl; gl.n = 0; gl.limit = T + 1; gl.dedup = !cfg.no_dedup; gl.sat = false;
+  bool feat_missing = false;
+  auto add_feat = [&](u32 f) { u32 g = L.feat_group[f]; if (g == NONE32) { feat_missing = true; return; } gl.add(g); };
+  bool use_intersection = false;
+  if (cfg.intersect_level != 0) {   // get_intersecting_reads 763-785 (array_tool Intersect: unique(A) kept when in B)
+    ec_each(e1, [&](u32 row) { if (qual_a(row) && feat_in_b(L.row_fid[row])) { use_intersection = true; return false; } return true; });
+  }
+  if (use_intersection) {
+    ec_each(e1, [&](u32 row) { if (qual_a(row) && feat_in_b(L.row_fid[row])) add_feat(L.row_fid[row]); return !gl.sat; });
+  } else if (cfg.intersect_level != 2) {   // get_all_calls 788-796 (concat; duplicates collapse in the roll-up unless nt_sequence)
+    ec_each(e1, [&](u32 row) { if (qual_a(row)) add_feat(L.row_fid[row]); return !gl.sat; });
+    ec_each(e2, [&](u32 row) { if (qual_b(row)) add_feat(L.row_fid[row]); return !gl.sat; });
+  }
+  if (feat_missing) atomicOr(&t.ctr->err, (unsigned)E_FEATURE);
+  // roll-up + discard_multi_hits + max hits, src/align.rs:229-242, 842-848
+  u32 cnt = gl.sat ? T + 1 : gl.n;
+  if (cfg.discard_multi_hits > 0 && cnt > cfg.discard_multi_hits) cnt = 0;
+  u32 triage = R_NONE;
+  if (cnt > cfg.max_hits) triage = R_MAX_HITS;
+  else if (cnt == 0) triage = R_TRIAGE_EMPTY;
+  u32 cs = CS_NONE;
+  if (triage == R_NONE) {
+    u32 slot = callset_intern(t, gl.g, gl.n);
+    if (slot == NONE32 || slot >= CS_NONE) atomicOr(&t.ctr->err, (unsigned)E_CS_FULL); else { cs = slot; out.callset = slot; }
+  }
+  out.triage = (u8)triage;
+  // ---- score_map.insert(read_key, ...): later duplicates overwrite (src/align.rs:685) => keep the highest order
+  u64 slot = key_insert(t, h0, h1);
+  if (slot == ~0ULL) atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL);
+  else atomicMax(t.kval + slot, (unsigned long long)(((b.order_base + p) << 24) | cs));
+  b.pres[p] = out;
+}
+
+// ------------------------------------------------------------------------------------------------ K4 fold
+// One vote per unique read_key (src/align.rs:440-449): results[callset] += 1 (245-251), keyed here by (cell, callset).
+__global__ void __launch_bounds__(256) k_fold(Tables t, const u32* cell_of_pair, u64 order_base) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx > t.key_mask) return;
+  ulonglong2 k = t.key[idx];
+  if (k.x == 0 && k.y == 0) return;
+  u64 v = t.kval[idx]; u32 cs = (u32)(v & 0xFFFFFFu);
+  if (cs == CS_NONE) return;
+  u32 cell = cell_of_pair ? cell_of_pair[(v >> 24) - order_base] : 0u;
+  unsigned long long ak = (((unsigned long long)cell << 24) | cs) + 1ULL;
+  u64 h = mix64(ak) & t.agg_mask;
+  for (u64 probes = 0; probes <= t.agg_mask; probes++) {
+    unsigned long long old = atomicCAS(t.agg_key + h, 0ULL, ak);
+    if (old == 0ULL) atomicAdd(&t.ctr->n_agg, 1ULL);
+    if (old == 0ULL || old == ak) { atomicAdd(t.agg_cnt + h, 1ULL); return; }
+    h = (h + 1) & t.agg_mask;
+  }
+  atomicOr(&t.ctr->err, (unsigned)E_AGG_FULL);
+}
+
+// ------------------------------------------------------------------------------------------------ exports
+struct ReadOut { u8 reason, pass; u16 score, mm, trimmed_len; u32 ec_len, ec_hash; };  // == nb_read_result
+__global__ void __launch_bounds__(256) k_export_reads(BatchDev b, DevIndex ix, Tables t, ReadOut* out) {
+  u32 ri = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ri >= b.n_reads) return;
+  ReadRes r = b.rres[ri];
+  ReadOut o; o.reason = (u8)(r.hdr & 0xFF); o.pass = (u8)((r.hdr >> 8) & 1); o.score = r.score; o.mm = r.mm; o.trimmed_len = (u16)b.len_trim[ri]; o.ec_len = r.ec_len;
+  u32 h = 2166136261u;
+  if (r.ec_len) {
+    EcView e; e.big = (r.hdr >> 9) & 1; e.n = r.ec_len; e.lsize = r.bsize; e.mask = r.mask; e.list = e.big ? (t.arena + r.ref) : (ix.col_ids + r.ref);
+    ec_each(e, [&](u32 x) { h = (h ^ x) * 16777619u; return true; });
+  }
+  o.ec_hash = h;
+  out[ri] = o;
+}
+
+__global__ void __launch_bounds__(256) k_rehash_keys(Tables o, Tables n) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx > o.key_mask) return;
+  ulonglong2 k = o.key[idx];
+  if (k.x == 0 && k.y == 0) return;
+  u64 slot = key_insert(n, k.x, k.y);
+  if (slot == ~0ULL) { atomicOr(&n.ctr->err, (unsigned)E_KEY_FULL); return; }
+  n.kval[slot] = o.kval[idx];
+}
+
+struct KeyRec { u64 k0, k1, order, tag; };
+__global__ void __launch_bounds__(256) k_keys_export(Tables t, KeyRec* rec, unsigned long long* n_out, u64 cap, u64 order_base) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx > t.key_mask) return;
+  ulonglong2 k = t.key[idx];
+  if (k.x == 0 && k.y == 0) return;
+  u64 v = t.kval[idx]; u32 cs = (u32)(v & 0xFFFFFFu);
+  unsigned long long at = atomicAdd(n_out, 1ULL);
+  if (at >= cap) return;
+  KeyRec r; r.k0 = k.x; r.k1 = k.y; r.order = (v >> 24) + order_base; r.tag = cs == CS_NONE ? 0ULL : t.cs_tag[cs];
+  rec[at] = r;
+}
+// import records from other ranks: the tag must already be present in this rank's dictionary (the host merges
+// dictionaries first); records whose tag is 0 carry "no callset" and only shadow older duplicates.
+__global__ void __launch_bounds__(256) k_keys_import(Tables t, const KeyRec* rec, u64 n) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  KeyRec r = rec[idx];
+  u32 cs = CS_NONE;
+  if (r.tag) {
+    u32 h = (u32)(r.tag >> 24) & t.cs_mask; bool ok = false;
+    for (u32 probes = 0; probes <= t.cs_mask; probes++) { u64 tg = t.cs_tag[h]; if (tg == r.tag) { ok = true; break; } if (tg == 0) break; h = (h + 1) & t.cs_mask; }
+    if (!ok) { atomicOr(&t.ctr->err, (unsigned)E_CS_FULL); return; }
+    cs = h;
+  }
+  u64 slot = key_insert(t, r.k0, r.k1);
+  if (slot == ~0ULL) { atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL); return; }
+  atomicMax(t.kval + slot, (unsigned long long)((r.order << 24) | cs));
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static inline unsigned blocks_for(u64 n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+void launch_pack(const BatchDev& b, cudaStream_t s) { u64 n = (u64)b.n_reads * b.W; if (n) k_pack<<<blocks_for(n, 256), 256, 0, s>>>(b); }
+void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_reads) k_trim<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, t); }
+void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s) {
+  if (!b.n_reads) return;
+  if (count_work) k_map<1><<<blocks_for(b.n_reads, 128), 128, 0, s>>>(b, ix, cfg, t);
+  else k_map<0><<<blocks_for(b.n_reads, 128), 128, 0, s>>>(b, ix, cfg, t);
+}
+void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s) {
+  if (b.n_pairs) k_pair<<<blocks_for(b.n_pairs, 128), 128, 0, s>>>(b, ix, lib, cfg, t);
+}
+void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s) { k_fold<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, cell_of_pair, order_base); }
+void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t, void* out, cudaStream_t s) {
+  if (b.n_reads) k_export_reads<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, ix, t, (ReadOut*)out);
+}
+void launch_rehash_keys(const Tables& o, const Tables& n, cudaStream_t s) { k_rehash_keys<<<blocks_for(o.key_mask + 1, 256), 256, 0, s>>>(o, n); }
+void launch_keys_export(const Tables& t, void* records, unsigned long long* n_out, u64 cap, u64 order_base, cudaStream_t s) {
+  k_keys_export<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, (KeyRec*)records, n_out, cap, order_base);
+}
+void launch_keys_import(const Tables& t, const void* records, u64 n, cudaStream_t s) { if (n) k_keys_import<<<blocks_for(n, 256), 256, 0, s>>>(t, (const KeyRec*)records, n); }
+
+}  // namespace nbk

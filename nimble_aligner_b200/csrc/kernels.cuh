@@ -1,0 +1,93 @@
+// kernels.cuh — device-side data layout and the hand-written sm_100a kernels of the alignment hot path.
+//
+//   K0 k_pack        ASCII -> 2-bit words (word-major), optional reverse-complement      (DnaString::from_acgt_bytes,
+//                    /root/reference/src/parse/fastq.rs:36, src/process/bam.rs:407-415)
+//   K1 k_trim        MAXINFO trim length from raw Phred bytes, exact i64                 (src/align.rs:866-925)
+//   K2 k_map         length/entropy gates + seed-and-walk pseudo-alignment + colour intersection + thresholds
+//                    (src/align.rs:945-989, Pseudoaligner::map_read_with_mismatch [SURVEY.md App. B], src/filter/align.rs:4-45)
+//   K3 k_pair        pair validity, orientation / strand / intersect logic, group roll-up, max-hits, callset interning,
+//                    128-bit read_key and de-duplication insert                          (src/align.rs:144-375, 576-685, 732-864)
+//   K4 k_fold        one vote per unique read_key -> (cell, callset) histogram            (src/align.rs:440-449, 245-251)
+// Tensor cores are not used: nothing here is a dense contraction (HBM/L2-latency bound integer work).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+namespace nbk {
+
+constexpr int K = 30;
+constexpr u64 KMASK = (1ULL << 60) - 1;
+constexpr u32 NONE32 = 0xFFFFFFFFu;
+constexpr u32 CS_NONE = 0xFFFFFFu;        // 24-bit "no callset" in the key-table value
+constexpr int GL_MAX = 64;                 // per-thread group list capacity (max(discard_multi_hits, max_hits_to_report)+1 <= 64)
+constexpr int ENT_NMAX = 1024;             // longest read the entropy table covers
+
+struct DevIndex {
+  const u64* tkey; const u64* tval; u64 tmask;
+  const u64* unitig;
+  const uint4* node;      // {start_lo, len, colour, lext | rext<<4 | start_hi<<8}
+  const uint4* redge; const uint4* ledge;
+  const u32* col_off; const u32* col_ids;
+};
+struct DevLib { const u32* row_fid; const u8* row_rev; const u32* row_of; const u32* feat_group; u32 n_rows; };
+struct DevCfg {
+  double score_percent; u32 score_threshold; u32 num_mismatches;
+  int discard_nonzero_mismatch, discard_multiple_matches, require_valid_pair, intersect_level, strand_filter, no_dedup;
+  u32 discard_multi_hits, max_hits, gcap, min_read_len;
+};
+// device-side error bits (Counters::err)
+enum { E_ARENA = 1, E_CS_FULL = 2, E_KEY_FULL = 4, E_FEATURE = 8, E_AGG_FULL = 16, E_GCAP = 32 };
+struct Counters {
+  unsigned long long arena_top; unsigned long long n_keys; unsigned long long n_callsets; unsigned long long n_agg;
+  unsigned long long probes, nodes, bases, colour_elems;   // work counters (roofline numerator cross-check)
+  unsigned int err; unsigned int pad;
+};
+
+// internal per-read record (32 B)
+struct ReadRes {
+  u32 hdr;        // reason | pass<<8 | big<<9 | skip<<10
+  u16 score, mm;
+  u32 ec_len;     // elements in the raw equivalence class
+  u32 bsize;      // mask mode: size of the base colour list
+  u64 ref;        // mask mode: offset of the base colour in col_ids; big mode: offset in the arena
+  u64 mask;       // mask mode: surviving elements of the base colour
+};
+struct PairRes { u32 callset; u8 triage, fr1, fr2, insertable; u64 key_lo, key_hi; };  // == nb_pair_result
+
+struct BatchDev {
+  u64 n_pairs; u32 sides; u32 n_reads; u32 W;             // W words per read incl. one zero pad word
+  const u8* a[2]; const u64* off[2]; const u8* q[2]; const u8* flags[2]; const u32* scope; const u32* cell;
+  u64* pk; u32* len_full; u32* len_trim;                  // pk[w * n_reads + ri], ri = p*sides + side
+  ReadRes* rres; PairRes* pres;
+  u64 order_base;
+};
+
+struct Tables {
+  // callset dictionary
+  u64* cs_tag; u32* cs_len; u32* cs_items; u32 cs_mask; u32 gcap;
+  // de-duplication key table (128-bit keys, CAS128) and value = order<<24 | callset slot
+  ulonglong2* key; unsigned long long* kval; u64 key_mask;
+  // (cell, callset) histogram
+  unsigned long long* agg_key; unsigned long long* agg_cnt; u64 agg_mask;
+  u32* arena; u64 arena_cap;
+  Counters* ctr;
+  const double* ent; const i64* ls; const i64* qp;
+};
+
+void launch_pack(const BatchDev& b, cudaStream_t s);
+void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s);
+void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s);
+void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s);
+void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s);
+void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t, void* out, cudaStream_t s);
+void launch_rehash_keys(const Tables& old_t, const Tables& new_t, cudaStream_t s);
+void launch_keys_export(const Tables& t, void* records, unsigned long long* n_out, u64 cap, u64 order_base, cudaStream_t s);
+void launch_keys_import(const Tables& t, const void* records, u64 n, cudaStream_t s);
+
+}  // namespace nbk

@@ -1,0 +1,364 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every test drives the CUDA path through the C ABI
+(libnimble_b200.so) and compares it with the CPU oracle and/or the reference's literal golden expectations:
+bit-exact per-read (reason, score, mismatches, trimmed length, equivalence class), per-pair (filter reasons, triage,
+callset) and per-scope callset counts."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import nimble_aligner_b200 as nb
+import oracle as orc
+import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+EXP = json.load(open(os.path.join(G, "expected.json")))
+CHEMS = ["unstranded", "fiveprime", "threeprime", "none"]
+
+
+def gpu_cfg(lib, ocfg):
+    return lib.config.copy(score_percent=ocfg["score_percent"], score_threshold=ocfg["score_threshold"], num_mismatches=ocfg["num_mismatches"],
+                           discard_multiple_matches=int(ocfg["discard_multiple_matches"]), require_valid_pair=int(ocfg["require_valid_pair"]),
+                           discard_multi_hits=ocfg["discard_multi_hits"], max_hits_to_report=ocfg["max_hits_to_report"],
+                           intersect_level=ocfg["intersect_level"], strand_filter=ocfg["strand_filter"],
+                           trim_target_length=ocfg["trim_target_length"], trim_strictness=ocfg["trim_strictness"])
+
+
+def compare(ctx, o, ocfg, r1, o1, r2=None, o2=None, q1=None, q2=None, flags1=None, flags2=None, scope=None, check_ecs=True, **ctx_kw):
+    """Runs one batch on the GPU and on the oracle and asserts bit-exact agreement. Returns the GPU counts."""
+    n = len(o1) - 1
+    skip1 = (flags1 & 1).astype(np.uint8) if flags1 is not None else None
+    skip2 = (flags2 & 1).astype(np.uint8) if flags2 is not None else None
+    scope_off = None
+    if scope is not None:
+        b = np.flatnonzero(np.diff(scope)) + 1
+        scope_off = np.concatenate([[0], b, [n]]).astype(np.uint64)
+    ref = o.run(r1, o1, r2, o2, q1=q1, q2=q2, skip1=skip1, skip2=skip2, scope_off=scope_off, threads=4)
+    ctx.reset()
+    ctx.set_config(gpu_cfg(ctx.library, ocfg))
+    reads, pairs = ctx.align_batch(r1, o1, r2, o2, q1=q1, q2=q2, flags1=flags1, flags2=flags2, scope_id=scope, want_reads=True, want_pairs=True)
+    res = ctx.counts()
+    # ---- per read
+    assert np.array_equal(reads["reason"], ref["read_reason"]), np.flatnonzero(reads["reason"] != ref["read_reason"])[:10]
+    assert np.array_equal(reads["pass"], ref["read_pass"])
+    assert np.array_equal(reads["score"], ref["read_score"]), np.flatnonzero(reads["score"] != ref["read_score"])[:10]
+    assert np.array_equal(reads["mismatches"], ref["read_mm"]), np.flatnonzero(reads["mismatches"] != ref["read_mm"])[:10]
+    assert np.array_equal(reads["ec_len"], ref["read_ec_len"]), np.flatnonzero(reads["ec_len"] != ref["read_ec_len"])[:10]
+    notskip = reads["reason"] != nb.R["SkippedAlignDueToUnpairedDummy"]
+    assert np.array_equal(reads["trimmed_len"][notskip], ref["read_trimmed_len"][notskip])
+    if check_ecs and n <= ctx_kw.get("max_batch_pairs", 1 << 20):
+        off, ids = ctx.last_batch_ecs(len(reads))
+        assert np.array_equal(ids, ref["read_ec"])
+    # ---- per pair
+    assert np.array_equal(pairs["fr1"], ref["pair_fr1"]), np.flatnonzero(pairs["fr1"] != ref["pair_fr1"])[:10]
+    assert np.array_equal(pairs["fr2"], ref["pair_fr2"])
+    assert np.array_equal(pairs["triage"], ref["pair_triage"]), np.flatnonzero(pairs["triage"] != ref["pair_triage"])[:10]
+    has = pairs["callset"] != 0xFFFFFFFF
+    assert np.array_equal(has, ref["pair_counted"].astype(bool))
+    s2c = res["slot_to_callset"]
+    scope_of = np.zeros(n, dtype=np.int64) if scope is None else (np.searchsorted(scope_off, np.arange(n), side="right") - 1)
+    for p in np.flatnonzero(has)[:: max(1, int(has.sum()) // 5000)]:
+        assert res["callsets"][s2c[pairs["callset"][p]]] == ref["scopes"][scope_of[p]][ref["pair_callset"][p]][0], p
+    # ---- per scope counts (rows sorted by Vec<String> Ord, like utils::sort_score_vector)
+    got = {}
+    for sc, cs, cnt in res["rows"]:
+        got.setdefault(sc, []).append((cs, cnt))
+    scope_ids = [0] if scope is None else [int(scope[int(a)]) for a in scope_off[:-1]]
+    for si, sid in enumerate(scope_ids):
+        assert got.get(sid, []) == ref["scopes"][si], (sid, got.get(sid), ref["scopes"][si])
+    assert sum(len(v) for v in got.values()) == sum(len(s) for s in ref["scopes"])
+    return res, ref
+
+
+def load_fixture(lib_name, chem="none", group=False):
+    path = os.path.join(G, "ref", "libraries", lib_name)
+    ocfg, oref = orc.get_reference_library(path, chem)
+    _, lib = nb.get_reference_library(path, chem)
+    if group:
+        oref.group_on = 4
+        oref.headers.append("test_group_on")
+        oref.columns.append(list(EXP["group_column"]))
+        lib.push_column("test_group_on", EXP["group_column"], set_group_on=True)
+    return ocfg, oref, lib
+
+
+# ------------------------------------------------------------------ C1: the reference's golden vectors
+@pytest.mark.parametrize("case", EXP["get_calls"], ids=[c["src"] for c in EXP["get_calls"]])
+def test_reference_goldens(case):
+    ocfg, oref, lib = load_fixture(case["lib"], "none", case["group"])
+    ocfg["num_mismatches"] = case["mm"]
+    reads, _ = orc.read_fastq(os.path.join(G, "ref", "reads", case["reads"]))
+    ix = nb.build_index(lib, 2)
+    rows, _, _ = nb.get_calls(reads, None, None, ix, lib, gpu_cfg(lib, ocfg))
+    assert [[cs, n] for cs, n in rows] == case["expect"]
+    r1, o1 = orc.pack_reads(reads)
+    compare(nb.Context(ix, lib), orc.Oracle(ocfg, oref), ocfg, r1, o1)
+
+
+def test_pseudoalign_known_answers():   # src/align.rs:1061-1107 (min_read_length 12 there)
+    cfg = nb.Config(score_percent=0.1, score_threshold=50, num_mismatches=3, max_hits_to_report=5, intersect_level=1, strand_filter=1,
+                    trim_target_length=15, trim_strictness=0.5)
+    lib = nb.Library.from_columns(["sequence_name", "sequence"], [["Gene1", "Gene2"], ["ACGT" * 8, "TGCA" * 8]], 0, 0, 1, cfg)
+    ix = nb.build_index(lib, 1)
+    ctx = nb.Context(ix, lib, min_read_length=12)
+    seqs = ["ACG", "A" * 30, "CCTGAGATTTCGAGCTCGTAACGTGACCTACGGACAC", "TGCA" * 8]
+    r1, o1 = nb.pack_reads(seqs)
+
+    def run(**kw):
+        ctx.reset()
+        ctx.set_config(cfg.copy(**kw))
+        reads, _ = ctx.align_batch(r1, o1, want_reads=True)
+        return reads
+
+    r = run(score_threshold=32)
+    assert [int(x) for x in r["reason"][:3]] == [nb.R["ShortRead"], nb.R["HighEntropy"], nb.R["NoMatch"]]
+    assert r["pass"][3] == 1 and r["score"][3] == 32 and r["ec_len"][3] == 1   # Some(([1], 1.0, 32))
+    off, ids = ctx.last_batch_ecs(4)
+    assert ids.tolist() == [1]
+    r = run(score_threshold=1000)
+    assert r["reason"][3] == nb.R["ScoreBelowThreshold"] and r["score"][3] == 32 and r["pass"][3] == 0
+
+
+# ------------------------------------------------------------------ C2-shaped synthetic parity (1k-transcript family library)
+@pytest.fixture(scope="module")
+def c2():
+    L = synth.SynthLibrary(seed=1234, n_fam=200, n_all=5, group_on="")
+    obj = L.to_json_obj()
+    return L, obj
+
+
+def make(obj, chem, group_on=""):
+    import copy
+    obj = [dict(obj[0]), obj[1]]
+    obj[0]["group_on"] = group_on
+    ocfg, oref = orc.parse_reference_library(obj, chem)
+    lib = nb.Library.from_text(json.dumps(obj), chem)
+    return ocfg, oref, lib
+
+
+@pytest.fixture(scope="module")
+def c2_built(c2):
+    L, obj = c2
+    built = {}
+    for group_on in ("", "family"):
+        ocfg, oref, lib = make(obj, "unstranded", group_on)
+        ix = nb.build_index(lib, 8)
+        built[group_on] = (ocfg, oref, lib, ix, orc.Oracle(ocfg, oref), nb.Context(ix, lib))
+    return L, built
+
+
+def test_c2_index_matches_oracle(c2_built):
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, ctx = built[""]
+    so, sp = o.index_stats(), ix.stats()
+    for k in so:
+        assert so[k] == sp[k], k
+    assert o.index_dump() == ix.dump()
+
+
+@pytest.mark.parametrize("mm", [0, 1, 2])
+@pytest.mark.parametrize("paired", [True, False])
+def test_c2_parity_mismatch_sweep(c2_built, mm, paired):   # also config C5's sweep
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, ctx = built[""]
+    cfg = dict(ocfg, num_mismatches=mm)
+    o.set_config(**cfg)
+    r1, o1, r2, o2 = synth.pairs(L, 0, 60000, paired=paired)
+    res, ref = compare(ctx, o, cfg, r1, o1, r2, o2)
+    assert res["n_unique_keys"] < 60000 and len(res["rows"]) > 100   # duplicates exist and many callsets are hit
+
+
+@pytest.mark.parametrize("chem", CHEMS)
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_c2_parity_chemistry_and_intersect(c2_built, chem, level):
+    L, built = c2_built
+    for group_on in ("", "family"):
+        ocfg, oref, lib, ix, o, ctx = built[group_on]
+        cfg = dict(ocfg, strand_filter=chem, intersect_level=level, num_mismatches=1)
+        o.set_config(**cfg)
+        r1, o1, r2, o2 = synth.pairs(L, 100000, 20000, paired=True)
+        compare(ctx, o, cfg, r1, o1, r2, o2, check_ecs=False)
+
+
+@pytest.mark.parametrize("kw", [dict(require_valid_pair=True), dict(discard_multiple_matches=True), dict(discard_multi_hits=1),
+                                dict(max_hits_to_report=1), dict(discard_multi_hits=2, max_hits_to_report=1), dict(score_threshold=140, score_percent=0.95),
+                                dict(require_valid_pair=True, strand_filter="none", intersect_level=2)])
+def test_c2_parity_filters(c2_built, kw):
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, ctx = built["family"]
+    cfg = dict(ocfg, num_mismatches=2)
+    cfg.update(kw)
+    o.set_config(**cfg)
+    r1, o1, r2, o2 = synth.pairs(L, 200000, 20000, paired=True)
+    compare(ctx, o, cfg, r1, o1, r2, o2, check_ecs=False)
+
+
+def test_multi_batch_equals_single_batch_and_is_idempotent(c2_built):
+    """Whole-run de-duplication across batches: chunked == single; feeding the same pairs twice changes nothing."""
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, _ = built[""]
+    o.set_config(**ocfg)
+    r1, o1, r2, o2 = synth.pairs(L, 0, 50000, paired=True)
+    ref = o.run(r1, o1, r2, o2, threads=4, want_records=False)["scopes"][0]
+    ctx = nb.Context(ix, lib, max_batch_pairs=7001, key_slots=1024)   # forces 8 chunks and several key-table growths
+    ctx.set_config(gpu_cfg(lib, ocfg))
+    ctx.align_batch(r1, o1, r2, o2)
+    ctx.align_batch(r1, o1, r2, o2)   # every pair again: duplicates of existing keys
+    res = ctx.counts()
+    assert [(cs, n) for _, cs, n in res["rows"]] == ref
+    assert res["n_pairs_seen"] == 100000
+
+
+# ------------------------------------------------------------------ C3-shaped: scoped (UMI, CB) groups, quality trim, dummy mates
+def test_c3_scoped_bam_like_parity(c2_built):
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, ctx = built[""]
+    u = synth.umi_reads(L, 0, 6000)
+    n = u["n_reads"]
+    # 10x single-end records become (dummy, real) pairs (sorted_bam_reader.rs:109-145): sequence slot = SKIP_ALIGN dummy
+    rng = np.random.default_rng(3)
+    flags2 = (rng.random(n) < 0.3).astype(np.uint8) * nb.FLAG_REVCOMP     # REVERSE records are reverse-complemented
+    flags1 = (flags2 | nb.FLAG_SKIP_ALIGN).astype(np.uint8)               # the dummy is a clone of the record (same REVERSE flag)
+    for chem in ("unstranded", "fiveprime", "threeprime"):
+        cfg = dict(ocfg, strand_filter=chem, trim_target_length=40, trim_strictness=0.9, num_mismatches=1)
+        o.set_config(**cfg)
+        # the oracle gets the reads already reverse-complemented / quals reversed, as process::bam::get_calls hands them over
+        bases = u["bases"][: n * 91].reshape(n, 91).copy()
+        qual = u["qual"][: n * 91].reshape(n, 91).copy()
+        rc = flags2.astype(bool)
+        comp = np.zeros(256, dtype=np.uint8)
+        for a, b in zip(b"ACGT", b"TGCA"):
+            comp[a] = b
+        ob, oq = bases.copy(), qual.copy()
+        ob[rc] = comp[bases[rc][:, ::-1]]
+        oq[rc] = qual[rc][:, ::-1]
+        skip1 = np.ones(n, dtype=np.uint8)
+        scope_off = np.concatenate([[0], np.cumsum(u["sizes"])]).astype(np.uint64)
+        ref = o.run(ob.reshape(-1), u["off"], ob.reshape(-1), u["off"], q1=oq.reshape(-1), q2=oq.reshape(-1), skip1=skip1, skip2=None, scope_off=scope_off, threads=4)
+        ctx.reset()
+        ctx.set_config(gpu_cfg(lib, cfg))
+        reads, pairs = ctx.align_batch(u["bases"], u["off"], u["bases"], u["off"], q1=u["qual"], q2=u["qual"], flags1=flags1, flags2=flags2,
+                                       scope_id=u["scope"], want_reads=True, want_pairs=True)
+        res = ctx.counts()
+        real = np.arange(n) * 2 + 1
+        assert np.array_equal(reads["reason"][real], ref["read_reason"][real])
+        assert np.all(reads["reason"][real - 1] == nb.R["SkippedAlignDueToUnpairedDummy"])
+        assert np.array_equal(reads["trimmed_len"][real], ref["read_trimmed_len"][real])
+        assert np.array_equal(reads["score"][real], ref["read_score"][real]) and np.array_equal(reads["mismatches"][real], ref["read_mm"][real])
+        assert len(np.unique(reads["trimmed_len"][real])) > 5          # the Q2 tails really trim
+        assert np.array_equal(pairs["triage"], ref["pair_triage"]) and np.array_equal(pairs["fr2"], ref["pair_fr2"])
+        got = {}
+        for sc, cs, cnt in res["rows"]:
+            got.setdefault(sc, []).append((cs, cnt))
+        for s in range(len(u["sizes"])):
+            assert got.get(s, []) == ref["scopes"][s], s
+        # per-cell table (cell_id given): sum over the cell's scopes
+        ctx.reset()
+        ctx.align_batch(u["bases"], u["off"], u["bases"], u["off"], q1=u["qual"], q2=u["qual"], flags1=flags1, flags2=flags2, scope_id=u["scope"], cell_id=u["cell"])
+        cells = {}
+        for sc, cs, cnt in ctx.counts()["rows"]:
+            cells[(sc, tuple(cs))] = cnt
+        want = {}
+        first = scope_off[:-1].astype(np.int64)
+        for s in range(len(u["sizes"])):
+            for cs, cnt in ref["scopes"][s]:
+                k = (int(u["cell"][first[s]]), tuple(cs))
+                want[k] = want.get(k, 0) + cnt
+        assert cells == want
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases_ragged_empty_nonacgt(c2_built):
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, ctx = built[""]
+    o.set_config(**ocfg)
+    seqs = L.sequences()
+    t = seqs[17]
+    reads = ["", "A", t[:39], t[:40], t[100:250], t[100:250].lower(), t[100:180] + "N" + t[181:250], "N" * 150, "ACGT" * 40, t[:1024],
+             t[-150:], t[-100:] + "ACGTTGCA" * 6, "G" * 29 + t[200:321], t[5:155][:75] + "T" + t[5:155][76:]]
+    mates = [r[::-1] for r in reads]
+    r1, o1 = orc.pack_reads(reads)
+    r2, o2 = orc.pack_reads(mates)
+    for mm in (0, 2):
+        cfg = dict(ocfg, num_mismatches=mm)
+        o.set_config(**cfg)
+        compare(ctx, o, cfg, r1, o1)
+        compare(ctx, o, cfg, r1, o1, r2, o2)
+    ctx.reset()
+    e = np.zeros(1, dtype=np.uint64)
+    ctx.align_batch(np.zeros(1, dtype=np.uint8), e)   # empty batch
+    assert ctx.counts()["rows"] == []
+    with pytest.raises(nb.NbError):   # longer than the device path supports -> loud error, not a silent wrong answer
+        big, ob = orc.pack_reads(["ACGT" * 300])
+        ctx.align_batch(big, ob)
+
+
+def test_left_extension_and_reseed_paths_are_exercised(c2_built):
+    """Reads with an error at positions 27..29 make every seed before position 30 miss, so the first hit is at
+    >= floor(0.2*len) and the left extension runs; the oracle's work counters must match the device's."""
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, _ = built[""]
+    seqs = L.sequences()
+    rng = np.random.default_rng(11)
+    reads = []
+    for i in range(4000):
+        t = seqs[int(rng.integers(len(seqs)))]
+        s = int(rng.integers(0, len(t) - 150))
+        r = list(t[s:s + 150])
+        for pos in rng.choice([27, 28, 29, 57, 58, 59, 100], size=int(rng.integers(1, 4)), replace=False):
+            r[pos] = "ACGT"[("ACGT".index(r[pos]) + 1 + int(rng.integers(3))) % 4]
+        reads.append("".join(r))
+    r1, o1 = orc.pack_reads(reads)
+    ctx = nb.Context(ix, lib, count_work=1)
+    for mm in (0, 1, 3):
+        cfg = dict(ocfg, num_mismatches=mm)
+        o.set_config(**cfg)
+        res, ref = compare(ctx, o, cfg, r1, o1)
+        w = ctx.work_counters()   # reset with the tables by compare()'s ctx.reset()
+        for k in ("probes", "nodes", "bases"):
+            assert w[k] == ref["work"][k], (mm, k, w[k], ref["work"][k])
+    assert w["probes"] > 4000 and w["nodes"] > 4000
+
+
+def test_work_counters_match_oracle(c2_built):
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, _ = built[""]
+    o.set_config(**ocfg)
+    r1, o1, r2, o2 = synth.pairs(L, 0, 30000, paired=True)
+    ref = o.run(r1, o1, r2, o2, threads=4, want_records=False)
+    ctx = nb.Context(ix, lib, count_work=1)
+    ctx.set_config(gpu_cfg(lib, ocfg))
+    ctx.align_batch(r1, o1, r2, o2)
+    w = ctx.work_counters()
+    for k in ("probes", "nodes", "bases"):
+        assert w[k] == ref["work"][k], (k, w[k], ref["work"][k])
+
+
+def test_fastq_driver_and_tsv_format(tmp_path, c2):
+    """process::fastq::process end to end: FASTQ(.gz) in, TSV out (append mode, header once) — src/utils.rs:27-51."""
+    import gzip
+    L, obj = c2
+    lib_json = tmp_path / "lib.json"
+    lib_json.write_text(json.dumps(obj))
+    r1, o1, r2, o2 = synth.pairs(L, 0, 3000, paired=True)
+
+    def fq(path, data, off, gz):
+        op = gzip.open if gz else open
+        with op(path, "wt") as f:
+            for i in range(len(off) - 1):
+                s = bytes(data[int(off[i]):int(off[i + 1])]).decode()
+                f.write("@r%d\n%s\n+\n%s\n" % (i, s, "I" * len(s)))
+    fq(tmp_path / "a_R1.fastq.gz", r1, o1, True)
+    fq(tmp_path / "a_R2.fastq", r2, o2, False)
+    out = tmp_path / "out.tsv"
+    nb.process_fastq([str(tmp_path / "a_R1.fastq.gz"), str(tmp_path / "a_R2.fastq")], [str(lib_json)], [str(out)], "unstranded", 4)
+    ocfg, oref = orc.parse_reference_library(obj, "unstranded")
+    ref = orc.Oracle(ocfg, oref).run(r1, o1, r2, o2, want_records=False)["scopes"][0]
+    want = "feature\tscore\n" + "".join("\t".join(cs) + "\t%d\n" % n for cs, n in ref)
+    assert out.read_text() == want
+    nb.process_fastq([str(tmp_path / "a_R1.fastq.gz"), str(tmp_path / "a_R2.fastq")], [str(lib_json)], [str(out)], "unstranded", 4)
+    assert out.read_text() == want + want[len("feature\tscore\n"):]   # append, no second header

@@ -1,0 +1,131 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads and exports every declared symbol, the library
+loader and the index builder agree with the oracle (independent implementations), and compute entry points fail
+loudly without a GPU.  No device compute here."""
+import ctypes
+import os
+import random
+import re
+
+import pytest
+
+import nimble_aligner_b200 as nb
+import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden", "ref")
+LIBS = ["basic.json", "basic-rev.json", "mismatch.json", "strandedness.json", "reference-library-correct.json",
+        "reference-library-rna.json", "reference-library-mixed-case-rna.json", "reference-library-no-rna-bases.json"]
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nimble_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(nb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) > 30
+    so = ctypes.CDLL(nb.SO_PATH)
+    missing = [s for s in declared if not hasattr(so, s)]
+    assert not missing, missing
+    assert nb.lib().nb_version().decode().startswith("nimble_b200")
+    assert nb.lib().nb_reason_str(10).decode() == "Low Entropy"   # src/align.rs:68
+
+
+@pytest.mark.parametrize("name", LIBS)
+def test_library_loader_matches_oracle_loader(name):
+    path = os.path.join(G, "libraries", name)
+    cfg, ref = orc.get_reference_library(path, "fiveprime")
+    c, lib = nb.get_reference_library(path, "fiveprime")
+    assert lib.headers == ref.headers
+    for i in range(len(ref.headers)):
+        assert lib.column(i) == ref.columns[i]
+    assert (lib.group_on, lib.sequence_name_idx, lib.sequence_idx) == (ref.group_on, ref.sequence_name_idx, ref.sequence_idx)
+    for k in ("score_percent", "score_threshold", "num_mismatches", "discard_multi_hits", "max_hits_to_report", "intersect_level",
+              "trim_target_length", "trim_strictness", "score_filter", "reference_genome_size"):
+        assert getattr(c, k) == cfg[k], k
+    assert bool(c.discard_multiple_matches) == cfg["discard_multiple_matches"] and bool(c.require_valid_pair) == cfg["require_valid_pair"]
+    assert c.strand_filter == nb.CHEM["fiveprime"] and c.discard_nonzero_mismatch == 0
+    seqs, names = nb.get_reference_sequence_data(lib)   # src/utils.rs:121-190
+    assert names == ref.columns[ref.sequence_name_idx] and seqs == ref.columns[ref.sequence_idx]
+
+
+@pytest.mark.parametrize("name", ["reference-library-missing-fields.json", "reference-library-types-broken.json", "reference-library-broken-format.json"])
+def test_library_loader_rejects_what_the_reference_panics_on(name):   # src/reference_library.rs:256-300
+    with pytest.raises(nb.NbError):
+        nb.get_reference_library(os.path.join(G, "libraries", name))
+    with pytest.raises(nb.NbError):
+        nb.get_reference_library(os.path.join(G, "libraries", "does-not-exist.json"))
+
+
+def test_sanity_check_align_config():   # src/reference_library.rs:209-226
+    _, lib = nb.get_reference_library(os.path.join(G, "libraries", "basic.json"))
+    for bad in (dict(score_percent=1.5), dict(score_percent=-0.1), dict(trim_strictness=2.0), dict(score_filter=-1)):
+        with pytest.raises(nb.NbError):
+            lib.set_config(lib.config.copy(**bad))
+    lib.set_config(lib.config.copy(score_percent=1.0, trim_strictness=0.0))
+
+
+def _index_parity(names, seqs, threads=3):
+    cfg = dict(score_percent=0.1, score_threshold=50, num_mismatches=0, discard_multiple_matches=False, require_valid_pair=False,
+               discard_multi_hits=0, max_hits_to_report=5, intersect_level=0, strand_filter="none", trim_target_length=15, trim_strictness=0.5)
+    o = orc.Oracle(cfg, orc.Reference(0, ["sequence_name", "sequence"], [names, seqs], 0, 1))
+    ix = nb.Index.from_sequences(seqs, threads)
+    so, sp = o.index_stats(), ix.stats()
+    for k in so:
+        assert so[k] == sp[k], k
+    assert o.index_dump() == ix.dump()
+
+
+@pytest.mark.parametrize("name", ["basic.json", "basic-rev.json", "mismatch.json", "strandedness.json"])
+def test_index_matches_oracle_on_reference_fixtures(name):
+    _, ref = orc.get_reference_library(os.path.join(G, "libraries", name), "none")
+    _index_parity(ref.columns[ref.sequence_name_idx], ref.columns[ref.sequence_idx])
+
+
+def test_index_matches_oracle_on_synthetic_family_library():
+    import synth
+    L = synth.SynthLibrary(seed=7, n_fam=12, n_all=5)
+    cfg, ref = orc.parse_reference_library(L.to_json_obj(), "none")
+    _index_parity(ref.columns[ref.sequence_name_idx], ref.columns[ref.sequence_idx], threads=4)
+
+
+def test_index_edge_cases_cycles_repeats_short_and_non_acgt():
+    rnd = random.Random(5)
+    rs = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))
+    core = rs(60)
+    seqs = ["A" * 50,                    # homopolymer: a k-mer that is its own successor (pure 1-cycle)
+            "AC" * 40, "CA" * 40,        # 2-cycle entered at different phases
+            "ACG" * 30,                  # 3-cycle
+            rs(29), "", rs(30),          # shorter than k contributes nothing; exactly k = one k-mer
+            core + rs(40), rs(35) + core + rs(20), core,   # shared segments -> colour changes and forks
+            "ACGTNNNNACGTRYKM" * 5,      # non-ACGT -> A
+            (rs(45) * 3)[:120],          # tandem repeat longer than k: cycle with a tail
+            "acgtacgtacgtacgtacgtacgtacgtacgtacgtacgt"]  # lowercase
+    names = ["s%d" % i for i in range(len(seqs))]
+    _index_parity(names, seqs, threads=2)
+    _index_parity(names, seqs, threads=1)
+
+
+def test_group_names_follow_natural_lexical_order():
+    cfg = nb.Config(score_percent=0.1, max_hits_to_report=5)
+    names = ["b10", "B9", "a1", "A02-LC", "A02-2"]
+    lib = nb.Library.from_columns(["sequence_name", "sequence"], [names, ["ACGT" * 10] * 5], 0, 0, 1, cfg)
+    import functools
+    assert lib.group_names() == sorted(names, key=functools.cmp_to_key(orc.natural_lexical_cmp))
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    if nb.lib().nb_device_count() > 0:
+        pytest.skip("GPU present")
+    _, lib = nb.get_reference_library(os.path.join(G, "libraries", "basic.json"))
+    ix = nb.build_index(lib, 2)
+    with pytest.raises(nb.NbError) as e:
+        nb.Context(ix, lib)
+    assert e.value.code == -6 and "no CPU path" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "nimble_aligner_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "import oracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
