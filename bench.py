@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — aligned reads/sec of the nimble-aligner hot path on B200 (BASELINE.json metric).
+
+Workload (config.workload "C2"): synthetic 1k-transcript family library (200 families x 5 alleles, seed 1234) and
+10 M 2x150 bp read pairs per GPU, FASTQ-mode semantics: one whole-run aggregation scope, counts over
+unique read pairs.  A "step" is one complete pass of the hot path (pack -> seed-and-walk map -> pair/orientation ->
+de-duplicate -> callset histogram -> counts on the host) over that input.
+
+  value   reads/s with the ASCII reads already resident in HBM (device-timed, CUDA events on the launching stream)
+  e2e     reads/s through the C ABI with pinned HOST buffers: H2D copies and the D2H of the counts inside the timed region
+  roofline  k_map (dominant kernel): algorithmic bytes per launch / mean launch time (CUDA events inside the library)
+  cpu_baseline  the CPU oracle ("port" of the reference; the Rust reference cannot be built here) on a bounded sample
+
+`--impl reference` times the oracle (reference cost structure: string-keyed maps, linear unmap) with all host threads.
+N > 1 (torchrun): reads shard over ranks, index replicated; the whole-run de-duplication exchanges 32-byte key
+records by key range (all_to_all over NCCL) and the per-callset counts are all-reduced.  Weak scaling: 10 M pairs per GPU.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aligned reads/sec per box, bit-exact counts vs CPU ref"
+UNIT = "reads/s"
+SEED = 1234
+READ_LEN = 150
+
+
+def algorithmic_bytes_per_read(work, n_reads_total):
+    """DESIGN.md 'Roofline': bytes k_map must touch per read = packed read words + 16 B per hash probe + 32 B node
+    record and c_v/4 unitig bytes per visited unitig + 4 B per colour id touched + 32 B result record."""
+    packed = 8 * ((READ_LEN + 31) // 32)
+    tot = packed * n_reads_total + 16 * work["probes"] + 32 * work["nodes"] + work["bases"] / 4.0 + 4 * work["colour_elems"] + 32 * n_reads_total
+    return tot / n_reads_total
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_library():
+    import synth
+    import nimble_aligner_b200 as nb
+    L = synth.SynthLibrary(seed=SEED, n_fam=200, n_all=5, group_on="")
+    obj = L.to_json_obj()
+    lib = nb.Library.from_text(json.dumps(obj), "unstranded")
+    return L, obj, lib
+
+
+def run_reference(args):
+    """CPU arm: the oracle with the reference's cost structure on a bounded sample, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as orc
+    import synth
+    L = synth.SynthLibrary(seed=SEED, n_fam=200, n_all=5, group_on="")
+    ocfg, oref = orc.parse_reference_library(L.to_json_obj(), "unstranded")
+    o = orc.Oracle(ocfg, oref, faithful_cost=True)
+    cores = os.cpu_count() or 1
+    n = args.ref_pairs
+    r1, o1, r2, o2 = synth.pairs(L, 0, n, seed=SEED, threads=cores)
+    for _ in range(args.warmup):
+        o.run(r1, o1[:n // 8 + 1], r2, o2[:n // 8 + 1], threads=cores, shard_single=True, want_records=False)
+    t0 = time.time()
+    for _ in range(args.steps):
+        o.run(r1, o1, r2, o2, threads=cores, shard_single=True, want_records=False)
+    dt = (time.time() - t0) / args.steps
+    v = 2 * n / dt
+    sample = "%d of the 10M C2 pairs per step (pairs 0..%d of the same seeded stream), %d threads over contiguous shards" % (n, n, cores)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer (f64 thresholds)",
+                      "data": "synthetic", "config": {"workload": "C2: 1k-transcript family library x 2x150 bp pairs, FASTQ-mode scope", "sample_pairs": n},
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def merge_across_ranks(ctx, nb, torch, dist, rank, world, pair_base):
+    """Whole-run de-duplication across GPUs: all-to-all of key records by key range, then all-reduce of counts."""
+    import ctypes as C
+    n = C.c_uint64(0)
+    nb._ck(nb.lib().nb_keys_export_count(ctx.h, C.byref(n)))
+    rec = torch.empty((max(n.value, 1), 4), dtype=torch.int64, device="cuda")
+    nb._ck(nb.lib().nb_keys_export(ctx.h, rec.data_ptr(), n.value, pair_base))
+    rec = rec[: n.value]
+    owner = ((rec[:, 0] >> 40) & 0xFFFF) % world            # key_lo is a 64-bit mix: any bit slice partitions evenly
+    order = torch.argsort(owner)
+    rec = rec[order].contiguous()
+    send = torch.bincount(owner, minlength=world)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    out = torch.empty((int(recv.sum().item()), 4), dtype=torch.int64, device="cuda")
+    dist.all_to_all_single(out, rec, output_split_sizes=[int(x) * 1 for x in recv.tolist()], input_split_sizes=[int(x) for x in send.tolist()])
+    # callset dictionaries: gather (tag, len, items) rows from every rank and import the union
+    cap = 1 << 18
+    nout, gcap = C.c_uint64(0), C.c_uint32(0)
+    nb._ck(nb.lib().nb_callsets_export(ctx.h, None, None, None, 0, C.byref(nout), C.byref(gcap)))
+    k, g = nout.value, gcap.value
+    tags, lens, items = np.zeros(max(k, 1), np.uint64), np.zeros(max(k, 1), np.uint32), np.zeros((max(k, 1), g), np.uint32)
+    nb._ck(nb.lib().nb_callsets_export(ctx.h, tags.ctypes.data, lens.ctypes.data, items.ctypes.data, k, C.byref(nout), C.byref(gcap)))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (tags[:k], lens[:k], items[:k]))
+    at = np.concatenate([x[0] for x in gathered]); al = np.concatenate([x[1] for x in gathered]); ai = np.concatenate([x[2] for x in gathered])
+    nb._ck(nb.lib().nb_callsets_import(ctx.h, at.ctypes.data, al.ctypes.data, np.ascontiguousarray(ai).ctypes.data, len(at)))
+    nb._ck(nb.lib().nb_keys_import(ctx.h, out.data_ptr(), out.shape[0]))
+    res = ctx.counts()
+    # per-callset counts keyed by the callset's names; summed over ranks
+    local = {tuple(cs): int(c) for _, cs, c in res["rows"]}
+    allc = [None] * world
+    dist.all_gather_object(allc, local)
+    total = {}
+    for d in allc:
+        for kx, v in d.items():
+            total[kx] = total.get(kx, 0) + v
+    return total, res["n_unique_keys"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=10_000_000, help="read pairs per GPU per step (C2: 10M)")
+    ap.add_argument("--ref-pairs", type=int, default=2_000_000, help="pairs per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--chunk", type=int, default=1 << 20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import nimble_aligner_b200 as nb
+    import synth
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.pairs
+    cores = os.cpu_count() or 1
+    L, obj, lib = build_library()
+    t0 = time.time()
+    ix = nb.build_index(lib, max(1, cores // max(1, world)))
+    index_build_s = time.time() - t0
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = nb.Context(ix, lib, device=local_rank, stream=stream, max_batch_pairs=args.chunk)
+    # ---- inputs: this rank's shard of the seeded stream, in pinned host memory and resident in HBM
+    pair_base = rank * n
+    o1 = np.zeros(n + 1, dtype=np.uint64); o2 = np.zeros(n + 1, dtype=np.uint64)
+    synth.lib().synth_pair_offsets(SEED, pair_base, n, READ_LEN, 0.1, o1.ctypes.data, o2.ctypes.data, cores)
+    h1 = torch.empty(int(o1[-1]) + 64, dtype=torch.uint8).pin_memory(); h2 = torch.empty(int(o2[-1]) + 64, dtype=torch.uint8).pin_memory()
+    synth.pairs(L, pair_base, n, seed=SEED, threads=max(1, cores // max(1, world)), out=(h1.numpy(), h2.numpy()))
+    ho1, ho2 = torch.from_numpy(o1.astype(np.int64)).pin_memory(), torch.from_numpy(o2.astype(np.int64)).pin_memory()
+    d1, d2, do1, do2 = h1.cuda(), h2.cuda(), ho1.cuda(), ho2.cuda()
+    n_reads = 2 * n
+
+    def step_device():
+        ctx.reset()
+        ctx.align_batch(d1, do1, d2, do2, n_pairs=n, max_read_len=READ_LEN, location=nb.NB_MEM_DEVICE)
+        if world > 1:
+            return merge_across_ranks(ctx, nb, torch, dist, rank, world, pair_base)
+        res = ctx.counts()
+        return {tuple(cs): int(c) for _, cs, c in res["rows"]}, res["n_unique_keys"]
+
+    def step_host():
+        ctx.reset()
+        # chunked submissions from pinned host memory; copies and kernels are stream-ordered inside the library
+        b = nb.Batch(n, nb.NB_MEM_HOST, READ_LEN, h1.data_ptr(), ho1.data_ptr(), h2.data_ptr(), ho2.data_ptr(), None, None, None, None, None, None)
+        import ctypes as C
+        nb._ck(nb.lib().nb_align_batch(ctx.h, C.byref(b), None, None))
+        if world > 1:
+            return merge_across_ranks(ctx, nb, torch, dist, rank, world, pair_base)
+        res = ctx.counts()
+        return {tuple(cs): int(c) for _, cs, c in res["rows"]}, res["n_unique_keys"]
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = max(e0.elapsed_time(e1), 0.0)
+        wall = (time.time() - w0) * 1e3
+        # the step ends with host-side work (count read-back + sort) after the last kernel: take the larger of the two clocks
+        ms = max(ms, wall)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, out
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.kernel_stats(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, (counts_dev, uniq_dev) = timed(step_device, args.steps)
+    ks = ctx.kernel_stats(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    step_host()
+    ms_host, (counts_host, uniq_host) = timed(step_host, args.steps)
+    assert counts_host == counts_dev, "host-fed and device-resident runs disagree"
+    if rank != 0:
+        return
+    value = n_reads * world / (ms_dev / 1e3)
+    e2e = n_reads * world / (ms_host / 1e3)
+    h2d = int(o1[-1]) + int(o2[-1]) + 2 * 8 * (n + 1)
+    d2h = 16 * (1 << 20) + (1 << 18) * (8 + 4 + 64) + 128     # count table + callset dictionary read back by nb_counts_finalize
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer (f64 thresholds)", "data": "synthetic",
+           "config": {"workload": "C2: synthetic 1k-transcript family library (200x5, seed 1234) x %d 2x150 bp pairs per GPU, FASTQ-mode whole-run scope" % n,
+                      "pairs_per_gpu": n, "reads_per_step": n_reads * world, "chunk_pairs": args.chunk, "l2": "inputs (%.1f GB ASCII per step) exceed the 126 MB L2" % ((int(o1[-1]) + int(o2[-1])) / 1e9),
+                      "index_device_mb": ix.stats()["device_bytes"] / 1e6, "index_build_s": index_build_s, "unique_pair_keys": int(uniq_dev), "callsets_counted": len(counts_dev)},
+           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_host},
+           "gpu_launches": ks["launches"], "clocks": clocks}
+    # ---- cpu baseline + roofline (rank 0, N=1 only)
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle as orc
+        ocfg, oref = orc.parse_reference_library(obj, "unstranded")
+        o = orc.Oracle(ocfg, oref, faithful_cost=True)
+        m = min(args.ref_pairs, n)
+        r1, oo1, r2, oo2 = synth.pairs(L, 0, m, seed=SEED, threads=cores)
+        t0 = time.time()
+        ref = o.run(r1, oo1, r2, oo2, threads=cores, shard_single=True, want_records=False)
+        dt = time.time() - t0
+        out["cpu_baseline"] = {"value": 2 * m / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": "first %d of the step's %d pairs, oracle with the reference's cost structure, %d threads over contiguous shards" % (m, n, cores)}
+        bpr = algorithmic_bytes_per_read(ref["work"], 2 * m)
+        launch_ms = ks["map_ms"] / max(1, ks["map_launches"])
+        reads_per_launch = ks["map_reads"] / max(1, ks["map_launches"])
+        achieved = bpr * reads_per_launch / (launch_ms / 1e3) / 1e9
+        peak, peak_src = 6650.0, "fallback"
+        try:
+            peak, peak_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k_map_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                           "kernel": "k_map", "peak_source": peak_src, "algorithmic_bytes_per_read": bpr, "reads_per_launch": reads_per_launch,
+                           "launch_ms": launch_ms, "kernel_share_of_step": ks["map_ms"] / (ms_dev * args.steps),
+                           "work_per_read": {k: ref["work"][k] / (2.0 * m) for k in ("probes", "nodes", "bases", "colour_elems")}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -65,7 +65,7 @@ struct nb_ctx {
   u64 max_batch_pairs = 1u << 20, arena_entries = 1u << 24, cs_slots = 1u << 18, key_slots = 1u << 22, agg_slots = 1u << 20;
   int count_work = 0; u32 min_read_len = 40;  // MIN_READ_LENGTH, src/align.rs:18 (tests pass 12, src/align.rs:1066)
   // persistent tables
-  DBuf d_cstag, d_cslen, d_csitems, d_key, d_kval, d_aggkey, d_aggcnt, d_arena, d_ctr, d_scratch, d_nout;
+  DBuf d_cstag, d_cslen, d_csitems, d_key, d_kval, d_klast, d_pslot, d_pres2, d_aggkey, d_aggcnt, d_arena, d_ctr, d_scratch, d_nout;
   u32 gcap = 16;
   bool tables_ready = false;
   // staging + per-batch buffers
@@ -85,7 +85,7 @@ struct nb_ctx {
 static Tables make_tables(nb_ctx* c) {
   Tables t;
   t.cs_tag = (u64*)c->d_cstag.p; t.cs_len = (u32*)c->d_cslen.p; t.cs_items = (u32*)c->d_csitems.p; t.cs_mask = (u32)c->cs_slots - 1; t.gcap = c->gcap;
-  t.key = (ulonglong2*)c->d_key.p; t.kval = (unsigned long long*)c->d_kval.p; t.key_mask = c->key_slots - 1;
+  t.key = (ulonglong2*)c->d_key.p; t.kval = (unsigned long long*)c->d_kval.p; t.klast = (unsigned long long*)c->d_klast.p; t.key_mask = c->key_slots - 1;
   t.agg_key = (unsigned long long*)c->d_aggkey.p; t.agg_cnt = (unsigned long long*)c->d_aggcnt.p; t.agg_mask = c->agg_slots - 1;
   t.arena = (u32*)c->d_arena.p; t.arena_cap = c->arena_entries; t.ctr = (Counters*)c->d_ctr.p;
   t.ent = (const double*)c->d_ent.p; t.ls = (const i64*)c->d_ls.p; t.qp = (const i64*)c->d_qp.p;
@@ -116,7 +116,8 @@ static int alloc_tables(nb_ctx* c) {
   c->gcap = std::max<u32>(16, (u32)c->hcfg.max_hits_to_report);
   c->dcfg.gcap = c->gcap;
   CK(c->d_cstag.ensure(c->cs_slots * 8, s)); CK(c->d_cslen.ensure(c->cs_slots * 4, s)); CK(c->d_csitems.ensure(c->cs_slots * (size_t)c->gcap * 4, s));
-  CK(c->d_key.ensure(c->key_slots * 16, s)); CK(c->d_kval.ensure(c->key_slots * 8, s));
+  CK(c->d_key.ensure(c->key_slots * 16, s)); CK(c->d_kval.ensure(c->key_slots * 8, s)); CK(c->d_klast.ensure(c->key_slots * 8, s));
+  CK(cudaMemsetAsync(c->d_klast.p, 0, c->key_slots * 8, s));
   CK(c->d_aggkey.ensure(c->agg_slots * 8, s)); CK(c->d_aggcnt.ensure(c->agg_slots * 8, s));
   CK(c->d_arena.ensure(c->arena_entries * 4, s)); CK(c->d_ctr.ensure(sizeof(Counters), s)); CK(c->d_nout.ensure(64, s));
   CK(cudaMemsetAsync(c->d_cstag.p, 0, c->cs_slots * 8, s)); CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s));
@@ -188,7 +189,7 @@ void nb_ctx_free(nb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_unitig, &c->d_node, &c->d_redge, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
-                 &c->d_ent, &c->d_ls, &c->d_qp, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
+                 &c->d_ent, &c->d_ls, &c->d_qp, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
                  &c->s_a[0], &c->s_a[1], &c->s_off[0], &c->s_off[1], &c->s_q[0], &c->s_q[1], &c->s_f[0], &c->s_f[1], &c->s_scope, &c->s_cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout};
   for (DBuf* b : all) b->release();
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -227,6 +228,7 @@ static int grow_keys(nb_ctx* c, u64 need_slots) {
   nbk::launch_rehash_keys(o, n, s); c->all_launches++;
   CK(cudaStreamSynchronize(s));
   c->d_key.release(); c->d_kval.release(); c->d_key = nk; c->d_kval = nv; c->key_slots = ns;
+  c->d_klast.release(); CK(c->d_klast.ensure(ns * 8, s)); CK(cudaMemsetAsync(c->d_klast.p, 0, ns * 8, s));
   return NB_OK;
 }
 
@@ -262,6 +264,7 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   }
   CK(c->d_pk.ensure((size_t)b.W * nr * 8, s)); CK(c->d_lenfull.ensure(nr * 4, s)); CK(c->d_lentrim.ensure(nr * 4, s));
   CK(c->d_rres.ensure(nr * sizeof(nbk::ReadRes), s)); CK(c->d_pres.ensure(np * sizeof(nbk::PairRes), s));
+  if (c->mode == 1) { CK(c->d_pslot.ensure(np * 8, s)); CK(c->d_pres2.ensure(np * sizeof(nbk::PairRes), s)); b.pslot = (u64*)c->d_pslot.p; b.pres2 = (nbk::PairRes*)c->d_pres2.p; }
   b.pk = (u64*)c->d_pk.p; b.len_full = (u32*)c->d_lenfull.p; b.len_trim = (u32*)c->d_lentrim.p; b.rres = (nbk::ReadRes*)c->d_rres.p; b.pres = (nbk::PairRes*)c->d_pres.p;
   // key-table capacity
   if (c->mode == 0) {
@@ -285,7 +288,8 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   nbk::launch_pair(b, c->dix, c->dlib, c->dcfg, t, s); c->all_launches++;
   if (c->mode == 1) {
     nbk::launch_fold(t, b.cell, b.order_base, s); c->all_launches++;
-    CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s));
+    if (pairs_out) { nbk::launch_resolve(b, t, s); c->all_launches++; }
+    CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s)); CK(cudaMemsetAsync(c->d_klast.p, 0, c->key_slots * 8, s));
   }
   cudaMemcpyKind okind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (reads_out) {
@@ -293,7 +297,7 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
     nbk::launch_export_reads(b, c->dix, t, c->d_rout.p, s); c->all_launches++;
     CK(cudaMemcpyAsync(reads_out + p0 * sides, c->d_rout.p, nr * sizeof(nb_read_result), okind, s));
   }
-  if (pairs_out) CK(cudaMemcpyAsync(pairs_out + p0, c->d_pres.p, np * sizeof(nb_pair_result), okind, s));
+  if (pairs_out) CK(cudaMemcpyAsync(pairs_out + p0, c->mode == 1 ? c->d_pres2.p : c->d_pres.p, np * sizeof(nb_pair_result), okind, s));
   CK(cudaGetLastError());
   c->pairs_seen += np; c->last_b = b; c->have_last = true;
   return NB_OK;

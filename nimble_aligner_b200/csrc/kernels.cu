@@ -393,9 +393,11 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
   if (paired && cfg.require_valid_pair) {
     bool bad = e1.n == 0 || e2.n == 0 || e1.n != e2.n;
     if (!bad) ec_each(e1, [&](u32 x) { if (!ec_has(e2, x)) { bad = true; return false; } return true; });
-    if (bad) { out.fr1 = out.fr2 = R_NOT_MATCHING_PAIR; b.pres[p] = out; return; }
+    if (bad) { out.fr1 = out.fr2 = R_NOT_MATCHING_PAIR; e1.n = e2.n = 0; }
   }
-  if (e1.n == 0 && e2.n == 0) { b.pres[p] = out; return; }   // failed alignment: bookkeeping only (src/align.rs:686-725)
+  u32 cs = CS_NONE;
+  const bool scoped = b.scope != nullptr;
+  if (e1.n != 0 || e2.n != 0) {   // else failed alignment: bookkeeping only (src/align.rs:686-725)
   out.insertable = 1;
   // ---- filter_and_coerce_sequence_call_orientations, src/align.rs:178-252, on integer ids
   int chem = cfg.strand_filter;
@@ -443,17 +445,40 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
   u32 triage = R_NONE;
   if (cnt > cfg.max_hits) triage = R_MAX_HITS;
   else if (cnt == 0) triage = R_TRIAGE_EMPTY;
-  u32 cs = CS_NONE;
   if (triage == R_NONE) {
     u32 slot = callset_intern(t, gl.g, gl.n);
     if (slot == NONE32 || slot >= CS_NONE) atomicOr(&t.ctr->err, (unsigned)E_CS_FULL); else { cs = slot; out.callset = slot; }
   }
   out.triage = (u8)triage;
-  // ---- score_map.insert(read_key, ...): later duplicates overwrite (src/align.rs:685) => keep the highest order
-  u64 slot = key_insert(t, h0, h1);
-  if (slot == ~0ULL) atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL);
-  else atomicMax(t.kval + slot, (unsigned long long)(((b.order_base + p) << 24) | cs));
+  }
+  // ---- score_map.insert(read_key, ...): later duplicates overwrite (src/align.rs:685) => keep the highest order.
+  // Scoped (BAM) batches also register non-insertable pairs: filter_reasons is keyed by read_key for every pair
+  // (src/align.rs:586-600) and k_resolve reports per-key outcomes.
+  if (out.insertable || scoped) {
+    u64 slot = key_insert(t, h0, h1);
+    if (slot == ~0ULL) atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL);
+    else {
+      unsigned long long ord1 = b.order_base + p + 1;
+      if (out.insertable) atomicMax(t.kval + slot, (ord1 << 24) | cs);
+      if (scoped) { atomicMax(t.klast + slot, ord1); b.pslot[p] = slot; }
+    }
+  }
   b.pres[p] = out;
+}
+
+// Per-pair records as the reference reports them (per read_key): filter reasons of the LAST pair carrying the key
+// (filter_reasons.insert overwrites, src/align.rs:586-600), triage / callset of the last pair that reached score_map
+// (src/align.rs:685, 440-449).  Scoped batches only; all pairs of a key live in the same batch.
+__global__ void __launch_bounds__(256) k_resolve(BatchDev b, Tables t) {
+  u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (p >= b.n_pairs) return;
+  PairRes out = b.pres[p];
+  u64 slot = b.pslot[p];
+  u64 last = t.klast[slot], v = t.kval[slot];
+  if (last) { const PairRes& l = b.pres[last - 1 - b.order_base]; out.fr1 = l.fr1; out.fr2 = l.fr2; }
+  if (v >> 24) { const PairRes& r = b.pres[(v >> 24) - 1 - b.order_base]; out.triage = r.triage; out.callset = r.callset; }
+  else { out.triage = R_NONE; out.callset = NONE32; }
+  b.pres2[p] = out;
 }
 
 // ------------------------------------------------------------------------------------------------ K4 fold
@@ -465,7 +490,7 @@ __global__ void __launch_bounds__(256) k_fold(Tables t, const u32* cell_of_pair,
   if (k.x == 0 && k.y == 0) return;
   u64 v = t.kval[idx]; u32 cs = (u32)(v & 0xFFFFFFu);
   if (cs == CS_NONE) return;
-  u32 cell = cell_of_pair ? cell_of_pair[(v >> 24) - order_base] : 0u;
+  u32 cell = cell_of_pair ? cell_of_pair[(v >> 24) - 1 - order_base] : 0u;
   unsigned long long ak = (((unsigned long long)cell << 24) | cs) + 1ULL;
   u64 h = mix64(ak) & t.agg_mask;
   for (u64 probes = 0; probes <= t.agg_mask; probes++) {
@@ -512,7 +537,7 @@ __global__ void __launch_bounds__(256) k_keys_export(Tables t, KeyRec* rec, unsi
   u64 v = t.kval[idx]; u32 cs = (u32)(v & 0xFFFFFFu);
   unsigned long long at = atomicAdd(n_out, 1ULL);
   if (at >= cap) return;
-  KeyRec r; r.k0 = k.x; r.k1 = k.y; r.order = (v >> 24) + order_base; r.tag = cs == CS_NONE ? 0ULL : t.cs_tag[cs];
+  KeyRec r; r.k0 = k.x; r.k1 = k.y; r.order = (v >> 24) - 1 + order_base; r.tag = cs == CS_NONE ? 0ULL : t.cs_tag[cs];
   rec[at] = r;
 }
 // import records from other ranks: the tag must already be present in this rank's dictionary (the host merges
@@ -530,7 +555,7 @@ __global__ void __launch_bounds__(256) k_keys_import(Tables t, const KeyRec* rec
   }
   u64 slot = key_insert(t, r.k0, r.k1);
   if (slot == ~0ULL) { atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL); return; }
-  atomicMax(t.kval + slot, (unsigned long long)((r.order << 24) | cs));
+  atomicMax(t.kval + slot, (unsigned long long)(((r.order + 1) << 24) | cs));
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -546,6 +571,7 @@ void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const
   if (b.n_pairs) k_pair<<<blocks_for(b.n_pairs, 128), 128, 0, s>>>(b, ix, lib, cfg, t);
 }
 void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s) { k_fold<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, cell_of_pair, order_base); }
+void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_pairs) k_resolve<<<blocks_for(b.n_pairs, 256), 256, 0, s>>>(b, t); }
 void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t, void* out, cudaStream_t s) {
   if (b.n_reads) k_export_reads<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, ix, t, (ReadOut*)out);
 }

@@ -65,6 +65,7 @@ struct BatchDev {
   const u8* a[2]; const u64* off[2]; const u8* q[2]; const u8* flags[2]; const u32* scope; const u32* cell;
   u64* pk; u32* len_full; u32* len_trim;                  // pk[w * n_reads + ri], ri = p*sides + side
   ReadRes* rres; PairRes* pres;
+  u64* pslot; PairRes* pres2;                            // scoped batches: key slot per pair, per-key resolved records
   u64 order_base;
 };
 
@@ -72,7 +73,7 @@ struct Tables {
   // callset dictionary
   u64* cs_tag; u32* cs_len; u32* cs_items; u32 cs_mask; u32 gcap;
   // de-duplication key table (128-bit keys, CAS128) and value = order<<24 | callset slot
-  ulonglong2* key; unsigned long long* kval; u64 key_mask;
+  ulonglong2* key; unsigned long long* kval; unsigned long long* klast; u64 key_mask;   // kval = (order+1)<<24 | callset slot
   // (cell, callset) histogram
   unsigned long long* agg_key; unsigned long long* agg_cnt; u64 agg_mask;
   u32* arena; u64 arena_cap;
@@ -85,6 +86,7 @@ void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s);
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s);
 void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s);
 void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s);
+void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s);
 void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t, void* out, cudaStream_t s);
 void launch_rehash_keys(const Tables& old_t, const Tables& new_t, cudaStream_t s);
 void launch_keys_export(const Tables& t, void* records, unsigned long long* n_out, u64 cap, u64 order_base, cudaStream_t s);

@@ -568,9 +568,13 @@ void run_scope(Oracle& o, const Input& in, u64 p0, u64 p1, ScopeResult& res, Wor
   res.n_pairs = p1 - p0;
   // per-pair projection: every pair sharing a key reports that key's triage / callset
   for (u64 p = p0; p < p1; p++) {
+    PairRec& pr = o.pairs[p];
+    // filter_reasons is keyed by read_key and overwritten by later pairs (src/align.rs:586-600); the BAM driver looks
+    // the reasons up by key (src/process/bam.rs:356-361), so every pair reports its key's last entry
+    auto fr = filter_reasons.find(keys[p - p0]);
+    if (fr != filter_reasons.end()) { pr.fr1 = fr->second.first; pr.fr2 = fr->second.second; }
     auto it = per_key.find(keys[p - p0]);
     if (it == per_key.end()) continue;
-    PairRec& pr = o.pairs[p];
     pr.triage = it->second.first;
     if (pr.triage == ReasonNone) {
       pr.counted = 1;
