@@ -43,35 +43,55 @@ def algorithmic_bytes_per_read(work, n_reads_total):
 
 
 class ClockSampler:
+    """Polls NVML (same counters as the nvidia-smi clocks line of B200_PROFILING.md) every ~2 ms from a thread, so that
+    even a sub-second timed region gets samples DURING it."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.stop_flag, self.thread, self.h = gpu_index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        rows = [r for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
+        mx = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
-                if v.lower().startswith("active"):
+            pass
+        reasons = set()
+        for _, _, rs in rows:
+            for name, bit in self.REASONS.items():
+                if rs & bit:
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(rows)}
 
 
 def build_library():
@@ -244,9 +264,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    tw0 = time.time()
     ms_dev, (counts_dev, uniq_dev) = timed(step_device, args.steps)
+    tw1 = time.time()
     ks = ctx.kernel_stats(reset=True)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     step_host()
     ms_host, (counts_host, uniq_host) = timed(step_host, args.steps)
     assert counts_host == counts_dev, "host-fed and device-resident runs disagree"

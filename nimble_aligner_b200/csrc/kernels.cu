@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(256) k_fold(Tables t, const u32* cell_of_pair,
   ulonglong2 k = t.key[idx];
   if (k.x == 0 && k.y == 0) return;
   u64 v = t.kval[idx]; u32 cs = (u32)(v & 0xFFFFFFu);
-  if (cs == CS_NONE) return;
+  if ((v >> 24) == 0 || cs == CS_NONE) return;   // key never reached score_map (scoped batches register every key) / triaged
   u32 cell = cell_of_pair ? cell_of_pair[(v >> 24) - 1 - order_base] : 0u;
   unsigned long long ak = (((unsigned long long)cell << 24) | cs) + 1ULL;
   u64 h = mix64(ak) & t.agg_mask;
