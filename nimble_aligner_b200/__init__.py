@@ -332,13 +332,34 @@ class Context:
 
     def counts(self):
         """nb_counts_finalize -> dict(rows=[(scope, [group names], count)], callsets=[[names]], n_pairs_seen, n_unique_keys)."""
+        raw = self.counts_raw()
+        return self.decode_counts(raw)
+
+    def counts_raw(self):
+        """nb_counts_finalize -> numpy copies of the C arrays (group indices, no strings)."""
         c = Counts()
         _ck(lib().nb_counts_finalize(self.h, C.byref(c)))
-        names = self.library.group_names()
-        callsets = []
-        for i in range(c.n_callsets):
-            callsets.append([names[c.callset_items[k]] for k in range(c.callset_off[i], c.callset_off[i + 1])])
-        rows = [(c.row_scope[r], callsets[c.row_callset[r]], c.row_count[r]) for r in range(c.n_rows)]
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(p, (n,)).copy() if n else np.zeros(0, dt)
+        n_items = int(c.callset_off[c.n_callsets]) if c.n_callsets else 0
+        return dict(row_scope=arr(c.row_scope, c.n_rows, np.uint32), row_callset=arr(c.row_callset, c.n_rows, np.uint32),
+                    row_count=arr(c.row_count, c.n_rows, np.int64), callset_off=arr(c.callset_off, c.n_callsets + 1, np.uint64),
+                    callset_items=arr(c.callset_items, n_items, np.uint32), n_pairs_seen=c.n_pairs_seen, n_unique_keys=c.n_unique_keys,
+                    slot_to_callset=arr(c.slot_to_callset, c.n_slots, np.uint32))
+
+    def decode_counts(self, raw):
+        if getattr(self, "_group_names", None) is None:
+            self._group_names = self.library.group_names()
+        names = self._group_names
+        off, items = raw["callset_off"].tolist(), raw["callset_items"].tolist()
+        callsets = [[names[g] for g in items[off[i]:off[i + 1]]] for i in range(len(off) - 1)]
+        rows = [(sc, callsets[cs], n) for sc, cs, n in zip(raw["row_scope"].tolist(), raw["row_callset"].tolist(), raw["row_count"].tolist())]
+        out = dict(raw)
+        out.update(rows=rows, callsets=callsets)
+        return out
+
+    def _unused_counts(self, c, rows, callsets):
         return dict(rows=rows, callsets=callsets, n_pairs_seen=c.n_pairs_seen, n_unique_keys=c.n_unique_keys,
                     row_scope=np.ctypeslib.as_array(c.row_scope, (c.n_rows,)).copy() if c.n_rows else np.zeros(0, np.uint32),
                     row_callset=np.ctypeslib.as_array(c.row_callset, (c.n_rows,)).copy() if c.n_rows else np.zeros(0, np.uint32),

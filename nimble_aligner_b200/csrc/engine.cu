@@ -374,27 +374,33 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   if (c->mode == 0 && !c->folded) { nbk::launch_fold(t, nullptr, 0, s); c->all_launches++; c->folded = true; }
   Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
   c->last_unique = h.n_keys;
-  // read back the (cell, callset) table and the callset dictionary
-  std::vector<u64> ak(c->agg_slots), ac(c->agg_slots);
-  CK(cudaMemcpyAsync(ak.data(), c->d_aggkey.p, c->agg_slots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(ac.data(), c->d_aggcnt.p, c->agg_slots * 8, cudaMemcpyDeviceToHost, s));
-  std::vector<u64> tag(c->cs_slots); std::vector<u32> len(c->cs_slots), items((size_t)c->cs_slots * c->gcap);
-  CK(cudaMemcpyAsync(tag.data(), c->d_cstag.p, c->cs_slots * 8, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(len.data(), c->d_cslen.p, c->cs_slots * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(items.data(), c->d_csitems.p, items.size() * 4, cudaMemcpyDeviceToHost, s));
+  // compact the occupied entries of the (cell, callset) table and of the callset dictionary on the device, then read
+  // back only those: rows of {key, count} and of {slot, len, items[gcap]}
+  u64 n_agg = h.n_agg, n_cs = h.n_callsets; u32 cw = 2 + c->gcap;
+  CK(c->d_scratch.ensure(n_agg * 16 + n_cs * (size_t)cw * 4 + 64, s));
+  u64* d_agg = (u64*)c->d_scratch.p; u32* d_cs = (u32*)((char*)c->d_scratch.p + n_agg * 16);
+  CK(cudaMemsetAsync(c->d_nout.p, 0, 16, s));
+  nbk::launch_compact(t, d_agg, n_agg, d_cs, n_cs, (unsigned long long*)c->d_nout.p, s); c->all_launches += 2;
+  std::vector<u64> agg(2 * n_agg); std::vector<u32> csr((size_t)n_cs * cw);
+  if (n_agg) CK(cudaMemcpyAsync(agg.data(), d_agg, n_agg * 16, cudaMemcpyDeviceToHost, s));
+  if (n_cs) CK(cudaMemcpyAsync(csr.data(), d_cs, n_cs * (size_t)cw * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   // callsets sorted by Vec<String> Ord (utils::sort_score_vector, src/utils.rs:54-59): bytewise on the group names
   const std::vector<std::string>& gn = c->lib->group_names;
-  std::vector<u32> slots; for (u32 i = 0; i < c->cs_slots; i++) if (tag[i]) slots.push_back(i);
+  std::vector<u32> slots(n_cs); for (u32 i = 0; i < n_cs; i++) slots[i] = i;   // indices into the compact rows
   auto cs_less = [&](u32 a, u32 b) {
-    u32 la = len[a], lb = len[b];
-    for (u32 i = 0; i < std::min(la, lb); i++) { u32 ga = items[(size_t)a * c->gcap + i], gb = items[(size_t)b * c->gcap + i]; if (ga != gb) { int cmp = gn[ga].compare(gn[gb]); if (cmp) return cmp < 0; } }
-    return la < lb;
+    const u32* ra = &csr[(size_t)a * cw]; const u32* rb = &csr[(size_t)b * cw];
+    u32 la = ra[1], lb = rb[1];
+    for (u32 i = 0; i < std::min(la, lb); i++) { u32 ga = ra[2 + i], gb = rb[2 + i]; if (ga != gb) { int cmp = gn[ga].compare(gn[gb]); if (cmp) return cmp < 0; } }
+    if (la != lb) return la < lb;
+    return ra[0] < rb[0];
   };
   std::sort(slots.begin(), slots.end(), cs_less);
   std::vector<u32>& dense = c->slot_dense; dense.assign(c->cs_slots, NONE32);
-  for (u32 i = 0; i < slots.size(); i++) { dense[slots[i]] = i; for (u32 k = 0; k < len[slots[i]]; k++) c->cs_items.push_back(items[(size_t)slots[i] * c->gcap + k]); c->cs_off.push_back(c->cs_items.size()); }
+  for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[2 + k]); c->cs_off.push_back(c->cs_items.size()); }
   struct Row { u32 cell, cs; i64 n; };
-  std::vector<Row> rows;
-  for (u64 i = 0; i < c->agg_slots; i++) if (ak[i]) { u64 k = ak[i] - 1; rows.push_back(Row{(u32)(k >> 24), dense[(u32)(k & 0xFFFFFF)], (i64)ac[i]}); }
+  std::vector<Row> rows; rows.reserve(n_agg);
+  for (u64 i = 0; i < n_agg; i++) { u64 k = agg[2 * i] - 1; rows.push_back(Row{(u32)(k >> 24), dense[(u32)(k & 0xFFFFFF)], (i64)agg[2 * i + 1]}); }
   std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.cell != b.cell ? a.cell < b.cell : a.cs < b.cs; });
   for (auto& r : rows) { c->row_scope.push_back(r.cell); c->row_callset.push_back(r.cs); c->row_count.push_back(r.n); }
   out->n_rows = rows.size(); out->row_scope = c->row_scope.data(); out->row_callset = c->row_callset.data(); out->row_count = c->row_count.data();
@@ -472,6 +478,8 @@ int nb_callsets_import(nb_ctx* c, const uint64_t* tags, const uint32_t* lens, co
     for (u64 pr = 0; pr <= mask; pr++) { if (tag[h] == tags[i]) { done = true; break; } if (!tag[h]) { tag[h] = tags[i]; len[h] = lens[i]; memcpy(&it[(size_t)h * c->gcap], items + i * c->gcap, c->gcap * 4); done = true; break; } h = (h + 1) & mask; }
     if (!done) return fail(NB_ERR_OVERFLOW, "callset dictionary full: raise option callset_slots");
   }
+  unsigned long long occupied = 0; for (u32 i = 0; i < c->cs_slots; i++) occupied += tag[i] != 0;
+  CK(cudaMemcpyAsync(&((Counters*)c->d_ctr.p)->n_callsets, &occupied, 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_cstag.p, tag.data(), c->cs_slots * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaMemcpyAsync(c->d_cslen.p, len.data(), c->cs_slots * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_csitems.p, it.data(), it.size() * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
   return NB_OK;

@@ -107,8 +107,8 @@ struct WorkCnt { u32 probes, nodes, bases, colour_elems; };
 // smallest-so-far colour list (<= 64 ids); "big mode": a private copy in the arena that shrinks in place.
 struct EcAcc {
   const u32* col_off; const u32* col_ids; u32* arena; Counters* ctr; u64 arena_cap;
-  bool any, big; u32 last, base, bsize, alen; u64 boff, aoff, mask;
-  __device__ void init(const DevIndex& ix, const Tables& t) { col_off = ix.col_off; col_ids = ix.col_ids; arena = t.arena; ctr = t.ctr; arena_cap = t.arena_cap; any = big = false; last = NONE32; base = NONE32; bsize = alen = 0; boff = aoff = 0; mask = 0; }
+  bool any, big; u32 last, prev2, base, bsize, alen; u64 boff, aoff, mask;
+  __device__ void init(const DevIndex& ix, const Tables& t) { col_off = ix.col_off; col_ids = ix.col_ids; arena = t.arena; ctr = t.ctr; arena_cap = t.arena_cap; any = big = false; last = prev2 = NONE32; base = NONE32; bsize = alen = 0; boff = aoff = 0; mask = 0; }
   __device__ void add(u32 cid, WorkCnt& wc) {
     if (cid == last) { return; }
     last = cid;
@@ -126,9 +126,20 @@ struct EcAcc {
       return;
     }
     if (!big) {
-      if (cid == base) return;
+      if (cid == base || cid == prev2) return;     // intersecting with an already-applied colour changes nothing
+      prev2 = cid;
       u64 m = mask;
-      while (m) { int i = __ffsll((long long)m) - 1; m &= m - 1; u32 idx; if (!bsearch32(col_ids + o, s, __ldg(col_ids + boff + i), idx)) mask &= ~(1ULL << i); }
+      if (s <= 16) {  // small colours (the common case): one linear merge pass over both sorted lists
+        u32 j = 0, cj = s ? __ldg(col_ids + o) : NONE32;
+        while (m) {
+          int i = __ffsll((long long)m) - 1; m &= m - 1;
+          u32 e = __ldg(col_ids + boff + i);
+          while (j < s && cj < e) { j++; cj = j < s ? __ldg(col_ids + o + j) : NONE32; }
+          if (j >= s || cj != e) mask &= ~(1ULL << i);
+        }
+      } else {
+        while (m) { int i = __ffsll((long long)m) - 1; m &= m - 1; u32 idx; if (!bsearch32(col_ids + o, s, __ldg(col_ids + boff + i), idx)) mask &= ~(1ULL << i); }
+      }
     } else if (s <= 64) {
       u64 nm = 0;
       for (u32 i = 0; i < s; i++) { u32 e = __ldg(col_ids + o + i); u32 lo = 0, hi = alen; while (lo < hi) { u32 mid = (lo + hi) >> 1; if (arena[aoff + mid] < e) lo = mid + 1; else hi = mid; } if (lo < alen && arena[aoff + lo] == e) nm |= 1ULL << i; }
@@ -193,91 +204,154 @@ __device__ __forceinline__ bool find_seed(const DevIndex& ix, const ReadView& rd
   return false;
 }
 
+// One table probe for the k-mer starting at `pos` (linear probing over 8-byte keys; load factor <= 0.5)
+__device__ __forceinline__ bool probe_kmer(const DevIndex& ix, const ReadView& rd, u32 pos, u32& node, u32& off) {
+  u64 km = rd.win(pos) & KMASK;
+  u64 h = mix64(km) & ix.tmask;
+  for (;;) {
+    u64 k = __ldg(ix.tkey + h);
+    if (!(k >> 63)) return false;
+    if ((k & KMASK) == km) { u64 v = __ldg(ix.tval + h); node = (u32)v; off = (u32)(v >> 32); return true; }
+    h = (h + 1) & ix.tmask;
+  }
+}
+
+// k_map is a warp-synchronous state machine, one read per lane:
+//   ST_SEED  the lane needs a seed at/after kp: two per-lane probes (the common hit), then the whole warp searches the
+//            remaining stride-3 seeds of that lane 32 at a time (off-target reads would otherwise hold the warp for
+//            ~41 serial probes) — first hit in seed order wins, exactly the sequential search of App. B;
+//   ST_WALK  one unitig per iteration: colour, base compare with the per-node mismatch budget, edge follow / re-seed.
+enum { ST_DONE = 0, ST_SEED = 1, ST_WALK = 2 };
+
 template <int COUNT_WORK>
 __global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg, Tables t) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const u32 lane = threadIdx.x & 31;
   u32 ri = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ri >= b.n_reads) return;
+  const bool valid = ri < b.n_reads;
+  if (!valid) ri = b.n_reads - 1;               // keep the lane in the warp-collective steps; it never stores
   u32 side = ri % b.sides; u64 p = ri / b.sides;
   ReadRes rr; rr.hdr = R_SUCCESS; rr.score = 0; rr.mm = 0; rr.ec_len = 0; rr.bsize = 0; rr.ref = 0; rr.mask = 0;
   WorkCnt wc = {0, 0, 0, 0};
   u32 n = b.len_trim[ri];
   bool skip = b.flags[side] != nullptr && (b.flags[side][p] & 1);
   ReadView rd{b.pk + ri, b.n_reads};
-  if (skip) { rr.hdr = R_SKIPPED | (1u << 10); }                                        // src/align.rs:527-528
-  else if (n < cfg.min_read_len) { rr.hdr = R_SHORT; }                                               // src/align.rs:955-957
+  int st = ST_DONE;
+  if (!valid) { }
+  else if (skip) { rr.hdr = R_SKIPPED | (1u << 10); }                                   // src/align.rs:527-528
+  else if (n < cfg.min_read_len) { rr.hdr = R_SHORT; }                                 // src/align.rs:955-957
   else {
     // shannon_entropy on the (trimmed) read, src/utils.rs:96-119; terms come from a host-built table of
     // f*log2(f) (same libm as the CPU reference), summed in the reference's A,T,C,G order.
-    u32 cA = 0, cC = 0, cG = 0, cT = 0;
+    u32 cC = 0, cG = 0, cT = 0;
     for (u32 w = 0; w * 32 < n; w++) {
       u64 x = rd.word(w); u32 c = min(32u, n - w * 32);
       u64 lo = x & 0x5555555555555555ULL, hi = (x >> 1) & 0x5555555555555555ULL;
-      u64 valid = c < 32 ? ((1ULL << (2 * c)) - 1) & 0x5555555555555555ULL : 0x5555555555555555ULL;
-      cC += __popcll(lo & ~hi & valid); cG += __popcll(hi & ~lo & valid); cT += __popcll(hi & lo & valid);
+      u64 vm = c < 32 ? ((1ULL << (2 * c)) - 1) & 0x5555555555555555ULL : 0x5555555555555555ULL;
+      cC += __popcll(lo & ~hi & vm); cG += __popcll(hi & ~lo & vm); cT += __popcll(hi & lo & vm);
     }
-    cA = n - cC - cG - cT;
+    u32 cA = n - cC - cG - cT;
     const double* et = t.ent + (size_t)n * (n + 1) / 2;
     double e = 0.0;
     if (cA) e += et[cA];
     if (cT) e += et[cT];
     if (cC) e += et[cC];
     if (cG) e += et[cG];
-    if (-e < 1.75) { rr.hdr = R_ENTROPY; }                                              // src/align.rs:960-962
-    else {
-      EcAcc acc; acc.init(ix, t);
-      u32 cov = 0, mm = 0, allowed = cfg.num_mismatches;
-      u32 last_kpos = n - K, kp = n < (u32)K ? 1u : 0u, node = 0, off = 0;  // n < k: map_read returns None
-      if (n < (u32)K) last_kpos = 0;
-      const u32* redge = (const u32*)ix.redge; const u32* ledge = (const u32*)ix.ledge;
-      bool found = find_seed(ix, rd, kp, last_kpos, node, off, wc);
-      if (found) {
-        u32 lthr = (u32)(0.2 * (double)n);
-        if (kp >= lthr) {  // left extension [App. B]
-          u32 lp = kp - 1, pn = node, po = off > 0 ? off - 1 : 0;
-          for (;;) {
-            uint4 nd = __ldg(ix.node + pn);
-            u64 start = (u64)nd.x | ((u64)(nd.w >> 8) << 32);
-            u32 m = min(lp + 1, po + 1), mb, snp; bool brk;
-            cmp_bwd(ix.unitig, start + po, rd, lp, m, allowed, mb, snp, brk);
-            mm += snp; cov += mb; wc.bases += mb + (brk ? 1 : 0);
-            if (lp + 1 - mb == 0 || brk) break;
-            lp -= mb;
-            u32 bs = rd.base(lp);
-            if ((nd.w >> bs) & 1) {
-              pn = __ldg(ledge + 4 * (u64)pn + bs);
-              uint4 n2 = __ldg(ix.node + pn);
-              po = n2.y - K; acc.add(n2.z, wc); wc.nodes++;
-            } else break;
-          }
-        }
-        for (;;) {  // forward walk
-          uint4 nd = __ldg(ix.node + node);
+    if (-e < 1.75) rr.hdr = R_ENTROPY;                                                  // src/align.rs:960-962
+    else if (n >= (u32)K) st = ST_SEED;                                                 // n < k: map_read returns None
+    else rr.hdr = R_NO_MATCH;
+  }
+  EcAcc acc; acc.init(ix, t);
+  u32 cov = 0, mm = 0; const u32 allowed = cfg.num_mismatches;
+  const u32 last_kpos = n >= (u32)K ? n - K : 0;
+  u32 kp = 0, node = 0, off = 0; bool first = true;
+  const u32* redge = (const u32*)ix.redge; const u32* ledge = (const u32*)ix.ledge;
+  while (__any_sync(FULL, st != ST_DONE)) {
+    // ---- (A) per-lane probes: the seed at kp and the next one
+    if (st == ST_SEED) {
+#pragma unroll 1
+      for (int tries = 0; tries < 2 && st == ST_SEED; tries++) {
+        if (kp > last_kpos) { st = ST_DONE; break; }
+        wc.probes++;
+        if (probe_kmer(ix, rd, kp, node, off)) st = ST_WALK; else kp += 3;
+      }
+      if (st == ST_SEED && kp > last_kpos) st = ST_DONE;
+    }
+    // ---- (B) warp-cooperative search for the lanes that are still looking
+    unsigned need = __ballot_sync(FULL, st == ST_SEED);
+    while (need) {
+      int l = __ffs(need) - 1; need &= need - 1;
+      u32 s_kp = __shfl_sync(FULL, kp, l), s_last = __shfl_sync(FULL, last_kpos, l), s_ri = __shfl_sync(FULL, ri, l);
+      ReadView srd{b.pk + s_ri, b.n_reads};
+      u32 f_kp = NONE32, f_node = 0, f_off = 0, tried = 0;
+      for (u32 base = s_kp; base <= s_last; base += 96) {
+        u32 my = base + 3 * lane, nd2 = 0, of2 = 0;
+        bool hit = my <= s_last && probe_kmer(ix, srd, my, nd2, of2);
+        unsigned hb = __ballot_sync(FULL, hit);
+        if (hb) { int f = __ffs(hb) - 1; f_node = __shfl_sync(FULL, nd2, f); f_off = __shfl_sync(FULL, of2, f); f_kp = base + 3 * f; tried += f + 1; break; }
+        tried += min(32u, (s_last - base) / 3 + 1);
+      }
+      if ((int)lane == l) {
+        wc.probes += tried;                     // same count as the sequential search: seeds up to and including the hit
+        if (f_kp != NONE32) { kp = f_kp; node = f_node; off = f_off; st = ST_WALK; } else st = ST_DONE;
+      }
+    }
+    // ---- (C) left extension, only after the first seed and only if it sits at >= 20 % of the read [App. B]
+    if (st == ST_WALK && first) {
+      first = false;
+      u32 lthr = (u32)(0.2 * (double)n);
+      if (kp >= lthr) {
+        u32 lp = kp - 1, pn = node, po = off > 0 ? off - 1 : 0;
+        for (;;) {
+          uint4 nd = __ldg(ix.node + pn);
           u64 start = (u64)nd.x | ((u64)(nd.w >> 8) << 32);
-          kp += K; cov += K; acc.add(nd.z, wc); wc.nodes++;
-          u32 ro = off + K, m = min(n - kp, nd.y - ro), mb, snp; bool brk;
-          cmp_fwd(ix.unitig, start + ro, rd, kp, m, allowed, mb, snp, brk);
-          mm += snp; cov += mb; kp += mb; wc.bases += mb + (brk ? 1 : 0);
-          if (kp >= n) break;
-          u32 bs = rd.base(kp);
-          if (!brk && ((nd.w >> (4 + bs)) & 1)) { node = __ldg(redge + 4 * (u64)node + bs); off = 0; kp -= K - 1; cov -= K - 1; }
-          else { if (kp > last_kpos) break; if (!find_seed(ix, rd, kp, last_kpos, node, off, wc)) break; }
+          u32 m = min(lp + 1, po + 1), mb, snp; bool brk;
+          cmp_bwd(ix.unitig, start + po, rd, lp, m, allowed, mb, snp, brk);
+          mm += snp; cov += mb; wc.bases += mb + (brk ? 1 : 0);
+          if (lp + 1 - mb == 0 || brk) break;
+          lp -= mb;
+          u32 bs = rd.base(lp);
+          if ((nd.w >> bs) & 1) {
+            pn = __ldg(ledge + 4 * (u64)pn + bs);
+            uint4 n2 = __ldg(ix.node + pn);
+            po = n2.y - K; acc.add(n2.z, wc); wc.nodes++;
+          } else break;
         }
       }
-      if (!acc.any) rr.hdr = R_NO_MATCH;                                               // src/align.rs:987
+    }
+    first = first && st != ST_DONE;
+    // ---- (D) one unitig of the forward walk
+    if (st == ST_WALK) {
+      uint4 nd = __ldg(ix.node + node);
+      u64 start = (u64)nd.x | ((u64)(nd.w >> 8) << 32);
+      kp += K; cov += K; acc.add(nd.z, wc); wc.nodes++;
+      u32 ro = off + K, m = min(n - kp, nd.y - ro), mb, snp; bool brk;
+      cmp_fwd(ix.unitig, start + ro, rd, kp, m, allowed, mb, snp, brk);
+      mm += snp; cov += mb; kp += mb; wc.bases += mb + (brk ? 1 : 0);
+      if (kp >= n) st = ST_DONE;
       else {
-        u32 ecl = acc.ec_len();
-        rr.score = (u16)cov; rr.mm = (u16)mm; rr.ec_len = ecl; rr.bsize = acc.big ? acc.alen : acc.bsize;
-        rr.ref = acc.big ? acc.aoff : acc.boff; rr.mask = acc.mask;
-        double norm = (double)cov / (double)n;
-        u32 reason;
-        if (cfg.discard_nonzero_mismatch && mm != 0) reason = R_NONZERO_MM;             // src/align.rs:971-973
-        else if (cov >= cfg.score_threshold && norm >= cfg.score_percent && ecl != 0) {  // src/filter/align.rs:17-45
-          if (cfg.discard_multiple_matches && ecl > 1) reason = R_MULTI;
-          else if (mm > cfg.num_mismatches) reason = R_ABOVE_MM;
-          else reason = R_SUCCESS | (1u << 8);
-        } else reason = R_SCORE_BELOW;
-        rr.hdr = reason | (acc.big ? (1u << 9) : 0u);
+        u32 bs = rd.base(kp);
+        if (!brk && ((nd.w >> (4 + bs)) & 1)) { node = __ldg(redge + 4 * (u64)node + bs); off = 0; kp -= K - 1; cov -= K - 1; }
+        else st = kp > last_kpos ? ST_DONE : ST_SEED;
       }
+    }
+  }
+  if (!valid) return;
+  if ((rr.hdr & 0xFF) == R_SUCCESS) {   // the read went through map_read_with_mismatch
+    if (!acc.any) rr.hdr = R_NO_MATCH;                                                  // src/align.rs:987
+    else {
+      u32 ecl = acc.ec_len();
+      rr.score = (u16)cov; rr.mm = (u16)mm; rr.ec_len = ecl; rr.bsize = acc.big ? acc.alen : acc.bsize;
+      rr.ref = acc.big ? acc.aoff : acc.boff; rr.mask = acc.mask;
+      double norm = (double)cov / (double)n;
+      u32 reason;
+      if (cfg.discard_nonzero_mismatch && mm != 0) reason = R_NONZERO_MM;               // src/align.rs:971-973
+      else if (cov >= cfg.score_threshold && norm >= cfg.score_percent && ecl != 0) {    // src/filter/align.rs:17-45
+        if (cfg.discard_multiple_matches && ecl > 1) reason = R_MULTI;
+        else if (mm > cfg.num_mismatches) reason = R_ABOVE_MM;
+        else reason = R_SUCCESS | (1u << 8);
+      } else reason = R_SCORE_BELOW;
+      rr.hdr = reason | (acc.big ? (1u << 9) : 0u);
     }
   }
   b.rres[ri] = rr;
@@ -574,6 +648,29 @@ void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaS
 void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_pairs) k_resolve<<<blocks_for(b.n_pairs, 256), 256, 0, s>>>(b, t); }
 void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t, void* out, cudaStream_t s) {
   if (b.n_reads) k_export_reads<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, ix, t, (ReadOut*)out);
+}
+// occupied entries of the count table -> {key, count} rows; of the callset dictionary -> {slot, len, items[gcap]} rows
+__global__ void __launch_bounds__(256) k_compact_agg(Tables t, u64* out, u64 cap, unsigned long long* n_out) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx > t.agg_mask) return;
+  unsigned long long k = t.agg_key[idx];
+  if (!k) return;
+  unsigned long long at = atomicAdd(n_out, 1ULL);
+  if (at < cap) { out[2 * at] = k; out[2 * at + 1] = t.agg_cnt[idx]; }
+}
+__global__ void __launch_bounds__(256) k_compact_cs(Tables t, u32* out, u64 cap, unsigned long long* n_out) {
+  u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx > t.cs_mask) return;
+  if (!t.cs_tag[idx]) return;
+  unsigned long long at = atomicAdd(n_out, 1ULL);
+  if (at >= cap) return;
+  u32* r = out + at * (2 + t.gcap); u32 n = t.cs_len[idx];
+  r[0] = idx; r[1] = n;
+  for (u32 i = 0; i < n; i++) r[2 + i] = t.cs_items[(u64)idx * t.gcap + i];
+}
+void launch_compact(const Tables& t, u64* agg_out, u64 agg_cap, u32* cs_out, u64 cs_cap, unsigned long long* n_out2, cudaStream_t s) {
+  k_compact_agg<<<blocks_for(t.agg_mask + 1, 256), 256, 0, s>>>(t, agg_out, agg_cap, n_out2);
+  k_compact_cs<<<blocks_for((u64)t.cs_mask + 1, 256), 256, 0, s>>>(t, cs_out, cs_cap, n_out2 + 1);
 }
 void launch_rehash_keys(const Tables& o, const Tables& n, cudaStream_t s) { k_rehash_keys<<<blocks_for(o.key_mask + 1, 256), 256, 0, s>>>(o, n); }
 void launch_keys_export(const Tables& t, void* records, unsigned long long* n_out, u64 cap, u64 order_base, cudaStream_t s) {

@@ -87,6 +87,7 @@ void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const 
 void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s);
 void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s);
 void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s);
+void launch_compact(const Tables& t, u64* agg_out, u64 agg_cap, u32* cs_out, u64 cs_cap, unsigned long long* n_out2, cudaStream_t s);
 void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t, void* out, cudaStream_t s);
 void launch_rehash_keys(const Tables& old_t, const Tables& new_t, cudaStream_t s);
 void launch_keys_export(const Tables& t, void* records, unsigned long long* n_out, u64 cap, u64 order_base, cudaStream_t s);
