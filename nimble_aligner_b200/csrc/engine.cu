@@ -60,7 +60,7 @@ struct nb_ctx {
   const nb_index* hix = nullptr; const nb_library* lib = nullptr;
   nb_config hcfg; DevCfg dcfg; DevIndex dix; DevLib dlib;
   // index + library device copies
-  DBuf d_tkey, d_tval, d_unitig, d_node, d_redge, d_ledge, d_coloff, d_colids, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp;
+  DBuf d_tkey, d_tval, d_unitig, d_node, d_redge, d_ledge, d_coloff, d_colids, d_colmeta, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp;
   // options
   u64 max_batch_pairs = 1u << 20, arena_entries = 1u << 24, cs_slots = 1u << 18, key_slots = 1u << 22, agg_slots = 1u << 20;
   int count_work = 0; u32 min_read_len = 40;  // MIN_READ_LENGTH, src/align.rs:18 (tests pass 12, src/align.rs:1066)
@@ -69,7 +69,10 @@ struct nb_ctx {
   u32 gcap = 16;
   bool tables_ready = false;
   // staging + per-batch buffers
-  DBuf s_a[2], s_off[2], s_q[2], s_f[2], s_scope, s_cell, d_pk, d_lenfull, d_lentrim, d_rres, d_pres, d_rout;
+  // host batches: two staging sets filled on a copy stream so that the H2D of chunk i+1 overlaps the kernels of chunk i
+  struct Staging { DBuf a[2], off[2], q[2], f[2], scope, cell; cudaEvent_t copied = nullptr, consumed = nullptr; bool used = false; } stg[2];
+  int stg_next = 0; cudaStream_t cstream = nullptr;
+  DBuf d_pk, d_lenfull, d_lentrim, d_rres, d_pres, d_rout;
   // state
   int mode = -1;  // -1 unset, 0 whole-run scope (keys persist), 1 scoped (keys live for one batch)
   bool folded = false;
@@ -160,11 +163,13 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   c->device = device; c->hix = index; c->lib = lib;
   if (cuda_stream) c->stream = (cudaStream_t)cuda_stream; else { if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(NB_ERR_CUDA, "cudaStreamCreate failed"); } c->own_stream = true; }
   cudaStream_t s = c->stream;
+  if (cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking) != cudaSuccess) { nb_ctx_free(c); return fail(NB_ERR_CUDA, "cudaStreamCreate failed"); }
+  for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&c->stg[i].copied, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->stg[i].consumed, cudaEventDisableTiming) != cudaSuccess) { nb_ctx_free(c); return fail(NB_ERR_CUDA, "cudaEventCreate failed"); }
   int rc = NB_OK;
   auto up = [&](cudaError_t e) { if (e != cudaSuccess && rc == NB_OK) rc = fail(NB_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e)); };
   up(upload(c->d_tkey, index->table_key, s)); up(upload(c->d_tval, index->table_val, s)); up(upload(c->d_unitig, index->unitig, s));
   up(upload(c->d_node, index->node, s)); up(upload(c->d_redge, index->redge, s)); up(upload(c->d_ledge, index->ledge, s));
-  up(upload(c->d_coloff, index->col_off, s)); up(upload(c->d_colids, index->col_ids, s));
+  up(upload(c->d_coloff, index->col_off, s)); up(upload(c->d_colids, index->col_ids, s)); up(upload(c->d_colmeta, index->col_meta, s));
   up(upload(c->d_rowfid, lib->row_fid, s)); up(upload(c->d_rowrev, lib->row_rev, s)); up(upload(c->d_rowof, lib->row_of, s)); up(upload(c->d_featgroup, lib->feat_group, s));
   {  // entropy terms f*log2(f), f = c/n, for every read length n <= ENT_NMAX (src/utils.rs:96-119)
     const int N = nbk::ENT_NMAX;
@@ -176,7 +181,7 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   if (rc != NB_OK) { nb_ctx_free(c); return rc; }
   c->dix.tkey = (const u64*)c->d_tkey.p; c->dix.tval = (const u64*)c->d_tval.p; c->dix.tmask = index->table_mask; c->dix.unitig = (const u64*)c->d_unitig.p;
   c->dix.node = (const uint4*)c->d_node.p; c->dix.redge = (const uint4*)c->d_redge.p; c->dix.ledge = (const uint4*)c->d_ledge.p;
-  c->dix.col_off = (const u32*)c->d_coloff.p; c->dix.col_ids = (const u32*)c->d_colids.p;
+  c->dix.col_off = (const u32*)c->d_coloff.p; c->dix.col_ids = (const u32*)c->d_colids.p; c->dix.col_meta = (const uint4*)c->d_colmeta.p;
   c->dlib.row_fid = (const u32*)c->d_rowfid.p; c->dlib.row_rev = (const u8*)c->d_rowrev.p; c->dlib.row_of = (const u32*)c->d_rowof.p; c->dlib.feat_group = (const u32*)c->d_featgroup.p; c->dlib.n_rows = lib->n_rows();
   rc = apply_config(c, lib->cfg);
   if (rc != NB_OK) { nb_ctx_free(c); return rc; }
@@ -187,19 +192,23 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
 void nb_ctx_free(nb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->cstream) cudaStreamSynchronize(c->cstream);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_unitig, &c->d_node, &c->d_redge, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
+  DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_unitig, &c->d_node, &c->d_redge, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
                  &c->d_ent, &c->d_ls, &c->d_qp, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
-                 &c->s_a[0], &c->s_a[1], &c->s_off[0], &c->s_off[1], &c->s_q[0], &c->s_q[1], &c->s_f[0], &c->s_f[1], &c->s_scope, &c->s_cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout};
+                 &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].scope, &c->stg[0].cell,
+                 &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout};
   for (DBuf* b : all) b->release();
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (int i = 0; i < 2; i++) { if (c->stg[i].copied) cudaEventDestroy(c->stg[i].copied); if (c->stg[i].consumed) cudaEventDestroy(c->stg[i].consumed); }
+  if (c->cstream) cudaStreamDestroy(c->cstream);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
 int nb_ctx_set_config(nb_ctx* c, const nb_config* cfg) { if (!c || !cfg) return fail(NB_ERR_INVALID, "null argument"); CK(cudaSetDevice(c->device)); return apply_config(c, *cfg); }
-int nb_ctx_sync(nb_ctx* c) { if (!c) return fail(NB_ERR_INVALID, "null argument"); CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return NB_OK; }
+int nb_ctx_sync(nb_ctx* c) { if (!c) return fail(NB_ERR_INVALID, "null argument"); CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->cstream)); CK(cudaStreamSynchronize(c->stream)); return NB_OK; }
 
 int nb_ctx_set_option(nb_ctx* c, const char* name, uint64_t value) {
   if (!c || !name) return fail(NB_ERR_INVALID, "null argument");
@@ -240,28 +249,36 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   BatchDev b; memset(&b, 0, sizeof b);
   b.n_pairs = np; b.sides = sides; b.n_reads = (u32)nr; b.W = (max_len + 31) / 32 + 1; b.order_base = c->pairs_seen;
   const u8* src_a[2] = {bt->r1, bt->r2}; const u64* src_off[2] = {bt->r1_off, bt->r2_off}; const u8* src_q[2] = {bt->q1, bt->q2}; const u8* src_f[2] = {bt->flags1, bt->flags2};
+  nb_ctx::Staging* S = nullptr; cudaStream_t cs = s;
+  if (host) {
+    S = &c->stg[c->stg_next]; c->stg_next ^= 1; cs = c->cstream;
+    if (S->used) CK(cudaStreamWaitEvent(cs, S->consumed, 0));   // the kernels that read this staging set two chunks ago are done
+  }
+  // staging buffers may be in use on either stream: drain both before a buffer is re-allocated
+  auto ens = [&](DBuf& d, size_t bytes) -> cudaError_t { if (bytes <= d.cap) return cudaSuccess; cudaError_t e = cudaStreamSynchronize(c->cstream); if (e != cudaSuccess) return e; return d.ensure(bytes, s); };
   for (u32 sd = 0; sd < sides; sd++) {
     if (host) {
       u64 a0 = src_off[sd][p0], a1 = src_off[sd][p1];
-      CK(c->s_a[sd].ensure(a1 - a0 + 64, s)); CK(c->s_off[sd].ensure((np + 1) * 8, s));
-      if (a1 > a0) CK(cudaMemcpyAsync(c->s_a[sd].p, src_a[sd] + a0, a1 - a0, kind, s));
-      CK(cudaMemcpyAsync(c->s_off[sd].p, src_off[sd] + p0, (np + 1) * 8, kind, s));
-      b.a[sd] = (const u8*)c->s_a[sd].p - a0; b.off[sd] = (const u64*)c->s_off[sd].p;
-      if (src_q[sd]) { CK(c->s_q[sd].ensure(a1 - a0 + 64, s)); if (a1 > a0) CK(cudaMemcpyAsync(c->s_q[sd].p, src_q[sd] + a0, a1 - a0, kind, s)); b.q[sd] = (const u8*)c->s_q[sd].p - a0; }
-      if (src_f[sd]) { CK(c->s_f[sd].ensure(np, s)); CK(cudaMemcpyAsync(c->s_f[sd].p, src_f[sd] + p0, np, kind, s)); b.flags[sd] = (const u8*)c->s_f[sd].p; }
+      CK(ens(S->a[sd], a1 - a0 + 64)); CK(ens(S->off[sd], (np + 1) * 8));
+      if (a1 > a0) CK(cudaMemcpyAsync(S->a[sd].p, src_a[sd] + a0, a1 - a0, kind, cs));
+      CK(cudaMemcpyAsync(S->off[sd].p, src_off[sd] + p0, (np + 1) * 8, kind, cs));
+      b.a[sd] = (const u8*)S->a[sd].p - a0; b.off[sd] = (const u64*)S->off[sd].p;
+      if (src_q[sd]) { CK(ens(S->q[sd], a1 - a0 + 64)); if (a1 > a0) CK(cudaMemcpyAsync(S->q[sd].p, src_q[sd] + a0, a1 - a0, kind, cs)); b.q[sd] = (const u8*)S->q[sd].p - a0; }
+      if (src_f[sd]) { CK(ens(S->f[sd], np)); CK(cudaMemcpyAsync(S->f[sd].p, src_f[sd] + p0, np, kind, cs)); b.flags[sd] = (const u8*)S->f[sd].p; }
     } else {
       b.a[sd] = src_a[sd]; b.off[sd] = src_off[sd] + p0; b.q[sd] = src_q[sd]; b.flags[sd] = src_f[sd] ? src_f[sd] + p0 : nullptr;
     }
   }
   if (bt->scope_id) {
-    if (host) { CK(c->s_scope.ensure(np * 4, s)); CK(cudaMemcpyAsync(c->s_scope.p, bt->scope_id + p0, np * 4, kind, s)); b.scope = (const u32*)c->s_scope.p; }
+    if (host) { CK(ens(S->scope, np * 4)); CK(cudaMemcpyAsync(S->scope.p, bt->scope_id + p0, np * 4, kind, cs)); b.scope = (const u32*)S->scope.p; }
     else b.scope = bt->scope_id + p0;
     b.cell = b.scope;
     if (bt->cell_id) {
-      if (host) { CK(c->s_cell.ensure(np * 4, s)); CK(cudaMemcpyAsync(c->s_cell.p, bt->cell_id + p0, np * 4, kind, s)); b.cell = (const u32*)c->s_cell.p; }
+      if (host) { CK(ens(S->cell, np * 4)); CK(cudaMemcpyAsync(S->cell.p, bt->cell_id + p0, np * 4, kind, cs)); b.cell = (const u32*)S->cell.p; }
       else b.cell = bt->cell_id + p0;
     }
   }
+  if (host) { CK(cudaEventRecord(S->copied, cs)); CK(cudaStreamWaitEvent(s, S->copied, 0)); }
   CK(c->d_pk.ensure((size_t)b.W * nr * 8, s)); CK(c->d_lenfull.ensure(nr * 4, s)); CK(c->d_lentrim.ensure(nr * 4, s));
   CK(c->d_rres.ensure(nr * sizeof(nbk::ReadRes), s)); CK(c->d_pres.ensure(np * sizeof(nbk::PairRes), s));
   if (c->mode == 1) { CK(c->d_pslot.ensure(np * 8, s)); CK(c->d_pres2.ensure(np * sizeof(nbk::PairRes), s)); b.pslot = (u64*)c->d_pslot.p; b.pres2 = (nbk::PairRes*)c->d_pres2.p; }
@@ -269,7 +286,10 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   // key-table capacity
   if (c->mode == 0) {
     if (2 * (c->keys_upper + np) > c->key_slots) {
+      CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
+      nbk::launch_count_keys(make_tables(c), s); c->all_launches++;
       Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
+      CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
       c->keys_upper = h.n_keys;
       if (2 * (c->keys_upper + np) > c->key_slots) { rc = grow_keys(c, 2 * (c->keys_upper + np)); if (rc) return rc; }
     }
@@ -291,6 +311,7 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
     if (pairs_out) { nbk::launch_resolve(b, t, s); c->all_launches++; }
     CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s)); CK(cudaMemsetAsync(c->d_klast.p, 0, c->key_slots * 8, s));
   }
+  if (host) { CK(cudaEventRecord(S->consumed, s)); S->used = true; }
   cudaMemcpyKind okind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (reads_out) {
     CK(c->d_rout.ensure(nr * sizeof(nb_read_result), s));
@@ -438,7 +459,11 @@ int nb_ctx_kernel_stats(nb_ctx* c, double* o, int reset) {
 int nb_keys_export_count(nb_ctx* c, uint64_t* n) {
   if (!c || !n) return fail(NB_ERR_INVALID, "null argument");
   if (!c->tables_ready) { *n = 0; return NB_OK; }
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, c->stream));
+  nbk::launch_count_keys(make_tables(c), c->stream); c->all_launches++;
   Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
+  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, c->stream));
   *n = h.n_keys; return NB_OK;
 }
 int nb_keys_export(nb_ctx* c, void* dev_records, uint64_t cap, uint64_t pair_index_base) {

@@ -67,10 +67,14 @@ struct nb_index {
   std::vector<u64> unitig;     // 2-bit packed, base i at bits 2*(i&31) of word i>>5, 2 zero pad words
   std::vector<NodeRec> node;
   std::vector<u32> redge, ledge;  // 4 per node, NONE32 when absent
-  std::vector<u32> col_off, col_ids;
+  std::vector<u32> col_off, col_ids;   // colour c = col_ids[col_off[c] .. col_off[c+1]); universe lists are appended after the colours
+  // Per colour {uni_off, uni_size, mask_lo, mask_hi}: sequences that ever share a colour form components ("universes");
+  // for a component of <= 64 sequences every colour is a 64-bit mask over its sorted member list
+  // col_ids[uni_off .. uni_off+uni_size), so intersecting two colours is one AND.  uni_size == 0: list path only.
+  std::vector<u32> col_meta;
   u64 n_kmers = 0, unitig_bases = 0, n_sequences = 0;
   u64 device_bytes() const {
-    return table_key.size() * 16 + unitig.size() * 8 + node.size() * 16 + (redge.size() + ledge.size()) * 4 + (col_off.size() + col_ids.size()) * 4;
+    return table_key.size() * 16 + unitig.size() * 8 + node.size() * 16 + (redge.size() + ledge.size()) * 4 + (col_off.size() + col_ids.size() + col_meta.size()) * 4;
   }
 };
 

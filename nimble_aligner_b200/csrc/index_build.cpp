@@ -136,6 +136,30 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
       col[g] = c; prev_a = sig_a[g]; prev_b = sig_b[g]; prev_c = c;
     }
   }
+  {  // ---- 3b. universes: connected components of sequences under "share a colour"; small ones get bitmap colours
+    u32 n_col = (u32)ix->col_off.size() - 1, n_seq = (u32)seqs.size(), n_ids = ix->col_off[n_col];
+    std::vector<u32> parent(n_seq);
+    for (u32 i = 0; i < n_seq; i++) parent[i] = i;
+    auto find = [&](u32 x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (u32 c = 0; c < n_col; c++) { u32 r0 = find(ix->col_ids[ix->col_off[c]]); for (u32 k = ix->col_off[c] + 1; k < ix->col_off[c + 1]; k++) { u32 r = find(ix->col_ids[k]); if (r != r0) parent[r] = r0; } }
+    std::vector<u32> comp_size(n_seq, 0), comp_off(n_seq, NONE32), fill(n_seq, 0);
+    for (u32 i = 0; i < n_seq; i++) comp_size[find(i)]++;
+    std::vector<char> used(n_seq, 0);
+    for (u32 c = 0; c < n_col; c++) used[find(ix->col_ids[ix->col_off[c]])] = 1;   // only components that own a colour
+    u64 at = n_ids;
+    for (u32 i = 0; i < n_seq; i++) if (used[i] && comp_size[i] <= 64) { comp_off[i] = (u32)at; at += comp_size[i]; }
+    if (at >= 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "colour table exceeds 2^32 entries"); }
+    ix->col_ids.resize(at);
+    for (u32 i = 0; i < n_seq; i++) { u32 r = find(i); if (comp_off[r] != NONE32) ix->col_ids[comp_off[r] + fill[r]++] = i; }   // ascending ids
+    ix->col_meta.assign(4 * (size_t)n_col, 0);
+    for (u32 c = 0; c < n_col; c++) {
+      u32 r = find(ix->col_ids[ix->col_off[c]]);
+      if (comp_off[r] == NONE32) continue;
+      const u32* u = &ix->col_ids[comp_off[r]]; u32 us = comp_size[r]; u64 mask = 0; u32 j = 0;
+      for (u32 k = ix->col_off[c]; k < ix->col_off[c + 1]; k++) { while (u[j] != ix->col_ids[k]) j++; mask |= 1ULL << j; }
+      ix->col_meta[4 * (size_t)c] = comp_off[r]; ix->col_meta[4 * (size_t)c + 1] = us; ix->col_meta[4 * (size_t)c + 2] = (u32)mask; ix->col_meta[4 * (size_t)c + 3] = (u32)(mask >> 32);
+    }
+  }
   std::vector<Occ>().swap(sorted); std::vector<u64>().swap(gstart); std::vector<u64>().swap(sig_a); std::vector<u64>().swap(sig_b);
   // ---- 4. open-addressed table over distinct k-mers (value = distinct index for now)
   u64 slots = 16; while (slots < 2 * n) slots <<= 1;
@@ -234,7 +258,7 @@ int nb_index_build(const nb_library* lib, int n_threads, nb_index** out) {
 void nb_index_free(nb_index* ix) { delete ix; }
 int nb_index_stats(const nb_index* ix, uint64_t* o) {
   if (!ix || !o) return fail(NB_ERR_INVALID, "null argument");
-  o[0] = ix->n_kmers; o[1] = ix->node.size(); o[2] = ix->col_off.size() - 1; o[3] = ix->col_ids.size(); o[4] = ix->unitig_bases;
+  o[0] = ix->n_kmers; o[1] = ix->node.size(); o[2] = ix->col_off.size() - 1; o[3] = ix->col_off.back(); o[4] = ix->unitig_bases;
   o[5] = ix->table_key.size(); o[6] = ix->device_bytes(); o[7] = ix->n_sequences;
   return NB_OK;
 }

@@ -105,13 +105,26 @@ struct WorkCnt { u32 probes, nodes, bases, colour_elems; };
 
 // Running intersection of the colours of the visited unitigs.  "mask mode": survivors are a 64-bit mask over the
 // smallest-so-far colour list (<= 64 ids); "big mode": a private copy in the arena that shrinks in place.
+// "universe mode" (the fast path): the colour has a precomputed 64-bit mask over its component of <= 64 sequences
+// (col_meta), so the running intersection is one AND; colours of different components are disjoint.
 struct EcAcc {
-  const u32* col_off; const u32* col_ids; u32* arena; Counters* ctr; u64 arena_cap;
-  bool any, big; u32 last, prev2, base, bsize, alen; u64 boff, aoff, mask;
-  __device__ void init(const DevIndex& ix, const Tables& t) { col_off = ix.col_off; col_ids = ix.col_ids; arena = t.arena; ctr = t.ctr; arena_cap = t.arena_cap; any = big = false; last = prev2 = NONE32; base = NONE32; bsize = alen = 0; boff = aoff = 0; mask = 0; }
+  const u32* col_off; const u32* col_ids; const uint4* col_meta; u32* arena; Counters* ctr; u64 arena_cap;
+  bool any, big, uni; u32 last, prev2, base, bsize, alen; u64 boff, aoff, mask;
+  __device__ void init(const DevIndex& ix, const Tables& t) { col_off = ix.col_off; col_ids = ix.col_ids; col_meta = ix.col_meta; arena = t.arena; ctr = t.ctr; arena_cap = t.arena_cap; any = big = uni = false; last = prev2 = NONE32; base = NONE32; bsize = alen = 0; boff = aoff = 0; mask = 0; }
   __device__ void add(u32 cid, WorkCnt& wc) {
     if (cid == last) { return; }
     last = cid;
+    uint4 cm = __ldg(col_meta + cid);
+    if (cm.y) {   // bitmap colour
+      u64 cmask = (u64)cm.z | ((u64)cm.w << 32);
+      wc.colour_elems += (u32)__popcll(cmask);
+      if (!any) { any = true; uni = true; boff = cm.x; bsize = cm.y; mask = cmask; }
+      else if (uni) mask = (cm.x == (u32)boff) ? (mask & cmask) : 0ULL;
+      else if (big) alen = 0;          // list state vs. a colour of another (small) component: disjoint
+      else mask = 0;
+      return;
+    }
+    if (uni) { mask = 0; return; }     // small-component state vs. a colour of a big component: disjoint
     u32 o = __ldg(col_off + cid), s = __ldg(col_off + cid + 1) - o;
     wc.colour_elems += s;
     if (!any) {
@@ -413,7 +426,7 @@ __device__ __forceinline__ u64 key_insert(const Tables& t, u64 k0, u64 k1) {
   for (u64 probes = 0; probes <= t.key_mask; probes++) {
     // the 128-bit CAS is also the (atomic) read: a plain 16-byte load could be torn against a concurrent insert
     u64 o0, o1; cas128(t.key + h, k0, k1, o0, o1);
-    if (o0 == 0 && o1 == 0) { atomicAdd(&t.ctr->n_keys, 1ULL); return h; }
+    if (o0 == 0 && o1 == 0) return h;   // new key (unique keys are counted by k_fold / k_count_keys, not here: one hot counter would serialise)
     if (o0 == k0 && o1 == k1) return h;
     h = (h + 1) & t.key_mask;
   }
@@ -457,7 +470,8 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
     if (s + 32 <= n1) w = rd1.win(s);
     else if (s >= n1) w = rd2.win(s - n1);
     else { u32 c1 = n1 - s; w = rd1.win(s) & ((1ULL << (2 * c1)) - 1); if (n2) w |= rd2.win(0) << (2 * c1); }
-    h0 = mix64(h0 ^ w); h1 = mix64(h1 + w * 0x9FB21C651E98DF25ULL);
+    h0 = (h0 ^ w) * 0x9E3779B97F4A7C15ULL; h0 ^= h0 >> 29;          // two multiply-xorshift lanes, avalanche at the end
+    h1 = (h1 + w) * 0xC2B2AE3D27D4EB4FULL; h1 ^= h1 >> 31;
   }
   u32 scope = b.scope ? b.scope[p] : 0u;
   h0 = mix64(h0 ^ tot ^ ((u64)scope << 32)); h1 = mix64(h1 + (u64)tot * 0xD6E8FEB86659FD93ULL + scope);
@@ -561,7 +575,10 @@ __global__ void __launch_bounds__(256) k_fold(Tables t, const u32* cell_of_pair,
   u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (idx > t.key_mask) return;
   ulonglong2 k = t.key[idx];
-  if (k.x == 0 && k.y == 0) return;
+  bool occ = !(k.x == 0 && k.y == 0);
+  unsigned ob = __ballot_sync(__activemask(), occ);          // unique read_keys, one atomic per warp
+  if (occ && (threadIdx.x & 31) == (unsigned)(__ffs(ob) - 1)) atomicAdd(&t.ctr->n_keys, (unsigned long long)__popc(ob));
+  if (!occ) return;
   u64 v = t.kval[idx]; u32 cs = (u32)(v & 0xFFFFFFu);
   if ((v >> 24) == 0 || cs == CS_NONE) return;   // key never reached score_map (scoped batches register every key) / triaged
   u32 cell = cell_of_pair ? cell_of_pair[(v >> 24) - 1 - order_base] : 0u;
@@ -672,6 +689,14 @@ void launch_compact(const Tables& t, u64* agg_out, u64 agg_cap, u32* cs_out, u64
   k_compact_agg<<<blocks_for(t.agg_mask + 1, 256), 256, 0, s>>>(t, agg_out, agg_cap, n_out2);
   k_compact_cs<<<blocks_for((u64)t.cs_mask + 1, 256), 256, 0, s>>>(t, cs_out, cs_cap, n_out2 + 1);
 }
+__global__ void __launch_bounds__(256) k_count_keys(Tables t) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  bool occ = false;
+  if (idx <= t.key_mask) { ulonglong2 k = t.key[idx]; occ = !(k.x == 0 && k.y == 0); }
+  unsigned ob = __ballot_sync(0xFFFFFFFFu, occ);
+  if ((threadIdx.x & 31) == 0 && ob) atomicAdd(&t.ctr->n_keys, (unsigned long long)__popc(ob));
+}
+void launch_count_keys(const Tables& t, cudaStream_t s) { k_count_keys<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t); }
 void launch_rehash_keys(const Tables& o, const Tables& n, cudaStream_t s) { k_rehash_keys<<<blocks_for(o.key_mask + 1, 256), 256, 0, s>>>(o, n); }
 void launch_keys_export(const Tables& t, void* records, unsigned long long* n_out, u64 cap, u64 order_base, cudaStream_t s) {
   k_keys_export<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, (KeyRec*)records, n_out, cap, order_base);

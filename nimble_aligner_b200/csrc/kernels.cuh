@@ -34,6 +34,7 @@ struct DevIndex {
   const uint4* node;      // {start_lo, len, colour, lext | rext<<4 | start_hi<<8}
   const uint4* redge; const uint4* ledge;
   const u32* col_off; const u32* col_ids;
+  const uint4* col_meta;  // {uni_off, uni_size (0: none), mask_lo, mask_hi} per colour (host.hpp nb_index::col_meta)
 };
 struct DevLib { const u32* row_fid; const u8* row_rev; const u32* row_of; const u32* feat_group; u32 n_rows; };
 struct DevCfg {
@@ -89,6 +90,7 @@ void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaS
 void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s);
 void launch_compact(const Tables& t, u64* agg_out, u64 agg_cap, u32* cs_out, u64 cs_cap, unsigned long long* n_out2, cudaStream_t s);
 void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t, void* out, cudaStream_t s);
+void launch_count_keys(const Tables& t, cudaStream_t s);
 void launch_rehash_keys(const Tables& old_t, const Tables& new_t, cudaStream_t s);
 void launch_keys_export(const Tables& t, void* records, unsigned long long* n_out, u64 cap, u64 order_base, cudaStream_t s);
 void launch_keys_import(const Tables& t, const void* records, u64 n, cudaStream_t s);

@@ -362,3 +362,40 @@ def test_fastq_driver_and_tsv_format(tmp_path, c2):
     assert out.read_text() == want
     nb.process_fastq([str(tmp_path / "a_R1.fastq.gz"), str(tmp_path / "a_R2.fastq")], [str(lib_json)], [str(out)], "unstranded", 4)
     assert out.read_text() == want + want[len("feature\tscore\n"):]   # append, no second header
+
+
+def test_big_component_list_and_arena_paths():
+    """Components of > 64 sequences have no bitmap colours: exercises the list-mask path (colour <= 64 ids), the arena
+    path (colour > 64 ids) and their transitions, plus mixing with small components."""
+    Lbig = synth.SynthLibrary(seed=99, n_fam=2, n_all=90)
+    # make the 90 alleles of each family near-identical (2 SNPs each) so that most k-mers are shared by > 64 sequences
+    rng = np.random.default_rng(17)
+    for f in range(2):
+        base = Lbig.seqs[int(Lbig.off[f * 90]):int(Lbig.off[f * 90 + 1])].copy()
+        for a in range(90):
+            s = base.copy()
+            for pos in rng.integers(0, len(s), size=2):
+                s[pos] = ord("ACGT"[(("ACGT".index(chr(s[pos]))) + 1 + int(rng.integers(3))) % 4])
+            Lbig.seqs[int(Lbig.off[f * 90 + a]):int(Lbig.off[f * 90 + a + 1])] = s
+    Lsmall = synth.SynthLibrary(seed=5, n_fam=6, n_all=4)
+    obj = Lbig.to_json_obj()
+    so = Lsmall.to_json_obj()
+    for ci in range(len(obj[1]["columns"])):
+        obj[1]["columns"][ci] = obj[1]["columns"][ci] + [("S" + x if ci in (1, 2) else x) for x in so[1]["columns"][ci]]
+    for group_on, kw in (("family", {}), ("", dict(max_hits_to_report=60, discard_multi_hits=0)), ("", dict(max_hits_to_report=3))):
+        ocfg, oref, lib = make(obj, "unstranded", group_on)
+        ocfg.update(kw)
+        ix = nb.build_index(lib, 4)
+        st = ix.stats()
+        o = orc.Oracle(ocfg, oref)
+        assert o.index_dump() == ix.dump()
+        ctx = nb.Context(ix, lib)
+        for mm in (0, 2):
+            cfg = dict(ocfg, num_mismatches=mm)
+            o.set_config(**cfg)
+            r1, o1, r2, o2 = synth.pairs(Lbig, 0, 6000, seed=77, paired=True)
+            s1, so1, s2, so2 = synth.pairs(Lsmall, 0, 2000, seed=78, paired=True)
+            a1 = np.concatenate([r1[: int(o1[-1])], s1[: int(so1[-1])]]); a2 = np.concatenate([r2[: int(o2[-1])], s2[: int(so2[-1])]])
+            b1 = np.concatenate([o1, so1[1:] + o1[-1]]); b2 = np.concatenate([o2, so2[1:] + o2[-1]])
+            res, ref = compare(ctx, o, cfg, a1, b1, a2, b2)
+            assert ref["read_ec_len"].max() > 64      # the arena path really ran
