@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=2_000_000, help="pairs per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--chunk", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="N>1: check the merged counts against one GPU over the union of shards")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
@@ -275,7 +276,20 @@ def main():
         counts_dev = {tuple(cs): int(c) for _, cs, c in ctx.decode_counts(counts_dev)["rows"]}
         counts_host = {tuple(cs): int(c) for _, cs, c in ctx.decode_counts(counts_host)["rows"]}
     assert counts_host == counts_dev, "host-fed and device-resident runs disagree"
+    if args.verify and world > 1 and rank == 0:
+        # the merged multi-GPU counts must equal one GPU processing the union of all ranks' shards
+        vo1 = np.zeros(n * world + 1, dtype=np.uint64); vo2 = np.zeros(n * world + 1, dtype=np.uint64)
+        synth.lib().synth_pair_offsets(SEED, 0, n * world, READ_LEN, 0.1, vo1.ctypes.data, vo2.ctypes.data, cores)
+        v1 = np.empty(int(vo1[-1]) + 64, dtype=np.uint8); v2 = np.empty(int(vo2[-1]) + 64, dtype=np.uint8)
+        synth.pairs(L, 0, n * world, seed=SEED, threads=cores, out=(v1, v2))
+        vctx = nb.Context(ix, lib, device=local_rank, max_batch_pairs=args.chunk)
+        vctx.align_batch(v1, vo1, v2, vo2, max_read_len=READ_LEN)
+        union = {tuple(cs): int(c) for _, cs, c in vctx.counts()["rows"]}
+        assert union == counts_dev, "multi-GPU merge differs from the single-GPU result over the union of shards"
+        print("verify: %d-GPU merged counts == single-GPU counts over the union (%d callsets)" % (world, len(union)), file=sys.stderr)
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     value = n_reads * world / (ms_dev / 1e3)
     e2e = n_reads * world / (ms_host / 1e3)
@@ -319,6 +333,9 @@ def main():
                            "launch_ms": launch_ms, "kernel_share_of_step": ks["map_ms"] / (ms_dev * args.steps),
                            "work_per_read": {k: ref["work"][k] / (2.0 * m) for k in ("probes", "nodes", "bases", "colour_elems")}}
     print(json.dumps(out))
+    sys.stdout.flush()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
