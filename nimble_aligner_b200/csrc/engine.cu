@@ -3,6 +3,8 @@
 // with NB_ERR_CUDA when the device cannot be used.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -60,7 +62,7 @@ struct nb_ctx {
   const nb_index* hix = nullptr; const nb_library* lib = nullptr;
   nb_config hcfg; DevCfg dcfg; DevIndex dix; DevLib dlib;
   // index + library device copies
-  DBuf d_tkey, d_tval, d_unitig, d_node, d_redge, d_ledge, d_coloff, d_colids, d_colmeta, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp;
+  DBuf d_tkey, d_tval, d_unitig, d_node, d_redge, d_ledge, d_coloff, d_colids, d_colmeta, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp, d_mincov;
   // options
   u64 max_batch_pairs = 1u << 20, arena_entries = 1u << 24, cs_slots = 1u << 18, key_slots = 1u << 22, agg_slots = 1u << 20;
   int count_work = 0; u32 min_read_len = 40;  // MIN_READ_LENGTH, src/align.rs:18 (tests pass 12, src/align.rs:1066)
@@ -91,7 +93,7 @@ static Tables make_tables(nb_ctx* c) {
   t.key = (ulonglong2*)c->d_key.p; t.kval = (unsigned long long*)c->d_kval.p; t.klast = (unsigned long long*)c->d_klast.p; t.key_mask = c->key_slots - 1;
   t.agg_key = (unsigned long long*)c->d_aggkey.p; t.agg_cnt = (unsigned long long*)c->d_aggcnt.p; t.agg_mask = c->agg_slots - 1;
   t.arena = (u32*)c->d_arena.p; t.arena_cap = c->arena_entries; t.ctr = (Counters*)c->d_ctr.p;
-  t.ent = (const double*)c->d_ent.p; t.ls = (const i64*)c->d_ls.p; t.qp = (const i64*)c->d_qp.p;
+  t.ent = (const double*)c->d_ent.p; t.ls = (const i64*)c->d_ls.p; t.qp = (const i64*)c->d_qp.p; t.mincov = (const u16*)c->d_mincov.p;
   return t;
 }
 
@@ -110,6 +112,9 @@ static int apply_config(nb_ctx* c, const nb_config& cfg) {
   d.discard_multi_hits = (u32)cfg.discard_multi_hits; d.max_hits = (u32)cfg.max_hits_to_report; d.gcap = c->gcap; d.min_read_len = c->min_read_len;
   std::vector<i64> ls, qp; build_maxinfo_tables(cfg.trim_target_length, cfg.trim_strictness, ls, qp);
   CK(upload(c->d_ls, ls, c->stream)); CK(upload(c->d_qp, qp, c->stream));
+  std::vector<u16> mincov(nbk::ENT_NMAX + 1, 0);
+  for (int n = 1; n <= nbk::ENT_NMAX; n++) { int m = n + 1; for (int k = 0; k <= n; k++) if ((double)k / (double)n >= cfg.score_percent) { m = k; break; } mincov[n] = (u16)m; }
+  CK(upload(c->d_mincov, mincov, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return NB_OK;
 }
@@ -120,7 +125,6 @@ static int alloc_tables(nb_ctx* c) {
   c->dcfg.gcap = c->gcap;
   CK(c->d_cstag.ensure(c->cs_slots * 8, s)); CK(c->d_cslen.ensure(c->cs_slots * 4, s)); CK(c->d_csitems.ensure(c->cs_slots * (size_t)c->gcap * 4, s));
   CK(c->d_key.ensure(c->key_slots * 16, s)); CK(c->d_kval.ensure(c->key_slots * 8, s)); CK(c->d_klast.ensure(c->key_slots * 8, s));
-  CK(cudaMemsetAsync(c->d_klast.p, 0, c->key_slots * 8, s));
   CK(c->d_aggkey.ensure(c->agg_slots * 8, s)); CK(c->d_aggcnt.ensure(c->agg_slots * 8, s));
   CK(c->d_arena.ensure(c->arena_entries * 4, s)); CK(c->d_ctr.ensure(sizeof(Counters), s)); CK(c->d_nout.ensure(64, s));
   CK(cudaMemsetAsync(c->d_cstag.p, 0, c->cs_slots * 8, s)); CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s));
@@ -195,7 +199,7 @@ void nb_ctx_free(nb_ctx* c) {
   if (c->cstream) cudaStreamSynchronize(c->cstream);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_unitig, &c->d_node, &c->d_redge, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
-                 &c->d_ent, &c->d_ls, &c->d_qp, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
+                 &c->d_ent, &c->d_ls, &c->d_qp, &c->d_mincov, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
                  &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].scope, &c->stg[0].cell,
                  &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout};
   for (DBuf* b : all) b->release();
@@ -248,6 +252,7 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   BatchDev b; memset(&b, 0, sizeof b);
   b.n_pairs = np; b.sides = sides; b.n_reads = (u32)nr; b.W = (max_len + 31) / 32 + 1; b.order_base = c->pairs_seen;
+  if (nr * (u64)b.W >= 0xFFFFFFFFull) return fail(NB_ERR_INVALID, "max_batch_pairs too large for this read length: lower option max_batch_pairs");
   const u8* src_a[2] = {bt->r1, bt->r2}; const u64* src_off[2] = {bt->r1_off, bt->r2_off}; const u8* src_q[2] = {bt->q1, bt->q2}; const u8* src_f[2] = {bt->flags1, bt->flags2};
   nb_ctx::Staging* S = nullptr; cudaStream_t cs = s;
   if (host) {
@@ -296,7 +301,7 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
     c->keys_upper += np;
   } else if (2 * np > c->key_slots) { int rc = grow_keys(c, 2 * np); if (rc) return rc; }
   Tables t = make_tables(c);
-  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->arena_top, 0, 8, s));
+  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->arena_top, 0, 16, s));   // arena_top + queue
   nbk::launch_pack(b, s); c->all_launches++;
   if (b.q[0] || b.q[1]) { nbk::launch_trim(b, t, s); c->all_launches++; }
   std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -335,7 +340,7 @@ int nb_align_batch(nb_ctx* c, const nb_batch* bt, nb_read_result* reads_out, nb_
   if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
   if (c->folded) return fail(NB_ERR_INVALID, "counts were finalized; call nb_counts_reset before aligning more batches");
   int mode = bt->scope_id ? 1 : 0;
-  if (c->mode == -1) c->mode = mode;
+  if (c->mode == -1) { c->mode = mode; if (mode == 1) CK(cudaMemsetAsync(c->d_klast.p, 0, c->key_slots * 8, c->stream)); }   // klast is only used by scoped batches
   else if (c->mode != mode) return fail(NB_ERR_INVALID, "cannot mix scoped and whole-run batches in one context without nb_counts_reset");
   if (bt->n_pairs == 0) return NB_OK;
   u32 max_len = bt->max_read_len;
@@ -443,6 +448,7 @@ int nb_ctx_work_counters(nb_ctx* c, uint64_t* out4) {
   if (!c->tables_ready) { out4[0] = out4[1] = out4[2] = out4[3] = 0; return NB_OK; }
   Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
   out4[0] = h.probes; out4[1] = h.nodes; out4[2] = h.bases; out4[3] = h.colour_elems;
+  if (getenv("NB_DEBUG_KMAP")) fprintf(stderr, "k_map dbg: iters=%llu walk_lanes=%llu seed_stages=%llu reseed_lanes=%llu ring_sum=%llu drained_iters=%llu\n", h.dbg[0], h.dbg[1], h.dbg[2], h.dbg[3], h.dbg[4], h.dbg[5]);
   return NB_OK;
 }
 

@@ -15,6 +15,7 @@
 #include <unordered_map>
 
 #include "host.hpp"
+#include "khash.h"
 
 using namespace nb;
 
@@ -34,10 +35,32 @@ void parallel_for(int n_threads, u64 n, const std::function<void(u64, u64, int)>
   for (auto& x : th) x.join();
 }
 
+// Bucketed cuckoo table: two candidate buckets of two slots each (nb_cuckoo_buckets), so a lookup is exactly two
+// 16-byte loads and four compares — no probe loop (the device k_map is issue/divergence bound, not bandwidth bound).
 struct Table {
-  std::vector<u64>& key; std::vector<u64>& val; u64 mask;
+  std::vector<u64>& key; std::vector<u64>& val; u64 bmask;
   // returns slot of kmer (device form) or ~0
-  u64 find(u64 dk) const { u64 h = mix64(dk) & mask; for (;;) { u64 k = key[h]; if (!(k >> 63)) return ~0ULL; if ((k & KMASK) == dk) return h; h = (h + 1) & mask; } }
+  u64 find(u64 dk) const {
+    u32 b1, b2; nb_cuckoo_buckets(dk, bmask, b1, b2); u64 want = dk | (1ULL << 63);
+    if (key[2 * (u64)b1] == want) return 2 * (u64)b1;
+    if (key[2 * (u64)b1 + 1] == want) return 2 * (u64)b1 + 1;
+    if (key[2 * (u64)b2] == want) return 2 * (u64)b2;
+    if (key[2 * (u64)b2 + 1] == want) return 2 * (u64)b2 + 1;
+    return ~0ULL;
+  }
+  // sequential cuckoo insertion (random-walk eviction); false if a cycle could not be resolved
+  bool insert(u64 dk, u64 v) {
+    u64 k = dk | (1ULL << 63); u64 rng = dk * 0x9E3779B97F4A7C15ULL + 1;
+    for (int kick = 0; kick < 500; kick++) {
+      u32 b1, b2; nb_cuckoo_buckets(k & KMASK, bmask, b1, b2);
+      u64 cand[4] = {2 * (u64)b1, 2 * (u64)b1 + 1, 2 * (u64)b2, 2 * (u64)b2 + 1};
+      for (u64 c : cand) if (!key[c]) { key[c] = k; val[c] = v; return true; }
+      rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+      u64 c = cand[rng & 3];
+      std::swap(k, key[c]); std::swap(v, val[c]);
+    }
+    return false;
+  }
 };
 
 }  // namespace
@@ -161,18 +184,17 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
     }
   }
   std::vector<Occ>().swap(sorted); std::vector<u64>().swap(gstart); std::vector<u64>().swap(sig_a); std::vector<u64>().swap(sig_b);
-  // ---- 4. open-addressed table over distinct k-mers (value = distinct index for now)
+  // ---- 4. bucketed cuckoo table over distinct k-mers (value = distinct index for now), load <= 0.5
   u64 slots = 16; while (slots < 2 * n) slots <<= 1;
-  ix->table_mask = slots - 1;
-  ix->table_key.assign(slots, 0); ix->table_val.assign(slots, 0);
-  {
-    std::atomic<u64>* keys = reinterpret_cast<std::atomic<u64>*>(ix->table_key.data());
-    parallel_for(n_threads, n, [&](u64 a, u64 b, int) {
-      for (u64 g = a; g < b; g++) {
-        u64 dk = to_device_form(kmers[g]) | (1ULL << 63); u64 h = mix64(dk & KMASK) & ix->table_mask;
-        for (;;) { u64 expect = 0; if (keys[h].compare_exchange_strong(expect, dk, std::memory_order_relaxed)) { ix->table_val[h] = g; break; } h = (h + 1) & ix->table_mask; }
-      }
-    });
+  for (;;) {
+    if (slots / 2 - 1 > 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "k-mer table exceeds 2^33 slots"); }
+    ix->table_mask = slots / 2 - 1;   // bucket mask
+    ix->table_key.assign(slots, 0); ix->table_val.assign(slots, 0);
+    Table tb{ix->table_key, ix->table_val, ix->table_mask};
+    bool ok = true;
+    for (u64 g = 0; g < n && ok; g++) ok = tb.insert(to_device_form(kmers[g]), g);
+    if (ok) break;
+    slots <<= 1;                      // practically never at load <= 0.5 with 2x2 cuckoo (threshold ~0.9)
   }
   Table tab{ix->table_key, ix->table_val, ix->table_mask};
   auto index_of = [&](u64 be) -> u64 { u64 s = tab.find(to_device_form(be)); return s == ~0ULL ? ~0ULL : ix->table_val[s]; };

@@ -2,6 +2,7 @@
 #include <float.h>
 
 #include "kernels.cuh"
+#include "khash.h"
 
 namespace nbk {
 
@@ -28,10 +29,10 @@ __device__ __forceinline__ u64 rev2(u64 x) {  // reverse the order of the 32 2-b
 }
 
 __global__ void __launch_bounds__(256) k_pack(BatchDev b) {
-  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-  if (idx >= (u64)b.n_reads * b.W) return;
-  u32 ri = (u32)(idx / b.W), w = (u32)(idx % b.W);
-  u32 side = ri % b.sides; u64 p = ri / b.sides;
+  u32 idx = blockIdx.x * blockDim.x + threadIdx.x;         // n_reads * W < 2^32 (checked by the host)
+  if (idx >= b.n_reads * b.W) return;
+  u32 ri = idx / b.W, w = idx - ri * b.W;                  // 32-bit divide by a small runtime constant
+  u32 side = b.sides == 2 ? (ri & 1) : 0; u64 p = b.sides == 2 ? (ri >> 1) : ri;
   u64 o0 = b.off[side][p]; u32 len = (u32)(b.off[side][p + 1] - o0);
   bool rc = b.flags[side] != nullptr && (b.flags[side][p] & 2);
   if (w == 0) { b.len_full[ri] = len; b.len_trim[ri] = len; }
@@ -55,14 +56,14 @@ __global__ void __launch_bounds__(256) k_pack(BatchDev b) {
     if (cnt < 32) word &= (1ULL << (2 * cnt)) - 1;
     if (rc) { word = rev2(word) >> (64 - 2 * cnt); word ^= cnt < 32 ? ((1ULL << (2 * cnt)) - 1) : ~0ULL; }
   }
-  b.pk[(u64)w * b.n_reads + ri] = word;
+  b.pk[(u64)ri * b.W + w] = word;
 }
 
 // ------------------------------------------------------------------------------------------------ K1 trim (maxinfo)
 __global__ void __launch_bounds__(256) k_trim(BatchDev b, Tables t) {
   u32 ri = blockIdx.x * blockDim.x + threadIdx.x;
   if (ri >= b.n_reads) return;
-  u32 side = ri % b.sides; u64 p = ri / b.sides;
+  u32 side = b.sides == 2 ? (ri & 1) : 0; u64 p = b.sides == 2 ? (ri >> 1) : ri;
   if (b.q[side] == nullptr) return;
   u64 o0 = b.off[side][p]; u32 len = (u32)(b.off[side][p + 1] - o0);
   bool rc = b.flags[side] != nullptr && (b.flags[side][p] & 2);
@@ -80,9 +81,9 @@ __global__ void __launch_bounds__(256) k_trim(BatchDev b, Tables t) {
 }
 
 // ------------------------------------------------------------------------------------------------ K2 map
-struct ReadView {
-  const u64* p; u32 stride;
-  __device__ __forceinline__ u64 word(u32 w) const { return __ldg(p + (u64)w * stride); }
+struct ReadView {   // one packed read: W consecutive words (read-major layout, zero padded)
+  const u64* p;
+  __device__ __forceinline__ u64 word(u32 w) const { return __ldg(p + w); }
   __device__ __forceinline__ u64 win(u32 pos) const {
     u32 w = pos >> 5, sh = (pos & 31) * 2; u64 lo = word(w);
     if (!sh) return lo;
@@ -111,6 +112,7 @@ struct EcAcc {
   const u32* col_off; const u32* col_ids; const uint4* col_meta; u32* arena; Counters* ctr; u64 arena_cap;
   bool any, big, uni; u32 last, prev2, base, bsize, alen; u64 boff, aoff, mask;
   __device__ void init(const DevIndex& ix, const Tables& t) { col_off = ix.col_off; col_ids = ix.col_ids; col_meta = ix.col_meta; arena = t.arena; ctr = t.ctr; arena_cap = t.arena_cap; any = big = uni = false; last = prev2 = NONE32; base = NONE32; bsize = alen = 0; boff = aoff = 0; mask = 0; }
+  __device__ void reset() { any = big = uni = false; last = prev2 = NONE32; base = NONE32; bsize = alen = 0; boff = aoff = 0; mask = 0; }
   __device__ void add(u32 cid, WorkCnt& wc) {
     if (cid == last) { return; }
     last = cid;
@@ -201,178 +203,7 @@ __device__ __forceinline__ void cmp_bwd(const u64* U, u64 uhi, const ReadView& r
   }
 }
 
-__device__ __forceinline__ bool find_seed(const DevIndex& ix, const ReadView& rd, u32& kp, u32 last_kpos, u32& node, u32& off, WorkCnt& wc) {
-  while (kp <= last_kpos) {  // seeds at stride 3 [App. B]
-    u64 km = rd.win(kp) & KMASK;
-    u64 h = mix64(km) & ix.tmask;
-    wc.probes++;
-    for (;;) {
-      u64 k = __ldg(ix.tkey + h);
-      if (!(k >> 63)) break;
-      if ((k & KMASK) == km) { u64 v = __ldg(ix.tval + h); node = (u32)v; off = (u32)(v >> 32); return true; }
-      h = (h + 1) & ix.tmask;
-    }
-    kp += 3;
-  }
-  return false;
-}
-
-// One table probe for the k-mer starting at `pos` (linear probing over 8-byte keys; load factor <= 0.5)
-__device__ __forceinline__ bool probe_kmer(const DevIndex& ix, const ReadView& rd, u32 pos, u32& node, u32& off) {
-  u64 km = rd.win(pos) & KMASK;
-  u64 h = mix64(km) & ix.tmask;
-  for (;;) {
-    u64 k = __ldg(ix.tkey + h);
-    if (!(k >> 63)) return false;
-    if ((k & KMASK) == km) { u64 v = __ldg(ix.tval + h); node = (u32)v; off = (u32)(v >> 32); return true; }
-    h = (h + 1) & ix.tmask;
-  }
-}
-
-// k_map is a warp-synchronous state machine, one read per lane:
-//   ST_SEED  the lane needs a seed at/after kp: two per-lane probes (the common hit), then the whole warp searches the
-//            remaining stride-3 seeds of that lane 32 at a time (off-target reads would otherwise hold the warp for
-//            ~41 serial probes) — first hit in seed order wins, exactly the sequential search of App. B;
-//   ST_WALK  one unitig per iteration: colour, base compare with the per-node mismatch budget, edge follow / re-seed.
-enum { ST_DONE = 0, ST_SEED = 1, ST_WALK = 2 };
-
-template <int COUNT_WORK>
-__global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg, Tables t) {
-  const unsigned FULL = 0xFFFFFFFFu;
-  const u32 lane = threadIdx.x & 31;
-  u32 ri = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = ri < b.n_reads;
-  if (!valid) ri = b.n_reads - 1;               // keep the lane in the warp-collective steps; it never stores
-  u32 side = ri % b.sides; u64 p = ri / b.sides;
-  ReadRes rr; rr.hdr = R_SUCCESS; rr.score = 0; rr.mm = 0; rr.ec_len = 0; rr.bsize = 0; rr.ref = 0; rr.mask = 0;
-  WorkCnt wc = {0, 0, 0, 0};
-  u32 n = b.len_trim[ri];
-  bool skip = b.flags[side] != nullptr && (b.flags[side][p] & 1);
-  ReadView rd{b.pk + ri, b.n_reads};
-  int st = ST_DONE;
-  if (!valid) { }
-  else if (skip) { rr.hdr = R_SKIPPED | (1u << 10); }                                   // src/align.rs:527-528
-  else if (n < cfg.min_read_len) { rr.hdr = R_SHORT; }                                 // src/align.rs:955-957
-  else {
-    // shannon_entropy on the (trimmed) read, src/utils.rs:96-119; terms come from a host-built table of
-    // f*log2(f) (same libm as the CPU reference), summed in the reference's A,T,C,G order.
-    u32 cC = 0, cG = 0, cT = 0;
-    for (u32 w = 0; w * 32 < n; w++) {
-      u64 x = rd.word(w); u32 c = min(32u, n - w * 32);
-      u64 lo = x & 0x5555555555555555ULL, hi = (x >> 1) & 0x5555555555555555ULL;
-      u64 vm = c < 32 ? ((1ULL << (2 * c)) - 1) & 0x5555555555555555ULL : 0x5555555555555555ULL;
-      cC += __popcll(lo & ~hi & vm); cG += __popcll(hi & ~lo & vm); cT += __popcll(hi & lo & vm);
-    }
-    u32 cA = n - cC - cG - cT;
-    const double* et = t.ent + (size_t)n * (n + 1) / 2;
-    double e = 0.0;
-    if (cA) e += et[cA];
-    if (cT) e += et[cT];
-    if (cC) e += et[cC];
-    if (cG) e += et[cG];
-    if (-e < 1.75) rr.hdr = R_ENTROPY;                                                  // src/align.rs:960-962
-    else if (n >= (u32)K) st = ST_SEED;                                                 // n < k: map_read returns None
-    else rr.hdr = R_NO_MATCH;
-  }
-  EcAcc acc; acc.init(ix, t);
-  u32 cov = 0, mm = 0; const u32 allowed = cfg.num_mismatches;
-  const u32 last_kpos = n >= (u32)K ? n - K : 0;
-  u32 kp = 0, node = 0, off = 0; bool first = true;
-  const u32* redge = (const u32*)ix.redge; const u32* ledge = (const u32*)ix.ledge;
-  while (__any_sync(FULL, st != ST_DONE)) {
-    // ---- (A) per-lane probes: the seed at kp and the next one
-    if (st == ST_SEED) {
-#pragma unroll 1
-      for (int tries = 0; tries < 2 && st == ST_SEED; tries++) {
-        if (kp > last_kpos) { st = ST_DONE; break; }
-        wc.probes++;
-        if (probe_kmer(ix, rd, kp, node, off)) st = ST_WALK; else kp += 3;
-      }
-      if (st == ST_SEED && kp > last_kpos) st = ST_DONE;
-    }
-    // ---- (B) warp-cooperative search for the lanes that are still looking
-    unsigned need = __ballot_sync(FULL, st == ST_SEED);
-    while (need) {
-      int l = __ffs(need) - 1; need &= need - 1;
-      u32 s_kp = __shfl_sync(FULL, kp, l), s_last = __shfl_sync(FULL, last_kpos, l), s_ri = __shfl_sync(FULL, ri, l);
-      ReadView srd{b.pk + s_ri, b.n_reads};
-      u32 f_kp = NONE32, f_node = 0, f_off = 0, tried = 0;
-      for (u32 base = s_kp; base <= s_last; base += 96) {
-        u32 my = base + 3 * lane, nd2 = 0, of2 = 0;
-        bool hit = my <= s_last && probe_kmer(ix, srd, my, nd2, of2);
-        unsigned hb = __ballot_sync(FULL, hit);
-        if (hb) { int f = __ffs(hb) - 1; f_node = __shfl_sync(FULL, nd2, f); f_off = __shfl_sync(FULL, of2, f); f_kp = base + 3 * f; tried += f + 1; break; }
-        tried += min(32u, (s_last - base) / 3 + 1);
-      }
-      if ((int)lane == l) {
-        wc.probes += tried;                     // same count as the sequential search: seeds up to and including the hit
-        if (f_kp != NONE32) { kp = f_kp; node = f_node; off = f_off; st = ST_WALK; } else st = ST_DONE;
-      }
-    }
-    // ---- (C) left extension, only after the first seed and only if it sits at >= 20 % of the read [App. B]
-    if (st == ST_WALK && first) {
-      first = false;
-      u32 lthr = (u32)(0.2 * (double)n);
-      if (kp >= lthr) {
-        u32 lp = kp - 1, pn = node, po = off > 0 ? off - 1 : 0;
-        for (;;) {
-          uint4 nd = __ldg(ix.node + pn);
-          u64 start = (u64)nd.x | ((u64)(nd.w >> 8) << 32);
-          u32 m = min(lp + 1, po + 1), mb, snp; bool brk;
-          cmp_bwd(ix.unitig, start + po, rd, lp, m, allowed, mb, snp, brk);
-          mm += snp; cov += mb; wc.bases += mb + (brk ? 1 : 0);
-          if (lp + 1 - mb == 0 || brk) break;
-          lp -= mb;
-          u32 bs = rd.base(lp);
-          if ((nd.w >> bs) & 1) {
-            pn = __ldg(ledge + 4 * (u64)pn + bs);
-            uint4 n2 = __ldg(ix.node + pn);
-            po = n2.y - K; acc.add(n2.z, wc); wc.nodes++;
-          } else break;
-        }
-      }
-    }
-    first = first && st != ST_DONE;
-    // ---- (D) one unitig of the forward walk
-    if (st == ST_WALK) {
-      uint4 nd = __ldg(ix.node + node);
-      u64 start = (u64)nd.x | ((u64)(nd.w >> 8) << 32);
-      kp += K; cov += K; acc.add(nd.z, wc); wc.nodes++;
-      u32 ro = off + K, m = min(n - kp, nd.y - ro), mb, snp; bool brk;
-      cmp_fwd(ix.unitig, start + ro, rd, kp, m, allowed, mb, snp, brk);
-      mm += snp; cov += mb; kp += mb; wc.bases += mb + (brk ? 1 : 0);
-      if (kp >= n) st = ST_DONE;
-      else {
-        u32 bs = rd.base(kp);
-        if (!brk && ((nd.w >> (4 + bs)) & 1)) { node = __ldg(redge + 4 * (u64)node + bs); off = 0; kp -= K - 1; cov -= K - 1; }
-        else st = kp > last_kpos ? ST_DONE : ST_SEED;
-      }
-    }
-  }
-  if (!valid) return;
-  if ((rr.hdr & 0xFF) == R_SUCCESS) {   // the read went through map_read_with_mismatch
-    if (!acc.any) rr.hdr = R_NO_MATCH;                                                  // src/align.rs:987
-    else {
-      u32 ecl = acc.ec_len();
-      rr.score = (u16)cov; rr.mm = (u16)mm; rr.ec_len = ecl; rr.bsize = acc.big ? acc.alen : acc.bsize;
-      rr.ref = acc.big ? acc.aoff : acc.boff; rr.mask = acc.mask;
-      double norm = (double)cov / (double)n;
-      u32 reason;
-      if (cfg.discard_nonzero_mismatch && mm != 0) reason = R_NONZERO_MM;               // src/align.rs:971-973
-      else if (cov >= cfg.score_threshold && norm >= cfg.score_percent && ecl != 0) {    // src/filter/align.rs:17-45
-        if (cfg.discard_multiple_matches && ecl > 1) reason = R_MULTI;
-        else if (mm > cfg.num_mismatches) reason = R_ABOVE_MM;
-        else reason = R_SUCCESS | (1u << 8);
-      } else reason = R_SCORE_BELOW;
-      rr.hdr = reason | (acc.big ? (1u << 9) : 0u);
-    }
-  }
-  b.rres[ri] = rr;
-  if (COUNT_WORK) {
-    atomicAdd(&t.ctr->probes, (unsigned long long)wc.probes); atomicAdd(&t.ctr->nodes, (unsigned long long)wc.nodes);
-    atomicAdd(&t.ctr->bases, (unsigned long long)wc.bases); atomicAdd(&t.ctr->colour_elems, (unsigned long long)wc.colour_elems);
-  }
-}
+#include "kmap.cuh"
 
 // ------------------------------------------------------------------------------------------------ K3 pair
 struct EcView { const u32* list; u64 mask; u32 lsize; u32 n; bool big; };
@@ -463,7 +294,7 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
   // ---- read_key = R1 string + R2 string (untrimmed, after revcomp), src/align.rs:576-579 — hashed to 128 bits over
   // the concatenated 2-bit stream so that, like the reference's string concatenation, only the joined bases matter.
   u32 n1 = b.len_full[ri1], n2 = paired ? b.len_full[ri1 + 1] : 0, tot = n1 + n2;
-  ReadView rd1{b.pk + ri1, b.n_reads}, rd2{b.pk + ri1 + 1, b.n_reads};
+  ReadView rd1{b.pk + (u64)ri1 * b.W}, rd2{b.pk + (u64)(ri1 + 1) * b.W};
   u64 h0 = 0x243F6A8885A308D3ULL, h1 = 0x13198A2E03707344ULL;
   for (u32 s = 0; s < tot; s += 32) {
     u64 w;
@@ -655,8 +486,13 @@ void launch_pack(const BatchDev& b, cudaStream_t s) { u64 n = (u64)b.n_reads * b
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_reads) k_trim<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, t); }
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s) {
   if (!b.n_reads) return;
-  if (count_work) k_map<1><<<blocks_for(b.n_reads, 128), 128, 0, s>>>(b, ix, cfg, t);
-  else k_map<0><<<blocks_for(b.n_reads, 128), 128, 0, s>>>(b, ix, cfg, t);
+  // persistent warps pulling reads from Counters::queue (zeroed by the host before the launch): enough blocks to fill
+  // every SM at the kernel's occupancy, never more than the work needs
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  unsigned blocks = min(blocks_for(b.n_reads, 128), (unsigned)(sms * 12));
+  if (count_work) k_map<1><<<blocks, 128, 0, s>>>(b, ix, cfg, t);
+  else k_map<0><<<blocks, 128, 0, s>>>(b, ix, cfg, t);
 }
 void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s) {
   if (b.n_pairs) k_pair<<<blocks_for(b.n_pairs, 128), 128, 0, s>>>(b, ix, lib, cfg, t);

@@ -45,9 +45,11 @@ struct DevCfg {
 // device-side error bits (Counters::err)
 enum { E_ARENA = 1, E_CS_FULL = 2, E_KEY_FULL = 4, E_FEATURE = 8, E_AGG_FULL = 16, E_GCAP = 32 };
 struct Counters {
-  unsigned long long arena_top; unsigned long long n_keys; unsigned long long n_callsets; unsigned long long n_agg;
+  unsigned long long arena_top; unsigned long long queue;   // both zeroed before every k_map launch
+  unsigned long long n_keys; unsigned long long n_callsets; unsigned long long n_agg;
   unsigned long long probes, nodes, bases, colour_elems;   // work counters (roofline numerator cross-check)
   unsigned int err; unsigned int pad;
+  unsigned long long dbg[8];   // k_map<COUNT_WORK=1> only: loop iterations, lanes walking, seed stages, lanes re-seeding, ...
 };
 
 // internal per-read record (32 B)
@@ -64,7 +66,7 @@ struct PairRes { u32 callset; u8 triage, fr1, fr2, insertable; u64 key_lo, key_h
 struct BatchDev {
   u64 n_pairs; u32 sides; u32 n_reads; u32 W;             // W words per read incl. one zero pad word
   const u8* a[2]; const u64* off[2]; const u8* q[2]; const u8* flags[2]; const u32* scope; const u32* cell;
-  u64* pk; u32* len_full; u32* len_trim;                  // pk[w * n_reads + ri], ri = p*sides + side
+  u64* pk; u32* len_full; u32* len_trim;                  // pk[ri * W + w] (read-major), ri = p*sides + side
   ReadRes* rres; PairRes* pres;
   u64* pslot; PairRes* pres2;                            // scoped batches: key slot per pair, per-key resolved records
   u64 order_base;
@@ -80,6 +82,7 @@ struct Tables {
   u32* arena; u64 arena_cap;
   Counters* ctr;
   const double* ent; const i64* ls; const i64* qp;
+  const u16* mincov;   // mincov[n] = smallest coverage c with (double)c / (double)n >= score_percent (exact stand-in for the f64 division)
 };
 
 void launch_pack(const BatchDev& b, cudaStream_t s);

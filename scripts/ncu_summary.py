@@ -18,6 +18,7 @@ for w in want:
             print("%-78s %-8s %s" % (c, units[i], [r[i][:28] for r in data]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
+OURS = ("kernels.cu", "kmap.cuh", "khash.h")
 cur = None; per = collections.OrderedDict(); hdr = None; fpath = None
 for r in rows:
     if r and r[0] == "File Path": fpath = r[1]
@@ -27,15 +28,17 @@ for r in rows:
     d = dict(zip(hdr, r))
     try: ln = int(d["Line No"])
     except: continue
-    if fpath and not fpath.endswith("kernels.cu"): ln = -abs(hash(fpath)) % 100000 - 100000   # fold other files (intrinsics headers) into one bucket per file
-    a = per[cur].setdefault(ln, [0.0, 0.0, 0.0])
+    base = (fpath or "").split("/")[-1]
+    if base not in OURS: ln = 0; base = "(toolkit headers)"
+    a = per[cur].setdefault((base, ln), [0.0, 0.0, 0.0])
     def f(x):
         try: return float(x)
         except Exception: return 0.0
     a[0] += f(d["Instructions Executed"]); a[1] += f(d["Thread Instructions Executed"]); a[2] += f(d["# Samples"])
-lines = open("nimble_aligner_b200/csrc/kernels.cu").read().split("\n")
+lines = {f: open("nimble_aligner_b200/csrc/" + f).read().split("\n") for f in OURS}
 for k, out in per.items():
     tot = sum(a[0] for a in out.values()) or 1; tots = sum(a[2] for a in out.values()) or 1
     print("\n== %s: inst=%d samples=%d" % (k, tot, tots))
-    for ln, (ie, te, smp) in sorted(out.items(), key=lambda x: -x[1][0])[:topn]:
-        print("%4d inst%%=%5.1f thr/inst=%5.1f samp%%=%5.1f | %s" % (ln, 100 * ie / tot, te / ie if ie else 0, 100 * smp / tots, lines[ln - 1].strip()[:105] if 0 < ln <= len(lines) else "(other file)"))
+    for (fn, ln), (ie, te, smp) in sorted(out.items(), key=lambda x: -x[1][0])[:topn]:
+        txt = lines[fn][ln - 1].strip()[:100] if fn in lines and 0 < ln <= len(lines[fn]) else ""
+        print("%-11s %4d inst%%=%5.1f thr/inst=%5.1f samp%%=%5.1f | %s" % (fn[:11], ln, 100 * ie / tot, te / ie if ie else 0, 100 * smp / tots, txt))
