@@ -196,6 +196,15 @@ int nb_write_fastq_tsv(const char* path, const nb_library* lib, const nb_counts*
 int nb_process_fastq(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,
                      uint32_t n_refs, int strand_filter, int num_cores, int device);
 
+/* process::bam::process (src/process/bam.rs:45-243) behind the same library loop: BGZF/BAM decode on host threads,
+ * UMIReader / SortedBamReader grouping (src/parse/bam.rs, src/parse/sorted_bam_reader.rs) with their quirks, one scoped
+ * batch per ~512k pairs, gzip TSV rows (header + row format of src/process/bam.rs:22-42, 90-121).  `trim`: the --trim
+ * option string "L:S,L:S,..." or NULL. */
+/* host-only: writes the (UMI, CB) groups the producer would send (one line per record) — parity tests of the feeder */
+int nb_bam_dump_groups(const char* input_file, int force_bam_paired, int num_cores, const char* out_path);
+int nb_process_bam(const char* input_file, const char* const* reference_json, const char* const* output_paths, uint32_t n_refs,
+                   int strand_filter, const char* trim, int num_cores, int force_bam_paired, int device);
+
 #ifdef __cplusplus
 }
 #endif

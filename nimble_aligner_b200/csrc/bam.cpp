@@ -1,0 +1,383 @@
+// bam.cpp — BAM-mode host pipeline: BGZF inflate on host threads, BAM record decode, UMI / cell-barcode grouping with the
+// reference's quirks, scoped batches into the device path, gzip TSV rows.
+//
+// Mirrors (paths under /root/reference):
+//   src/parse/sorted_bam_reader.rs:31-185  fill_buffer / add_dummy_paired_reads / filter_paired_reads / next
+//   src/parse/bam.rs:70-287                UMIReader: group key = UMI + CB[..len-2], 13-base TSO clip iff len == 124,
+//                                          38 metadata fields per record (BAM_FIELDS_TO_REPORT 9-49)
+//   src/process/bam.rs:45-243              producer loop (the last group is never sent when there are >= 2, 163-179),
+//                                          header + row format (22-42, 90-121), zero rows (329-353), reasons (356-396)
+// The reference runs cores-1 consumer threads over an mpsc channel; here one GPU context per library takes whole
+// batches of groups (scope_id = group number) and the row order is group order (the reference's order is arbitrary).
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_set>
+#include <vector>
+
+#include "host.hpp"
+
+using namespace nb;
+typedef int32_t i32;
+
+namespace {
+
+const char* FIELDS[38] = {"QNAME", "QUAL", "REVERSE", "MATE_REVERSE", "PAIRED", "PROPER_PAIRED", "PAIR_ORIENTATION", "UNMAPPED", "MATE_UNMAPPED",
+  "FIRST_IN_TEMPLATE", "LAST_IN_TEMPLATE", "STRAND", "MAPQ", "POS", "MATE_POS", "SEQ", "SEQ_LEN", "INSERT_SIZE", "QUALITY_FAILED", "SECONDARY",
+  "DUPLICATE", "SUPPLEMENTARY", "NH", "HI", "AS", "GN", "TX", "AN", "nM", "fx", "RE", "CR", "CY", "CB", "UR", "UY", "UB", "SKIP_ALIGN"};
+const size_t CLIP_LENGTH = 13;   // src/parse/bam.rs:7
+
+// ------------------------------------------------------------------ BGZF: all blocks located up front, inflated by a thread pool
+struct Bgzf {
+  std::vector<u8> file; std::vector<u8> data;   // compressed file image, inflated stream
+  int load(const std::string& path, int threads) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return fail(NB_ERR_IO, "could not open " + path);
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    file.resize((size_t)sz);
+    if (sz && fread(file.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(NB_ERR_IO, "short read on " + path); }
+    fclose(f);
+    struct Blk { size_t off, clen, uoff, ulen; };
+    std::vector<Blk> blks; size_t p = 0, utot = 0;
+    while (p + 18 <= file.size()) {
+      const u8* h = &file[p];
+      if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return fail(NB_ERR_PARSE, "not a BGZF file: " + path);
+      size_t xlen = h[10] | (h[11] << 8), q = p + 12, xend = q + xlen, bsize = 0;
+      while (q + 4 <= xend) { size_t slen = file[q + 2] | (file[q + 3] << 8); if (file[q] == 'B' && file[q + 1] == 'C' && slen == 2) bsize = (file[q + 4] | (file[q + 5] << 8)) + 1; q += 4 + slen; }
+      if (!bsize || p + bsize > file.size()) return fail(NB_ERR_PARSE, "corrupt BGZF block in " + path);
+      size_t isize = file[p + bsize - 4] | (file[p + bsize - 3] << 8) | (file[p + bsize - 2] << 16) | ((size_t)file[p + bsize - 1] << 24);
+      blks.push_back({xend, bsize - (xend - p) - 8, utot, isize});
+      utot += isize; p += bsize;
+    }
+    data.resize(utot);
+    std::atomic<size_t> next(0); std::atomic<int> bad(0);
+    auto work = [&]() {
+      for (;;) { size_t i = next.fetch_add(1); if (i >= blks.size()) break; const Blk& b = blks[i]; if (!b.ulen) continue;
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; continue; }
+        zs.next_in = &file[b.off]; zs.avail_in = (uInt)b.clen; zs.next_out = &data[b.uoff]; zs.avail_out = (uInt)b.ulen;
+        int rc = inflate(&zs, Z_FINISH); if (rc != Z_STREAM_END || zs.total_out != b.ulen) bad = 1;
+        inflateEnd(&zs); }
+    };
+    std::vector<std::thread> th; for (int t = 1; t < std::max(1, threads); t++) th.emplace_back(work);
+    work(); for (auto& t : th) t.join();
+    std::vector<u8>().swap(file);
+    if (bad) return fail(NB_ERR_PARSE, "BGZF inflate failed in " + path);
+    return NB_OK;
+  }
+};
+
+struct Rec {   // one decoded BAM record (views into Bgzf::data stay valid for the run)
+  const u8* p = nullptr;        // start of the fixed fields (after block_size)
+  u32 block = 0;
+  int skip_align = -1;          // the "SK" string aux the reference appends (sorted_bam_reader.rs:114-121): -1 absent (-p mode), 0 "FALSE", 1 "TRUE"
+  i32 refid() const { return rd32(0); } i32 pos() const { return rd32(4); }
+  u32 l_read_name() const { return p[8]; } u32 mapq() const { return p[9]; }
+  u32 n_cigar() const { return p[12] | (p[13] << 8); } u32 flag() const { return p[14] | (p[15] << 8); }
+  u32 l_seq() const { return (u32)rd32(16); } i32 mrefid() const { return rd32(20); } i32 mpos() const { return rd32(24); } i32 tlen() const { return rd32(28); }
+  i32 rd32(size_t o) const { i32 v; memcpy(&v, p + o, 4); return v; }
+  std::string qname() const { u32 l = l_read_name(); return std::string((const char*)p + 32, l ? l - 1 : 0); }
+  const u8* seq4() const { return p + 32 + l_read_name() + 4 * n_cigar(); }
+  const u8* qual() const { return seq4() + (l_seq() + 1) / 2; }
+  const u8* aux() const { return qual() + l_seq(); }
+  const u8* end() const { return p + block; }
+  bool is_paired() const { return flag() & 1; } bool is_reverse() const { return flag() & 16; } bool is_first() const { return flag() & 64; }
+  // Aux::String lookup by the first two bytes of `tag` (htslib bam_aux_get semantics)
+  bool aux_z(const char* tag, std::string& out) const {
+    const u8* a = aux(); const u8* e = end();
+    while (a + 3 <= e) {
+      char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2]; a += 3; const u8* v = a;
+      switch (ty) {
+        case 'A': case 'c': case 'C': a += 1; break; case 's': case 'S': a += 2; break; case 'i': case 'I': case 'f': a += 4; break;
+        case 'Z': case 'H': while (a < e && *a) a++; a++; break;
+        case 'B': { if (a + 5 > e) return false; char st = (char)a[0]; u32 n; memcpy(&n, a + 1, 4); size_t w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; a += 5 + w * n; break; }
+        default: return false;
+      }
+      if (t0 == tag[0] && t1 == tag[1]) { if (ty != 'Z') return false; out.assign((const char*)v); return true; }
+    }
+    return false;
+  }
+  std::string seq_ascii() const { static const char* T = "=ACMGRSVTWYHKDBN"; u32 n = l_seq(); std::string s(n, 'N'); const u8* q = seq4(); for (u32 i = 0; i < n; i++) s[i] = T[(q[i >> 1] >> ((~i & 1) << 2)) & 15]; return s; }
+};
+
+struct ParsedRec {   // what UMIReader keeps per record: clipped sequence, the 38 string fields, flags for the device
+  std::string seq;   // DnaString::from_acgt_bytes(clipped).to_string() (uppercase ACGT)
+  std::string qual;  // clipped raw Phred bytes, NOT reversed (the device reverses with NB_FLAG_REVCOMP); field 1 holds the reversed string
+  std::vector<std::string> f; bool reverse = false, skip = false;
+};
+
+std::string bstr(bool b) { return b ? "true" : "false"; }
+
+void parse_fields(const Rec& r, ParsedRec& o) {   // src/parse/bam.rs:186-236
+  bool rev = r.is_reverse(); o.reverse = rev; o.skip = r.skip_align == 1;
+  std::string raw = r.seq_ascii(); const u8* q = r.qual(); size_t n = raw.size();
+  size_t a = 0, b = n;
+  if (n == 124) { if (rev) b = n - CLIP_LENGTH; else a = CLIP_LENGTH; }                 // strip_nonbio_regions 258-268
+  o.seq.assign(b - a, 'A');
+  for (size_t i = a; i < b; i++) { char c = raw[i]; o.seq[i - a] = (c == 'C' || c == 'c') ? 'C' : (c == 'G' || c == 'g') ? 'G' : (c == 'T' || c == 't') ? 'T' : 'A'; }
+  o.qual.assign((const char*)q + a, b - a);
+  std::string qfield = o.qual; if (rev) std::reverse(qfield.begin(), qfield.end());     // strip_nonbio_regions_qual 271-286
+  u32 fl = r.flag(); bool paired = fl & 1, unm = fl & 4, munm = fl & 8, mrev = fl & 32, first = fl & 64;
+  std::string orient = "None";   // rust-htslib read_pair_orientation
+  if (paired && !unm && !munm && r.refid() == r.mrefid() && r.pos() != r.mpos()) {
+    i64 p1, p2; bool f1, f2;
+    if (first) { p1 = r.pos(); p2 = r.mpos(); f1 = !rev; f2 = !mrev; } else { p1 = r.mpos(); p2 = r.pos(); f1 = !mrev; f2 = !rev; }
+    if (p1 < p2) orient = std::string(f1 ? "F1" : "R1") + (f2 ? "F2" : "R2"); else orient = std::string(f2 ? "F2" : "R2") + (f1 ? "F1" : "R1");
+  }
+  o.f.resize(38);
+  for (int i = 0; i < 38; i++) {
+    std::string z;
+    if (i == 37 && r.skip_align >= 0) { o.f[i] = r.skip_align ? "TRUE" : "FALSE"; continue; }   // the appended "SK" string aux
+    if (r.aux_z(FIELDS[i], z)) { o.f[i] = z; continue; }
+    switch (i) {
+      case 0: o.f[i] = r.qname(); break; case 1: o.f[i] = qfield; break; case 2: o.f[i] = bstr(rev); break; case 3: o.f[i] = bstr(mrev); break;
+      case 4: o.f[i] = bstr(paired); break; case 5: o.f[i] = bstr(fl & 2); break; case 6: o.f[i] = orient; break; case 7: o.f[i] = bstr(unm); break;
+      case 8: o.f[i] = bstr(munm); break; case 9: o.f[i] = bstr(first); break; case 10: o.f[i] = bstr(fl & 128); break; case 11: o.f[i] = rev ? "-" : "+"; break;
+      case 12: o.f[i] = std::to_string(r.mapq()); break; case 13: o.f[i] = std::to_string(r.pos()); break; case 14: o.f[i] = std::to_string(r.mpos()); break;
+      case 15: o.f[i] = o.seq; break; case 16: o.f[i] = std::to_string(r.l_seq()); break; case 17: o.f[i] = std::to_string(r.tlen()); break;
+      case 18: o.f[i] = bstr(fl & 512); break; case 19: o.f[i] = bstr(fl & 256); break; case 20: o.f[i] = bstr(fl & 1024); break; case 21: o.f[i] = bstr(fl & 2048); break;
+      default: o.f[i].clear(); break;   // non-string aux (NH, HI, AS, nM, RE ...) -> String::new()
+    }
+  }
+}
+
+// ------------------------------------------------------------------ SortedBamReader (src/parse/sorted_bam_reader.rs)
+struct SortedReader {
+  const Bgzf& z; size_t cur = 0; bool force_paired; bool header_done = false;
+  std::string current_umi, next_umi; std::vector<Rec> buffer, next_records;   // buffer is popped from the back
+  SortedReader(const Bgzf& zz, bool fp) : z(zz), force_paired(fp) {}
+  int skip_header() {
+    const std::vector<u8>& d = z.data;
+    if (d.size() < 12 || memcmp(d.data(), "BAM\1", 4)) return fail(NB_ERR_PARSE, "not a BAM file");
+    u32 l_text; memcpy(&l_text, &d[4], 4); size_t p = 8 + (size_t)l_text; u32 n_ref; if (p + 4 > d.size()) return fail(NB_ERR_PARSE, "truncated BAM header"); memcpy(&n_ref, &d[p], 4); p += 4;
+    for (u32 i = 0; i < n_ref; i++) { if (p + 4 > d.size()) return fail(NB_ERR_PARSE, "truncated BAM header"); u32 l; memcpy(&l, &d[p], 4); p += 4 + (size_t)l + 4; }
+    cur = p; header_done = true; return NB_OK;
+  }
+  bool read_record(Rec& r) {
+    const std::vector<u8>& d = z.data;
+    if (cur + 4 > d.size()) return false;
+    u32 bs; memcpy(&bs, &d[cur], 4);
+    if (bs < 32 || cur + 4 + bs > d.size()) return false;
+    r.p = &d[cur + 4]; r.block = bs; r.skip_align = -1; cur += 4 + bs; return true;
+  }
+  int fill_buffer() {   // 31-107
+    buffer.clear(); buffer.swap(next_records); next_records.clear();
+    current_umi = next_umi;
+    Rec r;
+    while (read_record(r)) {
+      if (!r.is_paired() && force_paired) continue;
+      std::string cb, umi;
+      if (!r.aux_z("CB", cb)) continue;
+      if (!r.aux_z("UB", umi) && !r.aux_z("UR", umi)) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
+      if (umi == "AAAAAAAAAA") continue;
+      if (current_umi.empty()) current_umi = umi;
+      if (current_umi != umi) {
+        std::stable_sort(buffer.begin(), buffer.end(), [](const Rec& a, const Rec& b) { std::string x, y; a.aux_z("CB", x); b.aux_z("CB", y); return x < y; });
+        next_records.push_back(r); next_umi = umi;
+        return NB_OK;
+      }
+      buffer.push_back(r);
+    }
+    return NB_OK;   // end of file: this last buffer is NOT sorted by CB (quirk kept)
+  }
+  void add_dummy_paired_reads() {   // 109-125
+    std::vector<Rec> nb2;
+    for (const Rec& r : buffer) { Rec m = r; m.skip_align = 0; nb2.push_back(m); if (!r.is_paired()) { Rec d = r; d.skip_align = 1; nb2.push_back(d); } }
+    buffer.swap(nb2);
+  }
+  void filter_paired_reads() {      // 127-162
+    std::vector<Rec> out; size_t i = 0;
+    while (i < buffer.size()) {
+      if (i + 1 >= buffer.size()) break;
+      if (buffer[i].qname() == buffer[i + 1].qname()) {
+        if (buffer[i].is_first()) { out.push_back(buffer[i]); out.push_back(buffer[i + 1]); } else { out.push_back(buffer[i + 1]); out.push_back(buffer[i]); }
+        i += 2;
+      } else i += 1;
+    }
+    buffer.swap(out);
+  }
+  // 164-185; returns 1 record, 0 end of input, <0 error
+  int next(Rec& r) {
+    if (!buffer.empty()) { r = buffer.back(); buffer.pop_back(); return 1; }
+    int rc = fill_buffer(); if (rc) return rc;
+    if (!force_paired) add_dummy_paired_reads();
+    filter_paired_reads();
+    std::reverse(buffer.begin(), buffer.end());
+    if (buffer.empty()) return 0;
+    r = buffer.back(); buffer.pop_back(); return 1;
+  }
+};
+
+// ------------------------------------------------------------------ UMIReader (src/parse/bam.rs:100-253)
+struct UmiReader {
+  SortedReader rd; std::vector<ParsedRec> current, nextg; std::string current_key, next_key, current_umi, next_umi, current_cb, next_cb;
+  UmiReader(const Bgzf& z, bool fp) : rd(z, fp) {}
+  // returns 1: a following group exists (Some(true)); 0: end of input (None); <0 error
+  int get_umi() {
+    current.swap(nextg); nextg.clear(); current_key = next_key; next_key.clear(); current_umi = next_umi; next_umi.clear(); current_cb = next_cb; next_cb.clear();
+    for (;;) {
+      Rec r; int g = rd.next(r);
+      if (g < 0) return g;
+      if (g == 0) return 0;
+      std::string umi, cb;
+      if (!r.aux_z("UB", umi) && !r.aux_z("UR", umi)) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
+      if (!r.aux_z("CB", cb)) return fail(NB_ERR_PARSE, "Error Read without cell barcode, cannot excise read-mate.");
+      std::string cbs = cb.size() >= 2 ? cb.substr(0, cb.size() - 2) : std::string();
+      std::string key = umi + cbs;
+      if (current_umi.empty()) current_umi = umi;
+      if (current_key.empty()) current_key = key;
+      ParsedRec pr; parse_fields(r, pr);
+      if (current_key == key) { current.push_back(std::move(pr)); current_cb = cbs; }
+      else { nextg.push_back(std::move(pr)); next_umi = umi; next_cb = cbs; next_key = key; return 1; }
+    }
+  }
+};
+
+std::string data_header(const char* prefix) { std::string s; for (int i = 0; i < 38; i++) { if (i == 1 || i == 15) continue; if (!s.empty()) s += "\t"; s += prefix; s += "_"; s += FIELDS[i]; } return s; }
+void data_values(const std::vector<std::string>& f, std::string& s) { bool firstf = true; for (int i = 0; i < 38; i++) { if (i == 1 || i == 15) continue; if (!firstf) s += "\t"; firstf = false; s += f[i]; } }
+
+struct Group { std::vector<ParsedRec> recs; };
+
+}  // namespace
+
+// process::bam::process behind main.rs's library loop (src/bin/main.rs:95-156)
+extern "C" int nb_process_bam(const char* input_file, const char* const* reference_json, const char* const* output_paths, uint32_t n_refs, int strand_filter,
+                              const char* trim /* "L:S,L:S" or NULL */, int num_cores, int force_bam_paired, int device) {
+  if (!input_file || !reference_json || !output_paths || n_refs < 1) return fail(NB_ERR_INVALID, "need an input BAM and >=1 reference/output pair");
+  int threads = std::max(1, num_cores);
+  std::vector<nb_library*> libs(n_refs, nullptr); std::vector<nb_index*> idx(n_refs, nullptr); std::vector<nb_ctx*> ctx(n_refs, nullptr); std::vector<gzFile> outs(n_refs, nullptr);
+  std::vector<bool> first_write(n_refs, true);
+  int rc = NB_OK;
+  auto cleanup = [&]() { for (u32 i = 0; i < n_refs; i++) { if (outs[i]) gzclose(outs[i]); nb_ctx_free(ctx[i]); nb_index_free(idx[i]); nb_library_free(libs[i]); } };
+  std::vector<std::pair<u64, double>> trims;
+  if (trim && *trim) {   // src/bin/main.rs:74-93
+    std::string t(trim); size_t p = 0;
+    while (p <= t.size()) { size_t e = t.find(',', p); if (e == std::string::npos) e = t.size(); std::string one = t.substr(p, e - p); size_t c = one.find(':'); if (c == std::string::npos) return fail(NB_ERR_INVALID, "Invalid strictness"); trims.push_back({strtoull(one.substr(0, c).c_str(), nullptr, 10), strtod(one.substr(c + 1).c_str(), nullptr)}); p = e + 1; }
+    if (trims.size() != n_refs) return fail(NB_ERR_INVALID, "The number of trim options does not match the number of reference libraries");
+  }
+  for (u32 i = 0; i < n_refs && rc == NB_OK; i++) {
+    rc = nb_library_load_json(reference_json[i], strand_filter, &libs[i]);
+    if (rc == NB_OK && !trims.empty()) { nb_config c; nb_library_get_config(libs[i], &c); c.trim_target_length = trims[i].first; c.trim_strictness = trims[i].second; rc = nb_library_set_config(libs[i], &c); }
+    if (rc == NB_OK) rc = nb_index_build(libs[i], threads, &idx[i]);
+    if (rc == NB_OK) rc = nb_ctx_create(idx[i], libs[i], device, nullptr, &ctx[i]);
+    if (rc == NB_OK) { outs[i] = gzopen(output_paths[i], "wb"); if (!outs[i]) rc = fail(NB_ERR_IO, std::string("could not open output ") + output_paths[i]); }
+  }
+  Bgzf z;
+  if (rc == NB_OK) rc = z.load(input_file, threads);
+  if (rc != NB_OK) { cleanup(); return rc; }
+  UmiReader reader(z, force_bam_paired != 0);
+  rc = reader.rd.skip_header();
+  const size_t BATCH_PAIRS = 1u << 19;
+  std::vector<Group> groups; size_t pairs_in_batch = 0; bool has_aligned = false, done = false;
+  std::vector<u8> r1, r2, q1, q2, f1, f2; std::vector<u64> o1, o2; std::vector<u32> scope;
+  std::vector<nb_read_result> rres; std::vector<nb_pair_result> pres;
+  auto flush = [&]() -> int {
+    if (groups.empty()) return NB_OK;
+    r1.clear(); r2.clear(); q1.clear(); q2.clear(); f1.clear(); f2.clear(); o1.assign(1, 0); o2.assign(1, 0); scope.clear();
+    u32 maxlen = 1;
+    for (size_t g = 0; g < groups.size(); g++) {
+      const std::vector<ParsedRec>& v = groups[g].recs;
+      for (size_t j = 0; j + 1 < v.size(); j += 2) {   // even = sequence slot, odd = mate slot (src/process/bam.rs:257-292)
+        const ParsedRec& a = v[j]; const ParsedRec& b = v[j + 1];
+        r1.insert(r1.end(), a.seq.begin(), a.seq.end()); q1.insert(q1.end(), a.qual.begin(), a.qual.end()); o1.push_back(r1.size());
+        r2.insert(r2.end(), b.seq.begin(), b.seq.end()); q2.insert(q2.end(), b.qual.begin(), b.qual.end()); o2.push_back(r2.size());
+        f1.push_back((u8)((a.skip ? NB_FLAG_SKIP_ALIGN : 0) | (a.reverse ? NB_FLAG_REVCOMP : 0))); f2.push_back((u8)((b.skip ? NB_FLAG_SKIP_ALIGN : 0) | (b.reverse ? NB_FLAG_REVCOMP : 0)));
+        scope.push_back((u32)g); maxlen = std::max<u32>(maxlen, (u32)std::max(a.seq.size(), b.seq.size()));
+      }
+    }
+    size_t np = scope.size();
+    r1.resize(r1.size() + 64); r2.resize(r2.size() + 64); q1.resize(q1.size() + 64); q2.resize(q2.size() + 64);
+    for (u32 li = 0; li < n_refs; li++) {
+      nb_batch b; memset(&b, 0, sizeof b);
+      b.n_pairs = np; b.location = NB_MEM_HOST; b.max_read_len = maxlen; b.r1 = r1.data(); b.r1_off = o1.data(); b.r2 = r2.data(); b.r2_off = o2.data();
+      b.q1 = q1.data(); b.q2 = q2.data(); b.flags1 = f1.data(); b.flags2 = f2.data(); b.scope_id = scope.data();
+      rres.resize(2 * np); pres.resize(np);
+      int e = nb_counts_reset(ctx[li]); if (e) return e;
+      e = nb_ctx_set_option(ctx[li], "max_batch_pairs", std::max<size_t>(np, 1)); if (e) return e;
+      e = nb_align_batch(ctx[li], &b, rres.data(), pres.data()); if (e) return e;
+      nb_counts cts; e = nb_counts_finalize(ctx[li], &cts); if (e) return e;
+      // rows per scope, in group order
+      std::vector<u64> row_begin(groups.size() + 1, 0);
+      for (u64 r = 0; r < cts.n_rows; r++) row_begin[cts.row_scope[r] + 1]++;
+      for (size_t g = 0; g < groups.size(); g++) row_begin[g + 1] += row_begin[g];
+      std::string line; size_t pbase = 0;
+      for (size_t g = 0; g < groups.size(); g++) {
+        const std::vector<ParsedRec>& v = groups[g].recs; size_t gp = v.size() / 2;
+        if (row_begin[g + 1] > row_begin[g]) {   // scopes without a callset emit nothing at all (src/process/bam.rs:329-331)
+          std::unordered_set<std::string> scored;
+          auto emit = [&](const std::string& feats, long long score, size_t pj) {
+            const ParsedRec& sq = v[2 * pj]; const ParsedRec& mt = v[2 * pj + 1]; const nb_pair_result& pr = pres[pbase + pj];
+            const nb_read_result& ra = rres[2 * (pbase + pj)]; const nb_read_result& rb = rres[2 * (pbase + pj) + 1];
+            if (first_write[li]) { std::string h = "nimble_features\tnimble_score\t" + data_header("r1") + "\t" + data_header("r2") + "\tr1_filter_forward\tr1_forward_score\tr1_filter_reverse\tr1_reverse_score\tr2_filter_forward\tr2_forward_score\tr2_filter_reverse\tr2_reverse_score\ttriage_reason\taligndirection\n"; gzwrite(outs[li], h.data(), (unsigned)h.size()); first_write[li] = false; }
+            line.clear(); line += feats; line += "\t"; line += std::to_string(score); line += "\t";
+            data_values(mt.f, line); line += "\t"; data_values(sq.f, line); line += "\t";      // "r1" = mate slot, "r2" = sequence slot (108-117)
+            line += nb_reason_str(pr.fr2); line += "\t"; line += std::to_string(rb.pass ? rb.score : 0); line += "\tNone\t0\t";
+            line += nb_reason_str(pr.fr1); line += "\t"; line += std::to_string(ra.pass ? ra.score : 0); line += "\tNone\t0\t";
+            line += nb_reason_str(pr.triage); line += "\tNone\n";
+            gzwrite(outs[li], line.data(), (unsigned)line.size());
+          };
+          for (u64 r = row_begin[g]; r < row_begin[g + 1]; r++) {
+            u32 cs = cts.row_callset[r]; std::string feats;
+            for (u64 k = cts.callset_off[cs]; k < cts.callset_off[cs + 1]; k++) { if (!feats.empty()) feats += ","; feats += nb_library_group_name(libs[li], cts.callset_items[k]); }
+            // representative: the last pair of the scope whose read_key resolved to this callset (the reference keeps an arbitrary one)
+            size_t rep = gp;
+            for (size_t pj = gp; pj-- > 0;) { u32 slot = pres[pbase + pj].callset; if (slot != NONE32 && cts.slot_to_callset[slot] == cs) { rep = pj; break; } }
+            if (rep == gp) continue;
+            scored.insert(v[2 * rep].f[0]);
+            emit(feats, (long long)cts.row_count[r], rep);
+          }
+          for (size_t pj = 0; pj < gp; pj++) { if (scored.count(v[2 * pj + 1].f[0])) continue; emit("", 0, pj); }   // zero rows (332-353)
+        }
+        pbase += gp;
+      }
+    }
+    groups.clear(); pairs_in_batch = 0;
+    return NB_OK;
+  };
+  while (rc == NB_OK && !done) {   // producer loop, src/process/bam.rs:157-180
+    int g = reader.get_umi();
+    if (g < 0) { rc = g; break; }
+    bool final_umi = g == 0;
+    if (final_umi && has_aligned) { done = true; break; }   // the last group is never sent when a group was sent before
+    Group grp; grp.recs = reader.current;
+    pairs_in_batch += grp.recs.size() / 2; groups.push_back(std::move(grp));
+    has_aligned = true;
+    if (final_umi) { done = true; break; }
+    if (pairs_in_batch >= BATCH_PAIRS) rc = flush();
+  }
+  if (rc == NB_OK) rc = flush();
+  cleanup();
+  return rc;
+}
+
+// Host-only view of the feeder for parity tests: the groups the producer loop would send, one line per record:
+// group index, clipped sequence, hex of the clipped (unreversed) quals, then the 38 metadata fields (QUAL as hex).
+extern "C" int nb_bam_dump_groups(const char* input_file, int force_bam_paired, int num_cores, const char* out_path) {
+  if (!input_file || !out_path) return fail(NB_ERR_INVALID, "null argument");
+  Bgzf z; int rc = z.load(input_file, std::max(1, num_cores)); if (rc) return rc;
+  UmiReader reader(z, force_bam_paired != 0);
+  rc = reader.rd.skip_header(); if (rc) return rc;
+  FILE* f = fopen(out_path, "wb"); if (!f) return fail(NB_ERR_IO, std::string("could not open ") + out_path);
+  auto hex = [](const std::string& s) { static const char* H = "0123456789abcdef"; std::string o; for (unsigned char c : s) { o += H[c >> 4]; o += H[c & 15]; } return o; };
+  bool has_aligned = false; size_t gi = 0;
+  for (;;) {
+    int g = reader.get_umi();
+    if (g < 0) { fclose(f); return g; }
+    bool final_umi = g == 0;
+    if (final_umi && has_aligned) break;
+    for (const ParsedRec& r : reader.current) {
+      fprintf(f, "%zu\t%s\t%s", gi, r.seq.c_str(), hex(r.qual).c_str());
+      for (int i = 0; i < 38; i++) fprintf(f, "\t%s", i == 1 ? hex(r.f[i]).c_str() : r.f[i].c_str());
+      fputc('\n', f);
+    }
+    gi++; has_aligned = true;
+    if (final_umi) break;
+  }
+  fclose(f);
+  return NB_OK;
+}

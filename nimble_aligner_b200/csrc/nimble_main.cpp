@@ -53,8 +53,9 @@ int main(int argc, char** argv) {
     int rc = nb_process_fastq(in.data(), (uint32_t)std::min<size_t>(in.size(), 2), r.data(), o.data(), (uint32_t)r.size(), chem, (int)ncores, 0);
     if (rc != NB_OK) die(nb_last_error());
   } else if (ends(lower, ".bam")) {
-    (void)force_paired;
-    die("BAM input: the BGZF/BAM feeder is not part of this build yet (SURVEY.md 8f row 1); use the C ABI with scoped batches");
+    printf("Processing as BAM file\n");
+    int rc = nb_process_bam(in[0], r.data(), o.data(), (uint32_t)r.size(), chem, have_trim ? trim.c_str() : nullptr, (int)ncores, force_paired ? 1 : 0, 0);
+    if (rc != NB_OK) die(nb_last_error());
   } else die("Unsupported file format: " + (lower.find('.') == std::string::npos ? std::string("") : lower.substr(lower.rfind('.') + 1)));
   printf("Alignment successful, terminating.\n");
   return 0;
