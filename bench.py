@@ -132,43 +132,56 @@ def run_reference(args):
 
 
 def merge_across_ranks(ctx, nb, torch, dist, rank, world, pair_base):
-    """Whole-run de-duplication across GPUs: all-to-all of key records by key range, then all-reduce of counts."""
+    """Whole-run de-duplication across GPUs.  (1) every rank learns the union of the callset dictionaries
+    (all_gather of compact rows), so dictionary ids agree; (2) key records, grouped by owning rank on the device, cross
+    NVLink with one all_to_all; (3) each rank re-imports its key partition, folds it, and (4) the dense per-callset count
+    vector is summed with one NCCL all_reduce."""
     import ctypes as C
+    L = nb.lib()
+    # (1) callset dictionaries
+    nout, gcap = C.c_uint64(0), C.c_uint32(0)
+    nb._ck(L.nb_callsets_export(ctx.h, None, 0, C.byref(nout), C.byref(gcap)))
+    k, cw = nout.value, 4 + gcap.value
+    rows = np.zeros((max(k, 1), cw), dtype=np.uint32)
+    nb._ck(L.nb_callsets_export(ctx.h, rows.ctypes.data, k, C.byref(nout), C.byref(gcap)))
+    sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
+    sizes[rank] = k
+    dist.all_reduce(sizes)
+    kmax = int(sizes.max().item())
+    mine = torch.zeros((kmax, cw), dtype=torch.int32, device="cuda")
+    if k:
+        mine[:k] = torch.from_numpy(rows[:k].view(np.int32)).cuda()
+    allrows = torch.empty((world, kmax, cw), dtype=torch.int32, device="cuda")
+    dist.all_gather_into_tensor(allrows.view(-1), mine.view(-1))
+    szs = sizes.tolist()
+    others = torch.cat([allrows[r, : int(szs[r])] for r in range(world) if r != rank and szs[r]] or [allrows[0, :0]]).cpu().numpy().view(np.uint32)
+    others = np.ascontiguousarray(others)
+    nb._ck(L.nb_callsets_import(ctx.h, others.ctypes.data, others.shape[0]))
+    # (2) key records by owner
     n = C.c_uint64(0)
-    nb._ck(nb.lib().nb_keys_export_count(ctx.h, C.byref(n)))
+    nb._ck(L.nb_keys_export_count(ctx.h, C.byref(n)))
     rec = torch.empty((max(n.value, 1), 4), dtype=torch.int64, device="cuda")
-    nb._ck(nb.lib().nb_keys_export(ctx.h, rec.data_ptr(), n.value, pair_base))
-    rec = rec[: n.value]
-    owner = ((rec[:, 0] >> 40) & 0xFFFF) % world            # key_lo is a 64-bit mix: any bit slice partitions evenly
-    order = torch.argsort(owner)
-    rec = rec[order].contiguous()
-    send = torch.bincount(owner, minlength=world)
+    cnt = np.zeros(world, dtype=np.uint64)
+    nb._ck(L.nb_keys_export_partitioned(ctx.h, rec.data_ptr(), n.value, pair_base, world, cnt.ctypes.data))
+    send = torch.from_numpy(cnt.astype(np.int64)).cuda()
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send)
-    out = torch.empty((int(recv.sum().item()), 4), dtype=torch.int64, device="cuda")
-    dist.all_to_all_single(out, rec, output_split_sizes=[int(x) * 1 for x in recv.tolist()], input_split_sizes=[int(x) for x in send.tolist()])
-    # callset dictionaries: gather (tag, len, items) rows from every rank and import the union
-    cap = 1 << 18
-    nout, gcap = C.c_uint64(0), C.c_uint32(0)
-    nb._ck(nb.lib().nb_callsets_export(ctx.h, None, None, None, 0, C.byref(nout), C.byref(gcap)))
-    k, g = nout.value, gcap.value
-    tags, lens, items = np.zeros(max(k, 1), np.uint64), np.zeros(max(k, 1), np.uint32), np.zeros((max(k, 1), g), np.uint32)
-    nb._ck(nb.lib().nb_callsets_export(ctx.h, tags.ctypes.data, lens.ctypes.data, items.ctypes.data, k, C.byref(nout), C.byref(gcap)))
-    gathered = [None] * world
-    dist.all_gather_object(gathered, (tags[:k], lens[:k], items[:k]))
-    at = np.concatenate([x[0] for x in gathered]); al = np.concatenate([x[1] for x in gathered]); ai = np.concatenate([x[2] for x in gathered])
-    nb._ck(nb.lib().nb_callsets_import(ctx.h, at.ctypes.data, al.ctypes.data, np.ascontiguousarray(ai).ctypes.data, len(at)))
-    nb._ck(nb.lib().nb_keys_import(ctx.h, out.data_ptr(), out.shape[0]))
-    res = ctx.counts()
-    # per-callset counts keyed by the callset's names; summed over ranks
-    local = {tuple(cs): int(c) for _, cs, c in res["rows"]}
-    allc = [None] * world
-    dist.all_gather_object(allc, local)
-    total = {}
-    for d in allc:
-        for kx, v in d.items():
-            total[kx] = total.get(kx, 0) + v
-    return total, res["n_unique_keys"]
+    recv_l, send_l = recv.tolist(), cnt.astype(np.int64).tolist()
+    out = torch.empty((max(sum(recv_l), 1), 4), dtype=torch.int64, device="cuda")
+    dist.all_to_all_single(out[: sum(recv_l)], rec[: n.value], output_split_sizes=recv_l, input_split_sizes=send_l)
+    # (3) re-import this rank's key partition and fold it (same stream as the collective: ordered after it)
+    nb._ck(L.nb_keys_import(ctx.h, out.data_ptr(), sum(recv_l)))
+    raw = ctx.counts_raw()
+    # (4) dense all-reduce: after (1) every rank lists the same callsets in the same order
+    dense = torch.zeros(len(raw["callset_off"]) - 1, dtype=torch.int64, device="cuda")
+    if len(raw["row_callset"]):
+        dense.index_add_(0, torch.from_numpy(raw["row_callset"].astype(np.int64)).cuda(), torch.from_numpy(raw["row_count"]).cuda())
+    dist.all_reduce(dense)
+    uniq = torch.tensor([raw["n_unique_keys"]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(uniq)
+    raw = dict(raw)
+    raw["dense_counts"] = dense.cpu().numpy()
+    return raw, int(uniq.item())
 
 
 def main():
@@ -197,6 +210,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.pairs
     cores = os.cpu_count() or 1
@@ -204,7 +219,12 @@ def main():
     t0 = time.time()
     ix = nb.build_index(lib, max(1, cores // max(1, world)))
     index_build_s = time.time() - t0
-    stream = torch.cuda.current_stream().cuda_stream
+    # one explicit CUDA stream shared by torch (events, NCCL ordering) and the library (kernels, D2H); the legacy default
+    # stream has handle 0, which nb_ctx_create reads as "create your own"
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     ctx = nb.Context(ix, lib, device=local_rank, stream=stream, max_batch_pairs=args.chunk)
     # ---- inputs: this rank's shard of the seeded stream, in pinned host memory and resident in HBM
     pair_base = rank * n
@@ -272,9 +292,15 @@ def main():
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     step_host()
     ms_host, (counts_host, uniq_host) = timed(step_host, args.steps)
-    if world == 1:   # names are decoded outside the timed region (a C host would print them straight into the TSV)
-        counts_dev = {tuple(cs): int(c) for _, cs, c in ctx.decode_counts(counts_dev)["rows"]}
-        counts_host = {tuple(cs): int(c) for _, cs, c in ctx.decode_counts(counts_host)["rows"]}
+    def decode(raw):   # names are decoded outside the timed region (a C host would print them straight into the TSV)
+        d = ctx.decode_counts(raw)
+        if "dense_counts" in raw:
+            return {tuple(cs): int(c) for cs, c in zip(d["callsets"], raw["dense_counts"].tolist()) if c}
+        return {tuple(cs): int(c) for _, cs, c in d["rows"]}
+    counts_dev, counts_host = decode(counts_dev), decode(counts_host)
+    if counts_host != counts_dev:
+        diff = [(k, counts_dev.get(k), counts_host.get(k)) for k in set(counts_dev) | set(counts_host) if counts_dev.get(k) != counts_host.get(k)]
+        print("rank %d: %d callsets differ (dev total %d, host total %d, %d vs %d callsets); e.g. %s" % (rank, len(diff), sum(counts_dev.values()), sum(counts_host.values()), len(counts_dev), len(counts_host), diff[:3]), file=sys.stderr)
     assert counts_host == counts_dev, "host-fed and device-resident runs disagree"
     if args.verify and world > 1 and rank == 0:
         # the merged multi-GPU counts must equal one GPU processing the union of all ranks' shards

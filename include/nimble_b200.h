@@ -177,12 +177,16 @@ const char* nb_library_group_name(const nb_library*, uint32_t group);
  * are over unique read_keys of the whole run, so ranks exchange their de-duplication records by key range
  * (all-to-all over NCCL, driven by the host), re-import the partition they own and finalize; the per-callset counts
  * are then summed across ranks (all-reduce).  Records are 32 bytes {key_lo, key_hi, order = global pair index,
- * callset_tag}; dev_records are device pointers.  Callset dictionaries travel as (tag, len, items[gcap]) rows. */
+ * callset_tag}; dev_records are device pointers; nb_keys_export_partitioned groups them by owning rank (a 16-bit slice of
+ * key_lo mod world) so no sort is needed.  Callset dictionaries travel as rows of (4 + gcap) uint32:
+ * {slot, len, tag_lo, tag_hi, items[gcap]}; after importing the union every rank's nb_counts lists the same callsets in
+ * the same order, so the final merge is one all-reduce(sum) over a dense count vector. */
 int nb_keys_export_count(nb_ctx*, uint64_t* n);
 int nb_keys_export(nb_ctx*, void* dev_records, uint64_t cap, uint64_t pair_index_base);
 int nb_keys_import(nb_ctx*, const void* dev_records, uint64_t n);
-int nb_callsets_export(nb_ctx*, uint64_t* tags, uint32_t* lens, uint32_t* items, uint64_t cap, uint64_t* n_out, uint32_t* gcap_out);
-int nb_callsets_import(nb_ctx*, const uint64_t* tags, const uint32_t* lens, const uint32_t* items, uint64_t n);
+int nb_keys_export_partitioned(nb_ctx*, void* dev_records, uint64_t cap, uint64_t pair_index_base, uint32_t world, uint64_t* counts_out);
+int nb_callsets_export(nb_ctx*, uint32_t* rows, uint64_t cap_rows, uint64_t* n_out, uint32_t* gcap_out);
+int nb_callsets_import(nb_ctx*, const uint32_t* rows, uint64_t n);
 
 /* timing of the dominant kernel (seed_walk_map), CUDA events on the launching stream: out[0]=launches, out[1]=total ms,
  * out[2]=reads processed, out[3]=all kernels launched by this ctx since reset */

@@ -101,8 +101,9 @@ _SIGS = {
     "nb_keys_export_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "nb_keys_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "nb_keys_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
-    "nb_callsets_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
-    "nb_callsets_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "nb_keys_export_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "nb_callsets_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "nb_callsets_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "nb_ctx_kernel_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "nb_ctx_work_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),

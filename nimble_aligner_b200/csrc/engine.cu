@@ -402,7 +402,7 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   c->last_unique = h.n_keys;
   // compact the occupied entries of the (cell, callset) table and of the callset dictionary on the device, then read
   // back only those: rows of {key, count} and of {slot, len, items[gcap]}
-  u64 n_agg = h.n_agg, n_cs = h.n_callsets; u32 cw = 2 + c->gcap;
+  u64 n_agg = h.n_agg, n_cs = h.n_callsets; u32 cw = 4 + c->gcap;
   CK(c->d_scratch.ensure(n_agg * 16 + n_cs * (size_t)cw * 4 + 64, s));
   u64* d_agg = (u64*)c->d_scratch.p; u32* d_cs = (u32*)((char*)c->d_scratch.p + n_agg * 16);
   CK(cudaMemsetAsync(c->d_nout.p, 0, 16, s));
@@ -417,13 +417,13 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   auto cs_less = [&](u32 a, u32 b) {
     const u32* ra = &csr[(size_t)a * cw]; const u32* rb = &csr[(size_t)b * cw];
     u32 la = ra[1], lb = rb[1];
-    for (u32 i = 0; i < std::min(la, lb); i++) { u32 ga = ra[2 + i], gb = rb[2 + i]; if (ga != gb) { int cmp = gn[ga].compare(gn[gb]); if (cmp) return cmp < 0; } }
+    for (u32 i = 0; i < std::min(la, lb); i++) { u32 ga = ra[4 + i], gb = rb[4 + i]; if (ga != gb) { int cmp = gn[ga].compare(gn[gb]); if (cmp) return cmp < 0; } }
     if (la != lb) return la < lb;
     return ra[0] < rb[0];
   };
   std::sort(slots.begin(), slots.end(), cs_less);
   std::vector<u32>& dense = c->slot_dense; dense.assign(c->cs_slots, NONE32);
-  for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[2 + k]); c->cs_off.push_back(c->cs_items.size()); }
+  for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[4 + k]); c->cs_off.push_back(c->cs_items.size()); }
   struct Row { u32 cell, cs; i64 n; };
   std::vector<Row> rows; rows.reserve(n_agg);
   for (u64 i = 0; i < n_agg; i++) { u64 k = agg[2 * i] - 1; rows.push_back(Row{(u32)(k >> 24), dense[(u32)(k & 0xFFFFFF)], (i64)agg[2 * i + 1]}); }
@@ -481,39 +481,56 @@ int nb_keys_export(nb_ctx* c, void* dev_records, uint64_t cap, uint64_t pair_ind
   CK(cudaStreamSynchronize(c->stream));
   return NB_OK;
 }
-// callset dictionary entries as (tag, len, items[gcap]) rows so that ranks can merge dictionaries on the host
-int nb_callsets_export(nb_ctx* c, uint64_t* tags, uint32_t* lens, uint32_t* items, uint64_t cap, uint64_t* n_out, uint32_t* gcap_out) {
+// key records grouped by owning rank: counts_out[world] entries per owner, records of owner o start at sum(counts[0..o))
+int nb_keys_export_partitioned(nb_ctx* c, void* dev_records, uint64_t cap, uint64_t pair_index_base, uint32_t world, uint64_t* counts_out) {
+  if (!c || !counts_out || world == 0 || world > 64 || (!dev_records && cap)) return fail(NB_ERR_INVALID, "bad argument");
+  for (u32 i = 0; i < world; i++) counts_out[i] = 0;
+  if (!c->tables_ready) return NB_OK;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream; Tables t = make_tables(c);
+  CK(c->d_scratch.ensure(1024, s));
+  unsigned long long* d_cnt = (unsigned long long*)c->d_scratch.p;
+  CK(cudaMemsetAsync(d_cnt, 0, 64 * 8 * 2, s));
+  nbk::launch_keys_count_owner(t, world, d_cnt, s); c->all_launches++;
+  std::vector<unsigned long long> cnt(world), cur(world);
+  CK(cudaMemcpyAsync(cnt.data(), d_cnt, world * 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+  u64 tot = 0; for (u32 i = 0; i < world; i++) { cur[i] = tot; tot += cnt[i]; counts_out[i] = cnt[i]; }
+  if (tot > cap) return fail(NB_ERR_INVALID, "record buffer too small for nb_keys_export_partitioned");
+  CK(cudaMemcpyAsync(d_cnt + 64, cur.data(), world * 8, cudaMemcpyHostToDevice, s));
+  nbk::launch_keys_scatter(t, dev_records, d_cnt + 64, pair_index_base, world, s); c->all_launches++;
+  CK(cudaStreamSynchronize(s));
+  return NB_OK;
+}
+// callset dictionary as compact rows of (4 + gcap) u32: {slot, len, tag_lo, tag_hi, items[gcap]} so that ranks can merge
+// dictionaries; rows == NULL returns the count only
+int nb_callsets_export(nb_ctx* c, uint32_t* rows, uint64_t cap_rows, uint64_t* n_out, uint32_t* gcap_out) {
   if (!c || !n_out) return fail(NB_ERR_INVALID, "null argument");
   *n_out = 0; if (gcap_out) *gcap_out = c->gcap;
   if (!c->tables_ready) return NB_OK;
   CK(cudaSetDevice(c->device));
-  std::vector<u64> tag(c->cs_slots); std::vector<u32> len(c->cs_slots), it((size_t)c->cs_slots * c->gcap);
-  CK(cudaMemcpyAsync(tag.data(), c->d_cstag.p, c->cs_slots * 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaMemcpyAsync(len.data(), c->d_cslen.p, c->cs_slots * 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(it.data(), c->d_csitems.p, it.size() * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
-  u64 n = 0;
-  for (u32 i = 0; i < c->cs_slots; i++) if (tag[i]) { if (tags && n < cap) { tags[n] = tag[i]; lens[n] = len[i]; memcpy(items + n * c->gcap, &it[(size_t)i * c->gcap], c->gcap * 4); } n++; }
-  *n_out = n;
+  Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
+  *n_out = h.n_callsets;
+  if (!rows) return NB_OK;
+  if (cap_rows < h.n_callsets) return fail(NB_ERR_INVALID, "row buffer too small for nb_callsets_export");
+  cudaStream_t s = c->stream; u32 cw = 4 + c->gcap;
+  CK(c->d_scratch.ensure(h.n_callsets * (size_t)cw * 4 + 64, s));
+  CK(cudaMemsetAsync(c->d_nout.p, 0, 16, s));
+  nbk::launch_compact(make_tables(c), nullptr, 0, (u32*)c->d_scratch.p, h.n_callsets, (unsigned long long*)c->d_nout.p, s); c->all_launches += 2;
+  if (h.n_callsets) CK(cudaMemcpyAsync(rows, c->d_scratch.p, h.n_callsets * (size_t)cw * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return NB_OK;
 }
-// insert callsets received from other ranks (same tag function as the device uses) so that imported key records resolve
-int nb_callsets_import(nb_ctx* c, const uint64_t* tags, const uint32_t* lens, const uint32_t* items, uint64_t n) {
-  if (!c || (n && (!tags || !lens || !items))) return fail(NB_ERR_INVALID, "null argument");
+// insert callsets received from other ranks (rows as exported; device insert with the same tag function) so that
+// imported key records resolve and every rank ends up with the same dictionary
+int nb_callsets_import(nb_ctx* c, const uint32_t* rows, uint64_t n) {
+  if (!c || (n && !rows)) return fail(NB_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
   if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
-  std::vector<u64> tag(c->cs_slots); std::vector<u32> len(c->cs_slots), it((size_t)c->cs_slots * c->gcap);
-  CK(cudaMemcpyAsync(tag.data(), c->d_cstag.p, c->cs_slots * 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaMemcpyAsync(len.data(), c->d_cslen.p, c->cs_slots * 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(it.data(), c->d_csitems.p, it.size() * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
-  u32 mask = (u32)c->cs_slots - 1;
-  for (u64 i = 0; i < n; i++) {
-    u32 h = (u32)(tags[i] >> 24) & mask; bool done = false;
-    for (u64 pr = 0; pr <= mask; pr++) { if (tag[h] == tags[i]) { done = true; break; } if (!tag[h]) { tag[h] = tags[i]; len[h] = lens[i]; memcpy(&it[(size_t)h * c->gcap], items + i * c->gcap, c->gcap * 4); done = true; break; } h = (h + 1) & mask; }
-    if (!done) return fail(NB_ERR_OVERFLOW, "callset dictionary full: raise option callset_slots");
-  }
-  unsigned long long occupied = 0; for (u32 i = 0; i < c->cs_slots; i++) occupied += tag[i] != 0;
-  CK(cudaMemcpyAsync(&((Counters*)c->d_ctr.p)->n_callsets, &occupied, 8, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_cstag.p, tag.data(), c->cs_slots * 8, cudaMemcpyHostToDevice, c->stream)); CK(cudaMemcpyAsync(c->d_cslen.p, len.data(), c->cs_slots * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_csitems.p, it.data(), it.size() * 4, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
-  return NB_OK;
+  cudaStream_t s = c->stream; u32 cw = 4 + c->gcap;
+  CK(c->d_scratch.ensure(n * (size_t)cw * 4 + 64, s));
+  if (n) CK(cudaMemcpyAsync(c->d_scratch.p, rows, n * (size_t)cw * 4, cudaMemcpyHostToDevice, s));
+  nbk::launch_callsets_import(make_tables(c), (const u32*)c->d_scratch.p, n, s); c->all_launches++;
+  return check_device_errors(c);
 }
 // replace this context's whole-run key table by the received partition (records from all ranks whose keys fall in
 // this rank's range) so that nb_counts_finalize counts each unique read_key of the partition once

@@ -480,8 +480,55 @@ __global__ void __launch_bounds__(256) k_keys_import(Tables t, const KeyRec* rec
   atomicMax(t.kval + slot, (unsigned long long)(((r.order + 1) << 24) | cs));
 }
 
+
+// ---- multi-GPU exchange helpers: key records grouped by owning rank (owner = a 16-bit slice of key_lo mod world), so the
+// host can hand them to an all-to-all without sorting; warp-aggregated cursors (a handful of hot counters otherwise)
+__device__ __forceinline__ u32 key_owner(u64 k0, u32 world) { return (u32)((k0 >> 40) & 0xFFFFu) % world; }
+__global__ void __launch_bounds__(256) k_keys_count_owner(Tables t, u32 world, unsigned long long* counts) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  bool occ = false; u32 owner = 0;
+  if (idx <= t.key_mask) { ulonglong2 k = t.key[idx]; occ = !(k.x == 0 && k.y == 0); owner = key_owner(k.x, world); }
+  unsigned act = __ballot_sync(0xFFFFFFFFu, occ);
+  if (!occ) return;
+  unsigned peers = __match_any_sync(act, owner);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(counts + owner, (unsigned long long)__popc(peers));
+}
+__global__ void __launch_bounds__(256) k_keys_scatter(Tables t, KeyRec* rec, unsigned long long* cursors, u64 order_base, u32 world) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  bool occ = false; u32 owner = 0; ulonglong2 k = make_ulonglong2(0, 0);
+  if (idx <= t.key_mask) { k = t.key[idx]; occ = !(k.x == 0 && k.y == 0); owner = key_owner(k.x, world); }
+  unsigned act = __ballot_sync(0xFFFFFFFFu, occ);
+  if (!occ) return;
+  unsigned peers = __match_any_sync(act, owner); u32 lane = threadIdx.x & 31; int leader = __ffs(peers) - 1;
+  unsigned long long base = 0;
+  if ((int)lane == leader) base = atomicAdd(cursors + owner, (unsigned long long)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  u64 at = base + __popc(peers & ((1u << lane) - 1));
+  u64 v = t.kval[idx]; u32 cs = (u32)(v & 0xFFFFFFu);
+  KeyRec r; r.k0 = k.x; r.k1 = k.y; r.order = (v >> 24) - 1 + order_base; r.tag = ((v >> 24) == 0 || cs == CS_NONE) ? 0ULL : t.cs_tag[cs];
+  rec[at] = r;
+}
+// callsets received from other ranks (same tag function as callset_intern)
+__global__ void __launch_bounds__(256) k_callsets_import(Tables t, const u32* rows, u64 n) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const u32* r = rows + idx * (4 + t.gcap);
+  u64 tag = (u64)r[2] | ((u64)r[3] << 32); u32 len = r[1];
+  u32 h = (u32)(tag >> 24) & t.cs_mask;
+  for (u32 probes = 0; probes <= t.cs_mask; probes++) {
+    unsigned long long old = atomicCAS((unsigned long long*)(t.cs_tag + h), 0ULL, (unsigned long long)tag);
+    if (old == 0ULL) { t.cs_len[h] = len; for (u32 i = 0; i < len; i++) t.cs_items[(u64)h * t.gcap + i] = r[4 + i]; atomicAdd(&t.ctr->n_callsets, 1ULL); return; }
+    if (old == tag) return;
+    h = (h + 1) & t.cs_mask;
+  }
+  atomicOr(&t.ctr->err, (unsigned)E_CS_FULL);
+}
 // ------------------------------------------------------------------------------------------------ launchers
 static inline unsigned blocks_for(u64 n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+void launch_keys_count_owner(const Tables& t, u32 world, unsigned long long* counts, cudaStream_t s) { k_keys_count_owner<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, world, counts); }
+void launch_keys_scatter(const Tables& t, void* rec, unsigned long long* cursors, u64 order_base, u32 world, cudaStream_t s) { k_keys_scatter<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, (KeyRec*)rec, cursors, order_base, world); }
+void launch_callsets_import(const Tables& t, const u32* rows, u64 n, cudaStream_t s) { if (n) k_callsets_import<<<blocks_for(n, 256), 256, 0, s>>>(t, rows, n); }
+
 void launch_pack(const BatchDev& b, cudaStream_t s) { u64 n = (u64)b.n_reads * b.W; if (n) k_pack<<<blocks_for(n, 256), 256, 0, s>>>(b); }
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_reads) k_trim<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, t); }
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s) {
@@ -502,7 +549,7 @@ void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.
 void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t, void* out, cudaStream_t s) {
   if (b.n_reads) k_export_reads<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, ix, t, (ReadOut*)out);
 }
-// occupied entries of the count table -> {key, count} rows; of the callset dictionary -> {slot, len, items[gcap]} rows
+// occupied entries of the count table -> {key, count} rows; of the callset dictionary -> {slot, len, tag_lo, tag_hi, items[gcap]} rows
 __global__ void __launch_bounds__(256) k_compact_agg(Tables t, u64* out, u64 cap, unsigned long long* n_out) {
   u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (idx > t.agg_mask) return;
@@ -517,9 +564,9 @@ __global__ void __launch_bounds__(256) k_compact_cs(Tables t, u32* out, u64 cap,
   if (!t.cs_tag[idx]) return;
   unsigned long long at = atomicAdd(n_out, 1ULL);
   if (at >= cap) return;
-  u32* r = out + at * (2 + t.gcap); u32 n = t.cs_len[idx];
-  r[0] = idx; r[1] = n;
-  for (u32 i = 0; i < n; i++) r[2 + i] = t.cs_items[(u64)idx * t.gcap + i];
+  u32* r = out + at * (4 + t.gcap); u32 n = t.cs_len[idx]; u64 tag = t.cs_tag[idx];
+  r[0] = idx; r[1] = n; r[2] = (u32)tag; r[3] = (u32)(tag >> 32);
+  for (u32 i = 0; i < t.gcap; i++) r[4 + i] = i < n ? t.cs_items[(u64)idx * t.gcap + i] : 0u;
 }
 void launch_compact(const Tables& t, u64* agg_out, u64 agg_cap, u32* cs_out, u64 cs_cap, unsigned long long* n_out2, cudaStream_t s) {
   k_compact_agg<<<blocks_for(t.agg_mask + 1, 256), 256, 0, s>>>(t, agg_out, agg_cap, n_out2);

@@ -96,6 +96,9 @@ void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t,
 void launch_count_keys(const Tables& t, cudaStream_t s);
 void launch_rehash_keys(const Tables& old_t, const Tables& new_t, cudaStream_t s);
 void launch_keys_export(const Tables& t, void* records, unsigned long long* n_out, u64 cap, u64 order_base, cudaStream_t s);
+void launch_keys_count_owner(const Tables& t, u32 world, unsigned long long* counts, cudaStream_t s);
+void launch_keys_scatter(const Tables& t, void* rec, unsigned long long* cursors, u64 order_base, u32 world, cudaStream_t s);
+void launch_callsets_import(const Tables& t, const u32* rows, u64 n, cudaStream_t s);
 void launch_keys_import(const Tables& t, const void* records, u64 n, cudaStream_t s);
 
 }  // namespace nbk
