@@ -264,6 +264,13 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   for (u32 sd = 0; sd < sides; sd++) {
     if (host) {
       u64 a0 = src_off[sd][p0], a1 = src_off[sd][p1];
+      if (sd == 1 && src_a[1] == src_a[0] && src_off[1] == src_off[0] && src_q[1] == src_q[0]) {
+        // the mate slot is the same buffer as the sequence slot (10x single-end records: the SKIP_ALIGN dummy is a clone of
+        // the real record, sorted_bam_reader.rs:109-125): one copy serves both sides
+        b.a[1] = b.a[0]; b.off[1] = b.off[0]; b.q[1] = b.q[0];
+        if (src_f[sd]) { CK(ens(S->f[sd], np)); CK(cudaMemcpyAsync(S->f[sd].p, src_f[sd] + p0, np, kind, cs)); b.flags[sd] = (const u8*)S->f[sd].p; }
+        continue;
+      }
       CK(ens(S->a[sd], a1 - a0 + 64)); CK(ens(S->off[sd], (np + 1) * 8));
       if (a1 > a0) CK(cudaMemcpyAsync(S->a[sd].p, src_a[sd] + a0, a1 - a0, kind, cs));
       CK(cudaMemcpyAsync(S->off[sd].p, src_off[sd] + p0, (np + 1) * 8, kind, cs));
@@ -424,11 +431,22 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   std::sort(slots.begin(), slots.end(), cs_less);
   std::vector<u32>& dense = c->slot_dense; dense.assign(c->cs_slots, NONE32);
   for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[4 + k]); c->cs_off.push_back(c->cs_items.size()); }
-  struct Row { u32 cell, cs; i64 n; };
-  std::vector<Row> rows; rows.reserve(n_agg);
-  for (u64 i = 0; i < n_agg; i++) { u64 k = agg[2 * i] - 1; rows.push_back(Row{(u32)(k >> 24), dense[(u32)(k & 0xFFFFFF)], (i64)agg[2 * i + 1]}); }
-  std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.cell != b.cell ? a.cell < b.cell : a.cs < b.cs; });
-  for (auto& r : rows) { c->row_scope.push_back(r.cell); c->row_callset.push_back(r.cs); c->row_count.push_back(r.n); }
+  // rows ordered by (cell, callset): LSD radix sort on the 56-bit key (the table can hold millions of (cell, callset) rows)
+  std::vector<u64> key(n_agg), key2(n_agg); std::vector<i64> val(n_agg), val2(n_agg);
+  for (u64 i = 0; i < n_agg; i++) { u64 k = agg[2 * i] - 1; key[i] = ((k >> 24) << 24) | dense[(u32)(k & 0xFFFFFF)]; val[i] = (i64)agg[2 * i + 1]; }
+  if (n_agg > 1) {
+    u64 any = 0; for (u64 i = 0; i < n_agg; i++) any |= key[i];
+    for (int shift = 0; shift < 64 && (any >> shift); shift += 16) {
+      std::vector<u64> cnt(65537, 0);
+      for (u64 i = 0; i < n_agg; i++) cnt[((key[i] >> shift) & 0xFFFF) + 1]++;
+      for (int b = 0; b < 65536; b++) cnt[b + 1] += cnt[b];
+      for (u64 i = 0; i < n_agg; i++) { u64 at = cnt[(key[i] >> shift) & 0xFFFF]++; key2[at] = key[i]; val2[at] = val[i]; }
+      key.swap(key2); val.swap(val2);
+    }
+  }
+  c->row_scope.resize(n_agg); c->row_callset.resize(n_agg); c->row_count.resize(n_agg);
+  for (u64 i = 0; i < n_agg; i++) { c->row_scope[i] = (u32)(key[i] >> 24); c->row_callset[i] = (u32)(key[i] & 0xFFFFFF); c->row_count[i] = val[i]; }
+  struct { size_t n; size_t size() const { return n; } } rows{(size_t)n_agg};
   out->n_rows = rows.size(); out->row_scope = c->row_scope.data(); out->row_callset = c->row_callset.data(); out->row_count = c->row_count.data();
   out->n_callsets = slots.size(); out->callset_off = c->cs_off.data(); out->callset_items = c->cs_items.data();
   out->n_pairs_seen = c->pairs_seen; out->n_unique_keys = h.n_keys; out->n_slots = c->cs_slots; out->slot_to_callset = c->slot_dense.data();

@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's bench line): the other BASELINE.json config shapes on one GPU.
+  --workload c3   10x-style single-end records (L=91, quals, (UMI,CB) scopes, dummy mates, MAXINFO trim), per-cell counts
+  --workload c4s  scaled-down C4: a library whose index is far larger than the 126 MB L2 (HBM-bound probes), single-end 150 bp
+Prints one JSON line per run with reads/s device-timed from pinned host buffers (e2e) and k_map's launch time."""
+import argparse, json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import nimble_aligner_b200 as nb
+import synth
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--reads", type=int, default=20_000_000)
+    ap.add_argument("--families", type=int, default=8000)
+    ap.add_argument("--steps", type=int, default=3)
+    a = ap.parse_args()
+    cores = os.cpu_count() or 1
+    T = {"align": 0.0}
+    s = torch.cuda.Stream(); torch.cuda.set_stream(s)
+    if a.workload == "c3":
+        L = synth.SynthLibrary(seed=1234, n_fam=200, n_all=5, group_on="", trim_target_length=40, trim_strictness=0.9)
+        lib = nb.Library.from_text(json.dumps(L.to_json_obj()), "unstranded")
+        ix = nb.build_index(lib, cores)
+        u = synth.umi_reads(L, 0, a.reads // 4, seed=2345, threads=cores)
+        n = u["n_reads"]
+        pin = lambda x: torch.from_numpy(x).pin_memory()
+        bases, qual, off = pin(u["bases"]), pin(u["qual"]), pin(u["off"].astype(np.int64))
+        scope, cell = pin(u["scope"].astype(np.int32)), pin(u["cell"].astype(np.int32))
+        f1 = pin(np.full(n, nb.FLAG_SKIP_ALIGN, dtype=np.uint8)); f2 = pin(np.zeros(n, dtype=np.uint8))
+        ctx = nb.Context(ix, lib, stream=s.cuda_stream, max_batch_pairs=1 << 20, agg_slots=1 << 24)
+        import ctypes as C
+        def step():
+            ctx.reset()
+            b = nb.Batch(n, nb.NB_MEM_HOST, 91, bases.data_ptr(), off.data_ptr(), bases.data_ptr(), off.data_ptr(), qual.data_ptr(), qual.data_ptr(),
+                         f1.data_ptr(), f2.data_ptr(), scope.data_ptr(), cell.data_ptr())
+            nb._ck(nb.lib().nb_align_batch(ctx.h, C.byref(b), None, None))
+            ctx.sync(); T["align"] += time.time()
+            return ctx.counts_raw()
+        desc = "C3-shaped: %d single-end 91 bp records with quals in %d (UMI,CB) scopes, 8000 cells, 1k-transcript library" % (n, len(u["sizes"]))
+        h2d = int(u["off"][-1]) * 2 + n * (8 + 4 + 4 + 2)
+    else:
+        L = synth.SynthLibrary(seed=3456, n_fam=a.families, n_all=5, group_on="")
+        t0 = time.time(); lib = nb.Library.from_text(json.dumps(L.to_json_obj()), "unstranded"); t1 = time.time()
+        ix = nb.build_index(lib, cores); t2 = time.time()
+        n = a.reads
+        r1, o1, _, _ = synth.pairs(L, 0, n, seed=3456, paired=False, threads=cores)
+        hb, ho = torch.from_numpy(r1).pin_memory(), torch.from_numpy(o1.astype(np.int64)).pin_memory()
+        ctx = nb.Context(ix, lib, stream=s.cuda_stream, max_batch_pairs=1 << 20)
+        import ctypes as C
+        def step():
+            ctx.reset()
+            b = nb.Batch(n, nb.NB_MEM_HOST, 150, hb.data_ptr(), ho.data_ptr(), None, None, None, None, None, None, None, None)
+            nb._ck(nb.lib().nb_align_batch(ctx.h, C.byref(b), None, None))
+            ctx.sync(); T["align"] += time.time()
+            return ctx.counts_raw()
+        st = ix.stats()
+        desc = "C4-scaled: %d transcripts, index %.0f MB on the device (%d k-mers; library parse %.1fs, host index build %.1fs), %d single-end 150 bp reads" % (5 * a.families, st["device_bytes"] / 1e6, st["n_kmers"], t1 - t0, t2 - t1, n)
+        h2d = int(o1[-1]) + 8 * n
+    for _ in range(2):
+        raw = step()
+    ctx.kernel_stats(reset=True)
+    torch.cuda.synchronize(); t0 = time.time(); T["align"] = 0.0; starts = 0.0
+    for _ in range(a.steps):
+        starts += time.time()
+        raw = step()
+    torch.cuda.synchronize(); dt = (time.time() - t0) / a.steps
+    ks = ctx.kernel_stats()
+    align_s = (T["align"] - starts) / a.steps
+    print(json.dumps({"workload": desc, "e2e_reads_per_s": n / dt, "align_only_reads_per_s": n / align_s, "align_ms": align_s * 1e3, "finalize_ms": (dt - align_s) * 1e3, "ms_per_step": dt * 1e3, "h2d_gb_per_s": h2d / dt / 1e9, "count_rows": int(len(raw["row_count"])),
+                      "unique_keys": int(raw["n_unique_keys"]), "k_map_ms_per_launch": ks["map_ms"] / max(1, ks["map_launches"]), "k_map_reads_per_launch": ks["map_reads"] / max(1, ks["map_launches"]),
+                      "k_map_share": ks["map_ms"] / (dt * 1e3 * a.steps), "launches_per_step": ks["launches"] / a.steps}))
+
+
+if __name__ == "__main__":
+    main()

@@ -93,7 +93,8 @@ void synth_umi_reads(u64 seed, u64 first, u64 n, const u32* sizes, const u64* re
         else { u32 st = (u32)r.below((u64)tlen - L + 1); bool flip = r.uni() < 0.1; for (u32 i = 0; i < L; i++) o[i] = flip ? comp(lib[t0 + st + L - 1 - i]) : lib[t0 + st + i];
                for (u32 i = 0; i < L; i++) if (r.uni() < err) { char d; do d = B[r.below(4)]; while (d == o[i]); o[i] = d; } }
         bool tail = r.uni() < 0.1; u32 tail_at = tail ? 30 + (u32)r.below(L - 30) : L;
-        for (u32 i = 0; i < L; i++) { int v = i >= tail_at ? 2 : (int)std::lround(36.0 + 3.0 * r.normal()); if (v < 2) v = 2; if (v > 41) v = 41; q[i] = (u8)v; }
+        // Phred ~ N(36, 3) approximated by a sum of uniforms (Irwin-Hall, 8 x U[0,255]: sd = 209): no transcendental per base
+        for (u32 i = 0; i < L; i++) { int v = 2; if (i < tail_at) { u64 z = r.next(); int sum = 0; for (int k = 0; k < 8; k++) sum += (int)((z >> (8 * k)) & 255); v = 36 + (sum - 1020) * 3 / 209; if (v < 2) v = 2; if (v > 41) v = 41; } q[i] = (u8)v; }
       }
     }
   });
