@@ -399,3 +399,63 @@ def test_big_component_list_and_arena_paths():
             b1 = np.concatenate([o1, so1[1:] + o1[-1]]); b2 = np.concatenate([o2, so2[1:] + o2[-1]])
             res, ref = compare(ctx, o, cfg, a1, b1, a2, b2)
             assert ref["read_ec_len"].max() > 64      # the arena path really ran
+
+
+def test_tangled_orientations_all_configs():
+    """Adversarial library for the pair stage: features that contain each other's reverse complements, a feature that
+    carries one segment in both orientations, a reverse-palindromic feature (its fwd and §rev rows are identical), shared
+    and empty group strings.  Reads and mates in every orientation combination, then every chemistry x intersect level
+    x pair/hit filter combination is compared with the oracle's literal string pipeline."""
+    rng = np.random.default_rng(42)
+    rs = lambda n: "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    rc = lambda s: s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    f0 = rs(600)
+    f1 = rc(f0[100:400]) + rs(300)                 # F1 forward shares k-mers with F0 reverse
+    f2 = f0[0:300] + rs(50) + rc(f0[0:300])        # one segment in both orientations inside one feature
+    x = rs(200)
+    f3 = x + rc(x)                                 # reverse palindrome: F3 == revcomp(F3)
+    f4 = f0[:250] + rs(350)                        # plain sharing with F0 (same orientation)
+    f5 = rs(500)
+    f6 = f5[:200] + rc(f1[350:550]) + rs(100)
+    seqs = [f0, f1, f2, f3, f4, f5, f6]
+    names = ["T%d" % i for i in range(len(seqs))]
+    groups = ["gA", "gA", "", "gB", "gB", "", "gC"]
+    cfg0 = dict(synth.BASE_CONFIG, group_on="grp", num_mismatches=1)
+    obj = [cfg0, {"headers": ["sequence_name", "grp", "sequence"], "columns": [names, groups, seqs]}]
+    reads, mates = [], []
+    pool = seqs + [rc(s) for s in seqs]
+    for _ in range(2500):
+        a = pool[int(rng.integers(len(pool)))]
+        s = int(rng.integers(0, len(a) - 120)); r = a[s:s + 120]
+        k = rng.random()
+        if k < 0.4:      # proper FR mate from the same molecule
+            t = int(rng.integers(s, min(len(a) - 120, s + 200) + 1)); m = rc(a[t:t + 120])
+        elif k < 0.6:    # same orientation (FF / RR)
+            t = int(rng.integers(0, len(a) - 120)); m = a[t:t + 120]
+        elif k < 0.8:    # unrelated molecule
+            b = pool[int(rng.integers(len(pool)))]; t = int(rng.integers(0, len(b) - 120)); m = b[t:t + 120]
+        else:            # junk mate
+            m = rs(120)
+        if rng.random() < 0.1:
+            r = r[:60] + "ACGT"[("ACGT".index(r[60]) + 1) % 4] + r[61:]
+        reads.append(r); mates.append(m)
+    r1, o1 = orc.pack_reads(reads); r2, o2 = orc.pack_reads(mates)
+    n_callsets = 0
+    for group_on in ("grp", ""):
+        obj[0]["group_on"] = group_on
+        ocfg, oref, lib = make(obj, "unstranded", group_on)
+        ix = nb.build_index(lib, 2)
+        o = orc.Oracle(ocfg, oref)
+        assert o.index_dump() == ix.dump()
+        ctx = nb.Context(ix, lib)
+        for chem in CHEMS:
+            for level in (0, 1, 2):
+                for kw in (dict(), dict(require_valid_pair=True), dict(discard_multi_hits=1), dict(max_hits_to_report=1, discard_multiple_matches=True)):
+                    cfg = dict(ocfg, strand_filter=chem, intersect_level=level)
+                    cfg.update(kw)
+                    o.set_config(**cfg)
+                    res, ref = compare(ctx, o, cfg, r1, o1, r2, o2, check_ecs=(chem == "none" and level == 0 and not kw))
+                    n_callsets += len(res["rows"])
+        o.set_config(**dict(ocfg, strand_filter="fiveprime"))
+        compare(ctx, o, dict(ocfg, strand_filter="fiveprime"), r1, o1)     # single-end through the same logic
+    assert n_callsets > 200
