@@ -81,9 +81,9 @@ __global__ void __launch_bounds__(256) k_trim(BatchDev b, Tables t) {
 }
 
 // ------------------------------------------------------------------------------------------------ K2 map
-struct ReadView {   // one packed read: W consecutive words (read-major layout, zero padded)
-  const u64* p;
-  __device__ __forceinline__ u64 word(u32 w) const { return __ldg(p + w); }
+struct ReadView {   // one packed read: W words, zero padded; either global (read-major, stride 1) or a shared-memory column (stride 32)
+  const u64* p; u32 stride;
+  __device__ __forceinline__ u64 word(u32 w) const { return p[(size_t)w * stride]; }
   __device__ __forceinline__ u64 win(u32 pos) const {
     u32 w = pos >> 5, sh = (pos & 31) * 2; u64 lo = word(w);
     if (!sh) return lo;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
   // ---- read_key = R1 string + R2 string (untrimmed, after revcomp), src/align.rs:576-579 — hashed to 128 bits over
   // the concatenated 2-bit stream so that, like the reference's string concatenation, only the joined bases matter.
   u32 n1 = b.len_full[ri1], n2 = paired ? b.len_full[ri1 + 1] : 0, tot = n1 + n2;
-  ReadView rd1{b.pk + (u64)ri1 * b.W}, rd2{b.pk + (u64)(ri1 + 1) * b.W};
+  ReadView rd1{b.pk + (u64)ri1 * b.W, 1}, rd2{b.pk + (u64)(ri1 + 1) * b.W, 1};
   u64 h0 = 0x243F6A8885A308D3ULL, h1 = 0x13198A2E03707344ULL;
   for (u32 s = 0; s < tot; s += 32) {
     u64 w;

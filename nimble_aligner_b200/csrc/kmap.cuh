@@ -33,7 +33,7 @@ __device__ __forceinline__ bool probe_kmer(const DevIndex& ix, const ReadView& r
 // The warp searches the stride-3 seeds of lane l's read from position s_kp on; returns (to every lane) the first hit.
 __device__ __forceinline__ bool coop_find(const DevIndex& ix, const BatchDev& b, u32 lane, u32 s_ri, u32 s_kp, u32 s_last, u32& f_kp, u32& f_node, u32& f_off, u32& tried) {
   const unsigned FULL = 0xFFFFFFFFu;
-  ReadView srd{b.pk + (u64)s_ri * b.W};
+  ReadView srd{b.pk + (u64)s_ri * b.W, 1};
   tried = 0;
   for (u32 base = s_kp; base <= s_last; base += 96) {
     u32 my = base + 3 * lane, nd2 = 0, of2 = 0;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg
   // per-lane walk state
   int st = ST_DONE; bool has = false, first = true;
   u32 ri = 0, n = 0, cov = 0, mm = 0, kp = 0, node = 0, off = 0, last_kpos = 0;
-  ReadView rd{b.pk};
+  ReadView rd{b.pk, 1};
   EcAcc acc; acc.init(ix, t);
   for (;;) {
     // ---------------------------------------------------------------- (S) seed 32 fresh reads while the ring is low
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg
       if (COUNT_WORK && lane == 0) atomicAdd(&t.ctr->dbg[2], 1ULL);
       u32 q = base + lane; bool live = q < b.n_reads, seek = false, found = false;
       u32 qn = 0, qhdr = R_NO_MATCH, qkp = 0, qnode = 0, qoff = 0, qlast = 0;
-      ReadView qrd{b.pk + (u64)(live ? q : 0) * b.W};
+      ReadView qrd{b.pk + (u64)(live ? q : 0) * b.W, 1};
       if (live) {
         u32 side = b.sides == 2 ? (q & 1) : 0; u64 p = b.sides == 2 ? (q >> 1) : q;
         qn = b.len_trim[q];
@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg
       if (st == ST_DONE && rank < npop) {
         uint4 e = ring[(r_head + rank) % RING];
         ri = e.x; kp = e.y; node = e.z; off = e.w;
-        n = b.len_trim[ri]; last_kpos = n - K; rd.p = b.pk + (u64)ri * b.W;
+        n = b.len_trim[ri]; last_kpos = n - K;
+        rd.p = b.pk + (u64)ri * b.W; rd.stride = 1;   // (staging the read in shared memory was measured: no gain, +10 % time)
         cov = 0; mm = 0; acc.reset(); first = true; has = true; st = ST_WALK;
       }
       r_head = (r_head + npop) % RING; r_count -= npop;
