@@ -96,6 +96,9 @@ int nb_index_build(const nb_library* lib, int n_threads, nb_index** out);
 int nb_index_build_from_sequences(const uint8_t* seq_ascii, const uint64_t* seq_off, uint32_t n_seqs, int n_threads,
                                   nb_index** out);
 void nb_index_free(nb_index*);
+/* on-disk index cache: the flat arrays exactly as they are uploaded (the reference rebuilds its index on every run) */
+int nb_index_save(const nb_index*, const char* path);
+int nb_index_load(const char* path, nb_index** out);
 /* out[0..7] = n_kmers, n_nodes, n_colours, colour_elems, unitig_bases, table_slots, device_bytes, n_sequences */
 int nb_index_stats(const nb_index*, uint64_t* out8);
 /* canonical text dump (one line per unitig, sorted) used by the parity tests; returns bytes needed */

@@ -88,7 +88,8 @@ _SIGS = {
     "nb_library_n_groups": (C.c_uint32, [C.c_void_p]), "nb_library_group_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),
     "nb_index_build": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "nb_index_build_from_sequences": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]),
-    "nb_index_free": (None, [C.c_void_p]), "nb_index_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nb_index_free": (None, [C.c_void_p]),
+    "nb_index_save": (C.c_int, [C.c_void_p, C.c_char_p]), "nb_index_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]), "nb_index_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb_index_dump": (C.c_uint64, [C.c_void_p, C.c_char_p, C.c_uint64]),
     "nb_device_count": (C.c_int, []),
     "nb_ctx_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -243,6 +244,15 @@ class Index:
         if getattr(self, "h", None):
             lib().nb_index_free(self.h)
             self.h = None
+
+    def save(self, path):
+        _ck(lib().nb_index_save(self.h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path):
+        h = C.c_void_p()
+        _ck(lib().nb_index_load(str(path).encode(), C.byref(h)))
+        return cls(h)
 
     def stats(self):
         o = np.zeros(8, dtype=np.uint64)

@@ -302,3 +302,32 @@ uint64_t nb_index_dump(const nb_index* ix, char* buf, uint64_t cap) {
 }
 
 }  // extern "C"
+
+// ---- on-disk index cache: the flat arrays exactly as they are uploaded to HBM
+namespace {
+const char INDEX_MAGIC[8] = {'N', 'B', '2', 'I', 'D', 'X', '0', '3'};
+template <class T> bool put_vec(FILE* f, const std::vector<T>& v) { u64 n = v.size(); return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n); }
+template <class T> bool get_vec(FILE* f, std::vector<T>& v) { u64 n; if (fread(&n, 8, 1, f) != 1 || n > (1ULL << 40) / sizeof(T)) return false; v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
+}
+extern "C" int nb_index_save(const nb_index* ix, const char* path) {
+  if (!ix || !path) return fail(NB_ERR_INVALID, "null argument");
+  FILE* f = fopen(path, "wb"); if (!f) return fail(NB_ERR_IO, std::string("could not open ") + path);
+  u64 scalars[4] = {ix->table_mask, ix->n_kmers, ix->unitig_bases, ix->n_sequences};
+  bool ok = fwrite(INDEX_MAGIC, 8, 1, f) == 1 && fwrite(scalars, 8, 4, f) == 4 && put_vec(f, ix->table_key) && put_vec(f, ix->table_val) && put_vec(f, ix->unitig) &&
+            put_vec(f, ix->node) && put_vec(f, ix->redge) && put_vec(f, ix->ledge) && put_vec(f, ix->col_off) && put_vec(f, ix->col_ids) && put_vec(f, ix->col_meta);
+  ok = (fclose(f) == 0) && ok;
+  return ok ? NB_OK : fail(NB_ERR_IO, std::string("short write on ") + path);
+}
+extern "C" int nb_index_load(const char* path, nb_index** out) {
+  if (!path || !out) return fail(NB_ERR_INVALID, "null argument");
+  FILE* f = fopen(path, "rb"); if (!f) return fail(NB_ERR_IO, std::string("could not open ") + path);
+  nb_index* ix = new nb_index(); char magic[8]; u64 scalars[4];
+  bool ok = fread(magic, 8, 1, f) == 1 && !memcmp(magic, INDEX_MAGIC, 8) && fread(scalars, 8, 4, f) == 4 && get_vec(f, ix->table_key) && get_vec(f, ix->table_val) && get_vec(f, ix->unitig) &&
+            get_vec(f, ix->node) && get_vec(f, ix->redge) && get_vec(f, ix->ledge) && get_vec(f, ix->col_off) && get_vec(f, ix->col_ids) && get_vec(f, ix->col_meta);
+  fclose(f);
+  if (ok) { ix->table_mask = scalars[0]; ix->n_kmers = scalars[1]; ix->unitig_bases = scalars[2]; ix->n_sequences = scalars[3];
+    ok = ix->table_key.size() == 2 * (ix->table_mask + 1) && ix->table_val.size() == ix->table_key.size() && ix->redge.size() == 4 * ix->node.size() && ix->ledge.size() == ix->redge.size() &&
+         !ix->col_off.empty() && ix->col_meta.size() == 4 * (ix->col_off.size() - 1) && ix->unitig.size() >= (ix->unitig_bases + 31) / 32 + 2; }
+  if (!ok) { delete ix; return fail(NB_ERR_PARSE, std::string("not a nimble_b200 index file (or truncated): ") + path); }
+  *out = ix; return NB_OK;
+}

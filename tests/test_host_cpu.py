@@ -129,3 +129,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "import oracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
+
+
+def test_index_save_load_roundtrip(tmp_path):
+    _, lib = nb.get_reference_library(os.path.join(G, "libraries", "basic.json"))
+    ix = nb.build_index(lib, 2)
+    p = tmp_path / "basic.nbidx"
+    ix.save(p)
+    ix2 = nb.Index.load(p)
+    assert ix2.stats() == ix.stats() and ix2.dump() == ix.dump()
+    (tmp_path / "bad.nbidx").write_bytes(p.read_bytes()[:100])
+    with pytest.raises(nb.NbError):
+        nb.Index.load(tmp_path / "bad.nbidx")
+    with pytest.raises(nb.NbError):
+        nb.Index.load(tmp_path / "missing.nbidx")
