@@ -95,6 +95,16 @@ int nb_library_push_column(nb_library*, const char* header, const char* const* v
 int nb_index_build(const nb_library* lib, int n_threads, nb_index** out);
 int nb_index_build_from_sequences(const uint8_t* seq_ascii, const uint64_t* seq_off, uint32_t n_seqs, int n_threads,
                                   nb_index** out);
+/* K5: the same build on the GPU (sort / group / join / chain walk / cuckoo insertion as CUDA kernels); the artefact
+ * equals the host build's array for array, except where a k-mer sits among its four candidate table slots.  Falls
+ * back to the host builder for a library with pure k-mer cycles.  NB_ERR_CUDA when `device` is not usable. */
+int nb_index_build_gpu(const nb_library* lib, int device, int n_threads, nb_index** out);
+int nb_index_build_gpu_from_sequences(const uint8_t* seq_ascii, const uint64_t* seq_off, uint32_t n_seqs, int device,
+                                      int n_threads, nb_index** out);
+/* 0 when both artefacts describe the same index: all arrays equal and every k-mer of `a` resolves to the same
+ * (node, offset) in `b`; otherwise a positive code naming the first array that differs (1 scalars, 2 unitigs, 3 nodes,
+ * 4 edges, 5 colours, 6 universes, 7 table) */
+int nb_index_compare(const nb_index* a, const nb_index* b);
 void nb_index_free(nb_index*);
 /* on-disk index cache: the flat arrays exactly as they are uploaded (the reference rebuilds its index on every run) */
 int nb_index_save(const nb_index*, const char* path);

@@ -88,6 +88,9 @@ _SIGS = {
     "nb_library_n_groups": (C.c_uint32, [C.c_void_p]), "nb_library_group_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),
     "nb_index_build": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "nb_index_build_from_sequences": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]),
+    "nb_index_build_gpu": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "nb_index_build_gpu_from_sequences": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "nb_index_compare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb_index_free": (None, [C.c_void_p]),
     "nb_index_save": (C.c_int, [C.c_void_p, C.c_char_p]), "nb_index_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]), "nb_index_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb_index_dump": (C.c_uint64, [C.c_void_p, C.c_char_p, C.c_uint64]),
@@ -228,17 +231,28 @@ class Index:
         self.h = handle
 
     @classmethod
-    def build(cls, library, threads=1):
+    def build(cls, library, threads=1, device=None):
+        """device=None: host builder; device=i: the CUDA builder on GPU i (same artefact)."""
         h = C.c_void_p()
-        _ck(lib().nb_index_build(library.h, threads, C.byref(h)))
+        if device is None:
+            _ck(lib().nb_index_build(library.h, threads, C.byref(h)))
+        else:
+            _ck(lib().nb_index_build_gpu(library.h, device, threads, C.byref(h)))
         return cls(h)
 
     @classmethod
-    def from_sequences(cls, seqs, threads=1):
+    def from_sequences(cls, seqs, threads=1, device=None):
         data, off = pack_reads(seqs)
         h = C.c_void_p()
-        _ck(lib().nb_index_build_from_sequences(data.ctypes.data, off.ctypes.data, len(seqs), threads, C.byref(h)))
+        if device is None:
+            _ck(lib().nb_index_build_from_sequences(data.ctypes.data, off.ctypes.data, len(seqs), threads, C.byref(h)))
+        else:
+            _ck(lib().nb_index_build_gpu_from_sequences(data.ctypes.data, off.ctypes.data, len(seqs), device, threads, C.byref(h)))
         return cls(h)
+
+    def compare(self, other):
+        """0 when both artefacts describe the same index (nb_index_compare)."""
+        return lib().nb_index_compare(self.h, other.h)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -266,8 +280,8 @@ class Index:
         return buf.raw[:n].decode()
 
 
-def build_index(library, threads=1):
-    return Index.build(library, threads)
+def build_index(library, threads=1, device=None):
+    return Index.build(library, threads, device)
 
 
 def pack_reads(reads):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libnimble_b200.so")
 CLI = os.path.join(HERE, "nimble")
-SOURCES = ["library.cpp", "index_build.cpp", "fastq.cpp", "bam.cpp", "kernels.cu", "engine.cu"]
+SOURCES = ["library.cpp", "index_build.cpp", "fastq.cpp", "bam.cpp", "kernels.cu", "engine.cu", "index_build_gpu.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-extended-lambda",
          "-Xcompiler", "-fPIC,-pthread,-Wall,-Wno-unused-function", "-cudart", "shared"]

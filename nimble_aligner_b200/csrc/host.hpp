@@ -80,3 +80,5 @@ struct nb_index {
 };
 
 int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads, nb_index** out);
+int nb_build_universes(nb_index* ix, u32 n_seq);
+int nb_build_index_gpu(const std::vector<std::vector<u8>>& seqs, int device, int n_threads, nb_index** out);

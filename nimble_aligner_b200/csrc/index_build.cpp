@@ -65,6 +65,34 @@ struct Table {
 
 }  // namespace
 
+// Universes: connected components of sequences under "share a colour"; colours of components of <= 64 sequences get a
+// 64-bit mask over the component's sorted member list (appended to col_ids).  Shared by the host and the GPU builder.
+int nb_build_universes(nb_index* ix, u32 n_seq_arg) {
+    u32 n_col = (u32)ix->col_off.size() - 1, n_seq = n_seq_arg, n_ids = ix->col_off[n_col];
+    std::vector<u32> parent(n_seq);
+    for (u32 i = 0; i < n_seq; i++) parent[i] = i;
+    auto find = [&](u32 x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (u32 c = 0; c < n_col; c++) { u32 r0 = find(ix->col_ids[ix->col_off[c]]); for (u32 k = ix->col_off[c] + 1; k < ix->col_off[c + 1]; k++) { u32 r = find(ix->col_ids[k]); if (r != r0) parent[r] = r0; } }
+    std::vector<u32> comp_size(n_seq, 0), comp_off(n_seq, NONE32), fill(n_seq, 0);
+    for (u32 i = 0; i < n_seq; i++) comp_size[find(i)]++;
+    std::vector<char> used(n_seq, 0);
+    for (u32 c = 0; c < n_col; c++) used[find(ix->col_ids[ix->col_off[c]])] = 1;   // only components that own a colour
+    u64 at = n_ids;
+    for (u32 i = 0; i < n_seq; i++) if (used[i] && comp_size[i] <= 64) { comp_off[i] = (u32)at; at += comp_size[i]; }
+    if (at >= 0xFFFFFFFFull) return fail(NB_ERR_UNSUPPORTED, "colour table exceeds 2^32 entries");
+    ix->col_ids.resize(at);
+    for (u32 i = 0; i < n_seq; i++) { u32 r = find(i); if (comp_off[r] != NONE32) ix->col_ids[comp_off[r] + fill[r]++] = i; }   // ascending ids
+    ix->col_meta.assign(4 * (size_t)n_col, 0);
+    for (u32 c = 0; c < n_col; c++) {
+      u32 r = find(ix->col_ids[ix->col_off[c]]);
+      if (comp_off[r] == NONE32) continue;
+      const u32* u = &ix->col_ids[comp_off[r]]; u32 us = comp_size[r]; u64 mask = 0; u32 j = 0;
+      for (u32 k = ix->col_off[c]; k < ix->col_off[c + 1]; k++) { while (u[j] != ix->col_ids[k]) j++; mask |= 1ULL << j; }
+      ix->col_meta[4 * (size_t)c] = comp_off[r]; ix->col_meta[4 * (size_t)c + 1] = us; ix->col_meta[4 * (size_t)c + 2] = (u32)mask; ix->col_meta[4 * (size_t)c + 3] = (u32)(mask >> 32);
+    }
+    return NB_OK;
+}
+
 int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads, nb_index** out) {
   if (n_threads < 1) n_threads = 1;
   if (seqs.size() >= 0xFFFFFFFFull) return fail(NB_ERR_UNSUPPORTED, "too many reference sequences");
@@ -159,30 +187,7 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
       col[g] = c; prev_a = sig_a[g]; prev_b = sig_b[g]; prev_c = c;
     }
   }
-  {  // ---- 3b. universes: connected components of sequences under "share a colour"; small ones get bitmap colours
-    u32 n_col = (u32)ix->col_off.size() - 1, n_seq = (u32)seqs.size(), n_ids = ix->col_off[n_col];
-    std::vector<u32> parent(n_seq);
-    for (u32 i = 0; i < n_seq; i++) parent[i] = i;
-    auto find = [&](u32 x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
-    for (u32 c = 0; c < n_col; c++) { u32 r0 = find(ix->col_ids[ix->col_off[c]]); for (u32 k = ix->col_off[c] + 1; k < ix->col_off[c + 1]; k++) { u32 r = find(ix->col_ids[k]); if (r != r0) parent[r] = r0; } }
-    std::vector<u32> comp_size(n_seq, 0), comp_off(n_seq, NONE32), fill(n_seq, 0);
-    for (u32 i = 0; i < n_seq; i++) comp_size[find(i)]++;
-    std::vector<char> used(n_seq, 0);
-    for (u32 c = 0; c < n_col; c++) used[find(ix->col_ids[ix->col_off[c]])] = 1;   // only components that own a colour
-    u64 at = n_ids;
-    for (u32 i = 0; i < n_seq; i++) if (used[i] && comp_size[i] <= 64) { comp_off[i] = (u32)at; at += comp_size[i]; }
-    if (at >= 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "colour table exceeds 2^32 entries"); }
-    ix->col_ids.resize(at);
-    for (u32 i = 0; i < n_seq; i++) { u32 r = find(i); if (comp_off[r] != NONE32) ix->col_ids[comp_off[r] + fill[r]++] = i; }   // ascending ids
-    ix->col_meta.assign(4 * (size_t)n_col, 0);
-    for (u32 c = 0; c < n_col; c++) {
-      u32 r = find(ix->col_ids[ix->col_off[c]]);
-      if (comp_off[r] == NONE32) continue;
-      const u32* u = &ix->col_ids[comp_off[r]]; u32 us = comp_size[r]; u64 mask = 0; u32 j = 0;
-      for (u32 k = ix->col_off[c]; k < ix->col_off[c + 1]; k++) { while (u[j] != ix->col_ids[k]) j++; mask |= 1ULL << j; }
-      ix->col_meta[4 * (size_t)c] = comp_off[r]; ix->col_meta[4 * (size_t)c + 1] = us; ix->col_meta[4 * (size_t)c + 2] = (u32)mask; ix->col_meta[4 * (size_t)c + 3] = (u32)(mask >> 32);
-    }
-  }
+  { int urc = nb_build_universes(ix, (u32)seqs.size()); if (urc) { delete ix; return urc; } }
   std::vector<Occ>().swap(sorted); std::vector<u64>().swap(gstart); std::vector<u64>().swap(sig_a); std::vector<u64>().swap(sig_b);
   // ---- 4. bucketed cuckoo table over distinct k-mers (value = distinct index for now), load <= 0.5
   u64 slots = 16; while (slots < 2 * n) slots <<= 1;
@@ -278,6 +283,24 @@ int nb_index_build(const nb_library* lib, int n_threads, nb_index** out) {
   return nb_build_index_impl(seqs, n_threads, out);
 }
 void nb_index_free(nb_index* ix) { delete ix; }
+int nb_index_compare(const nb_index* a, const nb_index* b) {
+  if (!a || !b) return fail(NB_ERR_INVALID, "null argument");
+  if (a->n_kmers != b->n_kmers || a->unitig_bases != b->unitig_bases || a->n_sequences != b->n_sequences) return 1;
+  if (a->unitig != b->unitig) return 2;
+  if (a->node.size() != b->node.size() || (a->node.size() && memcmp(a->node.data(), b->node.data(), a->node.size() * sizeof(NodeRec)))) return 3;
+  if (a->redge != b->redge || a->ledge != b->ledge) return 4;
+  if (a->col_off != b->col_off || a->col_ids != b->col_ids) return 5;
+  if (a->col_meta != b->col_meta) return 6;
+  u64 na = 0, nbk = 0;
+  std::vector<u64> bk(b->table_key), bv(b->table_val);
+  Table tb{bk, bv, b->table_mask};
+  for (u64 h = 0; h < b->table_key.size(); h++) nbk += b->table_key[h] >> 63;
+  for (u64 h = 0; h < a->table_key.size(); h++) if (a->table_key[h] >> 63) {
+    na++; u64 s = tb.find(a->table_key[h] & KMASK);
+    if (s == ~0ULL || bv[s] != a->table_val[h]) return 7;
+  }
+  return (na == nbk && na == a->n_kmers) ? 0 : 7;
+}
 int nb_index_stats(const nb_index* ix, uint64_t* o) {
   if (!ix || !o) return fail(NB_ERR_INVALID, "null argument");
   o[0] = ix->n_kmers; o[1] = ix->node.size(); o[2] = ix->col_off.size() - 1; o[3] = ix->col_off.back(); o[4] = ix->unitig_bases;

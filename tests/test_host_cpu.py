@@ -143,3 +143,17 @@ def test_index_save_load_roundtrip(tmp_path):
         nb.Index.load(tmp_path / "bad.nbidx")
     with pytest.raises(nb.NbError):
         nb.Index.load(tmp_path / "missing.nbidx")
+
+
+def test_index_compare_and_gpu_builder_fails_loudly_without_a_gpu():
+    rnd = random.Random(9)
+    rs = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))
+    core = rs(50)
+    seqs = [core + rs(60), rs(20) + core, rs(90)]
+    a, b = nb.Index.from_sequences(seqs, 1), nb.Index.from_sequences(seqs, 4)
+    assert a.compare(b) == 0
+    assert a.compare(nb.Index.from_sequences(seqs[:2] + [rs(90)], 1)) != 0
+    if nb.lib().nb_device_count() == 0:
+        with pytest.raises(nb.NbError) as e:
+            nb.Index.from_sequences(seqs, 1, device=0)
+        assert e.value.code == -6
