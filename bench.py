@@ -327,7 +327,8 @@ def main():
                       "pairs_per_gpu": n, "reads_per_step": n_reads * world, "chunk_pairs": args.chunk, "l2": "inputs (%.1f GB ASCII per step) exceed the 126 MB L2" % ((int(o1[-1]) + int(o2[-1])) / 1e9),
                       "index_device_mb": ix.stats()["device_bytes"] / 1e6, "index_build_s": index_build_s, "unique_pair_keys": int(uniq_dev), "callsets_counted": len(counts_dev)},
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_host},
-           "gpu_launches": ks["launches"], "clocks": clocks}
+           "gpu_launches": ks["launches"], "clocks": clocks,
+           "k_map_ms_per_launch": ks["map_ms"] / max(1, ks["map_launches"]), "k_map_reads_per_launch": ks["map_reads"] / max(1, ks["map_launches"])}
     # ---- cpu baseline + roofline (rank 0, N=1 only)
     if world == 1 and not args.no_cpu_baseline:
         import oracle as orc

@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libnimble_b200.so")
+SO_PATH = os.environ.get("NIMBLE_B200_SO") or os.path.join(_HERE, "libnimble_b200.so")   # the override selects a tuning build (scripts/build_variant.sh)
 
 CHEM = {"unstranded": 0, "fiveprime": 1, "threeprime": 2, "none": 3}
 REASONS = ["ScoreBelowThreshold", "DiscardedMultipleMatch", "DiscardedNonzeroMismatch", "NoMatch", "NoMatchAndScoreBelowThreshold",

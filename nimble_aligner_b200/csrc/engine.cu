@@ -74,7 +74,7 @@ struct nb_ctx {
   // host batches: two staging sets filled on a copy stream so that the H2D of chunk i+1 overlaps the kernels of chunk i
   struct Staging { DBuf a[2], off[2], q[2], f[2], scope, cell; cudaEvent_t copied = nullptr, consumed = nullptr; bool used = false; } stg[2];
   int stg_next = 0; cudaStream_t cstream = nullptr;
-  DBuf d_pk, d_lenfull, d_lentrim, d_rres, d_pres, d_rout;
+  DBuf d_pk, d_lenfull, d_lentrim, d_rres, d_pres, d_rout, d_seeded;
   // state
   int mode = -1;  // -1 unset, 0 whole-run scope (keys persist), 1 scoped (keys live for one batch)
   bool folded = false;
@@ -171,8 +171,8 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&c->stg[i].copied, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->stg[i].consumed, cudaEventDisableTiming) != cudaSuccess) { nb_ctx_free(c); return fail(NB_ERR_CUDA, "cudaEventCreate failed"); }
   int rc = NB_OK;
   auto up = [&](cudaError_t e) { if (e != cudaSuccess && rc == NB_OK) rc = fail(NB_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e)); };
-  up(upload(c->d_tkey, index->table_key, s)); up(upload(c->d_tval, index->table_val, s)); up(upload(c->d_unitig, index->unitig, s));
-  up(upload(c->d_node, index->node, s)); up(upload(c->d_redge, index->redge, s)); up(upload(c->d_ledge, index->ledge, s));
+  up(upload(c->d_unitig, index->unitig, s)); up(upload(c->d_ledge, index->ledge, s));
+  up(upload(c->d_tkey, index->table_key, s)); up(upload(c->d_tval, index->table_val, s)); up(upload(c->d_node, index->node, s)); up(upload(c->d_redge, index->redge, s));
   up(upload(c->d_coloff, index->col_off, s)); up(upload(c->d_colids, index->col_ids, s)); up(upload(c->d_colmeta, index->col_meta, s));
   up(upload(c->d_rowfid, lib->row_fid, s)); up(upload(c->d_rowrev, lib->row_rev, s)); up(upload(c->d_rowof, lib->row_of, s)); up(upload(c->d_featgroup, lib->feat_group, s));
   {  // entropy terms f*log2(f), f = c/n, for every read length n <= ENT_NMAX (src/utils.rs:96-119)
@@ -183,8 +183,8 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   }
   if (rc == NB_OK) { cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) rc = fail(NB_ERR_CUDA, cudaGetErrorString(e)); }
   if (rc != NB_OK) { nb_ctx_free(c); return rc; }
-  c->dix.tkey = (const u64*)c->d_tkey.p; c->dix.tval = (const u64*)c->d_tval.p; c->dix.tmask = index->table_mask; c->dix.unitig = (const u64*)c->d_unitig.p;
-  c->dix.node = (const uint4*)c->d_node.p; c->dix.redge = (const uint4*)c->d_redge.p; c->dix.ledge = (const uint4*)c->d_ledge.p;
+  c->dix.n_buckets = (u32)index->table_buckets; c->dix.unitig = (const u64*)c->d_unitig.p; c->dix.ledge = (const uint4*)c->d_ledge.p;
+  c->dix.tkey = (const u64*)c->d_tkey.p; c->dix.tval = (const u64*)c->d_tval.p; c->dix.node = (const uint4*)c->d_node.p; c->dix.redge = (const uint4*)c->d_redge.p;
   c->dix.col_off = (const u32*)c->d_coloff.p; c->dix.col_ids = (const u32*)c->d_colids.p; c->dix.col_meta = (const uint4*)c->d_colmeta.p;
   c->dlib.row_fid = (const u32*)c->d_rowfid.p; c->dlib.row_rev = (const u8*)c->d_rowrev.p; c->dlib.row_of = (const u32*)c->d_rowof.p; c->dlib.feat_group = (const u32*)c->d_featgroup.p; c->dlib.n_rows = lib->n_rows();
   rc = apply_config(c, lib->cfg);
@@ -198,10 +198,10 @@ void nb_ctx_free(nb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->cstream) cudaStreamSynchronize(c->cstream);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_unitig, &c->d_node, &c->d_redge, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
+  DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_node, &c->d_redge, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
                  &c->d_ent, &c->d_ls, &c->d_qp, &c->d_mincov, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
                  &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].scope, &c->stg[0].cell,
-                 &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout};
+                 &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded};
   for (DBuf* b : all) b->release();
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -292,9 +292,9 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   }
   if (host) { CK(cudaEventRecord(S->copied, cs)); CK(cudaStreamWaitEvent(s, S->copied, 0)); }
   CK(c->d_pk.ensure((size_t)b.W * nr * 8, s)); CK(c->d_lenfull.ensure(nr * 4, s)); CK(c->d_lentrim.ensure(nr * 4, s));
-  CK(c->d_rres.ensure(nr * sizeof(nbk::ReadRes), s)); CK(c->d_pres.ensure(np * sizeof(nbk::PairRes), s));
+  CK(c->d_rres.ensure(nr * sizeof(nbk::ReadRes), s)); CK(c->d_pres.ensure(np * sizeof(nbk::PairRes), s)); CK(c->d_seeded.ensure(nr * 16, s));
   if (c->mode == 1) { CK(c->d_pslot.ensure(np * 8, s)); CK(c->d_pres2.ensure(np * sizeof(nbk::PairRes), s)); b.pslot = (u64*)c->d_pslot.p; b.pres2 = (nbk::PairRes*)c->d_pres2.p; }
-  b.pk = (u64*)c->d_pk.p; b.len_full = (u32*)c->d_lenfull.p; b.len_trim = (u32*)c->d_lentrim.p; b.rres = (nbk::ReadRes*)c->d_rres.p; b.pres = (nbk::PairRes*)c->d_pres.p;
+  b.pk = (u64*)c->d_pk.p; b.len_full = (u32*)c->d_lenfull.p; b.len_trim = (u32*)c->d_lentrim.p; b.rres = (nbk::ReadRes*)c->d_rres.p; b.pres = (nbk::PairRes*)c->d_pres.p; b.seeded = (uint4*)c->d_seeded.p;
   // key-table capacity
   if (c->mode == 0) {
     if (2 * (c->keys_upper + np) > c->key_slots) {
@@ -308,7 +308,7 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
     c->keys_upper += np;
   } else if (2 * np > c->key_slots) { int rc = grow_keys(c, 2 * np); if (rc) return rc; }
   Tables t = make_tables(c);
-  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->arena_top, 0, 16, s));   // arena_top + queue
+  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->arena_top, 0, 32, s));   // arena_top, queue, seeded_n, wqueue
   nbk::launch_pack(b, s); c->all_launches++;
   if (b.q[0] || b.q[1]) { nbk::launch_trim(b, t, s); c->all_launches++; }
   std::pair<cudaEvent_t, cudaEvent_t> ev;

@@ -64,7 +64,7 @@ struct nb_index {
   // bucketed cuckoo table: bucket b = slots 2b, 2b+1; a k-mer lives in one of its two candidate buckets (khash.h)
   std::vector<u64> table_key;  // device k-mer form (first base in the low bits) | bit63 set when occupied
   std::vector<u64> table_val;  // node | off<<32
-  u64 table_mask = 0;          // bucket mask = n_buckets - 1
+  u64 table_buckets = 0;       // n_buckets (any size, khash.h); table_key.size() == 2 * n_buckets
   std::vector<u64> unitig;     // 2-bit packed, base i at bits 2*(i&31) of word i>>5, 2 zero pad words
   std::vector<NodeRec> node;
   std::vector<u32> redge, ledge;  // 4 per node, NONE32 when absent

@@ -38,21 +38,22 @@ void parallel_for(int n_threads, u64 n, const std::function<void(u64, u64, int)>
 // Bucketed cuckoo table: two candidate buckets of two slots each (nb_cuckoo_buckets), so a lookup is exactly two
 // 16-byte loads and four compares — no probe loop (the device k_map is issue/divergence bound, not bandwidth bound).
 struct Table {
-  std::vector<u64>& key; std::vector<u64>& val; u64 bmask;
+  const std::vector<u64>& ckey; std::vector<u64>* mkey; std::vector<u64>* mval; u64 nbuckets;
   // returns slot of kmer (device form) or ~0
   u64 find(u64 dk) const {
-    u32 b1, b2; nb_cuckoo_buckets(dk, bmask, b1, b2); u64 want = dk | (1ULL << 63);
-    if (key[2 * (u64)b1] == want) return 2 * (u64)b1;
-    if (key[2 * (u64)b1 + 1] == want) return 2 * (u64)b1 + 1;
-    if (key[2 * (u64)b2] == want) return 2 * (u64)b2;
-    if (key[2 * (u64)b2 + 1] == want) return 2 * (u64)b2 + 1;
+    u32 b1, b2; nb_cuckoo_buckets(dk, nbuckets, b1, b2); u64 want = dk | (1ULL << 63);
+    if (ckey[2 * (u64)b1] == want) return 2 * (u64)b1;
+    if (ckey[2 * (u64)b1 + 1] == want) return 2 * (u64)b1 + 1;
+    if (ckey[2 * (u64)b2] == want) return 2 * (u64)b2;
+    if (ckey[2 * (u64)b2 + 1] == want) return 2 * (u64)b2 + 1;
     return ~0ULL;
   }
   // sequential cuckoo insertion (random-walk eviction); false if a cycle could not be resolved
   bool insert(u64 dk, u64 v) {
+    std::vector<u64>& key = *mkey; std::vector<u64>& val = *mval;
     u64 k = dk | (1ULL << 63); u64 rng = dk * 0x9E3779B97F4A7C15ULL + 1;
-    for (int kick = 0; kick < 500; kick++) {
-      u32 b1, b2; nb_cuckoo_buckets(k & KMASK, bmask, b1, b2);
+    for (int kick = 0; kick < 2000; kick++) {
+      u32 b1, b2; nb_cuckoo_buckets(k & KMASK, nbuckets, b1, b2);
       u64 cand[4] = {2 * (u64)b1, 2 * (u64)b1 + 1, 2 * (u64)b2, 2 * (u64)b2 + 1};
       for (u64 c : cand) if (!key[c]) { key[c] = k; val[c] = v; return true; }
       rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
@@ -190,18 +191,18 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
   { int urc = nb_build_universes(ix, (u32)seqs.size()); if (urc) { delete ix; return urc; } }
   std::vector<Occ>().swap(sorted); std::vector<u64>().swap(gstart); std::vector<u64>().swap(sig_a); std::vector<u64>().swap(sig_b);
   // ---- 4. bucketed cuckoo table over distinct k-mers (value = distinct index for now), load <= 0.5
-  u64 slots = 16; while (slots < 2 * n) slots <<= 1;
-  for (;;) {
-    if (slots / 2 - 1 > 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "k-mer table exceeds 2^33 slots"); }
-    ix->table_mask = slots / 2 - 1;   // bucket mask
+  u64 slots = 0;
+  for (int attempt = 0;; attempt++) {
+    u64 nbk = nb_cuckoo_size(n, attempt);
+    if (nbk > 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "k-mer table exceeds 2^33 slots"); }
+    ix->table_buckets = nbk; slots = 2 * nbk;
     ix->table_key.assign(slots, 0); ix->table_val.assign(slots, 0);
-    Table tb{ix->table_key, ix->table_val, ix->table_mask};
+    Table tb{ix->table_key, &ix->table_key, &ix->table_val, nbk};
     bool ok = true;
     for (u64 g = 0; g < n && ok; g++) ok = tb.insert(to_device_form(kmers[g]), g);
-    if (ok) break;
-    slots <<= 1;                      // practically never at load <= 0.5 with 2x2 cuckoo (threshold ~0.9)
+    if (ok) break;                    // load 0.75 is well under the 2x2 cuckoo threshold (~0.89): retries are practically never needed
   }
-  Table tab{ix->table_key, ix->table_val, ix->table_mask};
+  Table tab{ix->table_key, nullptr, nullptr, ix->table_buckets};
   auto index_of = [&](u64 be) -> u64 { u64 s = tab.find(to_device_form(be)); return s == ~0ULL ? ~0ULL : ix->table_val[s]; };
   // ---- 5. join relation
   std::vector<u32> succ(n, NONE32), pred(n, NONE32);
@@ -292,8 +293,8 @@ int nb_index_compare(const nb_index* a, const nb_index* b) {
   if (a->col_off != b->col_off || a->col_ids != b->col_ids) return 5;
   if (a->col_meta != b->col_meta) return 6;
   u64 na = 0, nbk = 0;
-  std::vector<u64> bk(b->table_key), bv(b->table_val);
-  Table tb{bk, bv, b->table_mask};
+  const std::vector<u64>& bv = b->table_val;
+  Table tb{b->table_key, nullptr, nullptr, b->table_buckets};
   for (u64 h = 0; h < b->table_key.size(); h++) nbk += b->table_key[h] >> 63;
   for (u64 h = 0; h < a->table_key.size(); h++) if (a->table_key[h] >> 63) {
     na++; u64 s = tb.find(a->table_key[h] & KMASK);
@@ -328,14 +329,14 @@ uint64_t nb_index_dump(const nb_index* ix, char* buf, uint64_t cap) {
 
 // ---- on-disk index cache: the flat arrays exactly as they are uploaded to HBM
 namespace {
-const char INDEX_MAGIC[8] = {'N', 'B', '2', 'I', 'D', 'X', '0', '3'};
+const char INDEX_MAGIC[8] = {'N', 'B', '2', 'I', 'D', 'X', '0', '4'};
 template <class T> bool put_vec(FILE* f, const std::vector<T>& v) { u64 n = v.size(); return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n); }
 template <class T> bool get_vec(FILE* f, std::vector<T>& v) { u64 n; if (fread(&n, 8, 1, f) != 1 || n > (1ULL << 40) / sizeof(T)) return false; v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
 }
 extern "C" int nb_index_save(const nb_index* ix, const char* path) {
   if (!ix || !path) return fail(NB_ERR_INVALID, "null argument");
   FILE* f = fopen(path, "wb"); if (!f) return fail(NB_ERR_IO, std::string("could not open ") + path);
-  u64 scalars[4] = {ix->table_mask, ix->n_kmers, ix->unitig_bases, ix->n_sequences};
+  u64 scalars[4] = {ix->table_buckets, ix->n_kmers, ix->unitig_bases, ix->n_sequences};
   bool ok = fwrite(INDEX_MAGIC, 8, 1, f) == 1 && fwrite(scalars, 8, 4, f) == 4 && put_vec(f, ix->table_key) && put_vec(f, ix->table_val) && put_vec(f, ix->unitig) &&
             put_vec(f, ix->node) && put_vec(f, ix->redge) && put_vec(f, ix->ledge) && put_vec(f, ix->col_off) && put_vec(f, ix->col_ids) && put_vec(f, ix->col_meta);
   ok = (fclose(f) == 0) && ok;
@@ -348,8 +349,8 @@ extern "C" int nb_index_load(const char* path, nb_index** out) {
   bool ok = fread(magic, 8, 1, f) == 1 && !memcmp(magic, INDEX_MAGIC, 8) && fread(scalars, 8, 4, f) == 4 && get_vec(f, ix->table_key) && get_vec(f, ix->table_val) && get_vec(f, ix->unitig) &&
             get_vec(f, ix->node) && get_vec(f, ix->redge) && get_vec(f, ix->ledge) && get_vec(f, ix->col_off) && get_vec(f, ix->col_ids) && get_vec(f, ix->col_meta);
   fclose(f);
-  if (ok) { ix->table_mask = scalars[0]; ix->n_kmers = scalars[1]; ix->unitig_bases = scalars[2]; ix->n_sequences = scalars[3];
-    ok = ix->table_key.size() == 2 * (ix->table_mask + 1) && ix->table_val.size() == ix->table_key.size() && ix->redge.size() == 4 * ix->node.size() && ix->ledge.size() == ix->redge.size() &&
+  if (ok) { ix->table_buckets = scalars[0]; ix->n_kmers = scalars[1]; ix->unitig_bases = scalars[2]; ix->n_sequences = scalars[3];
+    ok = ix->table_buckets >= 2 && ix->table_key.size() == 2 * ix->table_buckets && ix->table_val.size() == ix->table_key.size() && ix->redge.size() == 4 * ix->node.size() && ix->ledge.size() == ix->redge.size() &&
          !ix->col_off.empty() && ix->col_meta.size() == 4 * (ix->col_off.size() - 1) && ix->unitig.size() >= (ix->unitig_bases + 31) / 32 + 2; }
   if (!ok) { delete ix; return fail(NB_ERR_PARSE, std::string("not a nimble_b200 index file (or truncated): ") + path); }
   *out = ix; return NB_OK;

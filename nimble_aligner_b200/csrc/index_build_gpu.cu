@@ -146,12 +146,12 @@ __global__ void k_write_unitigs(const u64* kmers, const u32* succ, const u32* no
   node[i] = nr;
 }
 // concurrent bucketed cuckoo insertion (2 candidate buckets x 2 slots); only keys move, values are filled afterwards
-__global__ void k_cuckoo_insert(const u64* kmers, u64 n, unsigned long long* tkey, u64 bmask, int* failed) {
+__global__ void k_cuckoo_insert(const u64* kmers, u64 n, unsigned long long* tkey, u64 nbuckets, int* failed) {
   u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (g >= n) return;
   unsigned long long k = to_dev_form(kmers[g]) | (1ULL << 63); u64 rng = k * 0x9E3779B97F4A7C15ULL + g;
   for (int kick = 0; kick < 2000; kick++) {
-    u32 b1, b2; nb_cuckoo_buckets(k & KMASK, bmask, b1, b2);
+    u32 b1, b2; nb_cuckoo_buckets(k & KMASK, nbuckets, b1, b2);
     u64 cand[4] = {2 * (u64)b1, 2 * (u64)b1 + 1, 2 * (u64)b2, 2 * (u64)b2 + 1};
     for (int c = 0; c < 4; c++) if (atomicCAS(tkey + cand[c], 0ULL, k) == 0ULL) return;
     rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
@@ -293,17 +293,15 @@ int nb_build_index_gpu(const std::vector<std::vector<u8>>& seqs, int device, int
       ix->node.resize(n_nodes); GCK(cudaMemcpy(ix->node.data(), d_node, (size_t)n_nodes * sizeof(NodeRec), cudaMemcpyDeviceToHost)); }
     // 8. cuckoo table
     GCK(M.alloc(&d_flagint, 2));
-    slots = 16; while (slots < 2 * n) slots <<= 1;
-    for (;;) {
-      if (slots / 2 - 1 > 0xFFFFFFFFull) { rc = fail(NB_ERR_UNSUPPORTED, "k-mer table exceeds 2^33 slots"); goto done; }
+    for (int attempt = 0;; attempt++) {
+      u64 nbk = nb_cuckoo_size(n, attempt); slots = 2 * nbk;
+      if (nbk > 0xFFFFFFFFull) { rc = fail(NB_ERR_UNSUPPORTED, "k-mer table exceeds 2^33 slots"); goto done; }
       if (d_tkey) { cudaFree(d_tkey); d_tkey = nullptr; }
       GCK(cudaMalloc(&d_tkey, slots * 8)); GCK(cudaMemset(d_tkey, 0, slots * 8)); GCK(cudaMemset(d_flagint, 0, 8));
-      k_cuckoo_insert<<<nblk(n), 256>>>(d_kmers, n, d_tkey, slots / 2 - 1, d_flagint);
+      k_cuckoo_insert<<<nblk(n), 256>>>(d_kmers, n, d_tkey, nbk, d_flagint);
       GCK(cudaMemcpy(hflag, d_flagint, 8, cudaMemcpyDeviceToHost));
-      if (!hflag[0]) break;
-      slots <<= 1;
+      if (!hflag[0]) { ix->table_buckets = nbk; break; }
     }
-    ix->table_mask = slots / 2 - 1;
     GCK(M.alloc(&d_tval, slots)); GCK(cudaMemset(d_tval, 0, slots * 8));
     k_table_values<<<nblk(slots), 256>>>(d_tkey, slots, d_kmers, n, d_node_of, d_off_of, d_tval);
     ix->table_key.resize(slots); ix->table_val.resize(slots);

@@ -29,10 +29,11 @@ constexpr int GL_MAX = 64;                 // per-thread group list capacity (ma
 constexpr int ENT_NMAX = 1024;             // longest read the entropy table covers
 
 struct DevIndex {
-  const u64* tkey; const u64* tval; u64 tmask;
+  const u64* tkey; const u64* tval; u32 n_buckets;   // bucketed cuckoo table (khash.h): bucket b = keys 2b, 2b+1 (one 16-byte load), values apart
   const u64* unitig;
   const uint4* node;      // {start_lo, len, colour, lext | rext<<4 | start_hi<<8}
-  const uint4* redge; const uint4* ledge;
+  const uint4* redge;
+  const uint4* ledge;
   const u32* col_off; const u32* col_ids;
   const uint4* col_meta;  // {uni_off, uni_size (0: none), mask_lo, mask_hi} per colour (host.hpp nb_index::col_meta)
 };
@@ -45,7 +46,7 @@ struct DevCfg {
 // device-side error bits (Counters::err)
 enum { E_ARENA = 1, E_CS_FULL = 2, E_KEY_FULL = 4, E_FEATURE = 8, E_AGG_FULL = 16, E_GCAP = 32 };
 struct Counters {
-  unsigned long long arena_top; unsigned long long queue;   // both zeroed before every k_map launch
+  unsigned long long arena_top, queue, seeded_n, wqueue;   // all four zeroed before every map launch (seeded_n / wqueue: k_seed -> k_walk list)
   unsigned long long n_keys; unsigned long long n_callsets; unsigned long long n_agg;
   unsigned long long probes, nodes, bases, colour_elems;   // work counters (roofline numerator cross-check)
   unsigned int err; unsigned int pad;
@@ -68,6 +69,7 @@ struct BatchDev {
   const u8* a[2]; const u64* off[2]; const u8* q[2]; const u8* flags[2]; const u32* scope; const u32* cell;
   u64* pk; u32* len_full; u32* len_trim;                  // pk[ri * W + w] (read-major), ri = p*sides + side
   ReadRes* rres; PairRes* pres;
+  uint4* seeded;                                         // k_seed -> k_walk: {read, seed position, node, offset} of every read that found a seed
   u64* pslot; PairRes* pres2;                            // scoped batches: key slot per pair, per-key resolved records
   u64 order_base;
 };
