@@ -61,10 +61,10 @@ struct nb_library {
 // Flat index artefact (DESIGN.md "Index layout"); the same bytes are uploaded to HBM.
 struct NodeRec { u32 start_lo; u32 len; u32 colour; u32 exts_hi; };  // exts_hi: lext | rext<<4 | start_hi<<8
 struct nb_index {
-  // bucketed cuckoo table: bucket b = slots 2b, 2b+1; a k-mer lives in one of its two candidate buckets (khash.h)
+  // k-mer table (khash.h): bucket b = slots 4b .. 4b+3 (one 32-byte sector of keys); home bucket or the next with room
   std::vector<u64> table_key;  // device k-mer form (first base in the low bits) | bit63 set when occupied
   std::vector<u64> table_val;  // node | off<<32
-  u64 table_buckets = 0;       // n_buckets (any size, khash.h); table_key.size() == 2 * n_buckets
+  u64 table_buckets = 0;       // n_buckets (any size, khash.h); table_key.size() == 4 * n_buckets
   std::vector<u64> unitig;     // 2-bit packed, base i at bits 2*(i&31) of word i>>5, 2 zero pad words
   std::vector<NodeRec> node;
   std::vector<u32> redge, ledge;  // 4 per node, NONE32 when absent

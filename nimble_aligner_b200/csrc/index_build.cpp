@@ -6,7 +6,7 @@
 // sorted set of sequence ids containing the k-mer; exts = bases observed before / after any occurrence; unitigs join
 // x -> y iff |R(x)| == 1, |L(y)| == 1 and colour(x) == colour(y); a pure cycle starts at its smallest k-mer.
 // Method here (not the upstream's minimizer shards + MPHF): enumerate occurrences, bucketed parallel sort, group,
-// open-addressed table (linear probing, load <= 0.5) over the distinct k-mers, chain walk by list ranking on threads.
+// open-addressed bucketed table (khash.h) over the distinct k-mers, chain walk from the chain starts on threads.
 #include <algorithm>
 #include <atomic>
 #include <cstring>
@@ -35,32 +35,25 @@ void parallel_for(int n_threads, u64 n, const std::function<void(u64, u64, int)>
   for (auto& x : th) x.join();
 }
 
-// Bucketed cuckoo table: two candidate buckets of two slots each (nb_cuckoo_buckets), so a lookup is exactly two
-// 16-byte loads and four compares — no probe loop (the device k_map is issue/divergence bound, not bandwidth bound).
+// k-mer table (khash.h): buckets of four keys, linear probing by bucket.
 struct Table {
   const std::vector<u64>& ckey; std::vector<u64>* mkey; std::vector<u64>* mval; u64 nbuckets;
   // returns slot of kmer (device form) or ~0
   u64 find(u64 dk) const {
-    u32 b1, b2; nb_cuckoo_buckets(dk, nbuckets, b1, b2); u64 want = dk | (1ULL << 63);
-    if (ckey[2 * (u64)b1] == want) return 2 * (u64)b1;
-    if (ckey[2 * (u64)b1 + 1] == want) return 2 * (u64)b1 + 1;
-    if (ckey[2 * (u64)b2] == want) return 2 * (u64)b2;
-    if (ckey[2 * (u64)b2 + 1] == want) return 2 * (u64)b2 + 1;
+    u64 b = nb_table_bucket(dk, nbuckets), want = dk | (1ULL << 63);
+    for (u64 tries = 0; tries < nbuckets; tries++) {
+      for (u64 s = 4 * b; s < 4 * b + 4; s++) { if (ckey[s] == want) return s; if (!ckey[s]) return ~0ULL; }
+      if (++b == nbuckets) b = 0;
+    }
     return ~0ULL;
   }
-  // sequential cuckoo insertion (random-walk eviction); false if a cycle could not be resolved
-  bool insert(u64 dk, u64 v) {
+  void insert(u64 dk, u64 v) {   // distinct keys, load < 1: always finds room
     std::vector<u64>& key = *mkey; std::vector<u64>& val = *mval;
-    u64 k = dk | (1ULL << 63); u64 rng = dk * 0x9E3779B97F4A7C15ULL + 1;
-    for (int kick = 0; kick < 2000; kick++) {
-      u32 b1, b2; nb_cuckoo_buckets(k & KMASK, nbuckets, b1, b2);
-      u64 cand[4] = {2 * (u64)b1, 2 * (u64)b1 + 1, 2 * (u64)b2, 2 * (u64)b2 + 1};
-      for (u64 c : cand) if (!key[c]) { key[c] = k; val[c] = v; return true; }
-      rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
-      u64 c = cand[rng & 3];
-      std::swap(k, key[c]); std::swap(v, val[c]);
+    u64 b = nb_table_bucket(dk, nbuckets);
+    for (;;) {
+      for (u64 s = 4 * b; s < 4 * b + 4; s++) if (!key[s]) { key[s] = dk | (1ULL << 63); val[s] = v; return; }
+      if (++b == nbuckets) b = 0;
     }
-    return false;
   }
 };
 
@@ -192,15 +185,13 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
   std::vector<Occ>().swap(sorted); std::vector<u64>().swap(gstart); std::vector<u64>().swap(sig_a); std::vector<u64>().swap(sig_b);
   // ---- 4. bucketed cuckoo table over distinct k-mers (value = distinct index for now), load <= 0.5
   u64 slots = 0;
-  for (int attempt = 0;; attempt++) {
-    u64 nbk = nb_cuckoo_size(n, attempt);
-    if (nbk > 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "k-mer table exceeds 2^33 slots"); }
-    ix->table_buckets = nbk; slots = 2 * nbk;
+  {
+    u64 nbk = nb_table_size(n);
+    if (nbk > 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "k-mer table exceeds 2^34 slots"); }
+    ix->table_buckets = nbk; slots = 4 * nbk;
     ix->table_key.assign(slots, 0); ix->table_val.assign(slots, 0);
     Table tb{ix->table_key, &ix->table_key, &ix->table_val, nbk};
-    bool ok = true;
-    for (u64 g = 0; g < n && ok; g++) ok = tb.insert(to_device_form(kmers[g]), g);
-    if (ok) break;                    // load 0.75 is well under the 2x2 cuckoo threshold (~0.89): retries are practically never needed
+    for (u64 g = 0; g < n; g++) tb.insert(to_device_form(kmers[g]), g);
   }
   Table tab{ix->table_key, nullptr, nullptr, ix->table_buckets};
   auto index_of = [&](u64 be) -> u64 { u64 s = tab.find(to_device_form(be)); return s == ~0ULL ? ~0ULL : ix->table_val[s]; };
@@ -329,7 +320,7 @@ uint64_t nb_index_dump(const nb_index* ix, char* buf, uint64_t cap) {
 
 // ---- on-disk index cache: the flat arrays exactly as they are uploaded to HBM
 namespace {
-const char INDEX_MAGIC[8] = {'N', 'B', '2', 'I', 'D', 'X', '0', '4'};
+const char INDEX_MAGIC[8] = {'N', 'B', '2', 'I', 'D', 'X', '0', '5'};
 template <class T> bool put_vec(FILE* f, const std::vector<T>& v) { u64 n = v.size(); return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n); }
 template <class T> bool get_vec(FILE* f, std::vector<T>& v) { u64 n; if (fread(&n, 8, 1, f) != 1 || n > (1ULL << 40) / sizeof(T)) return false; v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
 }
@@ -350,7 +341,7 @@ extern "C" int nb_index_load(const char* path, nb_index** out) {
             get_vec(f, ix->node) && get_vec(f, ix->redge) && get_vec(f, ix->ledge) && get_vec(f, ix->col_off) && get_vec(f, ix->col_ids) && get_vec(f, ix->col_meta);
   fclose(f);
   if (ok) { ix->table_buckets = scalars[0]; ix->n_kmers = scalars[1]; ix->unitig_bases = scalars[2]; ix->n_sequences = scalars[3];
-    ok = ix->table_buckets >= 2 && ix->table_key.size() == 2 * ix->table_buckets && ix->table_val.size() == ix->table_key.size() && ix->redge.size() == 4 * ix->node.size() && ix->ledge.size() == ix->redge.size() &&
+    ok = ix->table_buckets >= 1 && ix->table_key.size() == 4 * ix->table_buckets && ix->table_val.size() == ix->table_key.size() && ix->redge.size() == 4 * ix->node.size() && ix->ledge.size() == ix->redge.size() &&
          !ix->col_off.empty() && ix->col_meta.size() == 4 * (ix->col_off.size() - 1) && ix->unitig.size() >= (ix->unitig_bases + 31) / 32 + 2; }
   if (!ok) { delete ix; return fail(NB_ERR_PARSE, std::string("not a nimble_b200 index file (or truncated): ") + path); }
   *out = ix; return NB_OK;

@@ -8,7 +8,7 @@
 //   5  k_join          succ/pred of the unitig join relation by binary search in the sorted distinct k-mers
 //   6  k_walk_chains   one thread per chain start: node / offset of every k-mer; scans give node ids and base offsets
 //   7  k_write_unitigs 2-bit unitig store (atomicOr per base word)
-//   8  k_cuckoo_insert concurrent bucketed cuckoo insertion (atomicCAS / atomicExch on 64-bit keys), then values by lookup
+//   8  k_table_insert  concurrent insertion into the bucketed k-mer table (atomicCAS on 64-bit keys), then values by lookup
 //   9  k_edges         left / right edges by lookup of the neighbouring k-mers
 // Universes / bitmap colours (O(colour ids)) are finished on the host (nb_build_universes).  A library with pure
 // k-mer cycles (periodic sequence; no chain start) falls back to the host builder, which owns the canonical cycle rule.
@@ -145,19 +145,17 @@ __global__ void k_write_unitigs(const u64* kmers, const u32* succ, const u32* no
   nr.exts_hi = (u32)Lm[node_first[i]] | ((u32)Rm[node_last[i]] << 4) | ((u32)(base_start[i] >> 32) << 8);
   node[i] = nr;
 }
-// concurrent bucketed cuckoo insertion (2 candidate buckets x 2 slots); only keys move, values are filled afterwards
-__global__ void k_cuckoo_insert(const u64* kmers, u64 n, unsigned long long* tkey, u64 nbuckets, int* failed) {
+// concurrent insertion into the bucketed table (khash.h): first empty slot of the home bucket, else of the next one;
+// only keys are placed, values are filled afterwards
+__global__ void k_table_insert(const u64* kmers, u64 n, unsigned long long* tkey, u64 nbuckets) {
   u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (g >= n) return;
-  unsigned long long k = to_dev_form(kmers[g]) | (1ULL << 63); u64 rng = k * 0x9E3779B97F4A7C15ULL + g;
-  for (int kick = 0; kick < 2000; kick++) {
-    u32 b1, b2; nb_cuckoo_buckets(k & KMASK, nbuckets, b1, b2);
-    u64 cand[4] = {2 * (u64)b1, 2 * (u64)b1 + 1, 2 * (u64)b2, 2 * (u64)b2 + 1};
-    for (int c = 0; c < 4; c++) if (atomicCAS(tkey + cand[c], 0ULL, k) == 0ULL) return;
-    rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
-    k = atomicExch(tkey + cand[rng & 3], k);      // evict; carry on with the evicted key
+  u64 dk = to_dev_form(kmers[g]); unsigned long long k = dk | (1ULL << 63);
+  u64 b = nb_table_bucket(dk, nbuckets);
+  for (;;) {
+    for (u64 s = 4 * b; s < 4 * b + 4; s++) if (tkey[s] == 0ULL && atomicCAS(tkey + s, 0ULL, k) == 0ULL) return;
+    if (++b == nbuckets) b = 0;
   }
-  *failed = 1;
 }
 __global__ void k_table_values(const unsigned long long* tkey, u64 slots, const u64* kmers, u64 n, const u32* node_of, const u32* off_of, u64* tval) {
   u64 h = blockIdx.x * (u64)blockDim.x + threadIdx.x;
@@ -293,14 +291,12 @@ int nb_build_index_gpu(const std::vector<std::vector<u8>>& seqs, int device, int
       ix->node.resize(n_nodes); GCK(cudaMemcpy(ix->node.data(), d_node, (size_t)n_nodes * sizeof(NodeRec), cudaMemcpyDeviceToHost)); }
     // 8. cuckoo table
     GCK(M.alloc(&d_flagint, 2));
-    for (int attempt = 0;; attempt++) {
-      u64 nbk = nb_cuckoo_size(n, attempt); slots = 2 * nbk;
-      if (nbk > 0xFFFFFFFFull) { rc = fail(NB_ERR_UNSUPPORTED, "k-mer table exceeds 2^33 slots"); goto done; }
-      if (d_tkey) { cudaFree(d_tkey); d_tkey = nullptr; }
-      GCK(cudaMalloc(&d_tkey, slots * 8)); GCK(cudaMemset(d_tkey, 0, slots * 8)); GCK(cudaMemset(d_flagint, 0, 8));
-      k_cuckoo_insert<<<nblk(n), 256>>>(d_kmers, n, d_tkey, nbk, d_flagint);
-      GCK(cudaMemcpy(hflag, d_flagint, 8, cudaMemcpyDeviceToHost));
-      if (!hflag[0]) { ix->table_buckets = nbk; break; }
+    {
+      u64 nbk = nb_table_size(n); slots = 4 * nbk;
+      if (nbk > 0xFFFFFFFFull) { rc = fail(NB_ERR_UNSUPPORTED, "k-mer table exceeds 2^34 slots"); goto done; }
+      GCK(cudaMalloc(&d_tkey, slots * 8)); GCK(cudaMemset(d_tkey, 0, slots * 8));
+      k_table_insert<<<nblk(n), 256>>>(d_kmers, n, d_tkey, nbk);
+      ix->table_buckets = nbk;
     }
     GCK(M.alloc(&d_tval, slots)); GCK(cudaMemset(d_tval, 0, slots * 8));
     k_table_values<<<nblk(slots), 256>>>(d_tkey, slots, d_kmers, n, d_node_of, d_off_of, d_tval);

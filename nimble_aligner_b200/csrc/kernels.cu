@@ -206,7 +206,6 @@ __device__ __forceinline__ void cmp_bwd(const u64* U, u64 uhi, const ReadView& r
 }
 
 #include "kmap.cuh"
-#include "kmap2.cuh"
 
 // ------------------------------------------------------------------------------------------------ K3 pair
 struct EcView { const u32* list; u64 mask; u32 lsize; u32 n; bool big; };
@@ -536,30 +535,17 @@ void launch_pack(const BatchDev& b, cudaStream_t s) { u64 n = (u64)b.n_reads * b
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_reads) k_trim<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, t); }
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s) {
   if (!b.n_reads) return;
-  // persistent warps pulling reads from a global queue (zeroed by the host before the launch): enough blocks to fill
-  // every SM at the kernel's occupancy, never more than the work needs
-  static int sms = 0, per_sm[2] = {0, 0}, split = 1, smem_reads = 1;
+  // k_walk: persistent warps popping seeded reads from the global list (counters zeroed by the host before the launch):
+  // enough blocks to fill every SM at the kernel's occupancy, never more than the work needs
+  static int sms = 0, per_sm[2] = {0, 0};
   if (!sms) {
     int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_map<0>, 128, 0) != cudaSuccess || per_sm[0] < 1) per_sm[0] = 8;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_map<1>, 128, 0) != cudaSuccess || per_sm[1] < 1) per_sm[1] = 8;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_walk<0>, 128, 0) != cudaSuccess || per_sm[0] < 1) per_sm[0] = 8;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_walk<1>, 128, 0) != cudaSuccess || per_sm[1] < 1) per_sm[1] = 8;
   }
-  { const char* e = getenv("NB_KMAP"); split = !(e && !strcmp(e, "fused"));       // A/B switch: the fused single-kernel form (kmap.cuh)
-    e = getenv("NB_WALK_SMEM"); smem_reads = !(e && !strcmp(e, "0")); }           // A/B switch: walk reads its read from global memory
-  int cw = count_work ? 1 : 0;
-  if (split) {
-    bool sm = smem_reads && b.W <= WALK_SMEM_W_MAX;
-    size_t shm = sm ? (size_t)128 * b.W * 8 : 0;
-    auto kw = cw ? (sm ? k_walk<1, true> : k_walk<1, false>) : (sm ? k_walk<0, true> : k_walk<0, false>);
-    int occ = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kw, 128, shm) != cudaSuccess || occ < 1) occ = 8;   // (host-side query, microseconds)
-    unsigned sb = blocks_for(b.n_reads, 128), wb = min(sb, (unsigned)(sms * occ));
-    if (cw) k_seed<1><<<sb, 128, 0, s>>>(b, ix, cfg, t); else k_seed<0><<<sb, 128, 0, s>>>(b, ix, cfg, t);
-    kw<<<wb, 128, shm, s>>>(b, ix, cfg, t);
-    return;
-  }
-  unsigned blocks = min(blocks_for(b.n_reads, 128), (unsigned)(sms * per_sm[cw]));
-  if (cw) k_map<1><<<blocks, 128, 0, s>>>(b, ix, cfg, t);
-  else k_map<0><<<blocks, 128, 0, s>>>(b, ix, cfg, t);
+  unsigned sb = blocks_for(b.n_reads, 128), wb = min(sb, (unsigned)(sms * per_sm[count_work ? 1 : 0]));
+  if (count_work) { k_seed<1><<<sb, 128, 0, s>>>(b, ix, cfg, t); k_walk<1><<<wb, 128, 0, s>>>(b, ix, cfg, t); }
+  else { k_seed<0><<<sb, 128, 0, s>>>(b, ix, cfg, t); k_walk<0><<<wb, 128, 0, s>>>(b, ix, cfg, t); }
 }
 void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s) {
   if (b.n_pairs) k_pair<<<blocks_for(b.n_pairs, 128), 128, 0, s>>>(b, ix, lib, cfg, t);

@@ -29,7 +29,7 @@ constexpr int GL_MAX = 64;                 // per-thread group list capacity (ma
 constexpr int ENT_NMAX = 1024;             // longest read the entropy table covers
 
 struct DevIndex {
-  const u64* tkey; const u64* tval; u32 n_buckets;   // bucketed cuckoo table (khash.h): bucket b = keys 2b, 2b+1 (one 16-byte load), values apart
+  const u64* tkey; const u64* tval; u32 n_buckets;   // k-mer table (khash.h): bucket b = keys 4b .. 4b+3 (one 32-byte sector, one 256-bit load), values apart
   const u64* unitig;
   const uint4* node;      // {start_lo, len, colour, lext | rext<<4 | start_hi<<8}
   const uint4* redge;

@@ -1,31 +1,50 @@
-// kmap.cuh — K2 k_map: length / entropy gates + seed-and-walk pseudo-alignment + colour intersection + thresholds.
+// kmap.cuh — K2: length / entropy gates + seed-and-walk pseudo-alignment + colour intersection + thresholds, as two
+// kernels: k_seed (gates + first seed of every read) and k_walk (the unitig walk).
 // Included by kernels.cu after ReadView / EcAcc / cmp_fwd / cmp_bwd.
 //
 // Replaces align::pseudoalign (/root/reference/src/align.rs:945-989), Pseudoaligner::map_read_with_mismatch
 // (call site src/align.rs:965; semantics SURVEY.md App. B) and filter_alignment_by_metrics (src/filter/align.rs:4-45).
 //
-// Execution model: persistent warps, two software stages per warp.
-//   (S) seed stage, 32 fresh reads at a time at full lane efficiency: gates, two per-lane probes (the common hit), then
-//       the whole warp searches the remaining stride-3 seeds of each still-seeking lane 32 at a time — first hit in
-//       seed order wins, exactly the sequential search of App. B (an off-target read would otherwise hold its warp for
-//       ~41 serial probes).  Seeded reads go into a per-warp shared-memory ring; gated / seedless reads are stored now.
-//   (W) walk stage, one read per lane, one unitig per iteration: colour AND, base compare with the ordered per-node
-//       mismatch budget, edge follow or re-seed.  A lane that finishes stores its read and pops the next seeded read
-//       from the ring, so a long walk no longer leaves the other lanes idle.
+// Execution model:
+//   k_seed  one read per lane, 32 consecutive reads per warp, at full lane efficiency: gates, two per-lane probes (the
+//           common hit), then the whole warp searches the remaining stride-3 seeds of each still-seeking lane 64 at a
+//           time — first hit in seed order wins, exactly the sequential search of App. B (an off-target read would
+//           otherwise hold its warp for ~41 serial probes).  Gated / seedless reads get their final record here; seeded
+//           reads go to a global list {read, seed position, node, offset} (16 B per read).  Finding a seed needs almost
+//           no per-lane state (40 registers), so this half runs at 48 warps per SM.
+//   k_walk  persistent warps, one seeded read per lane, one unitig per iteration: colour AND, base compare with the
+//           ordered per-node mismatch budget, edge follow or re-seed.  A lane that finishes stores its read and pops the
+//           next one from the list (batched: the pop runs when >= P_MIN lanes are idle).
+// A fused single-kernel form (seed stage feeding a shared-memory ring inside the walk loop) gave the same results
+// 4-7 % slower: it carried the walk state through the seed search (64 registers, 32 warps per SM).
 #pragma once
 
-// k-mer table lookup: bucketed cuckoo, exactly two 16-byte loads and four compares (no probe loop, no divergence)
+// k-mer table lookup (khash.h): one 256-bit load fetches the four keys of the home bucket = one 32-byte sector; a
+// bucket that neither holds the key nor has an empty slot (occupied slots are a prefix, so that is keys[3] != 0)
+// sends the search to the next bucket.  A miss costs 1.07 sectors on average, a hit one more for (node, offset).
+struct Bucket { u64 k0, k1, k2, k3; };
+__device__ __forceinline__ Bucket ld_bucket(const u64* tkey, u64 b) {
+  Bucket r;
+  asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.k0), "=l"(r.k1), "=l"(r.k2), "=l"(r.k3) : "l"(tkey + 4 * b));
+  return r;
+}
+// slot of `want` given its (already loaded) home bucket, or ~0
+__device__ __forceinline__ u64 probe_finish(const DevIndex& ix, u64 want, u64 b, Bucket k) {
+  for (;;) {   // (a branch-free select form of these compares was measured: +6 % k_seed time)
+    if (k.k0 == want) return 4 * b;
+    if (k.k1 == want) return 4 * b + 1;
+    if (k.k2 == want) return 4 * b + 2;
+    if (k.k3 == want) return 4 * b + 3;
+    if (k.k3 == 0) return ~0ULL;
+    if (++b == ix.n_buckets) b = 0;   // rare (7 % of buckets are full at load 0.4)
+    k = ld_bucket(ix.tkey, b);
+  }
+}
 __device__ __forceinline__ bool probe_kmer(const DevIndex& ix, const ReadView& rd, u32 pos, u32& node, u32& off) {
   u64 km = rd.win(pos) & KMASK;
-  u32 b1, b2; nb_cuckoo_buckets(km, ix.n_buckets, b1, b2);
-  const ulonglong2* T = (const ulonglong2*)ix.tkey;
-  ulonglong2 k1 = __ldg(T + b1), k2 = __ldg(T + b2);
-  u64 want = km | (1ULL << 63), slot;
-  if (k1.x == want) slot = 2 * (u64)b1;
-  else if (k1.y == want) slot = 2 * (u64)b1 + 1;
-  else if (k2.x == want) slot = 2 * (u64)b2;
-  else if (k2.y == want) slot = 2 * (u64)b2 + 1;
-  else return false;
+  u64 b = nb_table_bucket(km, ix.n_buckets);
+  u64 slot = probe_finish(ix, km | (1ULL << 63), b, ld_bucket(ix.tkey, b));
+  if (slot == ~0ULL) return false;
   u64 v = __ldg(ix.tval + slot); node = (u32)v; off = (u32)(v >> 32);
   return true;
 }
@@ -46,34 +65,45 @@ __device__ __forceinline__ bool coop_find(const DevIndex& ix, const BatchDev& b,
 }
 
 enum { ST_DONE = 0, ST_SEED = 1, ST_WALK = 2 };
-constexpr int RING = 64;   // seeded reads buffered per warp
 constexpr int P_MIN = 6;   // idle lanes needed before the store/pop path runs
 constexpr int S_MIN = 4;   // re-seeding lanes needed before the re-seed path runs
 
+// The warp searches the stride-3 seeds of one read from position s_kp on, 64 seeds per round (two per lane, the four
+// bucket loads of a round in flight together: an off-target 150 bp read is settled in one round trip instead of two);
+// returns (to every lane) the first hit in seed order and the number of seeds a sequential search would have tried.
+__device__ __forceinline__ bool coop_find2(const DevIndex& ix, const BatchDev& b, u32 lane, u32 s_ri, u32 s_kp, u32 s_last, u32& f_kp, u32& f_node, u32& f_off, u32& tried) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  ReadView srd{b.pk + (u64)s_ri * b.W, 1};
+  tried = 0;
+  for (u32 base = s_kp; base <= s_last; base += 192) {
+    u32 p0 = base + 3 * lane, p1 = p0 + 96;
+    bool v0 = p0 <= s_last, v1 = p1 <= s_last;
+    u64 w0 = (srd.win(v0 ? p0 : s_last) & KMASK), w1 = (srd.win(v1 ? p1 : s_last) & KMASK);
+    u64 b0 = nb_table_bucket(w0, ix.n_buckets), b1 = nb_table_bucket(w1, ix.n_buckets);
+    Bucket ka = ld_bucket(ix.tkey, b0), kb = ld_bucket(ix.tkey, b1);
+    u64 s0 = probe_finish(ix, w0 | (1ULL << 63), b0, ka), s1 = probe_finish(ix, w1 | (1ULL << 63), b1, kb);
+    unsigned hb0 = __ballot_sync(FULL, v0 && s0 != ~0ULL), hb1 = __ballot_sync(FULL, v1 && s1 != ~0ULL);
+    if (hb0 | hb1) {
+      int f = hb0 ? __ffs(hb0) - 1 : __ffs(hb1) - 1;
+      u32 nd2 = 0, of2 = 0;
+      if ((int)lane == f) { u64 v = __ldg(ix.tval + (hb0 ? s0 : s1)); nd2 = (u32)v; of2 = (u32)(v >> 32); }
+      f_node = __shfl_sync(FULL, nd2, f); f_off = __shfl_sync(FULL, of2, f);
+      u32 idx = (hb0 ? 0u : 32u) + (u32)f;
+      f_kp = base + 3 * idx; tried += idx + 1; return true;
+    }
+    tried += min(64u, (s_last - base) / 3 + 1);   // same count as the sequential search: every seed of the round missed
+  }
+  return false;
+}
+
+// ---- k_seed: one read per lane, 32 consecutive reads per warp.  Gated / seedless reads get their final record here.
 template <int COUNT_WORK>
-__global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg, Tables t) {
-  __shared__ uint4 s_ring[4][RING];
+__global__ void __launch_bounds__(128) k_seed(BatchDev b, DevIndex ix, DevCfg cfg, Tables t) {
   const unsigned FULL = 0xFFFFFFFFu;
   const u32 lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
-  uint4* ring = s_ring[threadIdx.x >> 5];
-  const u32* redge = (const u32*)ix.redge; const u32* ledge = (const u32*)ix.ledge;
-  const u32 allowed = cfg.num_mismatches;
   WorkCnt wc = {0, 0, 0, 0};
-  u32 r_head = 0, r_count = 0;                   // warp-uniform ring state
-  bool drained = false;                          // warp-uniform: the global queue has no more reads for this warp
-  // per-lane walk state
-  int st = ST_DONE; bool has = false, first = true;
-  u32 ri = 0, n = 0, cov = 0, mm = 0, kp = 0, node = 0, off = 0, last_kpos = 0;
-  ReadView rd{b.pk, 1};
-  EcAcc acc; acc.init(ix, t);
-  for (;;) {
-    // ---------------------------------------------------------------- (S) seed 32 fresh reads while the ring is low
-    while (!drained && r_count < 32) {
-      u32 base = 0;
-      if (lane == 0) base = (u32)atomicAdd(&t.ctr->queue, 32ULL);
-      base = __shfl_sync(FULL, base, 0);
-      if (base + 32 >= b.n_reads) drained = true;
-      if (COUNT_WORK && lane == 0) atomicAdd(&t.ctr->dbg[2], 1ULL);
+  const u32 base = (blockIdx.x * 128u + threadIdx.x) & ~31u;
+  {
       u32 q = base + lane; bool live = q < b.n_reads, seek = false, found = false;
       u32 qn = 0, qhdr = R_NO_MATCH, qkp = 0, qnode = 0, qoff = 0, qlast = 0;
       ReadView qrd{b.pk + (u64)(live ? q : 0) * b.W, 1};
@@ -116,7 +146,7 @@ __global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg
         int l = __ffs(need) - 1; need &= need - 1;
         u32 s_kp = __shfl_sync(FULL, qkp, l), s_last = __shfl_sync(FULL, qlast, l), s_ri = __shfl_sync(FULL, q, l);
         u32 f_kp = 0, f_node = 0, f_off = 0, tried = 0;
-        bool ok = coop_find(ix, b, lane, s_ri, s_kp, s_last, f_kp, f_node, f_off, tried);
+        bool ok = coop_find2(ix, b, lane, s_ri, s_kp, s_last, f_kp, f_node, f_off, tried);
         if ((int)lane == l) { wc.probes += tried; if (ok) { found = true; qkp = f_kp; qnode = f_node; qoff = f_off; } }
       }
       if (live && !found) {   // gated, or map_read_with_mismatch found no seed -> None -> NoMatch (src/align.rs:987)
@@ -124,14 +154,39 @@ __global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg
         b.rres[q] = rr;
       }
       unsigned pm = __ballot_sync(FULL, found);
-      if (found) ring[(r_head + r_count + __popc(pm & lt_mask)) % RING] = make_uint4(q, qkp, qnode, qoff);
-      r_count += __popc(pm);
-      __syncwarp();
-    }
-    // ---------------------------------------------------------------- (P) store finished reads, pop seeded ones.
-    // Both side paths below run for whichever lanes need them; to keep them from executing at 1-4 active lanes on
-    // every iteration they are batched: (P) waits for >= P_MIN idle lanes, (A)+(B) for >= S_MIN re-seeding lanes,
-    // unless no lane could walk otherwise.
+      if (pm) {
+        u32 at = 0;
+        if (lane == 0) at = (u32)atomicAdd(&t.ctr->seeded_n, (unsigned long long)__popc(pm));
+        at = __shfl_sync(FULL, at, 0);
+        if (found) b.seeded[at + __popc(pm & lt_mask)] = make_uint4(q, qkp, qnode, qoff);
+      }
+  }
+  if (COUNT_WORK) {
+    u32 p = wc.probes;
+    for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+    if (lane == 0 && p) atomicAdd(&t.ctr->probes, (unsigned long long)p);
+  }
+}
+
+// ---- k_walk: persistent warps, one seeded read per lane, one unitig per iteration (stages P, A+B, C, D of kmap.cuh)
+#ifndef NB_WALK_MINB
+#define NB_WALK_MINB 10   // 48 registers: 40 warps per SM (measured: 8 -> 10 blocks = -4 % time; 12 spills and loses)
+#endif
+template <int COUNT_WORK>
+__global__ void __launch_bounds__(128, NB_WALK_MINB) k_walk(BatchDev b, DevIndex ix, DevCfg cfg, Tables t) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const u32 lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
+  const u32* redge = (const u32*)ix.redge; const u32* ledge = (const u32*)ix.ledge;
+  const u32 allowed = cfg.num_mismatches;
+  const u32 total = (u32)t.ctr->seeded_n;        // written by k_seed, complete at this kernel's start
+  WorkCnt wc = {0, 0, 0, 0};
+  bool drained = false;                          // warp-uniform: the seeded list has no more reads for this warp
+  int st = ST_DONE; bool has = false, first = true;
+  u32 ri = 0, n = 0, cov = 0, mm = 0, kp = 0, node = 0, off = 0, last_kpos = 0;
+  ReadView rd{b.pk, 1};
+  EcAcc acc; acc.init(ix, t);
+  for (;;) {
+    // ---------------------------------------------------------------- (P) store finished reads, pop seeded ones (batched: >= P_MIN idle lanes)
     unsigned walkers = __ballot_sync(FULL, st == ST_WALK);
     unsigned idle0 = __ballot_sync(FULL, st == ST_DONE);
     const bool do_pop = __popc(idle0) >= P_MIN || walkers == 0;
@@ -153,23 +208,23 @@ __global__ void __launch_bounds__(128) k_map(BatchDev b, DevIndex ix, DevCfg cfg
       b.rres[ri] = rr;
       has = false;
     }
-    unsigned idle = idle0;
-    if (do_pop && idle && r_count) {
-      u32 npop = min((u32)__popc(idle), r_count), rank = __popc(idle & lt_mask);
-      if (st == ST_DONE && rank < npop) {
-        uint4 e = ring[(r_head + rank) % RING];
+    if (do_pop && idle0 && !drained) {
+      u32 want = __popc(idle0), at = 0, rank = __popc(idle0 & lt_mask);
+      if (lane == 0) at = (u32)atomicAdd(&t.ctr->wqueue, (unsigned long long)want);
+      at = __shfl_sync(FULL, at, 0);
+      if (at + want >= total) drained = true;
+      if (st == ST_DONE && at + rank < total) {
+        uint4 e = b.seeded[at + rank];
         ri = e.x; kp = e.y; node = e.z; off = e.w;
         n = b.len_trim[ri]; last_kpos = n - K;
-        rd.p = b.pk + (u64)ri * b.W; rd.stride = 1;   // (staging the read in shared memory was measured: no gain, +10 % time)
+        rd.p = b.pk + (u64)ri * b.W; rd.stride = 1;   // (copying the read into a shared-memory column was measured twice: -15 % L2 sectors, +17 % instructions, no gain)
         cov = 0; mm = 0; acc.reset(); first = true; has = true; st = ST_WALK;
       }
-      r_head = (r_head + npop) % RING; r_count -= npop;
-      __syncwarp();
     }
-    if (__all_sync(FULL, st == ST_DONE)) { if (drained && r_count == 0) break; continue; }   // (do_pop was true: everything is stored)
+    if (__all_sync(FULL, st == ST_DONE)) { if (drained) break; continue; }   // (do_pop was true: everything is stored)
     if (COUNT_WORK) {
       unsigned wl = __ballot_sync(FULL, st == ST_WALK), sl = __ballot_sync(FULL, st == ST_SEED);
-      if (lane == 0) { atomicAdd(&t.ctr->dbg[0], 1ULL); atomicAdd(&t.ctr->dbg[1], (unsigned long long)__popc(wl)); atomicAdd(&t.ctr->dbg[3], (unsigned long long)__popc(sl)); atomicAdd(&t.ctr->dbg[4], (unsigned long long)r_count); if (drained) atomicAdd(&t.ctr->dbg[5], 1ULL); }
+      if (lane == 0) { atomicAdd(&t.ctr->dbg[0], 1ULL); atomicAdd(&t.ctr->dbg[1], (unsigned long long)__popc(wl)); atomicAdd(&t.ctr->dbg[3], (unsigned long long)__popc(sl)); if (drained) atomicAdd(&t.ctr->dbg[5], 1ULL); }
     }
     // ---------------------------------------------------------------- (A)+(B) re-seeding lanes (after a budget trip / dead end)
     unsigned seekers = __ballot_sync(FULL, st == ST_SEED);
