@@ -356,7 +356,7 @@ def main():
         except Exception:
             pass
         out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                           "kernel": "k_map", "peak_source": peak_src, "algorithmic_bytes_per_read": bpr, "reads_per_launch": reads_per_launch,
+                           "kernel": "map stage = k_seed + k_walk (one launch pair per chunk; events bracket the pair)", "peak_source": peak_src, "algorithmic_bytes_per_read": bpr, "reads_per_launch": reads_per_launch,
                            "launch_ms": launch_ms, "kernel_share_of_step": ks["map_ms"] / (ms_dev * args.steps),
                            "work_per_read": {k: ref["work"][k] / (2.0 * m) for k in ("probes", "nodes", "bases", "colour_elems")}}
     print(json.dumps(out))

@@ -29,16 +29,15 @@ for r in rows:
     try: ln = int(d["Line No"])
     except: continue
     base = (fpath or "").split("/")[-1]
-    if base not in OURS: ln = 0; base = "(toolkit headers)"
-    a = per[cur].setdefault((base, ln), [0.0, 0.0, 0.0])
+    if "nimble_aligner_b200" not in (fpath or ""): ln = 0; base = "(toolkit headers)"
+    a = per[cur].setdefault((base, ln), [0.0, 0.0, 0.0, ""])
+    if base != "(toolkit headers)": a[3] = (r[1] if len(r) > 1 else "").strip()[:100]   # source text as embedded in the report (--import-source on)
     def f(x):
         try: return float(x)
         except Exception: return 0.0
     a[0] += f(d["Instructions Executed"]); a[1] += f(d["Thread Instructions Executed"]); a[2] += f(d["# Samples"])
-lines = {f: open("nimble_aligner_b200/csrc/" + f).read().split("\n") for f in OURS}
 for k, out in per.items():
     tot = sum(a[0] for a in out.values()) or 1; tots = sum(a[2] for a in out.values()) or 1
     print("\n== %s: inst=%d samples=%d" % (k, tot, tots))
-    for (fn, ln), (ie, te, smp) in sorted(out.items(), key=lambda x: -x[1][0])[:topn]:
-        txt = lines[fn][ln - 1].strip()[:100] if fn in lines and 0 < ln <= len(lines[fn]) else ""
+    for (fn, ln), (ie, te, smp, txt) in sorted(out.items(), key=lambda x: -x[1][0])[:topn]:
         print("%-11s %4d inst%%=%5.1f thr/inst=%5.1f samp%%=%5.1f | %s" % (fn[:11], ln, 100 * ie / tot, te / ie if ie else 0, 100 * smp / tots, txt))
