@@ -13,8 +13,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <unordered_set>
@@ -76,6 +78,27 @@ struct Rec {   // one decoded BAM record (views into Bgzf::data stay valid for t
   const u8* p = nullptr;        // start of the fixed fields (after block_size)
   u32 block = 0;
   int skip_align = -1;          // the "SK" string aux the reference appends (sorted_bam_reader.rs:114-121): -1 absent (-p mode), 0 "FALSE", 1 "TRUE"
+  const char* cb = nullptr; const char* umi = nullptr; u32 cb_len = 0, umi_len = 0;   // CB:Z and UB:Z (else UR:Z) values, found once by scan_keys(); nullptr = absent / not a string
+  // one pass over the aux block for the grouping keys (same first-match-by-two-bytes rule as aux_z)
+  void scan_keys() {
+    const u8* a = aux(); const u8* e = end(); const char* ub = nullptr; const char* ur = nullptr; bool seen_cb = false, seen_ub = false, seen_ur = false;
+    cb = umi = nullptr;
+    while (a + 3 <= e) {
+      char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2]; a += 3; const u8* v = a;
+      switch (ty) {
+        case 'A': case 'c': case 'C': a += 1; break; case 's': case 'S': a += 2; break; case 'i': case 'I': case 'f': a += 4; break;
+        case 'Z': case 'H': while (a < e && *a) a++; a++; break;
+        case 'B': { if (a + 5 > e) { a = e; break; } char st = (char)a[0]; u32 n; memcpy(&n, a + 1, 4); size_t w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; a += 5 + w * n; break; }
+        default: a = e; break;
+      }
+      if (t0 == 'C' && t1 == 'B' && !seen_cb) { seen_cb = true; if (ty == 'Z') cb = (const char*)v; }
+      else if (t0 == 'U' && t1 == 'B' && !seen_ub) { seen_ub = true; if (ty == 'Z') ub = (const char*)v; }
+      else if (t0 == 'U' && t1 == 'R' && !seen_ur) { seen_ur = true; if (ty == 'Z') ur = (const char*)v; }
+    }
+    umi = ub ? ub : ur;
+    cb_len = cb ? (u32)strlen(cb) : 0; umi_len = umi ? (u32)strlen(umi) : 0;
+  }
+  const char* qname_ptr() const { return (const char*)p + 32; } u32 qname_len() const { u32 l = l_read_name(); return l ? l - 1 : 0; }
   i32 refid() const { return rd32(0); } i32 pos() const { return rd32(4); }
   u32 l_read_name() const { return p[8]; } u32 mapq() const { return p[9]; }
   u32 n_cigar() const { return p[12] | (p[13] << 8); } u32 flag() const { return p[14] | (p[15] << 8); }
@@ -147,6 +170,9 @@ void parse_fields(const Rec& r, ParsedRec& o) {   // src/parse/bam.rs:186-236
 }
 
 // ------------------------------------------------------------------ SortedBamReader (src/parse/sorted_bam_reader.rs)
+inline bool same(const char* a, u32 al, const char* b, u32 bl) { return al == bl && (al == 0 || !memcmp(a, b, al)); }
+inline int cmp_bytes(const char* a, u32 al, const char* b, u32 bl) { int c = memcmp(a, b, std::min(al, bl)); return c ? c : (al < bl ? -1 : al > bl ? 1 : 0); }
+
 struct SortedReader {
   const Bgzf& z; size_t cur = 0; bool force_paired; bool header_done = false;
   std::string current_umi, next_umi; std::vector<Rec> buffer, next_records;   // buffer is popped from the back
@@ -163,7 +189,7 @@ struct SortedReader {
     if (cur + 4 > d.size()) return false;
     u32 bs; memcpy(&bs, &d[cur], 4);
     if (bs < 32 || cur + 4 + bs > d.size()) return false;
-    r.p = &d[cur + 4]; r.block = bs; r.skip_align = -1; cur += 4 + bs; return true;
+    r.p = &d[cur + 4]; r.block = bs; r.skip_align = -1; cur += 4 + bs; r.scan_keys(); return true;
   }
   int fill_buffer() {   // 31-107
     buffer.clear(); buffer.swap(next_records); next_records.clear();
@@ -171,14 +197,13 @@ struct SortedReader {
     Rec r;
     while (read_record(r)) {
       if (!r.is_paired() && force_paired) continue;
-      std::string cb, umi;
-      if (!r.aux_z("CB", cb)) continue;
-      if (!r.aux_z("UB", umi) && !r.aux_z("UR", umi)) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
-      if (umi == "AAAAAAAAAA") continue;
-      if (current_umi.empty()) current_umi = umi;
-      if (current_umi != umi) {
-        std::stable_sort(buffer.begin(), buffer.end(), [](const Rec& a, const Rec& b) { std::string x, y; a.aux_z("CB", x); b.aux_z("CB", y); return x < y; });
-        next_records.push_back(r); next_umi = umi;
+      if (!r.cb) continue;
+      if (!r.umi) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
+      if (r.umi_len == 10 && !memcmp(r.umi, "AAAAAAAAAA", 10)) continue;
+      if (current_umi.empty()) current_umi.assign(r.umi, r.umi_len);
+      if (!same(current_umi.data(), (u32)current_umi.size(), r.umi, r.umi_len)) {
+        std::stable_sort(buffer.begin(), buffer.end(), [](const Rec& a, const Rec& b) { return cmp_bytes(a.cb, a.cb_len, b.cb, b.cb_len) < 0; });
+        next_records.push_back(r); next_umi.assign(r.umi, r.umi_len);
         return NB_OK;
       }
       buffer.push_back(r);
@@ -186,15 +211,15 @@ struct SortedReader {
     return NB_OK;   // end of file: this last buffer is NOT sorted by CB (quirk kept)
   }
   void add_dummy_paired_reads() {   // 109-125
-    std::vector<Rec> nb2;
+    std::vector<Rec> nb2; nb2.reserve(2 * buffer.size());
     for (const Rec& r : buffer) { Rec m = r; m.skip_align = 0; nb2.push_back(m); if (!r.is_paired()) { Rec d = r; d.skip_align = 1; nb2.push_back(d); } }
     buffer.swap(nb2);
   }
   void filter_paired_reads() {      // 127-162
-    std::vector<Rec> out; size_t i = 0;
+    std::vector<Rec> out; out.reserve(buffer.size()); size_t i = 0;
     while (i < buffer.size()) {
       if (i + 1 >= buffer.size()) break;
-      if (buffer[i].qname() == buffer[i + 1].qname()) {
+      if (same(buffer[i].qname_ptr(), buffer[i].qname_len(), buffer[i + 1].qname_ptr(), buffer[i + 1].qname_len())) {
         if (buffer[i].is_first()) { out.push_back(buffer[i]); out.push_back(buffer[i + 1]); } else { out.push_back(buffer[i + 1]); out.push_back(buffer[i]); }
         i += 2;
       } else i += 1;
@@ -213,35 +238,120 @@ struct SortedReader {
   }
 };
 
-// ------------------------------------------------------------------ UMIReader (src/parse/bam.rs:100-253)
+// ------------------------------------------------------------------ UMIReader (src/parse/bam.rs:100-253), on undecoded records:
+// the 38 strings per record are only materialised for the rows that get written (and by the writer threads)
 struct UmiReader {
-  SortedReader rd; std::vector<ParsedRec> current, nextg; std::string current_key, next_key, current_umi, next_umi, current_cb, next_cb;
+  SortedReader rd; std::vector<Rec> current, nextg; std::string current_key, next_key, current_umi, next_umi;
   UmiReader(const Bgzf& z, bool fp) : rd(z, fp) {}
   // returns 1: a following group exists (Some(true)); 0: end of input (None); <0 error
   int get_umi() {
-    current.swap(nextg); nextg.clear(); current_key = next_key; next_key.clear(); current_umi = next_umi; next_umi.clear(); current_cb = next_cb; next_cb.clear();
+    current.swap(nextg); nextg.clear(); current_key = next_key; next_key.clear(); current_umi = next_umi; next_umi.clear();
+    std::string key;
     for (;;) {
       Rec r; int g = rd.next(r);
       if (g < 0) return g;
       if (g == 0) return 0;
-      std::string umi, cb;
-      if (!r.aux_z("UB", umi) && !r.aux_z("UR", umi)) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
-      if (!r.aux_z("CB", cb)) return fail(NB_ERR_PARSE, "Error Read without cell barcode, cannot excise read-mate.");
-      std::string cbs = cb.size() >= 2 ? cb.substr(0, cb.size() - 2) : std::string();
-      std::string key = umi + cbs;
-      if (current_umi.empty()) current_umi = umi;
+      if (!r.umi) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
+      if (!r.cb) return fail(NB_ERR_PARSE, "Error Read without cell barcode, cannot excise read-mate.");
+      key.assign(r.umi, r.umi_len); if (r.cb_len >= 2) key.append(r.cb, r.cb_len - 2);
+      if (current_umi.empty()) current_umi.assign(r.umi, r.umi_len);
       if (current_key.empty()) current_key = key;
-      ParsedRec pr; parse_fields(r, pr);
-      if (current_key == key) { current.push_back(std::move(pr)); current_cb = cbs; }
-      else { nextg.push_back(std::move(pr)); next_umi = umi; next_cb = cbs; next_key = key; return 1; }
+      if (current_key == key) current.push_back(r);
+      else { nextg.push_back(r); next_umi.assign(r.umi, r.umi_len); next_key = key; return 1; }
     }
   }
 };
 
-std::string data_header(const char* prefix) { std::string s; for (int i = 0; i < 38; i++) { if (i == 1 || i == 15) continue; if (!s.empty()) s += "\t"; s += prefix; s += "_"; s += FIELDS[i]; } return s; }
-void data_values(const std::vector<std::string>& f, std::string& s) { bool firstf = true; for (int i = 0; i < 38; i++) { if (i == 1 || i == 15) continue; if (!firstf) s += "\t"; firstf = false; s += f[i]; } }
+// The groups the producer loop sends, in order (src/process/bam.rs:157-180): records of group g are
+// stream[gstart[g] .. gstart[g+1]); the last group is never sent when a group was sent before.
+int collect_groups(const Bgzf& z, bool force_paired, std::vector<Rec>& stream, std::vector<u64>& gstart) {
+  UmiReader reader(z, force_paired);
+  int rc = reader.rd.skip_header(); if (rc) return rc;
+  stream.clear(); gstart.assign(1, 0);
+  bool has_aligned = false;
+  for (;;) {
+    int g = reader.get_umi();
+    if (g < 0) return g;
+    bool final_umi = g == 0;
+    if (final_umi && has_aligned) break;
+    stream.insert(stream.end(), reader.current.begin(), reader.current.end()); gstart.push_back(stream.size());
+    has_aligned = true;
+    if (final_umi) break;
+  }
+  return NB_OK;
+}
 
-struct Group { std::vector<ParsedRec> recs; };
+void parallel_ranges(int threads, size_t n, const std::function<void(size_t, size_t, int)>& fn) {
+  if (threads <= 1 || n < 2) { fn(0, n, 0); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++) th.emplace_back(fn, n * (size_t)t / threads, n * (size_t)(t + 1) / threads, t);
+  for (auto& x : th) x.join();
+}
+
+// clipped length / start of a record's sequence (strip_nonbio_regions, src/parse/bam.rs:258-268)
+inline void clip_of(const Rec& r, size_t& a, size_t& b) { size_t n = r.l_seq(); a = 0; b = n; if (n == 124) { if (r.is_reverse()) b = n - CLIP_LENGTH; else a = CLIP_LENGTH; } }
+
+// the 36 reported metadata values of one record, tab-joined, straight into the output line (same values as parse_fields)
+void append_data_values(const Rec& r, std::string& s) {
+  struct Aux { char t0, t1, ty; const char* v; } tab[48]; int nt = 0;
+  { const u8* a = r.aux(); const u8* e = r.end();
+    while (a + 3 <= e && nt < 48) {
+      char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2]; a += 3; const u8* v = a; bool ok = true;
+      switch (ty) {
+        case 'A': case 'c': case 'C': a += 1; break; case 's': case 'S': a += 2; break; case 'i': case 'I': case 'f': a += 4; break;
+        case 'Z': case 'H': while (a < e && *a) a++; a++; break;
+        case 'B': { if (a + 5 > e) { ok = false; break; } char st = (char)a[0]; u32 n; memcpy(&n, a + 1, 4); size_t w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; a += 5 + w * n; break; }
+        default: ok = false; break;
+      }
+      if (!ok) break;   // aux_z gives up at a malformed / unknown field: nothing behind it is visible
+      tab[nt++] = {t0, t1, ty, (const char*)v};
+    } }
+  u32 fl = r.flag(); bool rev = fl & 16, paired = fl & 1, unm = fl & 4, munm = fl & 8, mrev = fl & 32, first = fl & 64;
+  bool firstf = true; char num[24];
+  for (int i = 0; i < 38; i++) {
+    if (i == 1 || i == 15) continue;
+    if (!firstf) s += '\t';
+    firstf = false;
+    if (i == 37 && r.skip_align >= 0) { s += r.skip_align ? "TRUE" : "FALSE"; continue; }
+    const char* tag = FIELDS[i]; bool found = false, is_z = false; const char* zv = nullptr;
+    for (int k = 0; k < nt; k++) if (tab[k].t0 == tag[0] && tab[k].t1 == tag[1]) { found = true; is_z = tab[k].ty == 'Z'; zv = tab[k].v; break; }
+    if (found && is_z) { s += zv; continue; }
+    switch (i) {
+      case 0: s.append(r.qname_ptr(), r.qname_len()); break; case 2: s += rev ? "true" : "false"; break; case 3: s += mrev ? "true" : "false"; break;
+      case 4: s += paired ? "true" : "false"; break; case 5: s += (fl & 2) ? "true" : "false"; break;
+      case 6: {
+        if (paired && !unm && !munm && r.refid() == r.mrefid() && r.pos() != r.mpos()) {
+          i64 p1, p2; bool f1, f2;
+          if (first) { p1 = r.pos(); p2 = r.mpos(); f1 = !rev; f2 = !mrev; } else { p1 = r.mpos(); p2 = r.pos(); f1 = !mrev; f2 = !rev; }
+          if (p1 < p2) { s += f1 ? "F1" : "R1"; s += f2 ? "F2" : "R2"; } else { s += f2 ? "F2" : "R2"; s += f1 ? "F1" : "R1"; }
+        } else s += "None";
+        break; }
+      case 7: s += unm ? "true" : "false"; break; case 8: s += munm ? "true" : "false"; break; case 9: s += first ? "true" : "false"; break;
+      case 10: s += (fl & 128) ? "true" : "false"; break; case 11: s += rev ? "-" : "+"; break;
+      case 12: snprintf(num, sizeof num, "%u", r.mapq()); s += num; break; case 13: snprintf(num, sizeof num, "%d", r.pos()); s += num; break;
+      case 14: snprintf(num, sizeof num, "%d", r.mpos()); s += num; break; case 16: snprintf(num, sizeof num, "%u", r.l_seq()); s += num; break;
+      case 17: snprintf(num, sizeof num, "%d", r.tlen()); s += num; break;
+      case 18: s += (fl & 512) ? "true" : "false"; break; case 19: s += (fl & 256) ? "true" : "false"; break; case 20: s += (fl & 1024) ? "true" : "false"; break;
+      case 21: s += (fl & 2048) ? "true" : "false"; break;
+      default: break;   // non-string aux (NH, HI, AS, nM, RE ...) -> String::new()
+    }
+  }
+}
+// field 0 of a record as the row logic sees it (QNAME, or a "QN" string aux when one exists — aux lookup by two bytes)
+std::string field0(const Rec& r) { std::string z; if (r.aux_z("QNAME", z)) return z; return r.qname(); }
+
+std::string data_header(const char* prefix) { std::string s; for (int i = 0; i < 38; i++) { if (i == 1 || i == 15) continue; if (!s.empty()) s += "\t"; s += prefix; s += "_"; s += FIELDS[i]; } return s; }
+
+// one gzip member (concatenated members are one valid .gz stream): lets the writer threads deflate independently
+bool gzip_member(const std::string& text, int level, std::string& out) {
+  z_stream zs; memset(&zs, 0, sizeof zs);
+  if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+  out.resize(deflateBound(&zs, (uLong)text.size()) + 32);
+  zs.next_in = (Bytef*)text.data(); zs.avail_in = (uInt)text.size(); zs.next_out = (Bytef*)&out[0]; zs.avail_out = (uInt)out.size();
+  int rc = deflate(&zs, Z_FINISH); size_t n = zs.total_out; deflateEnd(&zs);
+  if (rc != Z_STREAM_END) return false;
+  out.resize(n); return true;
+}
 
 }  // namespace
 
@@ -250,10 +360,10 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
                               const char* trim /* "L:S,L:S" or NULL */, int num_cores, int force_bam_paired, int device) {
   if (!input_file || !reference_json || !output_paths || n_refs < 1) return fail(NB_ERR_INVALID, "need an input BAM and >=1 reference/output pair");
   int threads = std::max(1, num_cores);
-  std::vector<nb_library*> libs(n_refs, nullptr); std::vector<nb_index*> idx(n_refs, nullptr); std::vector<nb_ctx*> ctx(n_refs, nullptr); std::vector<gzFile> outs(n_refs, nullptr);
+  std::vector<nb_library*> libs(n_refs, nullptr); std::vector<nb_index*> idx(n_refs, nullptr); std::vector<nb_ctx*> ctx(n_refs, nullptr); std::vector<FILE*> outs(n_refs, nullptr);
   std::vector<bool> first_write(n_refs, true);
   int rc = NB_OK;
-  auto cleanup = [&]() { for (u32 i = 0; i < n_refs; i++) { if (outs[i]) gzclose(outs[i]); nb_ctx_free(ctx[i]); nb_index_free(idx[i]); nb_library_free(libs[i]); } };
+  auto cleanup = [&]() { for (u32 i = 0; i < n_refs; i++) { if (outs[i]) fclose(outs[i]); nb_ctx_free(ctx[i]); nb_index_free(idx[i]); nb_library_free(libs[i]); } };
   std::vector<std::pair<u64, double>> trims;
   if (trim && *trim) {   // src/bin/main.rs:74-93
     std::string t(trim); size_t p = 0;
@@ -265,34 +375,56 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
     if (rc == NB_OK && !trims.empty()) { nb_config c; nb_library_get_config(libs[i], &c); c.trim_target_length = trims[i].first; c.trim_strictness = trims[i].second; rc = nb_library_set_config(libs[i], &c); }
     if (rc == NB_OK) rc = nb_index_build(libs[i], threads, &idx[i]);
     if (rc == NB_OK) rc = nb_ctx_create(idx[i], libs[i], device, nullptr, &ctx[i]);
-    if (rc == NB_OK) { outs[i] = gzopen(output_paths[i], "wb"); if (!outs[i]) rc = fail(NB_ERR_IO, std::string("could not open output ") + output_paths[i]); }
+    if (rc == NB_OK) { outs[i] = fopen(output_paths[i], "wb"); if (!outs[i]) rc = fail(NB_ERR_IO, std::string("could not open output ") + output_paths[i]); }
   }
-  Bgzf z;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_load = 0, t_group = 0, t_fill = 0, t_gpu = 0, t_rows = 0, t_write = 0, t0 = now();   // NB_BAM_STATS=1 prints the phase times
+  Bgzf z; std::vector<Rec> stream; std::vector<u64> gstart;
   if (rc == NB_OK) rc = z.load(input_file, threads);
+  t_load = now() - t0; t0 = now();
+  if (rc == NB_OK) rc = collect_groups(z, force_bam_paired != 0, stream, gstart);
+  t_group = now() - t0;
   if (rc != NB_OK) { cleanup(); return rc; }
-  UmiReader reader(z, force_bam_paired != 0);
-  rc = reader.rd.skip_header();
-  const size_t BATCH_PAIRS = 1u << 19;
-  std::vector<Group> groups; size_t pairs_in_batch = 0; bool has_aligned = false, done = false;
+  const size_t n_groups = gstart.size() - 1;
+  const size_t BATCH_PAIRS = 1u << 20;
+  const int GZ_LEVEL = 4;
   std::vector<u8> r1, r2, q1, q2, f1, f2; std::vector<u64> o1, o2; std::vector<u32> scope;
   std::vector<nb_read_result> rres; std::vector<nb_pair_result> pres;
-  auto flush = [&]() -> int {
-    if (groups.empty()) return NB_OK;
-    r1.clear(); r2.clear(); q1.clear(); q2.clear(); f1.clear(); f2.clear(); o1.assign(1, 0); o2.assign(1, 0); scope.clear();
+  static const char* T16 = "=ACMGRSVTWYHKDBN";
+  // one batch = groups [g0, g1)
+  auto run_batch = [&](size_t g0, size_t g1) -> int {
+    const size_t ng = g1 - g0;
+    std::vector<u64> pair0(ng + 1, 0);   // first pair of each group within the batch
+    for (size_t g = 0; g < ng; g++) pair0[g + 1] = pair0[g] + (gstart[g0 + g + 1] - gstart[g0 + g]) / 2;
+    const size_t np = pair0[ng];
+    if (!np) return NB_OK;
+    double tb = now();
+    // ---- batch arrays, filled on the host threads: even record = sequence slot, odd = mate slot (src/process/bam.rs:257-292)
+    o1.assign(np + 1, 0); o2.assign(np + 1, 0); f1.resize(np); f2.resize(np); scope.resize(np);
+    parallel_ranges(threads, ng, [&](size_t a, size_t b, int) {
+      for (size_t g = a; g < b; g++) { const Rec* v = &stream[gstart[g0 + g]];
+        for (size_t j = 0; j < pair0[g + 1] - pair0[g]; j++) { size_t x, y; clip_of(v[2 * j], x, y); o1[pair0[g] + j + 1] = y - x; clip_of(v[2 * j + 1], x, y); o2[pair0[g] + j + 1] = y - x; } } });
     u32 maxlen = 1;
-    for (size_t g = 0; g < groups.size(); g++) {
-      const std::vector<ParsedRec>& v = groups[g].recs;
-      for (size_t j = 0; j + 1 < v.size(); j += 2) {   // even = sequence slot, odd = mate slot (src/process/bam.rs:257-292)
-        const ParsedRec& a = v[j]; const ParsedRec& b = v[j + 1];
-        r1.insert(r1.end(), a.seq.begin(), a.seq.end()); q1.insert(q1.end(), a.qual.begin(), a.qual.end()); o1.push_back(r1.size());
-        r2.insert(r2.end(), b.seq.begin(), b.seq.end()); q2.insert(q2.end(), b.qual.begin(), b.qual.end()); o2.push_back(r2.size());
-        f1.push_back((u8)((a.skip ? NB_FLAG_SKIP_ALIGN : 0) | (a.reverse ? NB_FLAG_REVCOMP : 0))); f2.push_back((u8)((b.skip ? NB_FLAG_SKIP_ALIGN : 0) | (b.reverse ? NB_FLAG_REVCOMP : 0)));
-        scope.push_back((u32)g); maxlen = std::max<u32>(maxlen, (u32)std::max(a.seq.size(), b.seq.size()));
-      }
-    }
-    size_t np = scope.size();
-    r1.resize(r1.size() + 64); r2.resize(r2.size() + 64); q1.resize(q1.size() + 64); q2.resize(q2.size() + 64);
+    for (size_t p = 0; p < np; p++) { maxlen = std::max<u32>(maxlen, (u32)std::max(o1[p + 1], o2[p + 1])); o1[p + 1] += o1[p]; o2[p + 1] += o2[p]; }
+    r1.resize(o1[np] + 64); q1.resize(o1[np] + 64); r2.resize(o2[np] + 64); q2.resize(o2[np] + 64);
+    parallel_ranges(threads, ng, [&](size_t a, size_t b, int) {
+      for (size_t g = a; g < b; g++) { const Rec* v = &stream[gstart[g0 + g]];
+        for (size_t j = 0; j < pair0[g + 1] - pair0[g]; j++) {
+          size_t p = pair0[g] + j;
+          for (int side = 0; side < 2; side++) {
+            const Rec& r = v[2 * j + side]; size_t x, y; clip_of(r, x, y);
+            u8* dst = (side ? r2.data() + o2[p] : r1.data() + o1[p]); u8* dq = (side ? q2.data() + o2[p] : q1.data() + o1[p]);
+            const u8* s4 = r.seq4(); const u8* q = r.qual();
+            for (size_t i = x; i < y; i++) { char c = T16[(s4[i >> 1] >> ((~i & 1) << 2)) & 15]; dst[i - x] = (c == 'C' || c == 'G' || c == 'T') ? (u8)c : (u8)'A'; }   // DnaString::from_acgt_bytes(...).to_string()
+            memcpy(dq, q + x, y - x);
+            u8 fl = (u8)((r.skip_align == 1 ? NB_FLAG_SKIP_ALIGN : 0) | (r.is_reverse() ? NB_FLAG_REVCOMP : 0));
+            if (side) f2[p] = fl; else f1[p] = fl;
+          }
+          scope[p] = (u32)g;
+        } } });
+    t_fill += now() - tb;
     for (u32 li = 0; li < n_refs; li++) {
+      tb = now();
       nb_batch b; memset(&b, 0, sizeof b);
       b.n_pairs = np; b.location = NB_MEM_HOST; b.max_read_len = maxlen; b.r1 = r1.data(); b.r1_off = o1.data(); b.r2 = r2.data(); b.r2_off = o2.data();
       b.q1 = q1.data(); b.q2 = q2.data(); b.flags1 = f1.data(); b.flags2 = f2.data(); b.scope_id = scope.data();
@@ -301,56 +433,68 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
       e = nb_ctx_set_option(ctx[li], "max_batch_pairs", std::max<size_t>(np, 1)); if (e) return e;
       e = nb_align_batch(ctx[li], &b, rres.data(), pres.data()); if (e) return e;
       nb_counts cts; e = nb_counts_finalize(ctx[li], &cts); if (e) return e;
+      t_gpu += now() - tb; tb = now();
       // rows per scope, in group order
-      std::vector<u64> row_begin(groups.size() + 1, 0);
+      std::vector<u64> row_begin(ng + 1, 0);
       for (u64 r = 0; r < cts.n_rows; r++) row_begin[cts.row_scope[r] + 1]++;
-      for (size_t g = 0; g < groups.size(); g++) row_begin[g + 1] += row_begin[g];
-      std::string line; size_t pbase = 0;
-      for (size_t g = 0; g < groups.size(); g++) {
-        const std::vector<ParsedRec>& v = groups[g].recs; size_t gp = v.size() / 2;
-        if (row_begin[g + 1] > row_begin[g]) {   // scopes without a callset emit nothing at all (src/process/bam.rs:329-331)
+      for (size_t g = 0; g < ng; g++) row_begin[g + 1] += row_begin[g];
+      // ---- rows: every writer thread formats a contiguous range of groups and deflates it into its own gzip member
+      const int parts = std::max(1, std::min<int>(threads, (int)((np + 4095) / 4096)));
+      std::vector<std::string> member(parts); std::vector<int> bad(parts, 0);
+      std::string header;
+      if (first_write[li]) header = "nimble_features\tnimble_score\t" + data_header("r1") + "\t" + data_header("r2") + "\tr1_filter_forward\tr1_forward_score\tr1_filter_reverse\tr1_reverse_score\tr2_filter_forward\tr2_forward_score\tr2_filter_reverse\tr2_reverse_score\ttriage_reason\taligndirection\n";
+      std::vector<size_t> cut(parts + 1, ng);   // group ranges balanced by pair count
+      cut[0] = 0; for (int t = 1; t < parts; t++) cut[t] = (size_t)(std::lower_bound(pair0.begin(), pair0.end(), np * (u64)t / parts) - pair0.begin());
+      for (int t = 1; t <= parts; t++) cut[t] = std::min(std::max(cut[t], cut[t - 1]), ng);
+      cut[parts] = ng;
+      std::vector<char> wrote(parts, 0);
+      parallel_ranges(parts, (size_t)parts, [&](size_t ta, size_t tb, int) {
+        for (size_t t = ta; t < tb; t++) {
+          std::string text; text.reserve(1 << 20); char num[32];
           std::unordered_set<std::string> scored;
-          auto emit = [&](const std::string& feats, long long score, size_t pj) {
-            const ParsedRec& sq = v[2 * pj]; const ParsedRec& mt = v[2 * pj + 1]; const nb_pair_result& pr = pres[pbase + pj];
-            const nb_read_result& ra = rres[2 * (pbase + pj)]; const nb_read_result& rb = rres[2 * (pbase + pj) + 1];
-            if (first_write[li]) { std::string h = "nimble_features\tnimble_score\t" + data_header("r1") + "\t" + data_header("r2") + "\tr1_filter_forward\tr1_forward_score\tr1_filter_reverse\tr1_reverse_score\tr2_filter_forward\tr2_forward_score\tr2_filter_reverse\tr2_reverse_score\ttriage_reason\taligndirection\n"; gzwrite(outs[li], h.data(), (unsigned)h.size()); first_write[li] = false; }
-            line.clear(); line += feats; line += "\t"; line += std::to_string(score); line += "\t";
-            data_values(mt.f, line); line += "\t"; data_values(sq.f, line); line += "\t";      // "r1" = mate slot, "r2" = sequence slot (108-117)
-            line += nb_reason_str(pr.fr2); line += "\t"; line += std::to_string(rb.pass ? rb.score : 0); line += "\tNone\t0\t";
-            line += nb_reason_str(pr.fr1); line += "\t"; line += std::to_string(ra.pass ? ra.score : 0); line += "\tNone\t0\t";
-            line += nb_reason_str(pr.triage); line += "\tNone\n";
-            gzwrite(outs[li], line.data(), (unsigned)line.size());
-          };
-          for (u64 r = row_begin[g]; r < row_begin[g + 1]; r++) {
-            u32 cs = cts.row_callset[r]; std::string feats;
-            for (u64 k = cts.callset_off[cs]; k < cts.callset_off[cs + 1]; k++) { if (!feats.empty()) feats += ","; feats += nb_library_group_name(libs[li], cts.callset_items[k]); }
-            // representative: the last pair of the scope whose read_key resolved to this callset (the reference keeps an arbitrary one)
-            size_t rep = gp;
-            for (size_t pj = gp; pj-- > 0;) { u32 slot = pres[pbase + pj].callset; if (slot != NONE32 && cts.slot_to_callset[slot] == cs) { rep = pj; break; } }
-            if (rep == gp) continue;
-            scored.insert(v[2 * rep].f[0]);
-            emit(feats, (long long)cts.row_count[r], rep);
+          for (size_t g = cut[t]; g < cut[t + 1]; g++) {
+            if (row_begin[g + 1] == row_begin[g]) continue;   // scopes without a callset emit nothing at all (src/process/bam.rs:329-331)
+            const Rec* v = &stream[gstart[g0 + g]]; const size_t gp = pair0[g + 1] - pair0[g], pbase = pair0[g];
+            scored.clear();
+            auto emit = [&](const std::string& feats, long long score, size_t pj) {
+              const Rec& sq = v[2 * pj]; const Rec& mt = v[2 * pj + 1]; const nb_pair_result& pr = pres[pbase + pj];
+              const nb_read_result& ra = rres[2 * (pbase + pj)]; const nb_read_result& rb = rres[2 * (pbase + pj) + 1];
+              text += feats; text += '\t'; snprintf(num, sizeof num, "%lld", score); text += num; text += '\t';
+              append_data_values(mt, text); text += '\t'; append_data_values(sq, text); text += '\t';      // "r1" = mate slot, "r2" = sequence slot (108-117)
+              text += nb_reason_str(pr.fr2); text += '\t'; snprintf(num, sizeof num, "%u", (unsigned)(rb.pass ? rb.score : 0)); text += num; text += "\tNone\t0\t";
+              text += nb_reason_str(pr.fr1); text += '\t'; snprintf(num, sizeof num, "%u", (unsigned)(ra.pass ? ra.score : 0)); text += num; text += "\tNone\t0\t";
+              text += nb_reason_str(pr.triage); text += "\tNone\n";
+            };
+            for (u64 r = row_begin[g]; r < row_begin[g + 1]; r++) {
+              u32 cs = cts.row_callset[r]; std::string feats;
+              for (u64 k = cts.callset_off[cs]; k < cts.callset_off[cs + 1]; k++) { if (!feats.empty()) feats += ","; feats += nb_library_group_name(libs[li], cts.callset_items[k]); }
+              // representative: the last pair of the scope whose read_key resolved to this callset (the reference keeps an arbitrary one)
+              size_t rep = gp;
+              for (size_t pj = gp; pj-- > 0;) { u32 slot = pres[pbase + pj].callset; if (slot != NONE32 && cts.slot_to_callset[slot] == cs) { rep = pj; break; } }
+              if (rep == gp) continue;
+              scored.insert(field0(v[2 * rep]));
+              emit(feats, (long long)cts.row_count[r], rep);
+            }
+            for (size_t pj = 0; pj < gp; pj++) { if (scored.count(field0(v[2 * pj + 1]))) continue; emit("", 0, pj); }   // zero rows (332-353)
           }
-          for (size_t pj = 0; pj < gp; pj++) { if (scored.count(v[2 * pj + 1].f[0])) continue; emit("", 0, pj); }   // zero rows (332-353)
-        }
-        pbase += gp;
-      }
+          if (!text.empty()) { wrote[t] = 1; if (!gzip_member(text, GZ_LEVEL, member[t])) bad[t] = 1; }
+        } });
+      t_rows += now() - tb; tb = now();
+      bool any = false; for (int t = 0; t < parts; t++) { if (bad[t]) return fail(NB_ERR_IO, "gzip of the TSV rows failed"); any = any || wrote[t]; }
+      if (any && first_write[li]) { std::string hm; if (!gzip_member(header, GZ_LEVEL, hm) || fwrite(hm.data(), 1, hm.size(), outs[li]) != hm.size()) return fail(NB_ERR_IO, "short write on the TSV"); first_write[li] = false; }
+      for (int t = 0; t < parts; t++) if (wrote[t] && fwrite(member[t].data(), 1, member[t].size(), outs[li]) != member[t].size()) return fail(NB_ERR_IO, "short write on the TSV");
+      t_write += now() - tb;
     }
-    groups.clear(); pairs_in_batch = 0;
     return NB_OK;
   };
-  while (rc == NB_OK && !done) {   // producer loop, src/process/bam.rs:157-180
-    int g = reader.get_umi();
-    if (g < 0) { rc = g; break; }
-    bool final_umi = g == 0;
-    if (final_umi && has_aligned) { done = true; break; }   // the last group is never sent when a group was sent before
-    Group grp; grp.recs = reader.current;
-    pairs_in_batch += grp.recs.size() / 2; groups.push_back(std::move(grp));
-    has_aligned = true;
-    if (final_umi) { done = true; break; }
-    if (pairs_in_batch >= BATCH_PAIRS) rc = flush();
+  for (size_t g0 = 0; g0 < n_groups && rc == NB_OK;) {
+    size_t g1 = g0, pairs = 0;
+    while (g1 < n_groups && pairs < BATCH_PAIRS) { pairs += (gstart[g1 + 1] - gstart[g1]) / 2; g1++; }
+    rc = run_batch(g0, g1);
+    g0 = g1;
   }
-  if (rc == NB_OK) rc = flush();
+  if (rc == NB_OK) for (u32 li = 0; li < n_refs; li++) if (first_write[li]) { std::string em; if (!gzip_member(std::string(), GZ_LEVEL, em) || fwrite(em.data(), 1, em.size(), outs[li]) != em.size()) rc = fail(NB_ERR_IO, "short write on the TSV"); }   // no row at all: an empty gzip stream, like the reference's untouched GzEncoder
+  if (getenv("NB_BAM_STATS")) fprintf(stderr, "nb_process_bam: %zu records in %zu groups; load+inflate %.2fs, grouping %.2fs, batch fill %.2fs, device align+finalize %.2fs, rows+gzip %.2fs, write %.2fs\n", stream.size(), n_groups, t_load, t_group, t_fill, t_gpu, t_rows, t_write);
   cleanup();
   return rc;
 }
@@ -360,23 +504,17 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
 extern "C" int nb_bam_dump_groups(const char* input_file, int force_bam_paired, int num_cores, const char* out_path) {
   if (!input_file || !out_path) return fail(NB_ERR_INVALID, "null argument");
   Bgzf z; int rc = z.load(input_file, std::max(1, num_cores)); if (rc) return rc;
-  UmiReader reader(z, force_bam_paired != 0);
-  rc = reader.rd.skip_header(); if (rc) return rc;
+  std::vector<Rec> stream; std::vector<u64> gstart;
+  rc = collect_groups(z, force_bam_paired != 0, stream, gstart); if (rc) return rc;
   FILE* f = fopen(out_path, "wb"); if (!f) return fail(NB_ERR_IO, std::string("could not open ") + out_path);
   auto hex = [](const std::string& s) { static const char* H = "0123456789abcdef"; std::string o; for (unsigned char c : s) { o += H[c >> 4]; o += H[c & 15]; } return o; };
-  bool has_aligned = false; size_t gi = 0;
-  for (;;) {
-    int g = reader.get_umi();
-    if (g < 0) { fclose(f); return g; }
-    bool final_umi = g == 0;
-    if (final_umi && has_aligned) break;
-    for (const ParsedRec& r : reader.current) {
+  for (size_t gi = 0; gi + 1 < gstart.size(); gi++) {
+    for (u64 k = gstart[gi]; k < gstart[gi + 1]; k++) {
+      ParsedRec r; parse_fields(stream[k], r);
       fprintf(f, "%zu\t%s\t%s", gi, r.seq.c_str(), hex(r.qual).c_str());
       for (int i = 0; i < 38; i++) fprintf(f, "\t%s", i == 1 ? hex(r.f[i]).c_str() : r.f[i].c_str());
       fputc('\n', f);
     }
-    gi++; has_aligned = true;
-    if (final_umi) break;
   }
   fclose(f);
   return NB_OK;

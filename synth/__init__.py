@@ -15,7 +15,7 @@ _lib = None
 def build(force=False):
     src = os.path.join(_HERE, "synth.cpp")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-pthread", "-shared", "-o", _SO, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-pthread", "-shared", "-o", _SO, src, "-lz"])
     return _SO
 
 
@@ -33,6 +33,8 @@ def lib():
         L.synth_umi_sizes.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.synth_umi_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.synth_write_bam.restype = C.c_uint64
+        L.synth_write_bam.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -100,3 +102,12 @@ def umi_reads(library, first_group, n_groups, seed=2345, L=91, n_cells=8000, err
                           library.off.ctypes.data, len(library.names), bases.ctypes.data, qual.ctypes.data, cell.ctypes.data, scope.ctypes.data, threads)
     off = np.arange(tot + 1, dtype=np.uint64) * L
     return dict(bases=bases, qual=qual, off=off, cell=cell, scope=scope, sizes=sizes, n_reads=int(tot))
+
+
+def write_umi_bam(path, u, L=91, first_scope=0, level=1, threads=8):
+    """Writes the records of `umi_reads` as a 10x-style unaligned BAM (threaded BGZF).  Returns the file size."""
+    n = lib().synth_write_bam(str(path).encode(), u["n_reads"], L, u["bases"].ctypes.data, u["qual"].ctypes.data, u["cell"].ctypes.data, u["scope"].ctypes.data,
+                              first_scope, level, threads)
+    if not n:
+        raise IOError("could not write %s" % path)
+    return int(n)

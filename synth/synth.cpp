@@ -7,7 +7,10 @@
 #include <functional>
 #include <thread>
 #include <vector>
-typedef uint8_t u8; typedef uint32_t u32; typedef uint64_t u64;
+#include <cstdio>
+#include <string>
+#include <zlib.h>
+typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64;
 namespace {
 struct Rng { u64 s; explicit Rng(u64 a, u64 b) { s = a * 0x9E3779B97F4A7C15ULL ^ (b + 0xD1B54A32D192ED03ULL) * 0xBF58476D1CE4E5B9ULL; next(); }
   u64 next() { u64 z = (s += 0x9E3779B97F4A7C15ULL); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31); }
@@ -98,5 +101,57 @@ void synth_umi_reads(u64 seed, u64 first, u64 n, const u32* sizes, const u64* re
       }
     }
   });
+}
+
+// 10x-style unaligned BAM of the reads synth_umi_reads made (C3): one record per read, tags CB:Z:<16 nt>-1, UB:Z / UR:Z
+// <12 nt> derived from the cell / group ids, CR, NH:i, RE:A; records of one group are contiguous (what UMIReader needs,
+// src/parse/sorted_bam_reader.rs:84).  BGZF blocks are deflated on `threads` threads.  Returns bytes written, 0 on error.
+static void nt_of(u64 v, int n, char* o) { for (int i = 0; i < n; i++) { o[i] = B[v & 3]; v >>= 2; } }
+u64 synth_write_bam(const char* path, u64 n_reads, u32 L, const char* bases, const u8* qual, const u32* cell, const u32* scope, u32 first_scope, int level, int threads) {
+  static const u8 code[256] = {0};
+  u8 c4[256]; memset(c4, 15, 256); c4[(u8)'A'] = 1; c4[(u8)'C'] = 2; c4[(u8)'G'] = 4; c4[(u8)'T'] = 8; (void)code;
+  const char* text = "@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:chr1\tLN:100000000\n";
+  std::string raw; raw.append("BAM\1", 4);
+  auto put32 = [&](std::string& d, u32 v) { d.append((const char*)&v, 4); };
+  put32(raw, (u32)strlen(text)); raw.append(text); put32(raw, 1); put32(raw, 5); raw.append("chr1\0", 5); put32(raw, 100000000);
+  const u64 rec_guess = 36 + 16 + (L + 1) / 2 + L + 80;
+  std::vector<std::string> parts(threads > 0 ? threads : 1);
+  par((int)parts.size(), n_reads, [&](u64 x, u64 y) {
+    size_t pi = 0; for (size_t t = 0; t < parts.size(); t++) if (n_reads * (u64)t / parts.size() == x) pi = t;   // the slice `par` gave this thread
+    std::string& d = parts[pi];
+    d.reserve((y - x) * rec_guess);
+    char name[32], cb[20], ub[13];
+    for (u64 i = x; i < y; i++) {
+      int ln = snprintf(name, sizeof name, "r%llu", (unsigned long long)i) + 1;
+      u64 g = (u64)scope[i] + first_scope; nt_of(g * 0x9E3779B97F4A7C15ULL >> 8, 12, ub); ub[12] = 0; nt_of((u64)cell[i] * 0xD1B54A32D192ED03ULL >> 8, 16, cb); cb[16] = '-'; cb[17] = '1'; cb[18] = 0;
+      std::string aux; aux.append("CBZ"); aux.append(cb, 19); aux.append("CRZ"); aux.append(cb, 16); aux.push_back(0); aux.append("UBZ"); aux.append(ub, 13); aux.append("URZ"); aux.append(ub, 13);
+      aux.append("NHC"); aux.push_back(1); aux.append("REA"); aux.push_back('E');
+      u32 body = 32 + ln + (L + 1) / 2 + L + (u32)aux.size();
+      put32(d, body); put32(d, (u32)-1); put32(d, (u32)-1);
+      u8 hdr8[4] = {(u8)ln, 255, (u8)(4680 & 255), (u8)(4680 >> 8)}; d.append((const char*)hdr8, 4);
+      u16 ncig = 0, flag = 4; d.append((const char*)&ncig, 2); d.append((const char*)&flag, 2);
+      put32(d, L); put32(d, (u32)-1); put32(d, (u32)-1); put32(d, 0);
+      d.append(name, ln);
+      const char* sq = bases + i * (u64)L;
+      for (u32 k = 0; k < L; k += 2) d.push_back((char)((c4[(u8)sq[k]] << 4) | (k + 1 < L ? c4[(u8)sq[k + 1]] : 0)));
+      d.append((const char*)(qual + i * (u64)L), L);
+      d.append(aux);
+    }
+  });
+  for (auto& d : parts) { raw.append(d); std::string().swap(d); }
+  const u64 BS = 60000; u64 nblk = (raw.size() + BS - 1) / BS;
+  std::vector<std::string> comp(nblk + 1);
+  auto deflate_block = [&](const char* src, u32 n, std::string& out) {
+    z_stream z; memset(&z, 0, sizeof z); deflateInit2(&z, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+    std::string buf(deflateBound(&z, n) + 64, '\0'); z.next_in = (Bytef*)src; z.avail_in = n; z.next_out = (Bytef*)&buf[0]; z.avail_out = (uInt)buf.size();
+    deflate(&z, Z_FINISH); u32 clen = (u32)z.total_out; deflateEnd(&z);
+    u8 h[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 0, 0}; u16 bsize = (u16)(clen + 25); h[16] = (u8)(bsize & 255); h[17] = (u8)(bsize >> 8);
+    out.assign((const char*)h, 18); out.append(buf.data(), clen); u32 crc = (u32)crc32(crc32(0, nullptr, 0), (const Bytef*)src, n); out.append((const char*)&crc, 4); out.append((const char*)&n, 4);
+  };
+  par(threads, nblk, [&](u64 x, u64 y) { for (u64 b = x; b < y; b++) deflate_block(raw.data() + b * BS, (u32)std::min<u64>(BS, raw.size() - b * BS), comp[b]); });
+  deflate_block("", 0, comp[nblk]);
+  FILE* f = fopen(path, "wb"); if (!f) return 0;
+  u64 tot = 0; for (auto& c : comp) { if (fwrite(c.data(), 1, c.size(), f) != c.size()) { fclose(f); return 0; } tot += c.size(); }
+  fclose(f); return tot;
 }
 }
