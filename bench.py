@@ -124,11 +124,11 @@ def run_reference(args):
     dt = (time.time() - t0) / args.steps
     v = 2 * n / dt
     sample = "%d of the 10M C2 pairs per step (pairs 0..%d of the same seeded stream), %d threads over contiguous shards" % (n, n, cores)
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    emit_json({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer (f64 thresholds)",
                       "data": "synthetic", "config": {"workload": "C2: 1k-transcript family library x 2x150 bp pairs, FASTQ-mode scope", "sample_pairs": n},
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def merge_across_ranks(ctx, nb, torch, dist, rank, world, pair_base):
@@ -184,7 +184,26 @@ def merge_across_ranks(ctx, nb, torch, dist, rank, world, pair_base):
     return raw, int(uniq.item())
 
 
+_JSON_OUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly one JSON line: everything else that any library prints there (NCCL's version banner,
+    torchrun notices of child ranks) is sent to stderr; emit_json writes to the saved descriptor."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit_json(obj):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -210,8 +229,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")             # at these two levels NCCL prints its version banner on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.pairs
     cores = os.cpu_count() or 1
@@ -359,8 +378,7 @@ def main():
                            "kernel": "map stage = k_seed + k_walk (one launch pair per chunk; events bracket the pair)", "peak_source": peak_src, "algorithmic_bytes_per_read": bpr, "reads_per_launch": reads_per_launch,
                            "launch_ms": launch_ms, "kernel_share_of_step": ks["map_ms"] / (ms_dev * args.steps),
                            "work_per_read": {k: ref["work"][k] / (2.0 * m) for k in ("probes", "nodes", "bases", "colour_elems")}}
-    print(json.dumps(out))
-    sys.stdout.flush()
+    emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <future>
 #include <string>
 #include <thread>
 #include <unordered_set>
@@ -169,12 +170,20 @@ void parse_fields(const Rec& r, ParsedRec& o) {   // src/parse/bam.rs:186-236
   }
 }
 
+void parallel_ranges(int threads, size_t n, const std::function<void(size_t, size_t, int)>& fn) {
+  if (threads <= 1 || n < 2) { fn(0, n, 0); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++) th.emplace_back(fn, n * (size_t)t / threads, n * (size_t)(t + 1) / threads, t);
+  for (auto& x : th) x.join();
+}
+
 // ------------------------------------------------------------------ SortedBamReader (src/parse/sorted_bam_reader.rs)
 inline bool same(const char* a, u32 al, const char* b, u32 bl) { return al == bl && (al == 0 || !memcmp(a, b, al)); }
 inline int cmp_bytes(const char* a, u32 al, const char* b, u32 bl) { int c = memcmp(a, b, std::min(al, bl)); return c ? c : (al < bl ? -1 : al > bl ? 1 : 0); }
 
 struct SortedReader {
   const Bgzf& z; size_t cur = 0; bool force_paired; bool header_done = false;
+  std::vector<Rec> all; size_t next_rec = 0;   // every record of the file, keys already scanned (prepare())
   std::string current_umi, next_umi; std::vector<Rec> buffer, next_records;   // buffer is popped from the back
   SortedReader(const Bgzf& zz, bool fp) : z(zz), force_paired(fp) {}
   int skip_header() {
@@ -184,13 +193,18 @@ struct SortedReader {
     for (u32 i = 0; i < n_ref; i++) { if (p + 4 > d.size()) return fail(NB_ERR_PARSE, "truncated BAM header"); u32 l; memcpy(&l, &d[p], 4); p += 4 + (size_t)l + 4; }
     cur = p; header_done = true; return NB_OK;
   }
-  bool read_record(Rec& r) {
+  // locate the records (serial walk over block sizes), then scan their grouping keys on `threads` threads
+  void prepare(int threads) {
     const std::vector<u8>& d = z.data;
-    if (cur + 4 > d.size()) return false;
-    u32 bs; memcpy(&bs, &d[cur], 4);
-    if (bs < 32 || cur + 4 + bs > d.size()) return false;
-    r.p = &d[cur + 4]; r.block = bs; r.skip_align = -1; cur += 4 + bs; r.scan_keys(); return true;
+    while (cur + 4 <= d.size()) {
+      u32 bs; memcpy(&bs, &d[cur], 4);
+      if (bs < 32 || cur + 4 + bs > d.size()) break;
+      Rec r; r.p = &d[cur + 4]; r.block = bs; all.push_back(r); cur += 4 + bs;
+      if (all.size() == 4096) all.reserve((size_t)((double)d.size() / (double)cur * 4096 * 1.1) + 4096);   // one allocation for the whole file
+    }
+    parallel_ranges(threads, all.size(), [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) all[i].scan_keys(); });
   }
+  bool read_record(Rec& r) { if (next_rec >= all.size()) return false; r = all[next_rec++]; return true; }
   int fill_buffer() {   // 31-107
     buffer.clear(); buffer.swap(next_records); next_records.clear();
     current_umi = next_umi;
@@ -210,13 +224,14 @@ struct SortedReader {
     }
     return NB_OK;   // end of file: this last buffer is NOT sorted by CB (quirk kept)
   }
+  std::vector<Rec> tmp;   // scratch reused across buffers (one UMI buffer is a handful of records: allocation would dominate)
   void add_dummy_paired_reads() {   // 109-125
-    std::vector<Rec> nb2; nb2.reserve(2 * buffer.size());
+    std::vector<Rec>& nb2 = tmp; nb2.clear();
     for (const Rec& r : buffer) { Rec m = r; m.skip_align = 0; nb2.push_back(m); if (!r.is_paired()) { Rec d = r; d.skip_align = 1; nb2.push_back(d); } }
     buffer.swap(nb2);
   }
   void filter_paired_reads() {      // 127-162
-    std::vector<Rec> out; out.reserve(buffer.size()); size_t i = 0;
+    std::vector<Rec>& out = tmp; out.clear(); size_t i = 0;
     while (i < buffer.size()) {
       if (i + 1 >= buffer.size()) break;
       if (same(buffer[i].qname_ptr(), buffer[i].qname_len(), buffer[i + 1].qname_ptr(), buffer[i + 1].qname_len())) {
@@ -264,9 +279,10 @@ struct UmiReader {
 
 // The groups the producer loop sends, in order (src/process/bam.rs:157-180): records of group g are
 // stream[gstart[g] .. gstart[g+1]); the last group is never sent when a group was sent before.
-int collect_groups(const Bgzf& z, bool force_paired, std::vector<Rec>& stream, std::vector<u64>& gstart) {
+int collect_groups(const Bgzf& z, bool force_paired, int threads, std::vector<Rec>& stream, std::vector<u64>& gstart) {
   UmiReader reader(z, force_paired);
   int rc = reader.rd.skip_header(); if (rc) return rc;
+  reader.rd.prepare(threads);
   stream.clear(); gstart.assign(1, 0);
   bool has_aligned = false;
   for (;;) {
@@ -279,13 +295,6 @@ int collect_groups(const Bgzf& z, bool force_paired, std::vector<Rec>& stream, s
     if (final_umi) break;
   }
   return NB_OK;
-}
-
-void parallel_ranges(int threads, size_t n, const std::function<void(size_t, size_t, int)>& fn) {
-  if (threads <= 1 || n < 2) { fn(0, n, 0); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < threads; t++) th.emplace_back(fn, n * (size_t)t / threads, n * (size_t)(t + 1) / threads, t);
-  for (auto& x : th) x.join();
 }
 
 // clipped length / start of a record's sequence (strip_nonbio_regions, src/parse/bam.rs:258-268)
@@ -378,123 +387,157 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
     if (rc == NB_OK) { outs[i] = fopen(output_paths[i], "wb"); if (!outs[i]) rc = fail(NB_ERR_IO, std::string("could not open output ") + output_paths[i]); }
   }
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  double t_load = 0, t_group = 0, t_fill = 0, t_gpu = 0, t_rows = 0, t_write = 0, t0 = now();   // NB_BAM_STATS=1 prints the phase times
+  double t_load = 0, t_group = 0, t_fill = 0, t_gpu = 0, t_rows = 0, t_align = 0, t_final = 0, t0 = now(); const double t_start = t0;   // NB_BAM_STATS=1 prints the phase times
   Bgzf z; std::vector<Rec> stream; std::vector<u64> gstart;
   if (rc == NB_OK) rc = z.load(input_file, threads);
   t_load = now() - t0; t0 = now();
-  if (rc == NB_OK) rc = collect_groups(z, force_bam_paired != 0, stream, gstart);
+  if (rc == NB_OK) rc = collect_groups(z, force_bam_paired != 0, threads, stream, gstart);
   t_group = now() - t0;
   if (rc != NB_OK) { cleanup(); return rc; }
   const size_t n_groups = gstart.size() - 1;
   const size_t BATCH_PAIRS = 1u << 20;
   const int GZ_LEVEL = 4;
-  std::vector<u8> r1, r2, q1, q2, f1, f2; std::vector<u64> o1, o2; std::vector<u32> scope;
-  std::vector<nb_read_result> rres; std::vector<nb_pair_result> pres;
   static const char* T16 = "=ACMGRSVTWYHKDBN";
-  // one batch = groups [g0, g1)
-  auto run_batch = [&](size_t g0, size_t g1) -> int {
-    const size_t ng = g1 - g0;
-    std::vector<u64> pair0(ng + 1, 0);   // first pair of each group within the batch
-    for (size_t g = 0; g < ng; g++) pair0[g + 1] = pair0[g] + (gstart[g0 + g + 1] - gstart[g0 + g]) / 2;
-    const size_t np = pair0[ng];
-    if (!np) return NB_OK;
+  // Three stages run concurrently on consecutive batches: (F) the host threads fill batch k+1 into pinned buffers,
+  // (D) the device aligns batch k and its counts are finalized, (R) the host threads format + gzip the rows of batch k-1.
+  struct Pinned { u8* p = nullptr; size_t cap = 0; int ensure(size_t n) { if (n <= cap) return NB_OK; nb_host_free(p); cap = n + n / 4 + 4096; p = (u8*)nb_host_alloc(cap); if (!p) { cap = 0; return fail(NB_ERR_CUDA, "pinned host allocation failed"); } return NB_OK; } ~Pinned() { nb_host_free(p); } };
+  struct BatchIn { size_t g0 = 0, g1 = 0, np = 0; u32 maxlen = 1; std::vector<u64> pair0, o1, o2; std::vector<u8> f1, f2; std::vector<u32> scope; Pinned r1, r2, q1, q2; };
+  struct BatchOut { std::vector<nb_read_result> rres; std::vector<nb_pair_result> pres; std::vector<u64> row_begin, callset_off; std::vector<u32> row_callset, callset_items, slot_to_callset; std::vector<i64> row_count; };
+  BatchIn bin[3]; BatchOut bout[2];
+  std::vector<std::pair<size_t, size_t>> batches;
+  for (size_t g0 = 0; g0 < n_groups;) { size_t g1 = g0, pairs = 0; while (g1 < n_groups && pairs < BATCH_PAIRS) { pairs += (gstart[g1 + 1] - gstart[g1]) / 2; g1++; } batches.push_back({g0, g1}); g0 = g1; }
+  std::atomic<u64> ns_fill(0), ns_rows(0);
+  // ---- (F) batch arrays: even record = sequence slot, odd = mate slot (src/process/bam.rs:257-292)
+  auto fill = [&](BatchIn& B, size_t g0, size_t g1) -> int {
     double tb = now();
-    // ---- batch arrays, filled on the host threads: even record = sequence slot, odd = mate slot (src/process/bam.rs:257-292)
-    o1.assign(np + 1, 0); o2.assign(np + 1, 0); f1.resize(np); f2.resize(np); scope.resize(np);
+    B.g0 = g0; B.g1 = g1; const size_t ng = g1 - g0;
+    B.pair0.assign(ng + 1, 0);
+    for (size_t g = 0; g < ng; g++) B.pair0[g + 1] = B.pair0[g] + (gstart[g0 + g + 1] - gstart[g0 + g]) / 2;
+    const size_t np = B.np = B.pair0[ng];
+    B.o1.assign(np + 1, 0); B.o2.assign(np + 1, 0); B.f1.resize(np); B.f2.resize(np); B.scope.resize(np);
     parallel_ranges(threads, ng, [&](size_t a, size_t b, int) {
       for (size_t g = a; g < b; g++) { const Rec* v = &stream[gstart[g0 + g]];
-        for (size_t j = 0; j < pair0[g + 1] - pair0[g]; j++) { size_t x, y; clip_of(v[2 * j], x, y); o1[pair0[g] + j + 1] = y - x; clip_of(v[2 * j + 1], x, y); o2[pair0[g] + j + 1] = y - x; } } });
-    u32 maxlen = 1;
-    for (size_t p = 0; p < np; p++) { maxlen = std::max<u32>(maxlen, (u32)std::max(o1[p + 1], o2[p + 1])); o1[p + 1] += o1[p]; o2[p + 1] += o2[p]; }
-    r1.resize(o1[np] + 64); q1.resize(o1[np] + 64); r2.resize(o2[np] + 64); q2.resize(o2[np] + 64);
+        for (size_t j = 0; j < B.pair0[g + 1] - B.pair0[g]; j++) { size_t x, y; clip_of(v[2 * j], x, y); B.o1[B.pair0[g] + j + 1] = y - x; clip_of(v[2 * j + 1], x, y); B.o2[B.pair0[g] + j + 1] = y - x; } } });
+    B.maxlen = 1;
+    for (size_t p = 0; p < np; p++) { B.maxlen = std::max<u32>(B.maxlen, (u32)std::max(B.o1[p + 1], B.o2[p + 1])); B.o1[p + 1] += B.o1[p]; B.o2[p + 1] += B.o2[p]; }
+    int e = B.r1.ensure(B.o1[np] + 64); if (!e) e = B.q1.ensure(B.o1[np] + 64); if (!e) e = B.r2.ensure(B.o2[np] + 64); if (!e) e = B.q2.ensure(B.o2[np] + 64); if (e) return e;
     parallel_ranges(threads, ng, [&](size_t a, size_t b, int) {
       for (size_t g = a; g < b; g++) { const Rec* v = &stream[gstart[g0 + g]];
-        for (size_t j = 0; j < pair0[g + 1] - pair0[g]; j++) {
-          size_t p = pair0[g] + j;
+        for (size_t j = 0; j < B.pair0[g + 1] - B.pair0[g]; j++) {
+          size_t p = B.pair0[g] + j;
           for (int side = 0; side < 2; side++) {
             const Rec& r = v[2 * j + side]; size_t x, y; clip_of(r, x, y);
-            u8* dst = (side ? r2.data() + o2[p] : r1.data() + o1[p]); u8* dq = (side ? q2.data() + o2[p] : q1.data() + o1[p]);
+            u8* dst = (side ? B.r2.p + B.o2[p] : B.r1.p + B.o1[p]); u8* dq = (side ? B.q2.p + B.o2[p] : B.q1.p + B.o1[p]);
             const u8* s4 = r.seq4(); const u8* q = r.qual();
             for (size_t i = x; i < y; i++) { char c = T16[(s4[i >> 1] >> ((~i & 1) << 2)) & 15]; dst[i - x] = (c == 'C' || c == 'G' || c == 'T') ? (u8)c : (u8)'A'; }   // DnaString::from_acgt_bytes(...).to_string()
             memcpy(dq, q + x, y - x);
             u8 fl = (u8)((r.skip_align == 1 ? NB_FLAG_SKIP_ALIGN : 0) | (r.is_reverse() ? NB_FLAG_REVCOMP : 0));
-            if (side) f2[p] = fl; else f1[p] = fl;
+            if (side) B.f2[p] = fl; else B.f1[p] = fl;
           }
-          scope[p] = (u32)g;
+          B.scope[p] = (u32)g;
         } } });
-    t_fill += now() - tb;
-    for (u32 li = 0; li < n_refs; li++) {
-      tb = now();
-      nb_batch b; memset(&b, 0, sizeof b);
-      b.n_pairs = np; b.location = NB_MEM_HOST; b.max_read_len = maxlen; b.r1 = r1.data(); b.r1_off = o1.data(); b.r2 = r2.data(); b.r2_off = o2.data();
-      b.q1 = q1.data(); b.q2 = q2.data(); b.flags1 = f1.data(); b.flags2 = f2.data(); b.scope_id = scope.data();
-      rres.resize(2 * np); pres.resize(np);
-      int e = nb_counts_reset(ctx[li]); if (e) return e;
-      e = nb_ctx_set_option(ctx[li], "max_batch_pairs", std::max<size_t>(np, 1)); if (e) return e;
-      e = nb_align_batch(ctx[li], &b, rres.data(), pres.data()); if (e) return e;
-      nb_counts cts; e = nb_counts_finalize(ctx[li], &cts); if (e) return e;
-      t_gpu += now() - tb; tb = now();
-      // rows per scope, in group order
-      std::vector<u64> row_begin(ng + 1, 0);
-      for (u64 r = 0; r < cts.n_rows; r++) row_begin[cts.row_scope[r] + 1]++;
-      for (size_t g = 0; g < ng; g++) row_begin[g + 1] += row_begin[g];
-      // ---- rows: every writer thread formats a contiguous range of groups and deflates it into its own gzip member
-      const int parts = std::max(1, std::min<int>(threads, (int)((np + 4095) / 4096)));
-      std::vector<std::string> member(parts); std::vector<int> bad(parts, 0);
-      std::string header;
-      if (first_write[li]) header = "nimble_features\tnimble_score\t" + data_header("r1") + "\t" + data_header("r2") + "\tr1_filter_forward\tr1_forward_score\tr1_filter_reverse\tr1_reverse_score\tr2_filter_forward\tr2_forward_score\tr2_filter_reverse\tr2_reverse_score\ttriage_reason\taligndirection\n";
-      std::vector<size_t> cut(parts + 1, ng);   // group ranges balanced by pair count
-      cut[0] = 0; for (int t = 1; t < parts; t++) cut[t] = (size_t)(std::lower_bound(pair0.begin(), pair0.end(), np * (u64)t / parts) - pair0.begin());
-      for (int t = 1; t <= parts; t++) cut[t] = std::min(std::max(cut[t], cut[t - 1]), ng);
-      cut[parts] = ng;
-      std::vector<char> wrote(parts, 0);
-      parallel_ranges(parts, (size_t)parts, [&](size_t ta, size_t tb, int) {
-        for (size_t t = ta; t < tb; t++) {
-          std::string text; text.reserve(1 << 20); char num[32];
-          std::unordered_set<std::string> scored;
-          for (size_t g = cut[t]; g < cut[t + 1]; g++) {
-            if (row_begin[g + 1] == row_begin[g]) continue;   // scopes without a callset emit nothing at all (src/process/bam.rs:329-331)
-            const Rec* v = &stream[gstart[g0 + g]]; const size_t gp = pair0[g + 1] - pair0[g], pbase = pair0[g];
-            scored.clear();
-            auto emit = [&](const std::string& feats, long long score, size_t pj) {
-              const Rec& sq = v[2 * pj]; const Rec& mt = v[2 * pj + 1]; const nb_pair_result& pr = pres[pbase + pj];
-              const nb_read_result& ra = rres[2 * (pbase + pj)]; const nb_read_result& rb = rres[2 * (pbase + pj) + 1];
-              text += feats; text += '\t'; snprintf(num, sizeof num, "%lld", score); text += num; text += '\t';
-              append_data_values(mt, text); text += '\t'; append_data_values(sq, text); text += '\t';      // "r1" = mate slot, "r2" = sequence slot (108-117)
-              text += nb_reason_str(pr.fr2); text += '\t'; snprintf(num, sizeof num, "%u", (unsigned)(rb.pass ? rb.score : 0)); text += num; text += "\tNone\t0\t";
-              text += nb_reason_str(pr.fr1); text += '\t'; snprintf(num, sizeof num, "%u", (unsigned)(ra.pass ? ra.score : 0)); text += num; text += "\tNone\t0\t";
-              text += nb_reason_str(pr.triage); text += "\tNone\n";
-            };
-            for (u64 r = row_begin[g]; r < row_begin[g + 1]; r++) {
-              u32 cs = cts.row_callset[r]; std::string feats;
-              for (u64 k = cts.callset_off[cs]; k < cts.callset_off[cs + 1]; k++) { if (!feats.empty()) feats += ","; feats += nb_library_group_name(libs[li], cts.callset_items[k]); }
-              // representative: the last pair of the scope whose read_key resolved to this callset (the reference keeps an arbitrary one)
-              size_t rep = gp;
-              for (size_t pj = gp; pj-- > 0;) { u32 slot = pres[pbase + pj].callset; if (slot != NONE32 && cts.slot_to_callset[slot] == cs) { rep = pj; break; } }
-              if (rep == gp) continue;
-              scored.insert(field0(v[2 * rep]));
-              emit(feats, (long long)cts.row_count[r], rep);
-            }
-            for (size_t pj = 0; pj < gp; pj++) { if (scored.count(field0(v[2 * pj + 1]))) continue; emit("", 0, pj); }   // zero rows (332-353)
-          }
-          if (!text.empty()) { wrote[t] = 1; if (!gzip_member(text, GZ_LEVEL, member[t])) bad[t] = 1; }
-        } });
-      t_rows += now() - tb; tb = now();
-      bool any = false; for (int t = 0; t < parts; t++) { if (bad[t]) return fail(NB_ERR_IO, "gzip of the TSV rows failed"); any = any || wrote[t]; }
-      if (any && first_write[li]) { std::string hm; if (!gzip_member(header, GZ_LEVEL, hm) || fwrite(hm.data(), 1, hm.size(), outs[li]) != hm.size()) return fail(NB_ERR_IO, "short write on the TSV"); first_write[li] = false; }
-      for (int t = 0; t < parts; t++) if (wrote[t] && fwrite(member[t].data(), 1, member[t].size(), outs[li]) != member[t].size()) return fail(NB_ERR_IO, "short write on the TSV");
-      t_write += now() - tb;
-    }
+    ns_fill += (u64)((now() - tb) * 1e9);
     return NB_OK;
   };
-  for (size_t g0 = 0; g0 < n_groups && rc == NB_OK;) {
-    size_t g1 = g0, pairs = 0;
-    while (g1 < n_groups && pairs < BATCH_PAIRS) { pairs += (gstart[g1 + 1] - gstart[g1]) / 2; g1++; }
-    rc = run_batch(g0, g1);
-    g0 = g1;
+  // ---- (D) device: align + finalize; the count rows are copied out (the context reuses that memory on the next finalize)
+  auto on_device = [&](const BatchIn& B, u32 li, BatchOut& O) -> int {
+    if (!B.np) { O.row_begin.assign(B.g1 - B.g0 + 1, 0); return NB_OK; }
+    double tb = now();
+    nb_batch b; memset(&b, 0, sizeof b);
+    b.n_pairs = B.np; b.location = NB_MEM_HOST; b.max_read_len = B.maxlen; b.r1 = B.r1.p; b.r1_off = B.o1.data(); b.r2 = B.r2.p; b.r2_off = B.o2.data();
+    b.q1 = B.q1.p; b.q2 = B.q2.p; b.flags1 = B.f1.data(); b.flags2 = B.f2.data(); b.scope_id = B.scope.data();
+    O.rres.resize(2 * B.np); O.pres.resize(B.np);
+    double ta = now();
+    int e = nb_counts_reset(ctx[li]); if (e) return e;
+    e = nb_ctx_set_option(ctx[li], "max_batch_pairs", std::max<size_t>(B.np, 1)); if (e) return e;
+    double tb1 = now();
+    e = nb_align_batch(ctx[li], &b, O.rres.data(), O.pres.data()); if (e) return e;
+    double tb2 = now(); nb_ctx_sync(ctx[li]); double tb3 = now();
+    if (getenv("NB_BAM_STATS")) fprintf(stderr, "  batch: np=%zu resize %.1f ms, reset+opt %.1f ms, align call %.1f ms, sync %.1f ms\n", B.np, (ta - tb) * 1e3, (tb1 - ta) * 1e3, (tb2 - tb1) * 1e3, (tb3 - tb2) * 1e3);
+    t_align += now() - tb; double tf = now();
+    nb_counts cts; e = nb_counts_finalize(ctx[li], &cts); if (e) return e;
+    t_final += now() - tf;
+    const size_t ng = B.g1 - B.g0;
+    O.row_begin.assign(ng + 1, 0);
+    for (u64 r = 0; r < cts.n_rows; r++) O.row_begin[cts.row_scope[r] + 1]++;
+    for (size_t g = 0; g < ng; g++) O.row_begin[g + 1] += O.row_begin[g];
+    O.row_callset.assign(cts.row_callset, cts.row_callset + cts.n_rows); O.row_count.assign(cts.row_count, cts.row_count + cts.n_rows);
+    O.callset_off.assign(cts.callset_off, cts.callset_off + cts.n_callsets + 1); O.callset_items.assign(cts.callset_items, cts.callset_items + cts.callset_off[cts.n_callsets]);
+    O.slot_to_callset.assign(cts.slot_to_callset, cts.slot_to_callset + cts.n_slots);
+    t_gpu += now() - tb;
+    return NB_OK;
+  };
+  // ---- (R) rows: every writer thread formats a contiguous range of groups and deflates it into its own gzip member
+  auto rows = [&](const BatchIn& B, u32 li, const BatchOut& O) -> int {
+    if (!B.np) return NB_OK;
+    double tb = now();
+    const size_t ng = B.g1 - B.g0, np = B.np, g0 = B.g0;
+    const std::vector<u64>& pair0 = B.pair0; const std::vector<u64>& row_begin = O.row_begin;
+    const int parts = std::max(1, std::min<int>(threads, (int)((np + 4095) / 4096)));
+    std::vector<std::string> member(parts); std::vector<int> bad(parts, 0); std::vector<char> wrote(parts, 0);
+    std::vector<size_t> cut(parts + 1, ng);   // group ranges balanced by pair count
+    cut[0] = 0; for (int t = 1; t < parts; t++) cut[t] = (size_t)(std::lower_bound(pair0.begin(), pair0.end(), np * (u64)t / parts) - pair0.begin());
+    for (int t = 1; t <= parts; t++) cut[t] = std::min(std::max(cut[t], cut[t - 1]), ng);
+    cut[parts] = ng;
+    parallel_ranges(parts, (size_t)parts, [&](size_t ta, size_t tb2, int) {
+      for (size_t t = ta; t < tb2; t++) {
+        std::string text; text.reserve(1 << 20); char num[32];
+        std::unordered_set<std::string> scored;
+        for (size_t g = cut[t]; g < cut[t + 1]; g++) {
+          if (row_begin[g + 1] == row_begin[g]) continue;   // scopes without a callset emit nothing at all (src/process/bam.rs:329-331)
+          const Rec* v = &stream[gstart[g0 + g]]; const size_t gp = pair0[g + 1] - pair0[g], pbase = pair0[g];
+          scored.clear();
+          auto emit = [&](const std::string& feats, long long score, size_t pj) {
+            const Rec& sq = v[2 * pj]; const Rec& mt = v[2 * pj + 1]; const nb_pair_result& pr = O.pres[pbase + pj];
+            const nb_read_result& ra = O.rres[2 * (pbase + pj)]; const nb_read_result& rb = O.rres[2 * (pbase + pj) + 1];
+            text += feats; text += '\t'; snprintf(num, sizeof num, "%lld", score); text += num; text += '\t';
+            append_data_values(mt, text); text += '\t'; append_data_values(sq, text); text += '\t';      // "r1" = mate slot, "r2" = sequence slot (108-117)
+            text += nb_reason_str(pr.fr2); text += '\t'; snprintf(num, sizeof num, "%u", (unsigned)(rb.pass ? rb.score : 0)); text += num; text += "\tNone\t0\t";
+            text += nb_reason_str(pr.fr1); text += '\t'; snprintf(num, sizeof num, "%u", (unsigned)(ra.pass ? ra.score : 0)); text += num; text += "\tNone\t0\t";
+            text += nb_reason_str(pr.triage); text += "\tNone\n";
+          };
+          for (u64 r = row_begin[g]; r < row_begin[g + 1]; r++) {
+            u32 cs = O.row_callset[r]; std::string feats;
+            for (u64 k = O.callset_off[cs]; k < O.callset_off[cs + 1]; k++) { if (!feats.empty()) feats += ","; feats += nb_library_group_name(libs[li], O.callset_items[k]); }
+            // representative: the last pair of the scope whose read_key resolved to this callset (the reference keeps an arbitrary one)
+            size_t rep = gp;
+            for (size_t pj = gp; pj-- > 0;) { u32 slot = O.pres[pbase + pj].callset; if (slot != NONE32 && O.slot_to_callset[slot] == cs) { rep = pj; break; } }
+            if (rep == gp) continue;
+            scored.insert(field0(v[2 * rep]));
+            emit(feats, (long long)O.row_count[r], rep);
+          }
+          for (size_t pj = 0; pj < gp; pj++) { if (scored.count(field0(v[2 * pj + 1]))) continue; emit("", 0, pj); }   // zero rows (332-353)
+        }
+        if (!text.empty()) { wrote[t] = 1; if (!gzip_member(text, GZ_LEVEL, member[t])) bad[t] = 1; }
+      } });
+    bool any = false; for (int t = 0; t < parts; t++) { if (bad[t]) return fail(NB_ERR_IO, "gzip of the TSV rows failed"); any = any || wrote[t]; }
+    if (any && first_write[li]) {
+      std::string header = "nimble_features\tnimble_score\t" + data_header("r1") + "\t" + data_header("r2") + "\tr1_filter_forward\tr1_forward_score\tr1_filter_reverse\tr1_reverse_score\tr2_filter_forward\tr2_forward_score\tr2_filter_reverse\tr2_reverse_score\ttriage_reason\taligndirection\n";
+      std::string hm; if (!gzip_member(header, GZ_LEVEL, hm) || fwrite(hm.data(), 1, hm.size(), outs[li]) != hm.size()) return fail(NB_ERR_IO, "short write on the TSV"); first_write[li] = false; }
+    for (int t = 0; t < parts; t++) if (wrote[t] && fwrite(member[t].data(), 1, member[t].size(), outs[li]) != member[t].size()) return fail(NB_ERR_IO, "short write on the TSV");
+    ns_rows += (u64)((now() - tb) * 1e9);
+    return NB_OK;
+  };
+  {
+    // pipeline items = (batch, library) in order; batch inputs rotate over three buffers, device results over two
+    const size_t nb_ = batches.size(); const size_t n_items = nb_ * n_refs;
+    std::future<int> fut_fill, fut_rows;
+    if (nb_) rc = fill(bin[0], batches[0].first, batches[0].second);
+    for (size_t it = 0; it < n_items && rc == NB_OK; it++) {
+      const size_t k = it / n_refs; const u32 li = (u32)(it % n_refs);
+      if (li == 0 && k + 1 < nb_) fut_fill = std::async(std::launch::async, fill, std::ref(bin[(k + 1) % 3]), batches[k + 1].first, batches[k + 1].second);
+      int e = on_device(bin[k % 3], li, bout[it % 2]);
+      if (fut_rows.valid()) { int er = fut_rows.get(); if (er && !e) e = er; }
+      if (!e) fut_rows = std::async(std::launch::async, rows, std::cref(bin[k % 3]), li, std::cref(bout[it % 2]));
+      if (li + 1 == n_refs && fut_fill.valid()) { int ef = fut_fill.get(); if (ef && !e) e = ef; }
+      rc = e;
+    }
+    if (fut_fill.valid()) fut_fill.get();
+    if (fut_rows.valid()) { int er = fut_rows.get(); if (er && rc == NB_OK) rc = er; }
   }
+  t_fill = ns_fill.load() * 1e-9; t_rows = ns_rows.load() * 1e-9;
   if (rc == NB_OK) for (u32 li = 0; li < n_refs; li++) if (first_write[li]) { std::string em; if (!gzip_member(std::string(), GZ_LEVEL, em) || fwrite(em.data(), 1, em.size(), outs[li]) != em.size()) rc = fail(NB_ERR_IO, "short write on the TSV"); }   // no row at all: an empty gzip stream, like the reference's untouched GzEncoder
-  if (getenv("NB_BAM_STATS")) fprintf(stderr, "nb_process_bam: %zu records in %zu groups; load+inflate %.2fs, grouping %.2fs, batch fill %.2fs, device align+finalize %.2fs, rows+gzip %.2fs, write %.2fs\n", stream.size(), n_groups, t_load, t_group, t_fill, t_gpu, t_rows, t_write);
+  if (getenv("NB_BAM_STATS")) fprintf(stderr, "nb_process_bam: %zu records in %zu groups; load+inflate %.2fs, grouping %.2fs, batch fill %.2fs, device align+finalize %.2fs (align %.2fs, finalize %.2fs), rows+gzip+write %.2fs (fill and rows overlap the device stage), total %.2fs\n", stream.size(), n_groups, t_load, t_group, t_fill, t_gpu, t_align, t_final, t_rows, now() - t_start);
   cleanup();
   return rc;
 }
@@ -505,7 +548,7 @@ extern "C" int nb_bam_dump_groups(const char* input_file, int force_bam_paired, 
   if (!input_file || !out_path) return fail(NB_ERR_INVALID, "null argument");
   Bgzf z; int rc = z.load(input_file, std::max(1, num_cores)); if (rc) return rc;
   std::vector<Rec> stream; std::vector<u64> gstart;
-  rc = collect_groups(z, force_bam_paired != 0, stream, gstart); if (rc) return rc;
+  rc = collect_groups(z, force_bam_paired != 0, std::max(1, num_cores), stream, gstart); if (rc) return rc;
   FILE* f = fopen(out_path, "wb"); if (!f) return fail(NB_ERR_IO, std::string("could not open ") + out_path);
   auto hex = [](const std::string& s) { static const char* H = "0123456789abcdef"; std::string o; for (unsigned char c : s) { o += H[c >> 4]; o += H[c & 15]; } return o; };
   for (size_t gi = 0; gi + 1 < gstart.size(); gi++) {
