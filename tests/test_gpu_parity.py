@@ -324,6 +324,50 @@ def test_left_extension_and_reseed_paths_are_exercised(c2_built):
     assert w["probes"] > 4000 and w["nodes"] > 4000
 
 
+def test_long_reads_multi_round_seed_search(c2_built):
+    """Reads of 300-1000 bases: the cooperative seed search needs several 64-seed rounds (first hit in round 2, 3, ...;
+    off-target reads exhaust up to 6 rounds), the walk crosses a whole transcript, long junk prefixes trigger the left
+    extension late.  Results and probe counts (= the sequential search's) must match the oracle."""
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, _ = built[""]
+    seqs = L.sequences()
+    rng = np.random.default_rng(23)
+    rnd = lambda n: "".join("ACGT"[int(x)] for x in rng.integers(0, 4, size=n))
+    reads = []
+    for i in range(600):
+        t = seqs[int(rng.integers(len(seqs)))]
+        kind = i % 6
+        if kind == 0:   # off-target, every seed of every round misses
+            reads.append(rnd(int(rng.integers(300, 1001))))
+        elif kind == 1:   # junk prefix: the first hit is at seed index prefix/3 (rounds 2..5), then the left extension
+            pre = int(rng.integers(200, 700)); seg = int(rng.integers(60, 300)); s0 = int(rng.integers(0, len(t) - seg))
+            reads.append((rnd(pre) + t[s0:s0 + seg])[:1024])
+        elif kind == 2:   # on-target, one error every 25 bases over the first 250-600 bases: no clean 30-mer until then
+            n = int(rng.integers(700, min(1000, len(t)))); r = list(t[:n]); stop = int(rng.integers(250, 600))
+            for pos in range(int(rng.integers(0, 25)), stop, 25):
+                r[pos] = "ACGT"[("ACGT".index(r[pos]) + 1 + int(rng.integers(3))) % 4]
+            reads.append("".join(r))
+        elif kind == 3:   # clean long read (walks hundreds of bases, many unitigs)
+            n = int(rng.integers(300, min(1024, len(t)))); s0 = int(rng.integers(0, len(t) - n + 1)); reads.append(t[s0:s0 + n])
+        elif kind == 4:   # chimera of two transcripts with junk in between (re-seed far into the read)
+            u = seqs[int(rng.integers(len(seqs)))]; reads.append((t[50:250] + rnd(int(rng.integers(100, 300))) + u[100:400])[:1024])
+        else:             # ordinary 150 bp read next to the long ones (ragged batch)
+            s0 = int(rng.integers(0, len(t) - 150)); reads.append(t[s0:s0 + 150])
+    assert max(len(r) for r in reads) > 900
+    r1, o1 = orc.pack_reads(reads)
+    r2, o2 = orc.pack_reads(reads[::-1])
+    ctx = nb.Context(ix, lib, count_work=1)
+    for mm in (0, 2):
+        cfg = dict(ocfg, num_mismatches=mm)
+        o.set_config(**cfg)
+        res, ref = compare(ctx, o, cfg, r1, o1)
+        w = ctx.work_counters()
+        for k in ("probes", "nodes", "bases"):
+            assert w[k] == ref["work"][k], (mm, k, w[k], ref["work"][k])
+        compare(ctx, o, cfg, r1, o1, r2, o2)
+    assert w["probes"] > 100 * 64     # the multi-round searches really ran
+
+
 def test_work_counters_match_oracle(c2_built):
     L, built = c2_built
     ocfg, oref, lib, ix, o, _ = built[""]
