@@ -137,7 +137,7 @@ def _ck(rc):
 
 
 def _strs(strs):
-    arr = (C.c_char_p * len(strs))(*[s.encode("utf-8") for s in strs])
+    arr = (C.c_char_p * len(strs))(*[str(s).encode("utf-8") for s in strs])
     return arr
 
 

@@ -4,8 +4,12 @@
 #include <zlib.h>
 
 #include <cstdio>
+#include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host.hpp"
@@ -14,32 +18,73 @@ using namespace nb;
 
 namespace {
 
+// One FASTQ(.gz) stream parsed in place: lines are views into the read buffer (a partial line at the end of the buffer
+// is moved to the front before the next gzread), no per-line strings.
 struct FastqReader {
   gzFile f = nullptr; std::string path; std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
-  bool open(const std::string& p) { path = p; f = gzopen(p.c_str(), "rb"); if (!f) return false; gzbuffer(f, 1 << 20); buf.resize(1 << 22); return true; }
+  bool open(const std::string& p) { path = p; f = gzopen(p.c_str(), "rb"); if (!f) return false; gzbuffer(f, 1 << 20); buf.resize(1 << 23); return true; }
   ~FastqReader() { if (f) gzclose(f); }
-  bool fill() { if (eof) return false; int n = gzread(f, buf.data(), (unsigned)buf.size()); if (n <= 0) { eof = true; return false; } pos = 0; len = (size_t)n; return true; }
-  // reads one line without the terminator; false at end of input
-  bool line(std::string& out) {
-    out.clear(); bool any = false;
+  // one line without its terminator as a view into buf; false at end of input; a line longer than the buffer grows it
+  bool line(const char*& out, size_t& n) {
     for (;;) {
-      if (pos >= len && !fill()) return any;
-      any = true;
-      const char* s = buf.data() + pos; const char* nl = (const char*)memchr(s, '\n', len - pos);
-      if (nl) { out.append(s, nl - s); pos += (nl - s) + 1; if (!out.empty() && out.back() == '\r') out.pop_back(); return true; }
-      out.append(s, len - pos); pos = len;
+      const char* s = buf.data() + pos; const char* nl = len > pos ? (const char*)memchr(s, '\n', len - pos) : nullptr;
+      if (nl) { out = s; n = (size_t)(nl - s); pos += n + 1; if (n && out[n - 1] == '\r') n--; return true; }
+      if (eof) { if (pos >= len) return false; out = s; n = len - pos; pos = len; if (n && out[n - 1] == '\r') n--; return true; }
+      if (pos) { memmove(buf.data(), buf.data() + pos, len - pos); len -= pos; pos = 0; }
+      if (len == buf.size()) buf.resize(buf.size() * 2);
+      int got = gzread(f, buf.data() + len, (unsigned)std::min<size_t>(buf.size() - len, 1u << 30));
+      if (got <= 0) eof = true; else len += (size_t)got;
     }
   }
-  // 1 record, 0 end of file, -1 malformed
-  int next(std::string& seq, std::string& qual, std::string& tmp) {
-    do { if (!line(tmp)) return 0; } while (tmp.empty());
-    if (tmp[0] != '@') return -1;
-    seq.clear(); qual.clear();
-    for (;;) { if (!line(tmp)) return -1; if (!tmp.empty() && tmp[0] == '+') break; seq += tmp; }
-    while (qual.size() < seq.size()) { if (!line(tmp)) return -1; qual += tmp; }
-    if (qual.size() != seq.size()) return -1;
-    return 1;
+};
+
+struct Pinned {
+  u8* p = nullptr; size_t cap = 0;
+  ~Pinned() { nb_host_free(p); }
+  bool ensure(size_t n, size_t keep) { if (n <= cap) return true; size_t nc = std::max(n, cap * 2 + (1 << 20)); u8* q = (u8*)nb_host_alloc(nc); if (!q) return false; if (keep) memcpy(q, p, keep); nb_host_free(p); p = q; cap = nc; return true; }
+};
+
+// up to `want` records of one stream, bases concatenated in pinned memory
+struct Block { Pinned seq; std::vector<u64> off; u64 n = 0; u32 maxlen = 0; size_t used = 0; int status = 1; };   // status: 1 more may follow, 0 end of file, -1 malformed, -2 out of pinned memory
+
+// fills b from r; multi-line records are accepted like bio::io::fastq does
+void parse_block(FastqReader& r, Block& b, u64 want) {
+  b.n = 0; b.maxlen = 0; b.used = 0; b.status = 1; b.off.assign(1, 0);
+  const char* s; size_t n;
+  while (b.n < want) {
+    do { if (!r.line(s, n)) { b.status = 0; return; } } while (n == 0);
+    if (s[0] != '@') { b.status = -1; return; }
+    size_t start = b.used;
+    for (;;) {
+      if (!r.line(s, n)) { b.status = -1; return; }
+      if (n && s[0] == '+') break;
+      if (!b.seq.ensure(b.used + n + 64, b.used)) { b.status = -2; return; }
+      memcpy(b.seq.p + b.used, s, n); b.used += n;
+    }
+    size_t slen = b.used - start, qlen = 0;
+    while (qlen < slen) { if (!r.line(s, n)) { b.status = -1; return; } qlen += n; }
+    if (qlen != slen) { b.status = -1; return; }
+    b.off.push_back(b.used); b.maxlen = std::max<u32>(b.maxlen, (u32)slen); b.n++;
   }
+}
+
+// a reader thread per input file: blocks circulate between `free` and `filled`
+struct Feeder {
+  FastqReader rd; Block blocks[3]; std::vector<Block*> free_q, filled_q; std::mutex m; std::condition_variable cv; bool stop = false; std::thread th; u64 want;
+  void run() {
+    for (;;) {
+      Block* b;
+      { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return stop || !free_q.empty(); }); if (stop) return; b = free_q.back(); free_q.pop_back(); }
+      parse_block(rd, *b, want);
+      { std::lock_guard<std::mutex> lk(m); filled_q.push_back(b); }
+      cv.notify_all();
+      if (b->status != 1) return;
+    }
+  }
+  void start(u64 w) { want = w; for (auto& b : blocks) free_q.push_back(&b); th = std::thread([this] { run(); }); }
+  Block* pop() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return !filled_q.empty(); }); Block* b = filled_q.front(); filled_q.erase(filled_q.begin()); return b; }
+  void recycle(Block* b) { { std::lock_guard<std::mutex> lk(m); free_q.push_back(b); } cv.notify_all(); }
+  void finish() { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); }
 };
 
 int write_tsv(const std::string& path, const nb_library* lib, const nb_counts& cts) {  // utils::write_to_tsv
@@ -55,12 +100,6 @@ int write_tsv(const std::string& path, const nb_library* lib, const nb_counts& c
   fclose(f);
   return NB_OK;
 }
-
-struct Pinned {
-  u8* p = nullptr; size_t cap = 0;
-  ~Pinned() { nb_host_free(p); }
-  bool ensure(size_t n, size_t keep) { if (n <= cap) return true; size_t nc = std::max(n, cap * 2 + (1 << 20)); u8* q = (u8*)nb_host_alloc(nc); if (!q) return false; if (keep) memcpy(q, p, keep); nb_host_free(p); p = q; cap = nc; return true; }
-};
 
 }  // namespace
 
@@ -80,39 +119,31 @@ extern "C" int nb_process_fastq(const char* const* input_files, uint32_t n_input
     if (rc == NB_OK) rc = nb_index_build(lib, num_cores, &ix);
     if (rc == NB_OK) rc = nb_ctx_create(ix, lib, device, nullptr, &ctx);
     if (rc == NB_OK) rc = nb_ctx_set_option(ctx, "max_batch_pairs", BATCH);
-    FastqReader r1, r2; bool paired = n_inputs > 1;
-    if (rc == NB_OK && !r1.open(input_files[0])) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[0]);
-    if (rc == NB_OK && paired && !r2.open(input_files[1])) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[1]);
-    // two pinned buffer sets: the library may still be copying set i while set i^1 is filled
-    Pinned seq[2][2]; std::vector<u64> off[2][2];
-    std::string s, q, tmp; int cur = 0; bool done = false;
-    while (rc == NB_OK && !done) {
-      size_t used[2] = {0, 0}; u64 n = 0; u32 maxlen = 0;
-      off[cur][0].assign(1, 0); off[cur][1].assign(1, 0);
-      while (n < BATCH) {
-        int g = r1.next(s, q, tmp);
-        if (g == 0) { done = true; if (paired && r2.next(s, q, tmp) == 1) rc = fail(NB_ERR_PARSE, "Error -- read and reverse read files do not have matching lengths: "); break; }
-        if (g < 0) { rc = fail(NB_ERR_PARSE, "Error -- could not parse read. Input R1 data malformed."); break; }
-        if (!seq[cur][0].ensure(used[0] + s.size(), used[0])) { rc = fail(NB_ERR_CUDA, "pinned allocation failed"); break; }
-        memcpy(seq[cur][0].p + used[0], s.data(), s.size()); used[0] += s.size(); off[cur][0].push_back(used[0]); maxlen = std::max<u32>(maxlen, (u32)s.size());
-        if (paired) {
-          g = r2.next(s, q, tmp);
-          if (g == 0) { rc = fail(NB_ERR_PARSE, "Error -- read and reverse read files do not have matching lengths: "); break; }
-          if (g < 0) { rc = fail(NB_ERR_PARSE, "Error -- could not parse reverse read. Input R2 data malformed."); break; }
-          if (!seq[cur][1].ensure(used[1] + s.size(), used[1])) { rc = fail(NB_ERR_CUDA, "pinned allocation failed"); break; }
-          memcpy(seq[cur][1].p + used[1], s.data(), s.size()); used[1] += s.size(); off[cur][1].push_back(used[1]); maxlen = std::max<u32>(maxlen, (u32)s.size());
-        }
-        n++;
+    // one reader thread per input file parses blocks of BATCH records into pinned memory while the device works
+    Feeder fd[2]; bool paired = n_inputs > 1;
+    if (rc == NB_OK && !fd[0].rd.open(input_files[0])) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[0]);
+    if (rc == NB_OK && paired && !fd[1].rd.open(input_files[1])) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[1]);
+    if (rc == NB_OK) { fd[0].start(BATCH); if (paired) fd[1].start(BATCH); }
+    while (rc == NB_OK) {
+      Block* a = fd[0].pop(); Block* b2 = paired ? fd[1].pop() : nullptr;
+      if (a->status == -2 || (b2 && b2->status == -2)) rc = fail(NB_ERR_CUDA, "pinned allocation failed");
+      else if (a->status == -1) rc = fail(NB_ERR_PARSE, "Error -- could not parse read. Input R1 data malformed.");
+      else if (b2 && b2->status == -1) rc = fail(NB_ERR_PARSE, "Error -- could not parse reverse read. Input R2 data malformed.");
+      else if (b2 && (a->n != b2->n || a->status != b2->status)) rc = fail(NB_ERR_PARSE, "Error -- read and reverse read files do not have matching lengths: ");
+      if (rc != NB_OK) break;
+      if (a->n) {
+        nb_batch b; memset(&b, 0, sizeof b);
+        b.n_pairs = a->n; b.location = NB_MEM_HOST; b.max_read_len = std::max<u32>(a->maxlen, b2 ? b2->maxlen : 0);
+        b.r1 = a->seq.p; b.r1_off = a->off.data();
+        if (b2) { b.r2 = b2->seq.p; b.r2_off = b2->off.data(); }
+        rc = nb_align_batch(ctx, &b, nullptr, nullptr);
+        if (rc == NB_OK) rc = nb_ctx_sync(ctx);   // the copies out of these blocks are done: they can be refilled (a batch is ~5 ms on the device, ~100 ms to parse)
       }
-      if (rc != NB_OK || n == 0) break;
-      nb_batch b; memset(&b, 0, sizeof b);
-      b.n_pairs = n; b.location = NB_MEM_HOST; b.max_read_len = maxlen;
-      b.r1 = seq[cur][0].p; b.r1_off = off[cur][0].data();
-      if (paired) { b.r2 = seq[cur][1].p; b.r2_off = off[cur][1].data(); }
-      rc = nb_align_batch(ctx, &b, nullptr, nullptr);
-      cur ^= 1;
-      if (rc == NB_OK && cur == 0) rc = nb_ctx_sync(ctx);   // both sets in flight: wait before refilling set 0
+      bool last = a->status == 0;
+      fd[0].recycle(a); if (b2) fd[1].recycle(b2);
+      if (last) break;
     }
+    fd[0].finish(); if (paired) fd[1].finish();
     nb_counts cts;
     if (rc == NB_OK) rc = nb_counts_finalize(ctx, &cts);
     if (rc == NB_OK) rc = write_tsv(output_paths[li], lib, cts);

@@ -33,6 +33,8 @@ def lib():
         L.synth_umi_sizes.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.synth_umi_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.synth_write_fastq.restype = C.c_uint64
+        L.synth_write_fastq.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.synth_write_bam.restype = C.c_uint64
         L.synth_write_bam.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int]
         _lib = L
@@ -108,6 +110,14 @@ def write_umi_bam(path, u, L=91, first_scope=0, level=1, threads=8):
     """Writes the records of `umi_reads` as a 10x-style unaligned BAM (threaded BGZF).  Returns the file size."""
     n = lib().synth_write_bam(str(path).encode(), u["n_reads"], L, u["bases"].ctypes.data, u["qual"].ctypes.data, u["cell"].ctypes.data, u["scope"].ctypes.data,
                               first_scope, level, threads)
+    if not n:
+        raise IOError("could not write %s" % path)
+    return int(n)
+
+
+def write_fastq(path, r, off, mate=1, level=1):
+    """FASTQ (gzip when the path ends in .gz) of the reads of `pairs`.  Returns the uncompressed size."""
+    n = lib().synth_write_fastq(str(path).encode(), len(off) - 1, r.ctypes.data, off.ctypes.data, mate, level)
     if not n:
         raise IOError("could not write %s" % path)
     return int(n)

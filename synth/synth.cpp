@@ -154,4 +154,22 @@ u64 synth_write_bam(const char* path, u64 n_reads, u32 L, const char* bases, con
   u64 tot = 0; for (auto& c : comp) { if (fwrite(c.data(), 1, c.size(), f) != c.size()) { fclose(f); return 0; } tot += c.size(); }
   fclose(f); return tot;
 }
+
+// FASTQ (plain, or gzip when the path ends in .gz) of reads r[off[i]..off[i+1]); names @r<i>/<mate>, quality 'I'.
+u64 synth_write_fastq(const char* path, u64 n, const char* r, const u64* off, int mate, int level) {
+  size_t pl = strlen(path); bool gz = pl > 3 && !strcmp(path + pl - 3, ".gz");
+  std::string buf; buf.reserve(1 << 24); u64 tot = 0;
+  FILE* f = nullptr; gzFile g = nullptr;
+  if (gz) { char mode[8]; snprintf(mode, sizeof mode, "wb%d", level); g = gzopen(path, mode); if (!g) return 0; } else { f = fopen(path, "wb"); if (!f) return 0; }
+  auto flush = [&]() { if (gz) gzwrite(g, buf.data(), (unsigned)buf.size()); else fwrite(buf.data(), 1, buf.size(), f); tot += buf.size(); buf.clear(); };
+  char name[48];
+  for (u64 i = 0; i < n; i++) {
+    int ln = snprintf(name, sizeof name, "@r%llu/%d\n", (unsigned long long)i, mate); buf.append(name, ln);
+    u64 a = off[i], b = off[i + 1]; buf.append(r + a, b - a); buf.append("\n+\n"); buf.append(b - a, 'I'); buf.push_back('\n');
+    if (buf.size() > (1u << 23)) flush();
+  }
+  flush();
+  if (gz) gzclose(g); else fclose(f);
+  return tot;
+}
 }

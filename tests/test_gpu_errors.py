@@ -96,3 +96,32 @@ def test_state_machine_misuse_is_rejected(small):
     ctx.align_batch(r1, o1, r2, o2)
     a = ctx.counts()["rows"]
     assert ctx.counts()["rows"] == a   # finalize is idempotent
+
+
+def test_fastq_driver_input_errors(tmp_path, small):
+    """process::fastq::process panics on malformed / unequal inputs (src/process/fastq.rs:20-24, src/parse/fastq.rs:30-33):
+    here a negative status and no TSV.  Also multi-line records, CRLF, blank lines and a missing final newline parse."""
+    L, lib, ix, _ = small
+    libp = tmp_path / "lib.json"
+    libp.write_text(json.dumps(L.to_json_obj()))
+    seqs = L.sequences()
+    rec = lambda i, s: "@r%d\n%s\n+\n%s\n" % (i, s, "I" * len(s))
+    good = "".join(rec(i, seqs[i % len(seqs)][10:160]) for i in range(50))
+    (tmp_path / "a.fastq").write_text(good)
+    (tmp_path / "short.fastq").write_text("".join(rec(i, seqs[i % len(seqs)][10:160]) for i in range(49)))
+    (tmp_path / "bad.fastq").write_text(good[:-40] + "garbage\n")
+    (tmp_path / "noat.fastq").write_text(good.replace("@r7\n", "r7\n"))
+    out = tmp_path / "o.tsv"
+    for r2 in ("short.fastq", "bad.fastq", "noat.fastq"):
+        with pytest.raises(nb.NbError) as e:
+            nb.process_fastq([tmp_path / "a.fastq", tmp_path / r2], [libp], [out])
+        assert e.value.code == -3 and not out.exists()
+    with pytest.raises(nb.NbError):
+        nb.process_fastq([tmp_path / "missing.fastq"], [libp], [out])
+    # tolerant parsing: sequence split over two lines, CRLF, blank line between records, no newline at the very end
+    s0, s1 = seqs[3][20:170], seqs[4][5:155]
+    (tmp_path / "odd.fastq").write_text("@x\r\n%s\r\n%s\r\n+\r\n%s\r\n%s\r\n\n@y\n%s\n+y\n%s" % (s0[:70], s0[70:], "I" * 70, "I" * 80, s1, "I" * 150))
+    (tmp_path / "plain.fastq").write_text(rec(0, s0) + rec(1, s1))
+    nb.process_fastq([tmp_path / "odd.fastq"], [libp], [tmp_path / "odd.tsv"])
+    nb.process_fastq([tmp_path / "plain.fastq"], [libp], [tmp_path / "plain.tsv"])
+    assert (tmp_path / "odd.tsv").read_text() == (tmp_path / "plain.tsv").read_text() and len((tmp_path / "odd.tsv").read_text().splitlines()) >= 2
