@@ -1,6 +1,7 @@
 // engine.cu — execution context behind the C ABI: device copies of the index / library tables, per-batch staging,
 // the K0..K4 launch sequence on one CUDA stream, and result read-back.  No CPU fallback: every entry point fails
 // with NB_ERR_CUDA when the device cannot be used.
+#include <time.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -404,8 +405,12 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   if (!c->tables_ready) { out->callset_off = c->cs_off.data(); return NB_OK; }
   cudaStream_t s = c->stream;
   Tables t = make_tables(c);
+  static const bool fstats = getenv("NB_FINALIZE_STATS") != nullptr; double ft[5] = {0, 0, 0, 0, 0};
+  auto fnow = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+  if (fstats) { cudaStreamSynchronize(s); ft[0] = fnow(); }
   if (c->mode == 0 && !c->folded) { nbk::launch_fold(t, nullptr, 0, s); c->all_launches++; c->folded = true; }
   Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
+  if (fstats) ft[1] = fnow();
   c->last_unique = h.n_keys;
   // compact the occupied entries of the (cell, callset) table and of the callset dictionary on the device, then read
   // back only those: rows of {key, count} and of {slot, len, items[gcap]}
@@ -418,19 +423,21 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   if (n_agg) CK(cudaMemcpyAsync(agg.data(), d_agg, n_agg * 16, cudaMemcpyDeviceToHost, s));
   if (n_cs) CK(cudaMemcpyAsync(csr.data(), d_cs, n_cs * (size_t)cw * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  if (fstats) ft[2] = fnow();
   // callsets sorted by Vec<String> Ord (utils::sort_score_vector, src/utils.rs:54-59): bytewise on the group names
-  const std::vector<std::string>& gn = c->lib->group_names;
+  const std::vector<u32>& gr = c->lib->group_byte_rank;   // compare ranks, not strings: this sort runs once per job over every callset
   std::vector<u32> slots(n_cs); for (u32 i = 0; i < n_cs; i++) slots[i] = i;   // indices into the compact rows
   auto cs_less = [&](u32 a, u32 b) {
     const u32* ra = &csr[(size_t)a * cw]; const u32* rb = &csr[(size_t)b * cw];
     u32 la = ra[1], lb = rb[1];
-    for (u32 i = 0; i < std::min(la, lb); i++) { u32 ga = ra[4 + i], gb = rb[4 + i]; if (ga != gb) { int cmp = gn[ga].compare(gn[gb]); if (cmp) return cmp < 0; } }
+    for (u32 i = 0; i < std::min(la, lb); i++) { u32 ga = ra[4 + i], gb = rb[4 + i]; if (ga != gb) return gr[ga] < gr[gb]; }
     if (la != lb) return la < lb;
     return ra[0] < rb[0];
   };
   std::sort(slots.begin(), slots.end(), cs_less);
   std::vector<u32>& dense = c->slot_dense; dense.assign(c->cs_slots, NONE32);
   for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[4 + k]); c->cs_off.push_back(c->cs_items.size()); }
+  if (fstats) ft[3] = fnow();
   // rows ordered by (cell, callset): LSD radix sort on the 56-bit key (the table can hold millions of (cell, callset) rows)
   std::vector<u64> key(n_agg), key2(n_agg); std::vector<i64> val(n_agg), val2(n_agg);
   for (u64 i = 0; i < n_agg; i++) { u64 k = agg[2 * i] - 1; key[i] = ((k >> 24) << 24) | dense[(u32)(k & 0xFFFFFF)]; val[i] = (i64)agg[2 * i + 1]; }
@@ -450,6 +457,7 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   out->n_rows = rows.size(); out->row_scope = c->row_scope.data(); out->row_callset = c->row_callset.data(); out->row_count = c->row_count.data();
   out->n_callsets = slots.size(); out->callset_off = c->cs_off.data(); out->callset_items = c->cs_items.data();
   out->n_pairs_seen = c->pairs_seen; out->n_unique_keys = h.n_keys; out->n_slots = c->cs_slots; out->slot_to_callset = c->slot_dense.data();
+  if (fstats) { ft[4] = fnow(); fprintf(stderr, "finalize: fold+counters %.3f ms, compact+D2H %.3f ms, callset sort %.3f ms, rows %.3f ms (%llu rows, %llu callsets, key slots %llu)\n", (ft[1] - ft[0]) * 1e3, (ft[2] - ft[1]) * 1e3, (ft[3] - ft[2]) * 1e3, (ft[4] - ft[3]) * 1e3, (unsigned long long)n_agg, (unsigned long long)n_cs, (unsigned long long)c->key_slots); }
   return NB_OK;
 }
 

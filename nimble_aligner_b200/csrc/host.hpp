@@ -54,6 +54,7 @@ struct nb_library {
   std::vector<u32> row_of;           // [2*fid + rev] -> row or NONE32
   std::vector<u32> feat_group;       // fid -> group rank of unmap(feature) row, NONE32 when unmap would panic
   std::vector<std::string> group_names;  // rank -> string; ranks follow natural_lexical_cmp
+  std::vector<u32> group_byte_rank;      // rank -> position of that string in plain byte order (distinct strings: no ties)
   void finalize();
   u32 n_rows() const { return columns.empty() ? 0 : (u32)columns[0].size(); }
 };

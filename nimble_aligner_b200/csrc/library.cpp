@@ -278,6 +278,11 @@ void nb_library::finalize() {
   for (auto& kv : distinct) group_names.push_back(kv.first);
   std::sort(group_names.begin(), group_names.end(), [](const std::string& a, const std::string& b) { return natural_lexical_cmp(a, b) < 0; });
   for (u32 i = 0; i < group_names.size(); i++) distinct[group_names[i]] = i;
+  {  // rank of every group name in plain byte order (Vec<String> Ord, utils::sort_score_vector): callsets sort on integers
+    std::vector<u32> ord(group_names.size()); for (u32 i = 0; i < ord.size(); i++) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](u32 a, u32 b) { return group_names[a] < group_names[b]; });
+    group_byte_rank.assign(group_names.size(), 0); for (u32 i = 0; i < ord.size(); i++) group_byte_rank[ord[i]] = i;
+  }
   feat_group.assign(n_features, NONE32);
   for (u32 f = 0; f < n_features; f++) if (has[f]) feat_group[f] = distinct[gs[f]];
   derived = true;
