@@ -97,12 +97,14 @@ __global__ void __launch_bounds__(256) k_trim(BatchDev b, Tables t) {
 struct ReadView {   // one packed read: W words, zero padded; either global (read-major, stride 1) or a shared-memory column (stride 32)
   const u64* p; u32 stride;
   __device__ __forceinline__ u64 word(u32 w) const { return p[(size_t)w * stride]; }
+  // 32 bases from base `pos` on.  (Three 32-bit loads + two funnel shifts instead of two 64-bit loads + 64-bit shifts
+  // were measured: fewer ALU instructions, one more load per window, +4 % map time — the load/store unit is the scarcer resource.)
   __device__ __forceinline__ u64 win(u32 pos) const {
     u32 w = pos >> 5, sh = (pos & 31) * 2; u64 lo = word(w);
     if (!sh) return lo;
     return (lo >> sh) | (word(w + 1) << (64 - sh));
   }
-  __device__ __forceinline__ u32 base(u32 pos) const { return (u32)(word(pos >> 5) >> ((pos & 31) * 2)) & 3u; }
+  __device__ __forceinline__ u32 base(u32 pos) const { return (((const u32*)p)[pos >> 4] >> ((pos & 15) * 2)) & 3u; }
 };
 __device__ __forceinline__ u64 uwin(const u64* U, u64 pos) {
   u64 w = pos >> 5; u32 sh = (u32)(pos & 31) * 2; u64 lo = __ldg(U + w);
@@ -183,15 +185,18 @@ struct EcAcc {
 
 // forward compare of m bases: unitig [upos, upos+m) vs read [rpos, rpos+m); the (allowed+1)-th mismatch trips the
 // per-node budget: it is counted in snp (-> mismatches) but not in mb (-> coverage)   [App. B]
-__device__ __forceinline__ void cmp_fwd(const u64* U, u64 upos, const ReadView& rd, u32 rpos, u32 m, u32 allowed, u32& mb, u32& snp, bool& brk) {
-  mb = 0; snp = 0; brk = false;
+// `next`: the read base right after the compared stretch (position rpos + m) when the compare ran to its end and that
+// base sits inside the last 32-base window that was loaded anyway; 4 = not available (caller loads it).
+__device__ __forceinline__ void cmp_fwd(const u64* U, u64 upos, const ReadView& rd, u32 rpos, u32 m, u32 allowed, u32& mb, u32& snp, bool& brk, u32& next) {
+  mb = 0; snp = 0; brk = false; next = 4;
   while (mb < m) {
     u32 c = min(32u, m - mb);
-    u64 x = uwin(U, upos + mb) ^ rd.win(rpos + mb);
+    u64 rw = rd.win(rpos + mb);
+    u64 x = uwin(U, upos + mb) ^ rw;
     u64 d = (x | (x >> 1)) & 0x5555555555555555ULL;
     if (c < 32) d &= (1ULL << (2 * c)) - 1;
     u32 cnt = (u32)__popcll(d);
-    if (snp + cnt <= allowed) { snp += cnt; mb += c; continue; }
+    if (snp + cnt <= allowed) { snp += cnt; mb += c; if (c < 32) next = (u32)(rw >> (2 * c)) & 3u; continue; }
     u32 need = allowed - snp;
     for (u32 i = 0; i < need; i++) d &= d - 1;
     mb += (u32)(__ffsll((long long)d) - 1) >> 1;

@@ -276,12 +276,12 @@ __global__ void __launch_bounds__(128, NB_WALK_MINB) k_walk(BatchDev b, DevIndex
       uint4 nd = __ldg(ix.node + node);
       u64 start = (u64)nd.x | ((u64)(nd.w >> 8) << 32);
       kp += K; cov += K; acc.add(nd.z, wc); wc.nodes++;
-      u32 ro = off + K, m = min(n - kp, nd.y - ro), mb, snp; bool brk;
-      cmp_fwd(ix.unitig, start + ro, rd, kp, m, allowed, mb, snp, brk);
+      u32 ro = off + K, m = min(n - kp, nd.y - ro), mb, snp, nxb; bool brk;
+      cmp_fwd(ix.unitig, start + ro, rd, kp, m, allowed, mb, snp, brk, nxb);
       mm += snp; cov += mb; kp += mb; wc.bases += mb + (brk ? 1 : 0);
       if (kp >= n) st = ST_DONE;
       else {
-        u32 bs = rd.base(kp);
+        u32 bs = (!brk && nxb < 4) ? nxb : rd.base(kp);   // usually already in the compare's last window: one load less per unitig
         if (!brk && ((nd.w >> (4 + bs)) & 1)) { node = __ldg(redge + 4 * (u64)node + bs); off = 0; kp -= K - 1; cov -= K - 1; }
         else st = kp > last_kpos ? ST_DONE : ST_SEED;
       }
