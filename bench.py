@@ -131,83 +131,6 @@ def run_reference(args):
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
-_MERGE = {}   # buffers reused across steps (allocation is not part of the job)
-
-
-def merge_across_ranks(ctx, nb, torch, dist, rank, world, pair_base, max_pairs):
-    """Whole-run de-duplication across GPUs.  Local: callset dictionary rows and the key records grouped
-    by owning rank (device scatter).  Then four collectives: (1) all_gather of the per-rank sizes, (2) all_gather of the
-    callset rows so dictionary ids agree, (3) one all_to_all of the key records over NVLink, after which each rank
-    re-imports its key partition and folds it, (4) one all_reduce of the dense per-callset counts (+ unique keys)."""
-    import ctypes as C
-    L = nb.lib()
-    st = _MERGE
-    if not st:
-        nout, gcap = C.c_uint64(0), C.c_uint32(0)
-        nb._ck(L.nb_callsets_export(ctx.h, None, 0, C.byref(nout), C.byref(gcap)))
-        st["cw"] = 4 + gcap.value
-        st["rows"] = np.zeros((1 << 18, st["cw"]), dtype=np.uint32)          # callset_slots default: the dictionary cannot hold more
-        st["rec"] = torch.empty((max_pairs, 4), dtype=torch.int64, device="cuda")   # unique keys <= pairs aligned on this rank
-        st["out"] = torch.empty((max_pairs + max_pairs // 4, 4), dtype=torch.int64, device="cuda")
-    cw, rows, rec = st["cw"], st["rows"], st["rec"]
-    stats = os.environ.get("NB_MERGE_STATS") and rank == 0
-    marks = []
-    def mark(name):
-        if stats:
-            torch.cuda.synchronize(); marks.append((name, time.time()))
-    mark("start")
-    nout, gcap = C.c_uint64(0), C.c_uint32(0)
-    nb._ck(L.nb_callsets_export(ctx.h, rows.ctypes.data, rows.shape[0], C.byref(nout), C.byref(gcap)))
-    k = nout.value
-    mark("callsets_export")
-    cnt = np.zeros(world, dtype=np.uint64)
-    nb._ck(L.nb_keys_export_partitioned(ctx.h, rec.data_ptr(), rec.shape[0], pair_base, world, cnt.ctypes.data))
-    mark("keys_export_partitioned")
-    # (1) sizes
-    meta = torch.from_numpy(np.concatenate([[k], cnt.astype(np.int64)]).astype(np.int64)).cuda()
-    allmeta = torch.empty((world, 1 + world), dtype=torch.int64, device="cuda")
-    dist.all_gather_into_tensor(allmeta.view(-1), meta)
-    am = allmeta.cpu().numpy()
-    szs, recv_l, send_l = am[:, 0].tolist(), am[:, 1 + rank].tolist(), cnt.astype(np.int64).tolist()
-    mark("sizes_all_gather")
-    # (2) callset dictionaries
-    kmax = max(max(szs), 1)
-    mine = torch.zeros((kmax, cw), dtype=torch.int32, device="cuda")
-    if k:
-        mine[:k] = torch.from_numpy(rows[:k].view(np.int32)).cuda()
-    allrows = torch.empty((world, kmax, cw), dtype=torch.int32, device="cuda")
-    dist.all_gather_into_tensor(allrows.view(-1), mine.view(-1))
-    others = torch.cat([allrows[r, : int(szs[r])] for r in range(world) if r != rank and szs[r]] or [allrows[0, :0]]).cpu().numpy().view(np.uint32)
-    others = np.ascontiguousarray(others)
-    nb._ck(L.nb_callsets_import(ctx.h, others.ctypes.data, others.shape[0]))
-    mark("callsets_exchange_import")
-    # (3) key records by owner; re-import this rank's partition and fold it (same stream as the collective: ordered after it)
-    tot_recv, tot_send = int(sum(recv_l)), int(sum(send_l))
-    if tot_recv > st["out"].shape[0]:
-        st["out"] = torch.empty((tot_recv + tot_recv // 4, 4), dtype=torch.int64, device="cuda")
-    out = st["out"]
-    dist.all_to_all_single(out[:tot_recv], rec[:tot_send], output_split_sizes=recv_l, input_split_sizes=send_l)
-    mark("keys_all_to_all")
-    nb._ck(L.nb_keys_import(ctx.h, out.data_ptr(), tot_recv))
-    mark("keys_import")
-    raw = ctx.counts_raw()
-    mark("finalize")
-    # (4) dense all-reduce: after (2) every rank lists the same callsets in the same order; the last element carries the unique-key count
-    ncs = len(raw["callset_off"]) - 1
-    dense = torch.zeros(ncs + 1, dtype=torch.int64, device="cuda")
-    if len(raw["row_callset"]):
-        dense.index_add_(0, torch.from_numpy(raw["row_callset"].astype(np.int64)).cuda(), torch.from_numpy(raw["row_count"]).cuda())
-    dense[ncs] = int(raw["n_unique_keys"])
-    dist.all_reduce(dense)
-    hd = dense.cpu().numpy()
-    mark("dense_all_reduce")
-    if stats:
-        print("merge: " + ", ".join("%s %.2f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3) for i in range(1, len(marks))), file=sys.stderr)
-    raw = dict(raw)
-    raw["dense_counts"] = hd[:ncs]
-    return raw, int(hd[ncs])
-
-
 _JSON_OUT = None
 
 
@@ -279,11 +202,14 @@ def main():
     d1, d2, do1, do2 = h1.cuda(), h2.cuda(), ho1.cuda(), ho2.cuda()
     n_reads = 2 * n
 
+    from nimble_aligner_b200.multigpu import merge_across_ranks, DeviceShard
+    shard = DeviceShard(ctx, nb, torch, pair_base, n) if world > 1 else None   # merge buffers are allocated once, outside the job
+
     def step_device():
         ctx.reset()
         ctx.align_batch(d1, do1, d2, do2, n_pairs=n, max_read_len=READ_LEN, location=nb.NB_MEM_DEVICE)
         if world > 1:
-            return merge_across_ranks(ctx, nb, torch, dist, rank, world, pair_base, n)
+            return merge_across_ranks(shard, torch, dist, rank, world, "cuda")
         raw = ctx.counts_raw()          # nb_counts_finalize: the job's result (group indices + counts) on the host
         return raw, raw["n_unique_keys"]
 
@@ -294,7 +220,7 @@ def main():
         import ctypes as C
         nb._ck(nb.lib().nb_align_batch(ctx.h, C.byref(b), None, None))
         if world > 1:
-            return merge_across_ranks(ctx, nb, torch, dist, rank, world, pair_base, n)
+            return merge_across_ranks(shard, torch, dist, rank, world, "cuda")
         raw = ctx.counts_raw()          # nb_counts_finalize: the job's result (group indices + counts) on the host
         return raw, raw["n_unique_keys"]
 

@@ -1,0 +1,119 @@
+"""Host side of the multi-GPU whole-run merge: what a C++ host would do with NCCL between the C-ABI
+calls, written once against a small shard interface so that the same choreography runs over NCCL with device shards
+(bench.py) and over gloo with a host model of the tables (tests/test_multirank_cpu.py, world_size 2, no GPU).
+
+Reads shard over ranks; counts are over unique read_keys of the whole run (src/align.rs:576-579, 685), so key records
+must meet on one rank: every key has an owner (a slice of its 128-bit value mod world).  Four collectives:
+  (1) all_gather of the per-rank sizes (callset rows, key records per owner),
+  (2) all_gather of the callset dictionary rows, after which every rank holds the same dictionary,
+  (3) one all_to_all of the key records {key_lo, key_hi, global pair order, callset tag}; each rank re-imports its
+      partition with the "later duplicate wins" rule and folds it,
+  (4) one all_reduce of the dense per-callset counts (+ the unique-key count in the last element).
+
+A shard provides:
+  callsets_export() -> np.uint32 [k, cw] rows {slot, len, tag_lo, tag_hi, items[gcap]}
+  keys_export_partitioned(world) -> (records int64 [n, 4] on the shard's device, grouped by owner; counts per owner)
+  callsets_import(rows np.uint32 [m, cw]);  keys_import(records int64 [m, 4] on the device)
+  recv_buffer(n) -> int64 [>= n, 4] on the device;  finalize() -> dict(callset_off, row_callset, row_count, n_unique_keys, ...)
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+
+def merge_across_ranks(shard, torch, dist, rank, world, device):
+    stats = os.environ.get("NB_MERGE_STATS") and rank == 0
+    marks = []
+
+    def mark(name):
+        if stats:
+            if device != "cpu":
+                torch.cuda.synchronize()
+            marks.append((name, time.time()))
+    mark("start")
+    rows = shard.callsets_export()
+    k, cw = rows.shape
+    mark("callsets_export")
+    rec, cnt = shard.keys_export_partitioned(world)
+    mark("keys_export_partitioned")
+    # (1) sizes
+    meta = torch.from_numpy(np.concatenate([[k], np.asarray(cnt, dtype=np.int64)]).astype(np.int64)).to(device)
+    allmeta = torch.empty((world, 1 + world), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allmeta.view(-1), meta)
+    am = allmeta.cpu().numpy()
+    szs, recv_l, send_l = am[:, 0].tolist(), am[:, 1 + rank].tolist(), [int(x) for x in cnt]
+    mark("sizes_all_gather")
+    # (2) callset dictionaries
+    kmax = max(max(szs), 1)
+    mine = torch.zeros((kmax, cw), dtype=torch.int32, device=device)
+    if k:
+        mine[:k] = torch.from_numpy(np.ascontiguousarray(rows).view(np.int32)).to(device)
+    allrows = torch.empty((world, kmax, cw), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(allrows.view(-1), mine.view(-1))
+    others = torch.cat([allrows[r, : int(szs[r])] for r in range(world) if r != rank and szs[r]] or [allrows[0, :0]]).cpu().numpy().view(np.uint32)
+    shard.callsets_import(np.ascontiguousarray(others))
+    mark("callsets_exchange_import")
+    # (3) key records by owner; re-import this rank's partition and fold it (same stream as the collective: ordered after it)
+    tot_recv, tot_send = int(sum(recv_l)), int(sum(send_l))
+    out = shard.recv_buffer(tot_recv)
+    dist.all_to_all_single(out[:tot_recv], rec[:tot_send], output_split_sizes=recv_l, input_split_sizes=send_l)
+    mark("keys_all_to_all")
+    shard.keys_import(out[:tot_recv])
+    mark("keys_import")
+    raw = shard.finalize()
+    mark("finalize")
+    # (4) dense all-reduce: after (2) every rank lists the same callsets in the same order; the last element carries the unique-key count
+    ncs = len(raw["callset_off"]) - 1
+    dense = torch.zeros(ncs + 1, dtype=torch.int64, device=device)
+    if len(raw["row_callset"]):
+        dense.index_add_(0, torch.from_numpy(np.asarray(raw["row_callset"]).astype(np.int64)).to(device), torch.from_numpy(np.asarray(raw["row_count"], dtype=np.int64)).to(device))
+    dense[ncs] = int(raw["n_unique_keys"])
+    dist.all_reduce(dense)
+    hd = dense.cpu().numpy()
+    mark("dense_all_reduce")
+    if stats:
+        print("merge: " + ", ".join("%s %.2f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3) for i in range(1, len(marks))), file=sys.stderr)
+    raw = dict(raw)
+    raw["dense_counts"] = hd[:ncs]
+    return raw, int(hd[ncs])
+
+
+class DeviceShard:
+    """One GPU's tables behind the C ABI (nb_callsets_export / nb_keys_export_partitioned / nb_callsets_import /
+    nb_keys_import / nb_counts_finalize).  Buffers are allocated once: unique keys <= pairs aligned on this rank."""
+
+    def __init__(self, ctx, nb, torch, pair_base, max_pairs):
+        self.ctx, self.nb, self.torch, self.pair_base = ctx, nb, torch, pair_base
+        self.rows = None
+        self.rec = torch.empty((max_pairs, 4), dtype=torch.int64, device="cuda")
+        self.out = torch.empty((max_pairs + max_pairs // 4, 4), dtype=torch.int64, device="cuda")
+
+    def callsets_export(self):
+        nout, gcap = C.c_uint64(0), C.c_uint32(0)
+        if self.rows is None:   # row width is known once the tables exist (after the first batch)
+            self.nb._ck(self.nb.lib().nb_callsets_export(self.ctx.h, None, 0, C.byref(nout), C.byref(gcap)))
+            self.rows = np.zeros((1 << 18, 4 + gcap.value), dtype=np.uint32)          # callset_slots default: the dictionary cannot hold more
+        self.nb._ck(self.nb.lib().nb_callsets_export(self.ctx.h, self.rows.ctypes.data, self.rows.shape[0], C.byref(nout), C.byref(gcap)))
+        return self.rows[: nout.value]
+
+    def keys_export_partitioned(self, world):
+        cnt = np.zeros(world, dtype=np.uint64)
+        self.nb._ck(self.nb.lib().nb_keys_export_partitioned(self.ctx.h, self.rec.data_ptr(), self.rec.shape[0], self.pair_base, world, cnt.ctypes.data))
+        return self.rec, cnt.astype(np.int64).tolist()
+
+    def callsets_import(self, rows):
+        self.nb._ck(self.nb.lib().nb_callsets_import(self.ctx.h, rows.ctypes.data, rows.shape[0]))
+
+    def recv_buffer(self, n):
+        if n > self.out.shape[0]:
+            self.out = self.torch.empty((n + n // 4, 4), dtype=self.torch.int64, device="cuda")
+        return self.out
+
+    def keys_import(self, rec):
+        self.nb._ck(self.nb.lib().nb_keys_import(self.ctx.h, rec.data_ptr(), rec.shape[0]))
+
+    def finalize(self):
+        return self.ctx.counts_raw()
