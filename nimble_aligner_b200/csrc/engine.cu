@@ -426,7 +426,11 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   if (fstats) ft[2] = fnow();
   // callsets sorted by Vec<String> Ord (utils::sort_score_vector, src/utils.rs:54-59): bytewise on the group names
   const std::vector<u32>& gr = c->lib->group_byte_rank;   // compare ranks, not strings: this sort runs once per job over every callset
-  std::vector<u32> slots(n_cs); for (u32 i = 0; i < n_cs; i++) slots[i] = i;   // indices into the compact rows
+  // sort on a packed prefix (byte ranks of the first two groups) and fall back to the full rows only on ties: at C4 there
+  // are several hundred thousand callsets and this sort is the job's serial tail
+  struct SortKey { u64 k; u32 idx; };
+  std::vector<SortKey> sk(n_cs);
+  for (u32 i = 0; i < n_cs; i++) { const u32* r = &csr[(size_t)i * cw]; u64 a = r[1] > 0 ? (u64)gr[r[4]] + 1 : 0, b = r[1] > 1 ? (u64)gr[r[5]] + 1 : 0; sk[i] = {(a << 32) | b, i}; }
   auto cs_less = [&](u32 a, u32 b) {
     const u32* ra = &csr[(size_t)a * cw]; const u32* rb = &csr[(size_t)b * cw];
     u32 la = ra[1], lb = rb[1];
@@ -434,7 +438,8 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
     if (la != lb) return la < lb;
     return ra[0] < rb[0];
   };
-  std::sort(slots.begin(), slots.end(), cs_less);
+  std::sort(sk.begin(), sk.end(), [&](const SortKey& x, const SortKey& y) { return x.k != y.k ? x.k < y.k : cs_less(x.idx, y.idx); });
+  std::vector<u32> slots(n_cs); for (u32 i = 0; i < n_cs; i++) slots[i] = sk[i].idx;   // indices into the compact rows
   std::vector<u32>& dense = c->slot_dense; dense.assign(c->cs_slots, NONE32);
   for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[4 + k]); c->cs_off.push_back(c->cs_items.size()); }
   if (fstats) ft[3] = fnow();

@@ -49,7 +49,7 @@ def main():
         n = a.reads
         r1, o1, _, _ = synth.pairs(L, 0, n, seed=3456, paired=False, threads=cores)
         hb, ho = torch.from_numpy(r1).pin_memory(), torch.from_numpy(o1.astype(np.int64)).pin_memory()
-        ctx = nb.Context(ix, lib, stream=s.cuda_stream, max_batch_pairs=1 << 20)
+        ctx = nb.Context(ix, lib, stream=s.cuda_stream, max_batch_pairs=1 << 20, callset_slots=1 << 22, agg_slots=1 << 23)
         import ctypes as C
         def step():
             ctx.reset()
