@@ -63,7 +63,7 @@ struct nb_ctx {
   const nb_index* hix = nullptr; const nb_library* lib = nullptr;
   nb_config hcfg; DevCfg dcfg; DevIndex dix; DevLib dlib;
   // index + library device copies
-  DBuf d_tkey, d_tval, d_unitig, d_node, d_redge, d_ledge, d_coloff, d_colids, d_colmeta, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp, d_mincov;
+  DBuf d_tkey, d_tval, d_unitig, d_node, d_walk, d_ledge, d_coloff, d_colids, d_colmeta, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp, d_mincov;
   // options
   u64 max_batch_pairs = 1u << 20, arena_entries = 1u << 24, cs_slots = 1u << 18, key_slots = 1u << 22, agg_slots = 1u << 20;
   int count_work = 0; u32 min_read_len = 40;  // MIN_READ_LENGTH, src/align.rs:18 (tests pass 12, src/align.rs:1066)
@@ -173,7 +173,21 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   int rc = NB_OK;
   auto up = [&](cudaError_t e) { if (e != cudaSuccess && rc == NB_OK) rc = fail(NB_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e)); };
   up(upload(c->d_unitig, index->unitig, s)); up(upload(c->d_ledge, index->ledge, s));
-  up(upload(c->d_tkey, index->table_key, s)); up(upload(c->d_tval, index->table_val, s)); up(upload(c->d_node, index->node, s)); up(upload(c->d_redge, index->redge, s));
+  up(upload(c->d_tkey, index->table_key, s)); up(upload(c->d_tval, index->table_val, s)); up(upload(c->d_node, index->node, s));
+  {  // walk records (kernels.cuh DevIndex::walk), derived from the flat index arrays at upload time
+    size_t nn = index->node.size(); std::vector<u32> w(16 * nn);
+    auto base_at = [&](u64 pos) -> u64 { return (index->unitig[pos >> 5] >> (2 * (pos & 31))) & 3; };
+    for (size_t v = 0; v < nn; v++) {
+      const NodeRec& nr = index->node[v]; u32* o = &w[16 * v];
+      o[0] = nr.start_lo; o[1] = nr.len; o[2] = nr.colour; o[3] = nr.exts_hi;
+      memcpy(o + 4, &index->redge[4 * v], 16); memcpy(o + 8, &index->col_meta[4 * (size_t)nr.colour], 16);
+      u64 st = (u64)nr.start_lo | ((u64)(nr.exts_hi >> 8) << 32), q[2] = {0, 0};
+      for (u32 i = 0; i < std::min<u32>(nr.len, 64); i++) q[i >> 5] |= base_at(st + i) << (2 * (i & 31));
+      memcpy(o + 12, q, 16);
+    }
+    up(upload(c->d_walk, w, s));
+    if (rc == NB_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(NB_ERR_CUDA, "index upload failed");   // the staging vector dies here
+  }
   up(upload(c->d_coloff, index->col_off, s)); up(upload(c->d_colids, index->col_ids, s)); up(upload(c->d_colmeta, index->col_meta, s));
   up(upload(c->d_rowfid, lib->row_fid, s)); up(upload(c->d_rowrev, lib->row_rev, s)); up(upload(c->d_rowof, lib->row_of, s)); up(upload(c->d_featgroup, lib->feat_group, s));
   {  // entropy terms f*log2(f), f = c/n, for every read length n <= ENT_NMAX (src/utils.rs:96-119)
@@ -185,7 +199,7 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   if (rc == NB_OK) { cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) rc = fail(NB_ERR_CUDA, cudaGetErrorString(e)); }
   if (rc != NB_OK) { nb_ctx_free(c); return rc; }
   c->dix.n_buckets = (u32)index->table_buckets; c->dix.unitig = (const u64*)c->d_unitig.p; c->dix.ledge = (const uint4*)c->d_ledge.p;
-  c->dix.tkey = (const u64*)c->d_tkey.p; c->dix.tval = (const u64*)c->d_tval.p; c->dix.node = (const uint4*)c->d_node.p; c->dix.redge = (const uint4*)c->d_redge.p;
+  c->dix.tkey = (const u64*)c->d_tkey.p; c->dix.tval = (const u64*)c->d_tval.p; c->dix.node = (const uint4*)c->d_node.p; c->dix.walk = (const uint4*)c->d_walk.p;
   c->dix.col_off = (const u32*)c->d_coloff.p; c->dix.col_ids = (const u32*)c->d_colids.p; c->dix.col_meta = (const uint4*)c->d_colmeta.p;
   c->dlib.row_fid = (const u32*)c->d_rowfid.p; c->dlib.row_rev = (const u8*)c->d_rowrev.p; c->dlib.row_of = (const u32*)c->d_rowof.p; c->dlib.feat_group = (const u32*)c->d_featgroup.p; c->dlib.n_rows = lib->n_rows();
   rc = apply_config(c, lib->cfg);
@@ -199,7 +213,7 @@ void nb_ctx_free(nb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->cstream) cudaStreamSynchronize(c->cstream);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_node, &c->d_redge, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
+  DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_node, &c->d_walk, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
                  &c->d_ent, &c->d_ls, &c->d_qp, &c->d_mincov, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
                  &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].scope, &c->stg[0].cell,
                  &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded};

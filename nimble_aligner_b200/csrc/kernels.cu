@@ -128,10 +128,11 @@ struct EcAcc {
   bool any, big, uni; u32 last, prev2, base, bsize, alen; u64 boff, aoff, mask;
   __device__ void init(const DevIndex& ix, const Tables& t) { col_off = ix.col_off; col_ids = ix.col_ids; col_meta = ix.col_meta; arena = t.arena; ctr = t.ctr; arena_cap = t.arena_cap; any = big = uni = false; last = prev2 = NONE32; base = NONE32; bsize = alen = 0; boff = aoff = 0; mask = 0; }
   __device__ void reset() { any = big = uni = false; last = prev2 = NONE32; base = NONE32; bsize = alen = 0; boff = aoff = 0; mask = 0; }
-  __device__ void add(u32 cid, WorkCnt& wc) {
+  __device__ void add(u32 cid, WorkCnt& wc) { if (cid == last) return; add(cid, __ldg(col_meta + cid), wc); }
+  // same, with col_meta[cid] already in hand (it rides in the unitig's walk record)
+  __device__ void add(u32 cid, uint4 cm, WorkCnt& wc) {
     if (cid == last) { return; }
     last = cid;
-    uint4 cm = __ldg(col_meta + cid);
     if (cm.y) {   // bitmap colour
       u64 cmask = (u64)cm.z | ((u64)cm.w << 32);
       wc.colour_elems += (u32)__popcll(cmask);
@@ -187,12 +188,17 @@ struct EcAcc {
 // per-node budget: it is counted in snp (-> mismatches) but not in mb (-> coverage)   [App. B]
 // `next`: the read base right after the compared stretch (position rpos + m) when the compare ran to its end and that
 // base sits inside the last 32-base window that was loaded anyway; 4 = not available (caller loads it).
-__device__ __forceinline__ void cmp_fwd(const u64* U, u64 upos, const ReadView& rd, u32 rpos, u32 m, u32 allowed, u32& mb, u32& snp, bool& brk, u32& next) {
+// `ro`, s0, s1: offset of the stretch inside its unitig and the unitig's first 64 bases (from the walk record): windows
+// that end inside them need no load from the unitig store.
+__device__ __forceinline__ void cmp_fwd(const u64* U, u64 ustart, u32 ro, u64 s0, u64 s1, const ReadView& rd, u32 rpos, u32 m, u32 allowed, u32& mb, u32& snp, bool& brk, u32& next) {
   mb = 0; snp = 0; brk = false; next = 4;
   while (mb < m) {
     u32 c = min(32u, m - mb);
     u64 rw = rd.win(rpos + mb);
-    u64 x = uwin(U, upos + mb) ^ rw;
+    u32 o = ro + mb; u64 uw;
+    if (o + c <= 64) { if (o < 32) { u32 sh = 2 * o; uw = sh ? (s0 >> sh) | (s1 << (64 - sh)) : s0; } else uw = s1 >> (2 * (o - 32)); }
+    else uw = uwin(U, ustart + o);
+    u64 x = uw ^ rw;
     u64 d = (x | (x >> 1)) & 0x5555555555555555ULL;
     if (c < 32) d &= (1ULL << (2 * c)) - 1;
     u32 cnt = (u32)__popcll(d);

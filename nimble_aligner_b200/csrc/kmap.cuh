@@ -170,13 +170,13 @@ __global__ void __launch_bounds__(128) k_seed(BatchDev b, DevIndex ix, DevCfg cf
 
 // ---- k_walk: persistent warps, one seeded read per lane, one unitig per iteration (stages P, A+B, C, D of kmap.cuh)
 #ifndef NB_WALK_MINB
-#define NB_WALK_MINB 10   // 48 registers: 40 warps per SM (measured: 8 -> 10 blocks = -4 % time; 12 spills and loses)
+#define NB_WALK_MINB 9    // 56 registers: 36 warps per SM (measured with the 64-byte walk record: 9 blocks beat 8 and 10, which spills)
 #endif
 template <int COUNT_WORK>
 __global__ void __launch_bounds__(128, NB_WALK_MINB) k_walk(BatchDev b, DevIndex ix, DevCfg cfg, Tables t) {
   const unsigned FULL = 0xFFFFFFFFu;
   const u32 lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1;
-  const u32* redge = (const u32*)ix.redge; const u32* ledge = (const u32*)ix.ledge;
+  const u32* ledge = (const u32*)ix.ledge;
   const u32 allowed = cfg.num_mismatches;
   const u32 total = (u32)t.ctr->seeded_n;        // written by k_seed, complete at this kernel's start
   WorkCnt wc = {0, 0, 0, 0};
@@ -271,18 +271,23 @@ __global__ void __launch_bounds__(128, NB_WALK_MINB) k_walk(BatchDev b, DevIndex
         }
       }
     }
-    // ---------------------------------------------------------------- (D) one unitig of the forward walk
+    // ---------------------------------------------------------------- (D) one unitig of the forward walk, off its 64-byte walk record:
+    // node fields, the four right edges, the colour's bitmap metadata and the first 64 bases arrive together (two
+    // 256-bit loads of one line), so a step on a unitig of <= 64 bases touches nothing else of the index
     if (st == ST_WALK) {
-      uint4 nd = __ldg(ix.node + node);
-      u64 start = (u64)nd.x | ((u64)(nd.w >> 8) << 32);
-      kp += K; cov += K; acc.add(nd.z, wc); wc.nodes++;
-      u32 ro = off + K, m = min(n - kp, nd.y - ro), mb, snp, nxb; bool brk;
-      cmp_fwd(ix.unitig, start + ro, rd, kp, m, allowed, mb, snp, brk, nxb);
+      const u64* wp = (const u64*)(ix.walk + 4 * (u64)node);
+      Bucket fa = ld_bucket(wp, 0), fb = ld_bucket(wp, 1);
+      const u32 nlen = (u32)(fa.k0 >> 32), ncol = (u32)fa.k1, nexts = (u32)(fa.k1 >> 32);
+      const u64 start = (fa.k0 & 0xFFFFFFFFULL) | ((u64)(nexts >> 8) << 32);
+      kp += K; cov += K;
+      acc.add(ncol, make_uint4((u32)fb.k0, (u32)(fb.k0 >> 32), (u32)fb.k1, (u32)(fb.k1 >> 32)), wc); wc.nodes++;
+      u32 ro = off + K, m = min(n - kp, nlen - ro), mb, snp, nxb; bool brk;
+      cmp_fwd(ix.unitig, start, ro, fb.k2, fb.k3, rd, kp, m, allowed, mb, snp, brk, nxb);
       mm += snp; cov += mb; kp += mb; wc.bases += mb + (brk ? 1 : 0);
       if (kp >= n) st = ST_DONE;
       else {
         u32 bs = (!brk && nxb < 4) ? nxb : rd.base(kp);   // usually already in the compare's last window: one load less per unitig
-        if (!brk && ((nd.w >> (4 + bs)) & 1)) { node = __ldg(redge + 4 * (u64)node + bs); off = 0; kp -= K - 1; cov -= K - 1; }
+        if (!brk && ((nexts >> (4 + bs)) & 1)) { u64 e = bs & 2 ? fa.k3 : fa.k2; node = bs & 1 ? (u32)(e >> 32) : (u32)e; off = 0; kp -= K - 1; cov -= K - 1; }
         else st = kp > last_kpos ? ST_DONE : ST_SEED;
       }
     }

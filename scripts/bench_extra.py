@@ -70,7 +70,25 @@ def main():
     torch.cuda.synchronize(); dt = (time.time() - t0) / a.steps
     ks = ctx.kernel_stats()
     align_s = (T["align"] - starts) / a.steps
-    print(json.dumps({"workload": desc, "e2e_reads_per_s": n / dt, "align_only_reads_per_s": n / align_s, "align_ms": align_s * 1e3, "finalize_ms": (dt - align_s) * 1e3, "ms_per_step": dt * 1e3, "h2d_gb_per_s": h2d / dt / 1e9, "count_rows": int(len(raw["row_count"])),
+    roof = None
+    if a.workload != "c3":
+        # algorithmic bytes per read from the device's own work counters (equal to the oracle's on every parity test):
+        # packed read + 16 B per probe + 32 B per visited unitig + compared bases / 4 + 4 B per colour id + 32 B result
+        m = min(n, 1 << 20)
+        wctx = nb.Context(ix, lib, stream=s.cuda_stream, max_batch_pairs=1 << 20, callset_slots=1 << 22, agg_slots=1 << 23, count_work=1)
+        wb = nb.Batch(m, nb.NB_MEM_HOST, 150, hb.data_ptr(), ho.data_ptr(), None, None, None, None, None, None, None, None)
+        nb._ck(nb.lib().nb_align_batch(wctx.h, C.byref(wb), None, None)); wctx.sync()
+        w = wctx.work_counters()
+        bpr = (8 * 5 * m + 16 * w["probes"] + 32 * w["nodes"] + w["bases"] / 4.0 + 4 * w["colour_elems"] + 32 * m) / m
+        ms = ks["map_ms"] / max(1, ks["map_launches"]); rpl = ks["map_reads"] / max(1, ks["map_launches"])
+        peak = 6458.4
+        try:
+            peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "algorithmic_bytes_per_read": bpr, "achieved_gb_s": bpr * rpl / (ms / 1e3) / 1e9, "peak_gb_s": peak, "frac": bpr * rpl / (ms / 1e3) / 1e9 / peak,
+                "work_per_read": {k: w[k] / m for k in w}}
+    print(json.dumps({"workload": desc, "map_stage_roofline": roof, "e2e_reads_per_s": n / dt, "align_only_reads_per_s": n / align_s, "align_ms": align_s * 1e3, "finalize_ms": (dt - align_s) * 1e3, "ms_per_step": dt * 1e3, "h2d_gb_per_s": h2d / dt / 1e9, "count_rows": int(len(raw["row_count"])),
                       "unique_keys": int(raw["n_unique_keys"]), "k_map_ms_per_launch": ks["map_ms"] / max(1, ks["map_launches"]), "k_map_reads_per_launch": ks["map_reads"] / max(1, ks["map_launches"]),
                       "k_map_share": ks["map_ms"] / (dt * 1e3 * a.steps), "launches_per_step": ks["launches"] / a.steps}))
 
