@@ -182,6 +182,9 @@ typedef struct nb_counts {
   uint64_t n_slots; const uint32_t* slot_to_callset;   /* nb_pair_result.callset (dictionary slot) -> callset id here */
 } nb_counts;
 int nb_counts_finalize(nb_ctx*, nb_counts* out);
+/* device copies of the row columns of the last nb_counts_finalize (row_scope u32[n], row_callset u32[n], row_count i64[n]),
+ * valid until the next finalize / reset: lets a multi-GPU host reduce per-cell tables without a host round trip */
+int nb_counts_device_rows(nb_ctx*, const void** row_scope, const void** row_callset, const void** row_count, uint64_t* n_rows);
 int nb_counts_reset(nb_ctx*);
 uint32_t nb_library_n_groups(const nb_library*);
 const char* nb_library_group_name(const nb_library*, uint32_t group);

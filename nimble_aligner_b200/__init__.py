@@ -101,7 +101,8 @@ _SIGS = {
     "nb_host_alloc": (C.c_void_p, [C.c_size_t]), "nb_host_free": (None, [C.c_void_p]),
     "nb_align_batch": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
     "nb_last_batch_ecs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
-    "nb_counts_finalize": (C.c_int, [C.c_void_p, C.POINTER(Counts)]), "nb_counts_reset": (C.c_int, [C.c_void_p]),
+    "nb_counts_finalize": (C.c_int, [C.c_void_p, C.POINTER(Counts)]),
+    "nb_counts_device_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]), "nb_counts_reset": (C.c_int, [C.c_void_p]),
     "nb_keys_export_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "nb_keys_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "nb_keys_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -362,18 +363,31 @@ class Context:
         raw = self.counts_raw()
         return self.decode_counts(raw)
 
-    def counts_raw(self):
-        """nb_counts_finalize -> numpy copies of the C arrays (group indices, no strings)."""
+    def counts_raw(self, rows=True):
+        """nb_counts_finalize -> numpy copies of the C arrays (group indices, no strings).  rows=False leaves the row
+        columns out (a multi-GPU host that reduces them on the device, counts_device_rows, has no use for host copies)."""
         c = Counts()
         _ck(lib().nb_counts_finalize(self.h, C.byref(c)))
 
         def arr(p, n, dt):
             return np.ctypeslib.as_array(p, (n,)).copy() if n else np.zeros(0, dt)
         n_items = int(c.callset_off[c.n_callsets]) if c.n_callsets else 0
-        return dict(row_scope=arr(c.row_scope, c.n_rows, np.uint32), row_callset=arr(c.row_callset, c.n_rows, np.uint32),
-                    row_count=arr(c.row_count, c.n_rows, np.int64), callset_off=arr(c.callset_off, c.n_callsets + 1, np.uint64),
+        nr = c.n_rows if rows else 0
+        return dict(row_scope=arr(c.row_scope, nr, np.uint32), row_callset=arr(c.row_callset, nr, np.uint32),
+                    row_count=arr(c.row_count, nr, np.int64), callset_off=arr(c.callset_off, c.n_callsets + 1, np.uint64),
                     callset_items=arr(c.callset_items, n_items, np.uint32), n_pairs_seen=c.n_pairs_seen, n_unique_keys=c.n_unique_keys,
                     slot_to_callset=arr(c.slot_to_callset, c.n_slots, np.uint32))
+
+    def counts_device_rows(self):
+        """(row_scope, row_callset, row_count) of the last finalize as objects with __cuda_array_interface__ (zero copy)."""
+        a, b, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        _ck(lib().nb_counts_device_rows(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+
+        class _Dev:
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr or 0, False), "version": 2}
+        n = n.value
+        return _Dev(a.value, n, "<u4"), _Dev(b.value, n, "<u4"), _Dev(c.value, n, "<i8"), n
 
     def decode_counts(self, raw):
         if getattr(self, "_group_names", None) is None:

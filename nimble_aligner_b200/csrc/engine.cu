@@ -85,7 +85,9 @@ struct nb_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
   double map_ms = 0; u64 map_launches = 0, map_reads = 0, all_launches = 0;
   // results
-  std::vector<u32> row_scope, row_callset, cs_items, slot_dense; std::vector<i64> row_count; std::vector<u64> cs_off;
+  std::vector<u32> cs_items, slot_dense; std::vector<u64> cs_off;
+  u8* h_rows = nullptr; size_t h_rows_cap = 0; u64 n_rows_dev = 0;   // pinned: row_scope | row_callset | row_count of the last finalize
+  DBuf d_rowwork, d_rowout, d_dense;
 };
 
 static Tables make_tables(nb_ctx* c) {
@@ -216,8 +218,9 @@ void nb_ctx_free(nb_ctx* c) {
   DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_node, &c->d_walk, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
                  &c->d_ent, &c->d_ls, &c->d_qp, &c->d_mincov, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
                  &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].scope, &c->stg[0].cell,
-                 &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded};
+                 &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded, &c->d_rowwork, &c->d_rowout, &c->d_dense};
   for (DBuf* b : all) b->release();
+  nb_host_free(c->h_rows); c->h_rows = nullptr;
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (int i = 0; i < 2; i++) { if (c->stg[i].copied) cudaEventDestroy(c->stg[i].copied); if (c->stg[i].consumed) cudaEventDestroy(c->stg[i].consumed); }
@@ -415,7 +418,7 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   if (!c || !out) return fail(NB_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
   memset(out, 0, sizeof *out);
-  c->row_scope.clear(); c->row_callset.clear(); c->row_count.clear(); c->cs_items.clear(); c->cs_off.assign(1, 0);
+  c->cs_items.clear(); c->cs_off.assign(1, 0);
   if (!c->tables_ready) { out->callset_off = c->cs_off.data(); return NB_OK; }
   cudaStream_t s = c->stream;
   Tables t = make_tables(c);
@@ -433,8 +436,7 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   u64* d_agg = (u64*)c->d_scratch.p; u32* d_cs = (u32*)((char*)c->d_scratch.p + n_agg * 16);
   CK(cudaMemsetAsync(c->d_nout.p, 0, 16, s));
   nbk::launch_compact(t, d_agg, n_agg, d_cs, n_cs, (unsigned long long*)c->d_nout.p, s); c->all_launches += 2;
-  std::vector<u64> agg(2 * n_agg); std::vector<u32> csr((size_t)n_cs * cw);
-  if (n_agg) CK(cudaMemcpyAsync(agg.data(), d_agg, n_agg * 16, cudaMemcpyDeviceToHost, s));
+  std::vector<u32> csr((size_t)n_cs * cw);
   if (n_cs) CK(cudaMemcpyAsync(csr.data(), d_cs, n_cs * (size_t)cw * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (fstats) ft[2] = fnow();
@@ -457,26 +459,35 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   std::vector<u32>& dense = c->slot_dense; dense.assign(c->cs_slots, NONE32);
   for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[4 + k]); c->cs_off.push_back(c->cs_items.size()); }
   if (fstats) ft[3] = fnow();
-  // rows ordered by (cell, callset): LSD radix sort on the 56-bit key (the table can hold millions of (cell, callset) rows)
-  std::vector<u64> key(n_agg), key2(n_agg); std::vector<i64> val(n_agg), val2(n_agg);
-  for (u64 i = 0; i < n_agg; i++) { u64 k = agg[2 * i] - 1; key[i] = ((k >> 24) << 24) | dense[(u32)(k & 0xFFFFFF)]; val[i] = (i64)agg[2 * i + 1]; }
-  if (n_agg > 1) {
-    u64 any = 0; for (u64 i = 0; i < n_agg; i++) any |= key[i];
-    for (int shift = 0; shift < 64 && (any >> shift); shift += 16) {
-      std::vector<u64> cnt(65537, 0);
-      for (u64 i = 0; i < n_agg; i++) cnt[((key[i] >> shift) & 0xFFFF) + 1]++;
-      for (int b = 0; b < 65536; b++) cnt[b + 1] += cnt[b];
-      for (u64 i = 0; i < n_agg; i++) { u64 at = cnt[(key[i] >> shift) & 0xFFFF]++; key2[at] = key[i]; val2[at] = val[i]; }
-      key.swap(key2); val.swap(val2);
-    }
+  // rows ordered by (cell, callset): remap to dense callset ids, radix sort and split on the device (kernels.cu), then one
+  // copy into pinned memory — the table can hold millions of (cell, callset) rows
+  if (n_agg >= (1ull << 31)) return fail(NB_ERR_UNSUPPORTED, "more than 2^31 (cell, callset) rows");
+  if (c->h_rows_cap < n_agg * 16) { nb_host_free(c->h_rows); c->h_rows_cap = n_agg * 16 + n_agg * 4 + 4096; c->h_rows = (u8*)nb_host_alloc(c->h_rows_cap); if (!c->h_rows) { c->h_rows_cap = 0; return fail(NB_ERR_CUDA, "pinned host allocation failed"); } }
+  u32* h_scope = (u32*)c->h_rows; u32* h_callset = h_scope + n_agg; i64* h_count = (i64*)(c->h_rows + 8 * n_agg);
+  c->n_rows_dev = n_agg;
+  if (n_agg) {
+    size_t tb = nbk::rows_sort_tmp_bytes(n_agg), work = n_agg * 32;
+    CK(c->d_rowwork.ensure(work + tb, s)); CK(c->d_rowout.ensure(n_agg * 16, s)); CK(c->d_dense.ensure(dense.size() * 4, s));
+    CK(cudaMemcpyAsync(c->d_dense.p, dense.data(), dense.size() * 4, cudaMemcpyHostToDevice, s));
+    u64* d_keys = (u64*)c->d_rowwork.p; i64* d_vals = (i64*)((char*)c->d_rowwork.p + n_agg * 16); void* d_tmp = (char*)c->d_rowwork.p + work;
+    u32* d_scope = (u32*)c->d_rowout.p; u32* d_callset = d_scope + n_agg; i64* d_count = (i64*)((char*)c->d_rowout.p + 8 * n_agg);
+    nbk::launch_rows_sort(d_agg, n_agg, (const u32*)c->d_dense.p, d_keys, d_vals, d_tmp, tb, d_scope, d_callset, d_count, s); c->all_launches += 3;
+    CK(cudaMemcpyAsync(c->h_rows, c->d_rowout.p, n_agg * 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
   }
-  c->row_scope.resize(n_agg); c->row_callset.resize(n_agg); c->row_count.resize(n_agg);
-  for (u64 i = 0; i < n_agg; i++) { c->row_scope[i] = (u32)(key[i] >> 24); c->row_callset[i] = (u32)(key[i] & 0xFFFFFF); c->row_count[i] = val[i]; }
   struct { size_t n; size_t size() const { return n; } } rows{(size_t)n_agg};
-  out->n_rows = rows.size(); out->row_scope = c->row_scope.data(); out->row_callset = c->row_callset.data(); out->row_count = c->row_count.data();
+  out->n_rows = rows.size(); out->row_scope = h_scope; out->row_callset = h_callset; out->row_count = h_count;
   out->n_callsets = slots.size(); out->callset_off = c->cs_off.data(); out->callset_items = c->cs_items.data();
   out->n_pairs_seen = c->pairs_seen; out->n_unique_keys = h.n_keys; out->n_slots = c->cs_slots; out->slot_to_callset = c->slot_dense.data();
   if (fstats) { ft[4] = fnow(); fprintf(stderr, "finalize: fold+counters %.3f ms, compact+D2H %.3f ms, callset sort %.3f ms, rows %.3f ms (%llu rows, %llu callsets, key slots %llu)\n", (ft[1] - ft[0]) * 1e3, (ft[2] - ft[1]) * 1e3, (ft[3] - ft[2]) * 1e3, (ft[4] - ft[3]) * 1e3, (unsigned long long)n_agg, (unsigned long long)n_cs, (unsigned long long)c->key_slots); }
+  return NB_OK;
+}
+
+int nb_counts_device_rows(nb_ctx* c, const void** row_scope, const void** row_callset, const void** row_count, uint64_t* n_rows) {
+  if (!c || !row_scope || !row_callset || !row_count || !n_rows) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->folded && c->mode != 1) return fail(NB_ERR_INVALID, "no finalized counts");
+  u64 n = c->n_rows_dev; *n_rows = n;
+  *row_scope = c->d_rowout.p; *row_callset = (const u32*)c->d_rowout.p + n; *row_count = (const char*)c->d_rowout.p + 8 * n;
   return NB_OK;
 }
 
@@ -484,7 +495,7 @@ int nb_counts_reset(nb_ctx* c) {
   if (!c) return fail(NB_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
   if (c->tables_ready) { CK(cudaStreamSynchronize(c->stream)); c->tables_ready = false; }
-  c->mode = -1; c->folded = false; c->pairs_seen = 0; c->keys_upper = 0; c->have_last = false;
+  c->mode = -1; c->folded = false; c->pairs_seen = 0; c->keys_upper = 0; c->have_last = false; c->n_rows_dev = 0;
   return NB_OK;
 }
 

@@ -81,15 +81,98 @@ def merge_across_ranks(shard, torch, dist, rank, world, device):
     return raw, int(hd[ncs])
 
 
+def merge_scoped_across_ranks(shard, torch, dist, rank, world, device, n_cells):
+    """BAM mode: (UMI, CB) scopes are independent, so whole scopes shard over ranks with no data-path
+    exchange; only the per-cell count table is combined.  (1) all_gather of the callset dictionary rows so every rank
+    numbers callsets alike, (2) dense [n_cells x n_callsets] all_reduce when that is small, else all_gather of the sparse
+    (cell, callset, count) rows which every rank sums.  Returns (cells, callsets, counts) int64 arrays, sorted by (cell, callset)."""
+    stats = os.environ.get("NB_MERGE_STATS") and rank == 0
+    marks = []
+
+    def mark(name):
+        if stats:
+            if device != "cpu":
+                torch.cuda.synchronize()
+            marks.append((name, time.time()))
+    mark("start")
+    rows = shard.callsets_export()
+    k, cw = rows.shape
+    mark("callsets_export")
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    sizes[rank] = k
+    dist.all_reduce(sizes)
+    szs = sizes.cpu().tolist()
+    kmax = max(max(szs), 1)
+    mine = torch.zeros((kmax, cw), dtype=torch.int32, device=device)
+    if k:
+        mine[:k] = torch.from_numpy(np.ascontiguousarray(rows).view(np.int32)).to(device)
+    allrows = torch.empty((world, kmax, cw), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(allrows.view(-1), mine.view(-1))
+    others = torch.cat([allrows[r, : int(szs[r])] for r in range(world) if r != rank and szs[r]] or [allrows[0, :0]]).cpu().numpy().view(np.uint32)
+    shard.callsets_import(np.ascontiguousarray(others))
+    mark("callsets_exchange_import")
+    raw = shard.finalize()
+    mark("finalize")
+    ncs = len(raw["callset_off"]) - 1
+    if n_cells * max(ncs, 1) <= (1 << 25):
+        dense = torch.zeros(n_cells * max(ncs, 1), dtype=torch.int64, device=device)
+        dev = shard.device_rows() if hasattr(shard, "device_rows") else None
+        if dev is not None:   # rows are still on the device: no host round trip
+            dcell, dcs, dcnt = dev
+            if dcnt.numel():
+                dense.index_add_(0, dcell.to(torch.int64) * ncs + dcs.to(torch.int64), dcnt)
+        elif len(raw["row_count"]):
+            cell = np.asarray(raw["row_scope"], dtype=np.int64); cs = np.asarray(raw["row_callset"], dtype=np.int64)
+            dense.index_add_(0, torch.from_numpy(cell * ncs + cs).to(device), torch.from_numpy(np.asarray(raw["row_count"], dtype=np.int64)).to(device))
+        mark("dense_fill")
+        dist.all_reduce(dense)
+        mark("all_reduce")
+        if rank != 0:
+            z = np.zeros(0, dtype=np.int64)
+            return raw, z, z, z          # the job's table is read back on rank 0 only
+        nz = torch.nonzero(dense).view(-1)
+        tri = torch.stack([nz // max(ncs, 1), nz % max(ncs, 1), dense[nz]])
+        if device == "cpu":
+            out = tri.numpy()
+        else:   # the merged table lands in pinned memory: one DMA instead of a pageable copy of ~200 MB
+            k = tri.shape[1]
+            if getattr(shard, "pin", None) is None or shard.pin.numel() < 3 * k:
+                shard.pin = torch.empty(3 * (k + k // 4 + 1), dtype=torch.int64, pin_memory=True)
+            shard.pin[: 3 * k].copy_(tri.reshape(-1), non_blocking=True)   # contiguous on both sides: one DMA
+            torch.cuda.current_stream().synchronize()
+            out = shard.pin[: 3 * k].view(3, k).numpy()
+        mark("readback")
+        if stats:
+            print("scoped merge: " + ", ".join("%s %.2f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3) for i in range(1, len(marks))), file=sys.stderr)
+        return raw, out[0], out[1], out[2]
+    cell = np.asarray(raw["row_scope"], dtype=np.int64); cs = np.asarray(raw["row_callset"], dtype=np.int64); cnt = np.asarray(raw["row_count"], dtype=np.int64)
+    n = torch.zeros(world, dtype=torch.int64, device=device)
+    n[rank] = len(cnt)
+    dist.all_reduce(n)
+    ns = n.cpu().tolist(); nmax = max(max(ns), 1)
+    tri = torch.zeros((nmax, 3), dtype=torch.int64, device=device)
+    if len(cnt):
+        tri[: len(cnt)] = torch.from_numpy(np.stack([cell, cs, cnt], axis=1)).to(device)
+    alltri = torch.empty((world, nmax, 3), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(alltri.view(-1), tri.view(-1))
+    t = torch.cat([alltri[r, : int(ns[r])] for r in range(world)]).cpu().numpy()
+    key = t[:, 0] * max(ncs, 1) + t[:, 1]
+    uk, inv = np.unique(key, return_inverse=True)
+    val = np.bincount(inv, weights=t[:, 2]).astype(np.int64) if len(uk) else np.zeros(0, dtype=np.int64)
+    return raw, uk // max(ncs, 1), uk % max(ncs, 1), val
+
+
 class DeviceShard:
     """One GPU's tables behind the C ABI (nb_callsets_export / nb_keys_export_partitioned / nb_callsets_import /
     nb_keys_import / nb_counts_finalize).  Buffers are allocated once: unique keys <= pairs aligned on this rank."""
 
     def __init__(self, ctx, nb, torch, pair_base, max_pairs):
         self.ctx, self.nb, self.torch, self.pair_base = ctx, nb, torch, pair_base
+        self.scoped = max_pairs == 0   # scoped (BAM) merges reduce the rows on the device
+        self.pin = None
         self.rows = None
-        self.rec = torch.empty((max_pairs, 4), dtype=torch.int64, device="cuda")
-        self.out = torch.empty((max_pairs + max_pairs // 4, 4), dtype=torch.int64, device="cuda")
+        self.rec = torch.empty((max_pairs, 4), dtype=torch.int64, device="cuda") if max_pairs else None   # (scoped merges exchange no key records)
+        self.out = torch.empty((max_pairs + max_pairs // 4, 4), dtype=torch.int64, device="cuda") if max_pairs else None
 
     def callsets_export(self):
         nout, gcap = C.c_uint64(0), C.c_uint32(0)
@@ -116,4 +199,12 @@ class DeviceShard:
         self.nb._ck(self.nb.lib().nb_keys_import(self.ctx.h, rec.data_ptr(), rec.shape[0]))
 
     def finalize(self):
-        return self.ctx.counts_raw()
+        return self.ctx.counts_raw(rows=not self.scoped)
+
+    def device_rows(self):
+        a, b, c, n = self.ctx.counts_device_rows()
+        if not n:
+            z = self.torch.zeros(0, dtype=self.torch.int64, device="cuda")
+            return z, z, z
+        t = self.torch
+        return t.as_tensor(a, device="cuda").view(t.int32), t.as_tensor(b, device="cuda").view(t.int32), t.as_tensor(c, device="cuda")

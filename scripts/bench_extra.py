@@ -18,27 +18,43 @@ def main():
     ap.add_argument("--families", type=int, default=8000)
     ap.add_argument("--steps", type=int, default=3)
     a = ap.parse_args()
-    cores = os.cpu_count() or 1
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    cores = max(1, (os.cpu_count() or 1) // world)
+    torch.cuda.set_device(local_rank)
+    if world > 1:   # C3 only: (UMI, CB) scopes shard over ranks, the per-cell tables are combined at the end of the job
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        assert a.workload == "c3"
     T = {"align": 0.0}
     s = torch.cuda.Stream(); torch.cuda.set_stream(s)
     if a.workload == "c3":
         L = synth.SynthLibrary(seed=1234, n_fam=200, n_all=5, group_on="", trim_target_length=40, trim_strictness=0.9)
         lib = nb.Library.from_text(json.dumps(L.to_json_obj()), "unstranded")
         ix = nb.build_index(lib, cores)
-        u = synth.umi_reads(L, 0, a.reads // 4, seed=2345, threads=cores)
+        groups = a.reads // 4
+        u = synth.umi_reads(L, rank * groups, groups, seed=2345, threads=cores)   # weak scaling: every rank takes its own run of (UMI, CB) groups
         n = u["n_reads"]
         pin = lambda x: torch.from_numpy(x).pin_memory()
         bases, qual, off = pin(u["bases"]), pin(u["qual"]), pin(u["off"].astype(np.int64))
         scope, cell = pin(u["scope"].astype(np.int32)), pin(u["cell"].astype(np.int32))
         f1 = pin(np.full(n, nb.FLAG_SKIP_ALIGN, dtype=np.uint8)); f2 = pin(np.zeros(n, dtype=np.uint8))
-        ctx = nb.Context(ix, lib, stream=s.cuda_stream, max_batch_pairs=1 << 20, agg_slots=1 << 24)
+        ctx = nb.Context(ix, lib, device=local_rank, stream=s.cuda_stream, max_batch_pairs=1 << 20, agg_slots=1 << 24)
         import ctypes as C
+        if world > 1:
+            from nimble_aligner_b200.multigpu import merge_scoped_across_ranks, DeviceShard
+            shard = DeviceShard(ctx, nb, torch, 0, 0)
         def step():
             ctx.reset()
             b = nb.Batch(n, nb.NB_MEM_HOST, 91, bases.data_ptr(), off.data_ptr(), bases.data_ptr(), off.data_ptr(), qual.data_ptr(), qual.data_ptr(),
                          f1.data_ptr(), f2.data_ptr(), scope.data_ptr(), cell.data_ptr())
             nb._ck(nb.lib().nb_align_batch(ctx.h, C.byref(b), None, None))
             ctx.sync(); T["align"] += time.time()
+            if world > 1:
+                raw, cells, css, vals = merge_scoped_across_ranks(shard, torch, dist, rank, world, "cuda", 8000)
+                raw = dict(raw); raw["row_count"] = vals
+                return raw
             return ctx.counts_raw()
         desc = "C3-shaped: %d single-end 91 bp records with quals in %d (UMI,CB) scopes, 8000 cells, 1k-transcript library" % (n, len(u["sizes"]))
         h2d = int(u["off"][-1]) * 2 + n * (8 + 4 + 4 + 2)
@@ -63,11 +79,19 @@ def main():
     for _ in range(2):
         raw = step()
     ctx.kernel_stats(reset=True)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize(); t0 = time.time(); T["align"] = 0.0; starts = 0.0
     for _ in range(a.steps):
         starts += time.time()
         raw = step()
     torch.cuda.synchronize(); dt = (time.time() - t0) / a.steps
+    if world > 1:   # max over ranks; rank 0 reports the whole job
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); dt = float(tt.item())
+        n = n * world
+        if rank != 0:
+            dist.destroy_process_group(); return
+        desc += " per rank x %d ranks (scopes sharded, per-cell tables merged)" % world
     ks = ctx.kernel_stats()
     align_s = (T["align"] - starts) / a.steps
     roof = None

@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 
 import oracle as orc
 import synth
-from nimble_aligner_b200.multigpu import merge_across_ranks
+from nimble_aligner_b200.multigpu import merge_across_ranks, merge_scoped_across_ranks
 
 GCAP = 16
 
@@ -144,3 +144,78 @@ def test_world_size_2_gloo_merge_equals_single_process_counts():
     assert merged == want
     keys = {k for k, ins, _ in _per_pair(orc.Oracle(ocfg, oref), ocfg, r1, o1, r2, o2, 0, len(o1) - 1) if ins}
     assert uniq == len(keys) and len(want) > 50 and sum(want.values()) > 1000
+
+
+# ------------------------------------------------------------------ BAM mode: scopes shard, per-cell tables add
+class ScopedModelShard(ModelShard):
+    def __init__(self, names_sorted):
+        super().__init__(names_sorted)
+        self.table = {}
+
+    def add_scope(self, cell, rows):
+        for cs, c in rows:
+            cs = tuple(cs); self.cs[_tag(cs)] = cs
+            self.table[(cell, cs)] = self.table.get((cell, cs), 0) + c
+
+    def finalize(self):
+        order = sorted(self.cs.items(), key=lambda kv: kv[1])
+        dense = {cs: i for i, (_, cs) in enumerate(order)}
+        items = sorted((cell, dense[cs], c) for (cell, cs), c in self.table.items())
+        a = np.array(items, dtype=np.int64).reshape(-1, 3)
+        return dict(callset_off=np.arange(len(order) + 1), row_scope=a[:, 0], row_callset=a[:, 1], row_count=a[:, 2], n_unique_keys=0, callsets=[cs for _, cs in order])
+
+
+def _scoped_inputs():
+    L = synth.SynthLibrary(seed=78, n_fam=40, n_all=5, group_on="")
+    u = synth.umi_reads(L, 0, 1200, seed=9, n_cells=50)
+    return L, L.to_json_obj(), u
+
+
+def _scoped_rows(o, u, s0, s1):
+    """Oracle over scopes [s0, s1): list of (cell, rows)."""
+    start = np.concatenate([[0], np.cumsum(u["sizes"])]).astype(np.int64)
+    a, b = int(start[s0]), int(start[s1]); L = 91
+    bases, qual = u["bases"][a * L:b * L], u["qual"][a * L:b * L]
+    off = (np.arange(b - a + 1, dtype=np.uint64) * L)
+    scope_off = (start[s0:s1 + 1] - start[s0]).astype(np.uint64)
+    ref = o.run(bases, off, bases, off, q1=qual, q2=qual, skip1=np.ones(b - a, dtype=np.uint8), skip2=None, scope_off=scope_off, threads=2, want_records=False)
+    return [(int(u["cell"][start[s]]), ref["scopes"][s - s0]) for s in range(s0, s1)]
+
+
+def _scoped_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L, obj, u = _scoped_inputs()
+        ocfg, oref = orc.parse_reference_library(obj, "unstranded")
+        o = orc.Oracle(ocfg, oref)
+        ns = len(u["sizes"]); per = ns // world; s0, s1 = rank * per, (rank + 1) * per if rank + 1 < world else ns
+        shard = ScopedModelShard(sorted(L.names))
+        for cell, rows in _scoped_rows(o, u, s0, s1):
+            shard.add_scope(cell, rows)
+        for force_sparse in (False, True):
+            raw, cells, css, vals = merge_scoped_across_ranks(shard, torch, dist, rank, world, "cpu", 50 if not force_sparse else (1 << 40))
+            if rank == 0:
+                q.put({(int(c), raw["callsets"][int(k)]): int(v) for c, k, v in zip(cells, css, vals)})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_scoped_merge_equals_single_process_table():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_scoped_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    dense, sparse = q.get(timeout=240), q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    L, obj, u = _scoped_inputs()
+    ocfg, oref = orc.parse_reference_library(obj, "unstranded")
+    want = {}
+    for cell, rows in _scoped_rows(orc.Oracle(ocfg, oref), u, 0, len(u["sizes"])):
+        for cs, c in rows:
+            want[(cell, tuple(cs))] = want.get((cell, tuple(cs)), 0) + c
+    assert dense == want and sparse == want and len(want) > 100
