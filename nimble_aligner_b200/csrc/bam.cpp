@@ -15,6 +15,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <future>
@@ -36,13 +37,24 @@ const char* FIELDS[38] = {"QNAME", "QUAL", "REVERSE", "MATE_REVERSE", "PAIRED", 
 const size_t CLIP_LENGTH = 13;   // src/parse/bam.rs:7
 
 // ------------------------------------------------------------------ BGZF: all blocks located up front, inflated by a thread pool
+// byte buffer without value-initialisation: the inflate threads are the first to touch the pages (a zero-filling
+// std::vector costs a single-threaded pass over gigabytes before the first block is inflated)
+struct RawBuf {
+  u8* p = nullptr; size_t n = 0;
+  ~RawBuf() { free(p); }
+  bool alloc(size_t bytes) { free(p); p = (u8*)malloc(bytes ? bytes : 1); n = p ? bytes : 0; return p != nullptr; }
+  void release() { free(p); p = nullptr; n = 0; }
+  size_t size() const { return n; } const u8* data() const { return p; } u8* data() { return p; }
+  const u8& operator[](size_t i) const { return p[i]; } u8& operator[](size_t i) { return p[i]; }
+};
+
 struct Bgzf {
-  std::vector<u8> file; std::vector<u8> data;   // compressed file image, inflated stream
+  RawBuf file, data;   // compressed file image, inflated stream
   int load(const std::string& path, int threads) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) return fail(NB_ERR_IO, "could not open " + path);
     fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
-    file.resize((size_t)sz);
+    if (!file.alloc((size_t)sz)) { fclose(f); return fail(NB_ERR_IO, "out of memory reading " + path); }
     if (sz && fread(file.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(NB_ERR_IO, "short read on " + path); }
     fclose(f);
     struct Blk { size_t off, clen, uoff, ulen; };
@@ -57,7 +69,7 @@ struct Bgzf {
       blks.push_back({xend, bsize - (xend - p) - 8, utot, isize});
       utot += isize; p += bsize;
     }
-    data.resize(utot);
+    if (!data.alloc(utot)) return fail(NB_ERR_IO, "out of memory inflating " + path);
     std::atomic<size_t> next(0); std::atomic<int> bad(0);
     auto work = [&]() {
       for (;;) { size_t i = next.fetch_add(1); if (i >= blks.size()) break; const Blk& b = blks[i]; if (!b.ulen) continue;
@@ -69,7 +81,7 @@ struct Bgzf {
     };
     std::vector<std::thread> th; for (int t = 1; t < std::max(1, threads); t++) th.emplace_back(work);
     work(); for (auto& t : th) t.join();
-    std::vector<u8>().swap(file);
+    file.release();
     if (bad) return fail(NB_ERR_PARSE, "BGZF inflate failed in " + path);
     return NB_OK;
   }
@@ -187,7 +199,7 @@ struct SortedReader {
   std::string current_umi, next_umi; std::vector<Rec> buffer, next_records;   // buffer is popped from the back
   SortedReader(const Bgzf& zz, bool fp) : z(zz), force_paired(fp) {}
   int skip_header() {
-    const std::vector<u8>& d = z.data;
+    const RawBuf& d = z.data;
     if (d.size() < 12 || memcmp(d.data(), "BAM\1", 4)) return fail(NB_ERR_PARSE, "not a BAM file");
     u32 l_text; memcpy(&l_text, &d[4], 4); size_t p = 8 + (size_t)l_text; u32 n_ref; if (p + 4 > d.size()) return fail(NB_ERR_PARSE, "truncated BAM header"); memcpy(&n_ref, &d[p], 4); p += 4;
     for (u32 i = 0; i < n_ref; i++) { if (p + 4 > d.size()) return fail(NB_ERR_PARSE, "truncated BAM header"); u32 l; memcpy(&l, &d[p], 4); p += 4 + (size_t)l + 4; }
@@ -195,7 +207,7 @@ struct SortedReader {
   }
   // locate the records (serial walk over block sizes), then scan their grouping keys on `threads` threads
   void prepare(int threads) {
-    const std::vector<u8>& d = z.data;
+    const RawBuf& d = z.data;
     while (cur + 4 <= d.size()) {
       u32 bs; memcpy(&bs, &d[cur], 4);
       if (bs < 32 || cur + 4 + bs > d.size()) break;
@@ -279,7 +291,7 @@ struct UmiReader {
 
 // The groups the producer loop sends, in order (src/process/bam.rs:157-180): records of group g are
 // stream[gstart[g] .. gstart[g+1]); the last group is never sent when a group was sent before.
-int collect_groups(const Bgzf& z, bool force_paired, int threads, std::vector<Rec>& stream, std::vector<u64>& gstart) {
+int collect_groups_serial(const Bgzf& z, bool force_paired, int threads, std::vector<Rec>& stream, std::vector<u64>& gstart) {
   UmiReader reader(z, force_paired);
   int rc = reader.rd.skip_header(); if (rc) return rc;
   reader.rd.prepare(threads);
@@ -294,6 +306,75 @@ int collect_groups(const Bgzf& z, bool force_paired, int threads, std::vector<Re
     has_aligned = true;
     if (final_umi) break;
   }
+  return NB_OK;
+}
+
+// group key of UMIReader: UMI + CB without its last two characters, compared without building the strings
+inline bool key_equal(const Rec& a, const Rec& b) {
+  u32 ca = a.cb_len >= 2 ? a.cb_len - 2 : 0, cb = b.cb_len >= 2 ? b.cb_len - 2 : 0;
+  if (a.umi_len + ca != b.umi_len + cb) return false;
+  if (a.umi_len == b.umi_len) return !memcmp(a.umi, b.umi, a.umi_len) && !memcmp(a.cb, b.cb, ca);
+  std::string x(a.umi, a.umi_len), y(b.umi, b.umi_len); x.append(a.cb, ca); y.append(b.cb, cb); return x == y;   // different split of the same concatenation
+}
+
+// The same stream and groups as collect_groups_serial, computed on `threads` threads.  The serial readers above define the
+// semantics; this restates them over whole runs: a SortedBamReader buffer is a maximal run of kept records with one UMI
+// (the last run of the file is the one that is not CB-sorted), buffers are independent, the stream ends at the first
+// buffer that is empty after pairing (next() returns None there), and UMIReader's groups are runs of equal keys.
+// Falls back to the serial readers when a kept record has an empty UMI string (their empty-string quirks apply then).
+int collect_groups(const Bgzf& z, bool force_paired, int threads, std::vector<Rec>& stream, std::vector<u64>& gstart) {
+  if (getenv("NB_BAM_SERIAL_GROUPING")) return collect_groups_serial(z, force_paired, threads, stream, gstart);
+  SortedReader rd(z, force_paired);
+  int rc = rd.skip_header(); if (rc) return rc;
+  rd.prepare(threads);
+  const std::vector<Rec>& all = rd.all;
+  // kept records, in file order
+  std::vector<u32> kept; kept.reserve(all.size());
+  if (all.size() >= 0xFFFFFFFFull) return collect_groups_serial(z, force_paired, threads, stream, gstart);
+  for (size_t i = 0; i < all.size(); i++) {
+    const Rec& r = all[i];
+    if (!r.is_paired() && force_paired) continue;
+    if (!r.cb) continue;
+    if (!r.umi) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
+    if (r.umi_len == 10 && !memcmp(r.umi, "AAAAAAAAAA", 10)) continue;
+    if (r.umi_len == 0) return collect_groups_serial(z, force_paired, threads, stream, gstart);
+    kept.push_back((u32)i);
+  }
+  stream.clear(); gstart.assign(1, 0);
+  if (kept.empty()) { gstart.push_back(0); return NB_OK; }   // the producer sends one (empty) group when there is nothing at all
+  std::vector<size_t> run;   // start of every UMI run in `kept`
+  for (size_t j = 0; j < kept.size(); j++) if (j == 0 || !same(all[kept[j]].umi, all[kept[j]].umi_len, all[kept[j - 1]].umi, all[kept[j - 1]].umi_len)) run.push_back(j);
+  const size_t nr = run.size(); run.push_back(kept.size());
+  const int T = std::max(1, std::min<int>(threads, (int)((nr + 63) / 64)));
+  std::vector<std::vector<Rec>> outs(T); std::vector<size_t> first_empty(T, (size_t)-1);
+  parallel_ranges(T, nr, [&](size_t ra, size_t rb, int) {
+    size_t t = 0; for (int k = 0; k < T; k++) if (nr * (size_t)k / T == ra) t = k;   // the slice parallel_ranges gave this thread
+    std::vector<Rec>& out = outs[t]; std::vector<Rec> buf, tmp;
+    for (size_t r = ra; r < rb; r++) {
+      buf.clear(); for (size_t j = run[r]; j < run[r + 1]; j++) buf.push_back(all[kept[j]]);
+      if (r + 1 != nr) std::stable_sort(buf.begin(), buf.end(), [](const Rec& a, const Rec& b) { return cmp_bytes(a.cb, a.cb_len, b.cb, b.cb_len) < 0; });   // the file's last buffer is not sorted (quirk kept)
+      if (!force_paired) { tmp.clear(); for (const Rec& x : buf) { Rec m = x; m.skip_align = 0; tmp.push_back(m); if (!x.is_paired()) { Rec d = x; d.skip_align = 1; tmp.push_back(d); } } buf.swap(tmp); }
+      size_t before = out.size(), i = 0;
+      while (i + 1 < buf.size()) {   // filter_paired_reads
+        if (same(buf[i].qname_ptr(), buf[i].qname_len(), buf[i + 1].qname_ptr(), buf[i + 1].qname_len())) {
+          if (buf[i].is_first()) { out.push_back(buf[i]); out.push_back(buf[i + 1]); } else { out.push_back(buf[i + 1]); out.push_back(buf[i]); }
+          i += 2;
+        } else i += 1;
+      }
+      if (out.size() == before) { first_empty[t] = r; return; }   // next() returns None on an empty buffer: the stream ends here
+    }
+  });
+  size_t total = 0; for (int t = 0; t < T; t++) { total += outs[t].size(); if (first_empty[t] != (size_t)-1) break; }
+  stream.reserve(total);
+  for (int t = 0; t < T; t++) { stream.insert(stream.end(), outs[t].begin(), outs[t].end()); std::vector<Rec>().swap(outs[t]); if (first_empty[t] != (size_t)-1) break; }
+  if (stream.empty()) { gstart.push_back(0); return NB_OK; }
+  // groups: runs of equal (UMI + CB[..len-2]) over the stream
+  std::vector<char> head(stream.size(), 0);
+  parallel_ranges(threads, stream.size(), [&](size_t a, size_t b, int) { for (size_t j = a; j < b; j++) head[j] = (j == 0 || !key_equal(stream[j - 1], stream[j])) ? 1 : 0; });
+  gstart.clear();
+  for (size_t j = 0; j < stream.size(); j++) if (head[j]) gstart.push_back(j);
+  gstart.push_back(stream.size());
+  if (gstart.size() > 2) { stream.resize(gstart[gstart.size() - 2]); gstart.pop_back(); }   // the last group is never sent when a group was sent before
   return NB_OK;
 }
 

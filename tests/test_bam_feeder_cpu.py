@@ -37,3 +37,20 @@ def test_feeder_groups_match_python_restatement(tmp_path, force_paired):
         assert any(it["f"][36] == "" for it in flat)                  # UB missing -> grouped by UR
     else:
         assert all(it["f"][37] == "" and it["f"][4] == "true" for it in flat)   # -p: no dummies, no SKIP_ALIGN aux
+
+
+@pytest.mark.parametrize("force_paired", [False, True])
+def test_parallel_grouping_equals_the_serial_readers(tmp_path, force_paired):
+    """collect_groups restates SortedBamReader / UMIReader over whole UMI runs on several threads; the serial readers
+    (kept in the library, NB_BAM_SERIAL_GROUPING=1) define the semantics.  Same dump on a BAM with thousands of groups."""
+    L = synth.SynthLibrary(seed=99, n_fam=20, n_all=5)
+    bam = make_bam(str(tmp_path / "big.bam"), L, n_groups=4000, seed=5)
+    a, b = str(tmp_path / "par.tsv"), str(tmp_path / "ser.tsv")
+    nb.bam_dump_groups(bam, a, force_bam_paired=force_paired, num_cores=8)
+    os.environ["NB_BAM_SERIAL_GROUPING"] = "1"
+    try:
+        nb.bam_dump_groups(bam, b, force_bam_paired=force_paired, num_cores=8)
+    finally:
+        del os.environ["NB_BAM_SERIAL_GROUPING"]
+    pa, se = open(a, "rb").read(), open(b, "rb").read()
+    assert pa == se and pa.count(b"\n") > (500 if force_paired else 5000)
