@@ -465,6 +465,7 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
     if (rc == NB_OK && !trims.empty()) { nb_config c; nb_library_get_config(libs[i], &c); c.trim_target_length = trims[i].first; c.trim_strictness = trims[i].second; rc = nb_library_set_config(libs[i], &c); }
     if (rc == NB_OK) rc = nb_index_build(libs[i], threads, &idx[i]);
     if (rc == NB_OK) rc = nb_ctx_create(idx[i], libs[i], device, nullptr, &ctx[i]);
+    if (rc == NB_OK) rc = nb_ctx_set_option(ctx[i], "agg_slots", 1u << 23);   // a batch of 2^20 pairs can hold that many one-pair scopes, each with its own (scope, callset) row: stay under half full
     if (rc == NB_OK) { outs[i] = fopen(output_paths[i], "wb"); if (!outs[i]) rc = fail(NB_ERR_IO, std::string("could not open output ") + output_paths[i]); }
   }
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
