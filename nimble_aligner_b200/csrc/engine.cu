@@ -471,7 +471,7 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
     CK(cudaMemcpyAsync(c->d_dense.p, dense.data(), dense.size() * 4, cudaMemcpyHostToDevice, s));
     u64* d_keys = (u64*)c->d_rowwork.p; i64* d_vals = (i64*)((char*)c->d_rowwork.p + n_agg * 16); void* d_tmp = (char*)c->d_rowwork.p + work;
     u32* d_scope = (u32*)c->d_rowout.p; u32* d_callset = d_scope + n_agg; i64* d_count = (i64*)((char*)c->d_rowout.p + 8 * n_agg);
-    nbk::launch_rows_sort(d_agg, n_agg, (const u32*)c->d_dense.p, d_keys, d_vals, d_tmp, tb, d_scope, d_callset, d_count, s); c->all_launches += 3;
+    nbk::launch_rows_sort(d_agg, n_agg, (const u32*)c->d_dense.p, d_keys, d_vals, d_tmp, tb, d_scope, d_callset, d_count, c->mode == 1 ? 56 : 24, s); c->all_launches += 3;
     CK(cudaMemcpyAsync(c->h_rows, c->d_rowout.p, n_agg * 16, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   }

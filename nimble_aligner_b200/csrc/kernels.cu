@@ -587,10 +587,10 @@ void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const 
 }
 size_t rows_sort_tmp_bytes(u64 n) { size_t tb = 0; cub::DeviceRadixSort::SortPairs(nullptr, tb, (const u64*)nullptr, (u64*)nullptr, (const i64*)nullptr, (i64*)nullptr, (int)n, 0, 56); return tb + 256; }
 // work: 2n u64 keys + 2n i64 values + temp; out: n u32 + n u32 + n i64 (all device)
-void launch_rows_sort(const u64* agg, u64 n, const u32* dense, u64* keys, i64* vals, void* tmp, size_t tmp_bytes, u32* scope, u32* callset, i64* count, cudaStream_t s) {
+void launch_rows_sort(const u64* agg, u64 n, const u32* dense, u64* keys, i64* vals, void* tmp, size_t tmp_bytes, u32* scope, u32* callset, i64* count, int key_bits, cudaStream_t s) {
   if (!n) return;
   k_rows_remap<<<blocks_for(n, 256), 256, 0, s>>>(agg, n, dense, keys, vals);
-  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const u64*)keys, keys + n, (const i64*)vals, vals + n, (int)n, 0, 56, s);
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const u64*)keys, keys + n, (const i64*)vals, vals + n, (int)n, 0, key_bits, s);   // whole-run scope: 24 key bits = 3 passes instead of 7
   k_rows_split<<<blocks_for(n, 256), 256, 0, s>>>(keys + n, vals + n, n, scope, callset, count);
 }
 void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s) {

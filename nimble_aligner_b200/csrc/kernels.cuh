@@ -92,7 +92,7 @@ void launch_pack(const BatchDev& b, cudaStream_t s);
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s);
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s);
 size_t rows_sort_tmp_bytes(u64 n);
-void launch_rows_sort(const u64* agg, u64 n, const u32* dense, u64* keys, i64* vals, void* tmp, size_t tmp_bytes, u32* scope, u32* callset, i64* count, cudaStream_t s);
+void launch_rows_sort(const u64* agg, u64 n, const u32* dense, u64* keys, i64* vals, void* tmp, size_t tmp_bytes, u32* scope, u32* callset, i64* count, int key_bits, cudaStream_t s);
 void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s);
 void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s);
 void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s);
