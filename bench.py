@@ -94,10 +94,10 @@ class ClockSampler:
         return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(rows)}
 
 
-def build_library():
+def build_library(mismatches=0):
     import synth
     import nimble_aligner_b200 as nb
-    L = synth.SynthLibrary(seed=SEED, n_fam=200, n_all=5, group_on="")
+    L = synth.SynthLibrary(seed=SEED, n_fam=200, n_all=5, group_on="", num_mismatches=mismatches)
     obj = L.to_json_obj()
     lib = nb.Library.from_text(json.dumps(obj), "unstranded")
     return L, obj, lib
@@ -110,7 +110,7 @@ def run_reference(args):
         return
     import oracle as orc
     import synth
-    L = synth.SynthLibrary(seed=SEED, n_fam=200, n_all=5, group_on="")
+    L = synth.SynthLibrary(seed=SEED, n_fam=200, n_all=5, group_on="", num_mismatches=args.mismatches)
     ocfg, oref = orc.parse_reference_library(L.to_json_obj(), "unstranded")
     o = orc.Oracle(ocfg, oref, faithful_cost=True)
     cores = os.cpu_count() or 1
@@ -126,7 +126,7 @@ def run_reference(args):
     sample = "%d of the 10M C2 pairs per step (pairs 0..%d of the same seeded stream), %d threads over contiguous shards" % (n, n, cores)
     emit_json({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer (f64 thresholds)",
-                      "data": "synthetic", "config": {"workload": "C2: 1k-transcript family library x 2x150 bp pairs, FASTQ-mode scope", "sample_pairs": n},
+                      "data": "synthetic", "config": {"workload": "C2: 1k-transcript family library x 2x150 bp pairs, FASTQ-mode scope", "sample_pairs": n, "num_mismatches": args.mismatches},
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="N>1: check the merged counts against one GPU over the union of shards")
+    ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="N>1: key records routed inside k_pair over NVLink peer stores (default), or exchanged with an NCCL all-to-all when the job ends")
+    ap.add_argument("--mismatches", type=int, default=0, help="num_mismatches of the library config (C5 sweeps 0/1/2)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
@@ -181,7 +183,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.pairs
     cores = os.cpu_count() or 1
-    L, obj, lib = build_library()
+    L, obj, lib = build_library(args.mismatches)
     t0 = time.time()
     ix = nb.build_index(lib, max(1, cores // max(1, world)))
     index_build_s = time.time() - t0
@@ -202,14 +204,15 @@ def main():
     d1, d2, do1, do2 = h1.cuda(), h2.cuda(), ho1.cuda(), ho2.cuda()
     n_reads = 2 * n
 
-    from nimble_aligner_b200.multigpu import merge_across_ranks, DeviceShard
-    shard = DeviceShard(ctx, nb, torch, pair_base, n) if world > 1 else None   # merge buffers are allocated once, outside the job
+    from nimble_aligner_b200.multigpu import merge_across_ranks, DeviceShard, setup_routes
+    routed = world > 1 and args.merge == "p2p" and setup_routes(ctx, torch, dist, rank, world, "cuda", pair_base, n + n // 4)
+    shard = DeviceShard(ctx, nb, torch, pair_base, n, routed=routed) if world > 1 else None   # merge buffers are allocated once, outside the job
 
     def step_device():
         ctx.reset()
         ctx.align_batch(d1, do1, d2, do2, n_pairs=n, max_read_len=READ_LEN, location=nb.NB_MEM_DEVICE)
         if world > 1:
-            return merge_across_ranks(shard, torch, dist, rank, world, "cuda")
+            return merge_across_ranks(shard, torch, dist, rank, world, "cuda", routed=routed)
         raw = ctx.counts_raw()          # nb_counts_finalize: the job's result (group indices + counts) on the host
         return raw, raw["n_unique_keys"]
 
@@ -220,7 +223,7 @@ def main():
         import ctypes as C
         nb._ck(nb.lib().nb_align_batch(ctx.h, C.byref(b), None, None))
         if world > 1:
-            return merge_across_ranks(shard, torch, dist, rank, world, "cuda")
+            return merge_across_ranks(shard, torch, dist, rank, world, "cuda", routed=routed)
         raw = ctx.counts_raw()          # nb_counts_finalize: the job's result (group indices + counts) on the host
         return raw, raw["n_unique_keys"]
 
@@ -293,6 +296,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer (f64 thresholds)", "data": "synthetic",
            "config": {"workload": "C2: synthetic 1k-transcript family library (200x5, seed 1234) x %d 2x150 bp pairs per GPU, FASTQ-mode whole-run scope" % n,
+                      "num_mismatches": args.mismatches, "merge": ("p2p-routed (k_pair stores key records into their owners' inboxes over NVLink)" if routed else "nccl all-to-all at job end") if world > 1 else "none (one GPU)",
                       "pairs_per_gpu": n, "reads_per_step": n_reads * world, "chunk_pairs": args.chunk, "l2": "inputs (%.1f GB ASCII per step) exceed the 126 MB L2" % ((int(o1[-1]) + int(o2[-1])) / 1e9),
                       "index_device_mb": ix.stats()["device_bytes"] / 1e6, "index_build_s": index_build_s, "unique_pair_keys": int(uniq_dev), "callsets_counted": len(counts_dev)},
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_host},

@@ -109,6 +109,12 @@ _SIGS = {
     "nb_keys_export_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "nb_callsets_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "nb_callsets_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "nb_route_create": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "nb_route_attach_ipc": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "nb_route_attach_ctx": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "nb_route_set_pair_base": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "nb_route_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "nb_route_detach": (C.c_int, [C.c_void_p]),
     "nb_ctx_kernel_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "nb_ctx_work_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),
@@ -414,6 +420,33 @@ class Context:
 
     def reset(self):
         _ck(lib().nb_counts_reset(self.h))
+
+    # ---- peer routing of the whole-run scope (nb_route_*)
+    def route_create(self, inbox_records):
+        """Allocates the inbox; returns its 64-byte CUDA IPC handle (np.uint8[64])."""
+        h = np.zeros(64, dtype=np.uint8)
+        _ck(lib().nb_route_create(self.h, int(inbox_records), h.ctypes.data))
+        return h
+
+    def route_attach_ipc(self, world, rank, handles, inbox_records, pair_index_base):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        assert handles.size == 64 * world
+        _ck(lib().nb_route_attach_ipc(self.h, world, rank, handles.ctypes.data, int(inbox_records), int(pair_index_base)))
+
+    def route_attach_ctx(self, world, rank, peers, pair_index_base):
+        arr = (C.c_void_p * world)(*[p.h for p in peers])
+        _ck(lib().nb_route_attach_ctx(self.h, world, rank, arr, int(pair_index_base)))
+
+    def route_set_pair_base(self, pair_index_base):
+        _ck(lib().nb_route_set_pair_base(self.h, int(pair_index_base)))
+
+    def route_import(self):
+        n = C.c_uint64(0)
+        _ck(lib().nb_route_import(self.h, C.byref(n)))
+        return n.value
+
+    def route_detach(self):
+        _ck(lib().nb_route_detach(self.h))
 
     def kernel_stats(self, reset=False):
         o = np.zeros(4, dtype=np.float64)

@@ -88,6 +88,8 @@ struct nb_ctx {
   std::vector<u32> cs_items, slot_dense; std::vector<u64> cs_off;
   u8* h_rows = nullptr; size_t h_rows_cap = 0; u64 n_rows_dev = 0;   // pinned: row_scope | row_callset | row_count of the last finalize
   DBuf d_rowwork, d_rowout, d_dense;
+  // peer routing of the whole-run scope (nb_route_*): own inbox = {cursor u64 @0, KeyRec records @256}
+  DBuf d_inbox; u64 inbox_cap = 0; bool route_on = false; nbk::Route route; std::vector<void*> ipc_opened;
 };
 
 static Tables make_tables(nb_ctx* c) {
@@ -146,6 +148,7 @@ static int check_device_errors(nb_ctx* c, Counters* out = nullptr) {
   if (h.err & nbk::E_CS_FULL) return fail(NB_ERR_OVERFLOW, "callset dictionary full: raise option callset_slots");
   if (h.err & nbk::E_KEY_FULL) return fail(NB_ERR_OVERFLOW, "read-key table full: raise option key_slots");
   if (h.err & nbk::E_AGG_FULL) return fail(NB_ERR_OVERFLOW, "count table full: raise option agg_slots");
+  if (h.err & nbk::E_INBOX_FULL) return fail(NB_ERR_OVERFLOW, "a peer's routing inbox is full: create the routes with more inbox_records");
   return NB_OK;
 }
 
@@ -220,6 +223,8 @@ void nb_ctx_free(nb_ctx* c) {
                  &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].scope, &c->stg[0].cell,
                  &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded, &c->d_rowwork, &c->d_rowout, &c->d_dense};
   for (DBuf* b : all) b->release();
+  for (void* q : c->ipc_opened) cudaIpcCloseMemHandle(q);
+  c->ipc_opened.clear(); c->d_inbox.release();
   nb_host_free(c->h_rows); c->h_rows = nullptr;
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -335,7 +340,9 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   nbk::launch_map(b, c->dix, c->dcfg, t, c->count_work, s); c->all_launches++;
   CK(cudaEventRecord(ev.second, s));
   c->ev_pending.push_back(ev); c->map_launches++; c->map_reads += nr;
-  nbk::launch_pair(b, c->dix, c->dlib, c->dcfg, t, s); c->all_launches++;
+  nbk::Route rt; memset(&rt, 0, sizeof rt);
+  if (c->route_on && c->mode == 0) rt = c->route;
+  nbk::launch_pair(b, c->dix, c->dlib, c->dcfg, t, rt, s); c->all_launches++;
   if (c->mode == 1) {
     nbk::launch_fold(t, b.cell, b.order_base, s); c->all_launches++;
     if (pairs_out) { nbk::launch_resolve(b, t, s); c->all_launches++; }
@@ -602,6 +609,107 @@ int nb_keys_import(nb_ctx* c, const void* dev_records, uint64_t n) {
   CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
   nbk::launch_keys_import(make_tables(c), dev_records, n, s); c->all_launches++;
   c->folded = false;
+  return check_device_errors(c);
+}
+
+// ---- peer routing of the whole-run scope over NVLink (kernels.cuh Route; DESIGN.md "Multi-GPU")
+int nb_route_create(nb_ctx* c, uint64_t inbox_records, void* ipc_handle_out) {
+  if (!c || inbox_records == 0) return fail(NB_ERR_INVALID, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == NB_ROUTE_HANDLE_BYTES, "IPC handle size");
+  CK(cudaSetDevice(c->device));
+  if (c->route_on) return fail(NB_ERR_INVALID, "routes are attached; call nb_route_detach first");
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->d_inbox.p && c->inbox_cap < inbox_records) c->d_inbox.release();
+  if (!c->d_inbox.p) { CK(c->d_inbox.ensure(256 + inbox_records * sizeof(nbk::KeyRec), c->stream)); c->inbox_cap = inbox_records; }
+  CK(cudaMemsetAsync(c->d_inbox.p, 0, 256, c->stream)); CK(cudaStreamSynchronize(c->stream));
+  if (ipc_handle_out) { cudaIpcMemHandle_t h; CK(cudaIpcGetMemHandle(&h, c->d_inbox.p)); memcpy(ipc_handle_out, &h, sizeof h); }
+  return NB_OK;
+}
+static int route_fill(nb_ctx* c, u32 world, u32 rank, void* const* bases, const u64* caps, u64 pair_index_base) {
+  nbk::Route& r = c->route; memset(&r, 0, sizeof r);
+  r.world = world; r.rank = rank; r.pair_base = pair_index_base; r.cap = ~0ULL;
+  for (u32 i = 0; i < world; i++) {
+    r.cursor[i] = (unsigned long long*)bases[i]; r.inbox[i] = (nbk::KeyRec*)((char*)bases[i] + 256);
+    r.cap = std::min<u64>(r.cap, caps[i]);
+  }
+  c->route_on = world > 1;
+  return NB_OK;
+}
+int nb_route_attach_ipc(nb_ctx* c, uint32_t world, uint32_t rank, const void* handles, uint64_t inbox_records, uint64_t pair_index_base) {
+  if (!c || !handles || world == 0 || world > (u32)nbk::ROUTE_MAX || rank >= world) return fail(NB_ERR_INVALID, "bad argument (world <= 16)");
+  if (!c->d_inbox.p) return fail(NB_ERR_INVALID, "nb_route_create first");
+  if (c->route_on) return fail(NB_ERR_INVALID, "routes already attached");
+  CK(cudaSetDevice(c->device));
+  void* bases[nbk::ROUTE_MAX]; u64 caps[nbk::ROUTE_MAX];
+  for (u32 i = 0; i < world; i++) {
+    caps[i] = i == rank ? c->inbox_cap : inbox_records;
+    if (i == rank) { bases[i] = c->d_inbox.p; continue; }
+    cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + (size_t)i * sizeof h, sizeof h);
+    void* q = nullptr; cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (void* o : c->ipc_opened) cudaIpcCloseMemHandle(o);
+      c->ipc_opened.clear();
+      return fail(NB_ERR_CUDA, std::string("cudaIpcOpenMemHandle failed for rank ") + std::to_string(i) + ": " + cudaGetErrorString(e));
+    }
+    c->ipc_opened.push_back(q); bases[i] = q;
+  }
+  return route_fill(c, world, rank, bases, caps, pair_index_base);
+}
+int nb_route_attach_ctx(nb_ctx* c, uint32_t world, uint32_t rank, nb_ctx* const* peers, uint64_t pair_index_base) {
+  if (!c || !peers || world == 0 || world > (u32)nbk::ROUTE_MAX || rank >= world || peers[rank] != c) return fail(NB_ERR_INVALID, "bad argument (world <= 16, peers[rank] must be this context)");
+  if (c->route_on) return fail(NB_ERR_INVALID, "routes already attached");
+  CK(cudaSetDevice(c->device));
+  void* bases[nbk::ROUTE_MAX]; u64 caps[nbk::ROUTE_MAX];
+  for (u32 i = 0; i < world; i++) {
+    if (!peers[i] || !peers[i]->d_inbox.p) return fail(NB_ERR_INVALID, "every peer needs nb_route_create first");
+    if (peers[i]->device != c->device) {
+      int can = 0; CK(cudaDeviceCanAccessPeer(&can, c->device, peers[i]->device));
+      if (!can) return fail(NB_ERR_CUDA, "no peer access between the devices of two routed contexts");
+      cudaError_t e = cudaDeviceEnablePeerAccess(peers[i]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(NB_ERR_CUDA, cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    bases[i] = peers[i]->d_inbox.p; caps[i] = peers[i]->inbox_cap;
+  }
+  return route_fill(c, world, rank, bases, caps, pair_index_base);
+}
+int nb_route_set_pair_base(nb_ctx* c, uint64_t pair_index_base) { if (!c) return fail(NB_ERR_INVALID, "null argument"); c->route.pair_base = pair_index_base; return NB_OK; }
+int nb_route_detach(nb_ctx* c) {
+  if (!c) return fail(NB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+  for (void* q : c->ipc_opened) cudaIpcCloseMemHandle(q);
+  c->ipc_opened.clear(); c->route_on = false; memset(&c->route, 0, sizeof c->route);
+  return NB_OK;
+}
+// Merge the records peers appended to this context's inbox into its key table (same "later duplicate wins" rule as
+// k_pair) and empty the inbox.  Every peer must have finished its nb_align_batch calls of this job AND this rank must
+// know it (any collective or barrier after the peers' last batch does); the callsets the records name must already be
+// in this context's dictionary (nb_callsets_import of the peers' rows first).
+int nb_route_import(nb_ctx* c, uint64_t* n_imported) {
+  if (!c) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->d_inbox.p) return fail(NB_ERR_INVALID, "nb_route_create first");
+  CK(cudaSetDevice(c->device));
+  if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
+  if (c->mode == 1) return fail(NB_ERR_INVALID, "routing applies to the whole-run scope only");
+  c->mode = 0;
+  cudaStream_t s = c->stream;
+  unsigned long long n = 0;
+  CK(cudaMemcpyAsync(&n, c->d_inbox.p, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+  if (n > c->inbox_cap) return fail(NB_ERR_OVERFLOW, "routing inbox overflow: create the routes with more inbox_records");
+  if (2 * (c->keys_upper + n) > c->key_slots) {
+    CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
+    nbk::launch_count_keys(make_tables(c), s); c->all_launches++;
+    Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
+    CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
+    c->keys_upper = h.n_keys;
+    if (2 * (c->keys_upper + n) > c->key_slots) { rc = grow_keys(c, 2 * (c->keys_upper + n)); if (rc) return rc; }
+  }
+  c->keys_upper += n;
+  nbk::launch_keys_import(make_tables(c), (const char*)c->d_inbox.p + 256, n, s); c->all_launches++;
+  CK(cudaMemsetAsync(c->d_inbox.p, 0, 8, s));
+  c->folded = false;
+  if (n_imported) *n_imported = n;
   return check_device_errors(c);
 }
 

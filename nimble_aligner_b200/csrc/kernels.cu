@@ -23,11 +23,25 @@ __host__ __device__ __forceinline__ u64 mix64(u64 x) {
 // realigned in registers (word select + funnel shift); 4 bases are classified per SIMD-in-register compare (non-ACGT
 // -> A like DnaString::from_acgt_bytes).  (Nine 4-byte loads per thread ran at 2.4 TB/s; staging the block's span in
 // shared memory was slower still — 8-way bank conflicts on the 32-byte-stride reads.)
-__device__ __forceinline__ u32 codes4(u32 v) {
+__device__ __forceinline__ u32 codes4(u32 v) {   // exact for any byte values: the fall-back of codes4_fast
   u32 u = v & 0xDFDFDFDFu;
   u32 c4 = (__vcmpeq4(u, 0x43434343u) & 0x01010101u) | (__vcmpeq4(u, 0x47474747u) & 0x02020202u) | (__vcmpeq4(u, 0x54545454u) & 0x03030303u);
   c4 = (c4 | (c4 >> 6)) & 0x000F000Fu;
   return (c4 | (c4 >> 12)) & 0xFFu;
+}
+// Four bases in about a dozen instructions.  For the eight valid letters the code is bits (1^2, 2^3) of the byte
+// (A 0x41 -> 0, C 0x43 -> 1, G 0x47 -> 2, T 0x54 -> 3, bit 5 = case is never looked at); one multiply gathers the four
+// 2-bit codes into the product's top byte (shifts 24/18/12/6: no two partial products overlap, so nothing carries).
+// Validity is checked bitwise: bits 7,6,3 must read 0,1,0 and (bit4,bit2,bit1,bit0) must be 0001/0011/0111 (A/C/G) or
+// 1100 (T) <=> T(b0,b1,b2) & (b0 ^ b4) with T = b0 ? (!b2 | b1) : (b2 & !b1).  Offending bits accumulate in `bad`; the
+// caller redoes the whole word with codes4 when any are set (non-ACGT -> A, rare).
+__device__ __forceinline__ u32 codes4_fast(u32 v, u32& bad) {
+  u32 s1 = v >> 1, s2 = v >> 2, s4 = v >> 4;
+  u32 code = (s1 ^ s2) & 0x03030303u;
+  u32 t = (v & (~s2 | s1)) | (~v & s2 & ~s1);
+  u32 ok = t & (v ^ s4);
+  bad |= (~ok & 0x01010101u) | ((v & 0xC8C8C8C8u) ^ 0x40404040u);
+  return code * 0x01041040u;   // top byte = the four codes, first base in the low bits
 }
 __device__ __forceinline__ u64 rev2(u64 x) {  // reverse the order of the 32 2-bit groups
   x = __brevll(x);
@@ -49,7 +63,7 @@ __global__ void __launch_bounds__(256) k_pack(BatchDev b) {
     const u8* addr = b.a[side] + src;
     const uint4* al = (const uint4*)((uintptr_t)addr & ~(uintptr_t)15);
     u32 sh = (u32)((uintptr_t)addr & 15), need = sh + cnt;   // bytes wanted from al on: <= 47
-    uint4 c0 = __ldg(al), c1 = make_uint4(0, 0, 0, 0), c2 = c1;
+    uint4 c0 = __ldg(al), c1 = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u), c2 = c1;
     if (need > 16) c1 = __ldg(al + 1);
     if (need > 32) c2 = __ldg(al + 2);
     u32 wv[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
@@ -63,10 +77,18 @@ __global__ void __launch_bounds__(256) k_pack(BatchDev b) {
       for (int j = 0; j < 11; j++) wv[j] = wv[j + 1];
       wv[11] = 0;
     }
+    // bytes behind the read's end (the next read's bases, or the 'A' fill of a chunk that was not needed) are classified
+    // too and masked off below; only a non-ACGT byte anywhere in the 32 sends the word through the exact path
+    u32 al4[8], pr[8], bad = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      u32 v = __funnelshift_r(wv[j], wv[j + 1], (sh & 3) * 8);
-      word |= (u64)codes4(v) << (8 * j);
+    for (int j = 0; j < 8; j++) { al4[j] = __funnelshift_r(wv[j], wv[j + 1], (sh & 3) * 8); pr[j] = codes4_fast(al4[j], bad); }
+    if (bad == 0) {
+      u32 lo = __byte_perm(__byte_perm(pr[0], pr[1], 0x0073), __byte_perm(pr[2], pr[3], 0x0073), 0x5410);
+      u32 hi = __byte_perm(__byte_perm(pr[4], pr[5], 0x0073), __byte_perm(pr[6], pr[7], 0x0073), 0x5410);
+      word = (u64)lo | ((u64)hi << 32);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) word |= (u64)codes4(al4[j]) << (8 * j);
     }
     if (cnt < 32) word &= (1ULL << (2 * cnt)) - 1;
     if (rc) { word = rev2(word) >> (64 - 2 * cnt); word ^= cnt < 32 ? ((1ULL << (2 * cnt)) - 1) : ~0ULL; }
@@ -308,7 +330,10 @@ __device__ __forceinline__ u32 callset_intern(const Tables& t, const u32* g, u32
   return NONE32;
 }
 
-__global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L, DevCfg cfg, Tables t) {
+// owning rank of a read_key in a multi-GPU whole-run scope: a 16-bit slice of key_lo mod world
+__device__ __forceinline__ u32 key_owner(u64 k0, u32 world) { return (u32)((k0 >> 40) & 0xFFFFu) % world; }
+
+__global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L, DevCfg cfg, Tables t, Route rt) {
   u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (p >= b.n_pairs) return;
   bool paired = b.sides == 2;
@@ -399,13 +424,36 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
   // ---- score_map.insert(read_key, ...): later duplicates overwrite (src/align.rs:685) => keep the highest order.
   // Scoped (BAM) batches also register non-insertable pairs: filter_reasons is keyed by read_key for every pair
   // (src/align.rs:586-600) and k_resolve reports per-key outcomes.
-  if (out.insertable || scoped) {
+  // Whole-run scope sharded over ranks (rt.world > 1): orders are global pair indices and a key this rank does not own
+  // goes to its owner's inbox over NVLink — one remote atomicAdd per (warp, owner) reserves the slots, then each lane
+  // stores its 32-byte record; the owner merges its inbox when the job ends (nb_route_import).
+  const bool routed = rt.world > 1 && !scoped;
+  u32 owner = routed ? key_owner(h0, rt.world) : 0u;
+  bool send = routed && out.insertable && owner != rt.rank;
+  if ((out.insertable || scoped) && !send) {
     u64 slot = key_insert(t, h0, h1);
     if (slot == ~0ULL) atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL);
     else {
-      unsigned long long ord1 = b.order_base + p + 1;
+      unsigned long long ord1 = (routed ? rt.pair_base : 0ULL) + b.order_base + p + 1;
       if (out.insertable) atomicMax(t.kval + slot, (ord1 << 24) | cs);
       if (scoped) { atomicMax(t.klast + slot, ord1); b.pslot[p] = slot; }
+    }
+  }
+  if (routed) {
+    unsigned sm = __ballot_sync(__activemask(), send);
+    if (send) {
+      unsigned peers = __match_any_sync(sm, owner); u32 lane = threadIdx.x & 31; int leader = __ffs(peers) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(rt.cursor[owner], (unsigned long long)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      u64 at = base + __popc(peers & ((1u << lane) - 1));
+      if (at >= rt.cap) atomicOr(&t.ctr->err, (unsigned)E_INBOX_FULL);
+      else {
+        KeyRec r; r.k0 = h0; r.k1 = h1; r.order = rt.pair_base + b.order_base + p; r.tag = cs == CS_NONE ? 0ULL : t.cs_tag[cs];
+        uint4* dst = (uint4*)(rt.inbox[owner] + at);
+        dst[0] = make_uint4((u32)r.k0, (u32)(r.k0 >> 32), (u32)r.k1, (u32)(r.k1 >> 32));
+        dst[1] = make_uint4((u32)r.order, (u32)(r.order >> 32), (u32)r.tag, (u32)(r.tag >> 32));
+      }
     }
   }
   b.pres[p] = out;
@@ -476,7 +524,6 @@ __global__ void __launch_bounds__(256) k_rehash_keys(Tables o, Tables n) {
   n.kval[slot] = o.kval[idx];
 }
 
-struct KeyRec { u64 k0, k1, order, tag; };
 __global__ void __launch_bounds__(256) k_keys_export(Tables t, KeyRec* rec, unsigned long long* n_out, u64 cap, u64 order_base) {
   u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (idx > t.key_mask) return;
@@ -509,7 +556,6 @@ __global__ void __launch_bounds__(256) k_keys_import(Tables t, const KeyRec* rec
 
 // ---- multi-GPU exchange helpers: key records grouped by owning rank (owner = a 16-bit slice of key_lo mod world), so the
 // host can hand them to an all-to-all without sorting; warp-aggregated cursors (a handful of hot counters otherwise)
-__device__ __forceinline__ u32 key_owner(u64 k0, u32 world) { return (u32)((k0 >> 40) & 0xFFFFu) % world; }
 __global__ void __launch_bounds__(256) k_keys_count_owner(Tables t, u32 world, unsigned long long* counts) {
   u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   bool occ = false; u32 owner = 0;
@@ -593,8 +639,8 @@ void launch_rows_sort(const u64* agg, u64 n, const u32* dense, u64* keys, i64* v
   cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const u64*)keys, keys + n, (const i64*)vals, vals + n, (int)n, 0, key_bits, s);   // whole-run scope: 24 key bits = 3 passes instead of 7
   k_rows_split<<<blocks_for(n, 256), 256, 0, s>>>(keys + n, vals + n, n, scope, callset, count);
 }
-void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s) {
-  if (b.n_pairs) k_pair<<<blocks_for(b.n_pairs, 128), 128, 0, s>>>(b, ix, lib, cfg, t);
+void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, const Route& rt, cudaStream_t s) {
+  if (b.n_pairs) k_pair<<<blocks_for(b.n_pairs, 128), 128, 0, s>>>(b, ix, lib, cfg, t, rt);
 }
 void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s) { k_fold<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, cell_of_pair, order_base); }
 void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_pairs) k_resolve<<<blocks_for(b.n_pairs, 256), 256, 0, s>>>(b, t); }

@@ -45,7 +45,7 @@ struct DevCfg {
   u32 discard_multi_hits, max_hits, gcap, min_read_len;
 };
 // device-side error bits (Counters::err)
-enum { E_ARENA = 1, E_CS_FULL = 2, E_KEY_FULL = 4, E_FEATURE = 8, E_AGG_FULL = 16, E_GCAP = 32 };
+enum { E_ARENA = 1, E_CS_FULL = 2, E_KEY_FULL = 4, E_FEATURE = 8, E_AGG_FULL = 16, E_GCAP = 32, E_INBOX_FULL = 64 };
 struct Counters {
   unsigned long long arena_top, queue, seeded_n, wqueue;   // all four zeroed before every map launch (seeded_n / wqueue: k_seed -> k_walk list)
   unsigned long long n_keys; unsigned long long n_callsets; unsigned long long n_agg;
@@ -88,12 +88,21 @@ struct Tables {
   const u16* mincov;   // mincov[n] = smallest coverage c with (double)c / (double)n >= score_percent (exact stand-in for the f64 division)
 };
 
+// De-duplication record exchanged between ranks: {key_lo, key_hi, global pair order, callset tag (0: none)}
+struct KeyRec { u64 k0, k1, order, tag; };
+// Peer routing of the whole-run scope (DESIGN.md "Multi-GPU"): every read_key has an owning rank; k_pair inserts the keys
+// this rank owns into its own table and appends the others straight into the owner's inbox over NVLink (peer stores),
+// so the exchange rides along with the alignment instead of following it.  inbox[r] / cursor[r] are peer pointers
+// (cudaIpcOpenMemHandle, or plain device pointers of contexts in the same process); world <= 1: routing off.
+constexpr int ROUTE_MAX = 16;
+struct Route { u32 world, rank; u64 pair_base, cap; KeyRec* inbox[ROUTE_MAX]; unsigned long long* cursor[ROUTE_MAX]; };
+
 void launch_pack(const BatchDev& b, cudaStream_t s);
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s);
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s);
 size_t rows_sort_tmp_bytes(u64 n);
 void launch_rows_sort(const u64* agg, u64 n, const u32* dense, u64* keys, i64* vals, void* tmp, size_t tmp_bytes, u32* scope, u32* callset, i64* count, int key_bits, cudaStream_t s);
-void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, cudaStream_t s);
+void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, const Route& rt, cudaStream_t s);
 void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s);
 void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s);
 void launch_compact(const Tables& t, u64* agg_out, u64 agg_cap, u32* cs_out, u64 cs_cap, unsigned long long* n_out2, cudaStream_t s);

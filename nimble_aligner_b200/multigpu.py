@@ -9,6 +9,8 @@ must meet on one rank: every key has an owner (a slice of its 128-bit value mod 
   (3) one all_to_all of the key records {key_lo, key_hi, global pair order, callset tag}; each rank re-imports its
       partition with the "later duplicate wins" rule and folds it,
   (4) one all_reduce of the dense per-callset counts (+ the unique-key count in the last element).
+With peer routing (setup_routes, nb_route_*) step (3) disappears: k_pair stores every record whose key another rank
+owns into that rank's inbox over NVLink while the alignment runs, and each rank merges its inbox locally.
 
 A shard provides:
   callsets_export() -> np.uint32 [k, cw] rows {slot, len, tag_lo, tag_hi, items[gcap]}
@@ -24,7 +26,32 @@ import time
 import numpy as np
 
 
-def merge_across_ranks(shard, torch, dist, rank, world, device):
+def setup_routes(ctx, torch, dist, rank, world, device, pair_base, inbox_records):
+    """Peer routing (nb_route_*, include/nimble_b200.h): every rank creates its inbox, the CUDA IPC handles travel by
+    all_gather, every rank opens its peers' inboxes.  Returns False — on every rank — when any rank could not (no NVLink
+    / IPC between the processes); the caller then keeps the exchange of merge_across_ranks(routed=False)."""
+    handle = ctx.route_create(inbox_records)
+    allh = torch.empty((world, 64), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allh.view(-1), torch.from_numpy(handle.copy()).to(device))
+    ok = 1
+    try:
+        ctx.route_attach_ipc(world, rank, allh.cpu().numpy(), inbox_records, pair_base)
+    except RuntimeError as e:
+        print("rank %d: peer routing unavailable (%s)" % (rank, e), file=sys.stderr)
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if ok:
+            ctx.route_detach()
+        return False
+    return True
+
+
+def merge_across_ranks(shard, torch, dist, rank, world, device, routed=False):
+    """routed=True: the key records already travelled during the alignment (k_pair stored them into their owners' inboxes
+    over NVLink); what is left is (1) sizes — also the barrier after which every peer's last batch is known to be done —
+    (2) dictionaries, the local merge of the inbox (shard.route_import) and (4) the count all_reduce."""
     stats = os.environ.get("NB_MERGE_STATS") and rank == 0
     marks = []
 
@@ -37,8 +64,11 @@ def merge_across_ranks(shard, torch, dist, rank, world, device):
     rows = shard.callsets_export()
     k, cw = rows.shape
     mark("callsets_export")
-    rec, cnt = shard.keys_export_partitioned(world)
-    mark("keys_export_partitioned")
+    if routed:
+        cnt = [0] * world
+    else:
+        rec, cnt = shard.keys_export_partitioned(world)
+        mark("keys_export_partitioned")
     # (1) sizes
     meta = torch.from_numpy(np.concatenate([[k], np.asarray(cnt, dtype=np.int64)]).astype(np.int64)).to(device)
     allmeta = torch.empty((world, 1 + world), dtype=torch.int64, device=device)
@@ -56,13 +86,17 @@ def merge_across_ranks(shard, torch, dist, rank, world, device):
     others = torch.cat([allrows[r, : int(szs[r])] for r in range(world) if r != rank and szs[r]] or [allrows[0, :0]]).cpu().numpy().view(np.uint32)
     shard.callsets_import(np.ascontiguousarray(others))
     mark("callsets_exchange_import")
-    # (3) key records by owner; re-import this rank's partition and fold it (same stream as the collective: ordered after it)
-    tot_recv, tot_send = int(sum(recv_l)), int(sum(send_l))
-    out = shard.recv_buffer(tot_recv)
-    dist.all_to_all_single(out[:tot_recv], rec[:tot_send], output_split_sizes=recv_l, input_split_sizes=send_l)
-    mark("keys_all_to_all")
-    shard.keys_import(out[:tot_recv])
-    mark("keys_import")
+    if routed:
+        shard.route_import()
+        mark("route_import")
+    else:
+        # (3) key records by owner; re-import this rank's partition and fold it (same stream as the collective: ordered after it)
+        tot_recv, tot_send = int(sum(recv_l)), int(sum(send_l))
+        out = shard.recv_buffer(tot_recv)
+        dist.all_to_all_single(out[:tot_recv], rec[:tot_send], output_split_sizes=recv_l, input_split_sizes=send_l)
+        mark("keys_all_to_all")
+        shard.keys_import(out[:tot_recv])
+        mark("keys_import")
     raw = shard.finalize()
     mark("finalize")
     # (4) dense all-reduce: after (2) every rank lists the same callsets in the same order; the last element carries the unique-key count
@@ -166,9 +200,11 @@ class DeviceShard:
     """One GPU's tables behind the C ABI (nb_callsets_export / nb_keys_export_partitioned / nb_callsets_import /
     nb_keys_import / nb_counts_finalize).  Buffers are allocated once: unique keys <= pairs aligned on this rank."""
 
-    def __init__(self, ctx, nb, torch, pair_base, max_pairs):
+    def __init__(self, ctx, nb, torch, pair_base, max_pairs, routed=False):
         self.ctx, self.nb, self.torch, self.pair_base = ctx, nb, torch, pair_base
-        self.scoped = max_pairs == 0   # scoped (BAM) merges reduce the rows on the device
+        if routed:
+            max_pairs = 0   # no export / receive buffers: the records travel inside k_pair
+        self.scoped = max_pairs == 0 and not routed   # scoped (BAM) merges reduce the rows on the device
         self.pin = None
         self.rows = None
         self.rec = torch.empty((max_pairs, 4), dtype=torch.int64, device="cuda") if max_pairs else None   # (scoped merges exchange no key records)
@@ -197,6 +233,9 @@ class DeviceShard:
 
     def keys_import(self, rec):
         self.nb._ck(self.nb.lib().nb_keys_import(self.ctx.h, rec.data_ptr(), rec.shape[0]))
+
+    def route_import(self):
+        return self.ctx.route_import()
 
     def finalize(self):
         return self.ctx.counts_raw(rows=not self.scoped)

@@ -85,6 +85,44 @@ class ModelShard:
                     callsets=[cs for _, cs in order])
 
 
+class RoutedModelShard(ModelShard):
+    """Peer routing (nb_route_*): a pair whose key another rank owns never enters this rank's table — k_pair appends its
+    record to the owner's inbox.  The NVLink peer stores are modelled by an object all_gather when the inbox is merged."""
+
+    def __init__(self, names_sorted, rank, world):
+        super().__init__(names_sorted)
+        self.rank, self.world = rank, world
+        self.outbox = [[] for _ in range(world)]
+
+    def add_pair(self, key, order, insertable, callset):
+        if not insertable:
+            return
+        lo = key & (2 ** 64 - 1)
+        owner = ((lo >> 40) & 0xFFFF) % self.world
+        if owner == self.rank:
+            return super().add_pair(key, order, insertable, callset)
+        tag = 0
+        if callset is not None:
+            tag = _tag(callset)
+            self.cs[tag] = callset      # interned locally, travels with the dictionary exchange
+        self.outbox[owner].append((key, order, tag))
+
+    def keys_export_partitioned(self, world):
+        raise AssertionError("a routed merge never exports its key table")
+
+    def route_import(self):
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, self.outbox)
+        n = 0
+        for r in range(self.world):
+            for key, order, tag in everyone[r][self.rank]:
+                n += 1
+                if key not in self.keys or self.keys[key][0] < order:
+                    self.keys[key] = (order, tag)
+        self.outbox = [[] for _ in range(self.world)]
+        return n
+
+
 def _inputs():
     L = synth.SynthLibrary(seed=77, n_fam=40, n_all=5, group_on="")
     obj = L.to_json_obj()
@@ -115,12 +153,14 @@ def _worker(rank, world, port, q):
         ocfg, oref = orc.parse_reference_library(obj, "unstranded")
         o = orc.Oracle(ocfg, oref)
         n = len(o1) - 1; per = n // world; lo, hi = rank * per, (rank + 1) * per if rank + 1 < world else n
-        shard = ModelShard(sorted(L.names))
-        for i, (key, ins, cs) in enumerate(_per_pair(o, ocfg, r1, o1, r2, o2, lo, hi)):
-            shard.add_pair(key, lo + i + 1, ins, cs)
-        raw, uniq = merge_across_ranks(shard, torch, dist, rank, world, "cpu")
-        if rank == 0:
-            q.put(({cs: int(c) for cs, c in zip(raw["callsets"], raw["dense_counts"].tolist()) if c}, uniq))
+        pairs = _per_pair(o, ocfg, r1, o1, r2, o2, lo, hi)
+        for routed in (False, True):
+            shard = RoutedModelShard(sorted(L.names), rank, world) if routed else ModelShard(sorted(L.names))
+            for i, (key, ins, cs) in enumerate(pairs):
+                shard.add_pair(key, lo + i + 1, ins, cs)
+            raw, uniq = merge_across_ranks(shard, torch, dist, rank, world, "cpu", routed=routed)
+            if rank == 0:
+                q.put(({cs: int(c) for cs, c in zip(raw["callsets"], raw["dense_counts"].tolist()) if c}, uniq))
     finally:
         dist.destroy_process_group()
 
@@ -133,9 +173,11 @@ def test_world_size_2_gloo_merge_equals_single_process_counts():
     for p in procs:
         p.start()
     merged, uniq = q.get(timeout=240)
+    merged_routed, uniq_routed = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    assert merged_routed == merged and uniq_routed == uniq   # peer-routed records give the same tables as the all-to-all
     # single process over the union
     L, obj, (r1, o1, r2, o2) = _inputs()
     ocfg, oref = orc.parse_reference_library(obj, "unstranded")
