@@ -205,7 +205,7 @@ def main():
     n_reads = 2 * n
 
     from nimble_aligner_b200.multigpu import merge_across_ranks, DeviceShard, setup_routes
-    routed = world > 1 and args.merge == "p2p" and setup_routes(ctx, torch, dist, rank, world, "cuda", pair_base, n + n // 4)
+    routed = world > 1 and args.merge == "p2p" and setup_routes(ctx, torch, dist, rank, world, "cuda", pair_base, (n + n // 2) // world + 4096)
     shard = DeviceShard(ctx, nb, torch, pair_base, n, routed=routed) if world > 1 else None   # merge buffers are allocated once, outside the job
 
     def step_device():

@@ -204,24 +204,26 @@ int nb_keys_export_partitioned(nb_ctx*, void* dev_records, uint64_t cap, uint64_
 int nb_callsets_export(nb_ctx*, uint32_t* rows, uint64_t cap_rows, uint64_t* n_out, uint32_t* gcap_out);
 int nb_callsets_import(nb_ctx*, const uint32_t* rows, uint64_t n);
 
-/* Peer routing of the whole-run scope: instead of exchanging the key tables when the job ends, k_pair sends every record
- * whose key another rank owns straight into that rank's inbox over NVLink (peer stores, slots reserved by one remote
- * atomicAdd per warp and owner) while the alignment runs; keys this rank owns go into its own table with global pair
- * orders.  When the job ends each rank merges its inbox (nb_route_import) — no all-to-all, no export pass.
- *   nb_route_create      allocate this context's inbox (inbox_records x 32 B) and hand out its CUDA IPC handle (64 B)
+/* Peer routing of the whole-run scope: instead of exchanging the key tables when the job ends, k_pair stores every
+ * record whose key another rank owns straight into that rank's inbox over NVLink while the alignment runs; keys this
+ * rank owns go into its own table with global pair orders.  An inbox has one region per source rank and the fill
+ * cursors stay on the source, so only the 32-byte record stores cross the link (no remote atomics).  When the job ends
+ * each rank merges its inbox (nb_route_import) — no all-to-all, no export pass over the key table.
+ *   nb_route_create      allocate this context's inbox (world x records_per_peer x 32 B); returns its CUDA IPC handle (64 B)
  *   nb_route_attach_ipc  one process per GPU: handles = world x 64 B gathered from all ranks (own entry ignored);
- *                        inbox_records = the capacity every peer created; NB_ERR_CUDA when a handle cannot be opened
- *                        (the host then keeps the NCCL exchange above)
+ *                        NB_ERR_CUDA when a handle cannot be opened (the host then keeps the NCCL exchange above)
  *   nb_route_attach_ctx  one process driving several contexts / GPUs: peers[world], peers[rank] == this context
- *   nb_route_import      merge the inbox; call after a collective / barrier that follows every peer's last batch and
- *                        after nb_callsets_import of the peers' dictionaries; empties the inbox for the next job
+ *   nb_route_sent        after this rank's last batch: records stored per destination rank (sent[world]); the host
+ *                        delivers sent[o] to rank o (one all_gather, which is also the barrier nb_route_import needs)
+ *   nb_route_import      merge counts[r] records from each rank r; call after nb_callsets_import of the peers' dictionaries
  * pair_index_base = global index of this rank's first pair (orders decide which duplicate wins, src/align.rs:685). */
 enum { NB_ROUTE_HANDLE_BYTES = 64 };
-int nb_route_create(nb_ctx*, uint64_t inbox_records, void* ipc_handle_out);
-int nb_route_attach_ipc(nb_ctx*, uint32_t world, uint32_t rank, const void* handles, uint64_t inbox_records, uint64_t pair_index_base);
+int nb_route_create(nb_ctx*, uint32_t world, uint64_t records_per_peer, void* ipc_handle_out);
+int nb_route_attach_ipc(nb_ctx*, uint32_t world, uint32_t rank, const void* handles, uint64_t pair_index_base);
 int nb_route_attach_ctx(nb_ctx*, uint32_t world, uint32_t rank, nb_ctx* const* peers, uint64_t pair_index_base);
 int nb_route_set_pair_base(nb_ctx*, uint64_t pair_index_base);
-int nb_route_import(nb_ctx*, uint64_t* n_imported);
+int nb_route_sent(nb_ctx*, uint64_t* sent);
+int nb_route_import(nb_ctx*, const uint64_t* counts, uint64_t* n_imported);
 int nb_route_detach(nb_ctx*);
 
 /* timing of the dominant kernel (seed_walk_map), CUDA events on the launching stream: out[0]=launches, out[1]=total ms,

@@ -109,11 +109,12 @@ _SIGS = {
     "nb_keys_export_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "nb_callsets_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "nb_callsets_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
-    "nb_route_create": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
-    "nb_route_attach_ipc": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "nb_route_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]),
+    "nb_route_attach_ipc": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "nb_route_sent": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nb_route_attach_ctx": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]),
     "nb_route_set_pair_base": (C.c_int, [C.c_void_p, C.c_uint64]),
-    "nb_route_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "nb_route_import": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "nb_route_detach": (C.c_int, [C.c_void_p]),
     "nb_ctx_kernel_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "nb_ctx_work_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -422,16 +423,17 @@ class Context:
         _ck(lib().nb_counts_reset(self.h))
 
     # ---- peer routing of the whole-run scope (nb_route_*)
-    def route_create(self, inbox_records):
-        """Allocates the inbox; returns its 64-byte CUDA IPC handle (np.uint8[64])."""
+    def route_create(self, world, records_per_peer):
+        """Allocates the inbox (one region per source rank); returns its 64-byte CUDA IPC handle (np.uint8[64])."""
         h = np.zeros(64, dtype=np.uint8)
-        _ck(lib().nb_route_create(self.h, int(inbox_records), h.ctypes.data))
+        _ck(lib().nb_route_create(self.h, int(world), int(records_per_peer), h.ctypes.data))
+        self._route_world = int(world)
         return h
 
-    def route_attach_ipc(self, world, rank, handles, inbox_records, pair_index_base):
+    def route_attach_ipc(self, world, rank, handles, pair_index_base):
         handles = np.ascontiguousarray(handles, dtype=np.uint8)
         assert handles.size == 64 * world
-        _ck(lib().nb_route_attach_ipc(self.h, world, rank, handles.ctypes.data, int(inbox_records), int(pair_index_base)))
+        _ck(lib().nb_route_attach_ipc(self.h, world, rank, handles.ctypes.data, int(pair_index_base)))
 
     def route_attach_ctx(self, world, rank, peers, pair_index_base):
         arr = (C.c_void_p * world)(*[p.h for p in peers])
@@ -440,9 +442,16 @@ class Context:
     def route_set_pair_base(self, pair_index_base):
         _ck(lib().nb_route_set_pair_base(self.h, int(pair_index_base)))
 
-    def route_import(self):
+    def route_sent(self):
+        """Records stored per destination rank since the last call (waits for the submitted batches)."""
+        o = np.zeros(16, dtype=np.uint64)
+        _ck(lib().nb_route_sent(self.h, o.ctypes.data))
+        return o[: self._route_world].copy()
+
+    def route_import(self, counts):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
         n = C.c_uint64(0)
-        _ck(lib().nb_route_import(self.h, C.byref(n)))
+        _ck(lib().nb_route_import(self.h, counts.ctypes.data, C.byref(n)))
         return n.value
 
     def route_detach(self):

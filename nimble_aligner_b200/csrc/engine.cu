@@ -88,8 +88,8 @@ struct nb_ctx {
   std::vector<u32> cs_items, slot_dense; std::vector<u64> cs_off;
   u8* h_rows = nullptr; size_t h_rows_cap = 0; u64 n_rows_dev = 0;   // pinned: row_scope | row_callset | row_count of the last finalize
   DBuf d_rowwork, d_rowout, d_dense;
-  // peer routing of the whole-run scope (nb_route_*): own inbox = {cursor u64 @0, KeyRec records @256}
-  DBuf d_inbox; u64 inbox_cap = 0; bool route_on = false; nbk::Route route; std::vector<void*> ipc_opened;
+  // peer routing of the whole-run scope (nb_route_*): own inbox = inbox_world regions of inbox_cap KeyRec, one per source rank; d_routecur = this rank's fill cursors
+  DBuf d_inbox, d_routecur; u64 inbox_cap = 0; u32 inbox_world = 0; bool route_on = false; nbk::Route route; std::vector<void*> ipc_opened;
 };
 
 static Tables make_tables(nb_ctx* c) {
@@ -148,7 +148,7 @@ static int check_device_errors(nb_ctx* c, Counters* out = nullptr) {
   if (h.err & nbk::E_CS_FULL) return fail(NB_ERR_OVERFLOW, "callset dictionary full: raise option callset_slots");
   if (h.err & nbk::E_KEY_FULL) return fail(NB_ERR_OVERFLOW, "read-key table full: raise option key_slots");
   if (h.err & nbk::E_AGG_FULL) return fail(NB_ERR_OVERFLOW, "count table full: raise option agg_slots");
-  if (h.err & nbk::E_INBOX_FULL) return fail(NB_ERR_OVERFLOW, "a peer's routing inbox is full: create the routes with more inbox_records");
+  if (h.err & nbk::E_INBOX_FULL) return fail(NB_ERR_OVERFLOW, "routing inbox region full: create the routes with more records_per_peer");
   return NB_OK;
 }
 
@@ -224,7 +224,7 @@ void nb_ctx_free(nb_ctx* c) {
                  &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded, &c->d_rowwork, &c->d_rowout, &c->d_dense};
   for (DBuf* b : all) b->release();
   for (void* q : c->ipc_opened) cudaIpcCloseMemHandle(q);
-  c->ipc_opened.clear(); c->d_inbox.release();
+  c->ipc_opened.clear(); c->d_inbox.release(); c->d_routecur.release();
   nb_host_free(c->h_rows); c->h_rows = nullptr;
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -613,36 +613,36 @@ int nb_keys_import(nb_ctx* c, const void* dev_records, uint64_t n) {
 }
 
 // ---- peer routing of the whole-run scope over NVLink (kernels.cuh Route; DESIGN.md "Multi-GPU")
-int nb_route_create(nb_ctx* c, uint64_t inbox_records, void* ipc_handle_out) {
-  if (!c || inbox_records == 0) return fail(NB_ERR_INVALID, "bad argument");
+int nb_route_create(nb_ctx* c, uint32_t world, uint64_t records_per_peer, void* ipc_handle_out) {
+  if (!c || records_per_peer == 0 || world < 2 || world > (u32)nbk::ROUTE_MAX) return fail(NB_ERR_INVALID, "bad argument (2 <= world <= 16)");
   static_assert(sizeof(cudaIpcMemHandle_t) == NB_ROUTE_HANDLE_BYTES, "IPC handle size");
   CK(cudaSetDevice(c->device));
   if (c->route_on) return fail(NB_ERR_INVALID, "routes are attached; call nb_route_detach first");
   CK(cudaStreamSynchronize(c->stream));
-  if (c->d_inbox.p && c->inbox_cap < inbox_records) c->d_inbox.release();
-  if (!c->d_inbox.p) { CK(c->d_inbox.ensure(256 + inbox_records * sizeof(nbk::KeyRec), c->stream)); c->inbox_cap = inbox_records; }
-  CK(cudaMemsetAsync(c->d_inbox.p, 0, 256, c->stream)); CK(cudaStreamSynchronize(c->stream));
+  size_t bytes = (size_t)world * records_per_peer * sizeof(nbk::KeyRec);
+  if (c->d_inbox.p && c->d_inbox.cap < bytes) c->d_inbox.release();
+  if (!c->d_inbox.p) CK(c->d_inbox.ensure(bytes, c->stream));
+  c->inbox_cap = records_per_peer; c->inbox_world = world;
+  CK(c->d_routecur.ensure(nbk::ROUTE_MAX * 8, c->stream));
+  CK(cudaMemsetAsync(c->d_routecur.p, 0, nbk::ROUTE_MAX * 8, c->stream)); CK(cudaStreamSynchronize(c->stream));
   if (ipc_handle_out) { cudaIpcMemHandle_t h; CK(cudaIpcGetMemHandle(&h, c->d_inbox.p)); memcpy(ipc_handle_out, &h, sizeof h); }
   return NB_OK;
 }
-static int route_fill(nb_ctx* c, u32 world, u32 rank, void* const* bases, const u64* caps, u64 pair_index_base) {
+static int route_fill(nb_ctx* c, u32 world, u32 rank, void* const* bases, u64 pair_index_base) {
   nbk::Route& r = c->route; memset(&r, 0, sizeof r);
-  r.world = world; r.rank = rank; r.pair_base = pair_index_base; r.cap = ~0ULL;
-  for (u32 i = 0; i < world; i++) {
-    r.cursor[i] = (unsigned long long*)bases[i]; r.inbox[i] = (nbk::KeyRec*)((char*)bases[i] + 256);
-    r.cap = std::min<u64>(r.cap, caps[i]);
-  }
-  c->route_on = world > 1;
+  r.world = world; r.rank = rank; r.pair_base = pair_index_base; r.cap = c->inbox_cap;
+  for (u32 i = 0; i < world; i++) r.inbox[i] = (nbk::KeyRec*)bases[i] + (size_t)rank * c->inbox_cap;   // this rank's region in rank i's inbox
+  r.cursor = (unsigned long long*)c->d_routecur.p;
+  c->route_on = true;
   return NB_OK;
 }
-int nb_route_attach_ipc(nb_ctx* c, uint32_t world, uint32_t rank, const void* handles, uint64_t inbox_records, uint64_t pair_index_base) {
-  if (!c || !handles || world == 0 || world > (u32)nbk::ROUTE_MAX || rank >= world) return fail(NB_ERR_INVALID, "bad argument (world <= 16)");
-  if (!c->d_inbox.p) return fail(NB_ERR_INVALID, "nb_route_create first");
+int nb_route_attach_ipc(nb_ctx* c, uint32_t world, uint32_t rank, const void* handles, uint64_t pair_index_base) {
+  if (!c || !handles || rank >= world) return fail(NB_ERR_INVALID, "bad argument");
+  if (!c->d_inbox.p || c->inbox_world != world) return fail(NB_ERR_INVALID, "nb_route_create with the same world first");
   if (c->route_on) return fail(NB_ERR_INVALID, "routes already attached");
   CK(cudaSetDevice(c->device));
-  void* bases[nbk::ROUTE_MAX]; u64 caps[nbk::ROUTE_MAX];
+  void* bases[nbk::ROUTE_MAX];
   for (u32 i = 0; i < world; i++) {
-    caps[i] = i == rank ? c->inbox_cap : inbox_records;
     if (i == rank) { bases[i] = c->d_inbox.p; continue; }
     cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + (size_t)i * sizeof h, sizeof h);
     void* q = nullptr; cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
@@ -654,15 +654,16 @@ int nb_route_attach_ipc(nb_ctx* c, uint32_t world, uint32_t rank, const void* ha
     }
     c->ipc_opened.push_back(q); bases[i] = q;
   }
-  return route_fill(c, world, rank, bases, caps, pair_index_base);
+  return route_fill(c, world, rank, bases, pair_index_base);
 }
 int nb_route_attach_ctx(nb_ctx* c, uint32_t world, uint32_t rank, nb_ctx* const* peers, uint64_t pair_index_base) {
-  if (!c || !peers || world == 0 || world > (u32)nbk::ROUTE_MAX || rank >= world || peers[rank] != c) return fail(NB_ERR_INVALID, "bad argument (world <= 16, peers[rank] must be this context)");
+  if (!c || !peers || rank >= world || world > (u32)nbk::ROUTE_MAX || peers[rank] != c) return fail(NB_ERR_INVALID, "bad argument (peers[rank] must be this context)");
   if (c->route_on) return fail(NB_ERR_INVALID, "routes already attached");
   CK(cudaSetDevice(c->device));
-  void* bases[nbk::ROUTE_MAX]; u64 caps[nbk::ROUTE_MAX];
+  void* bases[nbk::ROUTE_MAX];
   for (u32 i = 0; i < world; i++) {
-    if (!peers[i] || !peers[i]->d_inbox.p) return fail(NB_ERR_INVALID, "every peer needs nb_route_create first");
+    if (!peers[i] || !peers[i]->d_inbox.p || peers[i]->inbox_world != world || peers[i]->inbox_cap != c->inbox_cap)
+      return fail(NB_ERR_INVALID, "every peer needs nb_route_create with the same world and records_per_peer first");
     if (peers[i]->device != c->device) {
       int can = 0; CK(cudaDeviceCanAccessPeer(&can, c->device, peers[i]->device));
       if (!can) return fail(NB_ERR_CUDA, "no peer access between the devices of two routed contexts");
@@ -670,9 +671,9 @@ int nb_route_attach_ctx(nb_ctx* c, uint32_t world, uint32_t rank, nb_ctx* const*
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(NB_ERR_CUDA, cudaGetErrorString(e));
       cudaGetLastError();
     }
-    bases[i] = peers[i]->d_inbox.p; caps[i] = peers[i]->inbox_cap;
+    bases[i] = peers[i]->d_inbox.p;
   }
-  return route_fill(c, world, rank, bases, caps, pair_index_base);
+  return route_fill(c, world, rank, bases, pair_index_base);
 }
 int nb_route_set_pair_base(nb_ctx* c, uint64_t pair_index_base) { if (!c) return fail(NB_ERR_INVALID, "null argument"); c->route.pair_base = pair_index_base; return NB_OK; }
 int nb_route_detach(nb_ctx* c) {
@@ -682,21 +683,36 @@ int nb_route_detach(nb_ctx* c) {
   c->ipc_opened.clear(); c->route_on = false; memset(&c->route, 0, sizeof c->route);
   return NB_OK;
 }
-// Merge the records peers appended to this context's inbox into its key table (same "later duplicate wins" rule as
-// k_pair) and empty the inbox.  Every peer must have finished its nb_align_batch calls of this job AND this rank must
-// know it (any collective or barrier after the peers' last batch does); the callsets the records name must already be
-// in this context's dictionary (nb_callsets_import of the peers' rows first).
-int nb_route_import(nb_ctx* c, uint64_t* n_imported) {
-  if (!c) return fail(NB_ERR_INVALID, "null argument");
-  if (!c->d_inbox.p) return fail(NB_ERR_INVALID, "nb_route_create first");
+// Records this rank has stored into each peer's inbox since the last call (sent[world], sent[rank] = 0); waits for the
+// batches submitted so far and restarts the cursors for the next job.  The host hands sent[o] to rank o (one all_gather).
+int nb_route_sent(nb_ctx* c, uint64_t* sent) {
+  if (!c || !sent) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->route_on) return fail(NB_ERR_INVALID, "routes are not attached");
+  CK(cudaSetDevice(c->device));
+  unsigned long long h[nbk::ROUTE_MAX];
+  CK(cudaMemcpyAsync(h, c->d_routecur.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemsetAsync(c->d_routecur.p, 0, sizeof h, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (u32 i = 0; i < c->route.world; i++) {
+    if (h[i] > c->inbox_cap) return fail(NB_ERR_OVERFLOW, "routing inbox region overflow: create the routes with more records_per_peer");
+    sent[i] = h[i];
+  }
+  return NB_OK;
+}
+// Merge the records peers stored into this context's inbox (counts[r] from rank r, counts[rank] ignored) into its key
+// table with the same "later duplicate wins" rule as k_pair.  Every peer must have finished its batches of this job AND
+// this rank must know it (the collective that carried the counts does); the callsets the records name must already be in
+// this context's dictionary (nb_callsets_import of the peers' rows first).
+int nb_route_import(nb_ctx* c, const uint64_t* counts, uint64_t* n_imported) {
+  if (!c || !counts) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->route_on) return fail(NB_ERR_INVALID, "routes are not attached");
   CK(cudaSetDevice(c->device));
   if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
   if (c->mode == 1) return fail(NB_ERR_INVALID, "routing applies to the whole-run scope only");
   c->mode = 0;
   cudaStream_t s = c->stream;
-  unsigned long long n = 0;
-  CK(cudaMemcpyAsync(&n, c->d_inbox.p, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
-  if (n > c->inbox_cap) return fail(NB_ERR_OVERFLOW, "routing inbox overflow: create the routes with more inbox_records");
+  u64 n = 0;
+  for (u32 r = 0; r < c->route.world; r++) if (r != c->route.rank) { if (counts[r] > c->inbox_cap) return fail(NB_ERR_OVERFLOW, "routing inbox region overflow: create the routes with more records_per_peer"); n += counts[r]; }
   if (2 * (c->keys_upper + n) > c->key_slots) {
     CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
     nbk::launch_count_keys(make_tables(c), s); c->all_launches++;
@@ -706,11 +722,13 @@ int nb_route_import(nb_ctx* c, uint64_t* n_imported) {
     if (2 * (c->keys_upper + n) > c->key_slots) { rc = grow_keys(c, 2 * (c->keys_upper + n)); if (rc) return rc; }
   }
   c->keys_upper += n;
-  nbk::launch_keys_import(make_tables(c), (const char*)c->d_inbox.p + 256, n, s); c->all_launches++;
-  CK(cudaMemsetAsync(c->d_inbox.p, 0, 8, s));
+  Tables t = make_tables(c);
+  for (u32 r = 0; r < c->route.world; r++) if (r != c->route.rank && counts[r]) {
+    nbk::launch_keys_import(t, (const nbk::KeyRec*)c->d_inbox.p + (size_t)r * c->inbox_cap, counts[r], s); c->all_launches++;
+  }
   c->folded = false;
   if (n_imported) *n_imported = n;
-  return check_device_errors(c);
+  return NB_OK;   // device-side errors (table full, unknown callset) surface at nb_counts_finalize
 }
 
 }  // extern "C"

@@ -425,8 +425,9 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
   // Scoped (BAM) batches also register non-insertable pairs: filter_reasons is keyed by read_key for every pair
   // (src/align.rs:586-600) and k_resolve reports per-key outcomes.
   // Whole-run scope sharded over ranks (rt.world > 1): orders are global pair indices and a key this rank does not own
-  // goes to its owner's inbox over NVLink — one remote atomicAdd per (warp, owner) reserves the slots, then each lane
-  // stores its 32-byte record; the owner merges its inbox when the job ends (nb_route_import).
+  // goes to its owner's inbox over NVLink — one local atomicAdd per (warp, owner) reserves slots in this rank's region
+  // of that inbox, then each lane stores its 32-byte record (peer stores: the only traffic on the link); the owner
+  // merges its inbox when the job ends (nb_route_import).
   const bool routed = rt.world > 1 && !scoped;
   u32 owner = routed ? key_owner(h0, rt.world) : 0u;
   bool send = routed && out.insertable && owner != rt.rank;
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
     if (send) {
       unsigned peers = __match_any_sync(sm, owner); u32 lane = threadIdx.x & 31; int leader = __ffs(peers) - 1;
       unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(rt.cursor[owner], (unsigned long long)__popc(peers));
+      if ((int)lane == leader) base = atomicAdd(rt.cursor + owner, (unsigned long long)__popc(peers));
       base = __shfl_sync(peers, base, leader);
       u64 at = base + __popc(peers & ((1u << lane) - 1));
       if (at >= rt.cap) atomicOr(&t.ctr->err, (unsigned)E_INBOX_FULL);

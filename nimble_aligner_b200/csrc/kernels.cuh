@@ -91,11 +91,13 @@ struct Tables {
 // De-duplication record exchanged between ranks: {key_lo, key_hi, global pair order, callset tag (0: none)}
 struct KeyRec { u64 k0, k1, order, tag; };
 // Peer routing of the whole-run scope (DESIGN.md "Multi-GPU"): every read_key has an owning rank; k_pair inserts the keys
-// this rank owns into its own table and appends the others straight into the owner's inbox over NVLink (peer stores),
-// so the exchange rides along with the alignment instead of following it.  inbox[r] / cursor[r] are peer pointers
-// (cudaIpcOpenMemHandle, or plain device pointers of contexts in the same process); world <= 1: routing off.
+// this rank owns into its own table and stores the others straight into the owner's inbox over NVLink, so the exchange
+// rides along with the alignment instead of following it.  An inbox has one region of `cap` records per source rank and
+// the fill cursors live on the SOURCE (cursor[owner], local atomics): nothing but the 32-byte record stores crosses
+// the link — no remote atomic, no round trip.  inbox[o] = this rank's region inside rank o's inbox (a peer pointer from
+// cudaIpcOpenMemHandle, or a plain device pointer of a context in the same process); world <= 1: routing off.
 constexpr int ROUTE_MAX = 16;
-struct Route { u32 world, rank; u64 pair_base, cap; KeyRec* inbox[ROUTE_MAX]; unsigned long long* cursor[ROUTE_MAX]; };
+struct Route { u32 world, rank; u64 pair_base, cap; KeyRec* inbox[ROUTE_MAX]; unsigned long long* cursor; };
 
 void launch_pack(const BatchDev& b, cudaStream_t s);
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s);

@@ -26,16 +26,16 @@ import time
 import numpy as np
 
 
-def setup_routes(ctx, torch, dist, rank, world, device, pair_base, inbox_records):
+def setup_routes(ctx, torch, dist, rank, world, device, pair_base, records_per_peer):
     """Peer routing (nb_route_*, include/nimble_b200.h): every rank creates its inbox, the CUDA IPC handles travel by
     all_gather, every rank opens its peers' inboxes.  Returns False — on every rank — when any rank could not (no NVLink
     / IPC between the processes); the caller then keeps the exchange of merge_across_ranks(routed=False)."""
-    handle = ctx.route_create(inbox_records)
+    handle = ctx.route_create(world, records_per_peer)
     allh = torch.empty((world, 64), dtype=torch.uint8, device=device)
     dist.all_gather_into_tensor(allh.view(-1), torch.from_numpy(handle.copy()).to(device))
     ok = 1
     try:
-        ctx.route_attach_ipc(world, rank, allh.cpu().numpy(), inbox_records, pair_base)
+        ctx.route_attach_ipc(world, rank, allh.cpu().numpy(), pair_base)
     except RuntimeError as e:
         print("rank %d: peer routing unavailable (%s)" % (rank, e), file=sys.stderr)
         ok = 0
@@ -46,6 +46,9 @@ def setup_routes(ctx, torch, dist, rank, world, device, pair_base, inbox_records
             ctx.route_detach()
         return False
     return True
+
+
+_ROUTED_CAP = [4096]   # rows per rank in the routed merge's dictionary block (grows by doubling, alike on every rank)
 
 
 def merge_across_ranks(shard, torch, dist, rank, world, device, routed=False):
@@ -64,30 +67,56 @@ def merge_across_ranks(shard, torch, dist, rank, world, device, routed=False):
     rows = shard.callsets_export()
     k, cw = rows.shape
     mark("callsets_export")
-    if routed:
-        cnt = [0] * world
-    else:
+    if not routed:
         rec, cnt = shard.keys_export_partitioned(world)
         mark("keys_export_partitioned")
-    # (1) sizes
-    meta = torch.from_numpy(np.concatenate([[k], np.asarray(cnt, dtype=np.int64)]).astype(np.int64)).to(device)
-    allmeta = torch.empty((world, 1 + world), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(allmeta.view(-1), meta)
-    am = allmeta.cpu().numpy()
-    szs, recv_l, send_l = am[:, 0].tolist(), am[:, 1 + rank].tolist(), [int(x) for x in cnt]
-    mark("sizes_all_gather")
-    # (2) callset dictionaries
-    kmax = max(max(szs), 1)
-    mine = torch.zeros((kmax, cw), dtype=torch.int32, device=device)
-    if k:
-        mine[:k] = torch.from_numpy(np.ascontiguousarray(rows).view(np.int32)).to(device)
-    allrows = torch.empty((world, kmax, cw), dtype=torch.int32, device=device)
-    dist.all_gather_into_tensor(allrows.view(-1), mine.view(-1))
-    others = torch.cat([allrows[r, : int(szs[r])] for r in range(world) if r != rank and szs[r]] or [allrows[0, :0]]).cpu().numpy().view(np.uint32)
-    shard.callsets_import(np.ascontiguousarray(others))
-    mark("callsets_exchange_import")
     if routed:
-        shard.route_import()
+        # (1)+(2) in one collective: a fixed-capacity block per rank {k, sent[world], rows[cap]}; the capacity is a ratchet
+        # every rank raises alike (all ranks see all k) when a dictionary outgrows it.  The collective is also the barrier
+        # after which every peer's last k_pair — and with it every record bound for this rank's inbox — is complete.
+        sent = np.asarray(shard.route_sent(), dtype=np.int64)
+        hdr = 1 + 2 * world          # k, then sent[] as (lo, hi) int32 halves
+        while True:
+            cap = _ROUTED_CAP[0]
+            head = np.zeros(hdr, dtype=np.int32)
+            head[0] = k
+            head[1:] = sent.astype(np.int64).view(np.int32)
+            blk = torch.zeros(hdr + cap * cw, dtype=torch.int32, device=device)
+            body = np.ascontiguousarray(rows).view(np.int32).reshape(-1) if 0 < k <= cap else np.zeros(0, dtype=np.int32)
+            blk[: hdr + body.size] = torch.from_numpy(np.concatenate([head, body])).to(device)
+            allblk = torch.empty((world, hdr + cap * cw), dtype=torch.int32, device=device)
+            dist.all_gather_into_tensor(allblk.view(-1), blk)
+            hb = allblk.cpu().numpy()
+            szs = hb[:, 0].tolist()
+            if max(szs) <= cap:
+                break
+            while _ROUTED_CAP[0] < max(szs):
+                _ROUTED_CAP[0] *= 2
+        recv = np.ascontiguousarray(hb[:, 1:hdr]).view(np.int64)[:, rank].copy()   # records rank r stored into this rank's inbox
+        parts = [hb[r, hdr:hdr + int(szs[r]) * cw].reshape(-1, cw) for r in range(world) if r != rank and szs[r]]
+        others = (np.concatenate(parts) if parts else np.zeros((0, cw), dtype=np.int32)).view(np.uint32)
+        shard.callsets_import(np.ascontiguousarray(others))
+        mark("callsets_exchange_import")
+    else:
+        # (1) sizes
+        meta = torch.from_numpy(np.concatenate([[k], np.asarray(cnt, dtype=np.int64)]).astype(np.int64)).to(device)
+        allmeta = torch.empty((world, 1 + world), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allmeta.view(-1), meta)
+        am = allmeta.cpu().numpy()
+        szs, recv_l, send_l = am[:, 0].tolist(), am[:, 1 + rank].tolist(), [int(x) for x in cnt]
+        mark("sizes_all_gather")
+        # (2) callset dictionaries
+        kmax = max(max(szs), 1)
+        mine = torch.zeros((kmax, cw), dtype=torch.int32, device=device)
+        if k:
+            mine[:k] = torch.from_numpy(np.ascontiguousarray(rows).view(np.int32)).to(device)
+        allrows = torch.empty((world, kmax, cw), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(allrows.view(-1), mine.view(-1))
+        others = torch.cat([allrows[r, : int(szs[r])] for r in range(world) if r != rank and szs[r]] or [allrows[0, :0]]).cpu().numpy().view(np.uint32)
+        shard.callsets_import(np.ascontiguousarray(others))
+        mark("callsets_exchange_import")
+    if routed:
+        shard.route_import(recv)
         mark("route_import")
     else:
         # (3) key records by owner; re-import this rank's partition and fold it (same stream as the collective: ordered after it)
@@ -102,7 +131,11 @@ def merge_across_ranks(shard, torch, dist, rank, world, device, routed=False):
     # (4) dense all-reduce: after (2) every rank lists the same callsets in the same order; the last element carries the unique-key count
     ncs = len(raw["callset_off"]) - 1
     dense = torch.zeros(ncs + 1, dtype=torch.int64, device=device)
-    if len(raw["row_callset"]):
+    dev = shard.device_rows() if device != "cpu" and hasattr(shard, "device_rows") else None
+    if dev is not None:   # the rows of nb_counts_finalize are still on the device: no host round trip
+        if dev[2].numel():
+            dense.index_add_(0, dev[1].to(torch.int64), dev[2])
+    elif len(raw["row_callset"]):
         dense.index_add_(0, torch.from_numpy(np.asarray(raw["row_callset"]).astype(np.int64)).to(device), torch.from_numpy(np.asarray(raw["row_count"], dtype=np.int64)).to(device))
     dense[ncs] = int(raw["n_unique_keys"])
     dist.all_reduce(dense)
@@ -234,8 +267,11 @@ class DeviceShard:
     def keys_import(self, rec):
         self.nb._ck(self.nb.lib().nb_keys_import(self.ctx.h, rec.data_ptr(), rec.shape[0]))
 
-    def route_import(self):
-        return self.ctx.route_import()
+    def route_sent(self):
+        return self.ctx.route_sent()
+
+    def route_import(self, counts):
+        return self.ctx.route_import(counts)
 
     def finalize(self):
         return self.ctx.counts_raw(rows=not self.scoped)

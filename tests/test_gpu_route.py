@@ -38,7 +38,7 @@ def _routed_counts(ix, lib, data, world, n, chunk, cfg=None):
     per = n // world
     bounds = [(r * per, (r + 1) * per if r + 1 < world else n) for r in range(world)]
     for c in ctxs:
-        c.route_create(n + 64)
+        c.route_create(world, n // world + 64)
     for r, c in enumerate(ctxs):
         c.route_attach_ctx(world, r, ctxs, bounds[r][0])
     out = []
@@ -48,13 +48,13 @@ def _routed_counts(ix, lib, data, world, n, chunk, cfg=None):
             lo, hi = bounds[r]
             a1, b1 = _part(r1, o1, lo, hi); a2, b2 = _part(r2, o2, lo, hi)
             c.align_batch(a1, b1, a2, b2, max_read_len=150)
-        for c in ctxs:
-            c.sync()              # every "peer" has finished its last batch (the barrier / collective of a real job)
+        sent = np.stack([c.route_sent() for c in ctxs])     # waits for each "peer's" batches: the barrier / collective of a real job
+        assert all(sent[r, r] == 0 for r in range(world))
         rows = [_callset_rows(c) for c in ctxs]
         for r, c in enumerate(ctxs):
             others = np.ascontiguousarray(np.concatenate([rows[q] for q in range(world) if q != r]))
             nb._ck(nb.lib().nb_callsets_import(c.h, others.ctypes.data, others.shape[0]))
-        imported = [c.route_import() for c in ctxs]
+        imported = [c.route_import(sent[:, r]) for r, c in enumerate(ctxs)]
         merged, uniq = {}, 0
         for c in ctxs:
             d = c.counts()
@@ -98,19 +98,23 @@ def test_inbox_overflow_and_misuse_fail_loudly():
     r1, o1, r2, o2 = synth.pairs(L, 0, 20_000, seed=5)
     a, b = nb.Context(ix, lib), nb.Context(ix, lib)
     with pytest.raises(nb.NbError):
-        a.route_import()                                # no inbox yet
-    a.route_create(64); b.route_create(64)              # far too small for 10k routed records
+        a.route_import(np.zeros(2, dtype=np.uint64))    # no routes yet
+    with pytest.raises(nb.NbError):
+        a.route_create(1, 64)                           # world must be >= 2
+    a.route_create(2, 64); b.route_create(2, 64)        # far too small for ~10k routed records
     with pytest.raises(nb.NbError):
         a.route_attach_ctx(2, 1, [a, b], 0)             # peers[rank] must be the context itself
     a.route_attach_ctx(2, 0, [a, b], 0); b.route_attach_ctx(2, 1, [a, b], 20_000)
     with pytest.raises(nb.NbError):
-        a.route_create(128)                             # attached: detach first
+        a.route_create(2, 128)                          # attached: detach first
     a.align_batch(r1, o1, r2, o2, max_read_len=150)
+    with pytest.raises(nb.NbError) as e:
+        a.route_sent()
+    assert "inbox" in str(e.value)
     with pytest.raises(nb.NbError) as e:
         a.counts()
     assert "inbox" in str(e.value)
-    a.sync(); b.sync()
     with pytest.raises(nb.NbError) as e:
-        b.route_import()
+        b.route_import(np.array([1000, 0], dtype=np.uint64))   # more than a region holds
     assert "inbox" in str(e.value)
     a.route_detach(); b.route_detach()

@@ -110,11 +110,17 @@ class RoutedModelShard(ModelShard):
     def keys_export_partitioned(self, world):
         raise AssertionError("a routed merge never exports its key table")
 
-    def route_import(self):
+    def route_sent(self):
+        return [len(b) for b in self.outbox]
+
+    def route_import(self, counts):
         everyone = [None] * self.world
         dist.all_gather_object(everyone, self.outbox)
         n = 0
         for r in range(self.world):
+            if r == self.rank:
+                continue
+            assert int(counts[r]) == len(everyone[r][self.rank])      # the counts the merge delivered are the records that arrived
             for key, order, tag in everyone[r][self.rank]:
                 n += 1
                 if key not in self.keys or self.keys[key][0] < order:
