@@ -203,6 +203,7 @@ int nb_keys_import(nb_ctx*, const void* dev_records, uint64_t n);
 int nb_keys_export_partitioned(nb_ctx*, void* dev_records, uint64_t cap, uint64_t pair_index_base, uint32_t world, uint64_t* counts_out);
 int nb_callsets_export(nb_ctx*, uint32_t* rows, uint64_t cap_rows, uint64_t* n_out, uint32_t* gcap_out);
 int nb_callsets_import(nb_ctx*, const uint32_t* rows, uint64_t n);
+int nb_callsets_import_device(nb_ctx*, const uint32_t* dev_rows, uint64_t n);   /* rows already in this context's HBM; asynchronous */
 
 /* Peer routing of the whole-run scope: instead of exchanging the key tables when the job ends, k_pair stores every
  * record whose key another rank owns straight into that rank's inbox over NVLink while the alignment runs; keys this

@@ -109,6 +109,7 @@ _SIGS = {
     "nb_keys_export_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "nb_callsets_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "nb_callsets_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "nb_callsets_import_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "nb_route_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p]),
     "nb_route_attach_ipc": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]),
     "nb_route_sent": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -595,6 +595,15 @@ int nb_callsets_import(nb_ctx* c, const uint32_t* rows, uint64_t n) {
   nbk::launch_callsets_import(make_tables(c), (const u32*)c->d_scratch.p, n, s); c->all_launches++;
   return check_device_errors(c);
 }
+// the same from rows already on this context's device (e.g. inside an all_gather receive buffer): no host round trip and
+// no synchronisation; a full dictionary surfaces at nb_counts_finalize
+int nb_callsets_import_device(nb_ctx* c, const uint32_t* dev_rows, uint64_t n) {
+  if (!c || (n && !dev_rows)) return fail(NB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
+  nbk::launch_callsets_import(make_tables(c), dev_rows, n, c->stream); c->all_launches++;
+  return NB_OK;
+}
 // replace this context's whole-run key table by the received partition (records from all ranks whose keys fall in
 // this rank's range) so that nb_counts_finalize counts each unique read_key of the partition once
 int nb_keys_import(nb_ctx* c, const void* dev_records, uint64_t n) {

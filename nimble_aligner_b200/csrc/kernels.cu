@@ -5,6 +5,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "khash.h"
 
@@ -477,26 +479,55 @@ __global__ void __launch_bounds__(256) k_resolve(BatchDev b, Tables t) {
 
 // ------------------------------------------------------------------------------------------------ K4 fold
 // One vote per unique read_key (src/align.rs:440-449): results[callset] += 1 (245-251), keyed here by (cell, callset).
-__global__ void __launch_bounds__(256) k_fold(Tables t, const u32* cell_of_pair, u64 order_base) {
-  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-  if (idx > t.key_mask) return;
-  ulonglong2 k = t.key[idx];
-  bool occ = !(k.x == 0 && k.y == 0);
-  unsigned ob = __ballot_sync(__activemask(), occ);          // unique read_keys, one atomic per warp
-  if (occ && (threadIdx.x & 31) == (unsigned)(__ffs(ob) - 1)) atomicAdd(&t.ctr->n_keys, (unsigned long long)__popc(ob));
-  if (!occ) return;
-  u64 v = t.kval[idx]; u32 cs = (u32)(v & 0xFFFFFFu);
-  if ((v >> 24) == 0 || cs == CS_NONE) return;   // key never reached score_map (scoped batches register every key) / triaged
-  u32 cell = cell_of_pair ? cell_of_pair[(v >> 24) - 1 - order_base] : 0u;
-  unsigned long long ak = (((unsigned long long)cell << 24) | cs) + 1ULL;
+// Each block walks a contiguous range of key slots.  In the whole-run scope the votes land on a few thousand callsets,
+// so a block first counts them in a shared-memory table and adds each (callset, count) to the global table once
+// (7 M same-address global atomics per 10 M-pair job otherwise: the kernel was atomics-bound at 0.8 TB/s).  Scoped
+// batches have about as many (cell, callset) rows as votes and go to the global table directly.
+__device__ __forceinline__ void agg_add(const Tables& t, unsigned long long ak, unsigned long long n) {
   u64 h = mix64(ak) & t.agg_mask;
   for (u64 probes = 0; probes <= t.agg_mask; probes++) {
     unsigned long long old = atomicCAS(t.agg_key + h, 0ULL, ak);
     if (old == 0ULL) atomicAdd(&t.ctr->n_agg, 1ULL);
-    if (old == 0ULL || old == ak) { atomicAdd(t.agg_cnt + h, 1ULL); return; }
+    if (old == 0ULL || old == ak) { atomicAdd(t.agg_cnt + h, n); return; }
     h = (h + 1) & t.agg_mask;
   }
   atomicOr(&t.ctr->err, (unsigned)E_AGG_FULL);
+}
+constexpr int FOLD_S = 2048;   // shared-memory vote table entries per block (24 KB)
+__global__ void __launch_bounds__(256) k_fold(Tables t, const u32* cell_of_pair, u64 order_base, u64 slots_per_block) {
+  __shared__ unsigned long long s_key[FOLD_S];
+  __shared__ u32 s_cnt[FOLD_S];
+  __shared__ u32 s_occ;
+  const bool local = cell_of_pair == nullptr;
+  if (local) for (u32 i = threadIdx.x; i < FOLD_S; i += blockDim.x) { s_key[i] = 0ULL; s_cnt[i] = 0; }
+  if (threadIdx.x == 0) s_occ = 0;
+  __syncthreads();
+  u64 lo = blockIdx.x * slots_per_block, hi = min(lo + slots_per_block, t.key_mask + 1);
+  u32 nocc = 0;
+  for (u64 idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
+    ulonglong2 k = t.key[idx];
+    if (k.x == 0 && k.y == 0) continue;
+    nocc++;                                          // unique read_keys
+    u64 v = t.kval[idx]; u32 cs = (u32)(v & 0xFFFFFFu);
+    if ((v >> 24) == 0 || cs == CS_NONE) continue;   // key never reached score_map (scoped batches register every key) / triaged
+    u32 cell = cell_of_pair ? cell_of_pair[(v >> 24) - 1 - order_base] : 0u;
+    unsigned long long ak = (((unsigned long long)cell << 24) | cs) + 1ULL;
+    bool done = false;
+    if (local) {
+      u32 h = (u32)mix64(ak) & (FOLD_S - 1);
+      for (int probes = 0; probes < 8 && !done; probes++) {
+        unsigned long long old = atomicCAS(s_key + h, 0ULL, ak);
+        if (old == 0ULL || old == ak) { atomicAdd(s_cnt + h, 1u); done = true; }
+        h = (h + 1) & (FOLD_S - 1);
+      }
+    }
+    if (!done) agg_add(t, ak, 1ULL);
+  }
+  for (int o = 16; o; o >>= 1) nocc += __shfl_xor_sync(0xFFFFFFFFu, nocc, o);
+  if ((threadIdx.x & 31) == 0 && nocc) atomicAdd(&s_occ, nocc);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_occ) atomicAdd(&t.ctr->n_keys, (unsigned long long)s_occ);
+  if (local) for (u32 i = threadIdx.x; i < FOLD_S; i += blockDim.x) if (s_key[i]) agg_add(t, s_key[i], (unsigned long long)s_cnt[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ exports
@@ -643,7 +674,11 @@ void launch_rows_sort(const u64* agg, u64 n, const u32* dense, u64* keys, i64* v
 void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, const Route& rt, cudaStream_t s) {
   if (b.n_pairs) k_pair<<<blocks_for(b.n_pairs, 128), 128, 0, s>>>(b, ix, lib, cfg, t, rt);
 }
-void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s) { k_fold<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, cell_of_pair, order_base); }
+void launch_fold(const Tables& t, const u32* cell_of_pair, u64 order_base, cudaStream_t s) {
+  // contiguous slot ranges, a few blocks per SM (148 SMs x 8): enough votes per block for the shared-memory table to pay
+  u64 slots = t.key_mask + 1, blocks = std::min<u64>((slots + 255) / 256, 148 * 8), per = ((slots + blocks - 1) / blocks + 255) / 256 * 256;
+  k_fold<<<(unsigned)((slots + per - 1) / per), 256, 0, s>>>(t, cell_of_pair, order_base, per);
+}
 void launch_resolve(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_pairs) k_resolve<<<blocks_for(b.n_pairs, 256), 256, 0, s>>>(b, t); }
 void launch_export_reads(const BatchDev& b, const DevIndex& ix, const Tables& t, void* out, cudaStream_t s) {
   if (b.n_reads) k_export_reads<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, ix, t, (ReadOut*)out);

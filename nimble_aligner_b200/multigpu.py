@@ -86,16 +86,22 @@ def merge_across_ranks(shard, torch, dist, rank, world, device, routed=False):
             blk[: hdr + body.size] = torch.from_numpy(np.concatenate([head, body])).to(device)
             allblk = torch.empty((world, hdr + cap * cw), dtype=torch.int32, device=device)
             dist.all_gather_into_tensor(allblk.view(-1), blk)
-            hb = allblk.cpu().numpy()
+            on_dev = device != "cpu" and hasattr(shard, "callsets_import_device")
+            hb = (allblk[:, :hdr].contiguous() if on_dev else allblk).cpu().numpy()   # device shards: only the headers come to the host
             szs = hb[:, 0].tolist()
             if max(szs) <= cap:
                 break
             while _ROUTED_CAP[0] < max(szs):
                 _ROUTED_CAP[0] *= 2
         recv = np.ascontiguousarray(hb[:, 1:hdr]).view(np.int64)[:, rank].copy()   # records rank r stored into this rank's inbox
-        parts = [hb[r, hdr:hdr + int(szs[r]) * cw].reshape(-1, cw) for r in range(world) if r != rank and szs[r]]
-        others = (np.concatenate(parts) if parts else np.zeros((0, cw), dtype=np.int32)).view(np.uint32)
-        shard.callsets_import(np.ascontiguousarray(others))
+        if on_dev:   # the peers' rows are imported straight out of the all_gather buffer in HBM
+            for r in range(world):
+                if r != rank and szs[r]:
+                    shard.callsets_import_device(allblk[r, hdr:], int(szs[r]))
+        else:
+            parts = [hb[r, hdr:hdr + int(szs[r]) * cw].reshape(-1, cw) for r in range(world) if r != rank and szs[r]]
+            others = (np.concatenate(parts) if parts else np.zeros((0, cw), dtype=np.int32)).view(np.uint32)
+            shard.callsets_import(np.ascontiguousarray(others))
         mark("callsets_exchange_import")
     else:
         # (1) sizes
@@ -258,6 +264,9 @@ class DeviceShard:
 
     def callsets_import(self, rows):
         self.nb._ck(self.nb.lib().nb_callsets_import(self.ctx.h, rows.ctypes.data, rows.shape[0]))
+
+    def callsets_import_device(self, rows, n):
+        self.nb._ck(self.nb.lib().nb_callsets_import_device(self.ctx.h, rows.data_ptr(), n))
 
     def recv_buffer(self, n):
         if n > self.out.shape[0]:
