@@ -96,6 +96,43 @@ __device__ __forceinline__ bool coop_find2(const DevIndex& ix, const BatchDev& b
   return false;
 }
 
+// Variant (-DNB_SEED_PAIRED, not the default): two seeking reads per round, each half-warp searches the stride-3 seeds of
+// one read, 48 per round (three per lane, the bucket loads of both halves in flight together), so the serial chain of
+// round trips a warp sits through — one per seeking lane with coop_find2 — halves; a 150 bp read (41 seeds) is settled in
+// one round.  Bit-exact (166 parity / fuzz tests) but 56 registers instead of 40 (36 instead of 48 warps per SM) and
+// the map stage went 0.539 -> 0.566 ms per 2 M reads: the seed stage is not bound by that chain.  `act`: this half has a read
+// to search.  Results are uniform within a half: first hit in seed order and the number of seeds a sequential search
+// would have tried.
+__device__ __forceinline__ void coop_find_pair(const DevIndex& ix, const BatchDev& b, u32 lane, bool act, u32 s_ri, u32 s_kp, u32 s_last, bool& ok, u32& f_kp, u32& f_node, u32& f_off, u32& tried) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const u32 half = lane >> 4, hl = lane & 15;
+  ReadView srd{b.pk + (u64)s_ri * b.W, 1};
+  ok = false; tried = 0; f_kp = 0; f_node = 0; f_off = 0;
+  u32 base = s_kp;
+  bool live = act && base <= s_last;
+  while (__any_sync(FULL, live)) {
+    u32 p0 = base + 3 * hl, p1 = p0 + 48, p2 = p0 + 96;
+    bool v0 = live && p0 <= s_last, v1 = live && p1 <= s_last, v2 = live && p2 <= s_last;
+    u32 q0 = v0 ? p0 : s_last, q1 = v1 ? p1 : s_last, q2 = v2 ? p2 : s_last;   // (a dead half re-reads its own last window: harmless)
+    u64 w0 = srd.win(q0) & KMASK, w1 = srd.win(q1) & KMASK, w2 = srd.win(q2) & KMASK;
+    u64 b0 = nb_table_bucket(w0, ix.n_buckets), b1 = nb_table_bucket(w1, ix.n_buckets), b2 = nb_table_bucket(w2, ix.n_buckets);
+    Bucket ka = ld_bucket(ix.tkey, b0), kb = ld_bucket(ix.tkey, b1), kc = ld_bucket(ix.tkey, b2);
+    u64 s0 = probe_finish(ix, w0 | (1ULL << 63), b0, ka), s1 = probe_finish(ix, w1 | (1ULL << 63), b1, kb), s2 = probe_finish(ix, w2 | (1ULL << 63), b2, kc);
+    unsigned h0 = (__ballot_sync(FULL, v0 && s0 != ~0ULL) >> (16 * half)) & 0xFFFFu;
+    unsigned h1 = (__ballot_sync(FULL, v1 && s1 != ~0ULL) >> (16 * half)) & 0xFFFFu;
+    unsigned h2 = (__ballot_sync(FULL, v2 && s2 != ~0ULL) >> (16 * half)) & 0xFFFFu;
+    bool hit = live && (h0 | h1 | h2);
+    u32 j = h0 ? 0u : (h1 ? 1u : 2u);
+    int f = hit ? __ffs(h0 ? h0 : (h1 ? h1 : h2)) - 1 : 0;                       // winning lane within the half
+    u32 nd2 = 0, of2 = 0;
+    if (hit && (int)hl == f) { u64 v = __ldg(ix.tval + (j == 0 ? s0 : (j == 1 ? s1 : s2))); nd2 = (u32)v; of2 = (u32)(v >> 32); }
+    u32 src = 16 * half + (u32)f;
+    u32 rn = __shfl_sync(FULL, nd2, src), ro = __shfl_sync(FULL, of2, src);
+    if (hit) { u32 idx = 16 * j + (u32)f; f_node = rn; f_off = ro; f_kp = base + 3 * idx; tried += idx + 1; ok = true; live = false; }
+    else if (live) { tried += min(48u, (s_last - base) / 3 + 1); base += 144; live = base <= s_last; }
+  }
+}
+
 // ---- k_seed: one read per lane, 32 consecutive reads per warp.  Gated / seedless reads get their final record here.
 template <int COUNT_WORK>
 __global__ void __launch_bounds__(128) k_seed(BatchDev b, DevIndex ix, DevCfg cfg, Tables t) {
@@ -134,6 +171,7 @@ __global__ void __launch_bounds__(128) k_seed(BatchDev b, DevIndex ix, DevCfg cf
           else if (qn >= (u32)K) { seek = true; qlast = qn - K; }                       // n < k: map_read returns None
         }
       }
+#ifndef NB_SEED_PAIRED   // (default; -DNB_SEED_PAIRED: two seeking reads per round, measured slower — DESIGN.md §4)
       if (seek) {   // the seed at 0 and the next one, per lane
 #pragma unroll 1
         for (int tries = 0; tries < 2 && !found && qkp <= qlast; tries++) {
@@ -149,6 +187,38 @@ __global__ void __launch_bounds__(128) k_seed(BatchDev b, DevIndex ix, DevCfg cf
         bool ok = coop_find2(ix, b, lane, s_ri, s_kp, s_last, f_kp, f_node, f_off, tried);
         if ((int)lane == l) { wc.probes += tried; if (ok) { found = true; qkp = f_kp; qnode = f_node; qoff = f_off; } }
       }
+#else
+      if (seek) {   // the seeds at 0 and 3, per lane, both bucket loads in flight together (one round trip, not two, when the first misses)
+        bool two = qlast >= 3;
+        u64 w0 = qrd.win(0) & KMASK, w1 = qrd.win(two ? 3 : 0) & KMASK;
+        u64 b0 = nb_table_bucket(w0, ix.n_buckets), b1 = nb_table_bucket(w1, ix.n_buckets);
+        Bucket ka = ld_bucket(ix.tkey, b0), kb = ld_bucket(ix.tkey, b1);
+        u64 s0 = probe_finish(ix, w0 | (1ULL << 63), b0, ka);
+        wc.probes++;
+        u64 slot = s0;
+        if (s0 == ~0ULL) {
+          qkp = 3;
+          if (two) { wc.probes++; slot = probe_finish(ix, w1 | (1ULL << 63), b1, kb); if (slot == ~0ULL) qkp = 6; }
+        }
+        if (slot != ~0ULL) { u64 v = __ldg(ix.tval + slot); qnode = (u32)v; qoff = (u32)(v >> 32); found = true; }
+      }
+      unsigned need = __ballot_sync(FULL, seek && !found && qkp <= qlast);
+      while (need) {   // two seeking lanes per round, one per half-warp
+        int l0 = __ffs(need) - 1; need &= need - 1;
+        int l1 = need ? __ffs(need) - 1 : -1; if (l1 >= 0) need &= need - 1;
+        int mine = lane < 16 ? l0 : l1, src = mine < 0 ? l0 : mine;
+        u32 s_kp = __shfl_sync(FULL, qkp, src), s_last = __shfl_sync(FULL, qlast, src), s_ri = __shfl_sync(FULL, q, src);
+        u32 f_kp, f_node, f_off, tried; bool ok;
+        coop_find_pair(ix, b, lane, mine >= 0, s_ri, s_kp, s_last, ok, f_kp, f_node, f_off, tried);
+        u32 okb = __ballot_sync(FULL, ok);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {   // hand each half's answer (uniform within the half) to the lane that asked
+          int l = h ? l1 : l0;
+          u32 rk = __shfl_sync(FULL, f_kp, 16 * h), rn = __shfl_sync(FULL, f_node, 16 * h), ro = __shfl_sync(FULL, f_off, 16 * h), rt = __shfl_sync(FULL, tried, 16 * h);
+          if (l >= 0 && (int)lane == l) { wc.probes += rt; if ((okb >> (16 * h)) & 1u) { found = true; qkp = rk; qnode = rn; qoff = ro; } }
+        }
+      }
+#endif
       if (live && !found) {   // gated, or map_read_with_mismatch found no seed -> None -> NoMatch (src/align.rs:987)
         ReadRes rr; rr.hdr = qhdr; rr.score = 0; rr.mm = 0; rr.ec_len = 0; rr.bsize = 0; rr.ref = 0; rr.mask = 0;
         b.rres[q] = rr;
