@@ -210,7 +210,9 @@ int nb_callsets_import_device(nb_ctx*, const uint32_t* dev_rows, uint64_t n);   
  * rank owns go into its own table with global pair orders.  An inbox has one region per source rank and the fill
  * cursors stay on the source, so only the 32-byte record stores cross the link (no remote atomics).  When the job ends
  * each rank merges its inbox (nb_route_import) — no all-to-all, no export pass over the key table.
- *   nb_route_create      allocate this context's inbox (world x records_per_peer x 32 B); returns its CUDA IPC handle (64 B)
+ *   nb_route_create      allocate this context's inbox (world x records_per_peer x 32 B); returns its CUDA IPC handle (64 B).
+ *                        Every rank must pass the same world and records_per_peer (a region's place in an inbox is
+ *                        source rank x records_per_peer); a region that fills up fails the job loudly (NB_ERR_OVERFLOW)
  *   nb_route_attach_ipc  one process per GPU: handles = world x 64 B gathered from all ranks (own entry ignored);
  *                        NB_ERR_CUDA when a handle cannot be opened (the host then keeps the NCCL exchange above)
  *   nb_route_attach_ctx  one process driving several contexts / GPUs: peers[world], peers[rank] == this context
