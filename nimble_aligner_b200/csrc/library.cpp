@@ -52,6 +52,7 @@ struct JVal {
   bool b = false; i64 i = 0; double f = 0; std::string s;
   std::vector<JVal> a; std::vector<std::pair<std::string, JVal>> o;
   const JVal& key(const char* k) const { static const JVal null; if (t != Obj) return null; for (auto& kv : o) if (kv.first == k) return kv.second; return null; }
+  JVal& mkey(const char* k) { static thread_local JVal null; null = JVal(); if (t != Obj) return null; for (auto& kv : o) if (kv.first == k) return kv.second; return null; }
   const JVal& at(size_t n) const { static const JVal null; if (t != Arr || n >= a.size()) return null; return a[n]; }
 };
 struct JParser {
@@ -80,7 +81,11 @@ struct JParser {
             utf8(out, v); break; }
           default: return fail("bad escape");
         }
-      } else out += *p++;
+      } else {   // append the whole run up to the next quote or escape (a sequence value is one run of a kilobase)
+        const char* q = p;
+        while (q < e && *q != '"' && *q != '\\') q++;
+        out.append(p, q - p); p = q;
+      }
     }
     if (p >= e) return fail("unterminated string");
     p++; return true;
@@ -118,16 +123,13 @@ struct JParser {
 
 // utils::revcomp, src/utils.rs:61-94 (panics on non-DNA; N and others complement to 'N')
 static bool revcomp(const std::string& s, std::string& out, std::string& err) {
-  out.clear(); out.reserve(s.size());
-  for (size_t i = s.size(); i-- > 0;) {
-    char c = s[i], r;
-    switch (c) {
-      case 'a': r = 't'; break; case 'c': r = 'g'; break; case 't': r = 'a'; break; case 'g': r = 'c'; break; case 'u': r = 'a'; break;
-      case 'A': r = 'T'; break; case 'C': r = 'G'; break; case 'T': r = 'A'; break; case 'G': r = 'C'; break; case 'U': r = 'A'; break;
-      case 'N': case 'n': r = 'N'; break;
-      default: err = std::string("Input sequence base is not DNA: ") + c; return false;
-    }
-    out += r;
+  static const struct Tab { char t[256]; Tab() { memset(t, 0, sizeof t); const char* a = "actguACTGUNn"; const char* b = "tgacaTGACANN"; for (int i = 0; a[i]; i++) t[(unsigned char)a[i]] = b[i]; } } tab;
+  size_t n = s.size();
+  out.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    char c = s[n - 1 - i], r = tab.t[(unsigned char)c];
+    if (!r) { err = std::string("Input sequence base is not DNA: ") + c; return false; }
+    out[i] = r;
   }
   return true;
 }
@@ -139,7 +141,7 @@ static int sanity(const nb_config& c) {  // src/reference_library.rs:209-226
   return NB_OK;
 }
 
-static int parse_library(const char* text, size_t len, int strand_filter, nb_library** out) {
+static int parse_library(const char* text, size_t len, int strand_filter, nb_library** out) {   // (string values are moved, not copied, out of the parsed tree: a 200 k-transcript library is 230 MB of them)
   if (strand_filter < 0 || strand_filter > 3) return fail(NB_ERR_INVALID, "Could not parse strand_filter option.");
   JParser jp{text, text + len, ""};
   JVal v;
@@ -180,14 +182,17 @@ static int parse_library(const char* text, size_t len, int strand_filter, nb_lib
   cfg.strand_filter = strand_filter;
   cfg.discard_nonzero_mismatch = 0;  // src/reference_library.rs:116
 
-  const JVal& r = v.at(1);
-  auto to_strs = [&](const JVal& x, const char* name, std::vector<std::string>& o) -> bool {
+  static thread_local JVal jnull; jnull = JVal();
+  JVal& r = (v.t == JVal::Arr && v.a.size() > 1) ? v.a[1] : jnull;
+  auto to_strs = [&](JVal& x, const char* name, std::vector<std::string>& o) -> bool {
     if (x.t != JVal::Arr) { set_error(std::string("Error -- could not parse ") + name + " as array"); return false; }
-    for (auto& s : x.a) { if (s.t != JVal::Str) { set_error(std::string("Error -- could not parse ") + name + " element as a string"); return false; } o.push_back(s.s); }
+    o.reserve(x.a.size());
+    for (auto& s : x.a) { if (s.t != JVal::Str) { set_error(std::string("Error -- could not parse ") + name + " element as a string"); return false; } o.push_back(std::move(s.s)); }
+    std::vector<JVal>().swap(x.a);
     return true;
   };
   std::vector<std::string> headers;
-  if (!to_strs(r.key("headers"), "headers", headers)) return NB_ERR_PARSE;
+  if (!to_strs(r.mkey("headers"), "headers", headers)) return NB_ERR_PARSE;
   auto col_index = [&](const std::string& h) -> int { for (size_t i = 0; i < headers.size(); i++) if (headers[i] == h) return (int)i; return -1; };
   int name_idx = col_index("sequence_name");
   if (name_idx < 0) return fail(NB_ERR_PARSE, "Could not find header sequence_name");
@@ -195,7 +200,7 @@ static int parse_library(const char* text, size_t len, int strand_filter, nb_lib
   if (!group_on.empty()) { gidx = col_index(group_on); if (gidx < 0) return fail(NB_ERR_PARSE, "Error -- could not find column for group_on " + group_on); }
   int seq_idx = col_index("sequence");
   if (seq_idx < 0) return fail(NB_ERR_PARSE, "Error -- could not find sequences column");
-  const JVal& cols = r.key("columns");
+  JVal& cols = r.mkey("columns");
   if (cols.t != JVal::Arr) return fail(NB_ERR_PARSE, "Error -- could not parse columns as array");
   std::vector<std::vector<std::string>> columns;
   for (auto& cj : cols.a) { columns.emplace_back(); if (!to_strs(cj, "column", columns.back())) return NB_ERR_PARSE; }
@@ -210,13 +215,14 @@ static int parse_library(const char* text, size_t len, int strand_filter, nb_lib
   for (auto& cc : lib->columns) cc.reserve(2 * n_rows);
   std::string rc, err;
   for (size_t row = 0; row < n_rows; row++) {  // src/reference_library.rs:130-153
-    std::string seq = columns[seq_idx][row];
+    std::string& seq = columns[seq_idx][row];
     for (char& ch : seq) { if (ch == 'U') ch = 'T'; else if (ch == 'u') ch = 't'; }
     if (!revcomp(seq, rc, err)) { delete lib; return fail(NB_ERR_PARSE, err); }
     for (size_t ci = 0; ci < columns.size(); ci++) {
-      if ((int)ci == seq_idx) { lib->columns[ci].push_back(seq); lib->columns[ci].push_back(rc); }
-      else if ((int)ci == name_idx) { lib->columns[ci].push_back(columns[ci][row]); lib->columns[ci].push_back(columns[ci][row] + "\xC2\xA7rev"); }
-      else { lib->columns[ci].push_back(columns[ci][row]); lib->columns[ci].push_back(columns[ci][row]); }
+      std::vector<std::string>& dst = lib->columns[ci];
+      if ((int)ci == seq_idx) { dst.push_back(std::move(seq)); dst.push_back(rc); }
+      else if ((int)ci == name_idx) { dst.push_back(columns[ci][row] + "\xC2\xA7rev"); dst.push_back(std::move(columns[ci][row])); std::swap(dst[dst.size() - 2], dst[dst.size() - 1]); }
+      else { dst.push_back(columns[ci][row]); dst.push_back(std::move(columns[ci][row])); }
     }
   }
   int rcode = sanity(cfg);
@@ -306,9 +312,13 @@ int nb_library_parse_json(const char* text, size_t len, int strand_filter, nb_li
 }
 int nb_library_load_json(const char* path, int strand_filter, nb_library** out) {
   if (!path || !out) return fail(NB_ERR_INVALID, "null argument");
-  std::ifstream f(path, std::ios::binary);
+  FILE* f = fopen(path, "rb");
   if (!f) return fail(NB_ERR_IO, std::string("Error -- could not read reference library ") + path);
-  std::stringstream ss; ss << f.rdbuf(); std::string s = ss.str();
+  std::string s; char buf[1 << 16]; size_t got;
+  if (fseek(f, 0, SEEK_END) == 0) { long sz = ftell(f); if (sz > 0) s.reserve((size_t)sz); rewind(f); }
+  while ((got = fread(buf, 1, sizeof buf, f)) > 0) s.append(buf, got);
+  bool bad = ferror(f) != 0; fclose(f);
+  if (bad) return fail(NB_ERR_IO, std::string("Error -- could not read reference library ") + path);
   return parse_library(s.data(), s.size(), strand_filter, out);
 }
 int nb_library_from_columns(const char* const* headers, uint32_t n_headers, const char* const* const* columns, uint32_t n_rows,
