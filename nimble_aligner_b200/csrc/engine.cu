@@ -503,6 +503,7 @@ int nb_counts_reset(nb_ctx* c) {
   CK(cudaSetDevice(c->device));
   if (c->tables_ready) { CK(cudaStreamSynchronize(c->stream)); c->tables_ready = false; }
   c->mode = -1; c->folded = false; c->pairs_seen = 0; c->keys_upper = 0; c->have_last = false; c->n_rows_dev = 0;
+  if (c->d_routecur.p) CK(cudaMemsetAsync(c->d_routecur.p, 0, nbk::ROUTE_MAX * 8, c->stream));   // a job abandoned before nb_route_sent must not leak its records into the next one
   return NB_OK;
 }
 
