@@ -169,11 +169,15 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = None
+    if world > 1:   # one rank per GPU: keep each rank's pinned batches on its GPU's NUMA node (N=1 stays unbound: its cpu_baseline leg uses every core)
+        from nimble_aligner_b200.multigpu import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local_rank)
     import torch
     import torch.distributed as dist
     import nimble_aligner_b200 as nb
     import synth
-    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -297,6 +301,7 @@ def main():
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer (f64 thresholds)", "data": "synthetic",
            "config": {"workload": "C2: synthetic 1k-transcript family library (200x5, seed 1234) x %d 2x150 bp pairs per GPU, FASTQ-mode whole-run scope" % n,
                       "num_mismatches": args.mismatches, "merge": ("p2p-routed (k_pair stores key records into their owners' inboxes over NVLink)" if routed else "nccl all-to-all at job end") if world > 1 else "none (one GPU)",
+                      "numa_bind": ("each rank bound to the %d CPUs local to its GPU" % numa_cpus) if numa_cpus else "none",
                       "pairs_per_gpu": n, "reads_per_step": n_reads * world, "chunk_pairs": args.chunk, "l2": "inputs (%.1f GB ASCII per step) exceed the 126 MB L2" % ((int(o1[-1]) + int(o2[-1])) / 1e9),
                       "index_device_mb": ix.stats()["device_bytes"] / 1e6, "index_build_s": index_build_s, "unique_pair_keys": int(uniq_dev), "callsets_counted": len(counts_dev)},
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_host},

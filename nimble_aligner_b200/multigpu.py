@@ -26,6 +26,29 @@ import time
 import numpy as np
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Restricts this process to the CPUs NVML reports as local to its GPU, before any pinned buffer is allocated, so that
+    the pinned batches live on the GPU's own NUMA node (first touch) and H2D copies do not cross the socket link — with
+    eight ranks feeding eight GPUs the host fabric, not PCIe, is the limit.  No-op on a single-node host, when NVML or
+    the affinity call is unavailable, or with NB_NO_NUMA_BIND=1.  Returns the number of CPUs bound to, or None."""
+    if os.environ.get("NB_NO_NUMA_BIND"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 1) + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if len(cpus) >= 2 and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception as e:   # no NVML, no permission, cpuset mismatch: stay unbound
+        print("numa bind skipped: %s" % e, file=sys.stderr)
+    return None
+
+
 def setup_routes(ctx, torch, dist, rank, world, device, pair_base, records_per_peer):
     """Peer routing (nb_route_*, include/nimble_b200.h): every rank creates its inbox, the CUDA IPC handles travel by
     all_gather, every rank opens its peers' inboxes.  Returns False — on every rank — when any rank could not (no NVLink
