@@ -160,11 +160,15 @@ def _worker(rank, world, port, q):
         o = orc.Oracle(ocfg, oref)
         n = len(o1) - 1; per = n // world; lo, hi = rank * per, (rank + 1) * per if rank + 1 < world else n
         pairs = _per_pair(o, ocfg, r1, o1, r2, o2, lo, hi)
+        import nimble_aligner_b200.multigpu as mg
+        mg._ROUTED_CAP[0] = 16          # far below the dictionary sizes here: the block capacity must ratchet up, alike on both ranks
         for routed in (False, True):
             shard = RoutedModelShard(sorted(L.names), rank, world) if routed else ModelShard(sorted(L.names))
             for i, (key, ins, cs) in enumerate(pairs):
                 shard.add_pair(key, lo + i + 1, ins, cs)
             raw, uniq = merge_across_ranks(shard, torch, dist, rank, world, "cpu", routed=routed)
+            if routed:
+                assert mg._ROUTED_CAP[0] >= len(shard.cs) > 16
             if rank == 0:
                 q.put(({cs: int(c) for cs, c in zip(raw["callsets"], raw["dense_counts"].tolist()) if c}, uniq))
     finally:
