@@ -47,6 +47,33 @@ def test_library_loader_matches_oracle_loader(name):
     assert names == ref.columns[ref.sequence_name_idx] and seqs == ref.columns[ref.sequence_idx]
 
 
+@pytest.mark.parametrize("ensure_ascii", [True, False])
+def test_library_loader_strings_with_escapes_and_long_runs(ensure_ascii):
+    """The JSON reader appends unescaped runs wholesale and moves strings out of the parsed tree: escapes in the middle of
+    a run, \\u escapes incl. surrogate pairs, raw UTF-8, empty strings and a 100 kb sequence must come out as serde_json
+    (here: Python's json) reads them, and every row must get its revcomp twin (src/reference_library.rs:130-153)."""
+    import json
+    rng = random.Random(5)
+    names = ['plain', 'quote"inside', 'back\\slash', 'tab\there', '\u00e9-accent', 'emoji-\U0001F9EC-dna', 'slash/', 'ctl\x01', '', 'trailing\\']
+    seqs = ["".join(rng.choice("ACGTUacgtuNn") for _ in range(n)) for n in (31, 40, 100_000, 64, 1, 33, 257, 1024, 30, 4096)]
+    groups = ['g"1', 'g"1', '', 'g\\2', 'g\\2', 'g3', 'g3', '\u00e9', '\u00e9', '']
+    cfg = dict(score_percent=0.5, score_filter=25, score_threshold=50, num_mismatches=1, discard_multiple_matches=False, require_valid_pair=True,
+               discard_multi_hits=0, intersect_level=1, max_hits_to_report=4, group_on="grp", trim_target_length=40, trim_strictness=0.9)
+    obj = [cfg, {"headers": ["sequence_name", "grp", "sequence"], "columns": [names, groups, seqs]}]
+    text = json.dumps(obj, ensure_ascii=ensure_ascii, indent=1 if ensure_ascii else None)
+    lib = nb.Library.from_text(text, "unstranded")
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "a": "t", "c": "g", "g": "c", "t": "a", "N": "N", "n": "N"}
+    want_names, want_groups, want_seqs = [], [], []
+    for n, g, sq in zip(names, groups, seqs):
+        sq = sq.replace("U", "T").replace("u", "t")
+        want_names += [n, n + "\u00a7rev"]; want_groups += [g, g]
+        want_seqs += [sq, "".join(comp[c] for c in reversed(sq))]
+    assert lib.column(0) == want_names and lib.column(1) == want_groups and lib.column(2) == want_seqs
+    assert lib.headers == ["sequence_name", "grp", "sequence"] and lib.group_on == 1
+    c = lib.config
+    assert (c.score_percent, c.num_mismatches, c.max_hits_to_report, bool(c.require_valid_pair), c.reference_genome_size) == (0.5, 1, 4, True, 10)
+
+
 @pytest.mark.parametrize("name", ["reference-library-missing-fields.json", "reference-library-types-broken.json", "reference-library-broken-format.json"])
 def test_library_loader_rejects_what_the_reference_panics_on(name):   # src/reference_library.rs:256-300
     with pytest.raises(nb.NbError):
