@@ -9,6 +9,9 @@
 // open-addressed bucketed table (khash.h) over the distinct k-mers, chain walk from the chain starts on threads.
 #include <algorithm>
 #include <atomic>
+#include <ctime>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -26,7 +29,12 @@ struct Occ { u64 kmer; u32 id; u32 lr; };  // kmer big-endian (first base most s
 inline u64 mix64(u64 x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
 
 // big-endian 60-bit k-mer -> device form (base i at bits 2i)
-inline u64 to_device_form(u64 be) { u64 v = 0; for (int i = 0; i < K; i++) { v |= ((be >> (2 * (K - 1 - i))) & 3) << (2 * i); } return v; }
+inline u64 to_device_form(u64 be) {   // reverse the 32 two-bit groups of the word, then drop the two groups that were the unused top bits
+  u64 x = __builtin_bswap64(be);
+  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+  return x >> (2 * (32 - K));
+}
 
 void parallel_for(int n_threads, u64 n, const std::function<void(u64, u64, int)>& fn) {
   if (n_threads <= 1 || n < 4096) { fn(0, n, 0); return; }
@@ -47,11 +55,18 @@ struct Table {
     }
     return ~0ULL;
   }
-  void insert(u64 dk, u64 v) {   // distinct keys, load < 1: always finds room
-    std::vector<u64>& key = *mkey; std::vector<u64>& val = *mval;
-    u64 b = nb_table_bucket(dk, nbuckets);
+  // distinct keys, load < 1: always finds room.  Safe from several threads at once: a slot is claimed by compare-and-swap
+  // and slots of a bucket are only tried in order, so the occupied slots of a bucket stay a prefix and a key moves on to
+  // the next bucket only when its home bucket is full — what find() and the device probe rely on.  Which of its
+  // candidate slots a key ends up in depends on the interleaving (nb_index_compare looks keys up instead of comparing slots).
+  void insert(u64 dk, u64 v) {
+    u64* key = mkey->data(); u64* val = mval->data();
+    u64 b = nb_table_bucket(dk, nbuckets), want = dk | (1ULL << 63);
     for (;;) {
-      for (u64 s = 4 * b; s < 4 * b + 4; s++) if (!key[s]) { key[s] = dk | (1ULL << 63); val[s] = v; return; }
+      for (u64 s = 4 * b; s < 4 * b + 4; s++) {
+        u64 expect = 0;
+        if (__atomic_load_n(&key[s], __ATOMIC_RELAXED) == 0 && __atomic_compare_exchange_n(&key[s], &expect, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { val[s] = v; return; }
+      }
       if (++b == nbuckets) b = 0;
     }
   }
@@ -92,6 +107,10 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
   if (seqs.size() >= 0xFFFFFFFFull) return fail(NB_ERR_UNSUPPORTED, "too many reference sequences");
   nb_index* ix = new nb_index();
   ix->n_sequences = seqs.size();
+  static const bool stats = getenv("NB_INDEX_STATS") != nullptr;   // phase times on stderr
+  auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+  double t_prev = now();
+  auto phase = [&](const char* name) { if (!stats) return; double t = now(); fprintf(stderr, "index build: %-28s %.2f s\n", name, t - t_prev); t_prev = t; };
   // ---- 1. enumerate occurrences
   std::vector<u64> occ_off(seqs.size() + 1, 0);
   for (size_t s = 0; s < seqs.size(); s++) occ_off[s + 1] = occ_off[s] + (seqs[s].size() >= (size_t)K ? seqs[s].size() - K + 1 : 0);
@@ -112,6 +131,7 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
       }
     }
   });
+  phase("enumerate");
   // ---- 2. bucketed parallel sort by (kmer, id): bucket = top 10 bits (first 5 bases)
   const int NB = 1024;
   std::vector<Occ> sorted(n_occ);
@@ -131,6 +151,7 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
     std::vector<std::thread> th; for (int t = 1; t < n_threads; t++) th.emplace_back(work);
     work(); for (auto& x : th) x.join();
   }
+  phase("sort");
   std::vector<Occ>().swap(occ);
   // ---- 3. group into distinct k-mers (sorted order): exts, colour signature; intern colours
   std::vector<u64> gstart;  // start offset of each distinct k-mer in `sorted`
@@ -161,28 +182,50 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
       kmers[g] = sorted[gstart[g]].kmer; L[g] = l; R[g] = r; sig_a[g] = ha; sig_b[g] = hb;
     }
   });
+  phase("group + signatures");
   {
+    // colours are numbered in order of first appearance (ascending k-mer): every thread collects the first k-mer of each
+    // signature in its range, the per-thread maps are merged (minimum first k-mer), signatures sorted by that k-mer get
+    // their ids, and a second parallel pass labels the k-mers from the finished (read-only) map
     struct Sig { u64 a, b; bool operator==(const Sig& o) const { return a == o.a && b == o.b; } };
     struct SigHash { size_t operator()(const Sig& s) const { return (size_t)(s.a ^ (s.b * 0x9E3779B97F4A7C15ULL)); } };
-    std::unordered_map<Sig, u32, SigHash> intern;
+    int T = (n_threads <= 1 || n < 4096) ? 1 : n_threads;
+    std::vector<std::unordered_map<Sig, u64, SigHash>> local(T);
+    for (auto& m : local) m.reserve(1 << 16);
+    parallel_for(n_threads, n, [&](u64 a, u64 b, int t) {
+      auto& m = local[t]; u64 pa = 0, pb = 0; bool have = false;
+      for (u64 g = a; g < b; g++) {
+        if (have && sig_a[g] == pa && sig_b[g] == pb) continue;
+        pa = sig_a[g]; pb = sig_b[g]; have = true;
+        Sig k{pa, pb}; if (m.find(k) == m.end()) m.emplace(k, g);   // keeps the first (smallest) g of the range; (emplace alone allocates a node before it looks)
+      }
+    });
+    std::unordered_map<Sig, u64, SigHash> first;
+    for (auto& m : local) { for (auto& kv : m) { auto it = first.find(kv.first); if (it == first.end()) first.emplace(kv.first, kv.second); else if (kv.second < it->second) it->second = kv.second; } m.clear(); }
+    std::vector<std::pair<u64, Sig>> order; order.reserve(first.size());
+    for (auto& kv : first) order.emplace_back(kv.second, kv.first);
+    std::sort(order.begin(), order.end(), [](const std::pair<u64, Sig>& x, const std::pair<u64, Sig>& y) { return x.first < y.first; });
+    std::unordered_map<Sig, u32, SigHash> intern; intern.reserve(order.size() * 2);
     ix->col_off.push_back(0);
-    u64 prev_a = 0, prev_b = 0; u32 prev_c = NONE32;
-    for (u64 g = 0; g < n; g++) {
-      if (prev_c != NONE32 && sig_a[g] == prev_a && sig_b[g] == prev_b) { col[g] = prev_c; continue; }
-      auto it = intern.find(Sig{sig_a[g], sig_b[g]});
-      u32 c;
-      if (it == intern.end()) {
-        c = (u32)ix->col_off.size() - 1; intern.emplace(Sig{sig_a[g], sig_b[g]}, c);
-        u32 last = NONE32;
-        for (u64 i = gstart[g]; i < gstart[g + 1]; i++) if (sorted[i].id != last) { last = sorted[i].id; ix->col_ids.push_back(last); }
-        if (ix->col_ids.size() >= 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "colour table exceeds 2^32 entries"); }
-        ix->col_off.push_back((u32)ix->col_ids.size());
-      } else c = it->second;
-      col[g] = c; prev_a = sig_a[g]; prev_b = sig_b[g]; prev_c = c;
+    for (u32 c = 0; c < order.size(); c++) {
+      intern.emplace(order[c].second, c);
+      u64 g = order[c].first; u32 last = NONE32;
+      for (u64 i = gstart[g]; i < gstart[g + 1]; i++) if (sorted[i].id != last) { last = sorted[i].id; ix->col_ids.push_back(last); }
+      if (ix->col_ids.size() >= 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "colour table exceeds 2^32 entries"); }
+      ix->col_off.push_back((u32)ix->col_ids.size());
     }
+    parallel_for(n_threads, n, [&](u64 a, u64 b, int) {
+      u64 pa = 0, pb = 0; u32 pc = NONE32;
+      for (u64 g = a; g < b; g++) {
+        if (pc != NONE32 && sig_a[g] == pa && sig_b[g] == pb) { col[g] = pc; continue; }
+        pa = sig_a[g]; pb = sig_b[g]; pc = intern.find(Sig{pa, pb})->second; col[g] = pc;
+      }
+    });
   }
+  phase("colour interning");
   { int urc = nb_build_universes(ix, (u32)seqs.size()); if (urc) { delete ix; return urc; } }
   std::vector<Occ>().swap(sorted); std::vector<u64>().swap(gstart); std::vector<u64>().swap(sig_a); std::vector<u64>().swap(sig_b);
+  phase("universes");
   // ---- 4. bucketed cuckoo table over distinct k-mers (value = distinct index for now), load <= 0.5
   u64 slots = 0;
   {
@@ -191,10 +234,11 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
     ix->table_buckets = nbk; slots = 4 * nbk;
     ix->table_key.assign(slots, 0); ix->table_val.assign(slots, 0);
     Table tb{ix->table_key, &ix->table_key, &ix->table_val, nbk};
-    for (u64 g = 0; g < n; g++) tb.insert(to_device_form(kmers[g]), g);
+    parallel_for(n_threads, n, [&](u64 a, u64 b, int) { for (u64 g = a; g < b; g++) tb.insert(to_device_form(kmers[g]), g); });
   }
   Table tab{ix->table_key, nullptr, nullptr, ix->table_buckets};
   auto index_of = [&](u64 be) -> u64 { u64 s = tab.find(to_device_form(be)); return s == ~0ULL ? ~0ULL : ix->table_val[s]; };
+  phase("table insert");
   // ---- 5. join relation
   std::vector<u32> succ(n, NONE32), pred(n, NONE32);
   if (n >= 0xFFFFFFFFull) { delete ix; return fail(NB_ERR_UNSUPPORTED, "more than 2^32 distinct k-mers"); }
@@ -206,6 +250,7 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
       if (j != ~0ULL && __builtin_popcount(L[j]) == 1 && col[g] == col[j]) { succ[g] = (u32)j; pred[j] = (u32)g; }  // pred[j] has a single writer: |L(j)| == 1
     }
   });
+  phase("join");
   // ---- 6. unitigs: starts = k-mers without a joining predecessor; pure cycles start at their smallest k-mer
   std::vector<u64> starts;
   for (u64 g = 0; g < n; g++) if (pred[g] == NONE32) starts.push_back(g);
@@ -218,6 +263,7 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
   for (u64 g = 0; g < n; g++) if (node_of[g] == NONE32) {  // cycles (rare), ascending k-mer order
     u32 id = (u32)node_len.size(); auto r = walk(g, id); node_first.push_back(g); node_last.push_back(r.first); node_len.push_back(r.second);
   }
+  phase("chain walks");
   u64 n_nodes = node_len.size();
   std::vector<u64> base_start(n_nodes + 1, 0);
   for (u64 i = 0; i < n_nodes; i++) base_start[i + 1] = base_start[i] + node_len[i] + K - 1;
@@ -238,6 +284,7 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
       nr.exts_hi = (u32)L[node_first[i]] | ((u32)R[node_last[i]] << 4) | ((u32)(base_start[i] >> 32) << 8);
     }
   });
+  phase("unitig bases + nodes");
   // table values -> (node, offset)
   parallel_for(n_threads, slots, [&](u64 a, u64 b, int) { for (u64 h = a; h < b; h++) if (ix->table_key[h] >> 63) { u64 g = ix->table_val[h]; ix->table_val[h] = (u64)node_of[g] | ((u64)off_of[g] << 32); } });
   // distinct index of a k-mer is gone from the table now; edges need start/end node of neighbouring k-mers, which the
@@ -253,6 +300,7 @@ int nb_build_index_impl(const std::vector<std::vector<u8>>& seqs, int n_threads,
       }
     }
   });
+  phase("table values + edges");
   if (bad) { delete ix; return fail(NB_ERR_INVALID, "internal: de Bruijn edge does not land on a unitig boundary"); }
   *out = ix;
   return NB_OK;
