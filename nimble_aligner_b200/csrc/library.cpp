@@ -141,8 +141,29 @@ static int sanity(const nb_config& c) {  // src/reference_library.rs:209-226
   return NB_OK;
 }
 
+// fs::read_to_string (src/reference_library.rs:21) refuses a file that is not UTF-8: so does this loader
+static bool valid_utf8(const char* t, size_t n) {
+  const unsigned char* p = (const unsigned char*)t; const unsigned char* e = p + n;
+  while (p < e) {
+    if (e - p >= 8) { u64 w; memcpy(&w, p, 8); if (!(w & 0x8080808080808080ULL)) { p += 8; continue; } }
+    unsigned c = *p;
+    if (c < 0x80) { p++; continue; }
+    int need; unsigned cp, lo;
+    if ((c & 0xE0) == 0xC0) { need = 1; cp = c & 0x1F; lo = 0x80; }
+    else if ((c & 0xF0) == 0xE0) { need = 2; cp = c & 0x0F; lo = 0x800; }
+    else if ((c & 0xF8) == 0xF0) { need = 3; cp = c & 0x07; lo = 0x10000; }
+    else return false;
+    if (e - p <= need) return false;
+    for (int i = 1; i <= need; i++) { if ((p[i] & 0xC0) != 0x80) return false; cp = (cp << 6) | (p[i] & 0x3F); }
+    if (cp < lo || cp > 0x10FFFF || (cp >= 0xD800 && cp < 0xE000)) return false;
+    p += need + 1;
+  }
+  return true;
+}
+
 static int parse_library(const char* text, size_t len, int strand_filter, nb_library** out) {   // (string values are moved, not copied, out of the parsed tree: a 200 k-transcript library is 230 MB of them)
   if (strand_filter < 0 || strand_filter > 3) return fail(NB_ERR_INVALID, "Could not parse strand_filter option.");
+  if (!valid_utf8(text, len)) return fail(NB_ERR_PARSE, "Error -- could not read reference library: stream did not contain valid UTF-8");
   JParser jp{text, text + len, ""};
   JVal v;
   if (!jp.val(v)) return fail(NB_ERR_PARSE, "Error -- could not parse reference library JSON: " + jp.err);

@@ -74,6 +74,36 @@ def test_library_loader_strings_with_escapes_and_long_runs(ensure_ascii):
     assert (c.score_percent, c.num_mismatches, c.max_hits_to_report, bool(c.require_valid_pair), c.reference_genome_size) == (0.5, 1, 4, True, 10)
 
 
+def test_library_loader_survives_mutated_input():
+    """A library file is outside input: truncations, flipped bytes, stray structural characters and deletions must end in a
+    parsed library or an NbError (the reference panics with a message), never in a crash; bytes that are not UTF-8 are
+    refused like fs::read_to_string does (src/reference_library.rs:21)."""
+    base = open(os.path.join(G, "libraries", "basic.json"), "rb").read()
+    rng = random.Random(1)
+    parsed = rejected = 0
+    for _ in range(600):
+        b = bytearray(base)
+        k = rng.randint(0, 3)
+        if k == 0:
+            b = b[:rng.randint(0, len(b))]
+        elif k == 1:
+            for _ in range(rng.randint(1, 4)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        elif k == 2:
+            i = rng.randrange(len(b)); b[i:i] = bytes(rng.choice(b'{}[]",:\\u0123 \n') for _ in range(rng.randint(1, 6)))
+        else:
+            i = rng.randrange(len(b)); del b[i:min(len(b), i + rng.randint(1, 50))]
+        try:
+            lib = nb.Library.from_text(bytes(b), "unstranded")
+        except nb.NbError:
+            rejected += 1
+            continue
+        parsed += 1
+        bytes(b).decode()                                    # whatever was accepted is UTF-8
+        assert lib.n_rows % 2 == 0 and len(lib.group_names()) <= lib.n_rows
+    assert parsed > 20 and rejected > 200
+
+
 @pytest.mark.parametrize("name", ["reference-library-missing-fields.json", "reference-library-types-broken.json", "reference-library-broken-format.json"])
 def test_library_loader_rejects_what_the_reference_panics_on(name):   # src/reference_library.rs:256-300
     with pytest.raises(nb.NbError):
