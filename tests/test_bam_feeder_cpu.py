@@ -54,3 +54,51 @@ def test_parallel_grouping_equals_the_serial_readers(tmp_path, force_paired):
         del os.environ["NB_BAM_SERIAL_GROUPING"]
     pa, se = open(a, "rb").read(), open(b, "rb").read()
     assert pa == se and pa.count(b"\n") > (500 if force_paired else 5000)
+
+
+def test_feeder_fails_loudly_on_damaged_bam(tmp_path):
+    """A BAM is outside input: truncated files, flipped bytes in the compressed stream and damaged record fields inside
+    intact BGZF blocks must end in groups or an NbError (the reference panics inside htslib / on unwrap), never in a crash."""
+    import random
+    import struct
+    import zlib
+    L = synth.SynthLibrary(seed=1234, n_fam=20, n_all=5)
+    base = open(make_bam(str(tmp_path / "t.bam"), L, n_groups=30), "rb").read()
+    payload, i = b"", 0
+    while i < len(base):                                   # BGZF blocks -> the BAM byte stream
+        xlen = struct.unpack_from("<H", base, i + 10)[0]; bsize = struct.unpack_from("<H", base, i + 16)[0] + 1
+        payload += zlib.decompress(base[i + 12 + xlen:i + bsize - 8], -15); i += bsize
+
+    def bgzf(data):
+        out = b""
+        for k in range(0, max(len(data), 1), 20000):
+            c = data[k:k + 20000]; co = zlib.compressobj(6, zlib.DEFLATED, -15); cd = co.compress(c) + co.flush()
+            out += b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(cd) + 25) + cd + struct.pack("<II", zlib.crc32(c) & 0xFFFFFFFF, len(c))
+        return out + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    rng = random.Random(7)
+    ok = err = 0
+    for it in range(60):
+        kind = it % 5
+        if kind == 0:
+            b = base[:rng.randint(0, len(base))]
+        elif kind == 1:
+            b = bytearray(base)
+            for _ in range(rng.randint(1, 5)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        else:
+            p = bytearray(payload)
+            if kind == 2:
+                for _ in range(rng.randint(1, 6)):
+                    p[rng.randrange(len(p))] = rng.randrange(256)
+            elif kind == 3:
+                p = p[:rng.randint(0, len(p))]
+            else:
+                struct.pack_into("<i", p, rng.randrange(len(p) - 4), rng.choice([-1, 0, 1, 2 ** 31 - 1, -2 ** 31, 70000, 3]))
+            b = bgzf(bytes(p))
+        path = str(tmp_path / "m.bam"); open(path, "wb").write(bytes(b))
+        try:
+            nb.bam_dump_groups(path, str(tmp_path / "g.tsv"), force_bam_paired=bool(it & 1), num_cores=2)
+            ok += 1
+        except nb.NbError:
+            err += 1
+    assert ok + err == 60 and err >= 5
