@@ -366,31 +366,61 @@ uint64_t nb_index_dump(const nb_index* ix, char* buf, uint64_t cap) {
 
 }  // extern "C"
 
-// ---- on-disk index cache: the flat arrays exactly as they are uploaded to HBM
+// ---- on-disk index cache: the flat arrays exactly as they are uploaded to HBM, followed by a 64-bit
+// checksum of everything before it: a damaged cache would otherwise send the kernels out of bounds
 namespace {
-const char INDEX_MAGIC[8] = {'N', 'B', '2', 'I', 'D', 'X', '0', '5'};
-template <class T> bool put_vec(FILE* f, const std::vector<T>& v) { u64 n = v.size(); return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n); }
-template <class T> bool get_vec(FILE* f, std::vector<T>& v) { u64 n; if (fread(&n, 8, 1, f) != 1 || n > (1ULL << 40) / sizeof(T)) return false; v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
+const char INDEX_MAGIC[8] = {'N', 'B', '2', 'I', 'D', 'X', '0', '6'};
+struct Sum {
+  u64 h = 0x243F6A8885A308D3ULL;
+  void add(const void* p, size_t bytes) {
+    const u8* b = (const u8*)p; size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) { u64 w; memcpy(&w, b + i, 8); h = (h ^ w) * 0x9E3779B97F4A7C15ULL; h ^= h >> 29; }
+    if (i < bytes) { u64 w = 0; memcpy(&w, b + i, bytes - i); h = (h ^ w) * 0x9E3779B97F4A7C15ULL; h ^= h >> 29; }
+    h = (h ^ bytes) * 0xC2B2AE3D27D4EB4FULL; h ^= h >> 31;
+  }
+};
+template <class T> bool put_vec(FILE* f, const std::vector<T>& v, Sum& sum) {
+  u64 n = v.size(); sum.add(&n, 8); if (n) sum.add(v.data(), n * sizeof(T));
+  return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
+}
+template <class T> bool get_vec(FILE* f, std::vector<T>& v, Sum& sum, u64& left) {
+  u64 n;
+  if (left < 8 || fread(&n, 8, 1, f) != 1) return false;
+  left -= 8;
+  if (n > left / sizeof(T)) return false;   // an element count the file cannot hold (damaged header): refuse before allocating
+  v.resize(n);
+  if (n && fread(v.data(), sizeof(T), n, f) != n) return false;
+  left -= n * sizeof(T);
+  sum.add(&n, 8); if (n) sum.add(v.data(), n * sizeof(T));
+  return true;
+}
 }
 extern "C" int nb_index_save(const nb_index* ix, const char* path) {
   if (!ix || !path) return fail(NB_ERR_INVALID, "null argument");
   FILE* f = fopen(path, "wb"); if (!f) return fail(NB_ERR_IO, std::string("could not open ") + path);
   u64 scalars[4] = {ix->table_buckets, ix->n_kmers, ix->unitig_bases, ix->n_sequences};
-  bool ok = fwrite(INDEX_MAGIC, 8, 1, f) == 1 && fwrite(scalars, 8, 4, f) == 4 && put_vec(f, ix->table_key) && put_vec(f, ix->table_val) && put_vec(f, ix->unitig) &&
-            put_vec(f, ix->node) && put_vec(f, ix->redge) && put_vec(f, ix->ledge) && put_vec(f, ix->col_off) && put_vec(f, ix->col_ids) && put_vec(f, ix->col_meta);
+  Sum sum; sum.add(scalars, sizeof scalars);
+  bool ok = fwrite(INDEX_MAGIC, 8, 1, f) == 1 && fwrite(scalars, 8, 4, f) == 4 && put_vec(f, ix->table_key, sum) && put_vec(f, ix->table_val, sum) && put_vec(f, ix->unitig, sum) &&
+            put_vec(f, ix->node, sum) && put_vec(f, ix->redge, sum) && put_vec(f, ix->ledge, sum) && put_vec(f, ix->col_off, sum) && put_vec(f, ix->col_ids, sum) && put_vec(f, ix->col_meta, sum);
+  ok = ok && fwrite(&sum.h, 8, 1, f) == 1;
   ok = (fclose(f) == 0) && ok;
   return ok ? NB_OK : fail(NB_ERR_IO, std::string("short write on ") + path);
 }
 extern "C" int nb_index_load(const char* path, nb_index** out) {
   if (!path || !out) return fail(NB_ERR_INVALID, "null argument");
   FILE* f = fopen(path, "rb"); if (!f) return fail(NB_ERR_IO, std::string("could not open ") + path);
-  nb_index* ix = new nb_index(); char magic[8]; u64 scalars[4];
-  bool ok = fread(magic, 8, 1, f) == 1 && !memcmp(magic, INDEX_MAGIC, 8) && fread(scalars, 8, 4, f) == 4 && get_vec(f, ix->table_key) && get_vec(f, ix->table_val) && get_vec(f, ix->unitig) &&
-            get_vec(f, ix->node) && get_vec(f, ix->redge) && get_vec(f, ix->ledge) && get_vec(f, ix->col_off) && get_vec(f, ix->col_ids) && get_vec(f, ix->col_meta);
+  u64 left = 0;
+  if (fseek(f, 0, SEEK_END) == 0) { long long sz = ftello(f); if (sz > 0) left = (u64)sz; rewind(f); }
+  nb_index* ix = new nb_index(); char magic[8]; u64 scalars[4], want = 0; Sum sum;
+  bool ok = left >= 48 && fread(magic, 8, 1, f) == 1 && !memcmp(magic, INDEX_MAGIC, 8) && fread(scalars, 8, 4, f) == 4;
+  if (ok) { left -= 40; sum.add(scalars, sizeof scalars); }
+  ok = ok && get_vec(f, ix->table_key, sum, left) && get_vec(f, ix->table_val, sum, left) && get_vec(f, ix->unitig, sum, left) &&
+       get_vec(f, ix->node, sum, left) && get_vec(f, ix->redge, sum, left) && get_vec(f, ix->ledge, sum, left) && get_vec(f, ix->col_off, sum, left) && get_vec(f, ix->col_ids, sum, left) && get_vec(f, ix->col_meta, sum, left);
+  ok = ok && left == 8 && fread(&want, 8, 1, f) == 1 && want == sum.h;
   fclose(f);
   if (ok) { ix->table_buckets = scalars[0]; ix->n_kmers = scalars[1]; ix->unitig_bases = scalars[2]; ix->n_sequences = scalars[3];
     ok = ix->table_buckets >= 1 && ix->table_key.size() == 4 * ix->table_buckets && ix->table_val.size() == ix->table_key.size() && ix->redge.size() == 4 * ix->node.size() && ix->ledge.size() == ix->redge.size() &&
          !ix->col_off.empty() && ix->col_meta.size() == 4 * (ix->col_off.size() - 1) && ix->unitig.size() >= (ix->unitig_bases + 31) / 32 + 2; }
-  if (!ok) { delete ix; return fail(NB_ERR_PARSE, std::string("not a nimble_b200 index file (or truncated): ") + path); }
+  if (!ok) { delete ix; return fail(NB_ERR_PARSE, std::string("not a nimble_b200 index file (or truncated / damaged): ") + path); }
   *out = ix; return NB_OK;
 }

@@ -200,6 +200,23 @@ def test_index_save_load_roundtrip(tmp_path):
         nb.Index.load(tmp_path / "bad.nbidx")
     with pytest.raises(nb.NbError):
         nb.Index.load(tmp_path / "missing.nbidx")
+    # the file ends in a checksum: a single flipped byte anywhere, an element count the file cannot hold, or a missing
+    # tail is refused instead of being uploaded (a damaged node or edge id would send the kernels out of bounds)
+    good = p.read_bytes()
+    rng = random.Random(11)
+    for _ in range(40):
+        b = bytearray(good); i = rng.randrange(len(b)); b[i] ^= 1 << rng.randrange(8)
+        (tmp_path / "bad.nbidx").write_bytes(bytes(b))
+        with pytest.raises(nb.NbError):
+            nb.Index.load(tmp_path / "bad.nbidx")
+    for cut in (len(good) - 1, len(good) - 8, len(good) // 2):
+        (tmp_path / "bad.nbidx").write_bytes(good[:cut])
+        with pytest.raises(nb.NbError):
+            nb.Index.load(tmp_path / "bad.nbidx")
+    b = bytearray(good); b[40:48] = (2 ** 62).to_bytes(8, "little")   # first array's element count
+    (tmp_path / "bad.nbidx").write_bytes(bytes(b))
+    with pytest.raises(nb.NbError):
+        nb.Index.load(tmp_path / "bad.nbidx")
 
 
 def test_index_compare_and_gpu_builder_fails_loudly_without_a_gpu():
