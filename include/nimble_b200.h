@@ -236,6 +236,15 @@ int nb_ctx_kernel_stats(nb_ctx*, double* out4, int reset);
  * colour ids touched (the terms of the algorithmic-bytes formula, DESIGN.md "Roofline") */
 int nb_ctx_work_counters(nb_ctx*, uint64_t* out4);
 
+/* ---- roofs (diagnostics; nothing on the data path calls them).  SURVEY.md §8(d): the probe / walk traffic of the map
+ * stage (align::pseudoalign -> map_read_with_mismatch, src/align.rs:945-989) is random 32-byte buckets and 64-byte walk
+ * records, so its roof is the random-record gather bandwidth of the memory level the index lives in (L2 for the 1k
+ * library, HBM for the 200k one); the end-to-end number's roof is the pinned host -> device link.
+ *   nb_measure_gather  bytes gathered / s over a table of table_bytes (record_bytes 32 or 64), best of reps launches
+ *   nb_measure_h2d     n devices copying `bytes` x reps from pinned host memory at the same time: GB/s each and aggregate */
+int nb_measure_gather(int device, uint64_t table_bytes, uint32_t record_bytes, uint32_t reps, double* gbs_out);
+int nb_measure_h2d(const int* devices, uint32_t n, uint64_t bytes, uint32_t reps, double* out_per_device, double* aggregate_out);
+
 /* ---- drivers: process::fastq::process (src/process/fastq.rs:7-30) and utils::write_to_tsv (src/utils.rs:27-51) */
 int nb_write_fastq_tsv(const char* path, const nb_library* lib, const nb_counts* counts);
 int nb_process_fastq(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,

@@ -119,6 +119,8 @@ _SIGS = {
     "nb_route_detach": (C.c_int, [C.c_void_p]),
     "nb_ctx_kernel_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "nb_ctx_work_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nb_measure_gather": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]),
+    "nb_measure_h2d": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_double)]),
     "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),
     "nb_bam_dump_groups": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "nb_process_bam": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]),
@@ -408,13 +410,6 @@ class Context:
         out.update(rows=rows, callsets=callsets)
         return out
 
-    def _unused_counts(self, c, rows, callsets):
-        return dict(rows=rows, callsets=callsets, n_pairs_seen=c.n_pairs_seen, n_unique_keys=c.n_unique_keys,
-                    row_scope=np.ctypeslib.as_array(c.row_scope, (c.n_rows,)).copy() if c.n_rows else np.zeros(0, np.uint32),
-                    row_callset=np.ctypeslib.as_array(c.row_callset, (c.n_rows,)).copy() if c.n_rows else np.zeros(0, np.uint32),
-                    row_count=np.ctypeslib.as_array(c.row_count, (c.n_rows,)).copy() if c.n_rows else np.zeros(0, np.int64),
-                    slot_to_callset=np.ctypeslib.as_array(c.slot_to_callset, (c.n_slots,)).copy() if c.n_slots else np.zeros(0, np.uint32))
-
     def write_tsv(self, path):
         c = Counts()
         _ck(lib().nb_counts_finalize(self.h, C.byref(c)))
@@ -467,6 +462,22 @@ class Context:
         o = np.zeros(4, dtype=np.uint64)
         _ck(lib().nb_ctx_work_counters(self.h, o.ctypes.data))
         return dict(zip(["probes", "nodes", "bases", "colour_elems"], o.tolist()))
+
+
+def measure_gather(table_bytes, record_bytes=32, device=0, reps=3):
+    """Random-record gather bandwidth (GB/s) over a table of `table_bytes`: the L2 roof when it fits L2, else the HBM gather roof."""
+    g = C.c_double(0)
+    _ck(lib().nb_measure_gather(device, int(table_bytes), record_bytes, reps, C.byref(g)))
+    return g.value
+
+
+def measure_h2d(devices=(0,), nbytes=256 << 20, reps=8):
+    """Pinned host -> device bandwidth with all `devices` copying at once -> (per-device GB/s list, aggregate GB/s)."""
+    d = np.asarray(devices, dtype=np.int32)
+    per = np.zeros(len(d), dtype=np.float64)
+    agg = C.c_double(0)
+    _ck(lib().nb_measure_h2d(d.ctypes.data, len(d), int(nbytes), reps, per.ctypes.data, C.byref(agg)))
+    return per.tolist(), agg.value
 
 
 def get_calls(sequences, mate_sequences, sequence_metadata, index, reference, aligner_config, device=0):

@@ -74,8 +74,14 @@ __device__ __forceinline__ bool coop_find(const DevIndex& ix, const BatchDev& b,
 }
 
 enum { ST_DONE = 0, ST_SEED = 1, ST_WALK = 2 };
-constexpr int P_MIN = 6;   // idle lanes needed before the store/pop path runs
-constexpr int S_MIN = 4;   // re-seeding lanes needed before the re-seed path runs
+#ifndef NB_P_MIN
+#define NB_P_MIN 6
+#endif
+#ifndef NB_S_MIN
+#define NB_S_MIN 4
+#endif
+constexpr int P_MIN = NB_P_MIN;   // idle lanes needed before the store/pop path runs
+constexpr int S_MIN = NB_S_MIN;   // re-seeding lanes needed before the re-seed path runs
 
 // The warp searches the stride-3 seeds of one read from position s_kp on, 64 seeds per round (two per lane, the four
 // bucket loads of a round in flight together: an off-target 150 bp read is settled in one round trip instead of two);

@@ -32,6 +32,7 @@
 //   BAM scope rows   : src/process/bam.rs:305-405 (zero rows), 245-303
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -79,68 +80,124 @@ struct Node {
   u8 lext, rext;          // bit b set <=> base b observed left of first k-mer / right of last k-mer
   int32_t redge[4], ledge[4];
 };
+// Open-addressed k-mer map (test infrastructure of its own: the 200k-transcript parity library has 2e8 k-mers, far
+// beyond what node-based std::unordered_map holds in reasonable time / memory).  Keys are 60-bit k-mers; ~0 = empty.
+struct KmerMap {
+  struct E { u64 key, val; };
+  std::vector<E> e; u64 mask = 0, n = 0;
+  void init(size_t expect) { size_t c = 16; while (c < expect * 2) c <<= 1; e.assign(c, E{~0ULL, 0}); mask = c - 1; n = 0; }
+  static u64 h(u64 k) { k ^= k >> 31; k *= 0x9E3779B97F4A7C15ULL; k ^= k >> 29; return k; }
+  void put(u64 k, u64 v) { u64 i = h(k) & mask; while (e[i].key != ~0ULL && e[i].key != k) i = (i + 1) & mask; if (e[i].key == ~0ULL) n++; e[i].key = k; e[i].val = v; }
+  bool get(u64 k, u64& v) const { if (e.empty()) return false; u64 i = h(k) & mask; while (e[i].key != ~0ULL) { if (e[i].key == k) { v = e[i].val; return true; } i = (i + 1) & mask; } return false; }
+  u64 at(u64 k) const { u64 v = 0; if (!get(k, v)) abort(); return v; }
+};
 struct Index {
   std::vector<Node> nodes;
   std::vector<std::vector<u32>> colours;                   // eq_classes
-  std::unordered_map<u64, std::pair<u32, u32>> kmap;       // k-mer -> (node, offset)
+  KmerMap kmap;                                            // k-mer -> node | offset << 32
   u64 n_kmers = 0;
 };
 
 struct Occ { u64 kmer; u32 id; u8 l, r; };
 
 void build_index(const std::vector<Dna>& seqs, Index& ix) {
+  const bool tm = getenv("ORC_TIMING") != nullptr; auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) { if (!tm) return; auto t = std::chrono::steady_clock::now(); fprintf(stderr, "oracle build_index: %s %.2fs\n", what, std::chrono::duration<double>(t - t_last).count()); t_last = t; };
   std::vector<Occ> occ;
+  { size_t tot = 0; for (auto& d : seqs) if (d.size() >= (size_t)K) tot += d.size() - K + 1; occ.reserve(tot); }
   for (size_t s = 0; s < seqs.size(); s++) {
     const Dna& d = seqs[s];
     if (d.size() < (size_t)K) continue;
-    for (size_t p = 0; p + K <= d.size(); p++) {
-      Occ o; o.kmer = kmer_at(d, p); o.id = (u32)s;
-      o.l = p > 0 ? d[p - 1] : 4; o.r = p + K < d.size() ? d[p + K] : 4;
+    u64 km = 0;
+    for (size_t p = 0; p < d.size(); p++) {
+      km = ((km << 2) | d[p]) & KMASK;
+      if (p + 1 < (size_t)K) continue;
+      size_t st = p + 1 - K;
+      Occ o; o.kmer = km; o.id = (u32)s;
+      o.l = st > 0 ? d[st - 1] : 4; o.r = p + 1 < d.size() ? d[p + 1] : 4;
       occ.push_back(o);
     }
   }
-  std::sort(occ.begin(), occ.end(), [](const Occ& a, const Occ& b) { return a.kmer != b.kmer ? a.kmer < b.kmer : a.id < b.id; });
+  lap("enumerate");
+  auto occ_less = [](const Occ& a, const Occ& b) { return a.kmer != b.kmer ? a.kmer < b.kmer : a.id < b.id; };
+  {  // sort by (k-mer, id); large inputs: partition by the k-mer's top byte, sort the parts on threads
+    unsigned T = std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+    if (occ.size() < (1u << 20) || T == 1) std::sort(occ.begin(), occ.end(), occ_less);
+    else {
+      std::vector<size_t> cnt(257, 0);
+      for (auto& o : occ) cnt[(o.kmer >> 52) + 1]++;
+      for (int i = 0; i < 256; i++) cnt[i + 1] += cnt[i];
+      std::vector<Occ> tmp(occ.size()); std::vector<size_t> cur(cnt.begin(), cnt.end() - 1);
+      for (auto& o : occ) tmp[cur[o.kmer >> 52]++] = o;
+      occ.swap(tmp); tmp.clear(); tmp.shrink_to_fit();
+      std::atomic<int> next(0); std::vector<std::thread> th;
+      for (unsigned t = 0; t < T; t++) th.emplace_back([&]() { for (int b; (b = next++) < 256;) std::sort(occ.begin() + cnt[b], occ.begin() + cnt[b + 1], occ_less); });
+      for (auto& t : th) t.join();
+    }
+  }
+  lap("sort");
   std::vector<u64> kmers; std::vector<u8> L, R; std::vector<u32> col;
-  std::map<std::vector<u32>, u32> intern;
+  // colour interning: open-addressed table over a hash of the id list, every hit verified element-wise
+  kmers.reserve(occ.size() / 2); L.reserve(occ.size() / 2); R.reserve(occ.size() / 2); col.reserve(occ.size() / 2);
+  std::vector<u32> itab(1u << 16, 0xFFFFFFFFu); u64 imask = itab.size() - 1;
+  auto id_hash = [](const u32* p, size_t n) { u64 hv = 0x243F6A8885A308D3ULL ^ n; for (size_t i = 0; i < n; i++) { hv = (hv ^ p[i]) * 0x9E3779B97F4A7C15ULL; hv ^= hv >> 32; } return hv; };
+  std::vector<u32> ids;
   for (size_t i = 0; i < occ.size();) {
-    size_t j = i; u8 l = 0, r = 0; std::vector<u32> ids;
+    size_t j = i; u8 l = 0, r = 0; ids.clear();
     while (j < occ.size() && occ[j].kmer == occ[i].kmer) {
       if (occ[j].l < 4) l |= 1 << occ[j].l;
       if (occ[j].r < 4) r |= 1 << occ[j].r;
       if (ids.empty() || ids.back() != occ[j].id) ids.push_back(occ[j].id);
       j++;
     }
-    auto it = intern.find(ids);
-    u32 c;
-    if (it == intern.end()) { c = (u32)ix.colours.size(); intern.emplace(ids, c); ix.colours.push_back(ids); } else c = it->second;
+    u64 h = id_hash(ids.data(), ids.size()) & imask;
+    u32 c = 0xFFFFFFFFu;
+    for (;; h = (h + 1) & imask) {
+      u32 q = itab[h];
+      if (q == 0xFFFFFFFFu) break;
+      const std::vector<u32>& cq = ix.colours[q];
+      if (cq.size() == ids.size() && std::equal(cq.begin(), cq.end(), ids.begin())) { c = q; break; }
+    }
+    if (c == 0xFFFFFFFFu) {
+      c = (u32)ix.colours.size(); itab[h] = c; ix.colours.push_back(ids);
+      if (ix.colours.size() * 2 > itab.size()) {   // grow + rehash
+        itab.assign(itab.size() * 4, 0xFFFFFFFFu); imask = itab.size() - 1;
+        for (u32 q = 0; q < ix.colours.size(); q++) { u64 g = id_hash(ix.colours[q].data(), ix.colours[q].size()) & imask; while (itab[g] != 0xFFFFFFFFu) g = (g + 1) & imask; itab[g] = q; }
+      }
+    }
     kmers.push_back(occ[i].kmer); L.push_back(l); R.push_back(r); col.push_back(c);
     i = j;
   }
+  occ.clear(); occ.shrink_to_fit();
+  lap("group + colours");
   size_t n = kmers.size();
   ix.n_kmers = n;
-  std::unordered_map<u64, u32> kidx; kidx.reserve(n * 2);
-  for (size_t i = 0; i < n; i++) kidx[kmers[i]] = (u32)i;
+  KmerMap kidx; kidx.init(n);
+  for (size_t i = 0; i < n; i++) kidx.put(kmers[i], (u64)i);
+  lap("k-mer index");
   std::vector<int32_t> succ(n, -1), pred(n, -1);
   for (size_t i = 0; i < n; i++) {
     if (__builtin_popcount(R[i]) != 1) continue;
     int b = __builtin_ctz(R[i]);
     u64 y = ((kmers[i] << 2) | (u64)b) & KMASK;
-    u32 j = kidx.at(y);
+    u32 j = (u32)kidx.at(y);
     if (__builtin_popcount(L[j]) == 1 && col[i] == col[j]) { succ[i] = (int32_t)j; pred[j] = (int32_t)i; }
   }
+  lap("succ/pred");
   std::vector<int32_t> start_node(n, -1), end_node(n, -1);
   std::vector<char> used(n, 0);
+  ix.kmap.init(n);
   auto emit = [&](size_t s) {
     Node nd; nd.colour = col[s]; nd.lext = L[s];
     for (int i = K - 1; i >= 0; i--) nd.seq.push_back((u8)((kmers[s] >> (2 * i)) & 3));
     size_t cur = s; used[cur] = 1;
     u32 id = (u32)ix.nodes.size();
     u32 off = 0;
-    ix.kmap[kmers[cur]] = {id, off};
+    ix.kmap.put(kmers[cur], (u64)id | ((u64)off << 32));
     while (succ[cur] >= 0 && !used[succ[cur]]) {
       cur = (size_t)succ[cur]; used[cur] = 1; off++;
       nd.seq.push_back((u8)(kmers[cur] & 3));
-      ix.kmap[kmers[cur]] = {id, off};
+      ix.kmap.put(kmers[cur], (u64)id | ((u64)off << 32));
     }
     nd.rext = R[cur];
     for (int b = 0; b < 4; b++) nd.redge[b] = nd.ledge[b] = -1;
@@ -149,6 +206,7 @@ void build_index(const std::vector<Dna>& seqs, Index& ix) {
   };
   for (size_t i = 0; i < n; i++) if (pred[i] < 0) emit(i);
   for (size_t i = 0; i < n; i++) if (!used[i]) emit(i);   // pure cycles: smallest k-mer first (arrays are k-mer sorted)
+  lap("unitigs");
   for (size_t i = 0; i < n; i++) {
     if (start_node[i] >= 0) {
       Node& nd = ix.nodes[start_node[i]];
@@ -182,8 +240,8 @@ bool map_read(const Index& ix, const Dna& read, size_t allowed, std::vector<u32>
   auto find = [&](size_t& pos) -> bool {
     while (pos <= last_kpos) {
       w.probes++;
-      auto it = ix.kmap.find(kmer_at(read, pos));
-      if (it != ix.kmap.end()) { node = it->second.first; off = it->second.second; return true; }
+      u64 v;
+      if (ix.kmap.get(kmer_at(read, pos), v)) { node = (u32)v; off = (u32)(v >> 32); return true; }
       pos += 3;
     }
     return false;
