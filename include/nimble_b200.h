@@ -166,7 +166,14 @@ typedef struct nb_pair_result {
  * thresholds, pair / strand / orientation logic and folds the pairs into the context's per-scope de-duplicated
  * callset counts.  reads_out (2*n_pairs entries when paired, else n_pairs; side-major per pair: [2p]=sequence,
  * [2p+1]=mate) and pairs_out may be NULL.  Output buffers follow batch->location.  Asynchronous on the context's
- * stream: host buffers may be reused after nb_ctx_sync() or after the second following nb_align_batch() returns. */
+ * stream: host buffers may be reused after nb_ctx_sync() or after the second following nb_align_batch() returns (the
+ * library blocks on the copies of a staging set before it refills it, so a producer rotating THREE pinned buffers never
+ * overwrites one that is still being read; with two, call nb_ctx_sync() before each refill).
+ * read_key (src/align.rs:576-579: the R1 string followed by the R2 string) is represented by a 128-bit hash of the
+ * concatenated 2-bit base stream, the length and the scope: two DIFFERENT pairs of one scope are merged with probability
+ * about n^2 / 2^129 (1e-23 at 1e8 pairs) — the one place where the device path is exact only up to a hash.  nb_pair_result
+ * carries the key (key_lo, key_hi).  A scope with more pairs than max_batch_pairs is still de-duplicated as a whole: the
+ * chunk grows to the end of that scope. */
 int nb_align_batch(nb_ctx*, const nb_batch* batch, nb_read_result* reads_out, nb_pair_result* pairs_out);
 /* Debug / parity: full equivalence class of every read of the LAST batch: ec_off (n_reads+1) and ids. Host buffers. */
 int nb_last_batch_ecs(nb_ctx*, uint64_t* ec_off, uint32_t* ec_ids, uint64_t ec_cap, uint64_t* ec_total);

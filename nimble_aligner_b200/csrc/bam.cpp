@@ -62,10 +62,14 @@ struct Bgzf {
     while (p + 18 <= file.size()) {
       const u8* h = &file[p];
       if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return fail(NB_ERR_PARSE, "not a BGZF file: " + path);
+      // every size field comes from the file: nothing is read or handed to inflate() before it is checked against the
+      // block and the file (a damaged BAM must fail with NB_ERR_PARSE, never read out of bounds)
       size_t xlen = h[10] | (h[11] << 8), q = p + 12, xend = q + xlen, bsize = 0;
-      while (q + 4 <= xend) { size_t slen = file[q + 2] | (file[q + 3] << 8); if (file[q] == 'B' && file[q + 1] == 'C' && slen == 2) bsize = (file[q + 4] | (file[q + 5] << 8)) + 1; q += 4 + slen; }
-      if (!bsize || p + bsize > file.size()) return fail(NB_ERR_PARSE, "corrupt BGZF block in " + path);
+      if (xend > file.size()) return fail(NB_ERR_PARSE, "corrupt BGZF block (extra field runs past the end of the file) in " + path);
+      while (q + 4 <= xend) { size_t slen = file[q + 2] | (file[q + 3] << 8); if (q + 4 + slen > xend) break; if (file[q] == 'B' && file[q + 1] == 'C' && slen == 2) bsize = (file[q + 4] | (file[q + 5] << 8)) + 1; q += 4 + slen; }
+      if (!bsize || p + bsize > file.size() || 12 + xlen + 8 > bsize) return fail(NB_ERR_PARSE, "corrupt BGZF block in " + path);
       size_t isize = file[p + bsize - 4] | (file[p + bsize - 3] << 8) | (file[p + bsize - 2] << 16) | ((size_t)file[p + bsize - 1] << 24);
+      if (isize > 65536) return fail(NB_ERR_PARSE, "corrupt BGZF block (ISIZE beyond 64 KiB) in " + path);
       blks.push_back({xend, bsize - (xend - p) - 8, utot, isize});
       utot += isize; p += bsize;
     }
@@ -94,22 +98,31 @@ struct Rec {   // one decoded BAM record (views into Bgzf::data stay valid for t
   const char* cb = nullptr; const char* umi = nullptr; u32 cb_len = 0, umi_len = 0;   // CB:Z and UB:Z (else UR:Z) values, found once by scan_keys(); nullptr = absent / not a string
   // one pass over the aux block for the grouping keys (same first-match-by-two-bytes rule as aux_z)
   void scan_keys() {
-    const u8* a = aux(); const u8* e = end(); const char* ub = nullptr; const char* ur = nullptr; bool seen_cb = false, seen_ub = false, seen_ur = false;
-    cb = umi = nullptr;
+    const u8* a = aux(); const u8* e = end(); const char* ub = nullptr; const char* ur = nullptr; u32 ub_len = 0, ur_len = 0; bool seen_cb = false, seen_ub = false, seen_ur = false;
+    cb = umi = nullptr; cb_len = umi_len = 0;
     while (a + 3 <= e) {
-      char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2]; a += 3; const u8* v = a;
-      switch (ty) {
-        case 'A': case 'c': case 'C': a += 1; break; case 's': case 'S': a += 2; break; case 'i': case 'I': case 'f': a += 4; break;
-        case 'Z': case 'H': while (a < e && *a) a++; a++; break;
-        case 'B': { if (a + 5 > e) { a = e; break; } char st = (char)a[0]; u32 n; memcpy(&n, a + 1, 4); size_t w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; a += 5 + w * n; break; }
-        default: a = e; break;
-      }
-      if (t0 == 'C' && t1 == 'B' && !seen_cb) { seen_cb = true; if (ty == 'Z') cb = (const char*)v; }
-      else if (t0 == 'U' && t1 == 'B' && !seen_ub) { seen_ub = true; if (ty == 'Z') ub = (const char*)v; }
-      else if (t0 == 'U' && t1 == 'R' && !seen_ur) { seen_ur = true; if (ty == 'Z') ur = (const char*)v; }
+      char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2]; a += 3; const u8* v = a; u32 zlen = 0; bool zok = false;
+      if (!aux_skip(ty, a, e, zlen, zok)) break;
+      if (t0 == 'C' && t1 == 'B' && !seen_cb) { seen_cb = true; if (ty == 'Z' && zok) { cb = (const char*)v; cb_len = zlen; } }
+      else if (t0 == 'U' && t1 == 'B' && !seen_ub) { seen_ub = true; if (ty == 'Z' && zok) { ub = (const char*)v; ub_len = zlen; } }
+      else if (t0 == 'U' && t1 == 'R' && !seen_ur) { seen_ur = true; if (ty == 'Z' && zok) { ur = (const char*)v; ur_len = zlen; } }
     }
-    umi = ub ? ub : ur;
-    cb_len = cb ? (u32)strlen(cb) : 0; umi_len = umi ? (u32)strlen(umi) : 0;
+    umi = ub ? ub : ur; umi_len = ub ? ub_len : ur_len;
+  }
+  // Steps `a` over one aux value of type `ty` without ever passing `e` (the end of the record): false when the value is
+  // cut off or the type is unknown (the scan stops there).  Z / H: zlen = bytes before the NUL, zok = a NUL was found
+  // inside the record (an unterminated string is not a value: strlen() on it would run off the record).
+  static bool aux_skip(char ty, const u8*& a, const u8* e, u32& zlen, bool& zok) {
+    size_t left = (size_t)(e - a), w = 0;
+    switch (ty) {
+      case 'A': case 'c': case 'C': w = 1; break; case 's': case 'S': w = 2; break; case 'i': case 'I': case 'f': w = 4; break;
+      case 'Z': case 'H': { const u8* z = (const u8*)memchr(a, 0, left); if (!z) { a = e; return false; } zlen = (u32)(z - a); zok = true; a = z + 1; return true; }
+      case 'B': { if (left < 5) { a = e; return false; } char st = (char)a[0]; u32 n; memcpy(&n, a + 1, 4); size_t ew = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                  if ((size_t)n > (left - 5) / ew) { a = e; return false; } a += 5 + ew * n; return true; }
+      default: a = e; return false;
+    }
+    if (w > left) { a = e; return false; }
+    a += w; return true;
   }
   const char* qname_ptr() const { return (const char*)p + 32; } u32 qname_len() const { u32 l = l_read_name(); return l ? l - 1 : 0; }
   i32 refid() const { return rd32(0); } i32 pos() const { return rd32(4); }
@@ -127,14 +140,10 @@ struct Rec {   // one decoded BAM record (views into Bgzf::data stay valid for t
   bool aux_z(const char* tag, std::string& out) const {
     const u8* a = aux(); const u8* e = end();
     while (a + 3 <= e) {
-      char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2]; a += 3; const u8* v = a;
-      switch (ty) {
-        case 'A': case 'c': case 'C': a += 1; break; case 's': case 'S': a += 2; break; case 'i': case 'I': case 'f': a += 4; break;
-        case 'Z': case 'H': while (a < e && *a) a++; a++; break;
-        case 'B': { if (a + 5 > e) return false; char st = (char)a[0]; u32 n; memcpy(&n, a + 1, 4); size_t w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; a += 5 + w * n; break; }
-        default: return false;
-      }
-      if (t0 == tag[0] && t1 == tag[1]) { if (ty != 'Z') return false; out.assign((const char*)v); return true; }
+      char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2]; a += 3; const u8* v = a; u32 zlen = 0; bool zok = false;
+      bool ok = aux_skip(ty, a, e, zlen, zok);
+      if (t0 == tag[0] && t1 == tag[1]) { if (ty != 'Z' || !zok) return false; out.assign((const char*)v, zlen); return true; }
+      if (!ok) return false;
     }
     return false;
   }
@@ -206,15 +215,19 @@ struct SortedReader {
     cur = p; header_done = true; return NB_OK;
   }
   // locate the records (serial walk over block sizes), then scan their grouping keys on `threads` threads
-  void prepare(int threads) {
+  int prepare(int threads) {
     const RawBuf& d = z.data;
     while (cur + 4 <= d.size()) {
       u32 bs; memcpy(&bs, &d[cur], 4);
       if (bs < 32 || cur + 4 + bs > d.size()) break;
-      Rec r; r.p = &d[cur + 4]; r.block = bs; all.push_back(r); cur += 4 + bs;
+      Rec r; r.p = &d[cur + 4]; r.block = bs;
+      // l_read_name, n_cigar and l_seq come from the file: qname / cigar / 4-bit bases / quals must lie inside the record
+      if (32ull + r.l_read_name() + 4ull * r.n_cigar() + ((u64)r.l_seq() + 1) / 2 + (u64)r.l_seq() > bs) return fail(NB_ERR_PARSE, "corrupt BAM record (field lengths exceed its block size)");
+      all.push_back(r); cur += 4 + bs;
       if (all.size() == 4096) all.reserve((size_t)((double)d.size() / (double)cur * 4096 * 1.1) + 4096);   // one allocation for the whole file
     }
     parallel_ranges(threads, all.size(), [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) all[i].scan_keys(); });
+    return NB_OK;
   }
   bool read_record(Rec& r) { if (next_rec >= all.size()) return false; r = all[next_rec++]; return true; }
   int fill_buffer() {   // 31-107
@@ -294,7 +307,7 @@ struct UmiReader {
 int collect_groups_serial(const Bgzf& z, bool force_paired, int threads, std::vector<Rec>& stream, std::vector<u64>& gstart) {
   UmiReader reader(z, force_paired);
   int rc = reader.rd.skip_header(); if (rc) return rc;
-  reader.rd.prepare(threads);
+  rc = reader.rd.prepare(threads); if (rc) return rc;
   stream.clear(); gstart.assign(1, 0);
   bool has_aligned = false;
   for (;;) {
@@ -326,7 +339,7 @@ int collect_groups(const Bgzf& z, bool force_paired, int threads, std::vector<Re
   if (getenv("NB_BAM_SERIAL_GROUPING")) return collect_groups_serial(z, force_paired, threads, stream, gstart);
   SortedReader rd(z, force_paired);
   int rc = rd.skip_header(); if (rc) return rc;
-  rd.prepare(threads);
+  rc = rd.prepare(threads); if (rc) return rc;
   const std::vector<Rec>& all = rd.all;
   // kept records, in file order
   std::vector<u32> kept; kept.reserve(all.size());

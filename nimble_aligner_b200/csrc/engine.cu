@@ -13,6 +13,7 @@
 
 #include "host.hpp"
 #include "kernels.cuh"
+#include "khash.h"
 
 using namespace nb;
 using nbk::BatchDev; using nbk::Counters; using nbk::DevCfg; using nbk::DevIndex; using nbk::DevLib; using nbk::Tables;
@@ -63,7 +64,7 @@ struct nb_ctx {
   const nb_index* hix = nullptr; const nb_library* lib = nullptr;
   nb_config hcfg; DevCfg dcfg; DevIndex dix; DevLib dlib;
   // index + library device copies
-  DBuf d_tkey, d_tval, d_unitig, d_node, d_walk, d_ledge, d_coloff, d_colids, d_colmeta, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp, d_mincov;
+  DBuf d_ptab, d_bloom, d_unitig, d_node, d_walk, d_ledge, d_coloff, d_colids, d_colmeta, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp, d_mincov;
   // options
   u64 max_batch_pairs = 1u << 20, arena_entries = 1u << 24, cs_slots = 1u << 18, key_slots = 1u << 22, agg_slots = 1u << 20;
   int count_work = 0; u32 min_read_len = 40;  // MIN_READ_LENGTH, src/align.rs:18 (tests pass 12, src/align.rs:1066)
@@ -177,8 +178,32 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&c->stg[i].copied, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->stg[i].consumed, cudaEventDisableTiming) != cudaSuccess) { nb_ctx_free(c); return fail(NB_ERR_CUDA, "cudaEventCreate failed"); }
   int rc = NB_OK;
   auto up = [&](cudaError_t e) { if (e != cudaSuccess && rc == NB_OK) rc = fail(NB_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e)); };
-  up(upload(c->d_unitig, index->unitig, s)); up(upload(c->d_ledge, index->ledge, s));
-  up(upload(c->d_tkey, index->table_key, s)); up(upload(c->d_tval, index->table_val, s)); up(upload(c->d_node, index->node, s));
+  up(upload(c->d_unitig, index->unitig, s)); up(upload(c->d_ledge, index->ledge, s)); up(upload(c->d_node, index->node, s));
+  u64 n_pbuckets = nb_ptab_buckets(index->n_kmers), bloom_words = 0; u32 bloom_k = 0;
+  if (rc == NB_OK) {
+    // Probe table {key0, key1, value0, value1} per 32-byte bucket and, when it cannot live in L2, the Bloom prefilter: both
+    // built here on the device from the artefact's flat table (khash.h), which is only staged for the build.
+    if (n_pbuckets >= 0xFFFFFFFFull) rc = fail(NB_ERR_UNSUPPORTED, "index has too many k-mers for the 32-bit bucket index");
+    // the prefilter always exists (80 % of all probes are misses of seed searches: one word instead of a bucket walk);
+    // 16 bits per k-mer, at most 64 MB so that it stays L2-resident next to an HBM-resident table
+    bloom_words = std::min<u64>(std::max<u64>(index->n_kmers / 4, 1024), (64ull << 20) / 8);
+    bloom_k = index->n_kmers * 6 <= bloom_words * 64 ? 3 : 2;
+    const char* env = getenv("NB_L2_HINTS");   // test knob: 0 / 1 forces the kernel variant; default: tables beyond 64 MB are HBM-resident
+    c->dix.hbm = env ? (atoi(env) != 0) : (n_pbuckets * 32 > (64ull << 20));
+    DBuf t_key, t_val, t_err;
+    up(upload(t_key, index->table_key, s)); up(upload(t_val, index->table_val, s));
+    up(c->d_ptab.ensure(n_pbuckets * 32, s)); up(t_err.ensure(4, s));
+    up(c->d_bloom.ensure(bloom_words * 8, s));
+    if (rc == NB_OK) {
+      up(cudaMemsetAsync(c->d_ptab.p, 0, n_pbuckets * 32, s)); up(cudaMemsetAsync(t_err.p, 0, 4, s));
+      up(cudaMemsetAsync(c->d_bloom.p, 0, bloom_words * 8, s));
+      nbk::launch_probe_build((const u64*)t_key.p, (const u64*)t_val.p, index->table_key.size(), (u64*)c->d_ptab.p, (u32)n_pbuckets, (u64*)c->d_bloom.p, (u32)bloom_words, bloom_k, (unsigned int*)t_err.p, s);
+      unsigned int herr = 0;
+      up(cudaMemcpyAsync(&herr, t_err.p, 4, cudaMemcpyDeviceToHost, s)); up(cudaStreamSynchronize(s));
+      if (rc == NB_OK && herr) rc = fail(NB_ERR_CUDA, "probe table build overflowed");
+    }
+    cudaStreamSynchronize(s); t_key.release(); t_val.release(); t_err.release();
+  }
   {  // walk records (kernels.cuh DevIndex::walk), derived from the flat index arrays at upload time
     size_t nn = index->node.size(); std::vector<u32> w(16 * nn);
     auto base_at = [&](u64 pos) -> u64 { return (index->unitig[pos >> 5] >> (2 * (pos & 31))) & 3; };
@@ -203,8 +228,9 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   }
   if (rc == NB_OK) { cudaError_t e = cudaStreamSynchronize(s); if (e != cudaSuccess) rc = fail(NB_ERR_CUDA, cudaGetErrorString(e)); }
   if (rc != NB_OK) { nb_ctx_free(c); return rc; }
-  c->dix.n_buckets = (u32)index->table_buckets; c->dix.unitig = (const u64*)c->d_unitig.p; c->dix.ledge = (const uint4*)c->d_ledge.p;
-  c->dix.tkey = (const u64*)c->d_tkey.p; c->dix.tval = (const u64*)c->d_tval.p; c->dix.node = (const uint4*)c->d_node.p; c->dix.walk = (const uint4*)c->d_walk.p;
+  c->dix.unitig = (const u64*)c->d_unitig.p; c->dix.ledge = (const uint4*)c->d_ledge.p;
+  c->dix.ptab = (const u64*)c->d_ptab.p; c->dix.n_pbuckets = (u32)n_pbuckets; c->dix.bloom = (const u64*)c->d_bloom.p; c->dix.bloom_words = (u32)bloom_words; c->dix.bloom_k = bloom_k;
+  c->dix.node = (const uint4*)c->d_node.p; c->dix.walk = (const uint4*)c->d_walk.p;
   c->dix.col_off = (const u32*)c->d_coloff.p; c->dix.col_ids = (const u32*)c->d_colids.p; c->dix.col_meta = (const uint4*)c->d_colmeta.p;
   c->dlib.row_fid = (const u32*)c->d_rowfid.p; c->dlib.row_rev = (const u8*)c->d_rowrev.p; c->dlib.row_of = (const u32*)c->d_rowof.p; c->dlib.feat_group = (const u32*)c->d_featgroup.p; c->dlib.n_rows = lib->n_rows();
   rc = apply_config(c, lib->cfg);
@@ -218,7 +244,7 @@ void nb_ctx_free(nb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->cstream) cudaStreamSynchronize(c->cstream);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DBuf* all[] = {&c->d_tkey, &c->d_tval, &c->d_node, &c->d_walk, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
+  DBuf* all[] = {&c->d_ptab, &c->d_bloom, &c->d_node, &c->d_walk, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
                  &c->d_ent, &c->d_ls, &c->d_qp, &c->d_mincov, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
                  &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].scope, &c->stg[0].cell,
                  &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded, &c->d_rowwork, &c->d_rowout, &c->d_dense};
@@ -256,13 +282,14 @@ int nb_ctx_set_option(nb_ctx* c, const char* name, uint64_t value) {
 static int grow_keys(nb_ctx* c, u64 need_slots) {
   u64 ns = c->key_slots; while (ns < need_slots) ns <<= 1;
   DBuf nk, nv; cudaStream_t s = c->stream;
-  CK(nk.ensure(ns * 16, s)); CK(nv.ensure(ns * 8, s));
-  CK(cudaMemsetAsync(nk.p, 0, ns * 16, s)); CK(cudaMemsetAsync(nv.p, 0, ns * 8, s));
-  Tables o = make_tables(c); Tables n = o; n.key = (ulonglong2*)nk.p; n.kval = (unsigned long long*)nv.p; n.key_mask = ns - 1;
-  // n_keys is re-counted by the inserts of the rehash
-  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
-  nbk::launch_rehash_keys(o, n, s); c->all_launches++;
-  CK(cudaStreamSynchronize(s));
+  auto ck2 = [&](cudaError_t e) { if (e == cudaSuccess) return true; nk.release(); nv.release(); fail(NB_ERR_CUDA, std::string("key table growth: ") + cudaGetErrorString(e)); return false; };
+  if (!ck2(nk.ensure(ns * 16, s)) || !ck2(nv.ensure(ns * 8, s))) return NB_ERR_CUDA;
+  if (!ck2(cudaMemsetAsync(nk.p, 0, ns * 16, s)) || !ck2(cudaMemsetAsync(nv.p, 0, ns * 8, s))) return NB_ERR_CUDA;
+  if (c->mode != 1) {   // scoped batches clear the table after every chunk: nothing to carry over (and Counters::n_keys, which accumulates the per-chunk unique keys there, must stay)
+    Tables o = make_tables(c); Tables n = o; n.key = (ulonglong2*)nk.p; n.kval = (unsigned long long*)nv.p; n.key_mask = ns - 1;
+    nbk::launch_rehash_keys(o, n, s); c->all_launches++;
+  }
+  if (!ck2(cudaStreamSynchronize(s))) return NB_ERR_CUDA;
   c->d_key.release(); c->d_kval.release(); c->d_key = nk; c->d_kval = nv; c->key_slots = ns;
   c->d_klast.release(); CK(c->d_klast.ensure(ns * 8, s)); CK(cudaMemsetAsync(c->d_klast.p, 0, ns * 8, s));
   return NB_OK;
@@ -280,7 +307,14 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   nb_ctx::Staging* S = nullptr; cudaStream_t cs = s;
   if (host) {
     S = &c->stg[c->stg_next]; c->stg_next ^= 1; cs = c->cstream;
-    if (S->used) CK(cudaStreamWaitEvent(cs, S->consumed, 0));   // the kernels that read this staging set two chunks ago are done
+    if (S->used) {
+      // Reusing a staging set: the H2D copies that filled it two chunks ago must have RUN before this call returns, or the
+      // documented reuse rule for the caller's host buffers (nimble_b200.h: free again once the second following call has
+      // returned) would not hold — the host could otherwise run many batches ahead of the copy stream.  Blocking on that
+      // copy also bounds the run-ahead to two chunks.
+      CK(cudaEventSynchronize(S->copied));
+      CK(cudaStreamWaitEvent(cs, S->consumed, 0));   // the kernels that read this staging set two chunks ago are done
+    }
   }
   // staging buffers may be in use on either stream: drain both before a buffer is re-allocated
   auto ens = [&](DBuf& d, size_t bytes) -> cudaError_t { if (bytes <= d.cap) return cudaSuccess; cudaError_t e = cudaStreamSynchronize(c->cstream); if (e != cudaSuccess) return e; return d.ensure(bytes, s); };
@@ -382,17 +416,22 @@ int nb_align_batch(nb_ctx* c, const nb_batch* bt, nb_read_result* reads_out, nb_
   }
   if (max_len > (u32)nbk::ENT_NMAX) return fail(NB_ERR_UNSUPPORTED, "reads longer than 1024 bases are not supported by the device path");
   if (max_len == 0) max_len = 1;
-  u64 chunk = c->max_batch_pairs;
-  for (u64 p0 = 0; p0 < bt->n_pairs; p0 += chunk) {
+  const u64 chunk = c->max_batch_pairs;
+  for (u64 p0 = 0; p0 < bt->n_pairs;) {
     u64 p1 = std::min(bt->n_pairs, p0 + chunk);
-    if (c->mode == 1 && p1 < bt->n_pairs) {  // never split a scope across chunks
-      while (p1 > p0 + 1 && bt->location == NB_MEM_HOST && bt->scope_id[p1] == bt->scope_id[p1 - 1]) p1--;
+    if (c->mode == 1 && p1 < bt->n_pairs) {  // never split a scope across chunks: its key table lives for one chunk
       if (bt->location != NB_MEM_HOST) return fail(NB_ERR_INVALID, "scoped device-resident batches must fit max_batch_pairs");
-      chunk = p1 - p0;
+      while (p1 > p0 + 1 && bt->scope_id[p1] == bt->scope_id[p1 - 1]) p1--;
+      if (bt->scope_id[p1] == bt->scope_id[p1 - 1]) {
+        // one scope is larger than max_batch_pairs: it must still be de-duplicated as a whole, so the chunk grows to the
+        // end of that scope (the per-chunk buffers grow with it)
+        p1 = std::min(bt->n_pairs, p0 + chunk);
+        while (p1 < bt->n_pairs && bt->scope_id[p1] == bt->scope_id[p1 - 1]) p1++;
+      }
     }
     int rc = run_chunk(c, bt, p0, p1, max_len, reads_out, pairs_out);
     if (rc) return rc;
-    chunk = c->max_batch_pairs;
+    p0 = p1;     // (round 1 advanced by max_batch_pairs here and silently skipped the pairs a shortened chunk left behind)
   }
   return NB_OK;
 }

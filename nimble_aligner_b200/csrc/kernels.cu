@@ -141,6 +141,12 @@ __device__ __forceinline__ u64 uwin(const u64* U, u64 pos) {
   if (!sh) return lo;
   return (lo >> sh) | (__ldg(U + w + 1) << (64 - sh));
 }
+// the same from three 32-bit loads and two funnel shifts (fewer ALU instructions, one more load: for the rarer paths)
+__device__ __forceinline__ u64 uwin3(const u64* U, u64 pos) {
+  const u32* p = (const u32*)U + (pos >> 4); const u32 sh = (u32)(pos & 15) * 2;
+  const u32 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  return (u64)__funnelshift_r(a, b, sh) | ((u64)__funnelshift_r(b, c, sh) << 32);
+}
 __device__ __forceinline__ bool bsearch32(const u32* a, u32 n, u32 x, u32& idx) {
   u32 lo = 0, hi = n;
   while (lo < hi) { u32 mid = (lo + hi) >> 1; if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid; }
@@ -214,31 +220,6 @@ struct EcAcc {
   __device__ u32 ec_len() const { return !any ? 0u : (big ? alen : (u32)__popcll(mask)); }
 };
 
-// forward compare of m bases: unitig [upos, upos+m) vs read [rpos, rpos+m); the (allowed+1)-th mismatch trips the
-// per-node budget: it is counted in snp (-> mismatches) but not in mb (-> coverage)   [App. B]
-// `next`: the read base right after the compared stretch (position rpos + m) when the compare ran to its end and that
-// base sits inside the last 32-base window that was loaded anyway; 4 = not available (caller loads it).
-// `ro`, s0, s1: offset of the stretch inside its unitig and the unitig's first 64 bases (from the walk record): windows
-// that end inside them need no load from the unitig store.
-__device__ __forceinline__ void cmp_fwd(const u64* U, u64 ustart, u32 ro, u64 s0, u64 s1, const ReadView& rd, u32 rpos, u32 m, u32 allowed, u32& mb, u32& snp, bool& brk, u32& next) {
-  mb = 0; snp = 0; brk = false; next = 4;
-  while (mb < m) {
-    u32 c = min(32u, m - mb);
-    u64 rw = rd.win(rpos + mb);
-    u32 o = ro + mb; u64 uw;
-    if (o + c <= 64) { if (o < 32) { u32 sh = 2 * o; uw = sh ? (s0 >> sh) | (s1 << (64 - sh)) : s0; } else uw = s1 >> (2 * (o - 32)); }
-    else uw = uwin(U, ustart + o);
-    u64 x = uw ^ rw;
-    u64 d = (x | (x >> 1)) & 0x5555555555555555ULL;
-    if (c < 32) d &= (1ULL << (2 * c)) - 1;
-    u32 cnt = (u32)__popcll(d);
-    if (snp + cnt <= allowed) { snp += cnt; mb += c; if (c < 32) next = (u32)(rw >> (2 * c)) & 3u; continue; }
-    u32 need = allowed - snp;
-    for (u32 i = 0; i < need; i++) d &= d - 1;
-    mb += (u32)(__ffsll((long long)d) - 1) >> 1;
-    snp = allowed + 1; brk = true; break;
-  }
-}
 // backward compare: unitig positions uhi-i vs read positions rhi-i, i in [0, m)
 __device__ __forceinline__ void cmp_bwd(const u64* U, u64 uhi, const ReadView& rd, u32 rhi, u32 m, u32 allowed, u32& mb, u32& snp, bool& brk) {
   mb = 0; snp = 0; brk = false;
@@ -657,15 +638,42 @@ void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const 
   if (!b.n_reads) return;
   // k_walk: persistent warps popping seeded reads from the global list (counters zeroed by the host before the launch):
   // enough blocks to fill every SM at the kernel's occupancy, never more than the work needs
-  static int sms = 0, per_sm[2] = {0, 0};
+  static int sms = 0, per_sm[4] = {0, 0, 0, 0};
   if (!sms) {
     int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_walk<0>, 128, 0) != cudaSuccess || per_sm[0] < 1) per_sm[0] = 8;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_walk<1>, 128, 0) != cudaSuccess || per_sm[1] < 1) per_sm[1] = 8;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_walk<0, 0>, 128, 0) != cudaSuccess || per_sm[0] < 1) per_sm[0] = 8;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_walk<1, 0>, 128, 0) != cudaSuccess || per_sm[1] < 1) per_sm[1] = 8;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_walk<0, 1>, 128, 0) != cudaSuccess || per_sm[2] < 1) per_sm[2] = 8;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_walk<1, 1>, 128, 0) != cudaSuccess || per_sm[3] < 1) per_sm[3] = 8;
   }
-  unsigned sb = blocks_for(b.n_reads, 128), wb = min(sb, (unsigned)(sms * per_sm[count_work ? 1 : 0]));
-  if (count_work) { k_seed<1><<<sb, 128, 0, s>>>(b, ix, cfg, t); k_walk<1><<<wb, 128, 0, s>>>(b, ix, cfg, t); }
-  else { k_seed<0><<<sb, 128, 0, s>>>(b, ix, cfg, t); k_walk<0><<<wb, 128, 0, s>>>(b, ix, cfg, t); }
+  const int v = (count_work ? 1 : 0) | (ix.hbm ? 2 : 0);
+  unsigned sb = blocks_for(b.n_reads, SEED_BLOCK), wb = min(blocks_for(b.n_reads, 128), (unsigned)(sms * per_sm[v]));
+  switch (v) {
+    case 0: k_seed<0, 0><<<sb, SEED_BLOCK, 0, s>>>(b, ix, cfg, t); k_walk<0, 0><<<wb, 128, 0, s>>>(b, ix, cfg, t); break;
+    case 1: k_seed<1, 0><<<sb, SEED_BLOCK, 0, s>>>(b, ix, cfg, t); k_walk<1, 0><<<wb, 128, 0, s>>>(b, ix, cfg, t); break;
+    case 2: k_seed<0, 1><<<sb, SEED_BLOCK, 0, s>>>(b, ix, cfg, t); k_walk<0, 1><<<wb, 128, 0, s>>>(b, ix, cfg, t); break;
+    default: k_seed<1, 1><<<sb, SEED_BLOCK, 0, s>>>(b, ix, cfg, t); k_walk<1, 1><<<wb, 128, 0, s>>>(b, ix, cfg, t); break;
+  }
+}
+// ---- probe table + Bloom prefilter, built on the device from the artefact's flat table when a context is created
+__global__ void __launch_bounds__(256) k_probe_build(const u64* tkey, const u64* tval, u64 slots, u64* ptab, u32 n_pbuckets, u64* bloom, u32 bloom_words, u32 bloom_k, unsigned int* err) {
+  u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= slots) return;
+  const u64 key = tkey[i];
+  if (!(key >> 63)) return;
+  const u64 val = tval[i], hh = nb_khash(key & KMASK); const u32 h = (u32)hh;
+  if (bloom_words) atomicOr((unsigned long long*)(bloom + __umulhi((u32)(hh >> 32), bloom_words)), (unsigned long long)nb_bloom_bits(h, bloom_k));
+  u32 b = __umulhi(h, n_pbuckets);
+  for (u32 tries = 0; tries < n_pbuckets; tries++) {
+    unsigned long long* q = (unsigned long long*)(ptab + 4 * (u64)b);
+    if (atomicCAS(q, 0ULL, (unsigned long long)key) == 0ULL) { ptab[4 * (u64)b + 2] = val; return; }   // slot 0 first: occupied slots stay a prefix
+    if (atomicCAS(q + 1, 0ULL, (unsigned long long)key) == 0ULL) { ptab[4 * (u64)b + 3] = val; return; }
+    if (++b == n_pbuckets) b = 0;
+  }
+  atomicOr(err, 1u);
+}
+void launch_probe_build(const u64* tkey, const u64* tval, u64 slots, u64* ptab, u32 n_pbuckets, u64* bloom, u32 bloom_words, u32 bloom_k, unsigned int* err, cudaStream_t s) {
+  if (slots) k_probe_build<<<blocks_for(slots, 256), 256, 0, s>>>(tkey, tval, slots, ptab, n_pbuckets, bloom, bloom_words, bloom_k, err);
 }
 size_t rows_sort_tmp_bytes(u64 n) { size_t tb = 0; cub::DeviceRadixSort::SortPairs(nullptr, tb, (const u64*)nullptr, (u64*)nullptr, (const i64*)nullptr, (i64*)nullptr, (int)n, 0, 56); return tb + 256; }
 // work: 2n u64 keys + 2n i64 values + temp; out: n u32 + n u32 + n i64 (all device)

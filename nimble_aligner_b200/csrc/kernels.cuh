@@ -29,7 +29,9 @@ constexpr int GL_MAX = 64;                 // per-thread group list capacity (ma
 constexpr int ENT_NMAX = 1024;             // longest read the entropy table covers
 
 struct DevIndex {
-  const u64* tkey; const u64* tval; u32 n_buckets;   // k-mer table (khash.h): bucket b = keys 4b .. 4b+3 (one 32-byte sector, one 256-bit load), values apart
+  const u64* ptab; u32 n_pbuckets;                   // probe table (khash.h): bucket b = {key0, key1, value0, value1}, one 32-byte sector / one 256-bit load
+  const u64* bloom; u32 bloom_words; u32 bloom_k;    // blocked Bloom prefilter in front of it (64-bit words, k bits per k-mer)
+  u32 hbm;                                           // the table cannot live in L2: kernels use the L2 eviction hints (filter evict_last, buckets evict_first)
   const u64* unitig;
   const uint4* node;      // {start_lo, len, colour, lext | rext<<4 | start_hi<<8}
   const uint4* walk;      // 64-byte record per unitig, everything one forward step needs in one DRAM burst / two L2 sectors:
@@ -99,6 +101,8 @@ struct KeyRec { u64 k0, k1, order, tag; };
 constexpr int ROUTE_MAX = 16;
 struct Route { u32 world, rank; u64 pair_base, cap; KeyRec* inbox[ROUTE_MAX]; unsigned long long* cursor; };
 
+// device probe table + prefilter from the flat k-mer table of the index artefact (tkey/tval: 4-key buckets, host.hpp)
+void launch_probe_build(const u64* tkey, const u64* tval, u64 slots, u64* ptab, u32 n_pbuckets, u64* bloom, u32 bloom_words, u32 bloom_k, unsigned int* err, cudaStream_t s);
 void launch_pack(const BatchDev& b, cudaStream_t s);
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s);
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s);

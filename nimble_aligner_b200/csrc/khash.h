@@ -23,3 +23,14 @@ NB_HD uint64_t nb_khash(uint64_t km) {
 // 32-bit hash is range-reduced by multiply-high.
 NB_HD uint32_t nb_table_bucket(uint64_t km, uint64_t n_buckets) { return (uint32_t)(((uint64_t)(uint32_t)nb_khash(km) * n_buckets) >> 32); }
 NB_HD uint64_t nb_table_size(uint64_t n_kmers) { return (n_kmers * 5 + 7) / 8 + 4; }   // 4 slots per bucket, load 0.4
+// ---- device probe table (built at upload from the flat table above): buckets of two keys and their two values
+// {key0, key1, value0, value1} = one 32-byte sector, so a hit needs no second load for (unitig, offset); home bucket by the
+// same multiply-high reduction of h, linear probing by bucket.  2 slots at load 0.4: 5 % of buckets are full.
+NB_HD uint64_t nb_ptab_buckets(uint64_t n_kmers) { return n_kmers + n_kmers / 4 + 2; }
+// Blocked Bloom prefilter in front of it when the table cannot live in L2: one 64-bit word per k-mer (chosen by g, the
+// high half of nb_khash), k = 2 or 3 bits inside it from h's low bits.
+NB_HD uint64_t nb_bloom_bits(uint32_t h, uint32_t k) {
+  uint64_t m = (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63));
+  if (k > 2) m |= 1ULL << ((h >> 12) & 63);
+  return m;
+}

@@ -503,3 +503,40 @@ def test_tangled_orientations_all_configs():
         o.set_config(**dict(ocfg, strand_filter="fiveprime"))
         compare(ctx, o, dict(ocfg, strand_filter="fiveprime"), r1, o1)     # single-end through the same logic
     assert n_callsets > 200
+
+
+def test_scope_larger_than_max_batch_pairs_is_still_deduplicated_as_a_whole(c2_built):
+    """A (UMI, CB) scope with more pairs than max_batch_pairs: the chunk must grow to the end of the scope — cutting it would
+    clear the key table in the middle and count duplicate read_keys twice (src/align.rs:576-579, 685)."""
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, _ = built[""]
+    o.set_config(**ocfg)
+    r1, o1, r2, o2 = synth.pairs(L, 0, 700, dup_rate=0.5, paired=True)
+    n = len(o1) - 1
+    # scopes: 0 = pairs [0, 40), 1 = one big scope [40, 600) with many duplicates, 2.. = small ones
+    scope = np.zeros(n, dtype=np.uint32)
+    scope[40:600] = 1
+    scope[600:] = 2 + (np.arange(n - 600) // 7)
+    ctx = nb.Context(ix, lib, max_batch_pairs=64)
+    res, ref = compare(ctx, o, ocfg, r1, o1, r2, o2, scope=scope, check_ecs=False)
+    big = nb.Context(ix, lib, max_batch_pairs=1 << 20)
+    big.set_config(gpu_cfg(lib, ocfg))
+    big.align_batch(r1, o1, r2, o2, scope_id=scope)
+    assert big.counts()["rows"] == res["rows"]
+    assert sum(c for sc, _cs, c in res["rows"] if sc == 1) < 560     # duplicates inside the big scope really were merged
+
+
+def test_hbm_resident_kernel_variant_on_a_small_library(c2_built, monkeypatch):
+    """The kernels compiled for an HBM-resident index (L2 eviction hints on the prefilter and the table buckets) are chosen
+    by table size; NB_L2_HINTS=1 forces them for a small library so that both variants see the same parity cases."""
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, _ = built[""]
+    o.set_config(**ocfg)
+    monkeypatch.setenv("NB_L2_HINTS", "1")
+    ctx = nb.Context(ix, lib, count_work=1)
+    monkeypatch.delenv("NB_L2_HINTS")
+    r1, o1, r2, o2 = synth.pairs(L, 300_000, 20_000, paired=True)
+    res, ref = compare(ctx, o, ocfg, r1, o1, r2, o2)
+    w = ctx.work_counters()
+    for k in ("probes", "nodes", "bases"):
+        assert w[k] == ref["work"][k], (k, w[k], ref["work"][k])
