@@ -409,14 +409,12 @@ def run_c3(env, args):
             p1 -= 1
         cuts.append(p1)
     if world > 1:
-        from nimble_aligner_b200.multigpu import merge_scoped_across_ranks, DeviceShard
-        shard = DeviceShard(ctx, nb, torch, 0, 0)
+        from nimble_aligner_b200.multigpu import lib_comm
+        lib_comm(ctx, nb, torch, dist, rank, world)
 
     def finish():
         if world > 1:
-            raw, cells, css, vals = merge_scoped_across_ranks(shard, torch, dist, rank, world, "cuda", n_cells)
-            raw = dict(raw); raw["m_cells"], raw["m_css"], raw["m_vals"] = cells, css, vals
-            return raw
+            return ctx.merge_scoped(n_cells)   # nb_merge_scoped: dictionaries all-gathered, per-cell tables summed by one dense all-reduce
         return ctx.counts_raw()
 
     def step_device():
@@ -436,8 +434,6 @@ def run_c3(env, args):
         return finish()
 
     def table(raw):
-        if "m_vals" in raw:
-            return (np.asarray(raw["m_cells"]).astype(np.int64), np.asarray(raw["m_css"]).astype(np.int64), np.asarray(raw["m_vals"]).astype(np.int64))
         return (raw["row_scope"].astype(np.int64), raw["row_callset"].astype(np.int64), raw["row_count"].astype(np.int64))
 
     for _ in range(max(1, args.warmup - 1)):
@@ -455,7 +451,7 @@ def run_c3(env, args):
     total = n * world
     h2d = int(u["off"][-1]) * 2 + n * (8 + 4 + 4 + 2)
     out = {"workload": "C3-shaped: %d 10x-style single-end 91 bp records with raw Phred quals per GPU in %d (UMI,CB) scopes (dummy mates, MAXINFO trim 40:0.9), %d cells, 1k-transcript library; per-cell count table%s"
-                       % (n, len(u["sizes"]), n_cells, (", scopes sharded over %d ranks and the tables merged over NCCL" % world) if world > 1 else ""),
+                       % (n, len(u["sizes"]), n_cells, (", scopes sharded over %d ranks and the tables merged by nb_merge_scoped (NCCL all-gather + dense all-reduce inside the library)" % world) if world > 1 else ""),
            "value": total / (ms_dev / 1e3), "unit": UNIT, "ms_per_step": ms_dev, "steps": args.steps, "n_gpus": world, "records_per_step": total,
            "e2e": {"value": total / (ms_host / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 16 * len(td[0]) + 192, "ms_per_step": ms_host,
                    "h2d_gbs": h2d * world / (ms_host / 1e3) / 1e9, "of_h2d_ceiling": (h2d / (ms_host / 1e3) / 1e9) / env.h2d_ceiling if env.h2d_ceiling else None},
@@ -508,7 +504,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (parity + cpu_baseline + roofline): kernel tuning runs only")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the verification pass")
     ap.add_argument("--verify", action="store_true", help="N>1: ALSO check the full-size merged counts against one GPU over the union of all shards (slow)")
-    ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="N>1: key records routed inside k_pair over NVLink peer stores (default), or exchanged with an NCCL all-to-all when the job ends")
+    ap.add_argument("--merge", default="lib", choices=["lib", "py-p2p", "py-nccl"], help="N>1: merge inside the library over NCCL with key records routed inside k_pair (default); py-*: round 1's host-driven choreography (routed / NCCL all-to-all)")
     ap.add_argument("--mismatches", type=int, default=0, help="num_mismatches of the library config (C5 sweeps 0/1/2)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -565,9 +561,20 @@ def main():
     d1, d2, do1, do2 = h1.cuda(), h2.cuda(), ho1.cuda(), ho2.cuda()
     n_reads = 2 * n
 
-    from nimble_aligner_b200.multigpu import merge_across_ranks, DeviceShard, setup_routes
-    routed = world > 1 and args.merge == "p2p" and setup_routes(ctx, torch, dist, rank, world, "cuda", pair_base, (n + n // 2) // world + 4096)
-    shard = DeviceShard(ctx, nb, torch, pair_base, n, routed=routed) if world > 1 else None   # merge buffers are allocated once, outside the job
+    from nimble_aligner_b200.multigpu import merge_across_ranks, DeviceShard, setup_routes, lib_comm
+    # N>1, default: the merge runs inside the library (nb_merge_whole_run: NCCL called from C++ on the context's stream, key
+    # records routed inside k_pair over NVLink).  --merge py-p2p / py-nccl keep round 1's Python choreography for A/B.
+    in_lib = routed = False
+    if world > 1 and args.merge == "lib":
+        lib_comm(ctx, nb, torch, dist, rank, world)
+        try:
+            ctx.route_setup((n + n // 2) // world + 4096, pair_base)
+            in_lib = routed = True
+        except nb.NbError as e:   # no NVLink / IPC between the processes: every rank fails together
+            log("rank %d: in-library merge unavailable (%s); falling back to the NCCL all-to-all driven from the host" % (rank, e))
+    if world > 1 and not in_lib:
+        routed = args.merge != "py-nccl" and setup_routes(ctx, torch, dist, rank, world, "cuda", pair_base, (n + n // 2) // world + 4096)
+    shard = DeviceShard(ctx, nb, torch, pair_base, n, routed=routed) if world > 1 and not in_lib else None   # merge buffers are allocated once, outside the job
 
     def job(pairs, dev):
         """one whole job over this rank's first `pairs` pairs: device-resident or host-fed input"""
@@ -577,6 +584,9 @@ def main():
         else:
             b = nb.Batch(pairs, nb.NB_MEM_HOST, READ_LEN, h1.data_ptr(), ho1.data_ptr(), h2.data_ptr(), ho2.data_ptr(), None, None, None, None, None, None)
             nb._ck(nb.lib().nb_align_batch(ctx.h, C.byref(b), None, None))
+        if in_lib:
+            raw = ctx.merge_whole_run()  # nb_merge_whole_run: every rank ends with the whole job's counts
+            return raw, raw["n_unique_keys"]
         if world > 1:
             return merge_across_ranks(shard, torch, dist, rank, world, "cuda", routed=routed)
         raw = ctx.counts_raw()          # nb_counts_finalize: the job's result (group indices + counts) on the host
@@ -595,7 +605,27 @@ def main():
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     job(n, False)
     ms_host, (counts_host, uniq_host) = timed(env, lambda: job(n, False), args.steps)
+    # ---- the same job with the reads shipped 2-bit packed (NB_SEQ_2BIT: the boundary score::call really has — DnaStrings —
+    # and a quarter of the PCIe bytes); packing happens outside the timed region, as a host that holds packed reads would have it
+    p1 = torch.empty((int(o1[-1]) + 3) // 4 + 64, dtype=torch.uint8).pin_memory(); p2 = torch.empty((int(o2[-1]) + 3) // 4 + 64, dtype=torch.uint8).pin_memory()
+    synth.encode_2bit(h1.numpy(), int(o1[-1]), p1.numpy(), cores); synth.encode_2bit(h2.numpy(), int(o2[-1]), p2.numpy(), cores)
+
+    def job_packed():
+        ctx.reset()
+        b = nb.Batch(n, nb.NB_MEM_HOST, READ_LEN, p1.data_ptr(), ho1.data_ptr(), p2.data_ptr(), ho2.data_ptr(), None, None, None, None, None, None, nb.NB_SEQ_2BIT, 0, None, None)
+        nb._ck(nb.lib().nb_align_batch(ctx.h, C.byref(b), None, None))
+        if in_lib:
+            raw = ctx.merge_whole_run()
+            return raw, raw["n_unique_keys"]
+        if world > 1:
+            return merge_across_ranks(shard, torch, dist, rank, world, "cuda", routed=routed)
+        raw = ctx.counts_raw()
+        return raw, raw["n_unique_keys"]
+    job_packed()
+    ms_packed, (counts_packed, uniq_packed) = timed(env, job_packed, args.steps)
+    counts_packed = whole_counts(ctx, counts_packed)
     counts_dev, counts_host = whole_counts(ctx, counts_dev), whole_counts(ctx, counts_host)
+    assert counts_packed == counts_host and uniq_packed == uniq_host, "2-bit packed and ASCII host-fed runs disagree"
     if counts_host != counts_dev:
         diff = [(k, counts_dev.get(k), counts_host.get(k)) for k in set(counts_dev) | set(counts_host) if counts_dev.get(k) != counts_host.get(k)]
         log("rank %d: %d callsets differ (dev total %d, host total %d, %d vs %d callsets); e.g. %s" % (rank, len(diff), sum(counts_dev.values()), sum(counts_host.values()), len(counts_dev), len(counts_host), diff[:3]))
@@ -653,13 +683,17 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
                "config": {"workload": "C2: synthetic 1k-transcript family library (200x5, seed 1234) x %d 2x150 bp pairs per GPU, FASTQ-mode whole-run scope" % n,
-                          "num_mismatches": args.mismatches, "merge": ("p2p-routed (k_pair stores key records into their owners' inboxes over NVLink)" if routed else "nccl all-to-all at job end") if world > 1 else "none (one GPU)",
+                          "num_mismatches": args.mismatches, "merge": (("nb_merge_whole_run inside the library (NCCL from C++ on the context's stream; " if in_lib else "host-driven (") + ("k_pair stores key records into their owners' inboxes over NVLink)" if routed else "nccl all-to-all at job end)")) if world > 1 else "none (one GPU)",
                           "numa_bind": ("each rank bound to the %d CPUs local to its GPU" % numa_cpus) if numa_cpus else "none",
                           "pairs_per_gpu": n, "reads_per_step": n_reads * world, "chunk_pairs": args.chunk, "l2": "inputs (%.1f GB ASCII per step) exceed the 126 MB L2" % ((int(o1[-1]) + int(o2[-1])) / 1e9),
                           "index_device_mb": ix.stats()["device_bytes"] / 1e6, "index_build_s": index_build_s, "unique_pair_keys": int(uniq_dev), "callsets_counted": len(counts_dev)},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h, "ms_per_step": ms_host, "h2d_gbs_per_gpu": h2d_gbs,
                        "h2d_ceiling_gbs_per_gpu": env.h2d_ceiling, "of_h2d_ceiling": h2d_gbs / env.h2d_ceiling if env.h2d_ceiling else None,
                        "encoding": "ASCII bases (1 byte per base), the reference's FASTQ boundary"},
+               "e2e_packed": {"value": n_reads * world / (ms_packed / 1e3), "unit": UNIT, "ms_per_step": ms_packed, "encoding": "NB_SEQ_2BIT (2 bits per base, offsets in bases)",
+                              "h2d_bytes_per_step": ((int(o1[-1]) + 3) // 4 + (int(o2[-1]) + 3) // 4 + 2 * 8 * (n + 1)) * world, "d2h_bytes_per_step": d2h,
+                              "h2d_gbs_per_gpu": ((int(o1[-1]) + 3) // 4 + (int(o2[-1]) + 3) // 4 + 2 * 8 * (n + 1)) / (ms_packed / 1e3) / 1e9,
+                              "parity": "counts and unique-key count identical to the ASCII host-fed run of the same step (asserted)"},
                "gpu_launches": ks["launches"], "clocks": clocks,
                "k_map_ms_per_launch": ks["map_ms"] / max(1, ks["map_launches"]), "k_map_reads_per_launch": ks["map_reads"] / max(1, ks["map_launches"]),
                "roofs_measured_live": {"l2_gather_gbs_47MB_rec32": env.gather_l2, "hbm_gather_gbs_2GB_rec32": env.gather_hbm, "h2d_pinned_gbs": env.h2d_ceiling}}
@@ -697,7 +731,7 @@ def main():
         out["roofline"]["frac_of_hbm_stream_peak"] = out["roofline"]["achieved"] / hp
         out["roofline"]["hbm_stream_peak"] = hp
     ctx.close()
-    del d1, d2, do1, do2, h1, h2
+    del d1, d2, do1, do2, h1, h2, p1, p2
     torch.cuda.empty_cache()
     if "c4" in blocks and world == 1:
         t0 = time.time()

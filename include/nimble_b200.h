@@ -148,7 +148,20 @@ typedef struct nb_batch {
   const uint8_t* flags1; const uint8_t* flags2;
   const uint32_t* scope_id;
   const uint32_t* cell_id;     /* optional with scope_id: row key of the count table (e.g. the cell barcode); NULL = scope_id */
+  int32_t encoding;            /* NB_SEQ_ASCII (0, default) | NB_SEQ_2BIT | NB_SEQ_BAM4: how r1 / r2 hold the bases */
+  int32_t reserved;
+  const uint32_t* r1_len; const uint32_t* r2_len;   /* packed encodings, optional: explicit read lengths when the reads are not densely packed */
 } nb_batch;
+/* Packed encodings: what score::call really receives are 2-bit DnaStrings (src/score.rs:14-31) and BAM stores 4-bit bases
+ * (src/parse/bam.rs:186-189), so a host that already holds packed reads ships a quarter / half of the bytes.  r?_off then
+ * count BASES of the packed stream (n_pairs + 1 entries; a read may start at any base); lengths are r?_off[p+1] - r?_off[p]
+ * unless r?_len is given.  q1 / q2 stay one byte per base at the same base offsets.
+ *   NB_SEQ_2BIT  base j = bits 2(j&3)..2(j&3)+1 of byte j>>2, A=0 C=1 G=2 T=3 (a non-ACGT base must already be 0, as
+ *                DnaString::from_acgt_bytes makes it)
+ *   NB_SEQ_BAM4  nibble j = byte j>>1, high nibble first (BAM's seq field), code table "=ACMGRSVTWYHKDBN": everything but
+ *                A, C, G, T becomes A, exactly what the reference does with those letters
+ * Buffers must be readable for 16 bytes past the last base. */
+enum { NB_SEQ_ASCII = 0, NB_SEQ_2BIT = 1, NB_SEQ_BAM4 = 2 };
 
 /* Per-read outcome of align::pseudoalign (src/align.rs:945-989): reason is SuccessfulMatch when the read passed;
  * score / mismatches are map_read_with_mismatch's coverage and mismatch totals (0 when it returned None). */
@@ -235,6 +248,34 @@ int nb_route_set_pair_base(nb_ctx*, uint64_t pair_index_base);
 int nb_route_sent(nb_ctx*, uint64_t* sent);
 int nb_route_import(nb_ctx*, const uint64_t* counts, uint64_t* n_imported);
 int nb_route_detach(nb_ctx*);
+
+/* ---- multi-GPU merge inside the library, over NCCL (SURVEY.md §8b `nb_counts_allreduce(nb_ctx*, ncclComm_t)`, §8e).  The
+ * reference's parallel driver is N-1 consumer threads behind one producer (src/process/bam.rs:183-226); here it is one
+ * context per GPU.  NCCL is resolved from libnccl.so.2 at run time (a single-GPU host needs none); all collectives run on
+ * the context's stream and the host waits once per merge.
+ *   nb_comm_unique_id   ncclGetUniqueId (128 bytes): rank 0 creates it, the host hands it to every rank
+ *   nb_comm_init_rank   one process per GPU: ncclCommInitRank on the context's device; the communicator lives in the context
+ *   nb_comm_attach      adopt a communicator the host created (ncclComm_t); not destroyed by the library
+ *   nb_comm_init_all    one process driving n GPUs: ncclCommInitAll over the contexts' devices (rank i = ctxs[i])
+ *   nb_route_setup      one process per GPU: nb_route_create + all-gather of the IPC handles + nb_route_attach_ipc; fails on
+ *                       EVERY rank when any rank cannot open its peers (no NVLink / IPC)
+ *   nb_merge_whole_run  whole-run scope (FASTQ mode) with peer routing attached: dictionaries all-gathered, this rank's inbox
+ *                       merged, its keys folded, {callset, count} rows all-gathered and summed: every rank's `out` holds the
+ *                       job's counts (n_unique_keys = unique read_keys of the whole job), as nb_counts_finalize would on one GPU
+ *   nb_merge_scoped     scoped batches (BAM mode; whole scopes shard over ranks, no data-path exchange): dictionaries
+ *                       all-gathered, then the per-cell tables are summed with one dense [n_cells x callsets] all-reduce;
+ *                       row_scope of `out` = cell id.  n_cells = 1 + the largest cell_id of the job
+ * Collective calls: every rank of the communicator must make them in the same order. */
+enum { NB_COMM_ID_BYTES = 128 };
+int nb_comm_unique_id(void* id128_out);
+int nb_comm_init_rank(nb_ctx*, const void* id128, uint32_t world, uint32_t rank);
+int nb_comm_attach(nb_ctx*, void* nccl_comm);
+int nb_comm_init_all(nb_ctx* const* ctxs, uint32_t n);
+int nb_comm_free(nb_ctx*);
+int nb_comm_info(nb_ctx*, uint32_t* world, uint32_t* rank);
+int nb_route_setup(nb_ctx*, uint64_t records_per_peer, uint64_t pair_index_base);
+int nb_merge_whole_run(nb_ctx*, nb_counts* out);
+int nb_merge_scoped(nb_ctx*, uint64_t n_cells, nb_counts* out);
 
 /* timing of the dominant kernel (seed_walk_map), CUDA events on the launching stream: out[0]=launches, out[1]=total ms,
  * out[2]=reads processed, out[3]=all kernels launched by this ctx since reset */

@@ -27,6 +27,7 @@ REASONS = ["ScoreBelowThreshold", "DiscardedMultipleMatch", "DiscardedNonzeroMis
            "SkippedAlignDueToUnpairedDummy", "None"]
 R = {n: i for i, n in enumerate(REASONS)}
 NB_MEM_HOST, NB_MEM_DEVICE = 0, 1
+NB_SEQ_ASCII, NB_SEQ_2BIT, NB_SEQ_BAM4 = 0, 1, 2
 FLAG_SKIP_ALIGN, FLAG_REVCOMP = 1, 2
 
 
@@ -56,7 +57,8 @@ class Batch(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("location", C.c_int32), ("max_read_len", C.c_uint32),
                 ("r1", C.c_void_p), ("r1_off", C.c_void_p), ("r2", C.c_void_p), ("r2_off", C.c_void_p),
                 ("q1", C.c_void_p), ("q2", C.c_void_p), ("flags1", C.c_void_p), ("flags2", C.c_void_p),
-                ("scope_id", C.c_void_p), ("cell_id", C.c_void_p)]
+                ("scope_id", C.c_void_p), ("cell_id", C.c_void_p),
+                ("encoding", C.c_int32), ("reserved", C.c_int32), ("r1_len", C.c_void_p), ("r2_len", C.c_void_p)]
 
 
 class Counts(C.Structure):
@@ -119,6 +121,15 @@ _SIGS = {
     "nb_route_detach": (C.c_int, [C.c_void_p]),
     "nb_ctx_kernel_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "nb_ctx_work_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "nb_comm_init_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "nb_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nb_comm_init_all": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "nb_comm_free": (C.c_int, [C.c_void_p]),
+    "nb_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "nb_route_setup": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "nb_merge_whole_run": (C.c_int, [C.c_void_p, C.POINTER(Counts)]),
+    "nb_merge_scoped": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Counts)]),
     "nb_measure_gather": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]),
     "nb_measure_h2d": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_double)]),
     "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),
@@ -295,6 +306,37 @@ def build_index(library, threads=1, device=None):
     return Index.build(library, threads, device)
 
 
+def encode_2bit(ascii_bases, off):
+    """ASCII reads (uint8 array + uint64 offsets) -> NB_SEQ_2BIT stream with the same base offsets (host-side packer of the
+    harness; a real producer holds packed reads already).  Non-ACGT -> A like DnaString::from_acgt_bytes."""
+    n = int(off[-1])
+    lut = np.zeros(256, dtype=np.uint8)
+    for ch, code in ((b"C", 1), (b"c", 1), (b"G", 2), (b"g", 2), (b"T", 3), (b"t", 3)):
+        lut[ch[0]] = code
+    codes = lut[np.asarray(ascii_bases[:n])]
+    pad = (-n) % 4
+    if pad:
+        codes = np.concatenate([codes, np.zeros(pad, dtype=np.uint8)])
+    q = codes.reshape(-1, 4)
+    out = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
+    return np.concatenate([out, np.zeros(64, dtype=np.uint8)])
+
+
+def encode_bam4(ascii_bases, off):
+    """ASCII reads -> NB_SEQ_BAM4 nibble stream with the same base offsets (high nibble first, "=ACMGRSVTWYHKDBN")."""
+    n = int(off[-1])
+    lut = np.full(256, 15, dtype=np.uint8)   # anything unknown -> N
+    for i, ch in enumerate("=ACMGRSVTWYHKDBN"):
+        lut[ord(ch)] = i
+        lut[ord(ch.lower())] = i
+    codes = lut[np.asarray(ascii_bases[:n])]
+    if n % 2:
+        codes = np.concatenate([codes, np.zeros(1, dtype=np.uint8)])
+    q = codes.reshape(-1, 2)
+    out = ((q[:, 0] << 4) | q[:, 1]).astype(np.uint8)
+    return np.concatenate([out, np.zeros(64, dtype=np.uint8)])
+
+
 def pack_reads(reads):
     """list of str/bytes -> (uint8 array, uint64 offsets[n+1])."""
     bs = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
@@ -344,12 +386,14 @@ class Context:
         _ck(lib().nb_ctx_sync(self.h))
 
     def align_batch(self, r1, r1_off, r2=None, r2_off=None, q1=None, q2=None, flags1=None, flags2=None, scope_id=None, cell_id=None,
-                    n_pairs=None, max_read_len=0, location=NB_MEM_HOST, reads_out=None, pairs_out=None, want_reads=False, want_pairs=False):
+                    n_pairs=None, max_read_len=0, location=NB_MEM_HOST, reads_out=None, pairs_out=None, want_reads=False, want_pairs=False,
+                    encoding=NB_SEQ_ASCII, r1_len=None, r2_len=None):
         """nb_align_batch.  Host arrays are numpy; device arrays may be torch tensors or raw pointers (then pass n_pairs)."""
         keep = [np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a for a in (r1, r1_off, r2, r2_off, q1, q2, flags1, flags2, scope_id, cell_id)]
+        lens = [np.ascontiguousarray(a, dtype=np.uint32) if isinstance(a, np.ndarray) else a for a in (r1_len, r2_len)]
         if n_pairs is None:
             n_pairs = len(keep[1]) - 1
-        b = Batch(n_pairs, location, max_read_len, *[_ptr(a) for a in keep])
+        b = Batch(n_pairs, location, max_read_len, *[_ptr(a) for a in keep], encoding, 0, _ptr(lens[0]), _ptr(lens[1]))
         sides = 2 if r2 is not None else 1
         if want_reads and reads_out is None:
             reads_out = np.zeros(n_pairs * sides, dtype=READ_DT)
@@ -378,7 +422,10 @@ class Context:
         columns out (a multi-GPU host that reduces them on the device, counts_device_rows, has no use for host copies)."""
         c = Counts()
         _ck(lib().nb_counts_finalize(self.h, C.byref(c)))
+        return self._raw(c, rows)
 
+    @staticmethod
+    def _raw(c, rows=True):
         def arr(p, n, dt):
             return np.ctypeslib.as_array(p, (n,)).copy() if n else np.zeros(0, dt)
         n_items = int(c.callset_off[c.n_callsets]) if c.n_callsets else 0
@@ -387,6 +434,33 @@ class Context:
                     row_count=arr(c.row_count, nr, np.int64), callset_off=arr(c.callset_off, c.n_callsets + 1, np.uint64),
                     callset_items=arr(c.callset_items, n_items, np.uint32), n_pairs_seen=c.n_pairs_seen, n_unique_keys=c.n_unique_keys,
                     slot_to_callset=arr(c.slot_to_callset, c.n_slots, np.uint32))
+
+    # ---- multi-GPU merge inside the library (nb_comm_*, nb_merge_*)
+    def comm_init_rank(self, unique_id, world, rank):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        _ck(lib().nb_comm_init_rank(self.h, uid.ctypes.data, int(world), int(rank)))
+        self._route_world = int(world)
+
+    def comm_free(self):
+        _ck(lib().nb_comm_free(self.h))
+
+    def route_setup(self, records_per_peer, pair_index_base):
+        """nb_route_create + IPC handle all-gather + attach, over the context's communicator; raises on every rank when any
+        rank cannot open its peers."""
+        _ck(lib().nb_route_setup(self.h, int(records_per_peer), int(pair_index_base)))
+
+    def merge_whole_run(self):
+        """nb_merge_whole_run -> the whole job's counts (same dict as counts_raw), identical on every rank."""
+        c = Counts()
+        _ck(lib().nb_merge_whole_run(self.h, C.byref(c)))
+        return self._raw(c)
+
+    def merge_scoped(self, n_cells):
+        """nb_merge_scoped -> per-cell rows of the whole job (row_scope = cell id), identical on every rank."""
+        c = Counts()
+        _ck(lib().nb_merge_scoped(self.h, int(n_cells), C.byref(c)))
+        return self._raw(c)
 
     def counts_device_rows(self):
         """(row_scope, row_callset, row_count) of the last finalize as objects with __cuda_array_interface__ (zero copy)."""
@@ -478,6 +552,21 @@ def measure_h2d(devices=(0,), nbytes=256 << 20, reps=8):
     agg = C.c_double(0)
     _ck(lib().nb_measure_h2d(d.ctypes.data, len(d), int(nbytes), reps, per.ctypes.data, C.byref(agg)))
     return per.tolist(), agg.value
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (128 bytes): rank 0 creates it, the host hands it to every rank."""
+    uid = np.zeros(128, dtype=np.uint8)
+    _ck(lib().nb_comm_unique_id(uid.ctypes.data))
+    return uid
+
+
+def comm_init_all(contexts):
+    """One process driving several GPUs: ncclCommInitAll over the contexts' devices (rank i = contexts[i])."""
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    _ck(lib().nb_comm_init_all(arr, len(contexts)))
+    for c in contexts:
+        c._route_world = len(contexts)
 
 
 def get_calls(sequences, mate_sequences, sequence_metadata, index, reference, aligner_config, device=0):

@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
                 cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
                 subprocess.check_call(cmd)
             objs.append(o)
-        subprocess.check_call([NVCC, "-shared", "-cudart", "shared", "-o", SO] + objs + ["-lz", "-lpthread"])
+        subprocess.check_call([NVCC, "-shared", "-cudart", "shared", "-o", SO] + objs + ["-lz", "-lpthread", "-ldl"])
         if os.path.exists(AR):
             os.remove(AR)
         subprocess.check_call(["ar", "rcs", AR] + objs)

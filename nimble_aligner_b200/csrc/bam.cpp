@@ -9,6 +9,7 @@
 //                                          header + row format (22-42, 90-121), zero rows (329-353), reasons (356-396)
 // The reference runs cores-1 consumer threads over an mpsc channel; here one GPU context per library takes whole
 // batches of groups (scope_id = group number) and the row order is group order (the reference's order is arbitrary).
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -48,47 +49,83 @@ struct RawBuf {
   const u8& operator[](size_t i) const { return p[i]; } u8& operator[](size_t i) { return p[i]; }
 };
 
+// Streaming BGZF reader: the file is consumed window by window (about `target` inflated bytes at a time), each window's
+// blocks inflated in parallel on the host threads; nothing but the current windows is ever resident (the reference's reader
+// holds one UMI at a time, src/parse/sorted_bam_reader.rs:31-107, and its channel 50 groups, src/process/bam.rs:149).
 struct Bgzf {
-  RawBuf file, data;   // compressed file image, inflated stream
-  int load(const std::string& path, int threads) {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) return fail(NB_ERR_IO, "could not open " + path);
-    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
-    if (!file.alloc((size_t)sz)) { fclose(f); return fail(NB_ERR_IO, "out of memory reading " + path); }
-    if (sz && fread(file.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(NB_ERR_IO, "short read on " + path); }
-    fclose(f);
+  FILE* f = nullptr; std::string path; std::vector<u8> cbuf; size_t cpos = 0, cend = 0; bool file_done = false;
+  RawBuf data;   // whole-stream mode (window = everything): kept for callers that want one buffer
+  ~Bgzf() { if (f) fclose(f); }
+  int open(const std::string& p) {
+    path = p; f = fopen(p.c_str(), "rb");
+    if (!f) return fail(NB_ERR_IO, "could not open " + p);
+    cpos = cend = 0; file_done = false;
+    return NB_OK;
+  }
+  // Appends the inflated bytes of the next blocks (at least one block, about `target` bytes, everything left when target is
+  // SIZE_MAX) behind the first `keep` bytes of `out` (the carry-over of the previous window, already in place).  eof: the
+  // file is exhausted after this window.
+  int next(RawBuf& out, size_t keep, size_t target, int threads, size_t& n_out, bool& eof) {
     struct Blk { size_t off, clen, uoff, ulen; };
-    std::vector<Blk> blks; size_t p = 0, utot = 0;
-    while (p + 18 <= file.size()) {
-      const u8* h = &file[p];
+    std::vector<Blk> blks; size_t utot = 0;
+    for (;;) {
+      const size_t avail = cend - cpos;
+      if (avail < 18) { if (!refill(18)) { if (avail == 0) break; return fail(NB_ERR_PARSE, "truncated BGZF block at the end of " + path); } continue; }
+      const u8* h = &cbuf[cpos];
       if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return fail(NB_ERR_PARSE, "not a BGZF file: " + path);
       // every size field comes from the file: nothing is read or handed to inflate() before it is checked against the
-      // block and the file (a damaged BAM must fail with NB_ERR_PARSE, never read out of bounds)
-      size_t xlen = h[10] | (h[11] << 8), q = p + 12, xend = q + xlen, bsize = 0;
-      if (xend > file.size()) return fail(NB_ERR_PARSE, "corrupt BGZF block (extra field runs past the end of the file) in " + path);
-      while (q + 4 <= xend) { size_t slen = file[q + 2] | (file[q + 3] << 8); if (q + 4 + slen > xend) break; if (file[q] == 'B' && file[q + 1] == 'C' && slen == 2) bsize = (file[q + 4] | (file[q + 5] << 8)) + 1; q += 4 + slen; }
-      if (!bsize || p + bsize > file.size() || 12 + xlen + 8 > bsize) return fail(NB_ERR_PARSE, "corrupt BGZF block in " + path);
-      size_t isize = file[p + bsize - 4] | (file[p + bsize - 3] << 8) | (file[p + bsize - 2] << 16) | ((size_t)file[p + bsize - 1] << 24);
+      // block and the bytes that are really there (a damaged BAM must fail with NB_ERR_PARSE, never read out of bounds)
+      const size_t xlen = h[10] | (h[11] << 8);
+      if (avail < 12 + xlen) { if (!refill(12 + xlen)) return fail(NB_ERR_PARSE, "corrupt BGZF block (extra field runs past the end of the file) in " + path); continue; }
+      size_t q = cpos + 12, xend = q + xlen, bsize = 0;
+      while (q + 4 <= xend) { size_t slen = cbuf[q + 2] | (cbuf[q + 3] << 8); if (q + 4 + slen > xend) break; if (cbuf[q] == 'B' && cbuf[q + 1] == 'C' && slen == 2) bsize = (cbuf[q + 4] | (cbuf[q + 5] << 8)) + 1; q += 4 + slen; }
+      if (!bsize || 12 + xlen + 8 > bsize) return fail(NB_ERR_PARSE, "corrupt BGZF block in " + path);
+      if (avail < bsize) { if (!refill(bsize)) return fail(NB_ERR_PARSE, "corrupt BGZF block (runs past the end of the file) in " + path); continue; }
+      const size_t isize = cbuf[cpos + bsize - 4] | (cbuf[cpos + bsize - 3] << 8) | (cbuf[cpos + bsize - 2] << 16) | ((size_t)cbuf[cpos + bsize - 1] << 24);
       if (isize > 65536) return fail(NB_ERR_PARSE, "corrupt BGZF block (ISIZE beyond 64 KiB) in " + path);
-      blks.push_back({xend, bsize - (xend - p) - 8, utot, isize});
-      utot += isize; p += bsize;
+      blks.push_back({xend, bsize - (xend - cpos) - 8, utot, isize});
+      utot += isize; cpos += bsize;
+      if (utot >= target) break;
     }
-    if (!data.alloc(utot)) return fail(NB_ERR_IO, "out of memory inflating " + path);
-    std::atomic<size_t> next(0); std::atomic<int> bad(0);
+    // peek: is anything left after this window?
+    if (cend == cpos && !file_done) refill(65536);
+    eof = file_done && cend == cpos;
+    // grow `out` keeping its first `keep` bytes
+    if (out.size() < keep + utot) { RawBuf nb2; if (!nb2.alloc(keep + utot + (utot >> 3) + 64)) return fail(NB_ERR_IO, "out of memory inflating " + path); if (keep) memcpy(nb2.data(), out.data(), keep); std::swap(out.p, nb2.p); std::swap(out.n, nb2.n); }
+    std::atomic<size_t> next_blk(0); std::atomic<int> bad(0);
+    u8* dst = out.data() + keep; const u8* src = cbuf.data();
     auto work = [&]() {
-      for (;;) { size_t i = next.fetch_add(1); if (i >= blks.size()) break; const Blk& b = blks[i]; if (!b.ulen) continue;
+      for (;;) { size_t i = next_blk.fetch_add(1); if (i >= blks.size()) break; const Blk& b = blks[i]; if (!b.ulen) continue;
         z_stream zs; memset(&zs, 0, sizeof zs);
         if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; continue; }
-        zs.next_in = &file[b.off]; zs.avail_in = (uInt)b.clen; zs.next_out = &data[b.uoff]; zs.avail_out = (uInt)b.ulen;
+        zs.next_in = const_cast<u8*>(src + b.off); zs.avail_in = (uInt)b.clen; zs.next_out = dst + b.uoff; zs.avail_out = (uInt)b.ulen;
         int rc = inflate(&zs, Z_FINISH); if (rc != Z_STREAM_END || zs.total_out != b.ulen) bad = 1;
         inflateEnd(&zs); }
     };
-    std::vector<std::thread> th; for (int t = 1; t < std::max(1, threads); t++) th.emplace_back(work);
+    std::vector<std::thread> th; for (int t = 1; t < std::max(1, threads) && (size_t)t < blks.size(); t++) th.emplace_back(work);
     work(); for (auto& t : th) t.join();
-    file.release();
     if (bad) return fail(NB_ERR_PARSE, "BGZF inflate failed in " + path);
+    n_out = utot;
     return NB_OK;
   }
+  // whole file into `data` (tests and the whole-file fallback)
+  int load(const std::string& p, int threads) { int rc = open(p); if (rc) return rc; size_t n = 0; bool eof = false; rc = next(data, 0, SIZE_MAX, threads, n, eof); if (rc) return rc; data.n = n; return NB_OK; }
+ private:
+  // makes at least `want` unread bytes available when the file has them; false when nothing more could be read
+  bool refill(size_t want) {
+    if (file_done) return false;
+    // blocks already handed out in this window are still referenced by offset: compaction only happens between windows,
+    // so within a window the buffer only grows
+    size_t need = cend + std::max<size_t>(want, (size_t)8 << 20);
+    if (cbuf.size() < need) cbuf.resize(need + (need >> 2));
+    size_t got = fread(&cbuf[cend], 1, cbuf.size() - cend, f);
+    if (got == 0) { file_done = true; return false; }
+    cend += got;
+    return true;
+  }
+ public:
+  // between windows: drop the consumed compressed bytes
+  void compact() { if (cpos) { memmove(cbuf.data(), cbuf.data() + cpos, cend - cpos); cend -= cpos; cpos = 0; } }
 };
 
 struct Rec {   // one decoded BAM record (views into Bgzf::data stay valid for the run)
@@ -330,66 +367,146 @@ inline bool key_equal(const Rec& a, const Rec& b) {
   std::string x(a.umi, a.umi_len), y(b.umi, b.umi_len); x.append(a.cb, ca); y.append(b.cb, cb); return x == y;   // different split of the same concatenation
 }
 
-// The same stream and groups as collect_groups_serial, computed on `threads` threads.  The serial readers above define the
-// semantics; this restates them over whole runs: a SortedBamReader buffer is a maximal run of kept records with one UMI
-// (the last run of the file is the one that is not CB-sorted), buffers are independent, the stream ends at the first
-// buffer that is empty after pairing (next() returns None there), and UMIReader's groups are runs of equal keys.
-// Falls back to the serial readers when a kept record has an empty UMI string (their empty-string quirks apply then).
-int collect_groups(const Bgzf& z, bool force_paired, int threads, std::vector<Rec>& stream, std::vector<u64>& gstart) {
-  if (getenv("NB_BAM_SERIAL_GROUPING")) return collect_groups_serial(z, force_paired, threads, stream, gstart);
-  SortedReader rd(z, force_paired);
-  int rc = rd.skip_header(); if (rc) return rc;
-  rc = rd.prepare(threads); if (rc) return rc;
-  const std::vector<Rec>& all = rd.all;
-  // kept records, in file order
-  std::vector<u32> kept; kept.reserve(all.size());
-  if (all.size() >= 0xFFFFFFFFull) return collect_groups_serial(z, force_paired, threads, stream, gstart);
-  for (size_t i = 0; i < all.size(); i++) {
-    const Rec& r = all[i];
-    if (!r.is_paired() && force_paired) continue;
-    if (!r.cb) continue;
-    if (!r.umi) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
-    if (r.umi_len == 10 && !memcmp(r.umi, "AAAAAAAAAA", 10)) continue;
-    if (r.umi_len == 0) return collect_groups_serial(z, force_paired, threads, stream, gstart);
-    kept.push_back((u32)i);
-  }
-  stream.clear(); gstart.assign(1, 0);
-  if (kept.empty()) { gstart.push_back(0); return NB_OK; }   // the producer sends one (empty) group when there is nothing at all
-  std::vector<size_t> run;   // start of every UMI run in `kept`
-  for (size_t j = 0; j < kept.size(); j++) if (j == 0 || !same(all[kept[j]].umi, all[kept[j]].umi_len, all[kept[j - 1]].umi, all[kept[j - 1]].umi_len)) run.push_back(j);
-  const size_t nr = run.size(); run.push_back(kept.size());
-  const int T = std::max(1, std::min<int>(threads, (int)((nr + 63) / 64)));
-  std::vector<std::vector<Rec>> outs(T); std::vector<size_t> first_empty(T, (size_t)-1);
-  parallel_ranges(T, nr, [&](size_t ra, size_t rb, int) {
-    size_t t = 0; for (int k = 0; k < T; k++) if (nr * (size_t)k / T == ra) t = k;   // the slice parallel_ranges gave this thread
-    std::vector<Rec>& out = outs[t]; std::vector<Rec> buf, tmp;
-    for (size_t r = ra; r < rb; r++) {
-      buf.clear(); for (size_t j = run[r]; j < run[r + 1]; j++) buf.push_back(all[kept[j]]);
-      if (r + 1 != nr) std::stable_sort(buf.begin(), buf.end(), [](const Rec& a, const Rec& b) { return cmp_bytes(a.cb, a.cb_len, b.cb, b.cb_len) < 0; });   // the file's last buffer is not sorted (quirk kept)
-      if (!force_paired) { tmp.clear(); for (const Rec& x : buf) { Rec m = x; m.skip_align = 0; tmp.push_back(m); if (!x.is_paired()) { Rec d = x; d.skip_align = 1; tmp.push_back(d); } } buf.swap(tmp); }
-      size_t before = out.size(), i = 0;
-      while (i + 1 < buf.size()) {   // filter_paired_reads
-        if (same(buf[i].qname_ptr(), buf[i].qname_len(), buf[i + 1].qname_ptr(), buf[i + 1].qname_len())) {
-          if (buf[i].is_first()) { out.push_back(buf[i]); out.push_back(buf[i + 1]); } else { out.push_back(buf[i + 1]); out.push_back(buf[i]); }
-          i += 2;
-        } else i += 1;
-      }
-      if (out.size() == before) { first_empty[t] = r; return; }   // next() returns None on an empty buffer: the stream ends here
+// ------------------------------------------------------------------ windowed producer
+// The same stream and groups as collect_groups_serial, computed window by window on `threads` threads with bounded memory.
+// The serial readers above define the semantics; this restates them over whole runs: a SortedBamReader buffer is a maximal
+// run of kept records with one UMI (the last run of the FILE is the one that is not CB-sorted), buffers are independent,
+// the stream ends at the first buffer that is empty after pairing (next() returns None there), UMIReader's groups are runs
+// of equal keys, and the last group is never sent when a group was sent before.  A window that is not the file's last one
+// holds back its last complete non-empty run and everything behind it (a handful of records), so every group it emits is
+// complete and known not to be the last; the held-back bytes open the next window.
+// NEED_WHOLE: a kept record has an empty UMI string, or two different UMIs give the same UMI+CB concatenation across a
+// window boundary (both quirks of the serial readers that need the whole file): the caller restarts with one window.
+const int NEED_WHOLE = 1000;
+struct Window {
+  RawBuf data; size_t len = 0;                         // inflated bytes: carry-over of the previous window + this window's blocks
+  std::vector<Rec> all;                                // complete records, file order, keys scanned
+  std::vector<Rec> stream; std::vector<u64> gstart;    // what the producer sends: records and group boundaries
+  size_t carry_from = 0;                               // offset in data of the first held-back byte (== len: nothing held back)
+};
+struct GroupStreamer {
+  Bgzf z; bool force_paired = false; int threads = 1; size_t window_bytes = (size_t)256 << 20;
+  bool header_done = false, eof = false, ended = false; u64 groups_sent = 0, records_seen = 0; size_t peak_window = 0;
+  std::string last_umi, last_cb; bool have_last = false;     // key of the last record sent (cross-window coincidence check)
+  int open(const std::string& path, bool fp, int th, size_t wb) { force_paired = fp; threads = std::max(1, th); window_bytes = std::max<size_t>(wb, 1 << 16); return z.open(path); }
+  // fills w from the file position and the carry-over of `prev` (nullptr for the first window).  done: nothing was produced
+  // and nothing more will come.
+  int next(Window& w, const Window* prev, bool& done) {
+    done = false; w.all.clear(); w.stream.clear(); w.gstart.assign(1, 0); w.len = 0; w.carry_from = 0;
+    const bool has_carry = prev && prev->carry_from < prev->len;
+    if (ended || (eof && !has_carry)) { done = true; return NB_OK; }
+    if (has_carry) {
+      const size_t keep = prev->len - prev->carry_from;
+      if (w.data.size() < keep + 64) { if (!w.data.alloc(keep + window_bytes + (window_bytes >> 3) + 64)) return fail(NB_ERR_IO, "out of memory"); }
+      memcpy(w.data.data(), prev->data.data() + prev->carry_from, keep);
+      w.len = keep;
     }
-  });
-  size_t total = 0; for (int t = 0; t < T; t++) { total += outs[t].size(); if (first_empty[t] != (size_t)-1) break; }
-  stream.reserve(total);
-  for (int t = 0; t < T; t++) { stream.insert(stream.end(), outs[t].begin(), outs[t].end()); std::vector<Rec>().swap(outs[t]); if (first_empty[t] != (size_t)-1) break; }
-  if (stream.empty()) { gstart.push_back(0); return NB_OK; }
-  // groups: runs of equal (UMI + CB[..len-2]) over the stream
-  std::vector<char> head(stream.size(), 0);
-  parallel_ranges(threads, stream.size(), [&](size_t a, size_t b, int) { for (size_t j = a; j < b; j++) head[j] = (j == 0 || !key_equal(stream[j - 1], stream[j])) ? 1 : 0; });
-  gstart.clear();
-  for (size_t j = 0; j < stream.size(); j++) if (head[j]) gstart.push_back(j);
-  gstart.push_back(stream.size());
-  if (gstart.size() > 2) { stream.resize(gstart[gstart.size() - 2]); gstart.pop_back(); }   // the last group is never sent when a group was sent before
-  return NB_OK;
-}
+    size_t grow = window_bytes;
+    for (;;) {   // (repeats only when the window could not emit anything: one giant UMI run, or a header larger than the window)
+      if (!eof) { size_t n_out = 0; int rc = z.next(w.data, w.len, grow, threads, n_out, eof); if (rc) return rc; z.compact(); w.len += n_out; }
+      peak_window = std::max(peak_window, w.len);
+      size_t cur = 0;
+      if (!header_done) {
+        const RawBuf& d = w.data; bool ok = w.len >= 12;
+        if (ok && memcmp(d.data(), "BAM\1", 4)) return fail(NB_ERR_PARSE, "not a BAM file");
+        size_t p = 0;
+        if (ok) { u32 l_text; memcpy(&l_text, &d[4], 4); p = 8 + (size_t)l_text; ok = p + 4 <= w.len; }
+        if (ok) { u32 n_ref; memcpy(&n_ref, &d[p], 4); p += 4; for (u32 i = 0; i < n_ref && ok; i++) { if (p + 4 > w.len) { ok = false; break; } u32 l; memcpy(&l, &d[p], 4); p += 4 + (size_t)l + 4; } ok = ok && p <= w.len; }
+        if (!ok) { if (eof) return fail(NB_ERR_PARSE, w.len < 12 ? "not a BAM file" : "truncated BAM header"); grow *= 2; continue; }
+        cur = p;
+      }
+      // complete records of the window
+      w.all.clear();
+      const RawBuf& d = w.data;
+      while (cur + 4 <= w.len) {
+        u32 bs; memcpy(&bs, &d[cur], 4);
+        if (bs < 32) { if (!eof) return fail(NB_ERR_PARSE, "corrupt BAM record (block size below the fixed fields)"); break; }   // (trailing garbage at the very end is ignored, as before)
+        if (cur + 4 + bs > w.len) break;                                                        // cut by the window: carried over
+        Rec r; r.p = &d[cur + 4]; r.block = bs;
+        // l_read_name, n_cigar and l_seq come from the file: qname / cigar / 4-bit bases / quals must lie inside the record
+        if (32ull + r.l_read_name() + 4ull * r.n_cigar() + ((u64)r.l_seq() + 1) / 2 + (u64)r.l_seq() > bs) return fail(NB_ERR_PARSE, "corrupt BAM record (field lengths exceed its block size)");
+        w.all.push_back(r); cur += 4 + bs;
+      }
+      const size_t tail = cur;    // first byte that is not part of a complete record
+      std::vector<Rec>& all = w.all;
+      parallel_ranges(threads, all.size(), [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) all[i].scan_keys(); });
+      if (all.size() >= 0xFFFFFFFFull) return fail(NB_ERR_UNSUPPORTED, "more than 2^32 records in one window");
+      std::vector<u32> kept; kept.reserve(all.size());
+      for (size_t i = 0; i < all.size(); i++) {
+        const Rec& r = all[i];
+        if (!r.is_paired() && force_paired) continue;
+        if (!r.cb) continue;
+        if (!r.umi) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
+        if (r.umi_len == 10 && !memcmp(r.umi, "AAAAAAAAAA", 10)) continue;
+        if (r.umi_len == 0) return NEED_WHOLE;
+        kept.push_back((u32)i);
+      }
+      std::vector<size_t> run;   // start of every UMI run in `kept`
+      for (size_t j = 0; j < kept.size(); j++) if (j == 0 || !same(all[kept[j]].umi, all[kept[j]].umi_len, all[kept[j - 1]].umi, all[kept[j - 1]].umi_len)) run.push_back(j);
+      const size_t nr = run.size(); run.push_back(kept.size());
+      // one run -> the records the sorted reader hands on (CB sort unless it is the file's last run, dummy mates, pairing)
+      auto emit_run = [&](size_t r, std::vector<Rec>& out, std::vector<Rec>& buf, std::vector<Rec>& tmp) {
+        buf.clear(); for (size_t j = run[r]; j < run[r + 1]; j++) buf.push_back(all[kept[j]]);
+        if (!(eof && r + 1 == nr)) std::stable_sort(buf.begin(), buf.end(), [](const Rec& a, const Rec& b) { return cmp_bytes(a.cb, a.cb_len, b.cb, b.cb_len) < 0; });   // the file's last buffer is not sorted (quirk kept)
+        if (!force_paired) { tmp.clear(); for (const Rec& x : buf) { Rec m = x; m.skip_align = 0; tmp.push_back(m); if (!x.is_paired()) { Rec d2 = x; d2.skip_align = 1; tmp.push_back(d2); } } buf.swap(tmp); }
+        size_t before = out.size(), i = 0;
+        while (i + 1 < buf.size()) {   // filter_paired_reads
+          if (same(buf[i].qname_ptr(), buf[i].qname_len(), buf[i + 1].qname_ptr(), buf[i + 1].qname_len())) {
+            if (buf[i].is_first()) { out.push_back(buf[i]); out.push_back(buf[i + 1]); } else { out.push_back(buf[i + 1]); out.push_back(buf[i]); }
+            i += 2;
+          } else i += 1;
+        }
+        return out.size() - before;
+      };
+      size_t R = nr;   // runs [0, R) are emitted by this window
+      if (!eof) {
+        // hold back from the last COMPLETE run (index <= nr - 2) that is non-empty after pairing: what precedes it is then
+        // known to be followed by another group
+        std::vector<Rec> o, b1, b2; size_t rstar = (size_t)-1;
+        for (size_t r = nr >= 2 ? nr - 2 : (size_t)-1; r != (size_t)-1; r--) { o.clear(); if (emit_run(r, o, b1, b2)) { rstar = r; break; } if (r == 0) break; }
+        if (rstar == (size_t)-1 || rstar == 0) {
+          // nothing can be emitted yet: one run spans the window (or nothing complete and non-empty precedes the last run) -> read more into the same window
+          grow = std::max(grow, w.len); continue;
+        }
+        R = rstar;
+        w.carry_from = (size_t)((all[kept[run[rstar]]].p - 4) - d.data());
+      } else w.carry_from = w.len;
+      (void)tail;
+      if (kept.empty() || R == 0) {
+        if (eof && groups_sent == 0) w.gstart.push_back(0);   // the producer sends one (empty) group when there is nothing at all
+        records_seen += all.size(); header_done = true;
+        done = w.gstart.size() < 2;
+        return NB_OK;
+      }
+      const int T = std::max(1, std::min<int>(threads, (int)((R + 63) / 64)));
+      std::vector<std::vector<Rec>> outs(T); std::vector<size_t> first_empty(T, (size_t)-1);
+      parallel_ranges(T, R, [&](size_t ra, size_t rb, int) {
+        size_t t = 0; for (int k = 0; k < T; k++) if (R * (size_t)k / T == ra) t = k;   // the slice parallel_ranges gave this thread
+        std::vector<Rec>& out = outs[t]; std::vector<Rec> buf, tmp;
+        for (size_t r = ra; r < rb; r++) if (!emit_run(r, out, buf, tmp)) { first_empty[t] = r; return; }   // next() returns None on an empty buffer: the stream ends here
+      });
+      std::vector<Rec>& stream = w.stream; bool cut = false;
+      size_t total = 0; for (int t = 0; t < T; t++) { total += outs[t].size(); if (first_empty[t] != (size_t)-1) break; }
+      stream.reserve(total);
+      for (int t = 0; t < T; t++) { stream.insert(stream.end(), outs[t].begin(), outs[t].end()); std::vector<Rec>().swap(outs[t]); if (first_empty[t] != (size_t)-1) { cut = true; break; } }
+      if (cut) { ended = true; w.carry_from = w.len; }   // the reference's reader stops for good at an empty buffer
+      const bool final = eof || ended;
+      header_done = true; records_seen += all.size();
+      std::vector<u64>& gstart = w.gstart; gstart.clear();
+      if (stream.empty()) { gstart.assign(1, 0); if (final && groups_sent == 0) gstart.push_back(0); done = gstart.size() < 2; return NB_OK; }
+      // groups: runs of equal (UMI + CB[..len-2]) over the stream
+      if (have_last) { Rec lr; lr.umi = last_umi.data(); lr.umi_len = (u32)last_umi.size(); lr.cb = last_cb.data(); lr.cb_len = (u32)last_cb.size(); if (key_equal(lr, stream[0])) return NEED_WHOLE; }
+      std::vector<char> head(stream.size(), 0);
+      parallel_ranges(threads, stream.size(), [&](size_t a, size_t b, int) { for (size_t j = a; j < b; j++) head[j] = (j == 0 || !key_equal(stream[j - 1], stream[j])) ? 1 : 0; });
+      for (size_t j = 0; j < stream.size(); j++) if (head[j]) gstart.push_back(j);
+      gstart.push_back(stream.size());
+      if (final && groups_sent + (gstart.size() - 1) >= 2) { stream.resize(gstart[gstart.size() - 2]); gstart.pop_back(); }   // the last group is never sent when a group was sent before
+      groups_sent += gstart.size() - 1;
+      if (!stream.empty()) { const Rec& l = stream.back(); last_umi.assign(l.umi, l.umi_len); last_cb.assign(l.cb ? l.cb : "", l.cb_len); have_last = true; }
+      return NB_OK;
+    }
+  }
+};
 
 // clipped length / start of a record's sequence (strip_nonbio_regions, src/parse/bam.rs:258-268)
 inline void clip_of(const Rec& r, size_t& a, size_t& b) { size_t n = r.l_seq(); a = 0; b = n; if (n == 124) { if (r.is_reverse()) b = n - CLIP_LENGTH; else a = CLIP_LENGTH; } }
@@ -476,35 +593,34 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
   for (u32 i = 0; i < n_refs && rc == NB_OK; i++) {
     rc = nb_library_load_json(reference_json[i], strand_filter, &libs[i]);
     if (rc == NB_OK && !trims.empty()) { nb_config c; nb_library_get_config(libs[i], &c); c.trim_target_length = trims[i].first; c.trim_strictness = trims[i].second; rc = nb_library_set_config(libs[i], &c); }
-    if (rc == NB_OK) rc = nb_index_build(libs[i], threads, &idx[i]);
+    if (rc == NB_OK) rc = nb_index_build_gpu(libs[i], device, threads, &idx[i]);   // K5: the CUDA builder (same artefact as the host builder)
     if (rc == NB_OK) rc = nb_ctx_create(idx[i], libs[i], device, nullptr, &ctx[i]);
     if (rc == NB_OK) rc = nb_ctx_set_option(ctx[i], "agg_slots", 1u << 23);   // a batch of 2^20 pairs can hold that many one-pair scopes, each with its own (scope, callset) row: stay under half full
     if (rc == NB_OK) { outs[i] = fopen(output_paths[i], "wb"); if (!outs[i]) rc = fail(NB_ERR_IO, std::string("could not open output ") + output_paths[i]); }
   }
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_load = 0, t_group = 0, t_fill = 0, t_gpu = 0, t_rows = 0, t_align = 0, t_final = 0, t0 = now(); const double t_start = t0;   // NB_BAM_STATS=1 prints the phase times
-  Bgzf z; std::vector<Rec> stream; std::vector<u64> gstart;
-  if (rc == NB_OK) rc = z.load(input_file, threads);
-  t_load = now() - t0; t0 = now();
-  if (rc == NB_OK) rc = collect_groups(z, force_bam_paired != 0, threads, stream, gstart);
-  t_group = now() - t0;
+  // window size of the streaming producer: NB_BAM_WINDOW_MB (inflated bytes per window; tests use small ones), default 256 MB
+  size_t window_bytes = (size_t)256 << 20;
+  if (const char* e = getenv("NB_BAM_WINDOW_KB")) window_bytes = (size_t)strtoull(e, nullptr, 10) << 10;
+  else if (const char* e2 = getenv("NB_BAM_WINDOW_MB")) window_bytes = (size_t)strtoull(e2, nullptr, 10) << 20;
   if (rc != NB_OK) { cleanup(); return rc; }
-  const size_t n_groups = gstart.size() - 1;
   const size_t BATCH_PAIRS = 1u << 20;
   const int GZ_LEVEL = 4;
   static const char* T16 = "=ACMGRSVTWYHKDBN";
   // Three stages run concurrently on consecutive batches: (F) the host threads fill batch k+1 into pinned buffers,
   // (D) the device aligns batch k and its counts are finalized, (R) the host threads format + gzip the rows of batch k-1.
   struct Pinned { u8* p = nullptr; size_t cap = 0; int ensure(size_t n) { if (n <= cap) return NB_OK; nb_host_free(p); cap = n + n / 4 + 4096; p = (u8*)nb_host_alloc(cap); if (!p) { cap = 0; return fail(NB_ERR_CUDA, "pinned host allocation failed"); } return NB_OK; } ~Pinned() { nb_host_free(p); } };
-  struct BatchIn { size_t g0 = 0, g1 = 0, np = 0; u32 maxlen = 1; std::vector<u64> pair0, o1, o2; std::vector<u8> f1, f2; std::vector<u32> scope; Pinned r1, r2, q1, q2; };
+  struct BatchIn { const std::vector<Rec>* stream = nullptr; const std::vector<u64>* gstart = nullptr; size_t g0 = 0, g1 = 0, np = 0; u32 maxlen = 1; std::vector<u64> pair0, o1, o2; std::vector<u8> f1, f2; std::vector<u32> scope; Pinned r1, r2, q1, q2; };
   struct BatchOut { std::vector<nb_read_result> rres; std::vector<nb_pair_result> pres; std::vector<u64> row_begin, callset_off; std::vector<u32> row_callset, callset_items, slot_to_callset; std::vector<i64> row_count; };
   BatchIn bin[3]; BatchOut bout[2];
-  std::vector<std::pair<size_t, size_t>> batches;
-  for (size_t g0 = 0; g0 < n_groups;) { size_t g1 = g0, pairs = 0; while (g1 < n_groups && pairs < BATCH_PAIRS) { pairs += (gstart[g1 + 1] - gstart[g1]) / 2; g1++; } batches.push_back({g0, g1}); g0 = g1; }
+  // the window being processed (its records and groups): set by the window loop below, read by the three stages
+  const std::vector<Rec>* cur_stream = nullptr; const std::vector<u64>* cur_gstart = nullptr;
   std::atomic<u64> ns_fill(0), ns_rows(0);
   // ---- (F) batch arrays: even record = sequence slot, odd = mate slot (src/process/bam.rs:257-292)
   auto fill = [&](BatchIn& B, size_t g0, size_t g1) -> int {
     double tb = now();
+    B.stream = cur_stream; B.gstart = cur_gstart; const std::vector<Rec>& stream = *B.stream; const std::vector<u64>& gstart = *B.gstart;
     B.g0 = g0; B.g1 = g1; const size_t ng = g1 - g0;
     B.pair0.assign(ng + 1, 0);
     for (size_t g = 0; g < ng; g++) B.pair0[g + 1] = B.pair0[g] + (gstart[g0 + g + 1] - gstart[g0 + g]) / 2;
@@ -566,6 +682,7 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
   auto rows = [&](const BatchIn& B, u32 li, const BatchOut& O) -> int {
     if (!B.np) return NB_OK;
     double tb = now();
+    const std::vector<Rec>& stream = *B.stream; const std::vector<u64>& gstart = *B.gstart;
     const size_t ng = B.g1 - B.g0, np = B.np, g0 = B.g0;
     const std::vector<u64>& pair0 = B.pair0; const std::vector<u64>& row_begin = O.row_begin;
     const int parts = std::max(1, std::min<int>(threads, (int)((np + 4095) / 4096)));
@@ -613,26 +730,72 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
     ns_rows += (u64)((now() - tb) * 1e9);
     return NB_OK;
   };
-  {
-    // pipeline items = (batch, library) in order; batch inputs rotate over three buffers, device results over two
-    const size_t nb_ = batches.size(); const size_t n_items = nb_ * n_refs;
-    std::future<int> fut_fill, fut_rows;
-    if (nb_) rc = fill(bin[0], batches[0].first, batches[0].second);
-    for (size_t it = 0; it < n_items && rc == NB_OK; it++) {
-      const size_t k = it / n_refs; const u32 li = (u32)(it % n_refs);
-      if (li == 0 && k + 1 < nb_) fut_fill = std::async(std::launch::async, fill, std::ref(bin[(k + 1) % 3]), batches[k + 1].first, batches[k + 1].second);
-      int e = on_device(bin[k % 3], li, bout[it % 2]);
-      if (fut_rows.valid()) { int er = fut_rows.get(); if (er && !e) e = er; }
-      if (!e) fut_rows = std::async(std::launch::async, rows, std::cref(bin[k % 3]), li, std::cref(bout[it % 2]));
-      if (li + 1 == n_refs && fut_fill.valid()) { int ef = fut_fill.get(); if (ef && !e) e = ef; }
-      rc = e;
+  // Errors of the async stages are raised on their own threads (nb_last_error is thread-local): the stage returns the
+  // message with its code and the joining thread re-raises it.
+  typedef std::pair<int, std::string> Res;
+  auto wrap = [](int e) { return Res(e, e ? std::string(nb_last_error()) : std::string()); };
+  auto join = [](std::future<Res>& f) { if (!f.valid()) return 0; Res r = f.get(); if (r.first) set_error(r.second); return r.first; };
+  std::future<Res> fut_fill, fut_rows, fut_win;
+  size_t it_global = 0, bin_next = 0, n_groups_total = 0, n_records_total = 0;
+  // one window = a run of whole groups: its batches go through the three stages; the next window is read, inflated and
+  // grouped on the host threads meanwhile
+  auto process_window = [&](const std::vector<Rec>& stream, const std::vector<u64>& gstart) -> int {
+    const size_t n_groups = gstart.size() - 1;
+    n_groups_total += n_groups; n_records_total += stream.size();
+    std::vector<std::pair<size_t, size_t>> batches;
+    for (size_t g0 = 0; g0 < n_groups;) { size_t g1 = g0, pairs = 0; while (g1 < n_groups && pairs < BATCH_PAIRS) { pairs += (gstart[g1 + 1] - gstart[g1]) / 2; g1++; } batches.push_back({g0, g1}); g0 = g1; }
+    cur_stream = &stream; cur_gstart = &gstart;
+    const size_t nb_ = batches.size();
+    int e = 0;
+    size_t slot = bin_next;
+    if (nb_) e = fill(bin[slot % 3], batches[0].first, batches[0].second);
+    for (size_t k = 0; k < nb_ && !e; k++) {
+      for (u32 li = 0; li < n_refs && !e; li++, it_global++) {
+        if (li == 0 && k + 1 < nb_) fut_fill = std::async(std::launch::async, [&, k, slot]() { return wrap(fill(bin[(slot + k + 1) % 3], batches[k + 1].first, batches[k + 1].second)); });
+        e = on_device(bin[(slot + k) % 3], li, bout[it_global % 2]);
+        { int er = join(fut_rows); if (er && !e) e = er; }
+        if (!e) { const BatchIn* bi = &bin[(slot + k) % 3]; const BatchOut* bo = &bout[it_global % 2]; fut_rows = std::async(std::launch::async, [&, bi, bo, li]() { return wrap(rows(*bi, li, *bo)); }); }
+        if (li + 1 == n_refs) { int ef = join(fut_fill); if (ef && !e) e = ef; }
+      }
     }
-    if (fut_fill.valid()) fut_fill.get();
-    if (fut_rows.valid()) { int er = fut_rows.get(); if (er && rc == NB_OK) rc = er; }
+    { int ef = join(fut_fill); if (ef && !e) e = ef; }
+    { int er = join(fut_rows); if (er && !e) e = er; }   // the rows stage reads this window's records: finish before the window is recycled
+    bin_next = (slot + nb_) % 3;
+    return e;
+  };
+  double t_prod = 0; size_t peak_window = 0; bool whole_file = false;
+  {
+    GroupStreamer gs; Window win[2];
+    rc = gs.open(input_file, force_bam_paired != 0, threads, window_bytes);
+    bool done = false; int cur = 0;
+    if (rc == NB_OK) { double tp = now(); rc = gs.next(win[0], nullptr, done); t_prod += now() - tp; }
+    while (rc == NB_OK && !done) {
+      // produce the next window while this one is processed (it only reads this window's carry-over bytes)
+      bool ndone = false;
+      fut_win = std::async(std::launch::async, [&, cur]() { double tp = now(); int e = gs.next(win[cur ^ 1], &win[cur], ndone); t_prod += now() - tp; return wrap(e); });
+      int e = process_window(win[cur].stream, win[cur].gstart);
+      Res rw = fut_win.get();
+      if (rw.first && rw.first != NEED_WHOLE) set_error(rw.second);
+      rc = e ? e : rw.first;
+      done = ndone; cur ^= 1;
+    }
+    peak_window = gs.peak_window;
+    if (rc == NEED_WHOLE) whole_file = true;
   }
+  if (whole_file) {
+    // the serial readers' empty-UMI / key-concatenation quirks need the whole file: start over with everything resident
+    rc = NB_OK;
+    for (u32 li = 0; li < n_refs && rc == NB_OK; li++) { if (ftruncate(fileno(outs[li]), 0) != 0 || fseek(outs[li], 0, SEEK_SET) != 0) rc = fail(NB_ERR_IO, "could not rewind the output"); first_write[li] = true; }
+    Bgzf z; std::vector<Rec> stream; std::vector<u64> gstart;
+    if (rc == NB_OK) rc = z.load(input_file, threads);
+    if (rc == NB_OK) rc = collect_groups_serial(z, force_bam_paired != 0, threads, stream, gstart);
+    n_groups_total = n_records_total = 0;
+    if (rc == NB_OK) rc = process_window(stream, gstart);
+  }
+  t_load = t_prod; t_group = 0;
   t_fill = ns_fill.load() * 1e-9; t_rows = ns_rows.load() * 1e-9;
   if (rc == NB_OK) for (u32 li = 0; li < n_refs; li++) if (first_write[li]) { std::string em; if (!gzip_member(std::string(), GZ_LEVEL, em) || fwrite(em.data(), 1, em.size(), outs[li]) != em.size()) rc = fail(NB_ERR_IO, "short write on the TSV"); }   // no row at all: an empty gzip stream, like the reference's untouched GzEncoder
-  if (getenv("NB_BAM_STATS")) fprintf(stderr, "nb_process_bam: %zu records in %zu groups; load+inflate %.2fs, grouping %.2fs, batch fill %.2fs, device align+finalize %.2fs (align %.2fs, finalize %.2fs), rows+gzip+write %.2fs (fill and rows overlap the device stage), total %.2fs\n", stream.size(), n_groups, t_load, t_group, t_fill, t_gpu, t_align, t_final, t_rows, now() - t_start);
+  if (getenv("NB_BAM_STATS")) fprintf(stderr, "nb_process_bam: %zu records in %zu groups%s; windows (read+inflate+group, overlapped) %.2fs, largest window %.0f MB, batch fill %.2fs, device align+finalize %.2fs (align %.2fs, finalize %.2fs), rows+gzip+write %.2fs (fill and rows overlap the device stage), total %.2fs\n", n_records_total, n_groups_total, whole_file ? " (whole-file fallback)" : "", t_load, peak_window / 1048576.0, t_fill, t_gpu, t_align, t_final, t_rows, now() - t_start);
   cleanup();
   return rc;
 }
@@ -641,19 +804,39 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
 // group index, clipped sequence, hex of the clipped (unreversed) quals, then the 38 metadata fields (QUAL as hex).
 extern "C" int nb_bam_dump_groups(const char* input_file, int force_bam_paired, int num_cores, const char* out_path) {
   if (!input_file || !out_path) return fail(NB_ERR_INVALID, "null argument");
-  Bgzf z; int rc = z.load(input_file, std::max(1, num_cores)); if (rc) return rc;
-  std::vector<Rec> stream; std::vector<u64> gstart;
-  rc = collect_groups(z, force_bam_paired != 0, std::max(1, num_cores), stream, gstart); if (rc) return rc;
+  size_t window_bytes = (size_t)256 << 20;
+  if (const char* e = getenv("NB_BAM_WINDOW_KB")) window_bytes = (size_t)strtoull(e, nullptr, 10) << 10;
+  else if (const char* e2 = getenv("NB_BAM_WINDOW_MB")) window_bytes = (size_t)strtoull(e2, nullptr, 10) << 20;
   FILE* f = fopen(out_path, "wb"); if (!f) return fail(NB_ERR_IO, std::string("could not open ") + out_path);
   auto hex = [](const std::string& s) { static const char* H = "0123456789abcdef"; std::string o; for (unsigned char c : s) { o += H[c >> 4]; o += H[c & 15]; } return o; };
-  for (size_t gi = 0; gi + 1 < gstart.size(); gi++) {
-    for (u64 k = gstart[gi]; k < gstart[gi + 1]; k++) {
-      ParsedRec r; parse_fields(stream[k], r);
-      fprintf(f, "%zu\t%s\t%s", gi, r.seq.c_str(), hex(r.qual).c_str());
-      for (int i = 0; i < 38; i++) fprintf(f, "\t%s", i == 1 ? hex(r.f[i]).c_str() : r.f[i].c_str());
-      fputc('\n', f);
+  size_t gi0 = 0;
+  auto dump = [&](const std::vector<Rec>& stream, const std::vector<u64>& gstart) {
+    for (size_t gi = 0; gi + 1 < gstart.size(); gi++) {
+      for (u64 k = gstart[gi]; k < gstart[gi + 1]; k++) {
+        ParsedRec r; parse_fields(stream[k], r);
+        fprintf(f, "%zu\t%s\t%s", gi0 + gi, r.seq.c_str(), hex(r.qual).c_str());
+        for (int i = 0; i < 38; i++) fprintf(f, "\t%s", i == 1 ? hex(r.f[i]).c_str() : r.f[i].c_str());
+        fputc('\n', f);
+      }
     }
+    gi0 += gstart.size() - 1;
+  };
+  int rc = NB_OK;
+  {
+    GroupStreamer gs; Window win[2]; bool done = false; int cur = 0;
+    rc = getenv("NB_BAM_SERIAL_GROUPING") ? NEED_WHOLE : gs.open(input_file, force_bam_paired != 0, std::max(1, num_cores), window_bytes);
+    if (rc == NB_OK) rc = gs.next(win[0], nullptr, done);
+    while (rc == NB_OK && !done) { dump(win[cur].stream, win[cur].gstart); rc = gs.next(win[cur ^ 1], &win[cur], done); cur ^= 1; }
   }
+  if (rc == NEED_WHOLE) {
+    if (ftruncate(fileno(f), 0) != 0 || fseek(f, 0, SEEK_SET) != 0) { fclose(f); return fail(NB_ERR_IO, "could not rewind the output"); }
+    gi0 = 0;
+    Bgzf z; rc = z.load(input_file, std::max(1, num_cores));
+    std::vector<Rec> stream; std::vector<u64> gstart;
+    if (rc == NB_OK) rc = collect_groups_serial(z, force_bam_paired != 0, std::max(1, num_cores), stream, gstart);
+    if (rc == NB_OK) dump(stream, gstart);
+  }
+  if (rc) { fclose(f); return rc; }
   fclose(f);
   return NB_OK;
 }

@@ -11,6 +11,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the functions are resolved from libnccl.so.2 at run time (nccl_api below)
+
 #include "host.hpp"
 #include "kernels.cuh"
 #include "khash.h"
@@ -74,7 +77,7 @@ struct nb_ctx {
   bool tables_ready = false;
   // staging + per-batch buffers
   // host batches: two staging sets filled on a copy stream so that the H2D of chunk i+1 overlaps the kernels of chunk i
-  struct Staging { DBuf a[2], off[2], q[2], f[2], scope, cell; cudaEvent_t copied = nullptr, consumed = nullptr; bool used = false; } stg[2];
+  struct Staging { DBuf a[2], off[2], q[2], f[2], len[2], scope, cell; cudaEvent_t copied = nullptr, consumed = nullptr; bool used = false; } stg[2];
   int stg_next = 0; cudaStream_t cstream = nullptr;
   DBuf d_pk, d_lenfull, d_lentrim, d_rres, d_pres, d_rout, d_seeded;
   // state
@@ -91,6 +94,9 @@ struct nb_ctx {
   DBuf d_rowwork, d_rowout, d_dense;
   // peer routing of the whole-run scope (nb_route_*): own inbox = inbox_world regions of inbox_cap KeyRec, one per source rank; d_routecur = this rank's fill cursors
   DBuf d_inbox, d_routecur; u64 inbox_cap = 0; u32 inbox_world = 0; bool route_on = false; nbk::Route route; std::vector<void*> ipc_opened;
+  // multi-GPU merge (nb_comm_*, nb_merge_*): the NCCL communicator this context merges over and its exchange blocks
+  ncclComm_t comm = nullptr; bool own_comm = false; u32 cworld = 1, crank = 0; u64 merge_cap = 4096;
+  DBuf d_blk1, d_all1, d_blk2, d_all2, d_densetab, d_densework; u64* h_hdr = nullptr;
 };
 
 static Tables make_tables(nb_ctx* c) {
@@ -246,11 +252,14 @@ void nb_ctx_free(nb_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DBuf* all[] = {&c->d_ptab, &c->d_bloom, &c->d_node, &c->d_walk, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
                  &c->d_ent, &c->d_ls, &c->d_qp, &c->d_mincov, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
-                 &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].scope, &c->stg[0].cell,
-                 &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded, &c->d_rowwork, &c->d_rowout, &c->d_dense};
+                 &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].len[0], &c->stg[0].len[1], &c->stg[0].scope, &c->stg[0].cell,
+                 &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].len[0], &c->stg[1].len[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded, &c->d_rowwork, &c->d_rowout, &c->d_dense};
   for (DBuf* b : all) b->release();
   for (void* q : c->ipc_opened) cudaIpcCloseMemHandle(q);
   c->ipc_opened.clear(); c->d_inbox.release(); c->d_routecur.release();
+  nb_comm_free(c);
+  c->d_blk1.release(); c->d_all1.release(); c->d_blk2.release(); c->d_all2.release(); c->d_densetab.release(); c->d_densework.release();
+  nb_host_free(c->h_hdr); c->h_hdr = nullptr;
   nb_host_free(c->h_rows); c->h_rows = nullptr;
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -304,6 +313,9 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   b.n_pairs = np; b.sides = sides; b.n_reads = (u32)nr; b.W = (max_len + 31) / 32 + 1; b.order_base = c->pairs_seen;
   if (nr * (u64)b.W >= 0xFFFFFFFFull) return fail(NB_ERR_INVALID, "max_batch_pairs too large for this read length: lower option max_batch_pairs");
   const u8* src_a[2] = {bt->r1, bt->r2}; const u64* src_off[2] = {bt->r1_off, bt->r2_off}; const u8* src_q[2] = {bt->q1, bt->q2}; const u8* src_f[2] = {bt->flags1, bt->flags2};
+  const u32* src_len[2] = {bt->r1_len, bt->r2_len};
+  const u32 bits = bt->encoding == NB_SEQ_2BIT ? 2u : bt->encoding == NB_SEQ_BAM4 ? 4u : 8u;   // per base in r1 / r2 (offsets count bases)
+  b.enc = (u32)bt->encoding;
   nb_ctx::Staging* S = nullptr; cudaStream_t cs = s;
   if (host) {
     S = &c->stg[c->stg_next]; c->stg_next ^= 1; cs = c->cstream;
@@ -321,21 +333,23 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   for (u32 sd = 0; sd < sides; sd++) {
     if (host) {
       u64 a0 = src_off[sd][p0], a1 = src_off[sd][p1];
-      if (sd == 1 && src_a[1] == src_a[0] && src_off[1] == src_off[0] && src_q[1] == src_q[0]) {
+      if (sd == 1 && src_a[1] == src_a[0] && src_off[1] == src_off[0] && src_q[1] == src_q[0] && src_len[1] == src_len[0]) {
         // the mate slot is the same buffer as the sequence slot (10x single-end records: the SKIP_ALIGN dummy is a clone of
         // the real record, sorted_bam_reader.rs:109-125): one copy serves both sides
-        b.a[1] = b.a[0]; b.off[1] = b.off[0]; b.q[1] = b.q[0];
+        b.a[1] = b.a[0]; b.off[1] = b.off[0]; b.q[1] = b.q[0]; b.len[1] = b.len[0];
         if (src_f[sd]) { CK(ens(S->f[sd], np)); CK(cudaMemcpyAsync(S->f[sd].p, src_f[sd] + p0, np, kind, cs)); b.flags[sd] = (const u8*)S->f[sd].p; }
         continue;
       }
-      CK(ens(S->a[sd], a1 - a0 + 64)); CK(ens(S->off[sd], (np + 1) * 8));
-      if (a1 > a0) CK(cudaMemcpyAsync(S->a[sd].p, src_a[sd] + a0, a1 - a0, kind, cs));
+      const u64 ab0 = a0 * bits / 8 & ~(u64)7, ab1 = (a1 * bits + 7) / 8;   // byte range of the bases (8-byte aligned start: the packed kernels load aligned words)
+      CK(ens(S->a[sd], ab1 - ab0 + 64)); CK(ens(S->off[sd], (np + 1) * 8));
+      if (ab1 > ab0) CK(cudaMemcpyAsync(S->a[sd].p, src_a[sd] + ab0, ab1 - ab0, kind, cs));
       CK(cudaMemcpyAsync(S->off[sd].p, src_off[sd] + p0, (np + 1) * 8, kind, cs));
-      b.a[sd] = (const u8*)S->a[sd].p - a0; b.off[sd] = (const u64*)S->off[sd].p;
+      b.a[sd] = (const u8*)S->a[sd].p - ab0; b.off[sd] = (const u64*)S->off[sd].p;
+      if (src_len[sd]) { CK(ens(S->len[sd], np * 4)); CK(cudaMemcpyAsync(S->len[sd].p, src_len[sd] + p0, np * 4, kind, cs)); b.len[sd] = (const u32*)S->len[sd].p; }
       if (src_q[sd]) { CK(ens(S->q[sd], a1 - a0 + 64)); if (a1 > a0) CK(cudaMemcpyAsync(S->q[sd].p, src_q[sd] + a0, a1 - a0, kind, cs)); b.q[sd] = (const u8*)S->q[sd].p - a0; }
       if (src_f[sd]) { CK(ens(S->f[sd], np)); CK(cudaMemcpyAsync(S->f[sd].p, src_f[sd] + p0, np, kind, cs)); b.flags[sd] = (const u8*)S->f[sd].p; }
     } else {
-      b.a[sd] = src_a[sd]; b.off[sd] = src_off[sd] + p0; b.q[sd] = src_q[sd]; b.flags[sd] = src_f[sd] ? src_f[sd] + p0 : nullptr;
+      b.a[sd] = src_a[sd]; b.off[sd] = src_off[sd] + p0; b.q[sd] = src_q[sd]; b.flags[sd] = src_f[sd] ? src_f[sd] + p0 : nullptr; b.len[sd] = src_len[sd] ? src_len[sd] + p0 : nullptr;
     }
   }
   if (bt->scope_id) {
@@ -402,6 +416,8 @@ int nb_align_batch(nb_ctx* c, const nb_batch* bt, nb_read_result* reads_out, nb_
   CK(cudaSetDevice(c->device));
   if (bt->n_pairs && (!bt->r1 || !bt->r1_off || (bt->r2 && !bt->r2_off))) return fail(NB_ERR_INVALID, "batch needs r1/r1_off (and r2_off with r2)");
   if (bt->location != NB_MEM_HOST && bt->location != NB_MEM_DEVICE) return fail(NB_ERR_INVALID, "batch location must be NB_MEM_HOST or NB_MEM_DEVICE");
+  if (bt->encoding != NB_SEQ_ASCII && bt->encoding != NB_SEQ_2BIT && bt->encoding != NB_SEQ_BAM4) return fail(NB_ERR_INVALID, "batch encoding must be NB_SEQ_ASCII, NB_SEQ_2BIT or NB_SEQ_BAM4");
+  if (bt->encoding == NB_SEQ_ASCII && (bt->r1_len || bt->r2_len)) return fail(NB_ERR_INVALID, "explicit read lengths (r1_len / r2_len) belong to the packed encodings");
   if (!c->lib->injective) return fail(NB_ERR_UNSUPPORTED, "reference library not representable on the device pair stage: " + c->lib->irregular_reason);
   if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
   if (c->folded) return fail(NB_ERR_INVALID, "counts were finalized; call nb_counts_reset before aligning more batches");
@@ -412,7 +428,10 @@ int nb_align_batch(nb_ctx* c, const nb_batch* bt, nb_read_result* reads_out, nb_
   u32 max_len = bt->max_read_len;
   if (!max_len) {
     if (bt->location != NB_MEM_HOST) return fail(NB_ERR_INVALID, "device-resident batches must state max_read_len");
-    for (u64 p = 0; p < bt->n_pairs; p++) { max_len = std::max<u32>(max_len, (u32)(bt->r1_off[p + 1] - bt->r1_off[p])); if (bt->r2) max_len = std::max<u32>(max_len, (u32)(bt->r2_off[p + 1] - bt->r2_off[p])); }
+    for (u64 p = 0; p < bt->n_pairs; p++) {
+      max_len = std::max<u32>(max_len, bt->r1_len ? bt->r1_len[p] : (u32)(bt->r1_off[p + 1] - bt->r1_off[p]));
+      if (bt->r2) max_len = std::max<u32>(max_len, bt->r2_len ? bt->r2_len[p] : (u32)(bt->r2_off[p + 1] - bt->r2_off[p]));
+    }
   }
   if (max_len > (u32)nbk::ENT_NMAX) return fail(NB_ERR_UNSUPPORTED, "reads longer than 1024 bases are not supported by the device path");
   if (max_len == 0) max_len = 1;
@@ -460,7 +479,12 @@ int nb_last_batch_ecs(nb_ctx* c, uint64_t* ec_off, uint32_t* ec_ids, uint64_t ec
   return NB_OK;
 }
 
-int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
+struct NcclApi;
+static const NcclApi* nccl_api();
+static int dense_allreduce(nb_ctx* c, void* dense, u64 n);
+// dense_cells > 0 (nb_merge_scoped): the (cell, callset) rows of all ranks are summed through a dense [cells x callsets]
+// table (all-reduce over NCCL) before they are read back; 0: this context's own rows
+static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells) {
   if (!c || !out) return fail(NB_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
   memset(out, 0, sizeof *out);
@@ -507,6 +531,38 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   if (fstats) ft[3] = fnow();
   // rows ordered by (cell, callset): remap to dense callset ids, radix sort and split on the device (kernels.cu), then one
   // copy into pinned memory — the table can hold millions of (cell, callset) rows
+  if (dense_cells) {
+    // ---- scoped multi-GPU merge: after the dictionary exchange every rank numbers the callsets alike (same sort over the
+    // same dictionary), so the per-cell tables add up element-wise: scatter -> all-reduce -> rows by a scan (already ordered)
+    const u64 ncs = std::max<u64>(1, slots.size()), nd = dense_cells * ncs;
+    if (nd >= (1ull << 31)) return fail(NB_ERR_UNSUPPORTED, "cells x callsets too large for the dense merge (2^31 entries)");
+    size_t tb = nbk::merge_scan_tmp_bytes(nd);
+    CK(c->d_densetab.ensure(nd * 8, s)); CK(c->d_densework.ensure(nd * 16 + tb + 16, s)); CK(c->d_dense.ensure(dense.size() * 4, s));
+    CK(cudaMemcpyAsync(c->d_dense.p, dense.data(), dense.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(c->d_densetab.p, 0, nd * 8, s));
+    nbk::launch_merge_dense_fill(t, (const u32*)c->d_dense.p, (unsigned long long*)c->d_densetab.p, ncs, dense_cells, s); c->all_launches++;
+    rc = dense_allreduce(c, c->d_densetab.p, nd); if (rc) return rc;
+    unsigned long long* d_flag = (unsigned long long*)c->d_densework.p; unsigned long long* d_prefix = d_flag + nd; void* d_tmp = d_prefix + nd;
+    u64 last2[2];   // row count = flag[nd-1] + prefix[nd-1]
+    nbk::launch_merge_dense_scan((const unsigned long long*)c->d_densetab.p, nd, d_flag, d_prefix, d_tmp, tb, s); c->all_launches += 2;
+    CK(cudaMemcpyAsync(&last2[0], d_flag + nd - 1, 8, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(&last2[1], d_prefix + nd - 1, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    n_agg = last2[0] + last2[1];
+    rc = check_device_errors(c); if (rc) return rc;
+    if (c->h_rows_cap < n_agg * 16) { nb_host_free(c->h_rows); c->h_rows_cap = n_agg * 16 + n_agg * 4 + 4096; c->h_rows = (u8*)nb_host_alloc(c->h_rows_cap); if (!c->h_rows) { c->h_rows_cap = 0; return fail(NB_ERR_CUDA, "pinned host allocation failed"); } }
+    c->n_rows_dev = n_agg;
+    if (n_agg) {
+      CK(c->d_rowout.ensure(n_agg * 16, s));
+      u32* d_scope = (u32*)c->d_rowout.p; u32* d_callset = d_scope + n_agg; i64* d_count = (i64*)((char*)c->d_rowout.p + 8 * n_agg);
+      nbk::launch_merge_dense_rows((const unsigned long long*)c->d_densetab.p, nd, ncs, d_prefix, d_scope, d_callset, d_count, s); c->all_launches++;
+      CK(cudaMemcpyAsync(c->h_rows, c->d_rowout.p, n_agg * 16, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+    }
+    out->n_rows = n_agg; out->row_scope = (u32*)c->h_rows; out->row_callset = (u32*)c->h_rows + n_agg; out->row_count = (i64*)(c->h_rows + 8 * n_agg);
+    out->n_callsets = slots.size(); out->callset_off = c->cs_off.data(); out->callset_items = c->cs_items.data();
+    out->n_pairs_seen = c->pairs_seen; out->n_unique_keys = h.n_keys; out->n_slots = c->cs_slots; out->slot_to_callset = c->slot_dense.data();
+    return NB_OK;
+  }
   if (n_agg >= (1ull << 31)) return fail(NB_ERR_UNSUPPORTED, "more than 2^31 (cell, callset) rows");
   if (c->h_rows_cap < n_agg * 16) { nb_host_free(c->h_rows); c->h_rows_cap = n_agg * 16 + n_agg * 4 + 4096; c->h_rows = (u8*)nb_host_alloc(c->h_rows_cap); if (!c->h_rows) { c->h_rows_cap = 0; return fail(NB_ERR_CUDA, "pinned host allocation failed"); } }
   u32* h_scope = (u32*)c->h_rows; u32* h_callset = h_scope + n_agg; i64* h_count = (i64*)(c->h_rows + 8 * n_agg);
@@ -528,6 +584,8 @@ int nb_counts_finalize(nb_ctx* c, nb_counts* out) {
   if (fstats) { ft[4] = fnow(); fprintf(stderr, "finalize: fold+counters %.3f ms, compact+D2H %.3f ms, callset sort %.3f ms, rows %.3f ms (%llu rows, %llu callsets, key slots %llu)\n", (ft[1] - ft[0]) * 1e3, (ft[2] - ft[1]) * 1e3, (ft[3] - ft[2]) * 1e3, (ft[4] - ft[3]) * 1e3, (unsigned long long)n_agg, (unsigned long long)n_cs, (unsigned long long)c->key_slots); }
   return NB_OK;
 }
+
+int nb_counts_finalize(nb_ctx* c, nb_counts* out) { return finalize_impl(c, out, 0); }
 
 int nb_counts_device_rows(nb_ctx* c, const void** row_scope, const void** row_callset, const void** row_count, uint64_t* n_rows) {
   if (!c || !row_scope || !row_callset || !row_count || !n_rows) return fail(NB_ERR_INVALID, "null argument");
@@ -778,6 +836,221 @@ int nb_route_import(nb_ctx* c, const uint64_t* counts, uint64_t* n_imported) {
   c->folded = false;
   if (n_imported) *n_imported = n;
   return NB_OK;   // device-side errors (table full, unknown callset) surface at nb_counts_finalize
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ multi-GPU merge over NCCL
+// SURVEY.md §8(b) `nb_counts_allreduce(nb_ctx*, ncclComm_t)`, §8(e).  The reference's only parallel driver is N-1 consumer
+// threads behind one producer (src/process/bam.rs:183-226); its multi-GPU counterpart is one context per GPU whose tables are
+// merged here, inside the library, on the context's stream: NCCL is called from C++ (libnccl.so.2 resolved at run time, so a
+// single-GPU host needs no NCCL), every import kernel reads its sizes from the gathered headers on the device, and the host
+// waits once per job (the header read-back that sizes the key table) before the usual finalize.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*CommCount)(const ncclComm_t, int*);
+  ncclResult_t (*CommUserRank)(const ncclComm_t, int*);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char* (*GetErrorString)(ncclResult_t);
+};
+static const NcclApi* nccl_api() {
+  static NcclApi api; static int state = 0;   // 0 untried, 1 ok, -1 unavailable
+  if (state == 0) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);   // the copy already in the process (e.g. PyTorch's) when there is one
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    bool ok = h != nullptr;
+    auto sym = [&](const char* n) { void* p = ok ? dlsym(h, n) : nullptr; if (!p) ok = false; return p; };
+    *(void**)&api.GetUniqueId = sym("ncclGetUniqueId"); *(void**)&api.CommInitRank = sym("ncclCommInitRank"); *(void**)&api.CommInitAll = sym("ncclCommInitAll");
+    *(void**)&api.CommDestroy = sym("ncclCommDestroy"); *(void**)&api.CommCount = sym("ncclCommCount"); *(void**)&api.CommUserRank = sym("ncclCommUserRank");
+    *(void**)&api.AllGather = sym("ncclAllGather"); *(void**)&api.AllReduce = sym("ncclAllReduce"); *(void**)&api.Send = sym("ncclSend"); *(void**)&api.Recv = sym("ncclRecv");
+    *(void**)&api.GroupStart = sym("ncclGroupStart"); *(void**)&api.GroupEnd = sym("ncclGroupEnd"); *(void**)&api.GetErrorString = sym("ncclGetErrorString");
+    state = ok ? 1 : -1;
+  }
+  return state == 1 ? &api : nullptr;
+}
+#define NCK(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(NB_ERR_CUDA, std::string(#x) + ": " + N->GetErrorString(r_)); } while (0)
+#define NEED_NCCL() const NcclApi* N = nccl_api(); if (!N) return fail(NB_ERR_CUDA, "libnccl.so.2 could not be loaded: the multi-GPU merge needs NCCL")
+
+static int dense_allreduce(nb_ctx* c, void* dense, u64 n) {
+  if (!c->comm || c->cworld < 2) return NB_OK;
+  NEED_NCCL();
+  NCK(N->AllReduce(dense, dense, n, ncclUint64, ncclSum, c->comm, c->stream));
+  return NB_OK;
+}
+
+extern "C" {
+
+int nb_comm_unique_id(void* id128_out) {
+  if (!id128_out) return fail(NB_ERR_INVALID, "null argument");
+  NEED_NCCL();
+  static_assert(sizeof(ncclUniqueId) == NB_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id; NCK(N->GetUniqueId(&id)); memcpy(id128_out, &id, sizeof id);
+  return NB_OK;
+}
+static int comm_adopt(nb_ctx* c, ncclComm_t comm, bool own) {
+  NEED_NCCL();
+  int w = 0, r = 0; NCK(N->CommCount(comm, &w)); NCK(N->CommUserRank(comm, &r));
+  if (w < 1 || w > nbk::ROUTE_MAX) return fail(NB_ERR_UNSUPPORTED, "communicators of 1..16 ranks are supported");
+  c->comm = comm; c->own_comm = own; c->cworld = (u32)w; c->crank = (u32)r;
+  if (!c->h_hdr) { c->h_hdr = (u64*)nb_host_alloc(8 * (size_t)nbk::ROUTE_MAX * (nbk::MERGE_HDR1_WORDS + 2)); if (!c->h_hdr) return fail(NB_ERR_CUDA, "pinned host allocation failed"); }
+  return NB_OK;
+}
+int nb_comm_init_rank(nb_ctx* c, const void* id128, uint32_t world, uint32_t rank) {
+  if (!c || !id128 || rank >= world) return fail(NB_ERR_INVALID, "bad argument");
+  if (c->comm) return fail(NB_ERR_INVALID, "the context already has a communicator (nb_comm_free first)");
+  NEED_NCCL();
+  CK(cudaSetDevice(c->device));
+  ncclUniqueId id; memcpy(&id, id128, sizeof id);
+  ncclComm_t comm = nullptr; NCK(N->CommInitRank(&comm, (int)world, id, (int)rank));
+  return comm_adopt(c, comm, true);
+}
+int nb_comm_attach(nb_ctx* c, void* nccl_comm) {
+  if (!c || !nccl_comm) return fail(NB_ERR_INVALID, "null argument");
+  if (c->comm) return fail(NB_ERR_INVALID, "the context already has a communicator (nb_comm_free first)");
+  return comm_adopt(c, (ncclComm_t)nccl_comm, false);
+}
+int nb_comm_init_all(nb_ctx* const* ctxs, uint32_t n) {
+  if (!ctxs || n < 1 || n > (uint32_t)nbk::ROUTE_MAX) return fail(NB_ERR_INVALID, "bad argument (1..16 contexts)");
+  NEED_NCCL();
+  int devs[nbk::ROUTE_MAX]; ncclComm_t comms[nbk::ROUTE_MAX];
+  for (u32 i = 0; i < n; i++) { if (!ctxs[i] || ctxs[i]->comm) return fail(NB_ERR_INVALID, "null context, or a context that already has a communicator"); devs[i] = ctxs[i]->device; }
+  for (u32 i = 0; i < n; i++) for (u32 j = 0; j < i; j++) if (devs[i] == devs[j]) return fail(NB_ERR_INVALID, "nb_comm_init_all needs one context per distinct GPU");
+  NCK(N->CommInitAll(comms, (int)n, devs));
+  for (u32 i = 0; i < n; i++) { int rc = comm_adopt(ctxs[i], comms[i], true); if (rc) return rc; }
+  return NB_OK;
+}
+int nb_comm_free(nb_ctx* c) {
+  if (!c) return fail(NB_ERR_INVALID, "null argument");
+  if (c->comm && c->own_comm) { const NcclApi* N = nccl_api(); cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); if (N) N->CommDestroy(c->comm); }
+  c->comm = nullptr; c->own_comm = false; c->cworld = 1; c->crank = 0;
+  return NB_OK;
+}
+int nb_comm_info(nb_ctx* c, uint32_t* world, uint32_t* rank) {
+  if (!c) return fail(NB_ERR_INVALID, "null argument");
+  if (world) *world = c->comm ? c->cworld : 1; if (rank) *rank = c->comm ? c->crank : 0;
+  return NB_OK;
+}
+
+// one process per GPU: inbox + IPC handles gathered over the communicator + peers' inboxes opened, in one call
+int nb_route_setup(nb_ctx* c, uint64_t records_per_peer, uint64_t pair_index_base) {
+  if (!c) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->comm || c->cworld < 2) return fail(NB_ERR_INVALID, "nb_route_setup needs a communicator of >= 2 ranks (nb_comm_init_rank)");
+  NEED_NCCL();
+  u8 mine[NB_ROUTE_HANDLE_BYTES];
+  int rc = nb_route_create(c, c->cworld, records_per_peer, mine); if (rc) return rc;
+  cudaStream_t s = c->stream;
+  CK(c->d_blk1.ensure(NB_ROUTE_HANDLE_BYTES, s)); CK(c->d_all1.ensure((size_t)NB_ROUTE_HANDLE_BYTES * c->cworld, s));
+  CK(cudaMemcpyAsync(c->d_blk1.p, mine, sizeof mine, cudaMemcpyHostToDevice, s));
+  NCK(N->AllGather(c->d_blk1.p, c->d_all1.p, sizeof mine, ncclChar, c->comm, s));
+  std::vector<u8> all((size_t)NB_ROUTE_HANDLE_BYTES * c->cworld);
+  CK(cudaMemcpyAsync(all.data(), c->d_all1.p, all.size(), cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+  // every rank must end up routed or none: agree on the outcome (1 = attached) with a tiny all-reduce
+  int ok = nb_route_attach_ipc(c, c->cworld, c->crank, all.data(), pair_index_base) == NB_OK;
+  std::string why = ok ? std::string() : std::string(nb_last_error());
+  unsigned long long flag = ok ? 1ULL : 0ULL;
+  CK(cudaMemcpyAsync(c->d_blk1.p, &flag, 8, cudaMemcpyHostToDevice, s));
+  NCK(N->AllReduce(c->d_blk1.p, c->d_blk1.p, 1, ncclUint64, ncclMin, c->comm, s));
+  CK(cudaMemcpyAsync(&flag, c->d_blk1.p, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+  if (!flag) { if (ok) nb_route_detach(c); return fail(NB_ERR_CUDA, ok ? "peer routing unavailable on another rank" : "peer routing unavailable: " + why); }
+  return NB_OK;
+}
+
+// dictionary exchange shared by both merges: all-gather of {k, sent[], k rows} blocks (capacity: a ratchet all ranks raise
+// alike), headers to the host (the one wait of the merge), peers' rows imported straight out of the gather buffer.
+// recv[r] = records rank r stored into this rank's inbox; ksum = sum of the ranks' dictionary sizes.
+static int merge_dictionaries(nb_ctx* c, const unsigned long long* d_sent, u64* recv, u64* ksum) {
+  NEED_NCCL();
+  cudaStream_t s = c->stream; const u32 W = c->cworld, cw = 4 + c->gcap; const size_t hdr_b = 8 * (size_t)nbk::MERGE_HDR1_WORDS;
+  for (;;) {
+    const u64 cap = c->merge_cap; const size_t blk_b = (hdr_b + cap * cw * 4 + 15) & ~(size_t)15;
+    CK(c->d_blk1.ensure(blk_b, s)); CK(c->d_all1.ensure(blk_b * W, s));
+    CK(cudaMemsetAsync(c->d_nout.p, 0, 16, s));
+    nbk::launch_compact(make_tables(c), nullptr, 0, (u32*)((char*)c->d_blk1.p + hdr_b), cap, (unsigned long long*)c->d_nout.p, s); c->all_launches += 2;
+    nbk::launch_merge_hdr1((u64*)c->d_blk1.p, (const unsigned long long*)c->d_nout.p + 1, d_sent, W, s); c->all_launches++;
+    NCK(N->AllGather(c->d_blk1.p, c->d_all1.p, blk_b, ncclChar, c->comm, s));
+    CK(cudaMemcpy2DAsync(c->h_hdr, hdr_b, c->d_all1.p, blk_b, hdr_b, W, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    u64 kmax = 0; *ksum = 0;
+    for (u32 r = 0; r < W; r++) { u64 k = c->h_hdr[r * nbk::MERGE_HDR1_WORDS]; kmax = std::max(kmax, k); *ksum += k; recv[r] = c->h_hdr[r * nbk::MERGE_HDR1_WORDS + 1 + c->crank]; }
+    if (kmax <= cap) { nbk::launch_merge_import_callsets(make_tables(c), c->d_all1.p, blk_b, cap, W, c->crank, s); c->all_launches++; return NB_OK; }
+    while (c->merge_cap < kmax) c->merge_cap *= 2;   // every rank sees the same sizes: every rank repeats with the same capacity
+  }
+}
+
+int nb_merge_whole_run(nb_ctx* c, nb_counts* out) {
+  if (!c || !out) return fail(NB_ERR_INVALID, "null argument");
+  if (!c->comm || c->cworld < 2) return nb_counts_finalize(c, out);
+  NEED_NCCL();
+  CK(cudaSetDevice(c->device));
+  if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
+  if (c->mode == 1) return fail(NB_ERR_INVALID, "nb_merge_whole_run applies to the whole-run scope (use nb_merge_scoped for scoped batches)");
+  if (c->folded) return fail(NB_ERR_INVALID, "counts were finalized; call nb_counts_reset first");
+  if (!c->route_on) return fail(NB_ERR_INVALID, "nb_merge_whole_run needs peer routing (nb_route_setup / nb_route_attach_ctx): key records travel inside k_pair");
+  c->mode = 0;
+  cudaStream_t s = c->stream; const u32 W = c->cworld;
+  static const bool mstats = getenv("NB_MERGE_STATS") != nullptr; double mt[8]; int mi = 0;   // tuning aid: phase times with a stream sync at every mark
+  auto mark = [&]() { if (!mstats) return; cudaStreamSynchronize(s); timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); mt[mi++] = ts.tv_sec + ts.tv_nsec * 1e-9; };
+  mark();
+  u64 recv[nbk::ROUTE_MAX], ksum = 0;
+  int rc = merge_dictionaries(c, (const unsigned long long*)c->d_routecur.p, recv, &ksum); if (rc) return rc;
+  mark();
+  // ---- this rank's inbox: the records the peers' k_pair stored while they aligned (the all-gather above is the barrier that
+  // says every peer's last batch is complete), merged with the same "later duplicate wins" rule
+  u64 n_in = 0, n_max = 0;
+  for (u32 r = 0; r < W; r++) if (r != c->crank) { if (recv[r] > c->inbox_cap) return fail(NB_ERR_OVERFLOW, "routing inbox region overflow: create the routes with more records_per_peer"); n_in += recv[r]; n_max = std::max(n_max, recv[r]); }
+  if (2 * (c->keys_upper + n_in) > c->key_slots) {
+    CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
+    nbk::launch_count_keys(make_tables(c), s); c->all_launches++;
+    Counters h; rc = check_device_errors(c, &h); if (rc) return rc;
+    CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
+    c->keys_upper = h.n_keys;
+    if (2 * (c->keys_upper + n_in) > c->key_slots) { rc = grow_keys(c, 2 * (c->keys_upper + n_in)); if (rc) return rc; }
+  }
+  c->keys_upper += n_in;
+  Tables t = make_tables(c);
+  const size_t blk_b = (8 * (size_t)nbk::MERGE_HDR1_WORDS + c->merge_cap * (4 + c->gcap) * 4 + 15) & ~(size_t)15;
+  nbk::launch_merge_import_inbox(t, c->d_inbox.p, c->inbox_cap, n_max, c->d_all1.p, blk_b, W, c->crank, s); c->all_launches++;
+  CK(cudaMemsetAsync(c->d_routecur.p, 0, nbk::ROUTE_MAX * 8, s));   // the next job's records start at the head of the regions
+  mark();
+  // ---- fold the keys this rank owns, then exchange {callset tag, count} rows: every rank ends with the job's counts
+  nbk::launch_fold(t, nullptr, 0, s); c->all_launches++; c->folded = true;
+  const u64 cap2 = std::max<u64>(1, std::min<u64>(ksum, c->cs_slots)), w2 = 2 + 2 * cap2;
+  CK(c->d_blk2.ensure(w2 * 8, s)); CK(c->d_all2.ensure(w2 * 8 * W, s));
+  CK(cudaMemsetAsync(c->d_blk2.p, 0, 16, s));
+  nbk::launch_merge_export_counts(t, (u64*)c->d_blk2.p, cap2, s); c->all_launches++;
+  NCK(N->AllGather(c->d_blk2.p, c->d_all2.p, w2 * 8, ncclChar, c->comm, s));
+  CK(cudaMemsetAsync(c->d_aggkey.p, 0, c->agg_slots * 8, s)); CK(cudaMemsetAsync(c->d_aggcnt.p, 0, c->agg_slots * 8, s));
+  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s)); CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_agg, 0, 8, s));
+  nbk::launch_merge_import_counts(t, (const u64*)c->d_all2.p, w2, cap2, W, s); c->all_launches++;
+  mark();
+  rc = finalize_impl(c, out, 0);   // (folded: no second fold) counters, dictionary order, rows — as on one GPU
+  mark();
+  if (mstats && c->crank == 0) fprintf(stderr, "nb_merge_whole_run: wait for the stream (alignment) %.3f ms | dictionaries all-gather + header read-back %.3f | inbox import (%llu records) %.3f | fold + counts all-gather + import %.3f | finalize %.3f\n",
+                                       0.0, (mt[1] - mt[0]) * 1e3, (unsigned long long)n_in, (mt[2] - mt[1]) * 1e3, (mt[3] - mt[2]) * 1e3, (mt[4] - mt[3]) * 1e3);
+  return rc;
+}
+
+int nb_merge_scoped(nb_ctx* c, uint64_t n_cells, nb_counts* out) {
+  if (!c || !out || n_cells == 0) return fail(NB_ERR_INVALID, "bad argument");
+  if (!c->comm || c->cworld < 2) return nb_counts_finalize(c, out);
+  CK(cudaSetDevice(c->device));
+  if (!c->tables_ready) { int rc = alloc_tables(c); if (rc) return rc; }
+  if (c->mode == 0) return fail(NB_ERR_INVALID, "nb_merge_scoped applies to scoped batches");
+  c->mode = 1;
+  u64 recv[nbk::ROUTE_MAX], ksum = 0;
+  int rc = merge_dictionaries(c, nullptr, recv, &ksum); if (rc) return rc;
+  // unique keys of the job = sum over ranks (scopes are disjoint): rides in the dense all-reduce's last element? no — one more tiny all-reduce
+  NEED_NCCL();
+  NCK(N->AllReduce(&((Counters*)c->d_ctr.p)->n_keys, &((Counters*)c->d_ctr.p)->n_keys, 1, ncclUint64, ncclSum, c->comm, c->stream));
+  return finalize_impl(c, out, n_cells);
 }
 
 }  // extern "C"

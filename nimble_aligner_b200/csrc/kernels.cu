@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 
@@ -102,13 +103,70 @@ __global__ void __launch_bounds__(256) k_pack(BatchDev b) {
   b.pk[(u64)ri * b.W + w] = word;
 }
 
+// ---- packed input encodings (nb_batch.encoding): the host ships 2 or 4 bits per base instead of 8 — the boundary the
+// reference's hot path really has (score::call takes 2-bit DnaStrings, src/score.rs:14-31; BAM stores 4-bit nibbles,
+// src/parse/bam.rs:186-189) and a quarter / half of the PCIe bytes.  off[] counts BASES of the packed stream; a read may
+// start at any base position.  One thread per (read, data word) as above.
+//   NB_SEQ_2BIT  base j of the stream = bits 2(j&3) of byte j>>2 (A0 C1 G2 T3): the device word is a 64-bit window at an
+//                arbitrary bit offset (two aligned 8-byte loads + funnel shift)
+//   NB_SEQ_BAM4  nibble j = byte j>>1, HIGH nibble first (the BAM layout), codes "=ACMGRSVTWYHKDBN": 1,2,4,8 are A,C,G,T,
+//                everything else becomes A exactly as DnaString::from_acgt_bytes treats the letters M, R, ..., N
+__device__ __forceinline__ u64 ld_al64(const u8* al, u32 i) { return __ldg((const unsigned long long*)al + i); }
+__device__ __forceinline__ u64 swap_nibbles(u64 x) { return ((x & 0x0F0F0F0F0F0F0F0FULL) << 4) | ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL); }
+// 16 nibbles (one-hot 1,2,4,8 = A,C,G,T; else A) -> 16 two-bit codes in the low 32 bits
+__device__ __forceinline__ u64 nib16_to_codes(u64 x) {
+  const u64 M = 0x1111111111111111ULL;
+  u64 m1 = x & M, m2 = (x >> 1) & M, m4 = (x >> 2) & M, m8 = (x >> 3) & M;
+  u64 sum = m1 + m2 + m4 + m8;                                   // per nibble 0..4, no carry between nibbles
+  u64 v = sum & ~(sum >> 1) & ~(sum >> 2) & M;                   // exactly one bit set
+  u64 c = ((m2 | m8) & v) | ((((m4 | m8) & v)) << 1);            // code bits at [0,1] of every nibble
+  c = (c | (c >> 2)) & 0x0F0F0F0F0F0F0F0FULL; c = (c | (c >> 4)) & 0x00FF00FF00FF00FFULL;
+  c = (c | (c >> 8)) & 0x0000FFFF0000FFFFULL; c = (c | (c >> 16)) & 0xFFFFFFFFULL;
+  return c;
+}
+template <int ENC>
+__global__ void __launch_bounds__(256) k_pack_enc(BatchDev b) {
+  u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 Wd = b.W - 1;
+  if (idx >= b.n_reads * Wd) return;
+  u32 ri = idx / Wd, w = idx - ri * Wd;
+  if (w == Wd - 1) b.pk[(u64)ri * b.W + Wd] = 0;
+  u32 side = b.sides == 2 ? (ri & 1) : 0; u64 p = b.sides == 2 ? (ri >> 1) : ri;
+  u64 o0 = b.off[side][p]; u32 len = b.len[side] ? b.len[side][p] : (u32)(b.off[side][p + 1] - o0);
+  bool rc = b.flags[side] != nullptr && (b.flags[side][p] & 2);
+  if (w == 0) { b.len_full[ri] = len; b.len_trim[ri] = len; }
+  u64 word = 0; u32 s = w * 32;
+  if (s < len) {
+    u32 cnt = min(32u, len - s);
+    u64 src = rc ? (o0 + len - s - cnt) : (o0 + s);        // first base of the 32-base source stretch
+    if (ENC == 1) {
+      const u8* addr = b.a[side] + (src >> 2);
+      const u8* al = (const u8*)((uintptr_t)addr & ~(uintptr_t)7);
+      u32 sh = (u32)((uintptr_t)addr & 7) * 8 + (u32)(src & 3) * 2;          // <= 62
+      u64 lo = ld_al64(al, 0), hi = (sh + 2 * cnt > 64) ? ld_al64(al, 1) : 0ULL;
+      word = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+    } else {
+      const u8* addr = b.a[side] + (src >> 1);
+      const u8* al = (const u8*)((uintptr_t)addr & ~(uintptr_t)7);
+      u32 sh = (u32)((uintptr_t)addr & 7) * 8 + (u32)(src & 1) * 4;          // <= 60
+      u32 need = sh + 4 * cnt;                                                 // bits wanted from al on: <= 188
+      u64 w0 = swap_nibbles(ld_al64(al, 0)), w1 = need > 64 ? swap_nibbles(ld_al64(al, 1)) : 0ULL, w2 = need > 128 ? swap_nibbles(ld_al64(al, 2)) : 0ULL;
+      u64 lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0, hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+      word = nib16_to_codes(lo) | (nib16_to_codes(hi) << 32);
+    }
+    if (cnt < 32) word &= (1ULL << (2 * cnt)) - 1;
+    if (rc) { word = rev2(word) >> (64 - 2 * cnt); word ^= cnt < 32 ? ((1ULL << (2 * cnt)) - 1) : ~0ULL; }
+  }
+  b.pk[(u64)ri * b.W + w] = word;
+}
+
 // ------------------------------------------------------------------------------------------------ K1 trim (maxinfo)
 __global__ void __launch_bounds__(256) k_trim(BatchDev b, Tables t) {
   u32 ri = blockIdx.x * blockDim.x + threadIdx.x;
   if (ri >= b.n_reads) return;
   u32 side = b.sides == 2 ? (ri & 1) : 0; u64 p = b.sides == 2 ? (ri >> 1) : ri;
   if (b.q[side] == nullptr) return;
-  u64 o0 = b.off[side][p]; u32 len = (u32)(b.off[side][p + 1] - o0);
+  u64 o0 = b.off[side][p]; u32 len = b.len_full[ri];        // written by k_pack (packed encodings may carry explicit lengths)
   bool rc = b.flags[side] != nullptr && (b.flags[side][p] & 2);
   const u8* q = b.q[side] + o0;
   i64 acc = 0; double max_score = -DBL_MAX; u32 pos = 0;
@@ -628,11 +686,133 @@ __global__ void __launch_bounds__(256) k_rows_split(const u64* keys, const i64* 
 }
 // ------------------------------------------------------------------------------------------------ launchers
 static inline unsigned blocks_for(u64 n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+// ------------------------------------------------------------------------------------------------ multi-GPU merge (nb_merge_*)
+// The exchange blocks of engine.cu's merge: block 1 = {k, sent[ROUTE_MAX]} + k dictionary rows, block 2 = {n, n_keys} + n
+// rows {callset tag, count} (whole-run) — every kernel reads its sizes from the gathered headers ON THE DEVICE, so the host
+// never has to wait between the collective and the import.
+constexpr u32 MERGE_HDR1 = 1 + ROUTE_MAX;   // u64 words
+__global__ void k_merge_hdr1(u64* hdr, const unsigned long long* n_rows, const unsigned long long* route_cursor, u32 world) {
+  u32 i = threadIdx.x;
+  if (i == 0) hdr[0] = *n_rows;
+  if (i < (u32)ROUTE_MAX) hdr[1 + i] = (route_cursor && i < world) ? route_cursor[i] : 0ULL;
+}
+__device__ __forceinline__ void callset_import_row(const Tables& t, const u32* r) {
+  u64 tag = (u64)r[2] | ((u64)r[3] << 32); u32 len = r[1];
+  u32 h = (u32)(tag >> 24) & t.cs_mask;
+  for (u32 probes = 0; probes <= t.cs_mask; probes++) {
+    unsigned long long old = atomicCAS((unsigned long long*)(t.cs_tag + h), 0ULL, (unsigned long long)tag);
+    if (old == 0ULL) { t.cs_len[h] = len; for (u32 i = 0; i < len; i++) t.cs_items[(u64)h * t.gcap + i] = r[4 + i]; atomicAdd(&t.ctr->n_callsets, 1ULL); return; }
+    if (old == tag) return;
+    h = (h + 1) & t.cs_mask;
+  }
+  atomicOr(&t.ctr->err, (unsigned)E_CS_FULL);
+}
+// peers' dictionary rows straight out of the all-gather buffer: grid (rows, world), rank `self` skipped
+__global__ void __launch_bounds__(256) k_merge_import_callsets(Tables t, const u8* all, u64 blk_bytes, u64 cap, u32 self) {
+  const u32 r = blockIdx.y; if (r == self) return;
+  const u8* blk = all + (u64)r * blk_bytes; const u64 k = min(*(const u64*)blk, cap);
+  const u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (idx >= k) return;
+  callset_import_row(t, (const u32*)(blk + 8 * MERGE_HDR1) + idx * (4 + t.gcap));
+}
+__device__ __forceinline__ void key_import_rec(const Tables& t, const KeyRec& r) {
+  u32 cs = CS_NONE;
+  if (r.tag) {
+    u32 h = (u32)(r.tag >> 24) & t.cs_mask; bool ok = false;
+    for (u32 probes = 0; probes <= t.cs_mask; probes++) { u64 tg = t.cs_tag[h]; if (tg == r.tag) { ok = true; break; } if (tg == 0) break; h = (h + 1) & t.cs_mask; }
+    if (!ok) { atomicOr(&t.ctr->err, (unsigned)E_CS_FULL); return; }
+    cs = h;
+  }
+  u64 slot = key_insert(t, r.k0, r.k1);
+  if (slot == ~0ULL) { atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL); return; }
+  atomicMax(t.kval + slot, (unsigned long long)(((r.order + 1) << 24) | cs));
+}
+// the records peers stored into this rank's inbox, region by region; counts come from the gathered headers (sent[self] of rank r)
+__global__ void __launch_bounds__(256) k_merge_import_inbox(Tables t, const KeyRec* inbox, u64 inbox_cap, const u8* all, u64 blk_bytes, u32 self) {
+  const u32 r = blockIdx.y; if (r == self) return;
+  const u64 n = min(((const u64*)(all + (u64)r * blk_bytes))[1 + self], inbox_cap);
+  for (u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x; idx < n; idx += (u64)gridDim.x * blockDim.x) {
+    const uint4* p = (const uint4*)(inbox + (u64)r * inbox_cap + idx);
+    uint4 a = __ldcg(p), b = __ldcg(p + 1);      // written by a peer GPU: read through L2, never a stale L1 line
+    KeyRec rec; rec.k0 = (u64)a.x | ((u64)a.y << 32); rec.k1 = (u64)a.z | ((u64)a.w << 32); rec.order = (u64)b.x | ((u64)b.y << 32); rec.tag = (u64)b.z | ((u64)b.w << 32);
+    key_import_rec(t, rec);
+  }
+}
+// this rank's folded counts as {callset tag, count} rows + header {n, unique keys}
+__global__ void __launch_bounds__(256) k_merge_export_counts(Tables t, u64* blk2, u64 cap2) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx == 0) blk2[1] = t.ctr->n_keys;
+  if (idx > t.agg_mask) return;
+  unsigned long long k = t.agg_key[idx];
+  if (!k) return;
+  unsigned long long at = atomicAdd((unsigned long long*)blk2, 1ULL);
+  if (at < cap2) { u32 slot = (u32)((k - 1) & 0xFFFFFF); blk2[2 + 2 * at] = t.cs_tag[slot]; blk2[3 + 2 * at] = t.agg_cnt[idx]; }
+}
+// every rank's rows (own included) summed into the (cleared) count table by callset slot: after this each rank holds the job's counts
+__global__ void __launch_bounds__(256) k_merge_import_counts(Tables t, const u64* all2, u64 blk2_words, u64 cap2) {
+  const u32 r = blockIdx.y; const u64* blk = all2 + (u64)r * blk2_words; const u64 n = min(blk[0], cap2);
+  const u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx == 0) atomicAdd(&t.ctr->n_keys, (unsigned long long)blk[1]);
+  if (idx >= n) return;
+  const u64 tag = blk[2 + 2 * idx];
+  u32 h = (u32)(tag >> 24) & t.cs_mask;
+  for (u32 probes = 0; probes <= t.cs_mask; probes++) { u64 tg = t.cs_tag[h]; if (tg == tag) { agg_add(t, (unsigned long long)h + 1ULL, blk[3 + 2 * idx]); return; } if (tg == 0) break; h = (h + 1) & t.cs_mask; }
+  atomicOr(&t.ctr->err, (unsigned)E_CS_FULL);
+}
+// scoped merge: (cell, callset slot) counts -> dense [cells x callsets] table by the job-wide callset numbering, and back
+__global__ void __launch_bounds__(256) k_merge_dense_fill(Tables t, const u32* dense_id, unsigned long long* dense, u64 n_cs, u64 n_cells) {
+  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (idx > t.agg_mask) return;
+  unsigned long long k = t.agg_key[idx];
+  if (!k) return;
+  k -= 1; u64 cell = k >> 24; u32 id = dense_id[(u32)(k & 0xFFFFFF)];
+  if (cell >= n_cells || id == NONE32) { atomicOr(&t.ctr->err, (unsigned)E_AGG_FULL); return; }
+  atomicAdd(dense + cell * n_cs + id, t.agg_cnt[idx]);
+}
+__global__ void __launch_bounds__(256) k_merge_dense_rows(const unsigned long long* dense, u64 n, u64 n_cs, const unsigned long long* prefix, u32* scope, u32* callset, i64* count) {
+  // `prefix` = exclusive scan of (dense != 0): rows come out ordered by (cell, callset) without a sort
+  u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long v = dense[i];
+  if (!v) return;
+  u64 at = prefix[i]; scope[at] = (u32)(i / n_cs); callset[at] = (u32)(i % n_cs); count[at] = (i64)v;
+}
+__global__ void __launch_bounds__(256) k_merge_nonzero(const unsigned long long* dense, u64 n, unsigned long long* flag) {
+  u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = dense[i] ? 1ULL : 0ULL;
+}
+void launch_merge_hdr1(u64* hdr, const unsigned long long* n_rows, const unsigned long long* route_cursor, u32 world, cudaStream_t s) { k_merge_hdr1<<<1, 32, 0, s>>>(hdr, n_rows, route_cursor, world); }
+void launch_merge_import_callsets(const Tables& t, const void* all, u64 blk_bytes, u64 cap, u32 world, u32 self, cudaStream_t s) {
+  if (cap && world > 1) k_merge_import_callsets<<<dim3(blocks_for(cap, 256), world), 256, 0, s>>>(t, (const u8*)all, blk_bytes, cap, self);
+}
+void launch_merge_import_inbox(const Tables& t, const void* inbox, u64 inbox_cap, u64 max_count, const void* all, u64 blk_bytes, u32 world, u32 self, cudaStream_t s) {
+  if (max_count && world > 1) k_merge_import_inbox<<<dim3(std::min<unsigned>(blocks_for(max_count, 256), 148 * 16), world), 256, 0, s>>>(t, (const KeyRec*)inbox, inbox_cap, (const u8*)all, blk_bytes, self);
+}
+void launch_merge_export_counts(const Tables& t, u64* blk2, u64 cap2, cudaStream_t s) { k_merge_export_counts<<<blocks_for(t.agg_mask + 1, 256), 256, 0, s>>>(t, blk2, cap2); }
+void launch_merge_import_counts(const Tables& t, const u64* all2, u64 blk2_words, u64 cap2, u32 world, cudaStream_t s) {
+  k_merge_import_counts<<<dim3(blocks_for(std::max<u64>(cap2, 1), 256), world), 256, 0, s>>>(t, all2, blk2_words, cap2);
+}
+void launch_merge_dense_fill(const Tables& t, const u32* dense_id, unsigned long long* dense, u64 n_cs, u64 n_cells, cudaStream_t s) { k_merge_dense_fill<<<blocks_for(t.agg_mask + 1, 256), 256, 0, s>>>(t, dense_id, dense, n_cs, n_cells); }
+size_t merge_scan_tmp_bytes(u64 n) { size_t tb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tb, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)n); return tb + 256; }
+// dense table -> rows (scope, callset, count) ordered by (cell, callset), in two steps so that the host can size the row
+// buffers: (1) non-zero flags + exclusive scan (row count = flag[n-1] + prefix[n-1]), (2) the rows
+void launch_merge_dense_scan(const unsigned long long* dense, u64 n, unsigned long long* flag, unsigned long long* prefix, void* tmp, size_t tmp_bytes, cudaStream_t s) {
+  if (!n) return;
+  k_merge_nonzero<<<blocks_for(n, 256), 256, 0, s>>>(dense, n, flag);
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const unsigned long long*)flag, prefix, (int)n, s);
+}
+void launch_merge_dense_rows(const unsigned long long* dense, u64 n, u64 n_cs, const unsigned long long* prefix, u32* scope, u32* callset, i64* count, cudaStream_t s) {
+  if (n) k_merge_dense_rows<<<blocks_for(n, 256), 256, 0, s>>>(dense, n, n_cs, prefix, scope, callset, count);
+}
 void launch_keys_count_owner(const Tables& t, u32 world, unsigned long long* counts, cudaStream_t s) { k_keys_count_owner<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, world, counts); }
 void launch_keys_scatter(const Tables& t, void* rec, unsigned long long* cursors, u64 order_base, u32 world, cudaStream_t s) { k_keys_scatter<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, (KeyRec*)rec, cursors, order_base, world); }
 void launch_callsets_import(const Tables& t, const u32* rows, u64 n, cudaStream_t s) { if (n) k_callsets_import<<<blocks_for(n, 256), 256, 0, s>>>(t, rows, n); }
 
-void launch_pack(const BatchDev& b, cudaStream_t s) { u64 n = (u64)b.n_reads * (b.W - 1); if (n) k_pack<<<blocks_for(n, 256), 256, 0, s>>>(b); }
+void launch_pack(const BatchDev& b, cudaStream_t s) {
+  u64 n = (u64)b.n_reads * (b.W - 1); if (!n) return;
+  if (b.enc == 1) k_pack_enc<1><<<blocks_for(n, 256), 256, 0, s>>>(b);
+  else if (b.enc == 2) k_pack_enc<2><<<blocks_for(n, 256), 256, 0, s>>>(b);
+  else k_pack<<<blocks_for(n, 256), 256, 0, s>>>(b);
+}
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_reads) k_trim<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, t); }
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s) {
   if (!b.n_reads) return;

@@ -70,6 +70,7 @@ struct PairRes { u32 callset; u8 triage, fr1, fr2, insertable; u64 key_lo, key_h
 struct BatchDev {
   u64 n_pairs; u32 sides; u32 n_reads; u32 W;             // W words per read incl. one zero pad word
   const u8* a[2]; const u64* off[2]; const u8* q[2]; const u8* flags[2]; const u32* scope; const u32* cell;
+  u32 enc; u32 pad_; const u32* len[2];                  // nb_batch.encoding (0 ASCII, 1 2-bit, 2 BAM 4-bit: off[] then counts bases) and optional explicit read lengths
   u64* pk; u32* len_full; u32* len_trim;                  // pk[ri * W + w] (read-major), ri = p*sides + side
   ReadRes* rres; PairRes* pres;
   uint4* seeded;                                         // k_seed -> k_walk: {read, seed position, node, offset} of every read that found a seed
@@ -120,5 +121,17 @@ void launch_keys_count_owner(const Tables& t, u32 world, unsigned long long* cou
 void launch_keys_scatter(const Tables& t, void* rec, unsigned long long* cursors, u64 order_base, u32 world, cudaStream_t s);
 void launch_callsets_import(const Tables& t, const u32* rows, u64 n, cudaStream_t s);
 void launch_keys_import(const Tables& t, const void* records, u64 n, cudaStream_t s);
+
+// multi-GPU merge (engine.cu nb_merge_*): exchange blocks whose sizes the kernels read from the gathered headers on the device
+constexpr u32 MERGE_HDR1_WORDS = 1 + ROUTE_MAX;
+void launch_merge_hdr1(u64* hdr, const unsigned long long* n_rows, const unsigned long long* route_cursor, u32 world, cudaStream_t s);
+void launch_merge_import_callsets(const Tables& t, const void* all, u64 blk_bytes, u64 cap, u32 world, u32 self, cudaStream_t s);
+void launch_merge_import_inbox(const Tables& t, const void* inbox, u64 inbox_cap, u64 max_count, const void* all, u64 blk_bytes, u32 world, u32 self, cudaStream_t s);
+void launch_merge_export_counts(const Tables& t, u64* blk2, u64 cap2, cudaStream_t s);
+void launch_merge_import_counts(const Tables& t, const u64* all2, u64 blk2_words, u64 cap2, u32 world, cudaStream_t s);
+void launch_merge_dense_fill(const Tables& t, const u32* dense_id, unsigned long long* dense, u64 n_cs, u64 n_cells, cudaStream_t s);
+size_t merge_scan_tmp_bytes(u64 n);
+void launch_merge_dense_scan(const unsigned long long* dense, u64 n, unsigned long long* flag, unsigned long long* prefix, void* tmp, size_t tmp_bytes, cudaStream_t s);
+void launch_merge_dense_rows(const unsigned long long* dense, u64 n, u64 n_cs, const unsigned long long* prefix, u32* scope, u32* callset, i64* count, cudaStream_t s);
 
 }  // namespace nbk

@@ -49,6 +49,17 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+def lib_comm(ctx, nb, torch, dist, rank, world):
+    """Gives the context its own NCCL communicator (nb_comm_init_rank): rank 0 creates the unique id through the library,
+    the process group that launched the job carries it to the other ranks.  After this the merges run inside the library
+    (nb_route_setup, nb_merge_whole_run, nb_merge_scoped); this module is only their caller."""
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.from_numpy(nb.comm_unique_id()))
+    dist.broadcast(uid, 0)
+    ctx.comm_init_rank(uid.cpu().numpy(), world, rank)
+
+
 def setup_routes(ctx, torch, dist, rank, world, device, pair_base, records_per_peer):
     """Peer routing (nb_route_*, include/nimble_b200.h): every rank creates its inbox, the CUDA IPC handles travel by
     all_gather, every rank opens its peers' inboxes.  Returns False — on every rank — when any rank could not (no NVLink

@@ -1,8 +1,8 @@
-# usage: VARIANTS="_w9 _w10" [PAIRS=4000000] [ARGS="--group-seeds 0"] bash scripts/run_variants.sh   (kernel tuning builds from scripts/build_variant.sh; "-" = the default build)
+# usage: VARIANTS="_w9 _w10" [PAIRS=4000000] [ARGS="..."] bash scripts/run_variants.sh   (kernel tuning builds from scripts/build_variant.sh; "-" = the default build)
 for v in ${VARIANTS:--}; do
   [ "$v" = "-" ] && v=""
-  echo "== variant ${v:-default} ${ARGS}"
-  NIMBLE_B200_SO=$PWD/nimble_aligner_b200/libnimble_b200$v.so timeout 300 python bench.py --pairs ${PAIRS:-4000000} --steps 3 --warmup 3 --no-cpu-baseline ${ARGS} 2>&1 | python -c "
+  echo "== variant ${v:-default} ${ARGS:-}"
+  NIMBLE_B200_SO=$PWD/nimble_aligner_b200/libnimble_b200$v.so timeout 300 python bench.py --pairs ${PAIRS:-4000000} --steps 3 --warmup 3 --no-cpu-baseline --blocks none ${ARGS:-} 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

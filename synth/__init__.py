@@ -37,6 +37,7 @@ def lib():
         L.synth_write_fastq.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.synth_write_bam.restype = C.c_uint64
         L.synth_write_bam.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int]
+        L.synth_encode_2bit.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -121,3 +122,11 @@ def write_fastq(path, r, off, mate=1, level=1):
     if not n:
         raise IOError("could not write %s" % path)
     return int(n)
+
+
+def encode_2bit(src, n_bases, dst=None, threads=8):
+    """ASCII bases -> NB_SEQ_2BIT byte stream (4 bases per byte, first base in the low bits; non-ACGT -> A)."""
+    if dst is None:
+        dst = np.zeros((n_bases + 3) // 4 + 64, dtype=np.uint8)
+    lib().synth_encode_2bit(src.ctypes.data, int(n_bases), dst.ctypes.data, threads)
+    return dst

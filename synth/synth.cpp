@@ -172,4 +172,13 @@ u64 synth_write_fastq(const char* path, u64 n, const char* r, const u64* off, in
   if (gz) gzclose(g); else fclose(f);
   return tot;
 }
+// ASCII bases -> NB_SEQ_2BIT stream (base j = bits 2(j&3) of byte j>>2; non-ACGT -> A), threaded: what a producer that holds
+// packed reads would hand over; here only so that the bench can ship the same reads packed.  dst needs (n + 3) / 4 bytes.
+void synth_encode_2bit(const u8* src, u64 n_bases, u8* dst, int threads) {
+  u8 lut[256]; memset(lut, 0, sizeof lut); lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
+  u64 nb4 = (n_bases + 3) / 4;
+  par(threads, nb4, [&](u64 a, u64 b) {
+    for (u64 i = a; i < b; i++) { u8 v = 0; for (int k = 0; k < 4; k++) { u64 j = 4 * i + k; if (j < n_bases) v |= (u8)(lut[src[j]] << (2 * k)); } dst[i] = v; }
+  });
+}
 }

@@ -102,3 +102,70 @@ def test_feeder_fails_loudly_on_damaged_bam(tmp_path):
         except nb.NbError:
             err += 1
     assert ok + err == 60 and err >= 5
+
+
+@pytest.mark.parametrize("force_paired", [False, True])
+@pytest.mark.parametrize("window_kb", [64, 300])
+def test_streaming_windows_equal_the_whole_file_readers(tmp_path, monkeypatch, force_paired, window_kb):
+    """The producer reads the BAM window by window with bounded memory (a window holds back its last complete run and what
+    follows it); whatever the window size, the groups must be those of the serial whole-file readers — including the
+    end-of-file quirks (last buffer unsorted, last group never sent)."""
+    L = synth.SynthLibrary(seed=7, n_fam=20, n_all=5)
+    bam = make_bam(str(tmp_path / "w.bam"), L, n_groups=3000, seed=11)
+    a, b = str(tmp_path / "win.tsv"), str(tmp_path / "ser.tsv")
+    monkeypatch.setenv("NB_BAM_WINDOW_KB", str(window_kb))
+    nb.bam_dump_groups(bam, a, force_bam_paired=force_paired, num_cores=4)
+    monkeypatch.delenv("NB_BAM_WINDOW_KB")
+    monkeypatch.setenv("NB_BAM_SERIAL_GROUPING", "1")
+    nb.bam_dump_groups(bam, b, force_bam_paired=force_paired, num_cores=4)
+    wa, se = open(a, "rb").read(), open(b, "rb").read()
+    assert wa == se and wa.count(b"\n") > (300 if force_paired else 3000)
+    assert os.path.getsize(bam) > 4 * window_kb * 1024 // 4      # several windows of compressed data
+
+
+def test_feeder_rejects_size_fields_that_point_outside_the_file(tmp_path):
+    """ADVICE r1: xlen / bsize / isize of a BGZF block and l_read_name / n_cigar / l_seq of a record are trusted nowhere;
+    an unterminated Z aux value at the end of a record is not a string."""
+    import struct
+    import zlib
+    L = synth.SynthLibrary(seed=1234, n_fam=20, n_all=5)
+    base = open(make_bam(str(tmp_path / "t.bam"), L, n_groups=30), "rb").read()
+    out = str(tmp_path / "g.tsv")
+
+    def fails(b):
+        path = str(tmp_path / "d.bam"); open(path, "wb").write(bytes(b))
+        with pytest.raises(nb.NbError):
+            nb.bam_dump_groups(path, out, num_cores=2)
+    b = bytearray(base); struct.pack_into("<H", b, 10, 0xFFFF); fails(b)            # xlen runs past the file
+    b = bytearray(base); struct.pack_into("<H", b, 16, 5); fails(b)                 # bsize smaller than its own header
+    bs = struct.unpack_from("<H", base, 16)[0] + 1
+    b = bytearray(base); struct.pack_into("<I", b, bs - 4, 1 << 20); fails(b)       # isize beyond 64 KiB
+    # record fields inside intact BGZF blocks
+    payload, i = b"", 0
+    while i < len(base):
+        xlen = struct.unpack_from("<H", base, i + 10)[0]; bsz = struct.unpack_from("<H", base, i + 16)[0] + 1
+        payload += zlib.decompress(base[i + 12 + xlen:i + bsz - 8], -15); i += bsz
+
+    def bgzf(data):
+        o = b""
+        for k in range(0, len(data), 20000):
+            c = data[k:k + 20000]; co = zlib.compressobj(6, zlib.DEFLATED, -15); cd = co.compress(c) + co.flush()
+            o += b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(cd) + 25) + cd + struct.pack("<II", zlib.crc32(c) & 0xFFFFFFFF, len(c))
+        return o + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    l_text = struct.unpack_from("<I", payload, 4)[0]; p = 8 + l_text; n_ref = struct.unpack_from("<I", payload, p)[0]; p += 4
+    for _ in range(n_ref):
+        p += 4 + struct.unpack_from("<I", payload, p)[0] + 4
+    rec = p + 4                                                                     # first record's fixed fields
+    q = bytearray(payload); struct.pack_into("<i", q, rec + 16, 1 << 28); fails(bgzf(bytes(q)))      # l_seq
+    q = bytearray(payload); struct.pack_into("<H", q, rec + 12, 0xFFFF); fails(bgzf(bytes(q)))      # n_cigar
+    # unterminated Z value as the last aux field of the first record: it is not a CB / UB string, nothing is read past the record
+    blk = struct.unpack_from("<I", payload, p)[0]
+    q = bytearray(payload)
+    end = p + 4 + blk
+    z = bytes(q[p + 4:end]).rfind(b"\0")                                            # the NUL of the last Z value
+    q[p + 4 + z] = ord("X")
+    path = str(tmp_path / "z.bam"); open(path, "wb").write(bgzf(bytes(q)))
+    try:
+        nb.bam_dump_groups(path, out, num_cores=2)                                  # groups (the field is ignored) or a loud error, never a crash
+    except nb.NbError:
+        pass

@@ -540,3 +540,59 @@ def test_hbm_resident_kernel_variant_on_a_small_library(c2_built, monkeypatch):
     w = ctx.work_counters()
     for k in ("probes", "nodes", "bases"):
         assert w[k] == ref["work"][k], (k, w[k], ref["work"][k])
+
+
+# ------------------------------------------------------------------ packed input encodings (nb_batch.encoding)
+@pytest.mark.parametrize("enc", ["2bit", "bam4"])
+@pytest.mark.parametrize("read_len", [150, 151, 45])
+def test_packed_encodings_equal_the_ascii_path(c2_built, enc, read_len):
+    """NB_SEQ_2BIT / NB_SEQ_BAM4 batches (offsets in bases, reads starting at any base position — odd lengths put reads at
+    odd nibble / quarter-byte positions) must give the ASCII path's per-read and per-pair records and counts, which the
+    oracle pins; reverse-complement flags and non-ACGT letters included."""
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, _ = built[""]
+    o.set_config(**ocfg)
+    n = 30_000
+    r1, o1, r2, o2 = synth.pairs(L, 700_000, n, read_len=read_len, paired=True)
+    rng = np.random.default_rng(5)
+    for r, off in ((r1, o1), (r2, o2)):      # sprinkle N / IUPAC letters: both packed paths must turn them into A like from_acgt_bytes
+        pos = rng.integers(0, int(off[-1]), size=300)
+        r[pos] = np.frombuffer(b"NRYKMn", dtype=np.uint8)[rng.integers(0, 6, size=300)]
+    flags1 = (rng.random(n) < 0.3).astype(np.uint8) * nb.FLAG_REVCOMP
+    flags2 = (rng.random(n) < 0.3).astype(np.uint8) * nb.FLAG_REVCOMP
+    ctx = nb.Context(ix, lib, max_batch_pairs=7_001)       # chunk boundaries at arbitrary base offsets too
+    ra, pa = ctx.align_batch(r1, o1, r2, o2, flags1=flags1, flags2=flags2, want_reads=True, want_pairs=True)
+    ca = ctx.counts()["rows"]
+    f = nb.encode_2bit if enc == "2bit" else nb.encode_bam4
+    code = nb.NB_SEQ_2BIT if enc == "2bit" else nb.NB_SEQ_BAM4
+    p1, p2 = f(r1, o1), f(r2, o2)
+    ctx.reset()
+    rb, pb = ctx.align_batch(p1, o1, p2, o2, flags1=flags1, flags2=flags2, want_reads=True, want_pairs=True, encoding=code)
+    cb = ctx.counts()["rows"]
+    assert ra.tobytes() == rb.tobytes() and pa.tobytes() == pb.tobytes() and ca == cb and (len(ca) > 100 or read_len < 50)   # (45-base reads never reach score_threshold 50)
+    if read_len == 150 and enc == "2bit":    # and the ASCII path itself is the oracle's (unflagged reads)
+        ctx.reset()
+        ctx.align_batch(p1, o1, p2, o2, encoding=code)
+        ref = o.run(r1, o1, r2, o2, threads=4, want_records=False)
+        assert [(cs, c) for _, cs, c in ctx.counts()["rows"]] == ref["scopes"][0]
+
+
+def test_packed_encoding_with_explicit_lengths_and_gaps(c2_built):
+    """r1_len / r2_len: reads that are not densely packed (every read starts on a 32-base boundary of the 2-bit stream, the
+    natural layout of a host that keeps one word-aligned DnaString per read)."""
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, _ = built[""]
+    n = 5_000
+    r1, o1, _, _ = synth.pairs(L, 50_000, n, paired=False)
+    lens = np.diff(o1).astype(np.uint32)
+    starts = np.concatenate([[0], np.cumsum((lens + 31) // 32 * 32)]).astype(np.uint64)
+    wide = np.zeros(int(starts[-1]) + 64, dtype=np.uint8) + ord("A")
+    for i in range(n):
+        wide[int(starts[i]):int(starts[i]) + int(lens[i])] = r1[int(o1[i]):int(o1[i + 1])]
+    packed = nb.encode_2bit(wide, starts)
+    ctx = nb.Context(ix, lib)
+    ra, _ = ctx.align_batch(r1, o1, want_reads=True)
+    ca = ctx.counts()["rows"]
+    ctx.reset()
+    rb, _ = ctx.align_batch(packed, starts, want_reads=True, encoding=nb.NB_SEQ_2BIT, r1_len=lens)
+    assert ra.tobytes() == rb.tobytes() and ctx.counts()["rows"] == ca
