@@ -297,6 +297,10 @@ int nb_measure_h2d(const int* devices, uint32_t n, uint64_t bytes, uint32_t reps
 int nb_write_fastq_tsv(const char* path, const nb_library* lib, const nb_counts* counts);
 int nb_process_fastq(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,
                      uint32_t n_refs, int strand_filter, int num_cores, int device);
+/* host-only: the records the FASTQ feeder (src/parse/fastq.rs:21-43) hands to the device, one line per record ("SEQ" or
+ * "SEQ1<TAB>SEQ2") — parity tests of the parallel plain-text parser against a sequential one.  chunk_bytes: bytes of file per
+ * parse task (0 = default 8 MiB); num_cores host threads are split over the input files. */
+int nb_fastq_dump(const char* const* input_files, uint32_t n_inputs, int num_cores, uint64_t chunk_bytes, const char* out_path);
 
 /* process::bam::process (src/process/bam.rs:45-243) behind the same library loop: BGZF/BAM decode on host threads,
  * UMIReader / SortedBamReader grouping (src/parse/bam.rs, src/parse/sorted_bam_reader.rs) with their quirks, one scoped

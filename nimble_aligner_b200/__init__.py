@@ -134,6 +134,7 @@ _SIGS = {
     "nb_measure_h2d": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_double)]),
     "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),
     "nb_bam_dump_groups": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
+    "nb_fastq_dump": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_char_p]),
     "nb_process_bam": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]),
     "nb_process_fastq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]),
 }
@@ -598,6 +599,11 @@ def process_fastq(input_files, reference_json_paths, output_paths, strand_filter
     """process::fastq::process behind main.rs's library loop (src/process/fastq.rs:7-30, src/bin/main.rs:95-147)."""
     _ck(lib().nb_process_fastq(_strs(input_files), len(input_files), _strs(reference_json_paths), _strs(output_paths),
                                len(reference_json_paths), CHEM[strand_filter], num_cores, device))
+
+
+def fastq_dump(input_files, out_path, num_cores=1, chunk_bytes=0):
+    """host-only: what the FASTQ feeder would hand to the device (one line per record, mates TAB-separated)."""
+    _ck(lib().nb_fastq_dump(_strs(input_files), len(input_files), num_cores, chunk_bytes, str(out_path).encode()))
 
 
 def process_bam(input_file, reference_json_paths, output_paths, strand_filter="unstranded", trim=None, num_cores=1, force_bam_paired=False, device=0):

@@ -362,7 +362,7 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
     }
   }
   if (host) { CK(cudaEventRecord(S->copied, cs)); CK(cudaStreamWaitEvent(s, S->copied, 0)); }
-  CK(c->d_pk.ensure((size_t)b.W * nr * 8, s)); CK(c->d_lenfull.ensure(nr * 4, s)); CK(c->d_lentrim.ensure(nr * 4, s));
+  CK(c->d_pk.ensure((size_t)b.W * nr * 8 + 16, s));   /* k_walk reads up to two words past a row */ CK(c->d_lenfull.ensure(nr * 4, s)); CK(c->d_lentrim.ensure(nr * 4, s));
   CK(c->d_rres.ensure(nr * sizeof(nbk::ReadRes), s)); CK(c->d_pres.ensure(np * sizeof(nbk::PairRes), s)); CK(c->d_seeded.ensure(nr * 16, s));
   if (c->mode == 1) { CK(c->d_pslot.ensure(np * 8, s)); CK(c->d_pres2.ensure(np * sizeof(nbk::PairRes), s)); b.pslot = (u64*)c->d_pslot.p; b.pres2 = (nbk::PairRes*)c->d_pres2.p; }
   b.pk = (u64*)c->d_pk.p; b.len_full = (u32*)c->d_lenfull.p; b.len_trim = (u32*)c->d_lentrim.p; b.rres = (nbk::ReadRes*)c->d_rres.p; b.pres = (nbk::PairRes*)c->d_pres.p; b.seeded = (uint4*)c->d_seeded.p;

@@ -1,12 +1,32 @@
 // fastq.cpp — FASTQ(.gz) feeder, FASTQ-mode TSV writer and the process::fastq::process driver.
 // Mirrors /root/reference/src/parse/fastq.rs:8-43 (niffler gz autodetect + bio fastq records -> DnaString::from_acgt_bytes),
 // src/utils.rs:27-51 (write_to_tsv: append, header iff empty, features TAB-joined) and src/process/fastq.rs:7-30.
+//
+// Two feeders behind one interface (a stream of parsed segments: bases concatenated in pinned memory + offsets):
+//   MapStream  plain FASTQ: the file is mapped and cut into byte chunks that T host threads parse at the same time.  A chunk
+//              starts at the first record start at or after its byte boundary, found by a local pattern test ('@' line whose
+//              next-but-one line starts with '+' and whose sequence and quality lines are equally long).  That guess is never
+//              trusted: the consumer accepts chunk c only if it began exactly where the parse of chunk c-1 ended, and parses
+//              it again from that position otherwise (multi-line records can defeat the pattern; the result is then still
+//              that of the sequential parse, only slower).
+//   GzStream   gzip input (sniffed by its magic bytes, like niffler): inflate is serial per file, one thread inflates and
+//              parses blocks in place.
+// The consumer hands min(records left in R1's segment, records left in R2's) pairs to nb_align_batch at a time, so the two
+// files never have to be cut at the same record numbers.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <time.h>
 #include <zlib.h>
 
-#include <cstdio>
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -18,7 +38,41 @@ using namespace nb;
 
 namespace {
 
-// One FASTQ(.gz) stream parsed in place: lines are views into the read buffer (a partial line at the end of the buffer
+std::atomic<bool> g_pageable{false};   // nb_fastq_dump (host-only parity tests of the feeder) runs without a CUDA device
+struct Pinned {
+  u8* p = nullptr; size_t cap = 0; bool pageable = false;
+  void drop() { if (pageable) free(p); else nb_host_free(p); p = nullptr; cap = 0; }
+  ~Pinned() { drop(); }
+  bool ensure(size_t n, size_t keep) {
+    if (n <= cap) return true;
+    const size_t nc = std::max(n, cap * 2 + (1 << 20)); const bool pg = g_pageable.load();
+    u8* q = (u8*)(pg ? malloc(nc) : nb_host_alloc(nc)); if (!q) return false;
+    if (keep) memcpy(q, p, keep);
+    drop(); p = q; cap = nc; pageable = pg; return true;
+  }
+};
+
+// records of one stretch of one input stream: bases concatenated in pinned memory, n + 1 offsets (pinned too: they are copied
+// to the device asynchronously)
+struct Segment {
+  Pinned seq, offb; u64 n = 0; u32 maxlen = 0; size_t used = 0;
+  int status = 1;               // 1 more may follow, 0 end of file, -1 malformed, -2 out of pinned memory
+  size_t start = 0, end = 0;    // MapStream: byte positions of the first record and behind the last one
+  u64* off() const { return (u64*)offb.p; }
+  void clear() { n = 0; maxlen = 0; used = 0; status = 1; }
+  bool push_off() { if (!offb.ensure((n + 2) * 8, (n + 1) * 8)) return false; off()[n + 1] = used; return true; }
+  bool begin() { clear(); if (!offb.ensure(1 << 16, 0)) return false; off()[0] = 0; return true; }
+};
+
+struct SegStream {
+  virtual ~SegStream() {}
+  virtual Segment* next() = 0;            // blocks; the caller gives every segment back with recycle()
+  virtual void recycle(Segment*) = 0;
+  virtual void finish() = 0;              // stops the threads (also mid-stream, after an error elsewhere)
+};
+
+// ------------------------------------------------------------------------------------------------ gzip: serial inflate + parse
+// One FASTQ.gz stream parsed in place: lines are views into the read buffer (a partial line at the end of the buffer
 // is moved to the front before the next gzread), no per-line strings.
 struct FastqReader {
   gzFile f = nullptr; std::string path; std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
@@ -38,42 +92,35 @@ struct FastqReader {
   }
 };
 
-struct Pinned {
-  u8* p = nullptr; size_t cap = 0;
-  ~Pinned() { nb_host_free(p); }
-  bool ensure(size_t n, size_t keep) { if (n <= cap) return true; size_t nc = std::max(n, cap * 2 + (1 << 20)); u8* q = (u8*)nb_host_alloc(nc); if (!q) return false; if (keep) memcpy(q, p, keep); nb_host_free(p); p = q; cap = nc; return true; }
-};
-
-// up to `want` records of one stream, bases concatenated in pinned memory
-struct Block { Pinned seq; std::vector<u64> off; u64 n = 0; u32 maxlen = 0; size_t used = 0; int status = 1; };   // status: 1 more may follow, 0 end of file, -1 malformed, -2 out of pinned memory
-
-// fills b from r; multi-line records are accepted like bio::io::fastq does
-void parse_block(FastqReader& r, Block& b, u64 want) {
-  b.n = 0; b.maxlen = 0; b.used = 0; b.status = 1; b.off.assign(1, 0);
+// fills g from r; multi-line records are accepted like bio::io::fastq does
+void parse_block(FastqReader& r, Segment& g, u64 want) {
+  if (!g.begin()) { g.status = -2; return; }
   const char* s; size_t n;
-  while (b.n < want) {
-    do { if (!r.line(s, n)) { b.status = 0; return; } } while (n == 0);
-    if (s[0] != '@') { b.status = -1; return; }
-    size_t start = b.used;
+  while (g.n < want) {
+    do { if (!r.line(s, n)) { g.status = 0; return; } } while (n == 0);
+    if (s[0] != '@') { g.status = -1; return; }
+    size_t start = g.used;
     for (;;) {
-      if (!r.line(s, n)) { b.status = -1; return; }
+      if (!r.line(s, n)) { g.status = -1; return; }
       if (n && s[0] == '+') break;
-      if (!b.seq.ensure(b.used + n + 64, b.used)) { b.status = -2; return; }
-      memcpy(b.seq.p + b.used, s, n); b.used += n;
+      if (!g.seq.ensure(g.used + n + 64, g.used)) { g.status = -2; return; }
+      memcpy(g.seq.p + g.used, s, n); g.used += n;
     }
-    size_t slen = b.used - start, qlen = 0;
-    while (qlen < slen) { if (!r.line(s, n)) { b.status = -1; return; } qlen += n; }
-    if (qlen != slen) { b.status = -1; return; }
-    b.off.push_back(b.used); b.maxlen = std::max<u32>(b.maxlen, (u32)slen); b.n++;
+    size_t slen = g.used - start, qlen = 0;
+    while (qlen < slen) { if (!r.line(s, n)) { g.status = -1; return; } qlen += n; }
+    if (qlen != slen) { g.status = -1; return; }
+    if (!g.push_off()) { g.status = -2; return; }
+    g.maxlen = std::max<u32>(g.maxlen, (u32)slen); g.n++;
   }
 }
 
-// a reader thread per input file: blocks circulate between `free` and `filled`
-struct Feeder {
-  FastqReader rd; Block blocks[3]; std::vector<Block*> free_q, filled_q; std::mutex m; std::condition_variable cv; bool stop = false; std::thread th; u64 want;
+struct GzStream : SegStream {
+  FastqReader rd; Segment blocks[4]; std::vector<Segment*> free_q; std::deque<Segment*> filled_q; std::mutex m; std::condition_variable cv; bool stop = false; std::thread th; u64 want;
+  GzStream(u64 w) : want(w) {}
+  bool open(const std::string& p) { if (!rd.open(p)) return false; for (auto& b : blocks) free_q.push_back(&b); th = std::thread([this] { run(); }); return true; }
   void run() {
     for (;;) {
-      Block* b;
+      Segment* b;
       { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return stop || !free_q.empty(); }); if (stop) return; b = free_q.back(); free_q.pop_back(); }
       parse_block(rd, *b, want);
       { std::lock_guard<std::mutex> lk(m); filled_q.push_back(b); }
@@ -81,11 +128,157 @@ struct Feeder {
       if (b->status != 1) return;
     }
   }
-  void start(u64 w) { want = w; for (auto& b : blocks) free_q.push_back(&b); th = std::thread([this] { run(); }); }
-  Block* pop() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return !filled_q.empty(); }); Block* b = filled_q.front(); filled_q.erase(filled_q.begin()); return b; }
-  void recycle(Block* b) { { std::lock_guard<std::mutex> lk(m); free_q.push_back(b); } cv.notify_all(); }
-  void finish() { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); }
+  Segment* next() override { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return !filled_q.empty(); }); Segment* b = filled_q.front(); filled_q.pop_front(); return b; }
+  void recycle(Segment* b) override { { std::lock_guard<std::mutex> lk(m); free_q.push_back(b); } cv.notify_all(); }
+  void finish() override { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); }
+  ~GzStream() override { finish(); }
 };
+
+// ------------------------------------------------------------------------------------------------ plain text: mapped file, parallel chunks
+inline size_t next_line(const char* d, size_t size, size_t pos) {   // start of the line after the one holding pos (size when there is none)
+  if (pos >= size) return size;
+  const char* nl = (const char*)memchr(d + pos, '\n', size - pos);
+  return nl ? (size_t)(nl - d) + 1 : size;
+}
+inline size_t line_len(const char* d, size_t size, size_t pos) {    // without terminator / '\r'
+  size_t e = next_line(d, size, pos); size_t n = e - pos;
+  if (n && d[pos + n - 1] == '\n') n--;
+  if (n && d[pos + n - 1] == '\r') n--;
+  return n;
+}
+inline size_t skip_blank(const char* d, size_t size, size_t pos) {  // parse_block's `while (n == 0)`: empty lines between records
+  while (pos < size) { if (d[pos] == '\n') pos++; else if (d[pos] == '\r' && pos + 1 < size && d[pos + 1] == '\n') pos += 2; else if (d[pos] == '\r' && pos + 1 == size) pos++; else break; }
+  return pos;
+}
+// records whose first byte lies in [pos, bound): same grammar and the same failures as parse_block.  Appends to g; returns
+// the position of the next record (blank lines skipped).
+size_t parse_range(const char* d, size_t size, size_t pos, size_t bound, Segment& g) {
+  pos = skip_blank(d, size, pos);
+  while (pos < bound && pos < size) {
+    if (d[pos] != '@') { g.status = -1; return pos; }
+    size_t p = next_line(d, size, pos);
+    const size_t start = g.used;
+    for (;;) {                                      // sequence lines up to the '+' line
+      if (p >= size) { g.status = -1; return pos; }
+      size_t e = next_line(d, size, p), n = e - p;
+      if (n && d[p + n - 1] == '\n') n--;
+      if (n && d[p + n - 1] == '\r') n--;
+      if (n && d[p] == '+') { p = e; break; }
+      if (!g.seq.ensure(g.used + n + 64, g.used)) { g.status = -2; return pos; }
+      memcpy(g.seq.p + g.used, d + p, n); g.used += n; p = e;
+    }
+    const size_t slen = g.used - start; size_t qlen = 0;
+    while (qlen < slen) {
+      if (p >= size) { g.status = -1; return pos; }
+      size_t e = next_line(d, size, p), n = e - p;
+      if (n && d[p + n - 1] == '\n') n--;
+      if (n && d[p + n - 1] == '\r') n--;
+      qlen += n; p = e;
+    }
+    if (qlen != slen) { g.status = -1; return pos; }
+    if (!g.push_off()) { g.status = -2; return pos; }
+    g.maxlen = std::max<u32>(g.maxlen, (u32)slen); g.n++;
+    pos = skip_blank(d, size, p);
+  }
+  return pos;
+}
+// first position >= from that LOOKS like a record start (see the file comment); size when there is none
+size_t guess_start(const char* d, size_t size, size_t from) {
+  if (from == 0) return skip_blank(d, size, 0);
+  size_t pos = next_line(d, size, from - 1);
+  for (int tries = 0; tries < 4096; tries++) {
+    pos = skip_blank(d, size, pos);
+    if (pos >= size) return size;
+    if (d[pos] == '@') {
+      size_t l1 = next_line(d, size, pos), l2 = next_line(d, size, l1);
+      if (l2 < size && d[l2] == '+') { size_t l3 = next_line(d, size, l2); if (line_len(d, size, l1) == line_len(d, size, l3)) return pos; }
+    }
+    pos = next_line(d, size, pos);
+  }
+  return pos;
+}
+
+struct MapStream : SegStream {
+  const char* d = nullptr; size_t size = 0; int fd = -1; size_t chunk = 8u << 20; u64 n_chunks = 0;
+  struct Slot { Segment seg; bool filled = false; };
+  std::vector<std::unique_ptr<Slot>> ring; std::vector<std::thread> th;
+  std::mutex m; std::condition_variable cv; bool stop = false;
+  std::atomic<u64> next_chunk{0}; u64 take = 0, released = 0;   // chunks handed to the consumer / given back by it
+  size_t expected = 0; Segment tail;                               // tail: the empty end-of-file segment of an empty input
+
+  bool open(const std::string& p, int threads, size_t chunk_bytes) {
+    fd = ::open(p.c_str(), O_RDONLY); if (fd < 0) return false;
+    struct stat st; if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); fd = -1; return false; }
+    size = (size_t)st.st_size; chunk = std::max<size_t>(chunk_bytes, 4096);
+    if (size) {
+      void* q = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (q == MAP_FAILED) { ::close(fd); fd = -1; return false; }
+      d = (const char*)q; madvise(q, size, MADV_SEQUENTIAL);
+    }
+    n_chunks = (size + chunk - 1) / chunk;
+    threads = (int)std::max<u64>(1, std::min<u64>((u64)std::max(threads, 1), n_chunks));
+    for (int i = 0; i < 2 * threads + 4; i++) ring.emplace_back(new Slot());
+    expected = skip_blank(d, size, 0);
+    for (int i = 0; i < threads && n_chunks; i++) th.emplace_back([this] { work(); });
+    return true;
+  }
+  void parse_chunk(u64 c, size_t from, Segment& g) {
+    const size_t bound = std::min(size, (size_t)(c + 1) * chunk);
+    if (!g.begin()) { g.status = -2; g.start = g.end = from; return; }
+    g.start = from;
+    if (from >= bound) { g.end = from; return; }
+    if (!g.seq.ensure((bound - from) / 2 + (1 << 16), 0)) { g.status = -2; g.end = from; return; }
+    g.end = parse_range(d, size, from, bound, g);
+  }
+  void work() {
+    const u64 R = ring.size();
+    for (;;) {
+      const u64 c = next_chunk.fetch_add(1);
+      if (c >= n_chunks) return;
+      Slot& s = *ring[c % R];
+      { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return stop || c < released + R; }); if (stop) return; }   // slot c % R is free once chunk c - R came back
+      parse_chunk(c, guess_start(d, size, (size_t)c * chunk), s.seg);
+      { std::lock_guard<std::mutex> lk(m); s.filled = true; }
+      cv.notify_all();
+    }
+  }
+  Segment* next() override {
+    if (take >= n_chunks) { tail.status = tail.begin() ? 0 : -2; tail.n = 0; return &tail; }   // empty input (or a caller that asks again after the end)
+    const u64 c = take++; Slot& s = *ring[c % ring.size()];
+    { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return s.filled; }); s.filled = false; }
+    Segment& g = s.seg;
+    const size_t bound = std::min(size, (size_t)(c + 1) * chunk);
+    if (expected >= bound) { g.begin(); g.start = g.end = expected; }             // a record of the previous chunk runs past this whole chunk
+    else if (g.start != expected) parse_chunk(c, expected, g);                      // the guess was wrong: this chunk again, from where the sequential parse stands
+    expected = g.end;
+    if (g.status == 1 && c + 1 == n_chunks) g.status = 0;
+    return &g;
+  }
+  void recycle(Segment* g) override {
+    if (g == &tail) return;
+    // slots are reused in chunk order, so segments must come back in the order next() handed them out (consume() and the
+    // driver's `held` queue do)
+    { std::lock_guard<std::mutex> lk(m); released++; }
+    cv.notify_all();
+  }
+  void finish() override {
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    cv.notify_all();
+    for (auto& t : th) if (t.joinable()) t.join();
+    th.clear();
+  }
+  ~MapStream() override { finish(); if (d) munmap((void*)d, size); if (fd >= 0) ::close(fd); }
+};
+
+bool is_gzip(const std::string& p) { FILE* f = fopen(p.c_str(), "rb"); if (!f) return false; unsigned char h[2] = {0, 0}; size_t n = fread(h, 1, 2, f); fclose(f); return n == 2 && h[0] == 0x1f && h[1] == 0x8b; }
+
+std::unique_ptr<SegStream> open_stream(const std::string& path, int threads, u64 gz_block_records, size_t chunk_bytes) {
+  if (is_gzip(path)) { std::unique_ptr<GzStream> g(new GzStream(gz_block_records)); if (!g->open(path)) return nullptr; return g; }
+  std::unique_ptr<MapStream> s(new MapStream());
+  if (!s->open(path, threads, chunk_bytes)) return nullptr;
+  return s;
+}
+size_t chunk_bytes_default() { const char* e = getenv("NB_FASTQ_CHUNK"); size_t v = e ? (size_t)strtoull(e, nullptr, 10) : 0; return v ? v : (8u << 20); }
 
 int write_tsv(const std::string& path, const nb_library* lib, const nb_counts& cts) {  // utils::write_to_tsv
   FILE* f = fopen(path.c_str(), "ab");
@@ -101,6 +294,31 @@ int write_tsv(const std::string& path, const nb_library* lib, const nb_counts& c
   return NB_OK;
 }
 
+// The consumer loop shared by the driver and the host-only dump: walks the one or two segment streams in lockstep and calls
+// emit(seg1, first1, seg2, first2, m) for every stretch of m records both current segments still hold.  Error precedence
+// follows the reference's zip over the two readers (src/process/fastq.rs:20-24): the first bad record wins, R1 before R2.
+template <class Emit, class Retire>
+int consume(SegStream* s1, SegStream* s2, Emit emit, Retire retire) {
+  Segment* c1 = nullptr; Segment* c2 = nullptr; u64 k1 = 0, k2 = 0; bool end1 = false, end2 = !s2;
+  int rc = NB_OK;
+  for (;;) {
+    while (!end1 && (!c1 || k1 == c1->n)) {
+      if (c1) { int st = c1->status; retire(s1, c1); c1 = nullptr; if (st == 0) { end1 = true; break; } if (st == -2) return fail(NB_ERR_CUDA, "pinned allocation failed"); if (st == -1) return fail(NB_ERR_PARSE, "Error -- could not parse read. Input R1 data malformed."); }
+      c1 = s1->next(); k1 = 0;
+    }
+    while (s2 && !end2 && (!c2 || k2 == c2->n)) {
+      if (c2) { int st = c2->status; retire(s2, c2); c2 = nullptr; if (st == 0) { end2 = true; break; } if (st == -2) return fail(NB_ERR_CUDA, "pinned allocation failed"); if (st == -1) return fail(NB_ERR_PARSE, "Error -- could not parse reverse read. Input R2 data malformed."); }
+      c2 = s2->next(); k2 = 0;
+    }
+    if (s2 && end1 != end2) return fail(NB_ERR_PARSE, "Error -- read and reverse read files do not have matching lengths: ");
+    if (end1) break;
+    u64 m = c1->n - k1; if (s2) m = std::min<u64>(m, c2->n - k2);
+    if (m) { rc = emit(c1, k1, c2, k2, m); if (rc != NB_OK) return rc; }
+    k1 += m; k2 += m;
+  }
+  return NB_OK;
+}
+
 }  // namespace
 
 extern "C" int nb_write_fastq_tsv(const char* path, const nb_library* lib, const nb_counts* counts) {
@@ -108,45 +326,83 @@ extern "C" int nb_write_fastq_tsv(const char* path, const nb_library* lib, const
   return write_tsv(path, lib, *counts);
 }
 
+// host-only: the records the feeder hands to the device, one line per record ("SEQ" or "SEQ1\tSEQ2") — parity tests of the
+// parallel parser against a sequential one need no GPU.  chunk_bytes 0 = default.
+extern "C" int nb_fastq_dump(const char* const* input_files, uint32_t n_inputs, int num_cores, uint64_t chunk_bytes, const char* out_path) {
+  if (!input_files || n_inputs < 1 || n_inputs > 2 || !out_path) return fail(NB_ERR_INVALID, "need 1-2 inputs and an output path");
+  g_pageable = true;
+  struct Unset { ~Unset() { g_pageable = false; } } unset;
+  const int T = std::max(1, num_cores / (int)n_inputs);
+  std::unique_ptr<SegStream> s1 = open_stream(input_files[0], T, 1u << 16, chunk_bytes ? chunk_bytes : chunk_bytes_default()), s2;
+  if (!s1) return fail(NB_ERR_IO, std::string("could not open ") + input_files[0]);
+  if (n_inputs > 1) { s2 = open_stream(input_files[1], T, 1u << 16, chunk_bytes ? chunk_bytes : chunk_bytes_default()); if (!s2) return fail(NB_ERR_IO, std::string("could not open ") + input_files[1]); }
+  FILE* f = out_path[0] ? fopen(out_path, "wb") : nullptr;   // "" = parse only (timing the feeder)
+  if (!f && out_path[0]) return fail(NB_ERR_IO, std::string("Unable to open file ") + out_path);
+  int rc = consume(s1.get(), s2.get(),
+    [&](Segment* a, u64 ka, Segment* b, u64 kb, u64 m) {
+      for (u64 i = 0; f && i < m; i++) {
+        fwrite(a->seq.p + a->off()[ka + i], 1, a->off()[ka + i + 1] - a->off()[ka + i], f);
+        if (b) { fputc('\t', f); fwrite(b->seq.p + b->off()[kb + i], 1, b->off()[kb + i + 1] - b->off()[kb + i], f); }
+        fputc('\n', f);
+      }
+      return (int)NB_OK;
+    },
+    [&](SegStream* s, Segment* g) { s->recycle(g); });
+  if (f) fclose(f);
+  s1->finish(); if (s2) s2->finish();
+  return rc;
+}
+
 // process::fastq::process with the library loop of src/bin/main.rs:95-133 in front of it.
 extern "C" int nb_process_fastq(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,
                                 uint32_t n_refs, int strand_filter, int num_cores, int device) {
   if (!input_files || !reference_json || !output_paths || n_inputs < 1 || n_inputs > 2 || n_refs < 1) return fail(NB_ERR_INVALID, "need 1-2 inputs and >=1 reference/output pair");
-  const u64 BATCH = 1u << 19;
+  const u64 BATCH = 1u << 20;
+  const int T = std::max(1, num_cores / (int)n_inputs);
+  const bool stats = getenv("NB_FASTQ_STATS") != nullptr;   // phase times on stderr
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
   for (u32 li = 0; li < n_refs; li++) {
     nb_library* lib = nullptr; nb_index* ix = nullptr; nb_ctx* ctx = nullptr;
+    const double t0 = now();
     int rc = nb_library_load_json(reference_json[li], strand_filter, &lib);
-    if (rc == NB_OK) rc = nb_index_build(lib, num_cores, &ix);
+    const double t1 = now();
+    if (rc == NB_OK) rc = nb_index_build_gpu(lib, device, std::max(1, num_cores), &ix);   // K5: the CUDA builder (same artefact as nb_index_build)
+    const double t2 = now();
     if (rc == NB_OK) rc = nb_ctx_create(ix, lib, device, nullptr, &ctx);
     if (rc == NB_OK) rc = nb_ctx_set_option(ctx, "max_batch_pairs", BATCH);
-    // one reader thread per input file parses blocks of BATCH records into pinned memory while the device works
-    Feeder fd[2]; bool paired = n_inputs > 1;
-    if (rc == NB_OK && !fd[0].rd.open(input_files[0])) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[0]);
-    if (rc == NB_OK && paired && !fd[1].rd.open(input_files[1])) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[1]);
-    if (rc == NB_OK) { fd[0].start(BATCH); if (paired) fd[1].start(BATCH); }
-    while (rc == NB_OK) {
-      Block* a = fd[0].pop(); Block* b2 = paired ? fd[1].pop() : nullptr;
-      if (a->status == -2 || (b2 && b2->status == -2)) rc = fail(NB_ERR_CUDA, "pinned allocation failed");
-      else if (a->status == -1) rc = fail(NB_ERR_PARSE, "Error -- could not parse read. Input R1 data malformed.");
-      else if (b2 && b2->status == -1) rc = fail(NB_ERR_PARSE, "Error -- could not parse reverse read. Input R2 data malformed.");
-      else if (b2 && (a->n != b2->n || a->status != b2->status)) rc = fail(NB_ERR_PARSE, "Error -- read and reverse read files do not have matching lengths: ");
-      if (rc != NB_OK) break;
-      if (a->n) {
-        nb_batch b; memset(&b, 0, sizeof b);
-        b.n_pairs = a->n; b.location = NB_MEM_HOST; b.max_read_len = std::max<u32>(a->maxlen, b2 ? b2->maxlen : 0);
-        b.r1 = a->seq.p; b.r1_off = a->off.data();
-        if (b2) { b.r2 = b2->seq.p; b.r2_off = b2->off.data(); }
-        rc = nb_align_batch(ctx, &b, nullptr, nullptr);
-        if (rc == NB_OK) rc = nb_ctx_sync(ctx);   // the copies out of these blocks are done: they can be refilled (a batch is ~5 ms on the device, ~100 ms to parse)
-      }
-      bool last = a->status == 0;
-      fd[0].recycle(a); if (b2) fd[1].recycle(b2);
-      if (last) break;
+    const double t3 = now(); u64 n_pairs_fed = 0, n_calls = 0;
+    std::unique_ptr<SegStream> s1, s2;
+    if (rc == NB_OK) { s1 = open_stream(input_files[0], T, 1u << 19, chunk_bytes_default()); if (!s1) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[0]); }
+    if (rc == NB_OK && n_inputs > 1) { s2 = open_stream(input_files[1], T, 1u << 19, chunk_bytes_default()); if (!s2) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[1]); }
+    if (rc == NB_OK) {
+      // A segment goes back to its stream once the copies out of it have run: nb_align_batch blocks on the copies of a staging
+      // set before refilling it, so everything submitted before the last two calls is free again (nimble_b200.h).
+      struct Held { SegStream* s; Segment* g; u64 call; };
+      std::deque<Held> held; u64 calls = 0;
+      auto release = [&](bool all) { while (!held.empty() && (all || held.front().call + 2 <= calls)) { held.front().s->recycle(held.front().g); held.pop_front(); } };
+      rc = consume(s1.get(), s2.get(),
+        [&](Segment* a, u64 ka, Segment* b2, u64 kb, u64 m) {
+          nb_batch b; memset(&b, 0, sizeof b);
+          b.n_pairs = m; b.location = NB_MEM_HOST; b.max_read_len = std::max<u32>(a->maxlen, b2 ? b2->maxlen : 0);
+          b.r1 = a->seq.p; b.r1_off = a->off() + ka;
+          if (b2) { b.r2 = b2->seq.p; b.r2_off = b2->off() + kb; }
+          int r = nb_align_batch(ctx, &b, nullptr, nullptr);
+          calls++; release(false); n_pairs_fed += m; n_calls++;
+          return r;
+        },
+        [&](SegStream* s, Segment* g) { held.push_back({s, g, calls}); release(false); });
+      if (nb_ctx_sync(ctx) != NB_OK && rc == NB_OK) rc = NB_ERR_CUDA;
+      release(true);
     }
-    fd[0].finish(); if (paired) fd[1].finish();
+    if (s1) s1->finish();
+    if (s2) s2->finish();
+    const double t4 = now();
     nb_counts cts;
     if (rc == NB_OK) rc = nb_counts_finalize(ctx, &cts);
     if (rc == NB_OK) rc = write_tsv(output_paths[li], lib, cts);
+    s1.reset(); s2.reset();
+    if (stats) fprintf(stderr, "nb_process_fastq: library %.3f s, index (GPU) %.3f s, context %.3f s, parse+align %.3f s (%llu pairs in %llu calls, %d parser threads per file: %.1f M reads/s), finalize+tsv %.3f s\n",
+                       t1 - t0, t2 - t1, t3 - t2, t4 - t3, (unsigned long long)n_pairs_fed, (unsigned long long)n_calls, T, (double)n_pairs_fed * n_inputs / std::max(t4 - t3, 1e-9) / 1e6, now() - t4);
     nb_ctx_free(ctx); nb_index_free(ix); nb_library_free(lib);
     if (rc != NB_OK) return rc;
   }
