@@ -83,7 +83,11 @@ struct nb_ctx {
   // state
   int mode = -1;  // -1 unset, 0 whole-run scope (keys persist), 1 scoped (keys live for one batch)
   bool folded = false;
-  u64 pairs_seen = 0, keys_upper = 0, last_unique = 0;
+  u64 pairs_seen = 0, last_unique = 0;
+  // Whole-run scope: how full the key table is, known without a blocking pass.  The device keeps Counters::n_live; after every
+  // launch that inserts keys an 8-byte copy of it is queued into a pinned ring behind an event.  Upper bound on the current
+  // count = the newest value that has arrived + every key submitted since that copy was queued.
+  struct LiveRing { cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; u64* host = nullptr; u64 at[4] = {0, 0, 0, 0}; bool pending[4] = {false, false, false, false}; int next = 0; u64 known = 0, known_at = 0, submitted = 0; } live;
   BatchDev last_b; bool have_last = false;
   // timing
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
@@ -141,7 +145,9 @@ static int alloc_tables(nb_ctx* c) {
   CK(c->d_arena.ensure(c->arena_entries * 4, s)); CK(c->d_ctr.ensure(sizeof(Counters), s)); CK(c->d_nout.ensure(64, s));
   CK(cudaMemsetAsync(c->d_cstag.p, 0, c->cs_slots * 8, s)); CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s));
   CK(cudaMemsetAsync(c->d_aggkey.p, 0, c->agg_slots * 8, s)); CK(cudaMemsetAsync(c->d_aggcnt.p, 0, c->agg_slots * 8, s)); CK(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), s));
-  c->tables_ready = true; c->mode = -1; c->folded = false; c->pairs_seen = 0; c->keys_upper = 0; c->have_last = false;
+  c->tables_ready = true; c->mode = -1; c->folded = false; c->pairs_seen = 0; c->have_last = false;
+  for (int i = 0; i < 4; i++) { if (c->live.pending[i]) cudaEventSynchronize(c->live.ev[i]); c->live.pending[i] = false; }
+  c->live.known = c->live.known_at = c->live.submitted = 0;
   return NB_OK;
 }
 
@@ -260,6 +266,8 @@ void nb_ctx_free(nb_ctx* c) {
   nb_comm_free(c);
   c->d_blk1.release(); c->d_all1.release(); c->d_blk2.release(); c->d_all2.release(); c->d_densetab.release(); c->d_densework.release();
   nb_host_free(c->h_hdr); c->h_hdr = nullptr;
+  for (int i = 0; i < 4; i++) if (c->live.ev[i]) cudaEventDestroy(c->live.ev[i]);
+  nb_host_free(c->live.host); c->live.host = nullptr;
   nb_host_free(c->h_rows); c->h_rows = nullptr;
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -301,6 +309,35 @@ static int grow_keys(nb_ctx* c, u64 need_slots) {
   if (!ck2(cudaStreamSynchronize(s))) return NB_ERR_CUDA;
   c->d_key.release(); c->d_kval.release(); c->d_key = nk; c->d_kval = nv; c->key_slots = ns;
   c->d_klast.release(); CK(c->d_klast.ensure(ns * 8, s)); CK(cudaMemsetAsync(c->d_klast.p, 0, ns * 8, s));
+  return NB_OK;
+}
+
+// after a launch that inserted keys (live.submitted already counts them): queue a copy of the device's unique-key count
+static int live_note(nb_ctx* c) {
+  nb_ctx::LiveRing& L = c->live;
+  if (!L.host) {
+    L.host = (u64*)nb_host_alloc(4 * sizeof(u64)); if (!L.host) return fail(NB_ERR_CUDA, "pinned host allocation failed");
+    for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&L.ev[i], cudaEventDisableTiming));
+  }
+  const int i = L.next;
+  if (L.pending[i]) { if (cudaEventQuery(L.ev[i]) != cudaSuccess) return NB_OK; L.pending[i] = false; if (L.at[i] >= L.known_at) { L.known = L.host[i]; L.known_at = L.at[i]; } }   // ring full of copies still in flight: keep them
+  CK(cudaMemcpyAsync(&L.host[i], &((Counters*)c->d_ctr.p)->n_live, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventRecord(L.ev[i], c->stream));
+  L.at[i] = L.submitted; L.pending[i] = true; L.next = (i + 1) & 3;
+  return NB_OK;
+}
+// room for `incoming` more keys at load <= 0.5; blocks (and counts exactly) only when the bound says the table might not do
+static int ensure_key_capacity(nb_ctx* c, u64 incoming) {
+  nb_ctx::LiveRing& L = c->live;
+  for (int i = 0; i < 4; i++) if (L.pending[i] && cudaEventQuery(L.ev[i]) == cudaSuccess) { L.pending[i] = false; if (L.at[i] >= L.known_at) { L.known = L.host[i]; L.known_at = L.at[i]; } }
+  u64 upper = L.known + (L.submitted - L.known_at);
+  if (2 * (upper + incoming) > c->key_slots) {
+    Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;   // drains the stream: every queued copy has arrived too
+    for (int i = 0; i < 4; i++) L.pending[i] = false;
+    L.known = h.n_live; L.known_at = L.submitted;
+    if (2 * (h.n_live + incoming) > c->key_slots) { rc = grow_keys(c, 2 * (h.n_live + incoming)); if (rc) return rc; }
+  }
+  L.submitted += incoming;
   return NB_OK;
 }
 
@@ -367,17 +404,8 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   if (c->mode == 1) { CK(c->d_pslot.ensure(np * 8, s)); CK(c->d_pres2.ensure(np * sizeof(nbk::PairRes), s)); b.pslot = (u64*)c->d_pslot.p; b.pres2 = (nbk::PairRes*)c->d_pres2.p; }
   b.pk = (u64*)c->d_pk.p; b.len_full = (u32*)c->d_lenfull.p; b.len_trim = (u32*)c->d_lentrim.p; b.rres = (nbk::ReadRes*)c->d_rres.p; b.pres = (nbk::PairRes*)c->d_pres.p; b.seeded = (uint4*)c->d_seeded.p;
   // key-table capacity
-  if (c->mode == 0) {
-    if (2 * (c->keys_upper + np) > c->key_slots) {
-      CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
-      nbk::launch_count_keys(make_tables(c), s); c->all_launches++;
-      Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
-      CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
-      c->keys_upper = h.n_keys;
-      if (2 * (c->keys_upper + np) > c->key_slots) { rc = grow_keys(c, 2 * (c->keys_upper + np)); if (rc) return rc; }
-    }
-    c->keys_upper += np;
-  } else if (2 * np > c->key_slots) { int rc = grow_keys(c, 2 * np); if (rc) return rc; }
+  if (c->mode == 0) { int rc = ensure_key_capacity(c, np); if (rc) return rc; }
+  else if (2 * np > c->key_slots) { int rc = grow_keys(c, 2 * np); if (rc) return rc; }
   Tables t = make_tables(c);
   CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->arena_top, 0, 32, s));   // arena_top, queue, seeded_n, wqueue
   nbk::launch_pack(b, s); c->all_launches++;
@@ -391,6 +419,7 @@ static int run_chunk(nb_ctx* c, const nb_batch* bt, u64 p0, u64 p1, u32 max_len,
   nbk::Route rt; memset(&rt, 0, sizeof rt);
   if (c->route_on && c->mode == 0) rt = c->route;
   nbk::launch_pair(b, c->dix, c->dlib, c->dcfg, t, rt, s); c->all_launches++;
+  if (c->mode == 0) { int rc = live_note(c); if (rc) return rc; }
   if (c->mode == 1) {
     nbk::launch_fold(t, b.cell, b.order_base, s); c->all_launches++;
     if (pairs_out) { nbk::launch_resolve(b, t, s); c->all_launches++; }
@@ -599,7 +628,7 @@ int nb_counts_reset(nb_ctx* c) {
   if (!c) return fail(NB_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
   if (c->tables_ready) { CK(cudaStreamSynchronize(c->stream)); c->tables_ready = false; }
-  c->mode = -1; c->folded = false; c->pairs_seen = 0; c->keys_upper = 0; c->have_last = false; c->n_rows_dev = 0;
+  c->mode = -1; c->folded = false; c->pairs_seen = 0; c->have_last = false; c->n_rows_dev = 0;
   if (c->d_routecur.p) CK(cudaMemsetAsync(c->d_routecur.p, 0, nbk::ROUTE_MAX * 8, c->stream));   // a job abandoned before nb_route_sent must not leak its records into the next one
   return NB_OK;
 }
@@ -713,10 +742,13 @@ int nb_keys_import(nb_ctx* c, const void* dev_records, uint64_t n) {
   cudaStream_t s = c->stream;
   if (2 * n > c->key_slots) { c->d_key.release(); c->d_kval.release(); u64 ns = c->key_slots; while (ns < 2 * n) ns <<= 1; c->key_slots = ns; CK(c->d_key.ensure(ns * 16, s)); CK(c->d_kval.ensure(ns * 8, s)); }
   CK(cudaMemsetAsync(c->d_key.p, 0, c->key_slots * 16, s)); CK(cudaMemsetAsync(c->d_kval.p, 0, c->key_slots * 8, s));
-  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
+  CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s)); CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_live, 0, 8, s));
   nbk::launch_keys_import(make_tables(c), dev_records, n, s); c->all_launches++;
   c->folded = false;
-  return check_device_errors(c);
+  Counters h; int rc = check_device_errors(c, &h);   // drains the stream: the table now holds exactly the imported partition
+  for (int i = 0; i < 4; i++) c->live.pending[i] = false;
+  c->live.known = h.n_live; c->live.submitted = c->live.known_at = n;
+  return rc;
 }
 
 // ---- peer routing of the whole-run scope over NVLink (kernels.cuh Route; DESIGN.md "Multi-GPU")
@@ -820,15 +852,7 @@ int nb_route_import(nb_ctx* c, const uint64_t* counts, uint64_t* n_imported) {
   cudaStream_t s = c->stream;
   u64 n = 0;
   for (u32 r = 0; r < c->route.world; r++) if (r != c->route.rank) { if (counts[r] > c->inbox_cap) return fail(NB_ERR_OVERFLOW, "routing inbox region overflow: create the routes with more records_per_peer"); n += counts[r]; }
-  if (2 * (c->keys_upper + n) > c->key_slots) {
-    CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
-    nbk::launch_count_keys(make_tables(c), s); c->all_launches++;
-    Counters h; int rc = check_device_errors(c, &h); if (rc) return rc;
-    CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
-    c->keys_upper = h.n_keys;
-    if (2 * (c->keys_upper + n) > c->key_slots) { rc = grow_keys(c, 2 * (c->keys_upper + n)); if (rc) return rc; }
-  }
-  c->keys_upper += n;
+  { int rc = ensure_key_capacity(c, n); if (rc) return rc; }
   Tables t = make_tables(c);
   for (u32 r = 0; r < c->route.world; r++) if (r != c->route.rank && counts[r]) {
     nbk::launch_keys_import(t, (const nbk::KeyRec*)c->d_inbox.p + (size_t)r * c->inbox_cap, counts[r], s); c->all_launches++;
@@ -1006,15 +1030,7 @@ int nb_merge_whole_run(nb_ctx* c, nb_counts* out) {
   // says every peer's last batch is complete), merged with the same "later duplicate wins" rule
   u64 n_in = 0, n_max = 0;
   for (u32 r = 0; r < W; r++) if (r != c->crank) { if (recv[r] > c->inbox_cap) return fail(NB_ERR_OVERFLOW, "routing inbox region overflow: create the routes with more records_per_peer"); n_in += recv[r]; n_max = std::max(n_max, recv[r]); }
-  if (2 * (c->keys_upper + n_in) > c->key_slots) {
-    CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
-    nbk::launch_count_keys(make_tables(c), s); c->all_launches++;
-    Counters h; rc = check_device_errors(c, &h); if (rc) return rc;
-    CK(cudaMemsetAsync(&((Counters*)c->d_ctr.p)->n_keys, 0, 8, s));
-    c->keys_upper = h.n_keys;
-    if (2 * (c->keys_upper + n_in) > c->key_slots) { rc = grow_keys(c, 2 * (c->keys_upper + n_in)); if (rc) return rc; }
-  }
-  c->keys_upper += n_in;
+  rc = ensure_key_capacity(c, n_in); if (rc) return rc;
   Tables t = make_tables(c);
   const size_t blk_b = (8 * (size_t)nbk::MERGE_HDR1_WORDS + c->merge_cap * (4 + c->gcap) * 4 + 15) & ~(size_t)15;
   nbk::launch_merge_import_inbox(t, c->d_inbox.p, c->inbox_cap, n_max, c->d_all1.p, blk_b, W, c->crank, s); c->all_launches++;

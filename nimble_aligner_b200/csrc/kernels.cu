@@ -51,8 +51,9 @@ __device__ __forceinline__ u64 rev2(u64 x) {  // reverse the order of the 32 2-b
   return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
 }
 
-__global__ void __launch_bounds__(256) k_pack(BatchDev b) {
-  u32 idx = blockIdx.x * blockDim.x + threadIdx.x;         // n_reads * W < 2^32 (checked by the host)
+// one (read, data word) straight from global memory: 2-3 aligned 16-byte loads realigned in registers (round 1's k_pack; kept
+// for blocks whose span does not fit the staging buffer — reads longer than the batch declared)
+__device__ __forceinline__ void pack_word_direct(const BatchDev& b, u32 idx) {
   // one thread per DATA word; the last data word's thread also writes the read's zero pad word (a thread per pad word
   // idled one lane in W: measured 2.00 -> 2.03 G reads/s on the C2 step)
   const u32 Wd = b.W - 1;
@@ -102,6 +103,92 @@ __global__ void __launch_bounds__(256) k_pack(BatchDev b) {
   }
   b.pk[(u64)ri * b.W + w] = word;
 }
+
+
+// K0, staged variant (NB_PACK_BULK=1): ASCII -> 2-bit through shared memory, staged by bulk asynchronous copies.
+// A block owns RB consecutive reads (RB * Wd <= 256 word-threads; RB even when paired) = one contiguous ASCII span per side.
+//   A  one elected thread arms an mbarrier with the byte count and issues one cp.async.bulk (TMA engine, global -> shared)
+//      per side for the 16-byte-aligned cover of the span; the block waits on the barrier's phase
+//   B  every thread classifies aligned 16-byte chunks (conflict-free 128-bit shared loads, no realignment: the reads'
+//      arbitrary start offsets do not matter yet) into 32 bits of 2-bit codes -> a contiguous 2-bit image of the span
+//   C  thread (read, word) cuts its 64-bit window out of that image at the read's base offset (three 32-bit shared loads
+//      + two funnel shifts), masks the tail, reverse-complements if asked, writes the word (+ the zero pad word, lengths)
+// Round 1's kernel did the realignment on the ASCII bytes in registers (per thread: 2-3 misaligned-by-construction 16-byte
+// global loads, a 12-word select network, 8 funnel shifts) and ran at 0.48 of the HBM stream peak, issue-bound at 256
+// instructions per 32 bases; classifying aligned data first and realigning the 4x smaller 2-bit image halves that.
+constexpr int PACK_T = 256;
+constexpr int PACK_RAW = 8192 + 64;     // RB reads x at most 32 * Wd bytes <= 256 * 32, + the alignment slack of two spans
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(PACK_T) k_pack_bulk(BatchDev b, u32 RB, u32 inv_wd) {
+  __shared__ __align__(16) u8 s_raw[PACK_RAW];
+  __shared__ u32 s_bits[PACK_RAW / 16 + 2];
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ u64 s_g0[2]; __shared__ u32 s_lead[2], s_bytes[2];
+  const u32 tid = threadIdx.x, Wd = b.W - 1, sides = b.sides;
+  const u32 r0 = blockIdx.x * RB, rn = min(RB, b.n_reads - r0);          // this block's reads [r0, r0 + rn)
+  const u64 p0 = r0 / sides; const u32 pn = (rn + sides - 1) / sides;      // ... = pairs [p0, p0 + pn) on every side
+  if (tid < sides) {
+    const u64 g0 = b.off[tid][p0], g1 = b.off[tid][p0 + pn];
+    const uintptr_t a = (uintptr_t)(b.a[tid] + g0);
+    s_g0[tid] = g0; s_lead[tid] = (u32)(a & 15); s_bytes[tid] = (u32)min(((a & 15) + (g1 - g0) + 15) & ~(u64)15, (u64)0x40000000);
+  }
+  if (tid == 0) {
+    if (sides == 1) { s_bytes[1] = 0; s_lead[1] = 0; s_g0[1] = 0; }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const u32 bytes0 = s_bytes[0], bytes1 = s_bytes[1], total = bytes0 + bytes1;
+  if (total > (u32)PACK_RAW) {   // a read longer than the batch declared: no staging for this block
+    if (tid < rn * Wd) pack_word_direct(b, r0 * Wd + tid);
+    return;
+  }
+  // ---- A: bulk copies (global -> shared) signalled through the mbarrier's transaction count
+  if (total) {
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s_bar)), "r"(total) : "memory");
+      if (bytes0) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                               :: "r"(smem_u32(s_raw)), "l"((const u8*)(((uintptr_t)(b.a[0] + s_g0[0])) & ~(uintptr_t)15)), "r"(bytes0), "r"(smem_u32(&s_bar)) : "memory");
+      if (bytes1) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                               :: "r"(smem_u32(s_raw + bytes0)), "l"((const u8*)(((uintptr_t)(b.a[1] + s_g0[1])) & ~(uintptr_t)15)), "r"(bytes1), "r"(smem_u32(&s_bar)) : "memory");
+    }
+    asm volatile("{\n\t.reg .pred p;\n\tNB_PACK_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra NB_PACK_DONE;\n\tbra NB_PACK_WAIT;\n\tNB_PACK_DONE:\n\t}" :: "r"(smem_u32(&s_bar)) : "memory");
+  }
+  // ---- B: 16 aligned bytes -> 16 two-bit codes
+  for (u32 ch = tid; ch < total / 16; ch += PACK_T) {
+    const uint4 v = ((const uint4*)s_raw)[ch];
+    u32 bad = 0;
+    const u32 q0 = codes4_fast(v.x, bad), q1 = codes4_fast(v.y, bad), q2 = codes4_fast(v.z, bad), q3 = codes4_fast(v.w, bad);
+    u32 w;
+    if (bad == 0) w = __byte_perm(__byte_perm(q0, q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
+    else w = codes4(v.x) | (codes4(v.y) << 8) | (codes4(v.z) << 16) | (codes4(v.w) << 24);   // a non-ACGT byte (-> A): the exact compares
+    s_bits[ch] = w;
+  }
+  if (tid < 2) s_bits[total / 16 + tid] = 0;
+  __syncthreads();
+  // ---- C: one thread per (read, data word); the last data word's thread also writes the read's zero pad word
+  if (tid >= rn * Wd) return;
+  const u32 rl = (tid * inv_wd) >> 16, w = tid - rl * Wd, ri = r0 + rl;   // tid / Wd by a 16-bit reciprocal (exact for tid < 256, Wd <= 32)
+  const u32 side = sides == 2 ? (ri & 1) : 0; const u64 p = sides == 2 ? (ri >> 1) : ri;
+  const u64 o0 = b.off[side][p]; const u32 len = (u32)(b.off[side][p + 1] - o0);
+  const bool rc = b.flags[side] != nullptr && (b.flags[side][p] & 2);
+  if (w == Wd - 1) b.pk[(u64)ri * b.W + Wd] = 0;
+  if (w == 0) { b.len_full[ri] = len; b.len_trim[ri] = len; }
+  u64 word = 0; const u32 s = w * 32;
+  if (s < len) {
+    const u32 cnt = min(32u, len - s);
+    // base index of the stretch's first base in the 2-bit image (one base per staged byte)
+    const u32 bi = (side ? bytes0 : 0u) + s_lead[side] + (u32)(o0 - s_g0[side]) + (rc ? len - s - cnt : s);
+    const u32* q = s_bits + (bi >> 4); const u32 sh = (bi & 15) * 2;
+    const u32 x0 = q[0], x1 = q[1], x2 = q[2];
+    word = (u64)__funnelshift_r(x0, x1, sh) | ((u64)__funnelshift_r(x1, x2, sh) << 32);
+    if (cnt < 32) word &= (1ULL << (2 * cnt)) - 1;
+    if (rc) { word = rev2(word) >> (64 - 2 * cnt); word ^= cnt < 32 ? ((1ULL << (2 * cnt)) - 1) : ~0ULL; }
+  }
+  b.pk[(u64)ri * b.W + w] = word;
+}
+
+__global__ void __launch_bounds__(256) k_pack(BatchDev b) { pack_word_direct(b, blockIdx.x * blockDim.x + threadIdx.x); }
 
 // ---- packed input encodings (nb_batch.encoding): the host ships 2 or 4 bits per base instead of 8 — the boundary the
 // reference's hot path really has (score::call takes 2-bit DnaStrings, src/score.rs:14-31; BAM stores 4-bit nibbles,
@@ -344,17 +431,24 @@ __device__ __forceinline__ void cas128(ulonglong2* addr, u64 n0, u64 n1, u64& o0
   asm volatile("{\n\t.reg .b128 c, n, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\tatom.global.cas.b128 o, [%6], c, n;\n\tmov.b128 {%0, %1}, o;\n\t}\n"
                : "=l"(o0), "=l"(o1) : "l"(0ULL), "l"(0ULL), "l"(n0), "l"(n1), "l"(addr) : "memory");
 }
-// insert-or-find a 128-bit key; returns slot or ~0 when the table is full
-__device__ __forceinline__ u64 key_insert(const Tables& t, u64 k0, u64 k1) {
+// insert-or-find a 128-bit key; returns slot or ~0 when the table is full; fresh = this call created the entry
+__device__ __forceinline__ u64 key_insert(const Tables& t, u64 k0, u64 k1, bool& fresh) {
   u64 h = (k0 ^ (k1 >> 17)) & t.key_mask;
+  fresh = false;
   for (u64 probes = 0; probes <= t.key_mask; probes++) {
     // the 128-bit CAS is also the (atomic) read: a plain 16-byte load could be torn against a concurrent insert
     u64 o0, o1; cas128(t.key + h, k0, k1, o0, o1);
-    if (o0 == 0 && o1 == 0) return h;   // new key (unique keys are counted by k_fold / k_count_keys, not here: one hot counter would serialise)
+    if (o0 == 0 && o1 == 0) { fresh = true; return h; }
     if (o0 == k0 && o1 == k1) return h;
     h = (h + 1) & t.key_mask;
   }
   return ~0ULL;
+}
+// Counters::n_live += the new keys of the lanes that are converged here (one atomic per group: a per-key atomic on one
+// address would serialise).  The host sizes the key table from this count instead of re-counting the table (k_count_keys).
+__device__ __forceinline__ void count_fresh(const Tables& t, bool fresh) {
+  const unsigned act = __activemask(), fm = __ballot_sync(act, fresh);
+  if (fm && (threadIdx.x & 31) == (unsigned)(__ffs(fm) - 1)) atomicAdd(&t.ctr->n_live, (unsigned long long)__popc(fm));
 }
 __device__ __forceinline__ u32 callset_intern(const Tables& t, const u32* g, u32 n) {
   u64 tag = 0x9E3779B97F4A7C15ULL ^ n;
@@ -378,9 +472,8 @@ __device__ __forceinline__ u32 callset_intern(const Tables& t, const u32* g, u32
 // owning rank of a read_key in a multi-GPU whole-run scope: a 16-bit slice of key_lo mod world
 __device__ __forceinline__ u32 key_owner(u64 k0, u32 world) { return (u32)((k0 >> 40) & 0xFFFFu) % world; }
 
-__global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L, DevCfg cfg, Tables t, Route rt) {
-  u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-  if (p >= b.n_pairs) return;
+// one pair; returns true when the pair created a new entry of the whole-run key table (k_pair counts those per block)
+__device__ __forceinline__ bool pair_one(const BatchDev& b, const DevIndex& ix, const DevLib& L, const DevCfg& cfg, const Tables& t, const Route& rt, u64 p) {
   bool paired = b.sides == 2;
   u32 ri1 = (u32)(p * b.sides);
   ReadRes r1 = b.rres[ri1], r2;
@@ -476,8 +569,9 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
   const bool routed = rt.world > 1 && !scoped;
   u32 owner = routed ? key_owner(h0, rt.world) : 0u;
   bool send = routed && out.insertable && owner != rt.rank;
+  bool fresh = false;
   if ((out.insertable || scoped) && !send) {
-    u64 slot = key_insert(t, h0, h1);
+    u64 slot = key_insert(t, h0, h1, fresh);
     if (slot == ~0ULL) atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL);
     else {
       unsigned long long ord1 = (routed ? rt.pair_base : 0ULL) + b.order_base + p + 1;
@@ -503,6 +597,23 @@ __global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L,
     }
   }
   b.pres[p] = out;
+  return fresh && !scoped;
+}
+// Counters::n_live += the block's new keys: one shared-memory atomic per warp, one global atomic per block.  (A per-warp
+// global atomic issued from inside the divergent pair logic — several convergence groups per warp — cost 1.5 ms per 10 M pairs
+// on that one address.)
+__global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L, DevCfg cfg, Tables t, Route rt) {
+  __shared__ u32 s_new;
+  if (threadIdx.x == 0) s_new = 0;
+  __syncthreads();
+  const u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  bool fresh = false;
+  if (p < b.n_pairs) fresh = pair_one(b, ix, L, cfg, t, rt, p);
+  __syncwarp();
+  const unsigned fm = __ballot_sync(0xFFFFFFFFu, fresh);
+  if ((threadIdx.x & 31) == 0 && fm) atomicAdd(&s_new, (u32)__popc(fm));
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) atomicAdd(&t.ctr->n_live, (unsigned long long)s_new);
 }
 
 // Per-pair records as the reference reports them (per read_key): filter reasons of the LAST pair carrying the key
@@ -594,7 +705,8 @@ __global__ void __launch_bounds__(256) k_rehash_keys(Tables o, Tables n) {
   if (idx > o.key_mask) return;
   ulonglong2 k = o.key[idx];
   if (k.x == 0 && k.y == 0) return;
-  u64 slot = key_insert(n, k.x, k.y);
+  bool fresh;
+  u64 slot = key_insert(n, k.x, k.y, fresh);
   if (slot == ~0ULL) { atomicOr(&n.ctr->err, (unsigned)E_KEY_FULL); return; }
   n.kval[slot] = o.kval[idx];
 }
@@ -623,7 +735,9 @@ __global__ void __launch_bounds__(256) k_keys_import(Tables t, const KeyRec* rec
     if (!ok) { atomicOr(&t.ctr->err, (unsigned)E_CS_FULL); return; }
     cs = h;
   }
-  u64 slot = key_insert(t, r.k0, r.k1);
+  bool fresh;
+  u64 slot = key_insert(t, r.k0, r.k1, fresh);
+  count_fresh(t, fresh && slot != ~0ULL);
   if (slot == ~0ULL) { atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL); return; }
   atomicMax(t.kval + slot, (unsigned long long)(((r.order + 1) << 24) | cs));
 }
@@ -722,7 +836,9 @@ __device__ __forceinline__ void key_import_rec(const Tables& t, const KeyRec& r)
     if (!ok) { atomicOr(&t.ctr->err, (unsigned)E_CS_FULL); return; }
     cs = h;
   }
-  u64 slot = key_insert(t, r.k0, r.k1);
+  bool fresh;
+  u64 slot = key_insert(t, r.k0, r.k1, fresh);
+  count_fresh(t, fresh && slot != ~0ULL);
   if (slot == ~0ULL) { atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL); return; }
   atomicMax(t.kval + slot, (unsigned long long)(((r.order + 1) << 24) | cs));
 }
@@ -811,7 +927,17 @@ void launch_pack(const BatchDev& b, cudaStream_t s) {
   u64 n = (u64)b.n_reads * (b.W - 1); if (!n) return;
   if (b.enc == 1) k_pack_enc<1><<<blocks_for(n, 256), 256, 0, s>>>(b);
   else if (b.enc == 2) k_pack_enc<2><<<blocks_for(n, 256), 256, 0, s>>>(b);
-  else k_pack<<<blocks_for(n, 256), 256, 0, s>>>(b);
+  else {
+    // Measured on B200 (C2, 2 M reads per launch): the direct kernel 110 us, the bulk-copy kernel 145 us — one tile per block
+    // leaves each block's chain offsets -> TMA -> wait -> classify -> cut exposed (8 resident blocks do not cover it) and the
+    // classification, not the realignment, is most of the instructions.  The direct kernel stays the default;
+    // NB_PACK_BULK=1 selects the staged one (same results: the parity suite runs green on both).
+    const char* env = getenv("NB_PACK_BULK"); const bool bulk = env && atoi(env) != 0;   // read per launch: the tests switch it
+    const u32 Wd = b.W - 1;
+    if (!bulk || Wd > 32) { k_pack<<<blocks_for(n, 256), 256, 0, s>>>(b); return; }
+    u32 RB = PACK_T / Wd; if (b.sides == 2) RB &= ~1u;
+    k_pack_bulk<<<blocks_for(b.n_reads, RB), PACK_T, 0, s>>>(b, RB, (65536u + Wd - 1) / Wd);
+  }
 }
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s) { if (b.n_reads) k_trim<<<blocks_for(b.n_reads, 256), 256, 0, s>>>(b, t); }
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s) {

@@ -54,6 +54,7 @@ struct Counters {
   unsigned long long probes, nodes, bases, colour_elems;   // work counters (roofline numerator cross-check)
   unsigned int err; unsigned int pad;
   unsigned long long dbg[8];   // k_map<COUNT_WORK=1> only: loop iterations, lanes walking, seed stages, lanes re-seeding, ...
+  unsigned long long n_live;   // whole-run scope: unique read_keys in the table right now (every insert path counts its new keys, one atomic per warp)
 };
 
 // internal per-read record (32 B)

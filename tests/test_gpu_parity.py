@@ -542,6 +542,37 @@ def test_hbm_resident_kernel_variant_on_a_small_library(c2_built, monkeypatch):
         assert w[k] == ref["work"][k], (k, w[k], ref["work"][k])
 
 
+def test_bulk_copy_pack_variant(c2_built, monkeypatch):
+    """NB_PACK_BULK=1 routes ASCII batches through the staged K0 (cp.async.bulk into shared memory, 2-bit image, word cut):
+    same per-read / per-pair records and counts as the direct kernel, on ragged reads (empty, 1 base, 1024 bases), reverse
+    complement flags, lower case and non-ACGT letters, single and paired, chunk boundaries that are not block multiples."""
+    L, built = c2_built
+    ocfg, oref, lib, ix, o, _ = built[""]
+    o.set_config(**ocfg)
+    seqs = L.sequences()
+    t = seqs[23]
+    reads = ["", "A", t[:39], t[:40], t[100:250], t[100:250].lower(), t[100:180] + "N" + t[181:250], "NRYKM" * 30, "ACGT" * 40, t[:1024], t[-150:], "G" * 29 + t[200:321]] * 7
+    r1, o1 = orc.pack_reads(reads)
+    r2, o2 = orc.pack_reads([r[::-1] for r in reads])
+    rng = np.random.default_rng(11)
+    f1 = (rng.random(len(reads)) < 0.4).astype(np.uint8) * nb.FLAG_REVCOMP
+    f2 = (rng.random(len(reads)) < 0.4).astype(np.uint8) * nb.FLAG_REVCOMP
+    a1, b1, a2, b2 = synth.pairs(L, 900_000, 20_011, paired=True)
+    for args, kw in (((r1, o1), dict(flags1=f1)), ((r1, o1, r2, o2), dict(flags1=f1, flags2=f2)), ((a1, b1, a2, b2), {}), ((a1, b1), {})):
+        out = []
+        for bulk in ("0", "1"):
+            monkeypatch.setenv("NB_PACK_BULK", bulk)
+            ctx = nb.Context(ix, lib, max_batch_pairs=6_007)
+            rr, _ = ctx.align_batch(*args, want_reads=True, **kw)
+            out.append((rr.tobytes(), ctx.counts()["rows"]))
+            ctx.close()
+        assert out[0] == out[1]
+    monkeypatch.setenv("NB_PACK_BULK", "1")
+    ctx = nb.Context(ix, lib)
+    compare(ctx, o, ocfg, a1, b1, a2, b2)        # and the staged kernel against the oracle directly
+    ctx.close()
+
+
 # ------------------------------------------------------------------ packed input encodings (nb_batch.encoding)
 @pytest.mark.parametrize("enc", ["2bit", "bam4"])
 @pytest.mark.parametrize("read_len", [150, 151, 45])
@@ -561,14 +592,22 @@ def test_packed_encodings_equal_the_ascii_path(c2_built, enc, read_len):
     flags1 = (rng.random(n) < 0.3).astype(np.uint8) * nb.FLAG_REVCOMP
     flags2 = (rng.random(n) < 0.3).astype(np.uint8) * nb.FLAG_REVCOMP
     ctx = nb.Context(ix, lib, max_batch_pairs=7_001)       # chunk boundaries at arbitrary base offsets too
+    def dense(pairs):   # nb_pair_result.callset is a dictionary SLOT (which of two colliding callsets gets which slot is a race): compare callset ids
+        p = pairs.copy()
+        s2c = ctx.counts_raw()["slot_to_callset"]
+        has = p["callset"] != 0xFFFFFFFF
+        p["callset"][has] = s2c[p["callset"][has]]
+        return p
     ra, pa = ctx.align_batch(r1, o1, r2, o2, flags1=flags1, flags2=flags2, want_reads=True, want_pairs=True)
     ca = ctx.counts()["rows"]
+    pa = dense(pa)
     f = nb.encode_2bit if enc == "2bit" else nb.encode_bam4
     code = nb.NB_SEQ_2BIT if enc == "2bit" else nb.NB_SEQ_BAM4
     p1, p2 = f(r1, o1), f(r2, o2)
     ctx.reset()
     rb, pb = ctx.align_batch(p1, o1, p2, o2, flags1=flags1, flags2=flags2, want_reads=True, want_pairs=True, encoding=code)
     cb = ctx.counts()["rows"]
+    pb = dense(pb)
     assert ra.tobytes() == rb.tobytes() and pa.tobytes() == pb.tobytes() and ca == cb and (len(ca) > 100 or read_len < 50)   # (45-base reads never reach score_threshold 50)
     if read_len == 150 and enc == "2bit":    # and the ASCII path itself is the oracle's (unflagged reads)
         ctx.reset()
