@@ -413,9 +413,11 @@ def run_c3(env, args):
         lib_comm(ctx, nb, torch, dist, rank, world)
 
     def finish():
+        # the row columns (5 M rows here) are read as views of the library's pinned buffer, as a C host would: they stay valid
+        # until the next finalize, so every use below happens before the next step
         if world > 1:
-            return ctx.merge_scoped(n_cells)   # nb_merge_scoped: dictionaries all-gathered, per-cell tables summed by one dense all-reduce
-        return ctx.counts_raw()
+            return ctx.merge_scoped(n_cells, copy=False)   # nb_merge_scoped: dictionaries all-gathered, per-cell tables summed by one dense all-reduce
+        return ctx.counts_raw(copy=False)
 
     def step_device():
         ctx.reset()
@@ -440,13 +442,14 @@ def run_c3(env, args):
         step_device()
     ctx.kernel_stats(reset=True)
     ms_dev, raw_dev = timed(env, step_device, args.steps)
+    td = table(raw_dev)          # (copies: the views die with the next finalize)
     ks = ctx.kernel_stats(reset=True)
     step_host()
     ms_host, raw_host = timed(env, step_host, args.steps)
+    th = table(raw_host)
     if rank != 0:
         ctx.close()
         return None
-    td, th = table(raw_dev), table(raw_host)
     assert all(np.array_equal(a, b) for a, b in zip(td, th)), "C3: host-fed and device-resident runs disagree"
     total = n * world
     h2d = int(u["off"][-1]) * 2 + n * (8 + 4 + 4 + 2)

@@ -418,17 +418,22 @@ class Context:
         raw = self.counts_raw()
         return self.decode_counts(raw)
 
-    def counts_raw(self, rows=True):
+    def counts_raw(self, rows=True, copy=True):
         """nb_counts_finalize -> numpy copies of the C arrays (group indices, no strings).  rows=False leaves the row
-        columns out (a multi-GPU host that reduces them on the device, counts_device_rows, has no use for host copies)."""
+        columns out (a multi-GPU host that reduces them on the device, counts_device_rows, has no use for host copies).
+        copy=False returns views of the library's buffers instead: valid until the next finalize / reset / close, as the C ABI
+        says (a scoped job has millions of rows: copying them in numpy costs more than the library's whole finalize)."""
         c = Counts()
         _ck(lib().nb_counts_finalize(self.h, C.byref(c)))
-        return self._raw(c, rows)
+        return self._raw(c, rows, copy)
 
     @staticmethod
-    def _raw(c, rows=True):
+    def _raw(c, rows=True, copy=True):
         def arr(p, n, dt):
-            return np.ctypeslib.as_array(p, (n,)).copy() if n else np.zeros(0, dt)
+            if not n:
+                return np.zeros(0, dt)
+            a = np.ctypeslib.as_array(p, (n,))
+            return a.copy() if copy else a
         n_items = int(c.callset_off[c.n_callsets]) if c.n_callsets else 0
         nr = c.n_rows if rows else 0
         return dict(row_scope=arr(c.row_scope, nr, np.uint32), row_callset=arr(c.row_callset, nr, np.uint32),
@@ -457,11 +462,11 @@ class Context:
         _ck(lib().nb_merge_whole_run(self.h, C.byref(c)))
         return self._raw(c)
 
-    def merge_scoped(self, n_cells):
+    def merge_scoped(self, n_cells, copy=True):
         """nb_merge_scoped -> per-cell rows of the whole job (row_scope = cell id), identical on every rank."""
         c = Counts()
         _ck(lib().nb_merge_scoped(self.h, int(n_cells), C.byref(c)))
-        return self._raw(c)
+        return self._raw(c, True, copy)
 
     def counts_device_rows(self):
         """(row_scope, row_callset, row_count) of the last finalize as objects with __cuda_array_interface__ (zero copy)."""

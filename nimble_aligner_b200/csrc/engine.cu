@@ -68,6 +68,7 @@ struct nb_ctx {
   nb_config hcfg; DevCfg dcfg; DevIndex dix; DevLib dlib;
   // index + library device copies
   DBuf d_ptab, d_bloom, d_unitig, d_node, d_walk, d_ledge, d_coloff, d_colids, d_colmeta, d_rowfid, d_rowrev, d_rowof, d_featgroup, d_ent, d_ls, d_qp, d_mincov;
+  DBuf d_rowuoff, d_rowupos, d_rowother, d_rowgroup;   // per-row tables of the pair stage (kernels.cuh DevLib)
   // options
   u64 max_batch_pairs = 1u << 20, arena_entries = 1u << 24, cs_slots = 1u << 18, key_slots = 1u << 22, agg_slots = 1u << 20;
   int count_work = 0; u32 min_read_len = 40;  // MIN_READ_LENGTH, src/align.rs:18 (tests pass 12, src/align.rs:1066)
@@ -232,6 +233,24 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   }
   up(upload(c->d_coloff, index->col_off, s)); up(upload(c->d_colids, index->col_ids, s)); up(upload(c->d_colmeta, index->col_meta, s));
   up(upload(c->d_rowfid, lib->row_fid, s)); up(upload(c->d_rowrev, lib->row_rev, s)); up(upload(c->d_rowof, lib->row_of, s)); up(upload(c->d_featgroup, lib->feat_group, s));
+  {  // per row: its component list (offset in col_ids, position in it), its other orientation, its roll-up group
+    const u32 nr = lib->n_rows();
+    std::vector<u32> uoff(nr, NONE32), other(nr, NONE32), group(nr, NONE32); std::vector<u8> upos(nr, 0);
+    for (size_t col = 0; 4 * col + 3 < index->col_meta.size(); col++) {
+      const u32 uo = index->col_meta[4 * col], us = index->col_meta[4 * col + 1];
+      if (!us || (size_t)uo + us > index->col_ids.size()) continue;
+      const u32 first = index->col_ids[uo];
+      if (first < nr && uoff[first] == uo) continue;                      // this component's list was handled through another of its colours
+      for (u32 k = 0; k < us; k++) { const u32 row = index->col_ids[uo + k]; if (row < nr) { uoff[row] = uo; upos[row] = (u8)k; } }
+    }
+    for (u32 r = 0; r < nr && r < lib->row_fid.size(); r++) {
+      const u32 f = lib->row_fid[r]; const size_t o = 2 * (size_t)f + (1 - (lib->row_rev[r] ? 1 : 0));
+      if (o < lib->row_of.size()) other[r] = lib->row_of[o];
+      if (f < lib->feat_group.size()) group[r] = lib->feat_group[f];
+    }
+    up(upload(c->d_rowuoff, uoff, s)); up(upload(c->d_rowupos, upos, s)); up(upload(c->d_rowother, other, s)); up(upload(c->d_rowgroup, group, s));
+    if (rc == NB_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = fail(NB_ERR_CUDA, "library table upload failed");   // the vectors die here
+  }
   {  // entropy terms f*log2(f), f = c/n, for every read length n <= ENT_NMAX (src/utils.rs:96-119)
     const int N = nbk::ENT_NMAX;
     std::vector<double> ent((size_t)(N + 1) * (N + 2) / 2, 0.0);
@@ -245,6 +264,7 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
   c->dix.node = (const uint4*)c->d_node.p; c->dix.walk = (const uint4*)c->d_walk.p;
   c->dix.col_off = (const u32*)c->d_coloff.p; c->dix.col_ids = (const u32*)c->d_colids.p; c->dix.col_meta = (const uint4*)c->d_colmeta.p;
   c->dlib.row_fid = (const u32*)c->d_rowfid.p; c->dlib.row_rev = (const u8*)c->d_rowrev.p; c->dlib.row_of = (const u32*)c->d_rowof.p; c->dlib.feat_group = (const u32*)c->d_featgroup.p; c->dlib.n_rows = lib->n_rows();
+  c->dlib.row_uoff = (const u32*)c->d_rowuoff.p; c->dlib.row_upos = (const u8*)c->d_rowupos.p; c->dlib.row_other = (const u32*)c->d_rowother.p; c->dlib.row_group = (const u32*)c->d_rowgroup.p;
   rc = apply_config(c, lib->cfg);
   if (rc != NB_OK) { nb_ctx_free(c); return rc; }
   *out = c;
@@ -256,7 +276,7 @@ void nb_ctx_free(nb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->cstream) cudaStreamSynchronize(c->cstream);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DBuf* all[] = {&c->d_ptab, &c->d_bloom, &c->d_node, &c->d_walk, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup,
+  DBuf* all[] = {&c->d_ptab, &c->d_bloom, &c->d_node, &c->d_walk, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup, &c->d_rowuoff, &c->d_rowupos, &c->d_rowother, &c->d_rowgroup,
                  &c->d_ent, &c->d_ls, &c->d_qp, &c->d_mincov, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
                  &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].len[0], &c->stg[0].len[1], &c->stg[0].scope, &c->stg[0].cell,
                  &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].len[0], &c->stg[1].len[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded, &c->d_rowwork, &c->d_rowout, &c->d_dense};

@@ -248,23 +248,65 @@ __global__ void __launch_bounds__(256) k_pack_enc(BatchDev b) {
 }
 
 // ------------------------------------------------------------------------------------------------ K1 trim (maxinfo)
+// maxinfo, src/align.rs:873-925: position of the LAST maximum of (double)(ls[i] + sum_{j<=i} qp[q_j]) over the read.
+// Thread per read; the quality row is read as aligned 16-byte vectors (it starts at an arbitrary byte), the two tables live in
+// shared memory.  The reference compares f64 conversions of the i64 scores (`score as f64 >= max_score`): conversion is
+// monotonic, so s >= best (integers) already decides "true", and s < best can only still compare equal after rounding when the
+// two are within one ulp of 2^63 — only then are the doubles compared.  `best` is the score of the latest update, so
+// (double)best is always the running max_score.
 __global__ void __launch_bounds__(256) k_trim(BatchDev b, Tables t) {
-  u32 ri = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ri >= b.n_reads) return;
-  u32 side = b.sides == 2 ? (ri & 1) : 0; u64 p = b.sides == 2 ? (ri >> 1) : ri;
+  __shared__ i64 s_ls[1024], s_qp[256];
+  for (u32 i = threadIdx.x; i < 1024; i += blockDim.x) s_ls[i] = i < 1000 ? t.ls[i] : 0;
+  s_qp[threadIdx.x] = t.qp[min(threadIdx.x, 60u)];          // indexed by the raw byte (blockDim.x == 256): qualities above 60 count as 60
+  __syncthreads();
+  // thread -> read: all sequence-side reads first, then all mates, so that a warp works on one side (its quality rows are
+  // neighbours in one buffer) and the warps of a side whose reads are all SKIP_ALIGN dummies retire at once
+  const u32 tix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tix >= b.n_reads) return;
+  const u32 half = b.n_reads / b.sides, side = b.sides == 2 ? tix / half : 0u; const u64 p = b.sides == 2 ? tix - side * half : tix;
+  const u32 ri = (u32)(p * b.sides + side);
   if (b.q[side] == nullptr) return;
-  u64 o0 = b.off[side][p]; u32 len = b.len_full[ri];        // written by k_pack (packed encodings may carry explicit lengths)
-  bool rc = b.flags[side] != nullptr && (b.flags[side][p] & 2);
-  const u8* q = b.q[side] + o0;
-  i64 acc = 0; double max_score = -DBL_MAX; u32 pos = 0;
-  for (u32 i = 0; i < len; i++) {
-    u32 qq = rc ? q[len - 1 - i] : q[i];
-    if (qq > 60) qq = 60;
-    acc += t.qp[qq];
-    i64 score = (i < 1000 ? t.ls[i] : 0) + acc;
-    if ((double)score >= max_score) { max_score = (double)score; pos = i + 1; }
+  if (b.flags[side] != nullptr && (b.flags[side][p] & 1)) return;       // SKIP_ALIGN: the reference never trims (nor aligns) these, src/align.rs:527-528
+  const u64 o0 = b.off[side][p]; const u32 len = b.len_full[ri];        // written by k_pack (packed encodings may carry explicit lengths)
+  const bool rc = b.flags[side] != nullptr && (b.flags[side][p] & 2);
+  const uintptr_t a0 = (uintptr_t)(b.q[side] + o0), a1 = a0 + len;
+  i64 acc = 0, best = INT64_MIN; u32 pos = 0, i = 0;
+  auto step = [&](u32 qq) {
+    acc += s_qp[qq];
+    const i64 sc = s_ls[i] + acc;
+    i++;
+    bool upd = sc >= best;
+    if (!upd && best - sc <= 4096) upd = (double)sc >= (double)best;     // (never taken for scores below 2^53)
+    best = upd ? sc : best; pos = upd ? i : pos;
+  };
+  if (len) {
+    const uintptr_t c0 = a0 & ~(uintptr_t)15, c1 = (a1 - 1) & ~(uintptr_t)15;      // first and last aligned chunk
+    if (!rc) {
+      for (uintptr_t c = c0; c <= c1; c += 16) {
+        const uint4 v = __ldg((const uint4*)c); const u32 w[4] = {v.x, v.y, v.z, v.w};
+        if (c >= a0 && c + 16 <= a1) {
+#pragma unroll
+          for (int k = 0; k < 16; k++) step((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; k++) if (c + k >= a0 && c + k < a1) step((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+        }
+      }
+    } else {
+      for (uintptr_t c = c1;; c -= 16) {
+        const uint4 v = __ldg((const uint4*)c); const u32 w[4] = {v.x, v.y, v.z, v.w};
+        if (c >= a0 && c + 16 <= a1) {
+#pragma unroll
+          for (int k = 15; k >= 0; k--) step((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+        } else {
+#pragma unroll
+          for (int k = 15; k >= 0; k--) if (c + k >= a0 && c + k < a1) step((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+        }
+        if (c == c0) break;
+      }
+    }
   }
-  u32 r = (pos < 1 || max_score == 0.0) ? 0u : min(pos, len);
+  const u32 r = (pos < 1 || best == 0) ? 0u : min(pos, len);      // max_score == 0.0 <=> best == 0
   b.len_trim[ri] = r;
 }
 
@@ -386,16 +428,17 @@ __device__ __forceinline__ void cmp_bwd(const u64* U, u64 uhi, const ReadView& r
 #include "kmap.cuh"
 
 // ------------------------------------------------------------------------------------------------ K3 pair
-struct EcView { const u32* list; u64 mask; u32 lsize; u32 n; bool big; };
+struct EcView { const u32* list; u64 mask; u32 lsize; u32 n; bool big; bool uni; u32 ref32; };
 __device__ __forceinline__ EcView make_view(const ReadRes& r, const DevIndex& ix, const Tables& t) {
-  EcView e; e.n = 0; e.list = nullptr; e.mask = 0; e.lsize = 0; e.big = false;
+  EcView e; e.n = 0; e.list = nullptr; e.mask = 0; e.lsize = 0; e.big = false; e.uni = false; e.ref32 = 0;
   if (!((r.hdr >> 8) & 1)) return e;   // only passing alignments contribute an equivalence class (src/align.rs:561-572)
-  e.big = (r.hdr >> 9) & 1; e.n = r.ec_len; e.lsize = r.bsize; e.mask = r.mask;
+  e.big = (r.hdr >> 9) & 1; e.uni = (r.hdr >> 11) & 1; e.n = r.ec_len; e.lsize = r.bsize; e.mask = r.mask; e.ref32 = (u32)r.ref;
   e.list = e.big ? (t.arena + r.ref) : (ix.col_ids + r.ref);
   return e;
 }
-__device__ __forceinline__ bool ec_has(const EcView& e, u32 x) {
+__device__ __forceinline__ bool ec_has(const EcView& e, const DevLib& L, u32 x) {
   if (e.n == 0 || x == NONE32) return false;
+  if (e.uni) return L.row_uoff[x] == e.ref32 && ((e.mask >> L.row_upos[x]) & 1);   // bitmap over a component list: two loads, no search
   u32 lo = 0, hi = e.lsize;
   while (lo < hi) { u32 mid = (lo + hi) >> 1; if (e.list[mid] < x) lo = mid + 1; else hi = mid; }
   if (lo >= e.lsize || e.list[lo] != x) return false;
@@ -409,9 +452,8 @@ template <class F> __device__ __forceinline__ void ec_each(const EcView& e, F f)
 // membership after filter_read_calls_with_orientation (src/align.rs:144-171): a feature called in both orientations
 // by one mate is dropped from that mate's list
 __device__ __forceinline__ bool in_side(const EcView& e, const DevLib& L, u32 row) {
-  if (row == NONE32 || !ec_has(e, row)) return false;
-  u32 other = L.row_of[2 * (u64)L.row_fid[row] + (1 - L.row_rev[row])];
-  return !ec_has(e, other);
+  if (row == NONE32 || !ec_has(e, L, row)) return false;
+  return !ec_has(e, L, L.row_other[row]);
 }
 
 struct GroupList {
@@ -500,7 +542,7 @@ __device__ __forceinline__ bool pair_one(const BatchDev& b, const DevIndex& ix, 
   // ---- require_valid_pair, src/align.rs:582-588 + filter_pair 732-760
   if (paired && cfg.require_valid_pair) {
     bool bad = e1.n == 0 || e2.n == 0 || e1.n != e2.n;
-    if (!bad) ec_each(e1, [&](u32 x) { if (!ec_has(e2, x)) { bad = true; return false; } return true; });
+    if (!bad) ec_each(e1, [&](u32 x) { if (!ec_has(e2, L, x)) { bad = true; return false; } return true; });
     if (bad) { out.fr1 = out.fr2 = R_NOT_MATCHING_PAIR; e1.n = e2.n = 0; }
   }
   u32 cs = CS_NONE;
@@ -530,12 +572,13 @@ __device__ __forceinline__ bool pair_one(const BatchDev& b, const DevIndex& ix, 
   };
   auto feat_in_b = [&](u32 f) -> bool {
     u32 rf = L.row_of[2 * (u64)f], rr_ = L.row_of[2 * (u64)f + 1];
-    return (ec_has(e2, rf) && qual_b(rf)) || (ec_has(e2, rr_) && qual_b(rr_));
+    return (ec_has(e2, L, rf) && qual_b(rf)) || (ec_has(e2, L, rr_) && qual_b(rr_));
   };
   u32 T = max(cfg.discard_multi_hits, cfg.max_hits);
   GroupList gl; gl.n = 0; gl.limit = T + 1; gl.dedup = !cfg.no_dedup; gl.sat = false;
   bool feat_missing = false;
   auto add_feat = [&](u32 f) { u32 g = L.feat_group[f]; if (g == NONE32) { feat_missing = true; return; } gl.add(g); };
+  auto add_row = [&](u32 row) { u32 g = L.row_group[row]; if (g == NONE32) { feat_missing = true; return; } gl.add(g); };   // = add_feat(row_fid[row])
   bool use_intersection = false;
   if (cfg.intersect_level != 0) {   // get_intersecting_reads 763-785 (array_tool Intersect: unique(A) kept when in B)
     ec_each(e1, [&](u32 row) { if (qual_a(row) && feat_in_b(L.row_fid[row])) { use_intersection = true; return false; } return true; });
@@ -543,8 +586,8 @@ __device__ __forceinline__ bool pair_one(const BatchDev& b, const DevIndex& ix, 
   if (use_intersection) {
     ec_each(e1, [&](u32 row) { if (qual_a(row) && feat_in_b(L.row_fid[row])) add_feat(L.row_fid[row]); return !gl.sat; });
   } else if (cfg.intersect_level != 2) {   // get_all_calls 788-796 (concat; duplicates collapse in the roll-up unless nt_sequence)
-    ec_each(e1, [&](u32 row) { if (qual_a(row)) add_feat(L.row_fid[row]); return !gl.sat; });
-    ec_each(e2, [&](u32 row) { if (qual_b(row)) add_feat(L.row_fid[row]); return !gl.sat; });
+    ec_each(e1, [&](u32 row) { if (qual_a(row)) add_row(row); return !gl.sat; });
+    ec_each(e2, [&](u32 row) { if (qual_b(row)) add_row(row); return !gl.sat; });
   }
   if (feat_missing) atomicOr(&t.ctr->err, (unsigned)E_FEATURE);
   // roll-up + discard_multi_hits + max hits, src/align.rs:229-242, 842-848
@@ -637,27 +680,29 @@ __global__ void __launch_bounds__(256) k_resolve(BatchDev b, Tables t) {
 // so a block first counts them in a shared-memory table and adds each (callset, count) to the global table once
 // (7 M same-address global atomics per 10 M-pair job otherwise: the kernel was atomics-bound at 0.8 TB/s).  Scoped
 // batches have about as many (cell, callset) rows as votes and go to the global table directly.
-__device__ __forceinline__ void agg_add(const Tables& t, unsigned long long ak, unsigned long long n) {
+// returns 1 when the call created the (cell, callset) row: the caller adds those up and bumps Counters::n_agg once per
+// block (a scoped batch creates about one row per two votes — that many atomics on ONE address were most of k_fold's time)
+__device__ __forceinline__ u32 agg_add(const Tables& t, unsigned long long ak, unsigned long long n) {
   u64 h = mix64(ak) & t.agg_mask;
   for (u64 probes = 0; probes <= t.agg_mask; probes++) {
     unsigned long long old = atomicCAS(t.agg_key + h, 0ULL, ak);
-    if (old == 0ULL) atomicAdd(&t.ctr->n_agg, 1ULL);
-    if (old == 0ULL || old == ak) { atomicAdd(t.agg_cnt + h, n); return; }
+    if (old == 0ULL || old == ak) { atomicAdd(t.agg_cnt + h, n); return old == 0ULL ? 1u : 0u; }
     h = (h + 1) & t.agg_mask;
   }
   atomicOr(&t.ctr->err, (unsigned)E_AGG_FULL);
+  return 0u;
 }
 constexpr int FOLD_S = 2048;   // shared-memory vote table entries per block (24 KB)
 __global__ void __launch_bounds__(256) k_fold(Tables t, const u32* cell_of_pair, u64 order_base, u64 slots_per_block) {
   __shared__ unsigned long long s_key[FOLD_S];
   __shared__ u32 s_cnt[FOLD_S];
-  __shared__ u32 s_occ;
+  __shared__ u32 s_occ, s_new;
   const bool local = cell_of_pair == nullptr;
   if (local) for (u32 i = threadIdx.x; i < FOLD_S; i += blockDim.x) { s_key[i] = 0ULL; s_cnt[i] = 0; }
-  if (threadIdx.x == 0) s_occ = 0;
+  if (threadIdx.x == 0) { s_occ = 0; s_new = 0; }
   __syncthreads();
   u64 lo = blockIdx.x * slots_per_block, hi = min(lo + slots_per_block, t.key_mask + 1);
-  u32 nocc = 0;
+  u32 nocc = 0, nnew = 0;
   for (u64 idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
     ulonglong2 k = t.key[idx];
     if (k.x == 0 && k.y == 0) continue;
@@ -675,13 +720,17 @@ __global__ void __launch_bounds__(256) k_fold(Tables t, const u32* cell_of_pair,
         h = (h + 1) & (FOLD_S - 1);
       }
     }
-    if (!done) agg_add(t, ak, 1ULL);
+    if (!done) nnew += agg_add(t, ak, 1ULL);
   }
   for (int o = 16; o; o >>= 1) nocc += __shfl_xor_sync(0xFFFFFFFFu, nocc, o);
   if ((threadIdx.x & 31) == 0 && nocc) atomicAdd(&s_occ, nocc);
   __syncthreads();
   if (threadIdx.x == 0 && s_occ) atomicAdd(&t.ctr->n_keys, (unsigned long long)s_occ);
-  if (local) for (u32 i = threadIdx.x; i < FOLD_S; i += blockDim.x) if (s_key[i]) agg_add(t, s_key[i], (unsigned long long)s_cnt[i]);
+  if (local) for (u32 i = threadIdx.x; i < FOLD_S; i += blockDim.x) if (s_key[i]) nnew += agg_add(t, s_key[i], (unsigned long long)s_cnt[i]);
+  for (int o = 16; o; o >>= 1) nnew += __shfl_xor_sync(0xFFFFFFFFu, nnew, o);
+  if ((threadIdx.x & 31) == 0 && nnew) atomicAdd(&s_new, nnew);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) atomicAdd(&t.ctr->n_agg, (unsigned long long)s_new);
 }
 
 // ------------------------------------------------------------------------------------------------ exports
@@ -871,7 +920,7 @@ __global__ void __launch_bounds__(256) k_merge_import_counts(Tables t, const u64
   if (idx >= n) return;
   const u64 tag = blk[2 + 2 * idx];
   u32 h = (u32)(tag >> 24) & t.cs_mask;
-  for (u32 probes = 0; probes <= t.cs_mask; probes++) { u64 tg = t.cs_tag[h]; if (tg == tag) { agg_add(t, (unsigned long long)h + 1ULL, blk[3 + 2 * idx]); return; } if (tg == 0) break; h = (h + 1) & t.cs_mask; }
+  for (u32 probes = 0; probes <= t.cs_mask; probes++) { u64 tg = t.cs_tag[h]; if (tg == tag) { if (agg_add(t, (unsigned long long)h + 1ULL, blk[3 + 2 * idx])) atomicAdd(&t.ctr->n_agg, 1ULL); return; } if (tg == 0) break; h = (h + 1) & t.cs_mask; }
   atomicOr(&t.ctr->err, (unsigned)E_CS_FULL);
 }
 // scoped merge: (cell, callset slot) counts -> dense [cells x callsets] table by the job-wide callset numbering, and back

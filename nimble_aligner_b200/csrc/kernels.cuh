@@ -40,7 +40,14 @@ struct DevIndex {
   const u32* col_off; const u32* col_ids;
   const uint4* col_meta;  // {uni_off, uni_size (0: none), mask_lo, mask_hi} per colour (host.hpp nb_index::col_meta)
 };
-struct DevLib { const u32* row_fid; const u8* row_rev; const u32* row_of; const u32* feat_group; u32 n_rows; };
+struct DevLib {
+  const u32* row_fid; const u8* row_rev; const u32* row_of; const u32* feat_group; u32 n_rows;
+  // per row, derived at context creation so that the pair stage answers "is row x in this class" and "which row is x's other
+  // orientation" with one load each instead of a binary search / three dependent loads:
+  const u32* row_uoff; const u8* row_upos;   // the component (universe) list the row belongs to: its offset in col_ids (NONE32: none) and the row's position in it
+  const u32* row_other;                      // row_of[2 * fid + (1 - rev)]
+  const u32* row_group;                      // feat_group[row_fid[row]]
+};
 struct DevCfg {
   double score_percent; u32 score_threshold; u32 num_mismatches;
   int discard_nonzero_mismatch, discard_multiple_matches, require_valid_pair, intersect_level, strand_filter, no_dedup;
@@ -59,7 +66,7 @@ struct Counters {
 
 // internal per-read record (32 B)
 struct ReadRes {
-  u32 hdr;        // reason | pass<<8 | big<<9 | skip<<10
+  u32 hdr;        // reason | pass<<8 | big<<9 | skip<<10 | uni<<11 (the class is a bitmap over a component list)
   u16 score, mm;
   u32 ec_len;     // elements in the raw equivalence class
   u32 bsize;      // mask mode: size of the base colour list

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(128, NB_WALK_MINB) k_walk(BatchDev b, DevIndex
           else if (mm > cfg.num_mismatches) reason = R_ABOVE_MM;
           else reason = R_SUCCESS | (1u << 8);
         } else reason = R_SCORE_BELOW;
-        rr.hdr = reason | (acc.big ? (1u << 9) : 0u);
+        rr.hdr = reason | (acc.big ? (1u << 9) : 0u) | (acc.uni ? (1u << 11) : 0u);
       }
       b.rres[ri] = rr;
       has = false;
