@@ -297,6 +297,12 @@ int nb_measure_h2d(const int* devices, uint32_t n, uint64_t bytes, uint32_t reps
 int nb_write_fastq_tsv(const char* path, const nb_library* lib, const nb_counts* counts);
 int nb_process_fastq(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,
                      uint32_t n_refs, int strand_filter, int num_cores, int device);
+/* the same on several GPUs of one box: one context per device behind the one feeder, key records routed between the GPUs
+ * inside k_pair, counts merged by nb_merge_whole_run (the reference's parallel shape is N-1 consumers behind one producer,
+ * src/process/bam.rs:183-226; its FASTQ mode is single-threaded).  The routing inboxes are sized from the input size;
+ * NB_ROUTE_RECORDS=<records per peer> overrides, an inbox that fills up fails the job with NB_ERR_OVERFLOW. */
+int nb_process_fastq_devices(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,
+                             uint32_t n_refs, int strand_filter, int num_cores, const int* devices, uint32_t n_devices);
 /* host-only: the records the FASTQ feeder (src/parse/fastq.rs:21-43) hands to the device, one line per record ("SEQ" or
  * "SEQ1<TAB>SEQ2") — parity tests of the parallel plain-text parser against a sequential one.  chunk_bytes: bytes of file per
  * parse task (0 = default 8 MiB); num_cores host threads are split over the input files. */

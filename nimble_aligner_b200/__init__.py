@@ -135,6 +135,7 @@ _SIGS = {
     "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),
     "nb_bam_dump_groups": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "nb_fastq_dump": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_char_p]),
+    "nb_process_fastq_devices": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32]),
     "nb_process_bam": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]),
     "nb_process_fastq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]),
 }
@@ -600,8 +601,14 @@ def call(sequences, mate_sequences, per_sequence_metadata, reference_index, refe
     return get_calls(sequences, mate_sequences, per_sequence_metadata, reference_index, reference, aligner_config, device)
 
 
-def process_fastq(input_files, reference_json_paths, output_paths, strand_filter="unstranded", num_cores=1, device=0):
-    """process::fastq::process behind main.rs's library loop (src/process/fastq.rs:7-30, src/bin/main.rs:95-147)."""
+def process_fastq(input_files, reference_json_paths, output_paths, strand_filter="unstranded", num_cores=1, device=0, devices=None):
+    """process::fastq::process behind main.rs's library loop (src/process/fastq.rs:7-30, src/bin/main.rs:95-147).
+    devices=[...]: one context per listed GPU (nb_process_fastq_devices)."""
+    if devices is not None:
+        dv = (C.c_int * len(devices))(*devices)
+        _ck(lib().nb_process_fastq_devices(_strs(input_files), len(input_files), _strs(reference_json_paths), _strs(output_paths),
+                                           len(reference_json_paths), CHEM[strand_filter], num_cores, dv, len(devices)))
+        return
     _ck(lib().nb_process_fastq(_strs(input_files), len(input_files), _strs(reference_json_paths), _strs(output_paths),
                                len(reference_json_paths), CHEM[strand_filter], num_cores, device))
 

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <vector>
 
 #include <dlfcn.h>
@@ -561,20 +563,41 @@ static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells) {
   if (fstats) ft[2] = fnow();
   // callsets sorted by Vec<String> Ord (utils::sort_score_vector, src/utils.rs:54-59): bytewise on the group names
   const std::vector<u32>& gr = c->lib->group_byte_rank;   // compare ranks, not strings: this sort runs once per job over every callset
-  // sort on a packed prefix (byte ranks of the first two groups) and fall back to the full rows only on ties: at C4 there
-  // are several hundred thousand callsets and this sort is the job's serial tail
-  struct SortKey { u64 k; u32 idx; };
-  std::vector<SortKey> sk(n_cs);
-  for (u32 i = 0; i < n_cs; i++) { const u32* r = &csr[(size_t)i * cw]; u64 a = r[1] > 0 ? (u64)gr[r[4]] + 1 : 0, b = r[1] > 1 ? (u64)gr[r[5]] + 1 : 0; sk[i] = {(a << 32) | b, i}; }
-  auto cs_less = [&](u32 a, u32 b) {
-    const u32* ra = &csr[(size_t)a * cw]; const u32* rb = &csr[(size_t)b * cw];
-    u32 la = ra[1], lb = rb[1];
-    for (u32 i = 0; i < std::min(la, lb); i++) { u32 ga = ra[4 + i], gb = rb[4 + i]; if (ga != gb) return gr[ga] < gr[gb]; }
-    if (la != lb) return la < lb;
-    return ra[0] < rb[0];
-  };
-  std::sort(sk.begin(), sk.end(), [&](const SortKey& x, const SortKey& y) { return x.k != y.k ? x.k < y.k : cs_less(x.idx, y.idx); });
-  std::vector<u32> slots(n_cs); for (u32 i = 0; i < n_cs; i++) slots[i] = sk[i].idx;   // indices into the compact rows
+  // Rank matrix (one row of byte ranks + 1 per callset, zero padded: a shorter list sorts first, as Vec<String> Ord has it),
+  // split into buckets by the first rank, buckets sorted on host threads: a 40k-transcript library yields 74k callsets and
+  // this sort, done serially on the dictionary rows, was 11 of the job's 15 ms.
+  const u32 gc = c->gcap;
+  std::vector<u32> km((size_t)n_cs * gc, 0u);
+  std::vector<u32> slots(n_cs);
+  {
+    const u64 n_groups = gr.size() + 2;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const u32 T = n_cs >= 16384 ? std::min<u32>(16, hw) : 1, NB = T == 1 ? 1 : 8 * T;
+    auto par = [&](auto fn) {   // fn(t) on T threads
+      if (T == 1) { fn(0u); return; }
+      std::vector<std::thread> th; for (u32 t = 0; t < T; t++) th.emplace_back(fn, t);
+      for (auto& x : th) x.join();
+    };
+    std::vector<u32> bucket(n_cs), bcount((size_t)NB * T, 0);
+    par([&](u32 t) {
+      for (u64 q = (u64)n_cs * t / T; q < (u64)n_cs * (t + 1) / T; q++) {
+        const u32* r = &csr[(size_t)q * cw]; u32* k = &km[(size_t)q * gc];
+        for (u32 x = 0; x < r[1] && x < gc; x++) k[x] = gr[r[4 + x]] + 1;
+        const u32 b = (u32)((u64)k[0] * NB / n_groups); bucket[q] = b; bcount[(size_t)t * NB + b]++;
+      }
+    });
+    std::vector<u64> bstart((size_t)NB * T + 1, 0);   // scatter position of (bucket b, thread t): buckets in order, threads in order inside
+    { u64 at = 0; for (u32 b = 0; b < NB; b++) for (u32 t = 0; t < T; t++) { bstart[(size_t)t * NB + b] = at; at += bcount[(size_t)t * NB + b]; } }
+    std::vector<u64> bbeg(NB + 1, 0); for (u32 b = 0; b < NB; b++) bbeg[b] = bstart[b]; bbeg[NB] = n_cs;
+    par([&](u32 t) { for (u64 q = (u64)n_cs * t / T; q < (u64)n_cs * (t + 1) / T; q++) slots[bstart[(size_t)t * NB + bucket[q]]++] = (u32)q; });
+    auto less = [&](u32 a, u32 b) {
+      const u32* ka = &km[(size_t)a * gc]; const u32* kb = &km[(size_t)b * gc];
+      for (u32 x = 0; x < gc; x++) if (ka[x] != kb[x]) return ka[x] < kb[x];
+      return csr[(size_t)a * cw] < csr[(size_t)b * cw];
+    };
+    std::atomic<u32> next{0};
+    par([&](u32) { for (u32 b; (b = next.fetch_add(1)) < NB;) std::sort(slots.begin() + bbeg[b], slots.begin() + bbeg[b + 1], less); });
+  }
   std::vector<u32>& dense = c->slot_dense; dense.assign(c->cs_slots, NONE32);
   for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[4 + k]); c->cs_off.push_back(c->cs_items.size()); }
   if (fstats) ft[3] = fnow();
@@ -1049,7 +1072,10 @@ int nb_merge_whole_run(nb_ctx* c, nb_counts* out) {
   // ---- this rank's inbox: the records the peers' k_pair stored while they aligned (the all-gather above is the barrier that
   // says every peer's last batch is complete), merged with the same "later duplicate wins" rule
   u64 n_in = 0, n_max = 0;
-  for (u32 r = 0; r < W; r++) if (r != c->crank) { if (recv[r] > c->inbox_cap) return fail(NB_ERR_OVERFLOW, "routing inbox region overflow: create the routes with more records_per_peer"); n_in += recv[r]; n_max = std::max(n_max, recv[r]); }
+  // (every rank looks at every rank's counts: an overflow anywhere fails the merge on ALL ranks, before the next collective —
+  // a rank that left alone would leave the others waiting in it)
+  for (u32 r = 0; r < W; r++) for (u32 o = 0; o < W; o++) if (r != o && c->h_hdr[r * nbk::MERGE_HDR1_WORDS + 1 + o] > c->inbox_cap) return fail(NB_ERR_OVERFLOW, "routing inbox region overflow: create the routes with more records_per_peer");
+  for (u32 r = 0; r < W; r++) if (r != c->crank) { n_in += recv[r]; n_max = std::max(n_max, recv[r]); }
   rc = ensure_key_capacity(c, n_in); if (rc) return rc;
   Tables t = make_tables(c);
   const size_t blk_b = (8 * (size_t)nbk::MERGE_HDR1_WORDS + c->merge_cap * (4 + c->gcap) * 4 + 15) & ~(size_t)15;

@@ -115,9 +115,9 @@ void parse_block(FastqReader& r, Segment& g, u64 want) {
 }
 
 struct GzStream : SegStream {
-  FastqReader rd; Segment blocks[4]; std::vector<Segment*> free_q; std::deque<Segment*> filled_q; std::mutex m; std::condition_variable cv; bool stop = false; std::thread th; u64 want;
-  GzStream(u64 w) : want(w) {}
-  bool open(const std::string& p) { if (!rd.open(p)) return false; for (auto& b : blocks) free_q.push_back(&b); th = std::thread([this] { run(); }); return true; }
+  FastqReader rd; std::vector<std::unique_ptr<Segment>> blocks; std::vector<Segment*> free_q; std::deque<Segment*> filled_q; std::mutex m; std::condition_variable cv; bool stop = false; std::thread th; u64 want;
+  GzStream(u64 w, int extra) : want(w) { for (int i = 0; i < 4 + extra; i++) blocks.emplace_back(new Segment()); }   // the consumer holds up to 3 + extra segments
+  bool open(const std::string& p) { if (!rd.open(p)) return false; for (auto& b : blocks) free_q.push_back(b.get()); th = std::thread([this] { run(); }); return true; }
   void run() {
     for (;;) {
       Segment* b;
@@ -206,7 +206,7 @@ struct MapStream : SegStream {
   std::atomic<u64> next_chunk{0}; u64 take = 0, released = 0;   // chunks handed to the consumer / given back by it
   size_t expected = 0; Segment tail;                               // tail: the empty end-of-file segment of an empty input
 
-  bool open(const std::string& p, int threads, size_t chunk_bytes) {
+  bool open(const std::string& p, int threads, size_t chunk_bytes, int extra) {
     fd = ::open(p.c_str(), O_RDONLY); if (fd < 0) return false;
     struct stat st; if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); fd = -1; return false; }
     size = (size_t)st.st_size; chunk = std::max<size_t>(chunk_bytes, 4096);
@@ -217,7 +217,7 @@ struct MapStream : SegStream {
     }
     n_chunks = (size + chunk - 1) / chunk;
     threads = (int)std::max<u64>(1, std::min<u64>((u64)std::max(threads, 1), n_chunks));
-    for (int i = 0; i < 2 * threads + 4; i++) ring.emplace_back(new Slot());
+    for (int i = 0; i < 2 * threads + 4 + extra; i++) ring.emplace_back(new Slot());   // the consumer holds up to 3 + extra segments
     expected = skip_blank(d, size, 0);
     for (int i = 0; i < threads && n_chunks; i++) th.emplace_back([this] { work(); });
     return true;
@@ -272,12 +272,14 @@ struct MapStream : SegStream {
 
 bool is_gzip(const std::string& p) { FILE* f = fopen(p.c_str(), "rb"); if (!f) return false; unsigned char h[2] = {0, 0}; size_t n = fread(h, 1, 2, f); fclose(f); return n == 2 && h[0] == 0x1f && h[1] == 0x8b; }
 
-std::unique_ptr<SegStream> open_stream(const std::string& path, int threads, u64 gz_block_records, size_t chunk_bytes) {
-  if (is_gzip(path)) { std::unique_ptr<GzStream> g(new GzStream(gz_block_records)); if (!g->open(path)) return nullptr; return g; }
+// extra: segments the consumer may hold beyond the usual three (a driver feeding W contexts in turn holds 2 W + 1)
+std::unique_ptr<SegStream> open_stream(const std::string& path, int threads, u64 gz_block_records, size_t chunk_bytes, int extra = 0) {
+  if (is_gzip(path)) { std::unique_ptr<GzStream> g(new GzStream(gz_block_records, extra)); if (!g->open(path)) return nullptr; return g; }
   std::unique_ptr<MapStream> s(new MapStream());
-  if (!s->open(path, threads, chunk_bytes)) return nullptr;
+  if (!s->open(path, threads, chunk_bytes, extra)) return nullptr;
   return s;
 }
+u64 file_bytes(const char* p) { struct stat st; return stat(p, &st) == 0 ? (u64)st.st_size : 0; }
 size_t chunk_bytes_default() { const char* e = getenv("NB_FASTQ_CHUNK"); size_t v = e ? (size_t)strtoull(e, nullptr, 10) : 0; return v ? v : (8u << 20); }
 
 int write_tsv(const std::string& path, const nb_library* lib, const nb_counts& cts) {  // utils::write_to_tsv
@@ -353,58 +355,90 @@ extern "C" int nb_fastq_dump(const char* const* input_files, uint32_t n_inputs, 
   return rc;
 }
 
-// process::fastq::process with the library loop of src/bin/main.rs:95-133 in front of it.
-extern "C" int nb_process_fastq(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,
-                                uint32_t n_refs, int strand_filter, int num_cores, int device) {
+// process::fastq::process with the library loop of src/bin/main.rs:95-133 in front of it, on one or several GPUs.
+// Several devices: one context per GPU behind the one feeder (the reference's shape is N-1 consumers behind one producer,
+// src/process/bam.rs:183-226); batches go to the contexts in turn with their global pair numbers, k_pair routes every
+// read_key record to the GPU that owns the key (peer stores), and nb_merge_whole_run — NCCL inside the library, one host
+// thread per context for the collective calls — leaves the whole job's counts on every context.
+extern "C" int nb_process_fastq_devices(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,
+                                        uint32_t n_refs, int strand_filter, int num_cores, const int* devices, uint32_t n_devices) {
   if (!input_files || !reference_json || !output_paths || n_inputs < 1 || n_inputs > 2 || n_refs < 1) return fail(NB_ERR_INVALID, "need 1-2 inputs and >=1 reference/output pair");
+  if (!devices || n_devices < 1 || n_devices > 16) return fail(NB_ERR_INVALID, "need 1-16 devices");
   const u64 BATCH = 1u << 20;
   const int T = std::max(1, num_cores / (int)n_inputs);
+  const u32 W = n_devices;
   const bool stats = getenv("NB_FASTQ_STATS") != nullptr;   // phase times on stderr
   auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
   for (u32 li = 0; li < n_refs; li++) {
-    nb_library* lib = nullptr; nb_index* ix = nullptr; nb_ctx* ctx = nullptr;
+    nb_library* lib = nullptr; nb_index* ix = nullptr; std::vector<nb_ctx*> ctx(W, nullptr);
     const double t0 = now();
     int rc = nb_library_load_json(reference_json[li], strand_filter, &lib);
     const double t1 = now();
-    if (rc == NB_OK) rc = nb_index_build_gpu(lib, device, std::max(1, num_cores), &ix);   // K5: the CUDA builder (same artefact as nb_index_build)
+    if (rc == NB_OK) rc = nb_index_build_gpu(lib, devices[0], std::max(1, num_cores), &ix);   // K5: the CUDA builder (same artefact as nb_index_build)
     const double t2 = now();
-    if (rc == NB_OK) rc = nb_ctx_create(ix, lib, device, nullptr, &ctx);
-    if (rc == NB_OK) rc = nb_ctx_set_option(ctx, "max_batch_pairs", BATCH);
+    for (u32 d = 0; d < W && rc == NB_OK; d++) { rc = nb_ctx_create(ix, lib, devices[d], nullptr, &ctx[d]); if (rc == NB_OK) rc = nb_ctx_set_option(ctx[d], "max_batch_pairs", BATCH); }
+    if (rc == NB_OK && W > 1) {
+      // inbox regions hold every record a peer sends during the job: sized from the input (a record of a 100-base read is
+      // about 230 bytes of text, gzip packs it about five-fold); NB_ROUTE_RECORDS overrides; a region that fills up fails loudly
+      const char* e = getenv("NB_ROUTE_RECORDS");
+      u64 est = file_bytes(input_files[0]) / 100; if (is_gzip(input_files[0])) est *= 6;
+      const u64 rpp = e ? strtoull(e, nullptr, 10) : est * 2 / ((u64)W * W) + 65536;
+      rc = nb_comm_init_all(ctx.data(), W);
+      for (u32 d = 0; d < W && rc == NB_OK; d++) rc = nb_route_create(ctx[d], W, rpp, nullptr);
+      for (u32 d = 0; d < W && rc == NB_OK; d++) rc = nb_route_attach_ctx(ctx[d], W, d, ctx.data(), 0);
+    }
     const double t3 = now(); u64 n_pairs_fed = 0, n_calls = 0;
     std::unique_ptr<SegStream> s1, s2;
-    if (rc == NB_OK) { s1 = open_stream(input_files[0], T, 1u << 19, chunk_bytes_default()); if (!s1) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[0]); }
-    if (rc == NB_OK && n_inputs > 1) { s2 = open_stream(input_files[1], T, 1u << 19, chunk_bytes_default()); if (!s2) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[1]); }
+    if (rc == NB_OK) { s1 = open_stream(input_files[0], T, 1u << 19, chunk_bytes_default(), 2 * (int)W); if (!s1) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[0]); }
+    if (rc == NB_OK && n_inputs > 1) { s2 = open_stream(input_files[1], T, 1u << 19, chunk_bytes_default(), 2 * (int)W); if (!s2) rc = fail(NB_ERR_IO, std::string("could not open ") + input_files[1]); }
     if (rc == NB_OK) {
       // A segment goes back to its stream once the copies out of it have run: nb_align_batch blocks on the copies of a staging
-      // set before refilling it, so everything submitted before the last two calls is free again (nimble_b200.h).
+      // set before refilling it, so everything a context was given before its last two calls is free again (nimble_b200.h);
+      // with W contexts fed in turn that is everything older than 2 W calls.
       struct Held { SegStream* s; Segment* g; u64 call; };
       std::deque<Held> held; u64 calls = 0;
-      auto release = [&](bool all) { while (!held.empty() && (all || held.front().call + 2 <= calls)) { held.front().s->recycle(held.front().g); held.pop_front(); } };
+      std::vector<u64> fed(W, 0);
+      auto release = [&](bool all) { while (!held.empty() && (all || held.front().call + 2 * W <= calls)) { held.front().s->recycle(held.front().g); held.pop_front(); } };
       rc = consume(s1.get(), s2.get(),
         [&](Segment* a, u64 ka, Segment* b2, u64 kb, u64 m) {
+          const u32 d = (u32)(calls % W);
           nb_batch b; memset(&b, 0, sizeof b);
           b.n_pairs = m; b.location = NB_MEM_HOST; b.max_read_len = std::max<u32>(a->maxlen, b2 ? b2->maxlen : 0);
           b.r1 = a->seq.p; b.r1_off = a->off() + ka;
           if (b2) { b.r2 = b2->seq.p; b.r2_off = b2->off() + kb; }
-          int r = nb_align_batch(ctx, &b, nullptr, nullptr);
-          calls++; release(false); n_pairs_fed += m; n_calls++;
+          int r = NB_OK;
+          if (W > 1) r = nb_route_set_pair_base(ctx[d], n_pairs_fed - fed[d]);   // this batch's pairs are numbered n_pairs_fed.. in the job; the context adds its own count
+          if (r == NB_OK) r = nb_align_batch(ctx[d], &b, nullptr, nullptr);
+          calls++; release(false); n_pairs_fed += m; fed[d] += m; n_calls++;
           return r;
         },
         [&](SegStream* s, Segment* g) { held.push_back({s, g, calls}); release(false); });
-      if (nb_ctx_sync(ctx) != NB_OK && rc == NB_OK) rc = NB_ERR_CUDA;
+      for (u32 d = 0; d < W; d++) if (nb_ctx_sync(ctx[d]) != NB_OK && rc == NB_OK) rc = NB_ERR_CUDA;
       release(true);
     }
     if (s1) s1->finish();
     if (s2) s2->finish();
     const double t4 = now();
-    nb_counts cts;
-    if (rc == NB_OK) rc = nb_counts_finalize(ctx, &cts);
-    if (rc == NB_OK) rc = write_tsv(output_paths[li], lib, cts);
+    std::vector<nb_counts> cts(W);
+    if (rc == NB_OK && W == 1) rc = nb_counts_finalize(ctx[0], &cts[0]);
+    if (rc == NB_OK && W > 1) {   // collective: every context's call must be in flight at the same time
+      std::vector<int> rcs(W, NB_OK); std::vector<std::string> msgs(W); std::vector<std::thread> th;
+      for (u32 d = 0; d < W; d++) th.emplace_back([&, d] { rcs[d] = nb_merge_whole_run(ctx[d], &cts[d]); if (rcs[d] != NB_OK) msgs[d] = nb_last_error(); });
+      for (auto& x : th) x.join();
+      for (u32 d = 0; d < W && rc == NB_OK; d++) if (rcs[d] != NB_OK) rc = fail(rcs[d], msgs[d]);
+    }
+    if (rc == NB_OK) rc = write_tsv(output_paths[li], lib, cts[0]);
     s1.reset(); s2.reset();
-    if (stats) fprintf(stderr, "nb_process_fastq: library %.3f s, index (GPU) %.3f s, context %.3f s, parse+align %.3f s (%llu pairs in %llu calls, %d parser threads per file: %.1f M reads/s), finalize+tsv %.3f s\n",
-                       t1 - t0, t2 - t1, t3 - t2, t4 - t3, (unsigned long long)n_pairs_fed, (unsigned long long)n_calls, T, (double)n_pairs_fed * n_inputs / std::max(t4 - t3, 1e-9) / 1e6, now() - t4);
-    nb_ctx_free(ctx); nb_index_free(ix); nb_library_free(lib);
+    if (stats) fprintf(stderr, "nb_process_fastq: library %.3f s, index (GPU) %.3f s, %u context(s) %.3f s, parse+align %.3f s (%llu pairs in %llu calls, %d parser threads per file: %.1f M reads/s), finalize+tsv %.3f s\n",
+                       t1 - t0, t2 - t1, W, t3 - t2, t4 - t3, (unsigned long long)n_pairs_fed, (unsigned long long)n_calls, T, (double)n_pairs_fed * n_inputs / std::max(t4 - t3, 1e-9) / 1e6, now() - t4);
+    for (u32 d = 0; d < W; d++) nb_ctx_free(ctx[d]);
+    nb_index_free(ix); nb_library_free(lib);
     if (rc != NB_OK) return rc;
   }
   return NB_OK;
+}
+
+extern "C" int nb_process_fastq(const char* const* input_files, uint32_t n_inputs, const char* const* reference_json, const char* const* output_paths,
+                                uint32_t n_refs, int strand_filter, int num_cores, int device) {
+  return nb_process_fastq_devices(input_files, n_inputs, reference_json, output_paths, n_refs, strand_filter, num_cores, &device, 1);
 }

@@ -645,7 +645,10 @@ __device__ __forceinline__ bool pair_one(const BatchDev& b, const DevIndex& ix, 
 // Counters::n_live += the block's new keys: one shared-memory atomic per warp, one global atomic per block.  (A per-warp
 // global atomic issued from inside the divergent pair logic — several convergence groups per warp — cost 1.5 ms per 10 M pairs
 // on that one address.)
-__global__ void __launch_bounds__(128) k_pair(BatchDev b, DevIndex ix, DevLib L, DevCfg cfg, Tables t, Route rt) {
+#ifndef NB_PAIR_MINB
+#define NB_PAIR_MINB 1
+#endif
+__global__ void __launch_bounds__(128, NB_PAIR_MINB) k_pair(BatchDev b, DevIndex ix, DevLib L, DevCfg cfg, Tables t, Route rt) {
   __shared__ u32 s_new;
   if (threadIdx.x == 0) s_new = 0;
   __syncthreads();

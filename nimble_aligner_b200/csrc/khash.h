@@ -29,8 +29,9 @@ NB_HD uint64_t nb_table_size(uint64_t n_kmers) { return (n_kmers * 5 + 7) / 8 + 
 NB_HD uint64_t nb_ptab_buckets(uint64_t n_kmers) { return n_kmers + n_kmers / 4 + 2; }
 // Blocked Bloom prefilter in front of it when the table cannot live in L2: one 64-bit word per k-mer (chosen by g, the
 // high half of nb_khash), k = 2 or 3 bits inside it from h's low bits.
-NB_HD uint64_t nb_bloom_bits(uint32_t h, uint32_t k) {
-  uint64_t m = (1ULL << (h & 63)) | (1ULL << ((h >> 6) & 63));
-  if (k > 2) m |= 1ULL << ((h >> 12) & 63);
-  return m;
-}
+// The bits sit at fixed halves of the word (first and third in the low 32 bits, second in the high 32), so that building
+// and testing them is 32-bit shifts only (a 64-bit variable shift is two instructions on the device, and a probe of an
+// off-target read does nothing but this test).
+NB_HD uint32_t nb_bloom_lo(uint32_t h, uint32_t k) { uint32_t m = 1u << (h & 31); if (k > 2) m |= 1u << ((h >> 12) & 31); return m; }
+NB_HD uint32_t nb_bloom_hi(uint32_t h) { return 1u << ((h >> 6) & 31); }
+NB_HD uint64_t nb_bloom_bits(uint32_t h, uint32_t k) { return (uint64_t)nb_bloom_lo(h, k) | ((uint64_t)nb_bloom_hi(h) << 32); }

@@ -71,8 +71,8 @@ __device__ __forceinline__ bool probe_km(const DevIndex& ix, const ProbePolicy& 
   if (FILTER) {
     const u64* wp = ix.bloom + __umulhi((u32)(hh >> 32), ix.bloom_words);
     const u64 w = HINTS ? ld_u64_hint(wp, pol.last) : __ldg(wp);
-    const u64 need = nb_bloom_bits(h, ix.bloom_k);
-    if ((w & need) != need) return false;
+    const u32 nlo = nb_bloom_lo(h, ix.bloom_k), nhi = nb_bloom_hi(h);
+    if (((u32)w & nlo) != nlo || ((u32)(w >> 32) & nhi) != nhi) return false;
   }
   u32 b = __umulhi(h, ix.n_pbuckets);
   const u64 want = km | (1ULL << 63);
@@ -138,14 +138,16 @@ __global__ void __launch_bounds__(SEED_BLOCK) k_seed(BatchDev b, DevIndex ix, De
     else {
       // shannon_entropy on the (trimmed) read, src/utils.rs:96-119; terms come from a host-built table of
       // f*log2(f) (same libm as the CPU reference), summed in the reference's A,T,C,G order.
-      u32 cC = 0, cG = 0, cT = 0;
+      // C = 01, G = 10, T = 11: popc(low bits) = C + T, popc(high bits) = G + T, popc(both) = T; bases behind the (trimmed)
+      // end are cleared first and so read as A, which is counted from the length
+      u32 pl = 0, ph = 0, cT = 0;
       for (u32 w = 0; w * 32 < qn; w++) {
-        u64 x = qrd.word(w); u32 c = min(32u, qn - w * 32);
-        u64 lo = x & 0x5555555555555555ULL, hi = (x >> 1) & 0x5555555555555555ULL;
-        u64 vm = c < 32 ? ((1ULL << (2 * c)) - 1) & 0x5555555555555555ULL : 0x5555555555555555ULL;
-        cC += __popcll(lo & ~hi & vm); cG += __popcll(hi & ~lo & vm); cT += __popcll(hi & lo & vm);
+        u64 x = qrd.word(w); const u32 c = qn - w * 32;
+        if (c < 32) x &= (1ULL << (2 * c)) - 1;
+        const u64 lo = x & 0x5555555555555555ULL, hi = (x >> 1) & 0x5555555555555555ULL;
+        pl += __popcll(lo); ph += __popcll(hi); cT += __popcll(lo & hi);
       }
-      u32 cA = qn - cC - cG - cT;
+      const u32 cC = pl - cT, cG = ph - cT, cA = qn - pl - ph + cT;
       const double* et = t.ent + (size_t)qn * (qn + 1) / 2;
       double e = 0.0;
       if (cA) e += et[cA];
@@ -186,13 +188,33 @@ __global__ void __launch_bounds__(SEED_BLOCK) k_seed(BatchDev b, DevIndex ix, De
     for (u32 e = tid; e < E; e += SEED_BLOCK) q_best[e] = NONE32;
     if (tid == 0) q_n[cur ^ 1] = 0;
     __syncthreads();
-    for (u32 task = tid; task < (E << lg); task += SEED_BLOCK) {
-      const u32 e = task >> lg, j = task & (S - 1);
-      const u32 pos = q_kp[cur][e] + 3 * j;
-      if (pos <= q_last[cur][e] && j < q_best[e]) {      // (a hit at a smaller seed index already settles this entry)
-        ReadView srd{b.pk + (u64)q_ri[cur][e] * b.W, 1};
+    // two tasks per thread and iteration, their prefilter words requested together: a probe is a chain read words -> hash ->
+    // filter word -> (rarely) bucket, and the kernel waits on that chain (ncu: 12 cycles of long-scoreboard stall per issue)
+    for (u32 task = tid; task < (E << lg); task += 2 * SEED_BLOCK) {
+      u64 km[2], hh[2], fw[2]; bool live2[2]; u32 ee[2], jj[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const u32 tk = task + u * SEED_BLOCK;
+        live2[u] = tk < (E << lg);
+        const u32 e = live2[u] ? tk >> lg : 0u, j = tk & (S - 1);
+        ee[u] = e; jj[u] = j;
+        const u32 pos = q_kp[cur][e] + 3 * j;
+        live2[u] = live2[u] && pos <= q_last[cur][e] && j < q_best[e];      // (a hit at a smaller seed index already settles this entry)
+        km[u] = 0; hh[u] = 0; fw[u] = 0;
+        if (live2[u]) {
+          ReadView srd{b.pk + (u64)q_ri[cur][e] * b.W, 1};
+          km[u] = srd.win(pos) & KMASK; hh[u] = nb_khash(km[u]);
+          const u64* wp = ix.bloom + __umulhi((u32)(hh[u] >> 32), ix.bloom_words);
+          fw[u] = BLOOM ? ld_u64_hint(wp, pol.last) : __ldg(wp);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (!live2[u]) continue;
+        const u32 h = (u32)hh[u], nlo = nb_bloom_lo(h, ix.bloom_k), nhi = nb_bloom_hi(h);
+        if (((u32)fw[u] & nlo) != nlo || ((u32)(fw[u] >> 32) & nhi) != nhi) continue;
         u32 nd, of;
-        if (probe_kmer<BLOOM>(ix, pol, srd, pos, nd, of)) atomicMin(&q_best[e], j);
+        if (probe_km<BLOOM, 0>(ix, pol, km[u], nd, of)) atomicMin(&q_best[ee[u]], jj[u]);
       }
     }
     __syncthreads();

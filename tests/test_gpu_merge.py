@@ -124,3 +124,32 @@ def test_scoped_merge_in_library_sums_the_per_cell_tables(lib2):
         got = {(int(c), tuple(cs)): int(k) for c, cs, k in ctxs[d].decode_counts(raw)["rows"]}
         assert got == want, d
     assert len(want) > 10_000
+
+
+@needs2
+@pytest.mark.parametrize("world", [2, 4])
+def test_fastq_driver_on_several_gpus(tmp_path, world):
+    """nb_process_fastq_devices: one feeder, one context per GPU, key records routed inside k_pair, nb_merge_whole_run called
+    from the C++ driver.  The TSV must be byte-identical to the one-GPU driver's and to the oracle's counts (duplicated pairs
+    land on different GPUs: batches are dealt to the contexts in turn)."""
+    if _n_gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    L = synth.SynthLibrary(seed=1234, n_fam=40, n_all=5, group_on="")
+    obj = L.to_json_obj()
+    (tmp_path / "lib.json").write_text(json.dumps(obj))
+    n = 60_000
+    r1, o1, r2, o2 = synth.pairs(L, 0, n, seed=77, paired=True)
+    synth.write_fastq(str(tmp_path / "r1.fastq"), r1, o1, 1)
+    synth.write_fastq(str(tmp_path / "r2.fastq"), r2, o2, 2)
+    import os
+    os.environ["NB_FASTQ_CHUNK"] = "262144"          # many small batches: every context gets dozens of them
+    try:
+        nb.process_fastq([tmp_path / "r1.fastq", tmp_path / "r2.fastq"], [tmp_path / "lib.json"], [tmp_path / "one.tsv"], num_cores=4)
+        nb.process_fastq([tmp_path / "r1.fastq", tmp_path / "r2.fastq"], [tmp_path / "lib.json"], [tmp_path / "many.tsv"], num_cores=4, devices=list(range(world)))
+    finally:
+        del os.environ["NB_FASTQ_CHUNK"]
+    one, many = (tmp_path / "one.tsv").read_text(), (tmp_path / "many.tsv").read_text()
+    assert one == many and one.count("\n") > 50
+    ocfg, oref = orc.parse_reference_library(obj, "unstranded")
+    ref = orc.Oracle(ocfg, oref).run(r1, o1, r2, o2, threads=4, want_records=False)["scopes"][0]
+    assert one == "feature\tscore\n" + "".join("\t".join(cs) + "\t%d\n" % k for cs, k in ref)
