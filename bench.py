@@ -415,8 +415,8 @@ def run_c3(env, args):
     def finish():
         # the row columns (5 M rows here) are read as views of the library's pinned buffer, as a C host would: they stay valid
         # until the next finalize, so every use below happens before the next step
-        if world > 1:
-            return ctx.merge_scoped(n_cells, copy=False)   # nb_merge_scoped: dictionaries all-gathered, per-cell tables summed by one dense all-reduce
+        if world > 1:   # nb_merge_scoped_sharded: dictionaries all-gathered, per-cell tables summed by one dense reduce-scatter: every rank ends with (and reads back) the rows of its own range of cells
+            return ctx.merge_scoped(n_cells, copy=False, sharded=True)
         return ctx.counts_raw(copy=False)
 
     def step_device():
@@ -447,6 +447,11 @@ def run_c3(env, args):
     step_host()
     ms_host, raw_host = timed(env, step_host, args.steps)
     th = table(raw_host)
+    n_rows_job, n_pairs_job = int(len(td[0])), int(td[2].sum())
+    if world > 1:   # the job's table is the union of the ranks' shards
+        tt = torch.tensor([n_rows_job, n_pairs_job], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tt)
+        n_rows_job, n_pairs_job = int(tt[0].item()), int(tt[1].item())
     if rank != 0:
         ctx.close()
         return None
@@ -454,11 +459,11 @@ def run_c3(env, args):
     total = n * world
     h2d = int(u["off"][-1]) * 2 + n * (8 + 4 + 4 + 2)
     out = {"workload": "C3-shaped: %d 10x-style single-end 91 bp records with raw Phred quals per GPU in %d (UMI,CB) scopes (dummy mates, MAXINFO trim 40:0.9), %d cells, 1k-transcript library; per-cell count table%s"
-                       % (n, len(u["sizes"]), n_cells, (", scopes sharded over %d ranks and the tables merged by nb_merge_scoped (NCCL all-gather + dense all-reduce inside the library)" % world) if world > 1 else ""),
+                       % (n, len(u["sizes"]), n_cells, (", scopes sharded over %d ranks and the tables merged by nb_merge_scoped_sharded (NCCL all-gather + dense reduce-scatter inside the library; every rank reads back its own range of cells)" % world) if world > 1 else ""),
            "value": total / (ms_dev / 1e3), "unit": UNIT, "ms_per_step": ms_dev, "steps": args.steps, "n_gpus": world, "records_per_step": total,
-           "e2e": {"value": total / (ms_host / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 16 * len(td[0]) + 192, "ms_per_step": ms_host,
+           "e2e": {"value": total / (ms_host / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 16 * n_rows_job + 192 * world, "ms_per_step": ms_host,
                    "h2d_gbs": h2d * world / (ms_host / 1e3) / 1e9, "of_h2d_ceiling": (h2d / (ms_host / 1e3) / 1e9) / env.h2d_ceiling if env.h2d_ceiling else None},
-           "count_rows": int(len(td[0])), "counted_pairs": int(td[2].sum()), "gpu_launches": ks["launches"],
+           "count_rows": n_rows_job, "counted_pairs": n_pairs_job, "gpu_launches": ks["launches"],
            "k_map_ms_per_launch": ks["map_ms"] / max(1, ks["map_launches"]), "k_map_reads_per_launch": ks["map_reads"] / max(1, ks["map_launches"])}
     if not args.no_cpu_baseline:
         # ---- parity: per-cell table of the first scopes vs the oracle (string-level restatement of get_calls per scope)

@@ -264,7 +264,8 @@ int nb_route_detach(nb_ctx*);
  *                       job's counts (n_unique_keys = unique read_keys of the whole job), as nb_counts_finalize would on one GPU
  *   nb_merge_scoped     scoped batches (BAM mode; whole scopes shard over ranks, no data-path exchange): dictionaries
  *                       all-gathered, then the per-cell tables are summed with one dense [n_cells x callsets] all-reduce;
- *                       row_scope of `out` = cell id.  n_cells = 1 + the largest cell_id of the job
+ *                       row_scope of `out` = cell id.  n_cells = 1 + the largest cell_id of the job (nb_merge_scoped_sharded:
+ *                       every rank keeps only its own range of cells)
  * Collective calls: every rank of the communicator must make them in the same order. */
 enum { NB_COMM_ID_BYTES = 128 };
 int nb_comm_unique_id(void* id128_out);
@@ -276,6 +277,10 @@ int nb_comm_info(nb_ctx*, uint32_t* world, uint32_t* rank);
 int nb_route_setup(nb_ctx*, uint64_t records_per_peer, uint64_t pair_index_base);
 int nb_merge_whole_run(nb_ctx*, nb_counts* out);
 int nb_merge_scoped(nb_ctx*, uint64_t n_cells, nb_counts* out);
+/* the same with the result left SHARDED over the ranks: a reduce-scatter instead of the all-reduce; rank r's `out` holds the
+ * rows of cells [r * ceil(n_cells / world), (r + 1) * ceil(n_cells / world)) only (callsets numbered alike on every rank), so a
+ * job's rows cross PCIe once, not once per GPU — the shape for a host that writes each cell's rows from one place */
+int nb_merge_scoped_sharded(nb_ctx*, uint64_t n_cells, nb_counts* out);
 
 /* timing of the dominant kernel (seed_walk_map), CUDA events on the launching stream: out[0]=launches, out[1]=total ms,
  * out[2]=reads processed, out[3]=all kernels launched by this ctx since reset */

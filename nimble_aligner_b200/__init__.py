@@ -130,6 +130,7 @@ _SIGS = {
     "nb_route_setup": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "nb_merge_whole_run": (C.c_int, [C.c_void_p, C.POINTER(Counts)]),
     "nb_merge_scoped": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Counts)]),
+    "nb_merge_scoped_sharded": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Counts)]),
     "nb_measure_gather": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]),
     "nb_measure_h2d": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_double)]),
     "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),
@@ -463,10 +464,11 @@ class Context:
         _ck(lib().nb_merge_whole_run(self.h, C.byref(c)))
         return self._raw(c)
 
-    def merge_scoped(self, n_cells, copy=True):
-        """nb_merge_scoped -> per-cell rows of the whole job (row_scope = cell id), identical on every rank."""
+    def merge_scoped(self, n_cells, copy=True, sharded=False):
+        """nb_merge_scoped -> per-cell rows of the whole job (row_scope = cell id), identical on every rank;
+        sharded=True (nb_merge_scoped_sharded): this rank's range of cells only."""
         c = Counts()
-        _ck(lib().nb_merge_scoped(self.h, int(n_cells), C.byref(c)))
+        _ck((lib().nb_merge_scoped_sharded if sharded else lib().nb_merge_scoped)(self.h, int(n_cells), C.byref(c)))
         return self._raw(c, True, copy)
 
     def counts_device_rows(self):

@@ -533,9 +533,11 @@ int nb_last_batch_ecs(nb_ctx* c, uint64_t* ec_off, uint32_t* ec_ids, uint64_t ec
 struct NcclApi;
 static const NcclApi* nccl_api();
 static int dense_allreduce(nb_ctx* c, void* dense, u64 n);
+static int dense_reduce_scatter(nb_ctx* c, void* dense, u64 chunk);
 // dense_cells > 0 (nb_merge_scoped): the (cell, callset) rows of all ranks are summed through a dense [cells x callsets]
-// table (all-reduce over NCCL) before they are read back; 0: this context's own rows
-static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells) {
+// table (all-reduce over NCCL) before they are read back; 0: this context's own rows.  shard: reduce-scatter instead — every
+// rank keeps (and reads back) the rows of its own range of cells only
+static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells, bool shard = false) {
   if (!c || !out) return fail(NB_ERR_INVALID, "null argument");
   CK(cudaSetDevice(c->device));
   memset(out, 0, sizeof *out);
@@ -606,17 +608,25 @@ static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells) {
   if (dense_cells) {
     // ---- scoped multi-GPU merge: after the dictionary exchange every rank numbers the callsets alike (same sort over the
     // same dictionary), so the per-cell tables add up element-wise: scatter -> all-reduce -> rows by a scan (already ordered)
-    const u64 ncs = std::max<u64>(1, slots.size()), nd = dense_cells * ncs;
-    if (nd >= (1ull << 31)) return fail(NB_ERR_UNSUPPORTED, "cells x callsets too large for the dense merge (2^31 entries)");
+    const u32 Wm = (shard && c->comm) ? c->cworld : 1;
+    const u64 cells_per = (dense_cells + Wm - 1) / Wm;                 // sharded: rank r owns cells [r * cells_per, (r + 1) * cells_per)
+    dense_cells = cells_per * Wm;
+    const u64 ncs = std::max<u64>(1, slots.size()), nd_all = dense_cells * ncs;
+    if (nd_all >= (1ull << 31)) return fail(NB_ERR_UNSUPPORTED, "cells x callsets too large for the dense merge (2^31 entries)");
+    u64 nd = nd_all;
     size_t tb = nbk::merge_scan_tmp_bytes(nd);
     CK(c->d_densetab.ensure(nd * 8, s)); CK(c->d_densework.ensure(nd * 16 + tb + 16, s)); CK(c->d_dense.ensure(dense.size() * 4, s));
     CK(cudaMemcpyAsync(c->d_dense.p, dense.data(), dense.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(c->d_densetab.p, 0, nd * 8, s));
     nbk::launch_merge_dense_fill(t, (const u32*)c->d_dense.p, (unsigned long long*)c->d_densetab.p, ncs, dense_cells, s); c->all_launches++;
-    rc = dense_allreduce(c, c->d_densetab.p, nd); if (rc) return rc;
+    const unsigned long long* d_tab = (const unsigned long long*)c->d_densetab.p; u32 cell_base = 0;
+    if (Wm > 1) {   // in place: this rank's chunk of the sums lands where its chunk of the table is
+      nd = cells_per * ncs; cell_base = (u32)(c->crank * cells_per); d_tab += (size_t)c->crank * nd;
+      rc = dense_reduce_scatter(c, c->d_densetab.p, nd); if (rc) return rc;
+    } else { rc = dense_allreduce(c, c->d_densetab.p, nd); if (rc) return rc; }
     unsigned long long* d_flag = (unsigned long long*)c->d_densework.p; unsigned long long* d_prefix = d_flag + nd; void* d_tmp = d_prefix + nd;
     u64 last2[2];   // row count = flag[nd-1] + prefix[nd-1]
-    nbk::launch_merge_dense_scan((const unsigned long long*)c->d_densetab.p, nd, d_flag, d_prefix, d_tmp, tb, s); c->all_launches += 2;
+    nbk::launch_merge_dense_scan(d_tab, nd, d_flag, d_prefix, d_tmp, tb, s); c->all_launches += 2;
     CK(cudaMemcpyAsync(&last2[0], d_flag + nd - 1, 8, cudaMemcpyDeviceToHost, s)); CK(cudaMemcpyAsync(&last2[1], d_prefix + nd - 1, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     n_agg = last2[0] + last2[1];
@@ -626,7 +636,7 @@ static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells) {
     if (n_agg) {
       CK(c->d_rowout.ensure(n_agg * 16, s));
       u32* d_scope = (u32*)c->d_rowout.p; u32* d_callset = d_scope + n_agg; i64* d_count = (i64*)((char*)c->d_rowout.p + 8 * n_agg);
-      nbk::launch_merge_dense_rows((const unsigned long long*)c->d_densetab.p, nd, ncs, d_prefix, d_scope, d_callset, d_count, s); c->all_launches++;
+      nbk::launch_merge_dense_rows(d_tab, nd, ncs, d_prefix, d_scope, d_callset, d_count, cell_base, s); c->all_launches++;
       CK(cudaMemcpyAsync(c->h_rows, c->d_rowout.p, n_agg * 16, cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
     }
@@ -922,6 +932,7 @@ struct NcclApi {
   ncclResult_t (*CommUserRank)(const ncclComm_t, int*);
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*GroupStart)();
@@ -937,7 +948,7 @@ static const NcclApi* nccl_api() {
     auto sym = [&](const char* n) { void* p = ok ? dlsym(h, n) : nullptr; if (!p) ok = false; return p; };
     *(void**)&api.GetUniqueId = sym("ncclGetUniqueId"); *(void**)&api.CommInitRank = sym("ncclCommInitRank"); *(void**)&api.CommInitAll = sym("ncclCommInitAll");
     *(void**)&api.CommDestroy = sym("ncclCommDestroy"); *(void**)&api.CommCount = sym("ncclCommCount"); *(void**)&api.CommUserRank = sym("ncclCommUserRank");
-    *(void**)&api.AllGather = sym("ncclAllGather"); *(void**)&api.AllReduce = sym("ncclAllReduce"); *(void**)&api.Send = sym("ncclSend"); *(void**)&api.Recv = sym("ncclRecv");
+    *(void**)&api.AllGather = sym("ncclAllGather"); *(void**)&api.AllReduce = sym("ncclAllReduce"); *(void**)&api.ReduceScatter = sym("ncclReduceScatter"); *(void**)&api.Send = sym("ncclSend"); *(void**)&api.Recv = sym("ncclRecv");
     *(void**)&api.GroupStart = sym("ncclGroupStart"); *(void**)&api.GroupEnd = sym("ncclGroupEnd"); *(void**)&api.GetErrorString = sym("ncclGetErrorString");
     state = ok ? 1 : -1;
   }
@@ -950,6 +961,13 @@ static int dense_allreduce(nb_ctx* c, void* dense, u64 n) {
   if (!c->comm || c->cworld < 2) return NB_OK;
   NEED_NCCL();
   NCK(N->AllReduce(dense, dense, n, ncclUint64, ncclSum, c->comm, c->stream));
+  return NB_OK;
+}
+// in place: rank r's chunk of the element-wise sums replaces elements [r * chunk, (r + 1) * chunk) of its own table
+static int dense_reduce_scatter(nb_ctx* c, void* dense, u64 chunk) {
+  if (!c->comm || c->cworld < 2) return NB_OK;
+  NEED_NCCL();
+  NCK(N->ReduceScatter(dense, (unsigned long long*)dense + (size_t)c->crank * chunk, chunk, ncclUint64, ncclSum, c->comm, c->stream));
   return NB_OK;
 }
 
@@ -1100,7 +1118,10 @@ int nb_merge_whole_run(nb_ctx* c, nb_counts* out) {
   return rc;
 }
 
-int nb_merge_scoped(nb_ctx* c, uint64_t n_cells, nb_counts* out) {
+static int merge_scoped_impl(nb_ctx* c, uint64_t n_cells, nb_counts* out, bool shard);
+int nb_merge_scoped(nb_ctx* c, uint64_t n_cells, nb_counts* out) { return merge_scoped_impl(c, n_cells, out, false); }
+int nb_merge_scoped_sharded(nb_ctx* c, uint64_t n_cells, nb_counts* out) { return merge_scoped_impl(c, n_cells, out, true); }
+static int merge_scoped_impl(nb_ctx* c, uint64_t n_cells, nb_counts* out, bool shard) {
   if (!c || !out || n_cells == 0) return fail(NB_ERR_INVALID, "bad argument");
   if (!c->comm || c->cworld < 2) return nb_counts_finalize(c, out);
   CK(cudaSetDevice(c->device));
@@ -1112,7 +1133,7 @@ int nb_merge_scoped(nb_ctx* c, uint64_t n_cells, nb_counts* out) {
   // unique keys of the job = sum over ranks (scopes are disjoint): rides in the dense all-reduce's last element? no — one more tiny all-reduce
   NEED_NCCL();
   NCK(N->AllReduce(&((Counters*)c->d_ctr.p)->n_keys, &((Counters*)c->d_ctr.p)->n_keys, 1, ncclUint64, ncclSum, c->comm, c->stream));
-  return finalize_impl(c, out, n_cells);
+  return finalize_impl(c, out, n_cells, shard);
 }
 
 }  // extern "C"

@@ -486,12 +486,6 @@ __device__ __forceinline__ u64 key_insert(const Tables& t, u64 k0, u64 k1, bool&
   }
   return ~0ULL;
 }
-// Counters::n_live += the new keys of the lanes that are converged here (one atomic per group: a per-key atomic on one
-// address would serialise).  The host sizes the key table from this count instead of re-counting the table (k_count_keys).
-__device__ __forceinline__ void count_fresh(const Tables& t, bool fresh) {
-  const unsigned act = __activemask(), fm = __ballot_sync(act, fresh);
-  if (fm && (threadIdx.x & 31) == (unsigned)(__ffs(fm) - 1)) atomicAdd(&t.ctr->n_live, (unsigned long long)__popc(fm));
-}
 __device__ __forceinline__ u32 callset_intern(const Tables& t, const u32* g, u32 n) {
   u64 tag = 0x9E3779B97F4A7C15ULL ^ n;
   for (u32 i = 0; i < n; i++) tag = mix64(tag ^ g[i]) + 0x632BE59BD9B4E019ULL;
@@ -776,24 +770,7 @@ __global__ void __launch_bounds__(256) k_keys_export(Tables t, KeyRec* rec, unsi
 }
 // import records from other ranks: the tag must already be present in this rank's dictionary (the host merges
 // dictionaries first); records whose tag is 0 carry "no callset" and only shadow older duplicates.
-__global__ void __launch_bounds__(256) k_keys_import(Tables t, const KeyRec* rec, u64 n) {
-  u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  KeyRec r = rec[idx];
-  u32 cs = CS_NONE;
-  if (r.tag) {
-    u32 h = (u32)(r.tag >> 24) & t.cs_mask; bool ok = false;
-    for (u32 probes = 0; probes <= t.cs_mask; probes++) { u64 tg = t.cs_tag[h]; if (tg == r.tag) { ok = true; break; } if (tg == 0) break; h = (h + 1) & t.cs_mask; }
-    if (!ok) { atomicOr(&t.ctr->err, (unsigned)E_CS_FULL); return; }
-    cs = h;
-  }
-  bool fresh;
-  u64 slot = key_insert(t, r.k0, r.k1, fresh);
-  count_fresh(t, fresh && slot != ~0ULL);
-  if (slot == ~0ULL) { atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL); return; }
-  atomicMax(t.kval + slot, (unsigned long long)(((r.order + 1) << 24) | cs));
-}
-
+__global__ void __launch_bounds__(256) k_keys_import(Tables t, const KeyRec* rec, u64 n);
 
 // ---- multi-GPU exchange helpers: key records grouped by owning rank (owner = a 16-bit slice of key_lo mod world), so the
 // host can hand them to an all-to-all without sorting; warp-aggregated cursors (a handful of hot counters otherwise)
@@ -880,30 +857,45 @@ __global__ void __launch_bounds__(256) k_merge_import_callsets(Tables t, const u
   const u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (idx >= k) return;
   callset_import_row(t, (const u32*)(blk + 8 * MERGE_HDR1) + idx * (4 + t.gcap));
 }
-__device__ __forceinline__ void key_import_rec(const Tables& t, const KeyRec& r) {
+// returns 1 when the record created a key-table entry (the caller adds those up: Counters::n_live takes one atomic per warp)
+__device__ __forceinline__ u32 key_import_rec(const Tables& t, const KeyRec& r) {
   u32 cs = CS_NONE;
   if (r.tag) {
     u32 h = (u32)(r.tag >> 24) & t.cs_mask; bool ok = false;
     for (u32 probes = 0; probes <= t.cs_mask; probes++) { u64 tg = t.cs_tag[h]; if (tg == r.tag) { ok = true; break; } if (tg == 0) break; h = (h + 1) & t.cs_mask; }
-    if (!ok) { atomicOr(&t.ctr->err, (unsigned)E_CS_FULL); return; }
+    if (!ok) { atomicOr(&t.ctr->err, (unsigned)E_CS_FULL); return 0u; }
     cs = h;
   }
   bool fresh;
   u64 slot = key_insert(t, r.k0, r.k1, fresh);
-  count_fresh(t, fresh && slot != ~0ULL);
-  if (slot == ~0ULL) { atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL); return; }
+  if (slot == ~0ULL) { atomicOr(&t.ctr->err, (unsigned)E_KEY_FULL); return 0u; }
   atomicMax(t.kval + slot, (unsigned long long)(((r.order + 1) << 24) | cs));
+  return fresh ? 1u : 0u;
+}
+__device__ __forceinline__ void add_live(const Tables& t, u32 n_new) {   // every lane of the warp calls it, converged
+  for (int o = 16; o; o >>= 1) n_new += __shfl_xor_sync(0xFFFFFFFFu, n_new, o);
+  if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(&t.ctr->n_live, (unsigned long long)n_new);
+}
+__global__ void __launch_bounds__(256) k_keys_import(Tables t, const KeyRec* rec, u64 n) {
+  const u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  u32 n_new = 0;
+  if (idx < n) n_new = key_import_rec(t, rec[idx]);
+  __syncwarp();
+  add_live(t, n_new);
 }
 // the records peers stored into this rank's inbox, region by region; counts come from the gathered headers (sent[self] of rank r)
 __global__ void __launch_bounds__(256) k_merge_import_inbox(Tables t, const KeyRec* inbox, u64 inbox_cap, const u8* all, u64 blk_bytes, u32 self) {
   const u32 r = blockIdx.y; if (r == self) return;
   const u64 n = min(((const u64*)(all + (u64)r * blk_bytes))[1 + self], inbox_cap);
+  u32 n_new = 0;
   for (u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x; idx < n; idx += (u64)gridDim.x * blockDim.x) {
     const uint4* p = (const uint4*)(inbox + (u64)r * inbox_cap + idx);
     uint4 a = __ldcg(p), b = __ldcg(p + 1);      // written by a peer GPU: read through L2, never a stale L1 line
     KeyRec rec; rec.k0 = (u64)a.x | ((u64)a.y << 32); rec.k1 = (u64)a.z | ((u64)a.w << 32); rec.order = (u64)b.x | ((u64)b.y << 32); rec.tag = (u64)b.z | ((u64)b.w << 32);
-    key_import_rec(t, rec);
+    n_new += key_import_rec(t, rec);
   }
+  __syncwarp();
+  add_live(t, n_new);
 }
 // this rank's folded counts as {callset tag, count} rows + header {n, unique keys}
 __global__ void __launch_bounds__(256) k_merge_export_counts(Tables t, u64* blk2, u64 cap2) {
@@ -936,13 +928,13 @@ __global__ void __launch_bounds__(256) k_merge_dense_fill(Tables t, const u32* d
   if (cell >= n_cells || id == NONE32) { atomicOr(&t.ctr->err, (unsigned)E_AGG_FULL); return; }
   atomicAdd(dense + cell * n_cs + id, t.agg_cnt[idx]);
 }
-__global__ void __launch_bounds__(256) k_merge_dense_rows(const unsigned long long* dense, u64 n, u64 n_cs, const unsigned long long* prefix, u32* scope, u32* callset, i64* count) {
+__global__ void __launch_bounds__(256) k_merge_dense_rows(const unsigned long long* dense, u64 n, u64 n_cs, const unsigned long long* prefix, u32* scope, u32* callset, i64* count, u32 cell_base) {
   // `prefix` = exclusive scan of (dense != 0): rows come out ordered by (cell, callset) without a sort
   u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long v = dense[i];
   if (!v) return;
-  u64 at = prefix[i]; scope[at] = (u32)(i / n_cs); callset[at] = (u32)(i % n_cs); count[at] = (i64)v;
+  u64 at = prefix[i]; scope[at] = cell_base + (u32)(i / n_cs); callset[at] = (u32)(i % n_cs); count[at] = (i64)v;
 }
 __global__ void __launch_bounds__(256) k_merge_nonzero(const unsigned long long* dense, u64 n, unsigned long long* flag) {
   u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
@@ -968,8 +960,8 @@ void launch_merge_dense_scan(const unsigned long long* dense, u64 n, unsigned lo
   k_merge_nonzero<<<blocks_for(n, 256), 256, 0, s>>>(dense, n, flag);
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const unsigned long long*)flag, prefix, (int)n, s);
 }
-void launch_merge_dense_rows(const unsigned long long* dense, u64 n, u64 n_cs, const unsigned long long* prefix, u32* scope, u32* callset, i64* count, cudaStream_t s) {
-  if (n) k_merge_dense_rows<<<blocks_for(n, 256), 256, 0, s>>>(dense, n, n_cs, prefix, scope, callset, count);
+void launch_merge_dense_rows(const unsigned long long* dense, u64 n, u64 n_cs, const unsigned long long* prefix, u32* scope, u32* callset, i64* count, u32 cell_base, cudaStream_t s) {
+  if (n) k_merge_dense_rows<<<blocks_for(n, 256), 256, 0, s>>>(dense, n, n_cs, prefix, scope, callset, count, cell_base);
 }
 void launch_keys_count_owner(const Tables& t, u32 world, unsigned long long* counts, cudaStream_t s) { k_keys_count_owner<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, world, counts); }
 void launch_keys_scatter(const Tables& t, void* rec, unsigned long long* cursors, u64 order_base, u32 world, cudaStream_t s) { k_keys_scatter<<<blocks_for(t.key_mask + 1, 256), 256, 0, s>>>(t, (KeyRec*)rec, cursors, order_base, world); }

@@ -124,6 +124,22 @@ def test_scoped_merge_in_library_sums_the_per_cell_tables(lib2):
         got = {(int(c), tuple(cs)): int(k) for c, cs, k in ctxs[d].decode_counts(raw)["rows"]}
         assert got == want, d
     assert len(want) > 10_000
+    # nb_merge_scoped_sharded: every rank keeps its own range of cells; the shards are disjoint and their union is the table
+    for c in ctxs:
+        c.reset()
+
+    def shard2(d):
+        run(ctxs[d], us[d])
+        return ctxs[d].merge_scoped(n_cells, sharded=True)
+    raws = _parallel([lambda d=d: shard2(d) for d in range(world)])
+    union, per = {}, (n_cells + world - 1) // world
+    for d, raw in enumerate(raws):
+        rows = ctxs[d].decode_counts(raw)["rows"]
+        assert all(d * per <= int(c) < (d + 1) * per for c, _, _ in rows) and len(rows) > 1000
+        for c, cs, k in rows:
+            assert (int(c), tuple(cs)) not in union
+            union[(int(c), tuple(cs))] = int(k)
+    assert union == want
 
 
 @needs2
