@@ -795,7 +795,11 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
   t_load = t_prod; t_group = 0;
   t_fill = ns_fill.load() * 1e-9; t_rows = ns_rows.load() * 1e-9;
   if (rc == NB_OK) for (u32 li = 0; li < n_refs; li++) if (first_write[li]) { std::string em; if (!gzip_member(std::string(), GZ_LEVEL, em) || fwrite(em.data(), 1, em.size(), outs[li]) != em.size()) rc = fail(NB_ERR_IO, "short write on the TSV"); }   // no row at all: an empty gzip stream, like the reference's untouched GzEncoder
-  if (getenv("NB_BAM_STATS")) fprintf(stderr, "nb_process_bam: %zu records in %zu groups%s; windows (read+inflate+group, overlapped) %.2fs, largest window %.0f MB, batch fill %.2fs, device align+finalize %.2fs (align %.2fs, finalize %.2fs), rows+gzip+write %.2fs (fill and rows overlap the device stage), total %.2fs\n", n_records_total, n_groups_total, whole_file ? " (whole-file fallback)" : "", t_load, peak_window / 1048576.0, t_fill, t_gpu, t_align, t_final, t_rows, now() - t_start);
+  if (getenv("NB_BAM_STATS")) {
+    // peak resident set of THIS process image (VmHWM belongs to the mm, so unlike ru_maxrss it does not start at the forking parent's size)
+    double hwm_mb = 0; if (FILE* st = fopen("/proc/self/status", "r")) { char line[256]; while (fgets(line, sizeof line, st)) if (!strncmp(line, "VmHWM:", 6)) hwm_mb = strtod(line + 6, nullptr) / 1024.0; fclose(st); }
+    fprintf(stderr, "nb_process_bam: %zu records in %zu groups%s; windows (read+inflate+group, overlapped) %.2fs, largest window %.0f MB, batch fill %.2fs, device align+finalize %.2fs (align %.2fs, finalize %.2fs), rows+gzip+write %.2fs (fill and rows overlap the device stage), total %.2fs, peak RSS %.0f MB\n", n_records_total, n_groups_total, whole_file ? " (whole-file fallback)" : "", t_load, peak_window / 1048576.0, t_fill, t_gpu, t_align, t_final, t_rows, now() - t_start, hwm_mb);
+  }
   cleanup();
   return rc;
 }
