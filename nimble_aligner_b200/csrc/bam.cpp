@@ -607,11 +607,10 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
   if (rc != NB_OK) { cleanup(); return rc; }
   const size_t BATCH_PAIRS = 1u << 20;
   const int GZ_LEVEL = 4;
-  static const char* T16 = "=ACMGRSVTWYHKDBN";
   // Three stages run concurrently on consecutive batches: (F) the host threads fill batch k+1 into pinned buffers,
   // (D) the device aligns batch k and its counts are finalized, (R) the host threads format + gzip the rows of batch k-1.
   struct Pinned { u8* p = nullptr; size_t cap = 0; int ensure(size_t n) { if (n <= cap) return NB_OK; nb_host_free(p); cap = n + n / 4 + 4096; p = (u8*)nb_host_alloc(cap); if (!p) { cap = 0; return fail(NB_ERR_CUDA, "pinned host allocation failed"); } return NB_OK; } ~Pinned() { nb_host_free(p); } };
-  struct BatchIn { const std::vector<Rec>* stream = nullptr; const std::vector<u64>* gstart = nullptr; size_t g0 = 0, g1 = 0, np = 0; u32 maxlen = 1; std::vector<u64> pair0, o1, o2; std::vector<u8> f1, f2; std::vector<u32> scope; Pinned r1, r2, q1, q2; };
+  struct BatchIn { const std::vector<Rec>* stream = nullptr; const std::vector<u64>* gstart = nullptr; size_t g0 = 0, g1 = 0, np = 0; u32 maxlen = 1; std::vector<u64> pair0, o1, o2; std::vector<u32> l1, l2; std::vector<u8> f1, f2; std::vector<u32> scope; Pinned r1, r2, q1, q2; };
   struct BatchOut { std::vector<nb_read_result> rres; std::vector<nb_pair_result> pres; std::vector<u64> row_begin, callset_off; std::vector<u32> row_callset, callset_items, slot_to_callset; std::vector<i64> row_count; };
   BatchIn bin[3]; BatchOut bout[2];
   // the window being processed (its records and groups): set by the window loop below, read by the three stages
@@ -625,28 +624,41 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
     B.pair0.assign(ng + 1, 0);
     for (size_t g = 0; g < ng; g++) B.pair0[g + 1] = B.pair0[g] + (gstart[g0 + g + 1] - gstart[g0 + g]) / 2;
     const size_t np = B.np = B.pair0[ng];
-    B.o1.assign(np + 1, 0); B.o2.assign(np + 1, 0); B.f1.resize(np); B.f2.resize(np); B.scope.resize(np);
+    // The bases travel as BAM stores them — 4-bit nibbles (NB_SEQ_BAM4: the device turns =ACMGRSVTWYHKDBN into A/C/G/T with
+    // everything else A, exactly DnaString::from_acgt_bytes on the letters) — so a read is a byte copy out of its record, not a
+    // per-base expansion, and half the PCIe bytes.  Every read starts on a byte of the batch stream; offsets count BASES
+    // (2 x byte + the odd nibble a TSO clip may start on), lengths are explicit, quals sit one byte per base at the same offsets.
+    B.o1.assign(np + 1, 0); B.o2.assign(np + 1, 0); B.l1.resize(np); B.l2.resize(np); B.f1.resize(np); B.f2.resize(np); B.scope.resize(np);
+    std::vector<u64>& by1 = B.o1; std::vector<u64>& by2 = B.o2;   // first: nibble bytes per read, then their running sum, then base offsets
     parallel_ranges(threads, ng, [&](size_t a, size_t b, int) {
       for (size_t g = a; g < b; g++) { const Rec* v = &stream[gstart[g0 + g]];
-        for (size_t j = 0; j < B.pair0[g + 1] - B.pair0[g]; j++) { size_t x, y; clip_of(v[2 * j], x, y); B.o1[B.pair0[g] + j + 1] = y - x; clip_of(v[2 * j + 1], x, y); B.o2[B.pair0[g] + j + 1] = y - x; } } });
+        for (size_t j = 0; j < B.pair0[g + 1] - B.pair0[g]; j++) { size_t x, y; const size_t p = B.pair0[g] + j;
+          clip_of(v[2 * j], x, y); by1[p + 1] = ((y + 1) >> 1) - (x >> 1); B.l1[p] = (u32)(y - x);
+          clip_of(v[2 * j + 1], x, y); by2[p + 1] = ((y + 1) >> 1) - (x >> 1); B.l2[p] = (u32)(y - x); } } });
     B.maxlen = 1;
-    for (size_t p = 0; p < np; p++) { B.maxlen = std::max<u32>(B.maxlen, (u32)std::max(B.o1[p + 1], B.o2[p + 1])); B.o1[p + 1] += B.o1[p]; B.o2[p + 1] += B.o2[p]; }
-    int e = B.r1.ensure(B.o1[np] + 64); if (!e) e = B.q1.ensure(B.o1[np] + 64); if (!e) e = B.r2.ensure(B.o2[np] + 64); if (!e) e = B.q2.ensure(B.o2[np] + 64); if (e) return e;
+    for (size_t p = 0; p < np; p++) { B.maxlen = std::max<u32>(B.maxlen, std::max(B.l1[p], B.l2[p])); by1[p + 1] += by1[p]; by2[p + 1] += by2[p]; }
+    const u64 tot1 = by1[np], tot2 = by2[np];
+    int e = B.r1.ensure(tot1 + 64); if (!e) e = B.q1.ensure(2 * tot1 + 64); if (!e) e = B.r2.ensure(tot2 + 64); if (!e) e = B.q2.ensure(2 * tot2 + 64); if (e) return e;
     parallel_ranges(threads, ng, [&](size_t a, size_t b, int) {
       for (size_t g = a; g < b; g++) { const Rec* v = &stream[gstart[g0 + g]];
         for (size_t j = 0; j < B.pair0[g + 1] - B.pair0[g]; j++) {
           size_t p = B.pair0[g] + j;
           for (int side = 0; side < 2; side++) {
             const Rec& r = v[2 * j + side]; size_t x, y; clip_of(r, x, y);
-            u8* dst = (side ? B.r2.p + B.o2[p] : B.r1.p + B.o1[p]); u8* dq = (side ? B.q2.p + B.o2[p] : B.q1.p + B.o1[p]);
-            const u8* s4 = r.seq4(); const u8* q = r.qual();
-            for (size_t i = x; i < y; i++) { char c = T16[(s4[i >> 1] >> ((~i & 1) << 2)) & 15]; dst[i - x] = (c == 'C' || c == 'G' || c == 'T') ? (u8)c : (u8)'A'; }   // DnaString::from_acgt_bytes(...).to_string()
-            memcpy(dq, q + x, y - x);
+            const u64 byte0 = side ? by2[p] : by1[p], base0 = 2 * byte0 + (x & 1);
+            memcpy((side ? B.r2.p : B.r1.p) + byte0, r.seq4() + (x >> 1), ((y + 1) >> 1) - (x >> 1));
+            memcpy((side ? B.q2.p : B.q1.p) + base0, r.qual() + x, y - x);
             u8 fl = (u8)((r.skip_align == 1 ? NB_FLAG_SKIP_ALIGN : 0) | (r.is_reverse() ? NB_FLAG_REVCOMP : 0));
             if (side) B.f2[p] = fl; else B.f1[p] = fl;
           }
           B.scope[p] = (u32)g;
         } } });
+    // byte positions -> base offsets (in place, after every copy has used the byte positions): the odd start nibble of read p
+    parallel_ranges(threads, ng, [&](size_t a, size_t b, int) {
+      for (size_t g = a; g < b; g++) { const Rec* v = &stream[gstart[g0 + g]];
+        for (size_t j = 0; j < B.pair0[g + 1] - B.pair0[g]; j++) { size_t x, y; const size_t p = B.pair0[g] + j;
+          clip_of(v[2 * j], x, y); by1[p] = 2 * by1[p] + (x & 1); clip_of(v[2 * j + 1], x, y); by2[p] = 2 * by2[p] + (x & 1); } } });
+    by1[np] = 2 * tot1; by2[np] = 2 * tot2;
     ns_fill += (u64)((now() - tb) * 1e9);
     return NB_OK;
   };
@@ -657,6 +669,7 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
     nb_batch b; memset(&b, 0, sizeof b);
     b.n_pairs = B.np; b.location = NB_MEM_HOST; b.max_read_len = B.maxlen; b.r1 = B.r1.p; b.r1_off = B.o1.data(); b.r2 = B.r2.p; b.r2_off = B.o2.data();
     b.q1 = B.q1.p; b.q2 = B.q2.p; b.flags1 = B.f1.data(); b.flags2 = B.f2.data(); b.scope_id = B.scope.data();
+    b.encoding = NB_SEQ_BAM4; b.r1_len = B.l1.data(); b.r2_len = B.l2.data();
     O.rres.resize(2 * B.np); O.pres.resize(B.np);
     double ta = now();
     int e = nb_counts_reset(ctx[li]); if (e) return e;
