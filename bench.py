@@ -16,6 +16,10 @@ over unique read pairs).  A "step" is one complete pass of the hot path (pack ->
   cpu_baseline  the CPU oracle with the reference's cost structure on a bounded sample, all host cores
   parity_checked  GPU counts == oracle counts on a prefix of the same seeded stream (asserted; the run fails otherwise)
 
+Block `c5` (configs[4]: the mismatch-tolerance sweep on the C2 library and reads, with the count merge at N > 1): the points of
+the sweep (num_mismatches 0 / 1 / 2) the top-level line does not cover, timed on the same device-resident inputs, each
+with its own parity check (N = 1: counts and work counters == oracle on a prefix; N > 1: merged counts of a small sharded job
+== oracle == one GPU over the union).
 Blocks `c4` (configs[3] shape: library whose index is far larger than L2, single-end 150 bp, HBM-bound probes; N=1
 only) and `c3` (configs[2] shape: 10x-style single-end 91 bp records with quals in (UMI, CB) scopes, MAXINFO trim,
 dummy mates, per-cell count table; every N, scopes sharded over ranks) carry the same keys for their workloads.
@@ -491,6 +495,105 @@ def run_c3(env, args):
     return out
 
 
+def verify_sharded(env, args, job, counts_of, L, obj, lib, ix, n, mm=0):
+    """N > 1 (untimed): a small sharded job through the same merge path must equal (a) the oracle over the union of the
+    mini-shards and (b) one GPU over that union.  Every rank takes pairs [0, m) of ITS shard with its real global pair orders,
+    so ownership, routing and "later duplicate wins" are exercised across ranks.  Returns the note (rank 0) or None."""
+    nb, synth, rank, world, cores = env.nb, env.synth, env.rank, env.world, env.cores
+    m = max(1000, args.parity_reads // world)
+    mini, _u = job(m, False)
+    mini = counts_of(mini)
+    if rank != 0:
+        return None
+    import oracle as orc
+    parts1, parts2, offs1, offs2 = [], [], [np.zeros(1, dtype=np.uint64)], [np.zeros(1, dtype=np.uint64)]
+    for r in range(world):   # rank r's first m pairs = pairs [r*n, r*n + m) of the seeded stream
+        a1, b1, a2, b2 = synth.pairs(L, r * n, m, seed=SEED, threads=cores)
+        parts1.append(a1[: int(b1[-1])]); parts2.append(a2[: int(b2[-1])])
+        offs1.append(b1[1:] + offs1[-1][-1]); offs2.append(b2[1:] + offs2[-1][-1])
+    v1, v2 = np.concatenate(parts1 + [np.zeros(64, np.uint8)]), np.concatenate(parts2 + [np.zeros(64, np.uint8)])
+    vo1, vo2 = np.concatenate(offs1).astype(np.uint64), np.concatenate(offs2).astype(np.uint64)
+    ocfg, oref = orc.parse_reference_library(obj, "unstranded")
+    ref = orc.Oracle(ocfg, oref).run(v1, vo1, v2, vo2, threads=cores, want_records=False)
+    want = {tuple(cs): int(c) for cs, c in ref["scopes"][0]}
+    vctx = nb.Context(ix, lib, device=env.local_rank, max_batch_pairs=args.chunk)
+    vctx.align_batch(v1, vo1, v2, vo2, max_read_len=READ_LEN)
+    one = {tuple(cs): int(c) for _, cs, c in vctx.counts()["rows"]}
+    vctx.close()
+    assert one == want, "single-GPU counts over the union of the mini-shards differ from the oracle's (num_mismatches %d)" % mm
+    assert mini == want, "%d-GPU merged counts differ from the oracle's over the union of the mini-shards (num_mismatches %d)" % (world, mm)
+    note = "%d-GPU merged counts == oracle == one GPU over the union of %d pairs per rank (%d callsets)" % (world, m, len(want))
+    log("verify (num_mismatches %d): %s" % (mm, note))
+    return note
+
+
+# ---------------------------------------------------------------------------------------------- C5 block (every N)
+def run_c5(env, args, sh):
+    """BASELINE.json configs[4]: the mismatch-tolerance sweep on the C2 library and reads, with the count merge at N > 1.  The
+    top-level line is one point of the sweep (--mismatches, default 0); this block adds the other two on the same inputs:
+    device-resident jobs timed like the top level, and the same parity checks (N = 1: GPU counts and work counters == oracle on
+    a prefix; N > 1: merged counts of a small sharded job == oracle == one GPU over the union)."""
+    nb, synth, torch, dist, rank, world = env.nb, env.synth, env.torch, env.dist, env.rank, env.world
+    from nimble_aligner_b200.multigpu import lib_comm
+    n, out = sh["n"], {"workload": "C5: mismatch sweep on the C2 library and reads (same %d pairs per GPU per step, inputs resident in HBM)%s" % (sh["n"], ", merged by nb_merge_whole_run" if world > 1 else ""),
+                       "unit": UNIT, "sweep": {}}
+    for mm in (0, 1, 2):
+        if mm == args.mismatches:
+            continue
+        L = c2_library(mm)
+        obj = L.to_json_obj()
+        lib = nb.Library.from_text(json.dumps(obj), "unstranded")
+        ctx = nb.Context(sh["ix"], lib, device=env.local_rank, stream=env.stream, max_batch_pairs=args.chunk)
+        if world > 1:
+            lib_comm(ctx, nb, torch, dist, rank, world)
+            try:
+                ctx.route_setup((n + n // 2) // world + 4096, sh["pair_base"])
+            except nb.NbError as e:
+                ctx.close()
+                out["skipped"] = "peer routing unavailable (%s)" % e
+                return out
+
+        def job(pairs, dev, ctx=ctx):
+            ctx.reset()
+            if dev:
+                ctx.align_batch(sh["d1"], sh["do1"], sh["d2"], sh["do2"], n_pairs=pairs, max_read_len=READ_LEN, location=nb.NB_MEM_DEVICE)
+            else:
+                b = nb.Batch(pairs, nb.NB_MEM_HOST, READ_LEN, sh["h1"].data_ptr(), sh["ho1"].data_ptr(), sh["h2"].data_ptr(), sh["ho2"].data_ptr(), None, None, None, None, None, None)
+                nb._ck(nb.lib().nb_align_batch(ctx.h, C.byref(b), None, None))
+            raw = ctx.merge_whole_run() if world > 1 else ctx.counts_raw()
+            return raw, raw["n_unique_keys"]
+        for _ in range(2):
+            job(n, True)
+        ctx.kernel_stats(reset=True)
+        ms, (raw, uniq) = timed(env, lambda: job(n, True), args.steps)
+        ks = ctx.kernel_stats(reset=True)
+        e = {"value": 2 * n * world / (ms / 1e3), "ms_per_step": ms, "unique_pair_keys": int(uniq), "k_map_ms_per_launch": ks["map_ms"] / max(1, ks["map_launches"])}
+        if not args.no_cpu_baseline and not (world > 1 and args.no_verify):
+            if world == 1:
+                import oracle as orc
+                ocfg, oref = orc.parse_reference_library(obj, "unstranded")
+                mp = min(args.parity_reads, n)
+                ref = orc.Oracle(ocfg, oref).run(sh["h1"].numpy(), sh["o1"][: mp + 1], sh["h2"].numpy(), sh["o2"][: mp + 1], threads=env.cores, want_records=False)
+                want = {tuple(cs): int(c) for cs, c in ref["scopes"][0]}
+                pctx = nb.Context(sh["ix"], lib, device=env.local_rank, stream=env.stream, max_batch_pairs=args.chunk, count_work=1)
+                pctx.align_batch(sh["h1"].numpy(), sh["o1"][: mp + 1], sh["h2"].numpy(), sh["o2"][: mp + 1], max_read_len=READ_LEN)
+                got = {tuple(cs): int(c) for _, cs, c in pctx.counts()["rows"]}
+                assert got == want, "C5: GPU counts differ from the oracle's at num_mismatches %d" % mm
+                w = pctx.work_counters()
+                assert all(w[k] == ref["work"][k] for k in ("probes", "nodes", "bases")), "C5: device work counters differ from the oracle's at num_mismatches %d" % mm
+                pctx.close()
+                e["parity_checked"] = True
+                e["parity"] = "GPU counts == oracle counts (%d callsets) and work counters equal on the first %d pairs" % (len(want), mp)
+            else:
+                note = verify_sharded(env, args, job, lambda r, ctx=ctx: whole_counts(ctx, r), L, obj, lib, sh["ix"], n, mm)
+                if note:
+                    e["parity_checked"] = True
+                    e["parity"] = note
+        ctx.close()
+        out["sweep"]["mm%d" % mm] = e
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- main (C2 + blocks)
 def main():
     guard_stdout()
@@ -503,7 +606,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=2_000_000, help="pairs per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--parity-reads", type=int, default=200_000, help="prefix (pairs for C2, reads / records for C4 / C3) on which GPU counts are asserted equal to the oracle's")
     ap.add_argument("--chunk", type=int, default=1 << 20)
-    ap.add_argument("--blocks", default="c3,c4", help="extra workload blocks in the JSON line (c4: N=1 only)")
+    ap.add_argument("--blocks", default="c5,c3,c4", help="extra workload blocks in the JSON line (c5: the other points of the mismatch sweep; c4: N=1 only)")
     ap.add_argument("--c4-families", type=int, default=8000, help="C4 library: families x 5 alleles (8000 -> 40k transcripts, 1.9 GB index; 40000 = BASELINE's full 200k)")
     ap.add_argument("--c4-reads", type=int, default=8_000_000)
     ap.add_argument("--c4-ref-reads", type=int, default=400_000)
@@ -640,34 +743,10 @@ def main():
     assert counts_host == counts_dev, "host-fed and device-resident runs disagree"
     assert sum(counts_dev.values()) <= uniq_dev <= n * world, "count table inconsistent with the number of unique read_keys"
 
-    # ---- verification pass at N>1 (untimed): a small sharded job through the same merge path must equal (a) the oracle over
-    # the union of the mini-shards and (b) one GPU over that union.  Every rank takes pairs [0, m) of ITS shard with its real
-    # global pair orders, so ownership, routing and "later duplicate wins" are exercised across ranks.
+    # ---- verification pass at N>1 (untimed)
     verify_note = None
     if world > 1 and not args.no_verify:
-        m = max(1000, args.parity_reads // world)
-        mini, _u = job(m, False)
-        mini = whole_counts(ctx, mini)
-        if rank == 0:
-            import oracle as orc
-            parts1, parts2, offs1, offs2 = [], [], [np.zeros(1, dtype=np.uint64)], [np.zeros(1, dtype=np.uint64)]
-            for r in range(world):   # rank r's first m pairs = pairs [r*n, r*n + m) of the seeded stream
-                a1, b1, a2, b2 = synth.pairs(L, r * n, m, seed=SEED, threads=cores)
-                parts1.append(a1[: int(b1[-1])]); parts2.append(a2[: int(b2[-1])])
-                offs1.append(b1[1:] + offs1[-1][-1]); offs2.append(b2[1:] + offs2[-1][-1])
-            v1, v2 = np.concatenate(parts1 + [np.zeros(64, np.uint8)]), np.concatenate(parts2 + [np.zeros(64, np.uint8)])
-            vo1, vo2 = np.concatenate(offs1).astype(np.uint64), np.concatenate(offs2).astype(np.uint64)
-            ocfg, oref = orc.parse_reference_library(obj, "unstranded")
-            ref = orc.Oracle(ocfg, oref).run(v1, vo1, v2, vo2, threads=cores, want_records=False)
-            want = {tuple(cs): int(c) for cs, c in ref["scopes"][0]}
-            vctx = nb.Context(ix, lib, device=local_rank, max_batch_pairs=args.chunk)
-            vctx.align_batch(v1, vo1, v2, vo2, max_read_len=READ_LEN)
-            one = {tuple(cs): int(c) for _, cs, c in vctx.counts()["rows"]}
-            vctx.close()
-            assert one == want, "single-GPU counts over the union of the mini-shards differ from the oracle's"
-            assert mini == want, "%d-GPU merged counts differ from the oracle's over the union of the mini-shards" % world
-            verify_note = "%d-GPU merged counts == oracle == one GPU over the union of %d pairs per rank (%d callsets)" % (world, m, len(want))
-            log("verify: " + verify_note)
+        verify_note = verify_sharded(env, args, job, lambda r: whole_counts(ctx, r), L, obj, lib, ix, n, args.mismatches)
     if args.verify and world > 1 and rank == 0:
         # the merged multi-GPU counts must equal one GPU processing the union of all ranks' shards
         vo1 = np.zeros(n * world + 1, dtype=np.uint64); vo2 = np.zeros(n * world + 1, dtype=np.uint64)
@@ -738,6 +817,14 @@ def main():
         hp, hsrc = hbm_peak()
         out["roofline"]["frac_of_hbm_stream_peak"] = out["roofline"]["achieved"] / hp
         out["roofline"]["hbm_stream_peak"] = hp
+    c5 = None
+    if "c5" in blocks:
+        t0 = time.time()
+        c5 = run_c5(env, args, dict(n=n, ix=ix, pair_base=pair_base, d1=d1, d2=d2, do1=do1, do2=do2, h1=h1, h2=h2, ho1=ho1, ho2=ho2, o1=o1, o2=o2))
+        if rank == 0:
+            c5["sweep"]["mm%d" % args.mismatches] = {"value": out["value"], "ms_per_step": out["ms_per_step"], "k_map_ms_per_launch": out["k_map_ms_per_launch"], "parity_checked": out.get("parity_checked", False), "note": "the top-level line"}
+            c5["block_wall_s"] = time.time() - t0
+            out["c5"] = c5
     ctx.close()
     del d1, d2, do1, do2, h1, h2, p1, p2
     torch.cuda.empty_cache()
