@@ -160,7 +160,10 @@ typedef struct nb_batch {
  *                DnaString::from_acgt_bytes makes it)
  *   NB_SEQ_BAM4  nibble j = byte j>>1, high nibble first (BAM's seq field), code table "=ACMGRSVTWYHKDBN": everything but
  *                A, C, G, T becomes A, exactly what the reference does with those letters
- * Buffers must be readable for 16 bytes past the last base. */
+ * Buffers must be readable for 16 bytes past the last base.
+ * Device-resident batches (NB_MEM_DEVICE), any encoding: the kernels fetch bases and quals as aligned 16-byte vectors, so r1 / r2
+ * / q1 / q2 must be readable from the 16-byte boundary at or below their first byte to 48 bytes past their last one (any
+ * cudaMalloc'ed buffer is; host batches are staged by the library and need nothing). */
 enum { NB_SEQ_ASCII = 0, NB_SEQ_2BIT = 1, NB_SEQ_BAM4 = 2 };
 
 /* Per-read outcome of align::pseudoalign (src/align.rs:945-989): reason is SuccessfulMatch when the read passed;

@@ -96,9 +96,9 @@ struct nb_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
   double map_ms = 0; u64 map_launches = 0, map_reads = 0, all_launches = 0;
   // results
-  std::vector<u32> cs_items, slot_dense; std::vector<u64> cs_off;
+  std::vector<u32> cs_items, slot_dense, dense_prev, dense_ids; std::vector<u64> cs_off;   // dense_prev: the slots slot_dense held last time (only those are reset); dense_ids: slot of callset i, uploaded to fill d_dense on the device
   u8* h_rows = nullptr; size_t h_rows_cap = 0; u64 n_rows_dev = 0;   // pinned: row_scope | row_callset | row_count of the last finalize
-  DBuf d_rowwork, d_rowout, d_dense;
+  DBuf d_rowwork, d_rowout, d_dense, d_denseids;
   // peer routing of the whole-run scope (nb_route_*): own inbox = inbox_world regions of inbox_cap KeyRec, one per source rank; d_routecur = this rank's fill cursors
   DBuf d_inbox, d_routecur; u64 inbox_cap = 0; u32 inbox_world = 0; bool route_on = false; nbk::Route route; std::vector<void*> ipc_opened;
   // multi-GPU merge (nb_comm_*, nb_merge_*): the NCCL communicator this context merges over and its exchange blocks
@@ -281,7 +281,7 @@ void nb_ctx_free(nb_ctx* c) {
   DBuf* all[] = {&c->d_ptab, &c->d_bloom, &c->d_node, &c->d_walk, &c->d_unitig, &c->d_ledge, &c->d_coloff, &c->d_colids, &c->d_colmeta, &c->d_rowfid, &c->d_rowrev, &c->d_rowof, &c->d_featgroup, &c->d_rowuoff, &c->d_rowupos, &c->d_rowother, &c->d_rowgroup,
                  &c->d_ent, &c->d_ls, &c->d_qp, &c->d_mincov, &c->d_cstag, &c->d_cslen, &c->d_csitems, &c->d_key, &c->d_kval, &c->d_klast, &c->d_pslot, &c->d_pres2, &c->d_aggkey, &c->d_aggcnt, &c->d_arena, &c->d_ctr, &c->d_scratch, &c->d_nout,
                  &c->stg[0].a[0], &c->stg[0].a[1], &c->stg[0].off[0], &c->stg[0].off[1], &c->stg[0].q[0], &c->stg[0].q[1], &c->stg[0].f[0], &c->stg[0].f[1], &c->stg[0].len[0], &c->stg[0].len[1], &c->stg[0].scope, &c->stg[0].cell,
-                 &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].len[0], &c->stg[1].len[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded, &c->d_rowwork, &c->d_rowout, &c->d_dense};
+                 &c->stg[1].a[0], &c->stg[1].a[1], &c->stg[1].off[0], &c->stg[1].off[1], &c->stg[1].q[0], &c->stg[1].q[1], &c->stg[1].f[0], &c->stg[1].f[1], &c->stg[1].len[0], &c->stg[1].len[1], &c->stg[1].scope, &c->stg[1].cell, &c->d_pk, &c->d_lenfull, &c->d_lentrim, &c->d_rres, &c->d_pres, &c->d_rout, &c->d_seeded, &c->d_rowwork, &c->d_rowout, &c->d_dense, &c->d_denseids};
   for (DBuf* b : all) b->release();
   for (void* q : c->ipc_opened) cudaIpcCloseMemHandle(q);
   c->ipc_opened.clear(); c->d_inbox.release(); c->d_routecur.release();
@@ -597,11 +597,36 @@ static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells, bool shard 
       for (u32 x = 0; x < gc; x++) if (ka[x] != kb[x]) return ka[x] < kb[x];
       return csr[(size_t)a * cw] < csr[(size_t)b * cw];
     };
+    // sorted as 16-byte {prefix, index} pairs: the prefix packs the first ranks (four at 16 bits when they fit, else two at
+    // 32), so nearly every comparison is one integer compare; the rank rows are only walked on equal prefixes
+    struct PK { u64 k; u32 idx; u32 pad; };
+    std::vector<PK> pk(n_cs);
+    const bool r16 = n_groups < 65536;
+    par([&](u32 t) {
+      for (u64 q = (u64)n_cs * t / T; q < (u64)n_cs * (t + 1) / T; q++) {   // (position q of `slots`: buckets stay contiguous)
+        const u32 i = slots[q]; const u32* k = &km[(size_t)i * gc];
+        const u64 a = k[0], b = gc > 1 ? k[1] : 0, c2 = gc > 2 ? k[2] : 0, d = gc > 3 ? k[3] : 0;
+        pk[q].k = r16 ? (a << 48) | (b << 32) | (c2 << 16) | d : (a << 32) | b; pk[q].idx = i; pk[q].pad = 0;
+      }
+    });
     std::atomic<u32> next{0};
-    par([&](u32) { for (u32 b; (b = next.fetch_add(1)) < NB;) std::sort(slots.begin() + bbeg[b], slots.begin() + bbeg[b + 1], less); });
+    par([&](u32) { for (u32 b; (b = next.fetch_add(1)) < NB;) std::sort(pk.begin() + bbeg[b], pk.begin() + bbeg[b + 1], [&](const PK& x, const PK& y) { return x.k != y.k ? x.k < y.k : less(x.idx, y.idx); }); });
+    for (u64 q = 0; q < n_cs; q++) slots[q] = pk[q].idx;
   }
-  std::vector<u32>& dense = c->slot_dense; dense.assign(c->cs_slots, NONE32);
-  for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[4 + k]); c->cs_off.push_back(c->cs_items.size()); }
+  // slot -> callset id: only the entries set by the previous finalize are cleared (the table has callset_slots entries — millions
+  // for a big library — and a handful of thousand are in use); the device copy is filled by a kernel from the id list
+  std::vector<u32>& dense = c->slot_dense;
+  if (dense.size() != c->cs_slots) { dense.assign(c->cs_slots, NONE32); c->dense_prev.clear(); }
+  for (u32 sl : c->dense_prev) dense[sl] = NONE32;
+  c->dense_prev.clear(); c->dense_ids.resize(slots.size());
+  c->cs_items.reserve((size_t)n_cs * 4); c->cs_off.reserve(n_cs + 1);
+  for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; c->dense_prev.push_back(r[0]); c->dense_ids[i] = r[0]; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[4 + k]); c->cs_off.push_back(c->cs_items.size()); }
+  auto upload_dense = [&]() -> int {
+    CK(c->d_dense.ensure(dense.size() * 4, s)); CK(c->d_denseids.ensure(c->dense_ids.size() * 4 + 16, s));
+    CK(cudaMemsetAsync(c->d_dense.p, 0xFF, dense.size() * 4, s));
+    if (!c->dense_ids.empty()) { CK(cudaMemcpyAsync(c->d_denseids.p, c->dense_ids.data(), c->dense_ids.size() * 4, cudaMemcpyHostToDevice, s)); nbk::launch_dense_scatter((const u32*)c->d_denseids.p, c->dense_ids.size(), (u32*)c->d_dense.p, s); c->all_launches++; }
+    return NB_OK;
+  };
   if (fstats) ft[3] = fnow();
   // rows ordered by (cell, callset): remap to dense callset ids, radix sort and split on the device (kernels.cu), then one
   // copy into pinned memory — the table can hold millions of (cell, callset) rows
@@ -615,8 +640,8 @@ static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells, bool shard 
     if (nd_all >= (1ull << 31)) return fail(NB_ERR_UNSUPPORTED, "cells x callsets too large for the dense merge (2^31 entries)");
     u64 nd = nd_all;
     size_t tb = nbk::merge_scan_tmp_bytes(nd);
-    CK(c->d_densetab.ensure(nd * 8, s)); CK(c->d_densework.ensure(nd * 16 + tb + 16, s)); CK(c->d_dense.ensure(dense.size() * 4, s));
-    CK(cudaMemcpyAsync(c->d_dense.p, dense.data(), dense.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(c->d_densetab.ensure(nd * 8, s)); CK(c->d_densework.ensure(nd * 16 + tb + 16, s));
+    rc = upload_dense(); if (rc) return rc;
     CK(cudaMemsetAsync(c->d_densetab.p, 0, nd * 8, s));
     nbk::launch_merge_dense_fill(t, (const u32*)c->d_dense.p, (unsigned long long*)c->d_densetab.p, ncs, dense_cells, s); c->all_launches++;
     const unsigned long long* d_tab = (const unsigned long long*)c->d_densetab.p; u32 cell_base = 0;
@@ -651,8 +676,8 @@ static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells, bool shard 
   c->n_rows_dev = n_agg;
   if (n_agg) {
     size_t tb = nbk::rows_sort_tmp_bytes(n_agg), work = n_agg * 32;
-    CK(c->d_rowwork.ensure(work + tb, s)); CK(c->d_rowout.ensure(n_agg * 16, s)); CK(c->d_dense.ensure(dense.size() * 4, s));
-    CK(cudaMemcpyAsync(c->d_dense.p, dense.data(), dense.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(c->d_rowwork.ensure(work + tb, s)); CK(c->d_rowout.ensure(n_agg * 16, s));
+    rc = upload_dense(); if (rc) return rc;
     u64* d_keys = (u64*)c->d_rowwork.p; i64* d_vals = (i64*)((char*)c->d_rowwork.p + n_agg * 16); void* d_tmp = (char*)c->d_rowwork.p + work;
     u32* d_scope = (u32*)c->d_rowout.p; u32* d_callset = d_scope + n_agg; i64* d_count = (i64*)((char*)c->d_rowout.p + 8 * n_agg);
     nbk::launch_rows_sort(d_agg, n_agg, (const u32*)c->d_dense.p, d_keys, d_vals, d_tmp, tb, d_scope, d_callset, d_count, c->mode == 1 ? 56 : 24, s); c->all_launches += 3;

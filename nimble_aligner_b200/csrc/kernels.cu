@@ -1025,6 +1025,8 @@ __global__ void __launch_bounds__(256) k_probe_build(const u64* tkey, const u64*
 void launch_probe_build(const u64* tkey, const u64* tval, u64 slots, u64* ptab, u32 n_pbuckets, u64* bloom, u32 bloom_words, u32 bloom_k, unsigned int* err, cudaStream_t s) {
   if (slots) k_probe_build<<<blocks_for(slots, 256), 256, 0, s>>>(tkey, tval, slots, ptab, n_pbuckets, bloom, bloom_words, bloom_k, err);
 }
+__global__ void __launch_bounds__(256) k_dense_scatter(const u32* ids, u64 n, u32* dense) { u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; if (i < n) dense[ids[i]] = (u32)i; }
+void launch_dense_scatter(const u32* ids, u64 n, u32* dense, cudaStream_t s) { if (n) k_dense_scatter<<<blocks_for(n, 256), 256, 0, s>>>(ids, n, dense); }
 size_t rows_sort_tmp_bytes(u64 n) { size_t tb = 0; cub::DeviceRadixSort::SortPairs(nullptr, tb, (const u64*)nullptr, (u64*)nullptr, (const i64*)nullptr, (i64*)nullptr, (int)n, 0, 56); return tb + 256; }
 // work: 2n u64 keys + 2n i64 values + temp; out: n u32 + n u32 + n i64 (all device)
 void launch_rows_sort(const u64* agg, u64 n, const u32* dense, u64* keys, i64* vals, void* tmp, size_t tmp_bytes, u32* scope, u32* callset, i64* count, int key_bits, cudaStream_t s) {

@@ -115,6 +115,7 @@ void launch_probe_build(const u64* tkey, const u64* tval, u64 slots, u64* ptab, 
 void launch_pack(const BatchDev& b, cudaStream_t s);
 void launch_trim(const BatchDev& b, const Tables& t, cudaStream_t s);
 void launch_map(const BatchDev& b, const DevIndex& ix, const DevCfg& cfg, const Tables& t, int count_work, cudaStream_t s);
+void launch_dense_scatter(const u32* ids, u64 n, u32* dense, cudaStream_t s);   // dense[ids[i]] = i (slot -> callset id table on the device)
 size_t rows_sort_tmp_bytes(u64 n);
 void launch_rows_sort(const u64* agg, u64 n, const u32* dense, u64* keys, i64* vals, void* tmp, size_t tmp_bytes, u32* scope, u32* callset, i64* count, int key_bits, cudaStream_t s);
 void launch_pair(const BatchDev& b, const DevIndex& ix, const DevLib& lib, const DevCfg& cfg, const Tables& t, const Route& rt, cudaStream_t s);
