@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <thread>
 #include <atomic>
@@ -47,6 +48,24 @@ template <class T> cudaError_t upload(DBuf& d, const std::vector<T>& v, cudaStre
   if (bytes) e = cudaMemcpyAsync(d.p, v.data(), bytes, cudaMemcpyHostToDevice, s);
   return e;
 }
+
+// one team of host threads for a whole multi-phase job: spawned once, phases separated by a spin barrier
+struct HostTeam {
+  u32 T; std::atomic<u32> arrived{0}; std::atomic<u32> phase{0};
+  explicit HostTeam(u32 t) : T(t) {}
+  void barrier() {
+    if (T == 1) return;
+    const u32 ph = phase.load(std::memory_order_acquire);
+    if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == T) { arrived.store(0, std::memory_order_relaxed); phase.store(ph + 1, std::memory_order_release); }
+    else { u32 spins = 0; while (phase.load(std::memory_order_acquire) == ph) { if (++spins > 200) std::this_thread::yield(); } }
+  }
+  template <class F> void run(F fn) {
+    if (T == 1) { fn(0u); return; }
+    std::vector<std::thread> th; for (u32 t = 1; t < T; t++) th.emplace_back([&, t] { fn(t); });
+    fn(0u);
+    for (auto& x : th) x.join();
+  }
+};
 
 // maxinfo tables, src/align.rs:873-897 (built once per config on the host with the same libm as the CPU reference)
 i64 f64_as_i64(double v) { if (std::isnan(v)) return 0; if (v >= 9223372036854775807.0) return INT64_MAX; if (v <= -9223372036854775808.0) return INT64_MIN; return (i64)v; }
@@ -97,6 +116,7 @@ struct nb_ctx {
   double map_ms = 0; u64 map_launches = 0, map_reads = 0, all_launches = 0;
   // results
   std::vector<u32> cs_items, slot_dense, dense_prev, dense_ids; std::vector<u64> cs_off;   // dense_prev: the slots slot_dense held last time (only those are reset); dense_ids: slot of callset i, uploaded to fill d_dense on the device
+  u32* h_csr = nullptr; size_t h_csr_cap = 0;   // pinned: compacted dictionary rows of the last finalize
   u8* h_rows = nullptr; size_t h_rows_cap = 0; u64 n_rows_dev = 0;   // pinned: row_scope | row_callset | row_count of the last finalize
   DBuf d_rowwork, d_rowout, d_dense, d_denseids;
   // peer routing of the whole-run scope (nb_route_*): own inbox = inbox_world regions of inbox_cap KeyRec, one per source rank; d_routecur = this rank's fill cursors
@@ -291,6 +311,7 @@ void nb_ctx_free(nb_ctx* c) {
   for (int i = 0; i < 4; i++) if (c->live.ev[i]) cudaEventDestroy(c->live.ev[i]);
   nb_host_free(c->live.host); c->live.host = nullptr;
   nb_host_free(c->h_rows); c->h_rows = nullptr;
+  nb_host_free(c->h_csr); c->h_csr = nullptr;
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : c->ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (int i = 0; i < 2; i++) { if (c->stg[i].copied) cudaEventDestroy(c->stg[i].copied); if (c->stg[i].consumed) cudaEventDestroy(c->stg[i].consumed); }
@@ -559,68 +580,62 @@ static int finalize_impl(nb_ctx* c, nb_counts* out, u64 dense_cells, bool shard 
   u64* d_agg = (u64*)c->d_scratch.p; u32* d_cs = (u32*)((char*)c->d_scratch.p + n_agg * 16);
   CK(cudaMemsetAsync(c->d_nout.p, 0, 16, s));
   nbk::launch_compact(t, d_agg, n_agg, d_cs, n_cs, (unsigned long long*)c->d_nout.p, s); c->all_launches += 2;
-  std::vector<u32> csr((size_t)n_cs * cw);
-  if (n_cs) CK(cudaMemcpyAsync(csr.data(), d_cs, n_cs * (size_t)cw * 4, cudaMemcpyDeviceToHost, s));
+  // dictionary rows into pinned memory (a pageable vector made this 6 MB copy take a millisecond at C4)
+  { const size_t need = (size_t)n_cs * cw * 4 + 64; if (c->h_csr_cap < need) { nb_host_free(c->h_csr); c->h_csr_cap = need + need / 2; c->h_csr = (u32*)nb_host_alloc(c->h_csr_cap); if (!c->h_csr) { c->h_csr_cap = 0; return fail(NB_ERR_CUDA, "pinned host allocation failed"); } } }
+  const u32* csr = c->h_csr;
+  if (n_cs) CK(cudaMemcpyAsync(c->h_csr, d_cs, n_cs * (size_t)cw * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (fstats) ft[2] = fnow();
   // callsets sorted by Vec<String> Ord (utils::sort_score_vector, src/utils.rs:54-59): bytewise on the group names
   const std::vector<u32>& gr = c->lib->group_byte_rank;   // compare ranks, not strings: this sort runs once per job over every callset
-  // Rank matrix (one row of byte ranks + 1 per callset, zero padded: a shorter list sorts first, as Vec<String> Ord has it),
-  // split into buckets by the first rank, buckets sorted on host threads: a 40k-transcript library yields 74k callsets and
-  // this sort, done serially on the dictionary rows, was 11 of the job's 15 ms.
+  // One team of host threads does the whole host side of this phase (spawned once: sixteen threads per step of it cost more
+  // than the steps): rank rows (byte ranks + 1, zero padded: a shorter list sorts first, as Vec<String> Ord has it), buckets
+  // by first rank, buckets sorted as 16-byte {prefix of the first ranks, row} pairs (nearly every comparison is one integer
+  // compare), then the slot -> callset-id table and the item lists in callset order.  A 40k-transcript library yields 74k
+  // callsets; done serially on the dictionary rows this was 11 of the job's 15 ms.
   const u32 gc = c->gcap;
-  std::vector<u32> km((size_t)n_cs * gc, 0u);
   std::vector<u32> slots(n_cs);
-  {
-    const u64 n_groups = gr.size() + 2;
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const u32 T = n_cs >= 16384 ? std::min<u32>(16, hw) : 1, NB = T == 1 ? 1 : 8 * T;
-    auto par = [&](auto fn) {   // fn(t) on T threads
-      if (T == 1) { fn(0u); return; }
-      std::vector<std::thread> th; for (u32 t = 0; t < T; t++) th.emplace_back(fn, t);
-      for (auto& x : th) x.join();
-    };
-    std::vector<u32> bucket(n_cs), bcount((size_t)NB * T, 0);
-    par([&](u32 t) {
-      for (u64 q = (u64)n_cs * t / T; q < (u64)n_cs * (t + 1) / T; q++) {
-        const u32* r = &csr[(size_t)q * cw]; u32* k = &km[(size_t)q * gc];
-        for (u32 x = 0; x < r[1] && x < gc; x++) k[x] = gr[r[4 + x]] + 1;
-        const u32 b = (u32)((u64)k[0] * NB / n_groups); bucket[q] = b; bcount[(size_t)t * NB + b]++;
-      }
-    });
-    std::vector<u64> bstart((size_t)NB * T + 1, 0);   // scatter position of (bucket b, thread t): buckets in order, threads in order inside
-    { u64 at = 0; for (u32 b = 0; b < NB; b++) for (u32 t = 0; t < T; t++) { bstart[(size_t)t * NB + b] = at; at += bcount[(size_t)t * NB + b]; } }
-    std::vector<u64> bbeg(NB + 1, 0); for (u32 b = 0; b < NB; b++) bbeg[b] = bstart[b]; bbeg[NB] = n_cs;
-    par([&](u32 t) { for (u64 q = (u64)n_cs * t / T; q < (u64)n_cs * (t + 1) / T; q++) slots[bstart[(size_t)t * NB + bucket[q]]++] = (u32)q; });
-    auto less = [&](u32 a, u32 b) {
-      const u32* ka = &km[(size_t)a * gc]; const u32* kb = &km[(size_t)b * gc];
-      for (u32 x = 0; x < gc; x++) if (ka[x] != kb[x]) return ka[x] < kb[x];
-      return csr[(size_t)a * cw] < csr[(size_t)b * cw];
-    };
-    // sorted as 16-byte {prefix, index} pairs: the prefix packs the first ranks (four at 16 bits when they fit, else two at
-    // 32), so nearly every comparison is one integer compare; the rank rows are only walked on equal prefixes
-    struct PK { u64 k; u32 idx; u32 pad; };
-    std::vector<PK> pk(n_cs);
-    const bool r16 = n_groups < 65536;
-    par([&](u32 t) {
-      for (u64 q = (u64)n_cs * t / T; q < (u64)n_cs * (t + 1) / T; q++) {   // (position q of `slots`: buckets stay contiguous)
-        const u32 i = slots[q]; const u32* k = &km[(size_t)i * gc];
-        const u64 a = k[0], b = gc > 1 ? k[1] : 0, c2 = gc > 2 ? k[2] : 0, d = gc > 3 ? k[3] : 0;
-        pk[q].k = r16 ? (a << 48) | (b << 32) | (c2 << 16) | d : (a << 32) | b; pk[q].idx = i; pk[q].pad = 0;
-      }
-    });
-    std::atomic<u32> next{0};
-    par([&](u32) { for (u32 b; (b = next.fetch_add(1)) < NB;) std::sort(pk.begin() + bbeg[b], pk.begin() + bbeg[b + 1], [&](const PK& x, const PK& y) { return x.k != y.k ? x.k < y.k : less(x.idx, y.idx); }); });
-    for (u64 q = 0; q < n_cs; q++) slots[q] = pk[q].idx;
-  }
-  // slot -> callset id: only the entries set by the previous finalize are cleared (the table has callset_slots entries — millions
-  // for a big library — and a handful of thousand are in use); the device copy is filled by a kernel from the id list
   std::vector<u32>& dense = c->slot_dense;
   if (dense.size() != c->cs_slots) { dense.assign(c->cs_slots, NONE32); c->dense_prev.clear(); }
-  for (u32 sl : c->dense_prev) dense[sl] = NONE32;
-  c->dense_prev.clear(); c->dense_ids.resize(slots.size());
-  c->cs_items.reserve((size_t)n_cs * 4); c->cs_off.reserve(n_cs + 1);
-  for (u32 i = 0; i < slots.size(); i++) { const u32* r = &csr[(size_t)slots[i] * cw]; dense[r[0]] = i; c->dense_prev.push_back(r[0]); c->dense_ids[i] = r[0]; for (u32 k = 0; k < r[1]; k++) c->cs_items.push_back(r[4 + k]); c->cs_off.push_back(c->cs_items.size()); }
+  for (u32 sl : c->dense_prev) dense[sl] = NONE32;   // only the entries the previous finalize set (the table has callset_slots entries — millions for a big library)
+  c->dense_prev.resize(n_cs); c->dense_ids.resize(n_cs); c->cs_off.resize((size_t)n_cs + 1); c->cs_off[0] = 0;
+  if (n_cs) {
+    const u64 n_groups = gr.size() + 2; const bool r16 = n_groups < 65536;
+    const u32 T = n_cs >= 16384 ? std::min<u32>(16, std::max(1u, std::thread::hardware_concurrency())) : 1, NB = T == 1 ? 1 : 8 * T;
+    std::unique_ptr<u32[]> km(new u32[(size_t)n_cs * gc]);
+    struct PK { u64 k; u32 idx; u32 pad; };
+    std::unique_ptr<PK[]> pk(new PK[n_cs]);
+    std::vector<u32> bucket(n_cs), bcount((size_t)NB * T, 0), rank_of(n_cs); std::vector<u64> bstart((size_t)NB * T + 1, 0), bbeg(NB + 1, 0), part(T + 1, 0);
+    std::atomic<u32> next{0};
+    auto less = [&](u32 a, u32 b) { const u32* ka = &km[(size_t)a * gc]; const u32* kb = &km[(size_t)b * gc]; for (u32 x = 0; x < gc; x++) if (ka[x] != kb[x]) return ka[x] < kb[x]; return csr[(size_t)a * cw] < csr[(size_t)b * cw]; };
+    HostTeam team(T);
+    team.run([&](u32 t) {
+      const u64 q0 = n_cs * t / T, q1 = n_cs * (t + 1) / T;
+      for (u64 q = q0; q < q1; q++) {
+        const u32* r = &csr[(size_t)q * cw]; u32* k = &km[(size_t)q * gc];
+        for (u32 x = 0; x < gc; x++) k[x] = x < r[1] ? gr[r[4 + x]] + 1 : 0u;
+        const u32 b = (u32)((u64)k[0] * NB / n_groups); bucket[q] = b; bcount[(size_t)t * NB + b]++;
+      }
+      team.barrier();
+      if (t == 0) { u64 at = 0; for (u32 b = 0; b < NB; b++) { bbeg[b] = at; for (u32 u = 0; u < T; u++) { bstart[(size_t)u * NB + b] = at; at += bcount[(size_t)u * NB + b]; } } bbeg[NB] = n_cs; }
+      team.barrier();
+      for (u64 q = q0; q < q1; q++) {
+        const u64 at = bstart[(size_t)t * NB + bucket[q]]++; const u32* k = &km[(size_t)q * gc];
+        const u64 a = k[0], b = gc > 1 ? k[1] : 0, c2 = gc > 2 ? k[2] : 0, d = gc > 3 ? k[3] : 0;
+        pk[at].k = r16 ? (a << 48) | (b << 32) | (c2 << 16) | d : (a << 32) | b; pk[at].idx = (u32)q; pk[at].pad = 0;
+      }
+      team.barrier();
+      for (u32 b; (b = next.fetch_add(1)) < NB;) std::sort(pk.get() + bbeg[b], pk.get() + bbeg[b + 1], [&](const PK& x, const PK& y) { return x.k != y.k ? x.k < y.k : less(x.idx, y.idx); });
+      team.barrier();
+      { u64 sum = 0; for (u64 i = q0; i < q1; i++) { const u32 row = pk[i].idx; slots[i] = row; rank_of[row] = (u32)i; sum += csr[(size_t)row * cw + 1]; } part[t + 1] = sum; }
+      team.barrier();
+      if (t == 0) { for (u32 u = 0; u < T; u++) part[u + 1] += part[u]; c->cs_items.resize(part[T]); }
+      // the dictionary rows arrive in (roughly) slot order — k_compact_cs walks the slots — so the table is written in ROW order
+      for (u64 q = q0; q < q1; q++) { const u32 sl = csr[(size_t)q * cw]; dense[sl] = rank_of[q]; c->dense_prev[q] = sl; c->dense_ids[rank_of[q]] = sl; }
+      team.barrier();
+      { u64 at = part[t]; for (u64 i = q0; i < q1; i++) { const u32* r = &csr[(size_t)slots[i] * cw]; for (u32 k = 0; k < r[1]; k++) c->cs_items[at + k] = r[4 + k]; at += r[1]; c->cs_off[i + 1] = at; } }
+    });
+  }
   auto upload_dense = [&]() -> int {
     CK(c->d_dense.ensure(dense.size() * 4, s)); CK(c->d_denseids.ensure(c->dense_ids.size() * 4 + 16, s));
     CK(cudaMemsetAsync(c->d_dense.p, 0xFF, dense.size() * 4, s));
