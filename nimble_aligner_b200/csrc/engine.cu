@@ -247,7 +247,7 @@ int nb_ctx_create(const nb_index* index, const nb_library* lib, int device, void
       o[0] = nr.start_lo; o[1] = nr.len; o[2] = nr.colour; o[3] = nr.exts_hi;
       memcpy(o + 4, &index->redge[4 * v], 16); memcpy(o + 8, &index->col_meta[4 * (size_t)nr.colour], 16);
       u64 st = (u64)nr.start_lo | ((u64)(nr.exts_hi >> 8) << 32), q[2] = {0, 0};
-      for (u32 i = 0; i < std::min<u32>(nr.len, 64); i++) q[i >> 5] |= base_at(st + i) << (2 * (i & 31));
+      for (u32 i = 0; i < 64 && (u32)K + i < nr.len; i++) q[i >> 5] |= base_at(st + K + i) << (2 * (i & 31));   // unitig bases [K, K + 64): a forward compare never starts below base K
       memcpy(o + 12, q, 16);
     }
     up(upload(c->d_walk, w, s));

@@ -35,7 +35,7 @@ struct DevIndex {
   const u64* unitig;
   const uint4* node;      // {start_lo, len, colour, lext | rext<<4 | start_hi<<8}
   const uint4* walk;      // 64-byte record per unitig, everything one forward step needs in one DRAM burst / two L2 sectors:
-                          // [0] node {start_lo, len, colour, exts_hi}  [1] right edges by base  [2] col_meta of its colour  [3] its first 64 bases (2 x u64)
+                          // [0] node {start_lo, len, colour, exts_hi}  [1] right edges by base  [2] col_meta of its colour  [3] its bases [K, K + 64) (2 x u64)
   const uint4* ledge;
   const u32* col_off; const u32* col_ids;
   const uint4* col_meta;  // {uni_off, uni_size (0: none), mask_lo, mask_hi} per colour (host.hpp nb_index::col_meta)

@@ -372,17 +372,23 @@ __global__ void __launch_bounds__(128, NB_WALK_MINB) k_walk(BatchDev b, DevIndex
     // of them — touches nothing else of the index.
     __syncwarp();   // lanes coming out of the re-seed / left-extension paths rejoin the walkers here: without it the compiler lets them run the window code below a second time on their own
     if (st == ST_WALK) {
-      u64 s0 = 0, s1 = 0; bool fresh = false;
+      // Every step reads the record's second sector — colour bitmap metadata and the unitig's bases [K, K + 64): a forward
+      // compare never starts below base K — so a stretch that continues into a second window finds its bases where the first
+      // window found them (an L2 hit) instead of in the unitig array (three scattered loads on a divergent path in 86 % of
+      // the iterations, and a DRAM burst each when the index lives in HBM).
+      const u64* wp = (const u64*)(ix.walk + 4 * (u64)node);
+      const Bucket fb = ld_bucket(wp, 1);
+      const u64 s0 = fb.k2, s1 = fb.k3;
       if (enter) {
-        const u64* wp = (const u64*)(ix.walk + 4 * (u64)node);
-        const Bucket fa = ld_bucket(wp, 0), fb = ld_bucket(wp, 1);
+        const Bucket fa = ld_bucket(wp, 0);
         const u32 nlen = (u32)(fa.k0 >> 32);
         start_lo = (u32)fa.k0; nexts = (u32)(fa.k1 >> 32); e01 = fa.k2; e23 = fa.k3;
         kp += K; cov += K;
         acc.add((u32)fa.k1, make_uint4((u32)fb.k0, (u32)(fb.k0 >> 32), (u32)fb.k1, (u32)(fb.k1 >> 32)), wc); wc.nodes++;
         off += K; m = min(n - kp, nlen - off); snp = 0;
-        s0 = fb.k2; s1 = fb.k3; fresh = true; enter = false;
+        enter = false;
       }
+      const u32 o2 = off - K;                    // record base j = unitig base K + j (off >= K from the first step on)
       // the read's bases [kp, kp + 64): the window to compare and, right behind it, the base that picks the next edge (the
       // row's zero pad word makes word w + 1 always readable), so a step never waits for a second, dependent read load
       const u32 rsh = (kp & 31) * 2;
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(128, NB_WALK_MINB) k_walk(BatchDev b, DevIndex
       bool brk = false;
       if (c) {
         u64 uw;
-        if (fresh && off + c <= 64) { if (off < 32) { u32 sh = 2 * off; uw = sh ? (s0 >> sh) | (s1 << (64 - sh)) : s0; } else uw = s1 >> (2 * (off - 32)); }
+        if (o2 + c <= 64) { if (o2 < 32) { u32 sh = 2 * o2; uw = sh ? (s0 >> sh) | (s1 << (64 - sh)) : s0; } else uw = s1 >> (2 * (o2 - 32)); }
         else uw = uwin3(ix.unitig, ((u64)start_lo | ((u64)(nexts >> 8) << 32)) + off);
         const u64 x = uw ^ rw;
         u64 d = (x | (x >> 1)) & 0x5555555555555555ULL;
