@@ -606,7 +606,8 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
   else if (const char* e2 = getenv("NB_BAM_WINDOW_MB")) window_bytes = (size_t)strtoull(e2, nullptr, 10) << 20;
   if (rc != NB_OK) { cleanup(); return rc; }
   const size_t BATCH_PAIRS = 1u << 20;
-  const int GZ_LEVEL = 4;
+  int GZ_LEVEL = 4;   // NB_BAM_GZ_LEVEL=1..9 overrides (the rows are the same, the members smaller or faster to make)
+  if (const char* e = getenv("NB_BAM_GZ_LEVEL")) { int v = atoi(e); if (v >= 1 && v <= 9) GZ_LEVEL = v; }
   // Three stages run concurrently on consecutive batches: (F) the host threads fill batch k+1 into pinned buffers,
   // (D) the device aligns batch k and its counts are finalized, (R) the host threads format + gzip the rows of batch k-1.
   struct Pinned { u8* p = nullptr; size_t cap = 0; int ensure(size_t n) { if (n <= cap) return NB_OK; nb_host_free(p); cap = n + n / 4 + 4096; p = (u8*)nb_host_alloc(cap); if (!p) { cap = 0; return fail(NB_ERR_CUDA, "pinned host allocation failed"); } return NB_OK; } ~Pinned() { nb_host_free(p); } };
