@@ -110,7 +110,10 @@ __device__ __forceinline__ bool coop_find(const DevIndex& ix, const ProbePolicy&
 enum { ST_DONE = 0, ST_SEED = 1, ST_WALK = 2 };
 
 // ---- k_seed: 128 reads per block.  Gated / seedless reads get their final record here, seeded reads go to the list.
-constexpr int SEED_BLOCK = 128;
+#ifndef NB_SEED_BLOCK
+#define NB_SEED_BLOCK 128
+#endif
+constexpr int SEED_BLOCK = NB_SEED_BLOCK;
 constexpr int SEED_R0 = 16;    // seeds per queue entry in the first cooperative round (an error in the first k-mer is passed within 10)
 constexpr int SEED_R1 = 32;    // ... in the following rounds (off-target reads: all remaining seeds)
 template <int COUNT_WORK, int BLOOM>
