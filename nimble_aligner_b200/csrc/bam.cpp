@@ -388,6 +388,8 @@ struct GroupStreamer {
   Bgzf z; bool force_paired = false; int threads = 1; size_t window_bytes = (size_t)256 << 20;
   bool header_done = false, eof = false, ended = false; u64 groups_sent = 0, records_seen = 0; size_t peak_window = 0;
   std::string last_umi, last_cb; bool have_last = false;     // key of the last record sent (cross-window coincidence check)
+  double t_inflate = 0, t_scan = 0, t_keys = 0, t_runs = 0, t_emit = 0, t_groups = 0;   // phase times (NB_BAM_STATS)
+  static double clk() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
   int open(const std::string& path, bool fp, int th, size_t wb) { force_paired = fp; threads = std::max(1, th); window_bytes = std::max<size_t>(wb, 1 << 16); return z.open(path); }
   // fills w from the file position and the carry-over of `prev` (nullptr for the first window).  done: nothing was produced
   // and nothing more will come.
@@ -403,7 +405,9 @@ struct GroupStreamer {
     }
     size_t grow = window_bytes;
     for (;;) {   // (repeats only when the window could not emit anything: one giant UMI run, or a header larger than the window)
+      double tc = clk();
       if (!eof) { size_t n_out = 0; int rc = z.next(w.data, w.len, grow, threads, n_out, eof); if (rc) return rc; z.compact(); w.len += n_out; }
+      t_inflate += clk() - tc; tc = clk();
       peak_window = std::max(peak_window, w.len);
       size_t cur = 0;
       if (!header_done) {
@@ -429,7 +433,9 @@ struct GroupStreamer {
       }
       const size_t tail = cur;    // first byte that is not part of a complete record
       std::vector<Rec>& all = w.all;
+      t_scan += clk() - tc; tc = clk();
       parallel_ranges(threads, all.size(), [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) all[i].scan_keys(); });
+      t_keys += clk() - tc; tc = clk();
       if (all.size() >= 0xFFFFFFFFull) return fail(NB_ERR_UNSUPPORTED, "more than 2^32 records in one window");
       std::vector<u32> kept; kept.reserve(all.size());
       for (size_t i = 0; i < all.size(); i++) {
@@ -444,6 +450,7 @@ struct GroupStreamer {
       std::vector<size_t> run;   // start of every UMI run in `kept`
       for (size_t j = 0; j < kept.size(); j++) if (j == 0 || !same(all[kept[j]].umi, all[kept[j]].umi_len, all[kept[j - 1]].umi, all[kept[j - 1]].umi_len)) run.push_back(j);
       const size_t nr = run.size(); run.push_back(kept.size());
+      t_runs += clk() - tc; tc = clk();
       // one run -> the records the sorted reader hands on (CB sort unless it is the file's last run, dummy mates, pairing)
       auto emit_run = [&](size_t r, std::vector<Rec>& out, std::vector<Rec>& buf, std::vector<Rec>& tmp) {
         buf.clear(); for (size_t j = run[r]; j < run[r + 1]; j++) buf.push_back(all[kept[j]]);
@@ -492,6 +499,7 @@ struct GroupStreamer {
       if (cut) { ended = true; w.carry_from = w.len; }   // the reference's reader stops for good at an empty buffer
       const bool final = eof || ended;
       header_done = true; records_seen += all.size();
+      t_emit += clk() - tc; tc = clk();
       std::vector<u64>& gstart = w.gstart; gstart.clear();
       if (stream.empty()) { gstart.assign(1, 0); if (final && groups_sent == 0) gstart.push_back(0); done = gstart.size() < 2; return NB_OK; }
       // groups: runs of equal (UMI + CB[..len-2]) over the stream
@@ -503,6 +511,7 @@ struct GroupStreamer {
       if (final && groups_sent + (gstart.size() - 1) >= 2) { stream.resize(gstart[gstart.size() - 2]); gstart.pop_back(); }   // the last group is never sent when a group was sent before
       groups_sent += gstart.size() - 1;
       if (!stream.empty()) { const Rec& l = stream.back(); last_umi.assign(l.umi, l.umi_len); last_cb.assign(l.cb ? l.cb : "", l.cb_len); have_last = true; }
+      t_groups += clk() - tc;
       return NB_OK;
     }
   }
@@ -844,7 +853,9 @@ extern "C" int nb_bam_dump_groups(const char* input_file, int force_bam_paired, 
     GroupStreamer gs; Window win[2]; bool done = false; int cur = 0;
     rc = getenv("NB_BAM_SERIAL_GROUPING") ? NEED_WHOLE : gs.open(input_file, force_bam_paired != 0, std::max(1, num_cores), window_bytes);
     if (rc == NB_OK) rc = gs.next(win[0], nullptr, done);
-    while (rc == NB_OK && !done) { dump(win[cur].stream, win[cur].gstart); rc = gs.next(win[cur ^ 1], &win[cur], done); cur ^= 1; }
+    const bool none = out_path[0] && !strcmp(out_path, "/dev/null") && getenv("NB_BAM_DUMP_NONE");   // producer only (timing the reader)
+    while (rc == NB_OK && !done) { if (!none) dump(win[cur].stream, win[cur].gstart); rc = gs.next(win[cur ^ 1], &win[cur], done); cur ^= 1; }
+    if (getenv("NB_BAM_STATS")) fprintf(stderr, "bam producer: inflate %.2fs, record scan %.2fs, key scan %.2fs, runs %.2fs, emit %.2fs, groups %.2fs\n", gs.t_inflate, gs.t_scan, gs.t_keys, gs.t_runs, gs.t_emit, gs.t_groups);
   }
   if (rc == NEED_WHOLE) {
     if (ftruncate(fileno(f), 0) != 0 || fseek(f, 0, SEEK_SET) != 0) { fclose(f); return fail(NB_ERR_IO, "could not rewind the output"); }
