@@ -419,10 +419,60 @@ struct GroupStreamer {
         if (!ok) { if (eof) return fail(NB_ERR_PARSE, w.len < 12 ? "not a BAM file" : "truncated BAM header"); grow *= 2; continue; }
         cur = p;
       }
-      // complete records of the window
+      // complete records of the window.  The records form a chain (each block_size leads to the next record), and walking it
+      // serially was a quarter of the producer's critical path, every step a cache miss on data another core just inflated.
+      // So the window is cut into segments walked at the same time: a segment starts at a GUESSED record start (the first
+      // offset behind its boundary from which four consecutive records look sound) and the guess is never trusted — the
+      // segments are only accepted if each one begins exactly where the previous one's walk ended, else the serial walk runs.
       w.all.clear();
       const RawBuf& d = w.data;
-      while (cur + 4 <= w.len) {
+      const size_t walk_from = cur;
+      auto sound = [&](size_t o, size_t& next) -> bool {   // does a complete, self-consistent record start at o?
+        if (o + 36 > w.len) return false;
+        u32 bs; memcpy(&bs, &d[o], 4);
+        if (bs < 32 || bs > (1u << 24) || o + 4 + bs > w.len) return false;
+        const u8* q = &d[o + 4]; const u32 lrn = q[8], ncig = q[12] | (q[13] << 8); u32 lseq; memcpy(&lseq, q + 16, 4);
+        i32 refid; memcpy(&refid, q, 4);
+        if (lrn == 0 || refid < -1 || 32ull + lrn + 4ull * ncig + ((u64)lseq + 1) / 2 + (u64)lseq > bs || q[32 + lrn - 1] != 0) return false;
+        next = o + 4 + bs; return true;
+      };
+      bool walked = false;
+      const size_t par_min_bytes = getenv("NB_BAM_PAR_MIN_BYTES") ? (size_t)strtoull(getenv("NB_BAM_PAR_MIN_BYTES"), nullptr, 10) : ((size_t)8 << 20);   // (tests force the parallel passes on small files)
+      const size_t par_min_recs = getenv("NB_BAM_PAR_MIN_RECS") ? (size_t)strtoull(getenv("NB_BAM_PAR_MIN_RECS"), nullptr, 10) : 65536;
+      const int WT = (w.len - cur > par_min_bytes) ? threads : 1;
+      if (WT > 1) {
+        std::vector<std::vector<Rec>> part(WT); std::vector<size_t> seg_start(WT, 0), seg_end(WT, 0); std::vector<char> ok(WT, 1);
+        const size_t span = w.len - walk_from;
+        parallel_ranges(WT, (size_t)WT, [&](size_t ta, size_t tb, int) {
+          for (size_t t = ta; t < tb; t++) {
+            const size_t lo = walk_from + span * t / WT, hi = walk_from + span * (t + 1) / WT;   // records STARTING in [lo, hi) belong to segment t
+            size_t o = lo;
+            if (t > 0) {   // guess: first offset >= lo that begins a chain of four sound records (or runs into the window's end)
+              bool found = false;
+              for (; o < hi && o < lo + ((size_t)1 << 20); o++) { size_t n1 = o, n2; int k = 0; while (k < 4 && sound(n1, n2)) { n1 = n2; k++; } if (k == 4 || (k > 0 && n1 + 4 > w.len)) { found = true; break; } }
+              if (!found) { ok[t] = 0; continue; }
+            }
+            seg_start[t] = o;
+            std::vector<Rec>& out = part[t]; out.reserve((hi - lo) / 160 + 16);
+            while (o < hi) { size_t nx; if (!sound(o, nx)) break; Rec r; r.p = &d[o + 4]; r.block = (u32)(nx - o - 4); out.push_back(r); o = nx; }
+            seg_end[t] = o;     // first offset this segment did not consume: a record start >= hi, the cut record, or something unsound
+          }
+        });
+        bool good = true;
+        for (int t = 0; t < WT && good; t++) good = ok[t] && (t == 0 || seg_start[t] == seg_end[t - 1]);
+        if (good) {
+          // the last segment's end must be where the serial walk would stop: at a record the window cuts (or at the window's end)
+          const size_t e = seg_end[WT - 1]; u32 bs = 0; if (e + 4 <= w.len) memcpy(&bs, &d[e], 4);
+          good = e + 4 > w.len || (bs >= 32 && e + 4 + bs > w.len);
+          if (good) {
+            size_t total = 0; std::vector<size_t> at(WT + 1, 0); for (int t = 0; t < WT; t++) { at[t] = total; total += part[t].size(); }
+            w.all.resize(total);
+            parallel_ranges(WT, (size_t)WT, [&](size_t ta, size_t tb, int) { for (size_t t = ta; t < tb; t++) if (!part[t].empty()) memcpy(&w.all[at[t]], part[t].data(), part[t].size() * sizeof(Rec)); });
+            cur = e; walked = true;
+          }
+        }
+      }
+      while (!walked && cur + 4 <= w.len) {
         u32 bs; memcpy(&bs, &d[cur], 4);
         if (bs < 32) { if (!eof) return fail(NB_ERR_PARSE, "corrupt BAM record (block size below the fixed fields)"); break; }   // (trailing garbage at the very end is ignored, as before)
         if (cur + 4 + bs > w.len) break;                                                        // cut by the window: carried over
@@ -437,18 +487,38 @@ struct GroupStreamer {
       parallel_ranges(threads, all.size(), [&](size_t a, size_t b, int) { for (size_t i = a; i < b; i++) all[i].scan_keys(); });
       t_keys += clk() - tc; tc = clk();
       if (all.size() >= 0xFFFFFFFFull) return fail(NB_ERR_UNSUPPORTED, "more than 2^32 records in one window");
-      std::vector<u32> kept; kept.reserve(all.size());
-      for (size_t i = 0; i < all.size(); i++) {
-        const Rec& r = all[i];
-        if (!r.is_paired() && force_paired) continue;
-        if (!r.cb) continue;
-        if (!r.umi) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
-        if (r.umi_len == 10 && !memcmp(r.umi, "AAAAAAAAAA", 10)) continue;
-        if (r.umi_len == 0) return NEED_WHOLE;
-        kept.push_back((u32)i);
+      // which records the sorted reader keeps, and where its UMI runs start: flags in parallel, compaction by thread-local
+      // counts; the first offending record IN FILE ORDER decides between the two failures, as the serial loop did
+      std::vector<u32> kept; std::vector<size_t> run;
+      {
+        const int T = all.size() > par_min_recs ? threads : 1;
+        std::vector<u8> flag(all.size(), 0); std::vector<size_t> cnt(T + 1, 0), bad_at(T, (size_t)-1); std::vector<int> bad_kind(T, 0);
+        parallel_ranges(T, all.size(), [&](size_t a, size_t b, int t) {
+          size_t c = 0;
+          for (size_t i = a; i < b; i++) {
+            const Rec& r = all[i];
+            if (!r.is_paired() && force_paired) continue;
+            if (!r.cb) continue;
+            if (!r.umi) { bad_at[t] = i; bad_kind[t] = 1; break; }
+            if (r.umi_len == 10 && !memcmp(r.umi, "AAAAAAAAAA", 10)) continue;
+            if (r.umi_len == 0) { bad_at[t] = i; bad_kind[t] = 2; break; }
+            flag[i] = 1; c++;
+          }
+          cnt[t + 1] = c;
+        });
+        { size_t first = (size_t)-1; int kind = 0; for (int t = 0; t < T; t++) if (bad_at[t] < first) { first = bad_at[t]; kind = bad_kind[t]; }
+          if (kind == 1) return fail(NB_ERR_PARSE, "Error -- Could not read UMI.");
+          if (kind == 2) return NEED_WHOLE; }
+        for (int t = 0; t < T; t++) cnt[t + 1] += cnt[t];
+        kept.resize(cnt[T]);
+        parallel_ranges(T, all.size(), [&](size_t a, size_t b, int t) { size_t at = cnt[t]; for (size_t i = a; i < b; i++) if (flag[i]) kept[at++] = (u32)i; });
+        // run heads
+        const size_t nk = kept.size(); std::vector<u8> head(nk, 0); std::vector<size_t> hc(T + 1, 0);
+        parallel_ranges(T, nk, [&](size_t a, size_t b, int t) { size_t c = 0; for (size_t j = a; j < b; j++) if (j == 0 || !same(all[kept[j]].umi, all[kept[j]].umi_len, all[kept[j - 1]].umi, all[kept[j - 1]].umi_len)) { head[j] = 1; c++; } hc[t + 1] = c; });
+        for (int t = 0; t < T; t++) hc[t + 1] += hc[t];
+        run.resize(hc[T]);
+        parallel_ranges(T, nk, [&](size_t a, size_t b, int t) { size_t at = hc[t]; for (size_t j = a; j < b; j++) if (head[j]) run[at++] = j; });
       }
-      std::vector<size_t> run;   // start of every UMI run in `kept`
-      for (size_t j = 0; j < kept.size(); j++) if (j == 0 || !same(all[kept[j]].umi, all[kept[j]].umi_len, all[kept[j - 1]].umi, all[kept[j - 1]].umi_len)) run.push_back(j);
       const size_t nr = run.size(); run.push_back(kept.size());
       t_runs += clk() - tc; tc = clk();
       // one run -> the records the sorted reader hands on (CB sort unless it is the file's last run, dummy mates, pairing)

@@ -169,3 +169,24 @@ def test_feeder_rejects_size_fields_that_point_outside_the_file(tmp_path):
         nb.bam_dump_groups(path, out, num_cores=2)                                  # groups (the field is ignored) or a loud error, never a crash
     except nb.NbError:
         pass
+
+
+@pytest.mark.parametrize("force_paired", [False, True])
+@pytest.mark.parametrize("window_kb", [64, 700, 1 << 20])
+def test_parallel_record_walk_and_run_detection(tmp_path, monkeypatch, force_paired, window_kb):
+    """The windowed producer walks a window's record chain in segments (guessed starts, accepted only when every segment
+    begins where the previous one ended) and finds the kept records / UMI runs with thread-local counts.  Both are normally
+    used on windows of megabytes only; NB_BAM_PAR_MIN_* forces them on this small file, at several window sizes, and the
+    dump must stay byte-identical to the serial readers' (which define the semantics)."""
+    L = synth.SynthLibrary(seed=7, n_fam=20, n_all=5)
+    bam = make_bam(str(tmp_path / "w.bam"), L, n_groups=3000, seed=11)
+    ser, par = str(tmp_path / "ser.tsv"), str(tmp_path / "par.tsv")
+    monkeypatch.setenv("NB_BAM_SERIAL_GROUPING", "1")
+    nb.bam_dump_groups(bam, ser, force_bam_paired=force_paired, num_cores=5)
+    monkeypatch.delenv("NB_BAM_SERIAL_GROUPING")
+    monkeypatch.setenv("NB_BAM_PAR_MIN_BYTES", "1")
+    monkeypatch.setenv("NB_BAM_PAR_MIN_RECS", "1")
+    monkeypatch.setenv("NB_BAM_WINDOW_KB", str(window_kb))
+    nb.bam_dump_groups(bam, par, force_bam_paired=force_paired, num_cores=5)
+    a, b = open(ser, "rb").read(), open(par, "rb").read()
+    assert a == b and a.count(b"\n") > (300 if force_paired else 3000)
