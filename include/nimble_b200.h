@@ -315,6 +315,11 @@ int nb_process_fastq_devices(const char* const* input_files, uint32_t n_inputs, 
  * "SEQ1<TAB>SEQ2") — parity tests of the parallel plain-text parser against a sequential one.  chunk_bytes: bytes of file per
  * parse task (0 = default 8 MiB); num_cores host threads are split over the input files. */
 int nb_fastq_dump(const char* const* input_files, uint32_t n_inputs, int num_cores, uint64_t chunk_bytes, const char* out_path);
+/* host-only: the file drivers' own inflate (flate2 / htslib's place in src/parse/fastq.rs:21-43 and
+ * src/parse/sorted_bam_reader.rs:22-41) on a buffer — parity tests against zlib.  raw != 0: one raw deflate stream in one
+ * piece (a BGZF block); raw == 0: concatenated gzip members through windows of `window` bytes (0 = one window), CRC-32 and
+ * ISIZE checked.  NB_ERR_PARSE on a damaged stream, NB_ERR_OVERFLOW when out_cap is too small. */
+int nb_inflate(const void* in, uint64_t in_len, int raw, uint64_t window, void* out, uint64_t out_cap, uint64_t* out_len);
 
 /* process::bam::process (src/process/bam.rs:45-243) behind the same library loop: BGZF/BAM decode on host threads,
  * UMIReader / SortedBamReader grouping (src/parse/bam.rs, src/parse/sorted_bam_reader.rs) with their quirks, one scoped

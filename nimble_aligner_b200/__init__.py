@@ -136,6 +136,7 @@ _SIGS = {
     "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),
     "nb_bam_dump_groups": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "nb_fastq_dump": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_char_p]),
+    "nb_inflate": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "nb_process_fastq_devices": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32]),
     "nb_process_bam": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]),
     "nb_process_fastq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]),
@@ -624,6 +625,16 @@ def process_bam(input_file, reference_json_paths, output_paths, strand_filter="u
     """process::bam::process behind main.rs's library loop (src/process/bam.rs:45-243, src/bin/main.rs:95-156)."""
     _ck(lib().nb_process_bam(str(input_file).encode(), _strs(reference_json_paths), _strs(output_paths), len(reference_json_paths),
                              CHEM[strand_filter], trim.encode() if trim else None, num_cores, int(force_bam_paired), device))
+
+
+def inflate(data, raw=False, window=0, out_cap=None):
+    """The file drivers' own inflate on a buffer (tests against zlib): raw deflate in one piece, or gzip members through
+    windows of `window` bytes.  Returns the bytes; NbError on a damaged stream."""
+    cap = int(out_cap) if out_cap is not None else max(1 << 16, 1100 * len(data))
+    out = C.create_string_buffer(max(cap, 1))
+    n = C.c_uint64(0)
+    _ck(lib().nb_inflate(bytes(data), len(data), int(raw), int(window), out, cap, C.byref(n)))
+    return out.raw[:n.value]
 
 
 def bam_dump_groups(input_file, out_path, force_bam_paired=False, num_cores=1):

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "host.hpp"
+#include "inflate.hpp"
 
 using namespace nb;
 typedef int32_t i32;
@@ -94,13 +95,17 @@ struct Bgzf {
     if (out.size() < keep + utot) { RawBuf nb2; if (!nb2.alloc(keep + utot + (utot >> 3) + 64)) return fail(NB_ERR_IO, "out of memory inflating " + path); if (keep) memcpy(nb2.data(), out.data(), keep); std::swap(out.p, nb2.p); std::swap(out.n, nb2.n); }
     std::atomic<size_t> next_blk(0); std::atomic<int> bad(0);
     u8* dst = out.data() + keep; const u8* src = cbuf.data();
+    const bool check_crc = !getenv("NB_BAM_NO_CRC");
     auto work = [&]() {
+      // inflate.hpp's decoder, one block in one piece into its place in the window (it never writes past the block's
+      // ISIZE bytes: the neighbouring blocks are being written by other threads); the block's CRC-32 is checked like htslib does
+      std::unique_ptr<nbz::Inflater> inf(new nbz::Inflater());
       for (;;) { size_t i = next_blk.fetch_add(1); if (i >= blks.size()) break; const Blk& b = blks[i]; if (!b.ulen) continue;
-        z_stream zs; memset(&zs, 0, sizeof zs);
-        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; continue; }
-        zs.next_in = const_cast<u8*>(src + b.off); zs.avail_in = (uInt)b.clen; zs.next_out = dst + b.uoff; zs.avail_out = (uInt)b.ulen;
-        int rc = inflate(&zs, Z_FINISH); if (rc != Z_STREAM_END || zs.total_out != b.ulen) bad = 1;
-        inflateEnd(&zs); }
+        inf->start(src + b.off, src + b.off + b.clen);
+        u8* const o = dst + b.uoff; u8* q = o;
+        const int rc = inf->run(o, q, o + b.ulen);
+        u32 want; memcpy(&want, src + b.off + b.clen, 4);
+        if (rc != nbz::INF_END || (size_t)(q - o) != b.ulen || (check_crc && (u32)crc32_z(0L, o, b.ulen) != want)) bad = 1; }
     };
     std::vector<std::thread> th; for (int t = 1; t < std::max(1, threads) && (size_t)t < blks.size(); t++) th.emplace_back(work);
     work(); for (auto& t : th) t.join();
@@ -590,54 +595,74 @@ struct GroupStreamer {
 // clipped length / start of a record's sequence (strip_nonbio_regions, src/parse/bam.rs:258-268)
 inline void clip_of(const Rec& r, size_t& a, size_t& b) { size_t n = r.l_seq(); a = 0; b = n; if (n == 124) { if (r.is_reverse()) b = n - CLIP_LENGTH; else a = CLIP_LENGTH; } }
 
+// ---- the rows stage's formatter.  A 10x run writes two records' worth of metadata per output row (hundreds of millions of
+// records), so this is written for throughput: one pass over the aux block, no per-field search, no snprintf, one resize.
+// The reference looks a field up by the first two bytes of its NAME (rust-htslib aux(b"QNAME") -> bam_aux_get reads two
+// bytes), so several fields share a tag ("MA": MATE_REVERSE, MATE_UNMAPPED, MAPQ, MATE_POS): fields are put into CLASSES
+// by those two bytes, and the aux pass records the first occurrence of each class.
+struct FieldClasses {
+  u8 of_key[65536]; u8 of_field[38]; int n = 0;
+  FieldClasses() { memset(of_key, 0, sizeof of_key); for (int i = 0; i < 38; i++) { u32 key = (u8)FIELDS[i][0] | ((u32)(u8)FIELDS[i][1] << 8); if (!of_key[key]) of_key[key] = (u8)++n; of_field[i] = of_key[key]; } }
+};
+const FieldClasses FCLS;
+inline char* put_u32(char* p, u32 v) { char t[10]; int n = 0; do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *p++ = t[--n]; return p; }
+inline char* put_i32(char* p, i32 v) { if (v < 0) { *p++ = '-'; return put_u32(p, (u32)(-(i64)v)); } return put_u32(p, (u32)v); }
+inline char* put_bool(char* p, bool b) { if (b) { memcpy(p, "true", 4); return p + 4; } memcpy(p, "false", 5); return p + 5; }
+
 // the 36 reported metadata values of one record, tab-joined, straight into the output line (same values as parse_fields)
 void append_data_values(const Rec& r, std::string& s) {
-  struct Aux { char t0, t1, ty; const char* v; } tab[48]; int nt = 0;
+  const char* zv[40]; u32 zl[40]; u64 seen = 0, isz = 0;
   { const u8* a = r.aux(); const u8* e = r.end();
-    while (a + 3 <= e && nt < 48) {
-      char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2]; a += 3; const u8* v = a; bool ok = true;
-      switch (ty) {
-        case 'A': case 'c': case 'C': a += 1; break; case 's': case 'S': a += 2; break; case 'i': case 'I': case 'f': a += 4; break;
-        case 'Z': case 'H': while (a < e && *a) a++; a++; break;
-        case 'B': { if (a + 5 > e) { ok = false; break; } char st = (char)a[0]; u32 n; memcpy(&n, a + 1, 4); size_t w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; a += 5 + w * n; break; }
-        default: ok = false; break;
-      }
-      if (!ok) break;   // aux_z gives up at a malformed / unknown field: nothing behind it is visible
-      tab[nt++] = {t0, t1, ty, (const char*)v};
+    while (a + 3 <= e) {   // same rule as Rec::aux_z: the FIRST aux with the tag decides, a string only when NUL-terminated inside the record
+      const u32 key = a[0] | ((u32)a[1] << 8); const char ty = (char)a[2]; a += 3; const u8* v = a; u32 zlen = 0; bool zok = false;
+      const bool ok = Rec::aux_skip(ty, a, e, zlen, zok);
+      const u32 c = FCLS.of_key[key];
+      if (c && !((seen >> c) & 1)) { seen |= 1ull << c; if (ty == 'Z' && zok) { isz |= 1ull << c; zv[c] = (const char*)v; zl[c] = zlen; } }
+      if (!ok) break;
     } }
-  u32 fl = r.flag(); bool rev = fl & 16, paired = fl & 1, unm = fl & 4, munm = fl & 8, mrev = fl & 32, first = fl & 64;
-  bool firstf = true; char num[24];
+  size_t bound = 36 * 13 + r.qname_len();
+  if (isz) for (int i = 0; i < 38; i++) { const u32 c = FCLS.of_field[i]; if ((isz >> c) & 1) bound += zl[c]; }
+  const size_t old = s.size(); s.resize(old + bound);
+  char* p = &s[old];
+  const u32 fl = r.flag(); const bool rev = fl & 16, paired = fl & 1, unm = fl & 4, munm = fl & 8, mrev = fl & 32, first = fl & 64;
   for (int i = 0; i < 38; i++) {
     if (i == 1 || i == 15) continue;
-    if (!firstf) s += '\t';
-    firstf = false;
-    if (i == 37 && r.skip_align >= 0) { s += r.skip_align ? "TRUE" : "FALSE"; continue; }
-    const char* tag = FIELDS[i]; bool found = false, is_z = false; const char* zv = nullptr;
-    for (int k = 0; k < nt; k++) if (tab[k].t0 == tag[0] && tab[k].t1 == tag[1]) { found = true; is_z = tab[k].ty == 'Z'; zv = tab[k].v; break; }
-    if (found && is_z) { s += zv; continue; }
+    if (i) *p++ = '\t';
+    if (i == 37 && r.skip_align >= 0) { if (r.skip_align) { memcpy(p, "TRUE", 4); p += 4; } else { memcpy(p, "FALSE", 5); p += 5; } continue; }
+    const u32 c = FCLS.of_field[i];
+    if ((isz >> c) & 1) { memcpy(p, zv[c], zl[c]); p += zl[c]; continue; }
     switch (i) {
-      case 0: s.append(r.qname_ptr(), r.qname_len()); break; case 2: s += rev ? "true" : "false"; break; case 3: s += mrev ? "true" : "false"; break;
-      case 4: s += paired ? "true" : "false"; break; case 5: s += (fl & 2) ? "true" : "false"; break;
+      case 0: memcpy(p, r.qname_ptr(), r.qname_len()); p += r.qname_len(); break;
+      case 2: p = put_bool(p, rev); break; case 3: p = put_bool(p, mrev); break; case 4: p = put_bool(p, paired); break; case 5: p = put_bool(p, fl & 2); break;
       case 6: {
-        if (paired && !unm && !munm && r.refid() == r.mrefid() && r.pos() != r.mpos()) {
+        if (paired && !unm && !munm && r.refid() == r.mrefid() && r.pos() != r.mpos()) {   // rust-htslib read_pair_orientation
           i64 p1, p2; bool f1, f2;
           if (first) { p1 = r.pos(); p2 = r.mpos(); f1 = !rev; f2 = !mrev; } else { p1 = r.mpos(); p2 = r.pos(); f1 = !mrev; f2 = !rev; }
-          if (p1 < p2) { s += f1 ? "F1" : "R1"; s += f2 ? "F2" : "R2"; } else { s += f2 ? "F2" : "R2"; s += f1 ? "F1" : "R1"; }
-        } else s += "None";
-        break; }
-      case 7: s += unm ? "true" : "false"; break; case 8: s += munm ? "true" : "false"; break; case 9: s += first ? "true" : "false"; break;
-      case 10: s += (fl & 128) ? "true" : "false"; break; case 11: s += rev ? "-" : "+"; break;
-      case 12: snprintf(num, sizeof num, "%u", r.mapq()); s += num; break; case 13: snprintf(num, sizeof num, "%d", r.pos()); s += num; break;
-      case 14: snprintf(num, sizeof num, "%d", r.mpos()); s += num; break; case 16: snprintf(num, sizeof num, "%u", r.l_seq()); s += num; break;
-      case 17: snprintf(num, sizeof num, "%d", r.tlen()); s += num; break;
-      case 18: s += (fl & 512) ? "true" : "false"; break; case 19: s += (fl & 256) ? "true" : "false"; break; case 20: s += (fl & 1024) ? "true" : "false"; break;
-      case 21: s += (fl & 2048) ? "true" : "false"; break;
+          const char* x = f1 ? "F1" : "R1"; const char* y = f2 ? "F2" : "R2";
+          if (p1 < p2) { memcpy(p, x, 2); memcpy(p + 2, y, 2); } else { memcpy(p, y, 2); memcpy(p + 2, x, 2); }
+        } else memcpy(p, "None", 4);
+        p += 4; break; }
+      case 7: p = put_bool(p, unm); break; case 8: p = put_bool(p, munm); break; case 9: p = put_bool(p, first); break; case 10: p = put_bool(p, fl & 128); break;
+      case 11: *p++ = rev ? '-' : '+'; break;
+      case 12: p = put_u32(p, r.mapq()); break; case 13: p = put_i32(p, r.pos()); break; case 14: p = put_i32(p, r.mpos()); break;
+      case 16: p = put_u32(p, r.l_seq()); break; case 17: p = put_i32(p, r.tlen()); break;
+      case 18: p = put_bool(p, fl & 512); break; case 19: p = put_bool(p, fl & 256); break; case 20: p = put_bool(p, fl & 1024); break; case 21: p = put_bool(p, fl & 2048); break;
       default: break;   // non-string aux (NH, HI, AS, nM, RE ...) -> String::new()
     }
   }
+  s.resize((size_t)(p - s.data()));
 }
-// field 0 of a record as the row logic sees it (QNAME, or a "QN" string aux when one exists — aux lookup by two bytes)
-std::string field0(const Rec& r) { std::string z; if (r.aux_z("QNAME", z)) return z; return r.qname(); }
+// field 0 of a record as the row logic sees it (QNAME, or a "QN" string aux when one exists — aux lookup by two bytes), as a view
+inline void field0(const Rec& r, const char*& ptr, u32& len) {
+  const u8* a = r.aux(); const u8* e = r.end();
+  while (a + 3 <= e) {
+    const char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2]; a += 3; const u8* v = a; u32 zlen = 0; bool zok = false;
+    const bool ok = Rec::aux_skip(ty, a, e, zlen, zok);
+    if (t0 == 'Q' && t1 == 'N') { if (ty == 'Z' && zok) { ptr = (const char*)v; len = zlen; return; } break; }
+    if (!ok) break;
+  }
+  ptr = r.qname_ptr(); len = r.qname_len();
+}
 
 std::string data_header(const char* prefix) { std::string s; for (int i = 0; i < 38; i++) { if (i == 1 || i == 15) continue; if (!s.empty()) s += "\t"; s += prefix; s += "_"; s += FIELDS[i]; } return s; }
 
@@ -685,7 +710,7 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
   else if (const char* e2 = getenv("NB_BAM_WINDOW_MB")) window_bytes = (size_t)strtoull(e2, nullptr, 10) << 20;
   if (rc != NB_OK) { cleanup(); return rc; }
   const size_t BATCH_PAIRS = 1u << 20;
-  int GZ_LEVEL = 4;   // NB_BAM_GZ_LEVEL=1..9 overrides (the rows are the same, the members smaller or faster to make)
+  int GZ_LEVEL = 2;   // NB_BAM_GZ_LEVEL=1..9 overrides (the rows are the same, the members smaller or faster to make)
   if (const char* e = getenv("NB_BAM_GZ_LEVEL")) { int v = atoi(e); if (v >= 1 && v <= 9) GZ_LEVEL = v; }
   // Three stages run concurrently on consecutive batches: (F) the host threads fill batch k+1 into pinned buffers,
   // (D) the device aligns batch k and its counts are finalized, (R) the host threads format + gzip the rows of batch k-1.
@@ -787,7 +812,8 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
     parallel_ranges(parts, (size_t)parts, [&](size_t ta, size_t tb2, int) {
       for (size_t t = ta; t < tb2; t++) {
         std::string text; text.reserve(1 << 20); char num[32];
-        std::unordered_set<std::string> scored;
+        std::vector<std::pair<const char*, u32>> scored;   // field 0 of the records that got a count row in this scope (a handful at most)
+        auto is_scored = [&](const Rec& x) { const char* q; u32 l; field0(x, q, l); for (const auto& sc : scored) if (same(sc.first, sc.second, q, l)) return true; return false; };
         for (size_t g = cut[t]; g < cut[t + 1]; g++) {
           if (row_begin[g + 1] == row_begin[g]) continue;   // scopes without a callset emit nothing at all (src/process/bam.rs:329-331)
           const Rec* v = &stream[gstart[g0 + g]]; const size_t gp = pair0[g + 1] - pair0[g], pbase = pair0[g];
@@ -808,10 +834,10 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
             size_t rep = gp;
             for (size_t pj = gp; pj-- > 0;) { u32 slot = O.pres[pbase + pj].callset; if (slot != NONE32 && O.slot_to_callset[slot] == cs) { rep = pj; break; } }
             if (rep == gp) continue;
-            scored.insert(field0(v[2 * rep]));
+            { const char* q; u32 l; field0(v[2 * rep], q, l); scored.push_back({q, l}); }
             emit(feats, (long long)O.row_count[r], rep);
           }
-          for (size_t pj = 0; pj < gp; pj++) { if (scored.count(field0(v[2 * pj + 1]))) continue; emit("", 0, pj); }   // zero rows (332-353)
+          for (size_t pj = 0; pj < gp; pj++) { if (!scored.empty() && is_scored(v[2 * pj + 1])) continue; emit("", 0, pj); }   // zero rows (332-353)
         }
         if (!text.empty()) { wrote[t] = 1; if (!gzip_member(text, GZ_LEVEL, member[t])) bad[t] = 1; }
       } });
@@ -918,13 +944,23 @@ extern "C" int nb_bam_dump_groups(const char* input_file, int force_bam_paired, 
     }
     gi0 += gstart.size() - 1;
   };
+  // NB_BAM_DUMP_ROWFMT: instead, one line per record made by the rows stage's own formatter (append_data_values: the 36
+  // reported fields, tab-joined) — tests hold it against the fields above, and it times the formatter without a device
+  const bool rowfmt = getenv("NB_BAM_DUMP_ROWFMT") != nullptr;
+  auto dump_rowfmt = [&](const std::vector<Rec>& stream, bool write) { std::string line; for (const Rec& r : stream) { line.clear(); append_data_values(r, line); line += '\n'; if (write) fwrite(line.data(), 1, line.size(), f); } };
   int rc = NB_OK;
   {
     GroupStreamer gs; Window win[2]; bool done = false; int cur = 0;
     rc = getenv("NB_BAM_SERIAL_GROUPING") ? NEED_WHOLE : gs.open(input_file, force_bam_paired != 0, std::max(1, num_cores), window_bytes);
     if (rc == NB_OK) rc = gs.next(win[0], nullptr, done);
     const bool none = out_path[0] && !strcmp(out_path, "/dev/null") && getenv("NB_BAM_DUMP_NONE");   // producer only (timing the reader)
-    while (rc == NB_OK && !done) { if (!none) dump(win[cur].stream, win[cur].gstart); rc = gs.next(win[cur ^ 1], &win[cur], done); cur ^= 1; }
+    double t_fmt = 0; size_t n_fmt = 0;
+    while (rc == NB_OK && !done) {
+      if (rowfmt) { double tf = GroupStreamer::clk(); dump_rowfmt(win[cur].stream, !none); n_fmt += win[cur].stream.size(); t_fmt += GroupStreamer::clk() - tf; }
+      else if (!none) dump(win[cur].stream, win[cur].gstart);
+      rc = gs.next(win[cur ^ 1], &win[cur], done); cur ^= 1;
+    }
+    if (rowfmt && getenv("NB_BAM_STATS")) fprintf(stderr, "row formatter: %zu records in %.2f s = %.0f ns per record (one thread)\n", n_fmt, t_fmt, n_fmt ? t_fmt / n_fmt * 1e9 : 0.0);
     if (getenv("NB_BAM_STATS")) fprintf(stderr, "bam producer: inflate %.2fs, record scan %.2fs, key scan %.2fs, runs %.2fs, emit %.2fs, groups %.2fs\n", gs.t_inflate, gs.t_scan, gs.t_keys, gs.t_runs, gs.t_emit, gs.t_groups);
   }
   if (rc == NEED_WHOLE) {
@@ -933,7 +969,7 @@ extern "C" int nb_bam_dump_groups(const char* input_file, int force_bam_paired, 
     Bgzf z; rc = z.load(input_file, std::max(1, num_cores));
     std::vector<Rec> stream; std::vector<u64> gstart;
     if (rc == NB_OK) rc = collect_groups_serial(z, force_bam_paired != 0, std::max(1, num_cores), stream, gstart);
-    if (rc == NB_OK) dump(stream, gstart);
+    if (rc == NB_OK) { if (rowfmt) dump_rowfmt(stream, true); else dump(stream, gstart); }
   }
   if (rc) { fclose(f); return rc; }
   fclose(f);

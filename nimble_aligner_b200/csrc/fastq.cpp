@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "host.hpp"
+#include "inflate.hpp"
 
 using namespace nb;
 
@@ -56,7 +57,7 @@ struct Pinned {
 // to the device asynchronously)
 struct Segment {
   Pinned seq, offb; u64 n = 0; u32 maxlen = 0; size_t used = 0;
-  int status = 1;               // 1 more may follow, 0 end of file, -1 malformed, -2 out of pinned memory
+  int status = 1;               // 1 more may follow, 0 end of file, -1 malformed, -2 out of pinned memory, -3 damaged gzip stream
   size_t start = 0, end = 0;    // MapStream: byte positions of the first record and behind the last one
   u64* off() const { return (u64*)offb.p; }
   void clear() { n = 0; maxlen = 0; used = 0; status = 1; }
@@ -71,23 +72,74 @@ struct SegStream {
   virtual void finish() = 0;              // stops the threads (also mid-stream, after an error elsewhere)
 };
 
-// ------------------------------------------------------------------------------------------------ gzip: serial inflate + parse
-// One FASTQ.gz stream parsed in place: lines are views into the read buffer (a partial line at the end of the buffer
-// is moved to the front before the next gzread), no per-line strings.
-struct FastqReader {
-  gzFile f = nullptr; std::string path; std::vector<char> buf; size_t pos = 0, len = 0; bool eof = false;
-  bool open(const std::string& p) { path = p; f = gzopen(p.c_str(), "rb"); if (!f) return false; gzbuffer(f, 1 << 20); buf.resize(1 << 23); return true; }
-  ~FastqReader() { if (f) gzclose(f); }
-  // one line without its terminator as a view into buf; false at end of input; a line longer than the buffer grows it
-  bool line(const char*& out, size_t& n) {
+// ------------------------------------------------------------------------------------------------ gzip: inflate thread -> parse thread
+// A gzip stream cannot be entered in the middle, so one .gz file is inflated by ONE thread — with the decoder of inflate.hpp
+// over the mapped file (zlib's gzread ran at 0.4 GB/s per stream and was the whole cost of the .gz path) — into text chunks
+// that a second thread parses while the next chunk is inflated.  A chunk buffer starts with the 32 KiB of text before it
+// (the deflate window), then up to GZ_CHUNK bytes of new text.
+struct GzText {
+  static const size_t HIST = 32768; size_t GZ_CHUNK = (size_t)4 << 20;   // NB_GZ_CHUNK_KB overrides (tests: lines that straddle many chunk borders)
+  struct Chunk { std::vector<u8> buf; size_t len = 0; int status = 1; const char* data() const { return (const char*)buf.data() + HIST; } };   // status: 1 more follows, 0 last, -3 damaged gzip stream
+  int fd = -1; const u8* map = nullptr; size_t size = 0; nbz::GzipStream gz;
+  std::vector<std::unique_ptr<Chunk>> chunks; std::vector<Chunk*> free_q; std::deque<Chunk*> filled_q; std::mutex m; std::condition_variable cv; bool stop = false; std::thread th;
+  bool open(const std::string& p) {
+    fd = ::open(p.c_str(), O_RDONLY); if (fd < 0) return false;
+    struct stat st; if (fstat(fd, &st) != 0) return false;
+    size = (size_t)st.st_size;
+    if (size) { void* q = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0); if (q == MAP_FAILED) return false; map = (const u8*)q; madvise(q, size, MADV_SEQUENTIAL); }
+    gz.open(map, size);
+    if (const char* e = getenv("NB_GZ_CHUNK_KB")) { const size_t kb = (size_t)strtoull(e, nullptr, 10); if (kb >= 1) GZ_CHUNK = kb << 10; }
+    for (int i = 0; i < 4; i++) { chunks.emplace_back(new Chunk()); chunks.back()->buf.resize(HIST + GZ_CHUNK); free_q.push_back(chunks.back().get()); }
+    th = std::thread([this] { run(); });
+    return true;
+  }
+  void run() {
+    Chunk* prev = nullptr;
     for (;;) {
-      const char* s = buf.data() + pos; const char* nl = len > pos ? (const char*)memchr(s, '\n', len - pos) : nullptr;
-      if (nl) { out = s; n = (size_t)(nl - s); pos += n + 1; if (n && out[n - 1] == '\r') n--; return true; }
-      if (eof) { if (pos >= len) return false; out = s; n = len - pos; pos = len; if (n && out[n - 1] == '\r') n--; return true; }
-      if (pos) { memmove(buf.data(), buf.data() + pos, len - pos); len -= pos; pos = 0; }
-      if (len == buf.size()) buf.resize(buf.size() * 2);
-      int got = gzread(f, buf.data() + len, (unsigned)std::min<size_t>(buf.size() - len, 1u << 30));
-      if (got <= 0) eof = true; else len += (size_t)got;
+      Chunk* c;
+      { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return stop || !free_q.empty(); }); if (stop) return; c = free_q.back(); free_q.pop_back(); }
+      u8* b = c->buf.data();
+      if (prev) memcpy(b, prev->buf.data() + prev->len, HIST);      // the last HIST bytes of [history | text] of the chunk before (still intact: only this thread writes chunks)
+      const ptrdiff_t n = gz.read(prev ? b : b + HIST, b + HIST, b + HIST + GZ_CHUNK);
+      c->len = n < 0 ? 0 : (size_t)n; c->status = n < 0 ? -3 : gz.done() ? 0 : 1;
+      const int st = c->status; prev = c;
+      { std::lock_guard<std::mutex> lk(m); filled_q.push_back(c); }
+      cv.notify_all();
+      if (st != 1) return;
+    }
+  }
+  Chunk* next() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return !filled_q.empty(); }); Chunk* c = filled_q.front(); filled_q.pop_front(); return c; }
+  void recycle(Chunk* c) { { std::lock_guard<std::mutex> lk(m); free_q.insert(free_q.begin(), c); } cv.notify_all(); }   // (reused last: the inflate thread copies its history from the newest chunk)
+  void finish() { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); }
+  ~GzText() { finish(); if (map) munmap((void*)map, size); if (fd >= 0) ::close(fd); }
+};
+// One FASTQ.gz stream parsed in place: lines are views into the text chunks (a line that straddles two chunks is put
+// together in `carry`), no per-line strings.
+struct FastqReader {
+  GzText src; GzText::Chunk* cur = nullptr; size_t pos = 0; bool eof = false, damaged = false, carry_out = false; std::string carry;
+  bool open(const std::string& p) { return src.open(p); }
+  // one line without its terminator; false at end of input (or at a damaged gzip stream: `damaged`)
+  bool line(const char*& out, size_t& n) {
+    if (carry_out) { carry.clear(); carry_out = false; }
+    for (;;) {
+      if (cur) {
+        const char* s = cur->data() + pos; const size_t left = cur->len - pos;
+        const char* nl = left ? (const char*)memchr(s, '\n', left) : nullptr;
+        if (nl) {
+          const size_t k = (size_t)(nl - s); pos += k + 1;
+          if (carry.empty()) { out = s; n = k; } else { carry.append(s, k); out = carry.data(); n = carry.size(); carry_out = true; }
+          if (n && out[n - 1] == '\r') n--;
+          return true;
+        }
+        carry.append(s, left);
+        const int st = cur->status; src.recycle(cur); cur = nullptr;
+        if (st != 1) { eof = true; damaged = st < 0; }
+      }
+      if (eof) {
+        if (damaged || carry.empty()) return false;
+        out = carry.data(); n = carry.size(); carry_out = true; if (n && out[n - 1] == '\r') n--; return true;   // last line without a newline
+      }
+      cur = src.next(); pos = 0;
     }
   }
 };
@@ -97,17 +149,17 @@ void parse_block(FastqReader& r, Segment& g, u64 want) {
   if (!g.begin()) { g.status = -2; return; }
   const char* s; size_t n;
   while (g.n < want) {
-    do { if (!r.line(s, n)) { g.status = 0; return; } } while (n == 0);
+    do { if (!r.line(s, n)) { g.status = r.damaged ? -3 : 0; return; } } while (n == 0);
     if (s[0] != '@') { g.status = -1; return; }
     size_t start = g.used;
     for (;;) {
-      if (!r.line(s, n)) { g.status = -1; return; }
+      if (!r.line(s, n)) { g.status = r.damaged ? -3 : -1; return; }
       if (n && s[0] == '+') break;
       if (!g.seq.ensure(g.used + n + 64, g.used)) { g.status = -2; return; }
       memcpy(g.seq.p + g.used, s, n); g.used += n;
     }
     size_t slen = g.used - start, qlen = 0;
-    while (qlen < slen) { if (!r.line(s, n)) { g.status = -1; return; } qlen += n; }
+    while (qlen < slen) { if (!r.line(s, n)) { g.status = r.damaged ? -3 : -1; return; } qlen += n; }
     if (qlen != slen) { g.status = -1; return; }
     if (!g.push_off()) { g.status = -2; return; }
     g.maxlen = std::max<u32>(g.maxlen, (u32)slen); g.n++;
@@ -305,11 +357,11 @@ int consume(SegStream* s1, SegStream* s2, Emit emit, Retire retire) {
   int rc = NB_OK;
   for (;;) {
     while (!end1 && (!c1 || k1 == c1->n)) {
-      if (c1) { int st = c1->status; retire(s1, c1); c1 = nullptr; if (st == 0) { end1 = true; break; } if (st == -2) return fail(NB_ERR_CUDA, "pinned allocation failed"); if (st == -1) return fail(NB_ERR_PARSE, "Error -- could not parse read. Input R1 data malformed."); }
+      if (c1) { int st = c1->status; retire(s1, c1); c1 = nullptr; if (st == 0) { end1 = true; break; } if (st == -2) return fail(NB_ERR_CUDA, "pinned allocation failed"); if (st == -3) return fail(NB_ERR_PARSE, "Error -- could not read R1: damaged or truncated gzip stream."); if (st == -1) return fail(NB_ERR_PARSE, "Error -- could not parse read. Input R1 data malformed."); }
       c1 = s1->next(); k1 = 0;
     }
     while (s2 && !end2 && (!c2 || k2 == c2->n)) {
-      if (c2) { int st = c2->status; retire(s2, c2); c2 = nullptr; if (st == 0) { end2 = true; break; } if (st == -2) return fail(NB_ERR_CUDA, "pinned allocation failed"); if (st == -1) return fail(NB_ERR_PARSE, "Error -- could not parse reverse read. Input R2 data malformed."); }
+      if (c2) { int st = c2->status; retire(s2, c2); c2 = nullptr; if (st == 0) { end2 = true; break; } if (st == -2) return fail(NB_ERR_CUDA, "pinned allocation failed"); if (st == -3) return fail(NB_ERR_PARSE, "Error -- could not read R2: damaged or truncated gzip stream."); if (st == -1) return fail(NB_ERR_PARSE, "Error -- could not parse reverse read. Input R2 data malformed."); }
       c2 = s2->next(); k2 = 0;
     }
     if (s2 && end1 != end2) return fail(NB_ERR_PARSE, "Error -- read and reverse read files do not have matching lengths: ");
@@ -326,6 +378,44 @@ int consume(SegStream* s1, SegStream* s2, Emit emit, Retire retire) {
 extern "C" int nb_write_fastq_tsv(const char* path, const nb_library* lib, const nb_counts* counts) {
   if (!path || !lib || !counts) return fail(NB_ERR_INVALID, "null argument");
   return write_tsv(path, lib, *counts);
+}
+
+// host-only: the file drivers' inflate (inflate.hpp) on a buffer, for parity tests against zlib.  raw != 0: one raw deflate
+// stream decoded in one piece (how bam.cpp inflates a BGZF block; the output must fit out_cap exactly or loosely);
+// raw == 0: concatenated gzip members decoded through windows of `window` bytes behind a 32 KiB history (how fastq.cpp
+// reads a .gz file; window 0 = one window).  NB_ERR_PARSE on a damaged stream, NB_ERR_OVERFLOW when out_cap is too small.
+extern "C" int nb_inflate(const void* in, uint64_t in_len, int raw, uint64_t window, void* out, uint64_t out_cap, uint64_t* out_len) {
+  if ((!in && in_len) || (!out && out_cap) || !out_len) return fail(NB_ERR_INVALID, "null argument");
+  const u8* src = (const u8*)in; u8* dst = (u8*)out; *out_len = 0;
+  if (raw) {
+    std::unique_ptr<nbz::Inflater> inf(new nbz::Inflater()); inf->start(src, src + in_len);
+    u8* q = dst; const int r = inf->run(dst, q, dst + out_cap);
+    *out_len = (uint64_t)(q - dst);
+    if (r == nbz::INF_MORE) return fail(NB_ERR_OVERFLOW, "output buffer too small");
+    if (r != nbz::INF_END) return fail(NB_ERR_PARSE, "damaged deflate stream");
+    return NB_OK;
+  }
+  std::unique_ptr<nbz::GzipStream> gz(new nbz::GzipStream()); gz->open(src, in_len);
+  if (!window) {
+    while (!gz->done()) {
+      const ptrdiff_t n = gz->read(dst, dst + *out_len, dst + out_cap);
+      if (n < 0) return fail(NB_ERR_PARSE, "damaged gzip stream");
+      *out_len += (uint64_t)n;
+      if (!gz->done() && n == 0) return fail(NB_ERR_OVERFLOW, "output buffer too small");
+    }
+    return NB_OK;
+  }
+  if (window < 300) return fail(NB_ERR_INVALID, "window must hold the longest match");
+  const size_t HIST = 32768; std::vector<u8> a(HIST + window), b(HIST + window); u8* cur = a.data(); u8* prev = nullptr; size_t prev_len = 0;
+  while (!gz->done()) {
+    if (prev) memcpy(cur, prev + prev_len, HIST);
+    const ptrdiff_t n = gz->read(prev ? cur : cur + HIST, cur + HIST, cur + HIST + window);
+    if (n < 0) return fail(NB_ERR_PARSE, "damaged gzip stream");
+    if (*out_len + (uint64_t)n > out_cap) return fail(NB_ERR_OVERFLOW, "output buffer too small");
+    memcpy(dst + *out_len, cur + HIST, (size_t)n); *out_len += (uint64_t)n;
+    prev = cur; prev_len = (size_t)n; cur = cur == a.data() ? b.data() : a.data();
+  }
+  return NB_OK;
 }
 
 // host-only: the records the feeder hands to the device, one line per record ("SEQ" or "SEQ1\tSEQ2") — parity tests of the

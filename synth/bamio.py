@@ -23,7 +23,7 @@ def _pack_seq(seq):
 
 
 def encode_record(qname, flag, seq, qual, tags=(), refid=-1, pos=-1, mapq=255, next_refid=-1, next_pos=-1, tlen=0):
-    """tags: sequence of (two-letter tag, type in 'ZAi', value)."""
+    """tags: sequence of (two-letter tag, BAM aux type, value)."""
     name = qname.encode() + b"\0"
     aux = b""
     for tag, ty, val in tags:
@@ -33,6 +33,13 @@ def encode_record(qname, flag, seq, qual, tags=(), refid=-1, pos=-1, mapq=255, n
             aux += tag.encode() + b"A" + str(val).encode()[:1]
         elif ty == "i":
             aux += tag.encode() + b"i" + struct.pack("<i", int(val))
+        elif ty in "cCsSIf":
+            aux += tag.encode() + ty.encode() + struct.pack("<" + {"c": "b", "C": "B", "s": "h", "S": "H", "I": "I", "f": "f"}[ty], val)
+        elif ty == "H":
+            aux += tag.encode() + b"H" + str(val).encode() + b"\0"
+        elif ty == "B":      # val = (subtype in 'cCsSiIf', sequence of numbers)
+            st, xs = val
+            aux += tag.encode() + b"B" + st.encode() + struct.pack("<I", len(xs)) + b"".join(struct.pack("<" + {"c": "b", "C": "B", "s": "h", "S": "H", "i": "i", "I": "I", "f": "f"}[st], x) for x in xs)
         else:
             raise ValueError(ty)
     body = struct.pack("<iiBBHHHIiii", refid, pos, len(name), mapq, 4680, 0, flag, len(seq), next_refid, next_pos, tlen)

@@ -76,7 +76,7 @@ def test_feeder_fails_loudly_on_damaged_bam(tmp_path):
             out += b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(cd) + 25) + cd + struct.pack("<II", zlib.crc32(c) & 0xFFFFFFFF, len(c))
         return out + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
     rng = random.Random(7)
-    ok = err = 0
+    ok = err = fmt_checked = 0
     for it in range(60):
         kind = it % 5
         if kind == 0:
@@ -101,7 +101,20 @@ def test_feeder_fails_loudly_on_damaged_bam(tmp_path):
             ok += 1
         except nb.NbError:
             err += 1
-    assert ok + err == 60 and err >= 5
+            continue
+        # the rows stage's formatter walks the same damaged records: same values as the field parser, nothing read past a record
+        os.environ["NB_BAM_DUMP_ROWFMT"] = "1"
+        try:
+            nb.bam_dump_groups(path, str(tmp_path / "r.tsv"), force_bam_paired=bool(it & 1), num_cores=2)
+        finally:
+            del os.environ["NB_BAM_DUMP_ROWFMT"]
+        fl = open(tmp_path / "g.tsv", "rb").read().split(b"\n")[:-1]; rl = open(tmp_path / "r.tsv", "rb").read().split(b"\n")[:-1]
+        if len(fl) == len(rl) and all(l.count(b"\t") == 40 for l in fl):      # (no tab / newline inside a damaged value)
+            for a, b2 in zip(fl, rl):
+                f = a.split(b"\t")[3:]
+                assert b2 == b"\t".join(f[i] for i in range(38) if i not in (1, 15))
+            fmt_checked += len(fl)
+    assert ok + err == 60 and err >= 5 and fmt_checked > 1000
 
 
 @pytest.mark.parametrize("force_paired", [False, True])
@@ -190,3 +203,43 @@ def test_parallel_record_walk_and_run_detection(tmp_path, monkeypatch, force_pai
     nb.bam_dump_groups(bam, par, force_bam_paired=force_paired, num_cores=5)
     a, b = open(ser, "rb").read(), open(par, "rb").read()
     assert a == b and a.count(b"\n") > (300 if force_paired else 3000)
+
+
+def test_row_formatter_equals_the_field_parser(tmp_path, monkeypatch):
+    """The rows stage writes a record's 36 reported values with its own formatter (one pass over the aux block, fields
+    grouped by the two bytes htslib's aux lookup reads); the dump's field parser and oracle/bam_ref.py define the values.
+    Records here carry every aux type, tags that several fields share ("MA": MATE_REVERSE / MATE_UNMAPPED / MAPQ /
+    MATE_POS; "RE": REVERSE / RE; "QN": QNAME), repeated tags (the first one counts), negative positions and odd flags."""
+    import random
+    from synth import bamio
+    rng = random.Random(11)
+    nt = lambda n: "".join(rng.choice("ACGT") for _ in range(n))
+    extras = [("MA", "Z", "shared-by-four"), ("RE", "Z", "both"), ("RE", "A", "E"), ("QN", "Z", "renamed"), ("QN", "i", 5), ("SE", "Z", "seq-len-too"), ("PA", "Z", "p"),
+              ("NH", "Z", "as-string"), ("NH", "i", 3), ("HI", "C", 200), ("AS", "s", -300), ("nM", "S", 65535), ("fx", "Z", "feat;ure"), ("TX", "Z", "tx,+,1M"), ("AN", "H", "1AE3"),
+              ("xx", "B", ("s", [1, -2, 3])), ("GN", "B", ("C", [1, 2])), ("GN", "Z", "behind-an-array"), ("yy", "f", 1.5), ("zz", "I", 4000000000), ("cc", "c", -5), ("UY", "Z", ""), ("SK", "Z", "user-SK")]
+    recs = []
+    for g in range(400):
+        umi, cb = nt(12), nt(16) + "-1"
+        for k in range(rng.randint(1, 4)):
+            tags = [("CB", "Z", cb), ("UB", "Z", umi)] + rng.sample(extras, rng.randint(0, 6))
+            rng.shuffle(tags)
+            flags = rng.choice([[0], [16], [4], [256], [512 | 16], [1024], [2048 | 128], [0xFFE], [1 | 64 | 32, 1 | 128 | 16], [1 | 2 | 128, 1 | 2 | 64], [1 | 8 | 64, 1 | 4 | 128], [0xFFF, 0xFFF]])
+            for flag in flags:      # records flagged as paired come as two neighbours with one QNAME (anything else is filtered out)
+                L = rng.choice([91, 124, 30, 1])
+                recs.append(bamio.encode_record("q%d_%d" % (g, k), flag, nt(L), bytes(rng.randrange(2, 41) for _ in range(L)), tags, refid=rng.choice([-1, 0]), pos=rng.choice([-1, 0, 7, 2 ** 31 - 1]),
+                                                mapq=rng.randrange(256), next_refid=rng.choice([-1, 0]), next_pos=rng.choice([-1, 7, 99, 123456789]), tlen=rng.choice([0, -250, 2 ** 31 - 1, -2 ** 31])))
+    bam = bamio.write_bam(str(tmp_path / "f.bam"), recs, block_bytes=20000)
+    keep = [i for i in range(38) if i not in (1, 15)]
+    for force_paired in (False, True):
+        a, b = str(tmp_path / "fields.tsv"), str(tmp_path / "rows.tsv")
+        monkeypatch.delenv("NB_BAM_DUMP_ROWFMT", raising=False)
+        nb.bam_dump_groups(bam, a, force_bam_paired=force_paired, num_cores=3)
+        monkeypatch.setenv("NB_BAM_DUMP_ROWFMT", "1")
+        nb.bam_dump_groups(bam, b, force_bam_paired=force_paired, num_cores=3)
+        fields = [l.rstrip("\n").split("\t")[3:] for l in open(a, encoding="latin1")]
+        rows = [l.rstrip("\n").split("\t") for l in open(b, encoding="latin1")]
+        ref = [it["f"] for g in bam_ref.groups_of(bam_ref.read_bam(bam), force_paired) for it in g]
+        assert len(rows) == len(fields) == len(ref) > 300
+        for r, f, o in zip(rows, fields, ref):
+            assert r == [f[i] for i in keep] == [o[i] for i in keep]
+        assert any(r[0] == "renamed" for r in rows) and any(r[2] == r[7] == r[11] == r[13] == "shared-by-four" for r in rows) and any(r[1] == "both" for r in rows)

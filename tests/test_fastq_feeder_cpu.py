@@ -111,3 +111,40 @@ def test_feeder_errors(tmp_path):
     assert out.read_text() == ""
     nb.fastq_dump([tmp_path / "empty.fastq", tmp_path / "empty.fastq"], out, num_cores=2)
     assert out.read_text() == ""
+
+
+@pytest.mark.parametrize("chunk_kb", [1, 7, 4096])
+@pytest.mark.parametrize("kw", [dict(), dict(crlf=True, multiline=True, blanks=True), dict(final_newline=False)])
+def test_gzip_stream_through_the_inflate_thread(tmp_path, monkeypatch, chunk_kb, kw):
+    """.gz input: one thread inflates the mapped file (csrc/inflate.hpp) into text chunks, a second one parses them; lines
+    straddle chunk borders (1 KiB chunks: every few lines), the file may consist of several gzip members (bgzip, cat), and
+    the records must be those of the sequential parse of the plain text."""
+    monkeypatch.setenv("NB_GZ_CHUNK_KB", str(chunk_kb))
+    rng = random.Random(chunk_kb * 31 + len(kw))
+    t1, t2 = make_fastq(rng, 3000, **kw), make_fastq(rng, 3000, **kw)
+    with gzip.open(tmp_path / "r1.fastq.gz", "wb", compresslevel=1) as f:
+        f.write(t1.encode())
+    b2 = t2.encode(); cuts = sorted(rng.randrange(len(b2)) for _ in range(5))
+    (tmp_path / "r2.fastq.gz").write_bytes(b"".join(gzip.compress(b2[a:b], 9) for a, b in zip([0] + cuts, cuts + [len(b2)])))      # members cut anywhere, also inside lines
+    out = tmp_path / "p.txt"
+    nb.fastq_dump([tmp_path / "r1.fastq.gz", tmp_path / "r2.fastq.gz"], out, num_cores=4)
+    assert out.read_text().split("\n")[:-1] == ["%s\t%s" % (a, b) for a, b in zip(seq_parse(t1), seq_parse(t2))]
+
+
+def test_damaged_gzip_input_is_an_error_not_an_early_end(tmp_path):
+    """A truncated or corrupted .fastq.gz must fail the job (gzread's short count looked like the end of the file)."""
+    rng = random.Random(5)
+    text = make_fastq(rng, 4000, nasty_quals=False).encode()
+    good = gzip.compress(text, 6)
+    out = tmp_path / "o.txt"
+    cases = {"cut.fastq.gz": good[:len(good) // 2], "trailer.fastq.gz": good[:-3], "flip.fastq.gz": good[:5000] + bytes([good[5000] ^ 0x55]) + good[5001:],
+             "crc.fastq.gz": good[:-8] + bytes([good[-8] ^ 1]) + good[-7:]}
+    for name, b in cases.items():
+        (tmp_path / name).write_bytes(b)
+        with pytest.raises(nb.NbError) as e:
+            nb.fastq_dump([tmp_path / name], out, num_cores=2)
+        assert e.value.code == -3, name
+    assert any("gzip" in str(x) for x in [e.value])
+    (tmp_path / "ok.fastq.gz").write_bytes(good + b"\0" * 100)        # padding behind the last member is ignored (gzip -d does the same)
+    nb.fastq_dump([tmp_path / "ok.fastq.gz"], out, num_cores=2)
+    assert out.read_text().split("\n")[:-1] == seq_parse(text.decode())
