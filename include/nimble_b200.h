@@ -320,6 +320,9 @@ int nb_fastq_dump(const char* const* input_files, uint32_t n_inputs, int num_cor
  * piece (a BGZF block); raw == 0: concatenated gzip members through windows of `window` bytes (0 = one window), CRC-32 and
  * ISIZE checked.  NB_ERR_PARSE on a damaged stream, NB_ERR_OVERFLOW when out_cap is too small. */
 int nb_inflate(const void* in, uint64_t in_len, int raw, uint64_t window, void* out, uint64_t out_cap, uint64_t* out_len);
+/* host-only: a gzip file in memory through the FASTQ feeder's parallel reader (`threads` workers enter the deflate stream
+ * at guessed block headers of `chunk_bytes` byte ranges; nothing is emitted that the sequential decode does not confirm) */
+int nb_gunzip_parallel(const void* in, uint64_t in_len, int threads, uint64_t chunk_bytes, void* out, uint64_t out_cap, uint64_t* out_len);
 
 /* process::bam::process (src/process/bam.rs:45-243) behind the same library loop: BGZF/BAM decode on host threads,
  * UMIReader / SortedBamReader grouping (src/parse/bam.rs, src/parse/sorted_bam_reader.rs) with their quirks, one scoped

@@ -136,6 +136,7 @@ _SIGS = {
     "nb_write_fastq_tsv": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(Counts)]),
     "nb_bam_dump_groups": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "nb_fastq_dump": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_char_p]),
+    "nb_gunzip_parallel": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "nb_inflate": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "nb_process_fastq_devices": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32]),
     "nb_process_bam": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]),
@@ -634,6 +635,15 @@ def inflate(data, raw=False, window=0, out_cap=None):
     out = C.create_string_buffer(max(cap, 1))
     n = C.c_uint64(0)
     _ck(lib().nb_inflate(bytes(data), len(data), int(raw), int(window), out, cap, C.byref(n)))
+    return out.raw[:n.value]
+
+
+def gunzip_parallel(data, threads=4, chunk_bytes=1 << 20, out_cap=None):
+    """A gzip file in memory through the FASTQ feeder's parallel reader (tests against zlib)."""
+    cap = int(out_cap) if out_cap is not None else max(1 << 16, 1100 * len(data))
+    out = C.create_string_buffer(max(cap, 1))
+    n = C.c_uint64(0)
+    _ck(lib().nb_gunzip_parallel(bytes(data), len(data), int(threads), int(chunk_bytes), out, cap, C.byref(n)))
     return out.raw[:n.value]
 
 

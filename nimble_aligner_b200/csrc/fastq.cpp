@@ -34,6 +34,7 @@
 
 #include "host.hpp"
 #include "inflate.hpp"
+#include "pgunzip.hpp"
 
 using namespace nb;
 
@@ -204,14 +205,14 @@ inline size_t skip_blank(const char* d, size_t size, size_t pos) {  // parse_blo
 }
 // records whose first byte lies in [pos, bound): same grammar and the same failures as parse_block.  Appends to g; returns
 // the position of the next record (blank lines skipped).
-size_t parse_range(const char* d, size_t size, size_t pos, size_t bound, Segment& g) {
+size_t parse_range(const char* d, size_t size, size_t pos, size_t bound, Segment& g, bool* ran_out = nullptr) {   // ran_out: the data ended inside a record (status -1, nothing of that record kept)
   pos = skip_blank(d, size, pos);
   while (pos < bound && pos < size) {
     if (d[pos] != '@') { g.status = -1; return pos; }
     size_t p = next_line(d, size, pos);
     const size_t start = g.used;
     for (;;) {                                      // sequence lines up to the '+' line
-      if (p >= size) { g.status = -1; return pos; }
+      if (p >= size) { g.status = -1; g.used = start; if (ran_out) *ran_out = true; return pos; }
       size_t e = next_line(d, size, p), n = e - p;
       if (n && d[p + n - 1] == '\n') n--;
       if (n && d[p + n - 1] == '\r') n--;
@@ -221,13 +222,13 @@ size_t parse_range(const char* d, size_t size, size_t pos, size_t bound, Segment
     }
     const size_t slen = g.used - start; size_t qlen = 0;
     while (qlen < slen) {
-      if (p >= size) { g.status = -1; return pos; }
+      if (p >= size) { g.status = -1; g.used = start; if (ran_out) *ran_out = true; return pos; }
       size_t e = next_line(d, size, p), n = e - p;
       if (n && d[p + n - 1] == '\n') n--;
       if (n && d[p + n - 1] == '\r') n--;
       qlen += n; p = e;
     }
-    if (qlen != slen) { g.status = -1; return pos; }
+    if (qlen != slen) { g.status = -1; g.used = start; return pos; }
     if (!g.push_off()) { g.status = -2; return pos; }
     g.maxlen = std::max<u32>(g.maxlen, (u32)slen); g.n++;
     pos = skip_blank(d, size, p);
@@ -322,11 +323,101 @@ struct MapStream : SegStream {
   ~MapStream() override { finish(); if (d) munmap((void*)d, size); if (fd >= 0) ::close(fd); }
 };
 
+// ------------------------------------------------------------------------------------------------ gzip on several threads
+// pgunzip.hpp inflates one .gz file on T threads, chunk by chunk; each worker also PARSES the text of its chunk, from the
+// first position that looks like a record start (guess_start) to the last record that is complete in the chunk.  What lies in
+// front of the guess and behind the last complete record are a few lines per chunk; the consumer parses those — the bytes
+// carried over from the chunk before plus this chunk's head — in file order, and takes the worker's records only if that
+// parse ends exactly at the guess (then the guess was a record boundary of the sequential parse, and the worker's records
+// are what the sequential parse yields from there).  Otherwise it parses the chunk's text again from the carried bytes.
+struct GzParStream : SegStream {
+  int fd = -1; const u8* map = nullptr; size_t size = 0; nbz::ParallelGunzip pg;
+  struct Parsed { Segment* seg = nullptr; size_t head_end = 0, tail_start = 0; };   // a worker's result, carried by the chunk (user_ptr, user_a, user_b)
+  std::vector<std::unique_ptr<Segment>> segs; std::vector<Segment*> free_segs; std::mutex m; std::condition_variable cv; bool stop = false;
+  std::deque<Segment*> ready; std::string carry, piece; bool ended = false;
+  Segment* take_seg() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return stop || !free_segs.empty(); }); if (stop) return nullptr; Segment* g = free_segs.back(); free_segs.pop_back(); return g; }
+  void give_seg(Segment* g) { { std::lock_guard<std::mutex> lk(m); free_segs.push_back(g); } cv.notify_all(); }
+  bool open(const std::string& p, int threads, int extra) {
+    fd = ::open(p.c_str(), O_RDONLY); if (fd < 0) return false;
+    struct stat st; if (fstat(fd, &st) != 0) return false;
+    size = (size_t)st.st_size;
+    if (size) { void* q = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0); if (q == MAP_FAILED) return false; map = (const u8*)q; madvise(q, size, MADV_SEQUENTIAL); }
+    size_t cbytes = (size_t)1 << 20;                                                  // compressed bytes per chunk (about 4 MB of text)
+    if (const char* e = getenv("NB_GZ_CHUNK_KB")) { const size_t kb = (size_t)strtoull(e, nullptr, 10); if (kb >= 1) cbytes = kb << 10; }
+    const int n_segs = 2 * (2 * threads + 2) + 3 + extra + 4;                         // two per chunk in flight (its records, the junction's) + what the consumer holds
+    for (int i = 0; i < n_segs; i++) { segs.emplace_back(new Segment()); free_segs.push_back(segs.back().get()); }
+    pg.open(map, size, threads, cbytes, [this](size_t k, nbz::PgChunk& c) { parse_chunk(k, c); });
+    return true;
+  }
+  // worker: the records that lie completely inside this chunk's text
+  void parse_chunk(size_t k, nbz::PgChunk& c) {
+    Parsed p;
+    struct Put { Parsed& p; nbz::PgChunk& c; ~Put() { c.user_ptr = p.seg; c.user_a = p.head_end; c.user_b = p.tail_start; } } put{p, c};
+    const char* d = (const char*)c.text.data(); const size_t n = c.text.size();
+    p.head_end = p.tail_start = n;
+    if (c.status < 0 || !n) return;
+    const size_t g = k == 0 ? skip_blank(d, n, 0) : guess_start(d, n, 1);
+    if (g >= n) return;
+    Segment* sg = take_seg(); if (!sg) return;
+    if (!sg->begin()) { sg->status = -2; p.seg = sg; p.head_end = g; return; }
+    bool ran_out = false;
+    const size_t e = parse_range(d, n, g, n, *sg, &ran_out);
+    if (sg->status == -1 && ran_out) sg->status = 1;                                  // the last record continues in the next chunk
+    p.seg = sg; p.head_end = g; p.tail_start = e;                                     // (status -1 left: not a record where the guess said — the consumer parses again)
+  }
+  Segment* next() override {
+    while (ready.empty()) {
+      if (ended) return nullptr;
+      nbz::PgChunk* c = pg.next();
+      Segment* out = take_seg(); if (!out) return nullptr;
+      if (!c || c->status < 0 || !out->begin()) { out->clear(); out->status = !c || c->status < 0 ? -3 : -2; ready.push_back(out); ended = true; if (c) pg.recycle(c); break; }
+      Parsed p; p.seg = (Segment*)c->user_ptr; p.head_end = c->user_a; p.tail_start = c->user_b; c->user_ptr = nullptr;
+      const char* d = (const char*)c->text.data(); const size_t n = c->text.size(); const bool last = c->status == 0;
+      bool taken = false;
+      if (p.seg && p.seg->status == 1 && p.head_end < n) {
+        piece.assign(carry); piece.append(d, p.head_end);
+        bool ro = false; const size_t e = parse_range(piece.data(), piece.size(), 0, piece.size(), *out, &ro);
+        if (out->status == 1 && e >= piece.size()) {                                   // the junction parses up to the guess: the worker's records follow
+          ready.push_back(out); ready.push_back(p.seg); p.seg = nullptr;
+          carry.assign(d + p.tail_start, n - p.tail_start); taken = true;
+        } else if (out->status == -2) { ready.push_back(out); ended = true; pg.recycle(c); break; }
+        else out->begin();
+      }
+      if (!taken) {                                                                    // no usable guess in this chunk: its text behind the carried bytes, sequentially
+        if (p.seg) { if (p.seg->status == -2) { out->clear(); out->status = -2; } give_seg(p.seg); p.seg = nullptr; }
+        if (out->status == 1) {
+          piece.assign(carry); piece.append(d, n);
+          bool ro = false; const size_t e = parse_range(piece.data(), piece.size(), 0, piece.size(), *out, &ro);
+          if (out->status == -1 && ro) out->status = 1;
+          carry.assign(piece.data() + e, piece.size() - e);
+        }
+        ready.push_back(out);
+        if (out->status != 1) { ended = true; pg.recycle(c); break; }
+      }
+      pg.recycle(c);
+      if (last) {
+        ended = true;
+        Segment* fin = ready.back();
+        if (!carry.empty()) { fin->status = -1; }                                      // the file ends inside a record
+        else fin->status = 0;
+      }
+    }
+    Segment* g = ready.front(); ready.pop_front(); return g;
+  }
+  void recycle(Segment* g) override { give_seg(g); }
+  void finish() override { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); pg.finish(); }
+  ~GzParStream() override { finish(); if (map) munmap((void*)map, size); if (fd >= 0) ::close(fd); }
+};
+
 bool is_gzip(const std::string& p) { FILE* f = fopen(p.c_str(), "rb"); if (!f) return false; unsigned char h[2] = {0, 0}; size_t n = fread(h, 1, 2, f); fclose(f); return n == 2 && h[0] == 0x1f && h[1] == 0x8b; }
 
 // extra: segments the consumer may hold beyond the usual three (a driver feeding W contexts in turn holds 2 W + 1)
 std::unique_ptr<SegStream> open_stream(const std::string& path, int threads, u64 gz_block_records, size_t chunk_bytes, int extra = 0) {
-  if (is_gzip(path)) { std::unique_ptr<GzStream> g(new GzStream(gz_block_records, extra)); if (!g->open(path)) return nullptr; return g; }
+  if (is_gzip(path)) {
+    int gt = threads; if (const char* e = getenv("NB_GZ_THREADS")) gt = atoi(e);      // (1: the serial reader)
+    if (gt >= 2) { std::unique_ptr<GzParStream> g(new GzParStream()); if (!g->open(path, gt, extra)) return nullptr; return g; }
+    std::unique_ptr<GzStream> g(new GzStream(gz_block_records, extra)); if (!g->open(path)) return nullptr; return g;
+  }
   std::unique_ptr<MapStream> s(new MapStream());
   if (!s->open(path, threads, chunk_bytes, extra)) return nullptr;
   return s;
@@ -414,6 +505,21 @@ extern "C" int nb_inflate(const void* in, uint64_t in_len, int raw, uint64_t win
     if (*out_len + (uint64_t)n > out_cap) return fail(NB_ERR_OVERFLOW, "output buffer too small");
     memcpy(dst + *out_len, cur + HIST, (size_t)n); *out_len += (uint64_t)n;
     prev = cur; prev_len = (size_t)n; cur = cur == a.data() ? b.data() : a.data();
+  }
+  return NB_OK;
+}
+
+// host-only: a gzip file in memory through the parallel reader (pgunzip.hpp) with `threads` workers and `chunk_bytes` of
+// compressed data per chunk — parity tests against zlib
+extern "C" int nb_gunzip_parallel(const void* in, uint64_t in_len, int threads, uint64_t chunk_bytes, void* out, uint64_t out_cap, uint64_t* out_len) {
+  if ((!in && in_len) || (!out && out_cap) || !out_len) return fail(NB_ERR_INVALID, "null argument");
+  *out_len = 0;
+  nbz::ParallelGunzip pg; pg.open((const u8*)in, in_len, threads, chunk_bytes);
+  while (nbz::PgChunk* c = pg.next()) {
+    if (c->status < 0) return fail(NB_ERR_PARSE, "damaged gzip stream");
+    if (*out_len + c->text.size() > out_cap) return fail(NB_ERR_OVERFLOW, "output buffer too small");
+    memcpy((u8*)out + *out_len, c->text.data(), c->text.size()); *out_len += c->text.size();
+    pg.recycle(c);
   }
   return NB_OK;
 }

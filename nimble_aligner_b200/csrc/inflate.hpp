@@ -29,7 +29,7 @@ namespace nbz {
 
 typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64;
 
-enum { INF_MORE = 0, INF_END = 1, INF_ERROR = -1 };
+enum { INF_MORE = 0, INF_END = 1, INF_STOP = 2, INF_ERROR = -1 };
 
 // base values and extra bits of the length symbols 257..285 and the distance symbols 0..29 (RFC 1951 3.2.5)
 static const u16 LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -40,7 +40,20 @@ static const u8 DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6
 class Inflater {
  public:
   // [in, in_end): the whole remaining compressed input
-  void start(const u8* in, const u8* in_end) { in_ = in; end_ = in_end; bb_ = 0; bc_ = 0; in_block_ = false; final_ = false; stored_left_ = 0; btype_ = 0; }
+  void start(const u8* in, const u8* in_end) { origin_ = in_ = in; end_ = in_end; bb_ = 0; bc_ = 0; in_block_ = false; final_ = false; stored_left_ = 0; btype_ = 0; stop_bit_ = ~0ull; stop_out_ = ~(size_t)0; }
+  // ---- for the parallel reader (pgunzip.hpp): decoding that starts at a block header at any BIT of `data`, stops in front
+  // of the first block header at or behind bit `stop` (run / run16 return INF_STOP there), and reports where it is
+  void start_at_bit(const u8* data, const u8* in_end, u64 bit, u64 stop, size_t stop_out = ~(size_t)0) {   // stop_out: also stop in front of the first block header behind that many output elements
+    start(data + (bit >> 3), in_end); origin_ = data; stop_bit_ = stop; stop_out_ = stop_out;
+    if (bit & 7) { if (need(8)) take((u32)(bit & 7)); else in_ = end_; }
+  }
+  u64 bit_pos() const { return (u64)(in_ - origin_) * 8 - bc_; }       // of the next unread bit (meaningful between blocks)
+  bool header_at_bit(const u8* data, const u8* in_end, u64 bit) { start_at_bit(data, in_end, bit, ~0ull); return block_header() && btype_ == 2 && !final_; }   // is there a sound non-final dynamic block header?
+  // The same decoding into 16-bit symbols, for a stream entered in the middle, where the 32 KiB before the entry point are
+  // unknown: [out - 32768, out) must exist and hold the values 0x8000 + i (i = 0..32767) at the first call, so that a match
+  // reaching back behind the entry point copies PLACEHOLDERS for those bytes like any other symbol; whoever knows the real
+  // window replaces every value >= 0x8000 by window[value - 0x8000] afterwards.  base: the start of that placeholder window.
+  inline int run16(const u16* base, u16*& out, u16* out_end);
   // Decodes into [out, out_end); [base, out) must hold the output so far (at least its last 32 KiB).  Returns INF_END at
   // the end of the final block (out = end of the data; next_byte() = the first byte behind the deflate stream), INF_MORE
   // when the next symbol does not fit into the window (out = what was produced; call again with a new window),
@@ -58,6 +71,7 @@ class Inflater {
   //                         distance 30-16 base | 11-8 extra bits | 3-0 consume      (D_SUB: 24-16 start | 11-8 index bits)
   static const ptrdiff_t FAST_IN = 16, FAST_OUT = 258 + 32;   // margins of the fast loop: two refills; nine literals + the longest match + the stores' overrun
   const u8* in_ = nullptr; const u8* end_ = nullptr; u64 bb_ = 0; u32 bc_ = 0;   // invariant between calls: bits of bb_ above bc_ are zero
+  const u8* origin_ = nullptr; u64 stop_bit_ = ~0ull; size_t stop_out_ = ~(size_t)0;
   bool in_block_ = false, final_ = false; int btype_ = 0; u32 stored_left_ = 0;
   const u32* lt_ = nullptr; const u32* dt_ = nullptr;
   u32 ltab_[LCAP]; u32 dtab_[DCAP];
@@ -84,7 +98,17 @@ class Inflater {
   u32 take(u32 n) { u32 v = (u32)(bb_ & ((1ull << n) - 1)); bb_ >>= n; bc_ -= n; return v; }
   bool get(u32 n, u32& v) { if (!need(n)) return false; v = take(n); return true; }
   inline bool block_header();
-  inline int huff(const u8* base, u8*& out, u8* out_end);   // 0: block ended, 1: window full, -1: error
+  template <typename T> inline int huff(const T* base, T*& out, T* out_end);   // 0: block ended, 1: window full, -1: error.  T: u8, or u16 for run16
+  static void put_lits(u8* out, u32 w) { memcpy(out, &w, 4); }                   // three literals (or fewer and zeros) packed into w's bytes
+  static void put_lits(u16* out, u32 w) { const u64 x = (u64)(w & 0xFF) | ((u64)((w >> 8) & 0xFF) << 16) | ((u64)(w >> 16) << 32); memcpy(out, &x, 8); }
+  template <typename T> static void copy_match(T* dst, const T* src, T* end, u32 dist) {       // 8 bytes at a time; may write up to 16 bytes - 1 element past end
+    const u32 W = 8 / sizeof(T);
+    if (dist >= W) {
+      memcpy(dst, src, 8); memcpy(dst + W, src + W, 8);
+      if (end - dst > (ptrdiff_t)(2 * W)) { dst += 2 * W; src += 2 * W; do { memcpy(dst, src, 8); dst += W; src += W; } while (dst < end); }
+    } else if (dist == 1) { const T v = *src; if (sizeof(T) == 1) memset(dst, (int)v, (size_t)(end - dst)); else do { *dst++ = v; } while (dst < end); }
+    else { do { *dst++ = *src++; } while (dst < end); }
+  }
 };
 
 inline bool Inflater::build(const u8* lens, int n, int kind, u32* tab, int cap) {
@@ -198,16 +222,16 @@ inline bool Inflater::block_header() {
   return true;
 }
 
-inline int Inflater::huff(const u8* base, u8*& out_ref, u8* out_end) {
+template <typename T> inline int Inflater::huff(const T* base, T*& out_ref, T* out_end) {
   const u32* const lt = lt_; const u32* const dt = dt_;
-  u64 bb = bb_; u32 bc = bc_; const u8* in = in_; u8* out = out_ref;
+  u64 bb = bb_; u32 bc = bc_; const u8* in = in_; T* out = out_ref;
   const u32 LMASK = (1u << LP) - 1, DMASK = (1u << DP) - 1;
   int rc = -1;
 #define NBZ_REFILL() do { bb |= load64(in) << bc; in += (63 - bc) >> 3; bc |= 56; } while (0)
   // ---- fast loop: room for two refills and nine literals + the longest match (plus the stores' overrun) without looking.
   // The next symbol's entry is looked up BEFORE the match is copied and before the refill (whose load does not touch the
   // bits the lookup used: above bc the buffer already holds stream bits), so the table load overlaps both.
-#define NBZ_LITS() do { bb >>= (e & 15); bc -= (e & 15); const u32 w = (e >> 8) & 0x7FFFFF; memcpy(out, &w, 4); out += 1 + ((e >> 4) & 3); } while (0)
+#define NBZ_LITS() do { bb >>= (e & 15); bc -= (e & 15); put_lits(out, (e >> 8) & 0x7FFFFF); out += 1 + ((e >> 4) & 3); } while (0)
   if (end_ - in >= FAST_IN && out_end - out >= FAST_OUT) {
     NBZ_REFILL();
     u32 e = lt[bb & LMASK];
@@ -244,13 +268,8 @@ inline int Inflater::huff(const u8* base, u8*& out_ref, u8* out_end) {
         const u32 dist = ((d >> 16) & 0x7FFF) + (u32)(bb & ((1u << db) - 1)); bb >>= db; bc -= db;
         if (dist > (size_t)(out - base)) goto done;  // before the start of the output
         e = lt[bb & LMASK];                          // (at most 48 bits used since the refill: 16 stream bits are left)
-        const u8* src = out - dist; u8* dst = out; out += len;
-        if (dist >= 8) {                             // (writes up to 15 bytes past the match: inside FAST_OUT)
-          memcpy(dst, src, 8); memcpy(dst + 8, src + 8, 8);
-          if (len > 16) { dst += 16; src += 16; do { memcpy(dst, src, 8); dst += 8; src += 8; } while (dst < out); }
-        }
-        else if (dist == 1) { memset(dst, *src, len); }
-        else { do { *dst++ = *src++; } while (dst < out); }
+        T* const dst = out; out += len;
+        copy_match(dst, dst - dist, out, dist);         // (writes up to 15 elements past the match: inside FAST_OUT)
         NBZ_REFILL();
       }
     next:
@@ -272,7 +291,7 @@ inline int Inflater::huff(const u8* base, u8*& out_ref, u8* out_end) {
     if ((int32_t)e < 0) {
       const u32 n = 1 + ((e >> 4) & 3);
       if ((size_t)(out_end - out) < n) { bb = s_bb; bc = s_bc; in = s_in; rc = 1; goto done; }
-      u32 w = e >> 8; for (u32 i = 0; i < n; i++, w >>= 8) *out++ = (u8)(i == 2 ? (w & 0x7F) : w);
+      u32 w = e >> 8; for (u32 i = 0; i < n; i++, w >>= 8) *out++ = (T)(i == 2 ? (w & 0x7F) : (w & 0xFF));
       bc = (u32)left; continue;
     }
     if (e & L_EXC) { if (e & L_EOB) { bc = (u32)left; rc = 0; } goto done; }
@@ -287,7 +306,7 @@ inline int Inflater::huff(const u8* base, u8*& out_ref, u8* out_end) {
     if (left < 0) goto done;
     if (dist > (size_t)(out - base)) goto done;
     if (len > (size_t)(out_end - out)) { bb = s_bb; bc = s_bc; in = s_in; rc = 1; goto done; }
-    { const u8* src = out - dist; for (u32 i = 0; i < len; i++) out[i] = src[i]; out += len; }
+    { const T* src = out - dist; for (u32 i = 0; i < len; i++) out[i] = src[i]; out += len; }
     bc = (u32)left;
   }
 done:
@@ -299,6 +318,7 @@ inline int Inflater::run(const u8* base, u8*& out, u8* out_end) {
   for (;;) {
     if (!in_block_) {
       if (final_) return INF_END;
+      if (bit_pos() >= stop_bit_ || (size_t)(out - base) >= stop_out_) return INF_STOP;
       if (!block_header()) return INF_ERROR;
       in_block_ = true;
     }
@@ -309,7 +329,30 @@ inline int Inflater::run(const u8* base, u8*& out, u8* out_end) {
       if (stored_left_) return INF_MORE;
       in_block_ = false; continue;
     }
-    const int r = huff(base, out, out_end);
+    const int r = huff<u8>(base, out, out_end);
+    if (r < 0) return INF_ERROR;
+    if (r == 1) return INF_MORE;
+    in_block_ = false;
+  }
+}
+
+inline int Inflater::run16(const u16* base, u16*& out, u16* out_end) {
+  for (;;) {
+    if (!in_block_) {
+      if (final_) return INF_END;
+      if (bit_pos() >= stop_bit_ || (size_t)(out - base) >= stop_out_) return INF_STOP;
+      if (!block_header()) return INF_ERROR;
+      in_block_ = true;
+    }
+    if (btype_ == 0) {
+      size_t n = stored_left_; if (n > (size_t)(out_end - out)) n = (size_t)(out_end - out);
+      if (n > (size_t)(end_ - in_)) return INF_ERROR;
+      for (size_t i = 0; i < n; i++) out[i] = in_[i];
+      out += n; in_ += n; stored_left_ -= (u32)n;
+      if (stored_left_) return INF_MORE;
+      in_block_ = false; continue;
+    }
+    const int r = huff<u16>(base, out, out_end);
     if (r < 0) return INF_ERROR;
     if (r == 1) return INF_MORE;
     in_block_ = false;

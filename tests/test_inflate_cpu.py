@@ -193,3 +193,89 @@ def test_code_sets_zlib_accepts_or_rejects():
     sk[65 + 14] = 15; sk[256] = 15
     syms = [("l", 65 + i, 0, 0) for i in range(15)] * 3 + [("l", 256, 0, 0)]
     assert both(block(sk, [0], syms)) == bytes(range(65, 80)) * 3
+
+
+# ---------------------------------------------------------------------------------------------- several threads on one gzip file
+@pytest.mark.parametrize("name", sorted(CORPUS))
+def test_parallel_reader_equals_zlib(name):
+    """pgunzip.hpp: workers enter the deflate stream at guessed block headers with the window unknown; the text must be
+    zlib's whatever the chunk size (4 KiB chunks: hundreds of entry points, many of them useless) and thread count."""
+    data = CORPUS[name]
+    for level, strategy, memlevel in ((6, zlib.Z_DEFAULT_STRATEGY, 8), (1, zlib.Z_DEFAULT_STRATEGY, 8), (9, zlib.Z_DEFAULT_STRATEGY, 1), (0, zlib.Z_DEFAULT_STRATEGY, 8),
+                                      (6, zlib.Z_FIXED, 8), (6, zlib.Z_HUFFMAN_ONLY, 8)):
+        g = deflate(data, level, strategy, wbits=31, memlevel=memlevel)
+        assert zlib.decompress(g, 31) == data
+        for threads, chunk in ((1, 4096), (2, 4096), (5, 9000), (3, 1 << 20)):
+            assert nb.gunzip_parallel(g, threads, chunk, out_cap=len(data) + 64) == data, (level, strategy, threads, chunk)
+
+
+def test_parallel_reader_members_and_ratios():
+    rng = random.Random(21)
+    data = CORPUS["fastq"] * 3
+    # many members (bgzip: one per 64 KiB), members cut anywhere, empty members, bytes behind the last member
+    cuts = sorted(rng.randrange(len(data)) for _ in range(40))
+    members = b"".join(gzip.compress(data[a:b], rng.choice([1, 6, 9])) for a, b in zip([0] + cuts, cuts + [len(data)]))
+    for threads, chunk in ((4, 4096), (3, 50_000), (2, 1 << 20)):
+        assert nb.gunzip_parallel(members, threads, chunk, out_cap=len(data) + 64) == data
+        assert nb.gunzip_parallel(members + gzip.compress(b"") + b"\0" * 5000, threads, chunk, out_cap=len(data) + 64) == data
+    # text that expands a thousandfold: chunks are cut by their output size, the reader keeps working in bounded pieces
+    big = bytes(40_000_000)
+    g = gzip.compress(big, 6)
+    assert len(g) < 50_000
+    for threads, chunk in ((4, 4096), (2, 1 << 20)):
+        out = nb.gunzip_parallel(g, threads, chunk, out_cap=len(big) + 64)
+        assert len(out) == len(big) and out == big
+    mixed = gzip.compress(big[:20_000_000] + data + big[:9_000_000] + data, 6)
+    assert nb.gunzip_parallel(mixed, 4, 4096, out_cap=30_000_000 + 2 * len(data)) == big[:20_000_000] + data + big[:9_000_000] + data
+
+
+def test_parallel_reader_fails_loudly_on_damage():
+    rng = random.Random(4)
+    data = CORPUS["fastq"] * 2
+    good = gzip.compress(data, 6)
+    with pytest.raises(nb.NbError):
+        nb.gunzip_parallel(b"", 4, 4096)
+    with pytest.raises(nb.NbError):
+        nb.gunzip_parallel(data[:5000], 4, 4096)
+    with pytest.raises(nb.NbError):
+        nb.gunzip_parallel(good[:-5], 4, 4096, out_cap=len(data) + 64)
+    ok = err = 0
+    for it in range(150):
+        b = bytearray(good)
+        if it % 3 == 0:
+            b = b[:rng.randrange(20, len(b))]
+        else:
+            for _ in range(rng.randint(1, 3)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        try:
+            out = nb.gunzip_parallel(bytes(b), rng.choice([2, 4]), rng.choice([4096, 30_000]), out_cap=len(data) + 200_000)
+            assert out == data
+            ok += 1
+        except nb.NbError:
+            err += 1
+    assert err > 130
+
+
+def test_inflate_under_sanitizers(tmp_path):
+    """tests/native/inflate_harness.cpp built with -fsanitize=address,undefined: corpus files and damaged copies of them through
+    the parallel and the serial reader (bounds, overflows, misaligned access; the same harness runs clean under -fsanitize=thread)."""
+    import os
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "harness")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+                        os.path.join(here, "native", "inflate_harness.cpp"), "-lz", "-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("sanitizer runtime not installed")
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = []
+    for i, (name, level, strategy) in enumerate([("fastq", 6, zlib.Z_DEFAULT_STRATEGY), ("fastq", 1, zlib.Z_HUFFMAN_ONLY), ("skewed", 9, zlib.Z_DEFAULT_STRATEGY),
+                                                  ("far", 6, zlib.Z_DEFAULT_STRATEGY), ("random", 6, zlib.Z_DEFAULT_STRATEGY), ("period7", 6, zlib.Z_FIXED), ("zeros", 6, zlib.Z_DEFAULT_STRATEGY)]):
+        p = tmp_path / ("c%d.gz" % i); p.write_bytes(deflate(CORPUS[name], level, strategy, wbits=31)); files.append(str(p))
+    data = CORPUS["fastq"]
+    p = tmp_path / "members.gz"; p.write_bytes(b"".join(gzip.compress(data[a:a + 70_000], 6) for a in range(0, len(data), 70_000)) + b"\0" * 50); files.append(str(p))
+    r = subprocess.run([exe] + files, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "done: 0 problems" in r.stdout and "runtime error" not in r.stderr and "ERROR" not in r.stderr, (r.stdout[-1500:], r.stderr[-3000:])
