@@ -2,15 +2,17 @@
 // Mirrors /root/reference/src/parse/fastq.rs:8-43 (niffler gz autodetect + bio fastq records -> DnaString::from_acgt_bytes),
 // src/utils.rs:27-51 (write_to_tsv: append, header iff empty, features TAB-joined) and src/process/fastq.rs:7-30.
 //
-// Two feeders behind one interface (a stream of parsed segments: bases concatenated in pinned memory + offsets):
+// Three feeders behind one interface (a stream of parsed segments: bases concatenated in pinned memory + offsets):
 //   MapStream  plain FASTQ: the file is mapped and cut into byte chunks that T host threads parse at the same time.  A chunk
 //              starts at the first record start at or after its byte boundary, found by a local pattern test ('@' line whose
 //              next-but-one line starts with '+' and whose sequence and quality lines are equally long).  That guess is never
 //              trusted: the consumer accepts chunk c only if it began exactly where the parse of chunk c-1 ended, and parses
 //              it again from that position otherwise (multi-line records can defeat the pattern; the result is then still
 //              that of the sequential parse, only slower).
-//   GzStream   gzip input (sniffed by its magic bytes, like niffler): inflate is serial per file, one thread inflates and
-//              parses blocks in place.
+//   GzParStream  gzip input (sniffed by its magic bytes, like niffler) with two or more threads for the file: pgunzip.hpp
+//              inflates it on all of them (entry points at guessed block headers, confirmed by a chain through the chunks),
+//              each worker parses the text of its chunk, the consumer parses the few lines at the chunk junctions.
+//   GzStream   gzip input with one thread: one thread inflates (inflate.hpp over the mapped file), a second one parses.
 // The consumer hands min(records left in R1's segment, records left in R2's) pairs to nb_align_batch at a time, so the two
 // files never have to be cut at the same record numbers.
 #include <fcntl.h>
