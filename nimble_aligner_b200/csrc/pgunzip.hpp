@@ -161,8 +161,50 @@ class ParallelGunzip {
     // ---- speculative decode of this range, entered at a guessed block header
     size_t nsym = 0; u64 s = ~0ull, e = 0; int s_end = INF_ERROR; const u8* s_next = nullptr;
     u64 t0 = now_ns();
+    // A file of many members (bgzip: one per 64 KiB; cat of .gz files) needs no guessing about windows: a member starts with an
+    // empty one.  The worker looks for a member header in its range — the first candidate whose member decodes to the CRC-32 and
+    // ISIZE of its trailer — and decodes whole members from there, as bytes; the chain takes them if it arrives at that very
+    // byte between two members.
+    std::vector<u8> btext; std::vector<std::pair<size_t, std::pair<u32, u32>>> bmembers;   // (end offset in btext, (CRC-32, ISIZE) of the trailer)
+    size_t b_start = ~(size_t)0, b_end = 0;
     if (k > 0 && T_ > 1 && lo < (u64)n_ * 8) {
-      s = find_block(lo, limit == ~0ull ? (u64)n_ * 8 : limit, scratch);
+      const size_t lo_b = (size_t)(lo >> 3), hi_b = limit == ~0ull ? n_ : (size_t)(limit >> 3);
+      for (size_t h = lo_b; h + 18 <= n_ && h < hi_b; h++) {
+        const u8* q = (const u8*)memchr(data_ + h, 0x1F, (hi_b < n_ - 17 ? hi_b : n_ - 17) - h); if (!q) break;
+        h = (size_t)(q - data_);
+        if (q[1] != 0x8B || q[2] != 8 || (q[3] & 0xE0)) continue;
+        const u8* d = gzip_header(q, data_ + n_); if (!d) continue;
+        if (btext.size() < ((size_t)1 << 20)) btext.resize((size_t)1 << 20);
+        inf.start(d, data_ + n_);
+        u8* o = btext.data(); int r;
+        for (;;) { r = inf.run(btext.data(), o, btext.data() + btext.size()); if (r != INF_MORE || btext.size() >= out_cap()) break; const size_t at = (size_t)(o - btext.data()); btext.resize(btext.size() * 2); o = btext.data() + at; }
+        const u8* tr = inf.next_byte();
+        if (r != INF_END || (size_t)(data_ + n_ - tr) < 8) continue;
+        u32 wc, ws; memcpy(&wc, tr, 4); memcpy(&ws, tr + 4, 4);
+        if (ws != (u32)(o - btext.data()) || wc != (u32)crc32_z(0L, btext.data(), (size_t)(o - btext.data()))) continue;
+        b_start = h; break;
+      }
+      if (b_start != ~(size_t)0) {
+        const u8* p = data_ + b_start; const size_t cap = out_cap(); bool good = true;
+        if (btext.size() < cap + (1u << 20)) btext.resize(cap + (1u << 20));
+        size_t used = 0;
+        while (good && p < data_ + n_ && (size_t)(p - data_) < hi_b && used < cap) {
+          const u8* d = gzip_header(p, data_ + n_); if (!d) break;
+          inf.start(d, data_ + n_);
+          u8* o = btext.data() + used; int r;
+          for (;;) { r = inf.run(btext.data() + used, o, btext.data() + btext.size()); if (r != INF_MORE) break; const size_t at = (size_t)(o - btext.data()); btext.resize(btext.size() * 2); o = btext.data() + at; }
+          const u8* tr = inf.next_byte();
+          if (r != INF_END || (size_t)(data_ + n_ - tr) < 8) { good = false; break; }
+          u32 wc, ws; memcpy(&wc, tr, 4); memcpy(&ws, tr + 4, 4);
+          used = (size_t)(o - btext.data()); bmembers.push_back({used, {wc, ws}}); p = tr + 8;
+        }
+        if (!good || bmembers.empty()) { b_start = ~(size_t)0; bmembers.clear(); } else { b_end = (size_t)(p - data_); btext.resize(used); }
+      }
+      { const u64 t1 = now_ns(); ns_find_ += t1 - t0; t0 = t1; }
+    }
+    if (k > 0 && T_ > 1 && lo < (u64)n_ * 8 && b_start == ~(size_t)0) {
+      { u64 to = limit == ~0ull ? (u64)n_ * 8 : limit; if (to - lo > ((u64)4 << 20)) to = lo + ((u64)4 << 20);      // (no block header in half a megabyte: stored or giant blocks — left to the chain)
+        s = find_block(lo, to, scratch); }
       { const u64 t1 = now_ns(); ns_find_ += t1 - t0; t0 = t1; }
       if (s != ~0ull) {
         if (sym.size() < 32768 + C_ * 6 + 4096) sym.resize(32768 + C_ * 6 + 4096);
@@ -191,7 +233,7 @@ class ParallelGunzip {
     { std::lock_guard<std::mutex> lk(m_); if (!text_pool_.empty()) { text = std::move(text_pool_.back()); text_pool_.pop_back(); } }   // (a buffer whose pages exist already)
     text.clear();
     std::vector<Piece> pieces; std::vector<size_t> seg_end; std::vector<Seg> seg_info;   // (segment ends as offsets into text)
-    bool spec_used = false, capped = false; const bool s_found = nsym > 0 || s != ~0ull; std::vector<u8> buf;
+    bool spec_used = false, capped = false; const bool s_found = nsym > 0 || s != ~0ull || b_start != ~(size_t)0; std::vector<u8> buf;
     auto end_member = [&](const u8* trailer) -> bool {               // trailer: 8 bytes behind the deflate stream
       if ((size_t)(data_ + n_ - trailer) < 8) return false;
       Seg g; g.len = 0; g.crc = 0; g.ends_member = true; memcpy(&g.want_crc, trailer, 4); memcpy(&g.want_size, trailer + 4, 4);
@@ -203,6 +245,14 @@ class ParallelGunzip {
       if (!cs.in_member) {
         if (cs.hdr >= n_) { if (!cs.members) cs.error = true; cs.done = true; break; }
         if ((u64)cs.hdr * 8 >= limit) break;                          // the next member begins in a later chunk's range
+        if (b_start != ~(size_t)0 && cs.hdr == b_start) {              // the members this worker decoded on its own begin exactly here
+          size_t a = 0; const size_t off = text.size();
+          text.insert(text.end(), btext.begin(), btext.end());
+          for (const auto& mb : bmembers) { Seg g; g.len = 0; g.crc = 0; g.ends_member = true; g.want_crc = mb.second.first; g.want_size = mb.second.second; seg_end.push_back(off + mb.first); seg_info.push_back(g); a = mb.first; }
+          (void)a; cs.hdr = b_end; cs.members += bmembers.size(); cs.window.clear(); b_start = ~(size_t)0; n_spec_++;
+          continue;
+        }
+        if (b_start != ~(size_t)0 && cs.hdr > b_start) b_start = ~(size_t)0;   // that signature was not a member boundary
         const u8* d = gzip_header(data_ + cs.hdr, data_ + n_);
         if (!d) { if (!cs.members) cs.error = true; cs.done = true; break; }      // bytes behind the last member that are no member: ignored
         cs.in_member = true; cs.bit = (u64)(d - data_) * 8; cs.window.clear();
@@ -247,7 +297,7 @@ class ParallelGunzip {
       is_last = false;
     }
     if (is_last && !cs.error && !cs.done) cs.error = true;   // the data ended inside a member
-    if (s_found && !spec_used) n_bad_++;
+    if (s_found && !spec_used && (s != ~0ull || b_start != ~(size_t)0 || nsym)) { if (bmembers.empty() || b_start != ~(size_t)0) n_bad_++; }
     publish_chain(t, cs);
     { const u64 t1 = now_ns(); ns_chain_ += t1 - t0; t0 = t1; }
     // ---- off the chain: placeholders -> bytes, checksums

@@ -218,6 +218,18 @@ def test_parallel_reader_members_and_ratios():
     for threads, chunk in ((4, 4096), (3, 50_000), (2, 1 << 20)):
         assert nb.gunzip_parallel(members, threads, chunk, out_cap=len(data) + 64) == data
         assert nb.gunzip_parallel(members + gzip.compress(b"") + b"\0" * 5000, threads, chunk, out_cap=len(data) + 64) == data
+    # bgzip's layout (a BC extra field per member, an empty member at the end): workers enter at member headers
+    def bgzf(d):
+        out = []
+        for k in range(0, len(d), 65280):
+            c = d[k:k + 65280]; cd = deflate(c, 6)
+            out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(cd) + 25) + cd + struct.pack("<II", zlib.crc32(c) & 0xFFFFFFFF, len(c)))
+        return b"".join(out) + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    for threads, chunk in ((4, 4096), (4, 100_000)):
+        assert nb.gunzip_parallel(bgzf(data), threads, chunk, out_cap=len(data) + 64) == data
+    damaged = bytearray(bgzf(data)); damaged[len(damaged) // 2] ^= 0x10
+    with pytest.raises(nb.NbError):
+        nb.gunzip_parallel(bytes(damaged), 4, 100_000, out_cap=len(data) + 64)
     # text that expands a thousandfold: chunks are cut by their output size, the reader keeps working in bounded pieces
     big = bytes(40_000_000)
     g = gzip.compress(big, 6)
