@@ -361,7 +361,7 @@ struct GzParStream : SegStream {
     const size_t g = k == 0 ? skip_blank(d, n, 0) : guess_start(d, n, 1);
     if (g >= n) return;
     Segment* sg = take_seg(); if (!sg) return;
-    if (!sg->begin()) { sg->status = -2; p.seg = sg; p.head_end = g; return; }
+    if (!sg->begin() || !sg->seq.ensure(n / 2 + 65536, 0) || !sg->offb.ensure((n / 64 + 1024) * 8, 8)) { sg->status = -2; p.seg = sg; p.head_end = g; return; }   // sized once: growing a pinned buffer step by step costs a cudaMallocHost and a copy each time
     bool ran_out = false;
     const size_t e = parse_range(d, n, g, n, *sg, &ran_out);
     if (sg->status == -1 && ran_out) sg->status = 1;                                  // the last record continues in the next chunk
