@@ -113,13 +113,17 @@ def test_feeder_errors(tmp_path):
     assert out.read_text() == ""
 
 
+@pytest.mark.parametrize("gz_threads", [1, 3])
 @pytest.mark.parametrize("chunk_kb", [1, 7, 4096])
 @pytest.mark.parametrize("kw", [dict(), dict(crlf=True, multiline=True, blanks=True), dict(final_newline=False)])
-def test_gzip_stream_through_the_inflate_thread(tmp_path, monkeypatch, chunk_kb, kw):
-    """.gz input: one thread inflates the mapped file (csrc/inflate.hpp) into text chunks, a second one parses them; lines
-    straddle chunk borders (1 KiB chunks: every few lines), the file may consist of several gzip members (bgzip, cat), and
-    the records must be those of the sequential parse of the plain text."""
+def test_gzip_streams(tmp_path, monkeypatch, chunk_kb, kw, gz_threads):
+    """.gz input.  One thread for the file: it inflates the mapped file (csrc/inflate.hpp) into text chunks, a second one
+    parses them.  More threads: csrc/pgunzip.hpp inflates on all of them and every worker parses its own chunk, the consumer
+    the few lines at the junctions.  Either way lines and records straddle chunk borders (1 KiB / 4 KiB chunks: every few
+    lines), the file may consist of several gzip members (bgzip, cat) cut anywhere, and the records must be those of the
+    sequential parse of the plain text."""
     monkeypatch.setenv("NB_GZ_CHUNK_KB", str(chunk_kb))
+    monkeypatch.setenv("NB_GZ_THREADS", str(gz_threads))
     rng = random.Random(chunk_kb * 31 + len(kw))
     t1, t2 = make_fastq(rng, 3000, **kw), make_fastq(rng, 3000, **kw)
     with gzip.open(tmp_path / "r1.fastq.gz", "wb", compresslevel=1) as f:
@@ -141,9 +145,10 @@ def test_damaged_gzip_input_is_an_error_not_an_early_end(tmp_path):
              "crc.fastq.gz": good[:-8] + bytes([good[-8] ^ 1]) + good[-7:]}
     for name, b in cases.items():
         (tmp_path / name).write_bytes(b)
-        with pytest.raises(nb.NbError) as e:
-            nb.fastq_dump([tmp_path / name], out, num_cores=2)
-        assert e.value.code == -3, name
+        for cores in (1, 2, 5):                                      # the serial reader and the parallel one
+            with pytest.raises(nb.NbError) as e:
+                nb.fastq_dump([tmp_path / name], out, num_cores=cores)
+            assert e.value.code == -3, name
     assert any("gzip" in str(x) for x in [e.value])
     (tmp_path / "ok.fastq.gz").write_bytes(good + b"\0" * 100)        # padding behind the last member is ignored (gzip -d does the same)
     nb.fastq_dump([tmp_path / "ok.fastq.gz"], out, num_cores=2)
