@@ -811,7 +811,10 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
     cut[parts] = ng;
     parallel_ranges(parts, (size_t)parts, [&](size_t ta, size_t tb2, int) {
       for (size_t t = ta; t < tb2; t++) {
-        std::string text; text.reserve(1 << 20); char num[32];
+        std::string text; text.reserve((size_t)(pair0[cut[t + 1]] - pair0[cut[t]]) * 448 + 4096); char num[32];   // (about 400 bytes per row)
+        std::vector<std::string> feats_of(O.callset_off.size()); std::vector<char> feats_made(O.callset_off.size(), 0);    // callset -> "name,name,..." (made on first use)
+        const std::string no_feats;
+        auto put_num = [&](long long x) { char* e = num; if (x < 0) { *e++ = '-'; x = -x; } if ((unsigned long long)x <= 0xFFFFFFFFull) e = put_u32(e, (u32)x); else e += snprintf(e, 24, "%lld", x); text.append(num, (size_t)(e - num)); };
         std::vector<std::pair<const char*, u32>> scored;   // field 0 of the records that got a count row in this scope (a handful at most)
         auto is_scored = [&](const Rec& x) { const char* q; u32 l; field0(x, q, l); for (const auto& sc : scored) if (same(sc.first, sc.second, q, l)) return true; return false; };
         for (size_t g = cut[t]; g < cut[t + 1]; g++) {
@@ -821,15 +824,15 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
           auto emit = [&](const std::string& feats, long long score, size_t pj) {
             const Rec& sq = v[2 * pj]; const Rec& mt = v[2 * pj + 1]; const nb_pair_result& pr = O.pres[pbase + pj];
             const nb_read_result& ra = O.rres[2 * (pbase + pj)]; const nb_read_result& rb = O.rres[2 * (pbase + pj) + 1];
-            text += feats; text += '\t'; snprintf(num, sizeof num, "%lld", score); text += num; text += '\t';
+            text += feats; text += '\t'; put_num(score); text += '\t';
             append_data_values(mt, text); text += '\t'; append_data_values(sq, text); text += '\t';      // "r1" = mate slot, "r2" = sequence slot (108-117)
-            text += nb_reason_str(pr.fr2); text += '\t'; snprintf(num, sizeof num, "%u", (unsigned)(rb.pass ? rb.score : 0)); text += num; text += "\tNone\t0\t";
-            text += nb_reason_str(pr.fr1); text += '\t'; snprintf(num, sizeof num, "%u", (unsigned)(ra.pass ? ra.score : 0)); text += num; text += "\tNone\t0\t";
+            text += nb_reason_str(pr.fr2); text += '\t'; put_num(rb.pass ? rb.score : 0); text += "\tNone\t0\t";
+            text += nb_reason_str(pr.fr1); text += '\t'; put_num(ra.pass ? ra.score : 0); text += "\tNone\t0\t";
             text += nb_reason_str(pr.triage); text += "\tNone\n";
           };
           for (u64 r = row_begin[g]; r < row_begin[g + 1]; r++) {
-            u32 cs = O.row_callset[r]; std::string feats;
-            for (u64 k = O.callset_off[cs]; k < O.callset_off[cs + 1]; k++) { if (!feats.empty()) feats += ","; feats += nb_library_group_name(libs[li], O.callset_items[k]); }
+            const u32 cs = O.row_callset[r]; std::string& feats = feats_of[cs];
+            if (!feats_made[cs]) { feats_made[cs] = 1; for (u64 k = O.callset_off[cs]; k < O.callset_off[cs + 1]; k++) { if (!feats.empty()) feats += ","; feats += nb_library_group_name(libs[li], O.callset_items[k]); } }
             // representative: the last pair of the scope whose read_key resolved to this callset (the reference keeps an arbitrary one)
             size_t rep = gp;
             for (size_t pj = gp; pj-- > 0;) { u32 slot = O.pres[pbase + pj].callset; if (slot != NONE32 && O.slot_to_callset[slot] == cs) { rep = pj; break; } }
@@ -837,7 +840,7 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
             { const char* q; u32 l; field0(v[2 * rep], q, l); scored.push_back({q, l}); }
             emit(feats, (long long)O.row_count[r], rep);
           }
-          for (size_t pj = 0; pj < gp; pj++) { if (!scored.empty() && is_scored(v[2 * pj + 1])) continue; emit("", 0, pj); }   // zero rows (332-353)
+          for (size_t pj = 0; pj < gp; pj++) { if (!scored.empty() && is_scored(v[2 * pj + 1])) continue; emit(no_feats, 0, pj); }   // zero rows (332-353)
         }
         if (!text.empty()) { wrote[t] = 1; if (!gzip_member(text, GZ_LEVEL, member[t])) bad[t] = 1; }
       } });
