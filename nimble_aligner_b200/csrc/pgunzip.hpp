@@ -42,7 +42,7 @@ class ParallelGunzip {
  public:
   ~ParallelGunzip() {
     finish();
-    if (getenv("NB_GZ_STATS") && n_) fprintf(stderr, "parallel gunzip: %zu chunks of %zu KiB on %d threads: %zu entered at a guessed block header, %zu guesses discarded, %.1f MB decoded the ordinary way\n",
+    if (getenv("NB_GZ_STATS") && n_) fprintf(stderr, "parallel gunzip: %zu chunks of %zu KiB on %d threads: %zu entered at a guessed block / member header, %zu guesses discarded, %.1f MB decoded the ordinary way\n",
                                              tasks_.size(), C_ >> 10, T_, (size_t)n_spec_, (size_t)n_bad_, (double)serial_bytes_ / 1e6),
                                      fprintf(stderr, "  thread time: find %.2fs, entered decode %.2fs, waiting for the chain %.2fs, on the chain %.2fs, placeholders %.2fs, crc %.2fs, parse %.2fs\n",
                                              ns_find_ / 1e9, ns_spec_ / 1e9, ns_wait_ / 1e9, ns_chain_ / 1e9, ns_resolve_ / 1e9, ns_crc_ / 1e9, ns_post_ / 1e9);
@@ -125,14 +125,14 @@ class ParallelGunzip {
 
   void work() {
     std::unique_ptr<Inflater> inf(new Inflater()), scratch(new Inflater());
-    std::vector<u16> sym;                            // this worker's symbol buffer, kept between chunks (fresh pages are not free)
+    std::vector<u16> sym; std::vector<u8> btext;     // this worker's symbol / member-text buffers, kept between chunks (fresh pages are not free)
     for (;;) {
       size_t k;
       { std::unique_lock<std::mutex> lk(m_);
         cv_.wait(lk, [&] { return stop_ || (next_task_ < tasks_.size() && next_task_ < recycled_ + look_); });
         if (stop_) return;
         k = next_task_++; }
-      run_task(k, *inf, *scratch, sym);
+      run_task(k, *inf, *scratch, sym, btext);
     }
   }
 
@@ -153,7 +153,7 @@ class ParallelGunzip {
     w.insert(w.end(), p, p + n);
   }
 
-  void run_task(size_t k, Inflater& inf, Inflater& scratch, std::vector<u16>& sym) {
+  void run_task(size_t k, Inflater& inf, Inflater& scratch, std::vector<u16>& sym, std::vector<u8>& btext) {
     Task* tp; bool is_last;
     { std::lock_guard<std::mutex> lk(m_); tp = tasks_[k].get(); is_last = k + 1 == tasks_.size(); }   // (the list may grow: see the end of the chain loop)
     Task& t = *tp;
@@ -165,8 +165,8 @@ class ParallelGunzip {
     // empty one.  The worker looks for a member header in its range — the first candidate whose member decodes to the CRC-32 and
     // ISIZE of its trailer — and decodes whole members from there, as bytes; the chain takes them if it arrives at that very
     // byte between two members.
-    std::vector<u8> btext; std::vector<std::pair<size_t, std::pair<u32, u32>>> bmembers;   // (end offset in btext, (CRC-32, ISIZE) of the trailer)
-    size_t b_start = ~(size_t)0, b_end = 0;
+    std::vector<std::pair<size_t, std::pair<u32, u32>>> bmembers;   // (end offset in btext, (CRC-32, ISIZE) of the trailer)
+    size_t b_start = ~(size_t)0, b_end = 0, b_used = 0;
     if (k > 0 && T_ > 1 && lo < (u64)n_ * 8) {
       const size_t lo_b = (size_t)(lo >> 3), hi_b = limit == ~0ull ? n_ : (size_t)(limit >> 3);
       for (size_t h = lo_b; h + 18 <= n_ && h < hi_b; h++) {
@@ -198,7 +198,7 @@ class ParallelGunzip {
           u32 wc, ws; memcpy(&wc, tr, 4); memcpy(&ws, tr + 4, 4);
           used = (size_t)(o - btext.data()); bmembers.push_back({used, {wc, ws}}); p = tr + 8;
         }
-        if (!good || bmembers.empty()) { b_start = ~(size_t)0; bmembers.clear(); } else { b_end = (size_t)(p - data_); btext.resize(used); }
+        if (!good || bmembers.empty()) { b_start = ~(size_t)0; bmembers.clear(); } else { b_end = (size_t)(p - data_); b_used = used; }
       }
       { const u64 t1 = now_ns(); ns_find_ += t1 - t0; t0 = t1; }
     }
@@ -233,7 +233,7 @@ class ParallelGunzip {
     { std::lock_guard<std::mutex> lk(m_); if (!text_pool_.empty()) { text = std::move(text_pool_.back()); text_pool_.pop_back(); } }   // (a buffer whose pages exist already)
     text.clear();
     std::vector<Piece> pieces; std::vector<size_t> seg_end; std::vector<Seg> seg_info;   // (segment ends as offsets into text)
-    bool spec_used = false, capped = false; const bool s_found = nsym > 0 || s != ~0ull || b_start != ~(size_t)0; std::vector<u8> buf;
+    bool spec_used = false, guess_used = false, capped = false; const bool have_guess = s != ~0ull || b_start != ~(size_t)0; std::vector<u8> buf;
     auto end_member = [&](const u8* trailer) -> bool {               // trailer: 8 bytes behind the deflate stream
       if ((size_t)(data_ + n_ - trailer) < 8) return false;
       Seg g; g.len = 0; g.crc = 0; g.ends_member = true; memcpy(&g.want_crc, trailer, 4); memcpy(&g.want_size, trailer + 4, 4);
@@ -246,10 +246,10 @@ class ParallelGunzip {
         if (cs.hdr >= n_) { if (!cs.members) cs.error = true; cs.done = true; break; }
         if ((u64)cs.hdr * 8 >= limit) break;                          // the next member begins in a later chunk's range
         if (b_start != ~(size_t)0 && cs.hdr == b_start) {              // the members this worker decoded on its own begin exactly here
-          size_t a = 0; const size_t off = text.size();
-          text.insert(text.end(), btext.begin(), btext.end());
-          for (const auto& mb : bmembers) { Seg g; g.len = 0; g.crc = 0; g.ends_member = true; g.want_crc = mb.second.first; g.want_size = mb.second.second; seg_end.push_back(off + mb.first); seg_info.push_back(g); a = mb.first; }
-          (void)a; cs.hdr = b_end; cs.members += bmembers.size(); cs.window.clear(); b_start = ~(size_t)0; n_spec_++;
+          const size_t off = text.size();
+          text.insert(text.end(), btext.begin(), btext.begin() + b_used);
+          for (const auto& mb : bmembers) { Seg g; g.len = 0; g.crc = 0; g.ends_member = true; g.want_crc = mb.second.first; g.want_size = mb.second.second; seg_end.push_back(off + mb.first); seg_info.push_back(g); }
+          cs.hdr = b_end; cs.members += bmembers.size(); cs.window.clear(); b_start = ~(size_t)0; guess_used = true; n_spec_++;
           continue;
         }
         if (b_start != ~(size_t)0 && cs.hdr > b_start) b_start = ~(size_t)0;   // that signature was not a member boundary
@@ -261,7 +261,7 @@ class ParallelGunzip {
       if (cs.bit >= limit) break;
       if (s != ~0ull && !spec_used && cs.bit == s) {
         // the guess was a block boundary the real decode arrives at: this chunk's symbols are its text
-        spec_used = true; n_spec_++;
+        spec_used = guess_used = true; n_spec_++;
         Piece p; p.spec = true; p.off = text.size(); p.len = nsym; p.window = cs.window;
         text.resize(text.size() + nsym);
         // the window behind the piece: only its last 32 KiB have to be real bytes now
@@ -297,7 +297,7 @@ class ParallelGunzip {
       is_last = false;
     }
     if (is_last && !cs.error && !cs.done) cs.error = true;   // the data ended inside a member
-    if (s_found && !spec_used && (s != ~0ull || b_start != ~(size_t)0 || nsym)) { if (bmembers.empty() || b_start != ~(size_t)0) n_bad_++; }
+    if (have_guess && !guess_used) n_bad_++;
     publish_chain(t, cs);
     { const u64 t1 = now_ns(); ns_chain_ += t1 - t0; t0 = t1; }
     // ---- off the chain: placeholders -> bytes, checksums
