@@ -322,6 +322,8 @@ int nb_fastq_dump(const char* const* input_files, uint32_t n_inputs, int num_cor
 int nb_inflate(const void* in, uint64_t in_len, int raw, uint64_t window, void* out, uint64_t out_cap, uint64_t* out_len);
 /* host-only: a gzip file in memory through the FASTQ feeder's parallel reader (`threads` workers enter the deflate stream
  * at guessed block headers of `chunk_bytes` byte ranges; nothing is emitted that the sequential decode does not confirm) */
+/* host-only: one gzip member made by the BAM driver's TSV compressor (GzEncoder's place in src/process/bam.rs:22-42) */
+int nb_gzip_fast(const void* in, uint64_t in_len, void* out, uint64_t out_cap, uint64_t* out_len);
 int nb_gunzip_parallel(const void* in, uint64_t in_len, int threads, uint64_t chunk_bytes, void* out, uint64_t out_cap, uint64_t* out_len);
 
 /* process::bam::process (src/process/bam.rs:45-243) behind the same library loop: BGZF/BAM decode on host threads,

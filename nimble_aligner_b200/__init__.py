@@ -137,6 +137,7 @@ _SIGS = {
     "nb_bam_dump_groups": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "nb_fastq_dump": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_char_p]),
     "nb_gunzip_parallel": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "nb_gzip_fast": (C.c_int, [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "nb_inflate": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "nb_process_fastq_devices": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32]),
     "nb_process_bam": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]),
@@ -644,6 +645,15 @@ def gunzip_parallel(data, threads=4, chunk_bytes=1 << 20, out_cap=None):
     out = C.create_string_buffer(max(cap, 1))
     n = C.c_uint64(0)
     _ck(lib().nb_gunzip_parallel(bytes(data), len(data), int(threads), int(chunk_bytes), out, cap, C.byref(n)))
+    return out.raw[:n.value]
+
+
+def gzip_fast(data):
+    """One gzip member made by the BAM driver's TSV compressor (tests inflate it with zlib)."""
+    cap = len(data) + len(data) // 4 + 4096
+    out = C.create_string_buffer(cap)
+    n = C.c_uint64(0)
+    _ck(lib().nb_gzip_fast(bytes(data), len(data), out, cap, C.byref(n)))
     return out.raw[:n.value]
 
 

@@ -23,7 +23,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("host.hpp", "kernels.cuh", "khash.h", "kmap.cuh", "inflate.hpp", "pgunzip.hpp")] + [os.path.join(HERE, "..", "include", "nimble_b200.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("host.hpp", "kernels.cuh", "khash.h", "kmap.cuh", "inflate.hpp", "pgunzip.hpp", "deflate_fast.hpp")] + [os.path.join(HERE, "..", "include", "nimble_b200.h")]
     if force or _stale(SO, deps):
         objs = []
         for s in srcs:

@@ -27,6 +27,7 @@
 
 #include "host.hpp"
 #include "inflate.hpp"
+#include "deflate_fast.hpp"
 
 using namespace nb;
 typedef int32_t i32;
@@ -679,6 +680,17 @@ bool gzip_member(const std::string& text, int level, std::string& out) {
 
 }  // namespace
 
+// host-only: one gzip member made by the rows stage's compressor (deflate_fast.hpp) — tests inflate it with zlib
+extern "C" int nb_gzip_fast(const void* in, uint64_t in_len, void* out, uint64_t out_cap, uint64_t* out_len) {
+  if ((!in && in_len) || (!out && out_cap) || !out_len) return fail(NB_ERR_INVALID, "null argument");
+  std::unique_ptr<nbz::FastDeflate> fd(new nbz::FastDeflate()); std::string o;
+  fd->gzip_member((const u8*)in, in_len, o);
+  *out_len = o.size();
+  if (o.size() > out_cap) return fail(NB_ERR_OVERFLOW, "output buffer too small");
+  memcpy(out, o.data(), o.size());
+  return NB_OK;
+}
+
 // process::bam::process behind main.rs's library loop (src/bin/main.rs:95-156)
 extern "C" int nb_process_bam(const char* input_file, const char* const* reference_json, const char* const* output_paths, uint32_t n_refs, int strand_filter,
                               const char* trim /* "L:S,L:S" or NULL */, int num_cores, int force_bam_paired, int device) {
@@ -710,7 +722,7 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
   else if (const char* e2 = getenv("NB_BAM_WINDOW_MB")) window_bytes = (size_t)strtoull(e2, nullptr, 10) << 20;
   if (rc != NB_OK) { cleanup(); return rc; }
   const size_t BATCH_PAIRS = 1u << 20;
-  int GZ_LEVEL = 2;   // NB_BAM_GZ_LEVEL=1..9 overrides (the rows are the same, the members smaller or faster to make)
+  int GZ_LEVEL = 0;   // 0: the rows' own compressor (deflate_fast.hpp); NB_BAM_GZ_LEVEL=1..9: zlib at that level (the rows are the same, the members smaller or slower to make)
   if (const char* e = getenv("NB_BAM_GZ_LEVEL")) { int v = atoi(e); if (v >= 1 && v <= 9) GZ_LEVEL = v; }
   // Three stages run concurrently on consecutive batches: (F) the host threads fill batch k+1 into pinned buffers,
   // (D) the device aligns batch k and its counts are finalized, (R) the host threads format + gzip the rows of batch k-1.
@@ -842,12 +854,16 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
           }
           for (size_t pj = 0; pj < gp; pj++) { if (!scored.empty() && is_scored(v[2 * pj + 1])) continue; emit(no_feats, 0, pj); }   // zero rows (332-353)
         }
-        if (!text.empty()) { wrote[t] = 1; if (!gzip_member(text, GZ_LEVEL, member[t])) bad[t] = 1; }
+        if (!text.empty()) {
+          wrote[t] = 1;
+          if (GZ_LEVEL) { if (!gzip_member(text, GZ_LEVEL, member[t])) bad[t] = 1; }
+          else { std::unique_ptr<nbz::FastDeflate> fd(new nbz::FastDeflate()); member[t].reserve(text.size() / 16 + 4096); fd->gzip_member((const u8*)text.data(), text.size(), member[t]); }
+        }
       } });
     bool any = false; for (int t = 0; t < parts; t++) { if (bad[t]) return fail(NB_ERR_IO, "gzip of the TSV rows failed"); any = any || wrote[t]; }
     if (any && first_write[li]) {
       std::string header = "nimble_features\tnimble_score\t" + data_header("r1") + "\t" + data_header("r2") + "\tr1_filter_forward\tr1_forward_score\tr1_filter_reverse\tr1_reverse_score\tr2_filter_forward\tr2_forward_score\tr2_filter_reverse\tr2_reverse_score\ttriage_reason\taligndirection\n";
-      std::string hm; if (!gzip_member(header, GZ_LEVEL, hm) || fwrite(hm.data(), 1, hm.size(), outs[li]) != hm.size()) return fail(NB_ERR_IO, "short write on the TSV"); first_write[li] = false; }
+      std::string hm; if (!gzip_member(header, GZ_LEVEL ? GZ_LEVEL : 2, hm) || fwrite(hm.data(), 1, hm.size(), outs[li]) != hm.size()) return fail(NB_ERR_IO, "short write on the TSV"); first_write[li] = false; }
     for (int t = 0; t < parts; t++) if (wrote[t] && fwrite(member[t].data(), 1, member[t].size(), outs[li]) != member[t].size()) return fail(NB_ERR_IO, "short write on the TSV");
     ns_rows += (u64)((now() - tb) * 1e9);
     return NB_OK;
@@ -916,7 +932,7 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
   }
   t_load = t_prod; t_group = 0;
   t_fill = ns_fill.load() * 1e-9; t_rows = ns_rows.load() * 1e-9;
-  if (rc == NB_OK) for (u32 li = 0; li < n_refs; li++) if (first_write[li]) { std::string em; if (!gzip_member(std::string(), GZ_LEVEL, em) || fwrite(em.data(), 1, em.size(), outs[li]) != em.size()) rc = fail(NB_ERR_IO, "short write on the TSV"); }   // no row at all: an empty gzip stream, like the reference's untouched GzEncoder
+  if (rc == NB_OK) for (u32 li = 0; li < n_refs; li++) if (first_write[li]) { std::string em; if (!gzip_member(std::string(), GZ_LEVEL ? GZ_LEVEL : 2, em) || fwrite(em.data(), 1, em.size(), outs[li]) != em.size()) rc = fail(NB_ERR_IO, "short write on the TSV"); }   // no row at all: an empty gzip stream, like the reference's untouched GzEncoder
   if (getenv("NB_BAM_STATS")) {
     // peak resident set of THIS process image (VmHWM belongs to the mm, so unlike ru_maxrss it does not start at the forking parent's size)
     double hwm_mb = 0; if (FILE* st = fopen("/proc/self/status", "r")) { char line[256]; while (fgets(line, sizeof line, st)) if (!strncmp(line, "VmHWM:", 6)) hwm_mb = strtod(line + 6, nullptr) / 1024.0; fclose(st); }

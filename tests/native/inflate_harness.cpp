@@ -4,6 +4,7 @@
 // when both accept, or the parallel and the serial reader disagreeing.  Built and run by tests/test_inflate_cpu.py with
 // -fsanitize=address,undefined (and by hand with -fsanitize=thread).
 #include "../../nimble_aligner_b200/csrc/pgunzip.hpp"
+#include "../../nimble_aligner_b200/csrc/deflate_fast.hpp"
 #include <cstdio>
 #include <random>
 #include <string>
@@ -38,6 +39,12 @@ int main(int argc, char** argv) {
     bool ok = zref(in, want);
     for (int T : {1, 3}) for (size_t C : {(size_t)4096, (size_t)30000}) { int r = ours_par(in, T, C, got); if ((r == 0) != ok || (ok && got != want)) { printf("%s: parallel T=%d C=%zu mismatch (r=%d ok=%d)\n", argv[i], T, C, r, ok); bad++; } }
     for (size_t w : {(size_t)300, (size_t)5000, (size_t)(1 << 20)}) { int r = ours_ser(in, w, got); if ((r == 0) != ok || (ok && got != want)) { printf("%s: serial window %zu mismatch\n", argv[i], w); bad++; } }
+    if (ok) {   // the BAM driver's compressor on the same text: zlib and the serial reader must give it back
+      std::string z; FastDeflate fd; fd.gzip_member(want.data(), want.size(), z);
+      std::vector<u8> zin(z.begin(), z.end()), back;
+      if (!zref(zin, back) || back != want) { printf("%s: fast deflate -> zlib mismatch\n", argv[i]); bad++; }
+      if (ours_ser(zin, 70000, got) != 0 || got != want) { printf("%s: fast deflate -> own inflate mismatch\n", argv[i]); bad++; }
+    }
     if (in.size() > 5000000 || want.size() > 5000000) continue;
     for (int f = 0; f < 12; f++) {      // damaged copies: any outcome but a crash / sanitizer report / different text than zlib when both accept
       std::vector<u8> d = in; if (f % 3 == 0) d.resize(rng() % d.size()); else for (int k = 0; k < 1 + (int)(rng() % 3); k++) d[rng() % d.size()] = (u8)rng();

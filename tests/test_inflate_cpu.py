@@ -291,3 +291,49 @@ def test_inflate_under_sanitizers(tmp_path):
     p = tmp_path / "members.gz"; p.write_bytes(b"".join(gzip.compress(data[a:a + 70_000], 6) for a in range(0, len(data), 70_000)) + b"\0" * 50); files.append(str(p))
     r = subprocess.run([exe] + files, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "done: 0 problems" in r.stdout and "runtime error" not in r.stderr and "ERROR" not in r.stderr, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+# ---------------------------------------------------------------------------------------------- the BAM driver's TSV compressor
+def test_fast_deflate_round_trips(tmp_path):
+    """deflate_fast.hpp (the rows stage's gzip members): whatever goes in must come out of zlib and of inflate.hpp unchanged —
+    corpus files, row text as the driver writes it, inputs around the block size (64 Ki tokens), tiny inputs, runs at the
+    maximum match length and distance."""
+    import synth
+    from tests.bamcases import make_bam
+    import os
+    cases = dict(CORPUS)
+    L = synth.SynthLibrary(seed=1234, n_fam=20, n_all=5)
+    bam = make_bam(str(tmp_path / "t.bam"), L, n_groups=1500)
+    os.environ["NB_BAM_DUMP_ROWFMT"] = "1"
+    try:
+        nb.bam_dump_groups(bam, str(tmp_path / "rows.txt"), num_cores=2)
+    finally:
+        del os.environ["NB_BAM_DUMP_ROWFMT"]
+    rows = open(tmp_path / "rows.txt", "rb").read()
+    assert len(rows) > 1_000_000
+    cases["rows"] = rows
+    rng = random.Random(12)
+    cases["literals_over_a_block"] = bytes(rng.randrange(256) for _ in range(70_000))                 # > 64 Ki literal tokens: two blocks
+    cases["exactly_a_block"] = bytes(rng.randrange(256) for _ in range(65_536 + 12))
+    cases["one_symbol"] = b"a" * 100_000
+    cases["two_symbols"] = bytes(rng.choice(b"ab") for _ in range(50_000))
+    cases["max_distance"] = (lambda blk: blk + bytes(rng.randrange(256) for _ in range(32768 - len(blk))) + blk * 3)(bytes(rng.randrange(256) for _ in range(300)))
+    for n in range(0, 40):
+        cases["tiny%d" % n] = bytes(rng.choice(b"abc") for _ in range(n))
+    for name, data in cases.items():
+        g = nb.gzip_fast(data)
+        assert zlib.decompress(g, 31) == data, name
+        assert nb.inflate(g, window=4096 if len(data) else 0, out_cap=len(data) + 64) == data, name
+    assert len(nb.gzip_fast(rows)) < len(zlib.compress(rows, 2)) * 1.1              # no worse than the zlib level it replaces
+    for it in range(300):                                                           # structured random inputs: repeats at all distances and lengths
+        parts = []
+        for _ in range(rng.randint(1, 60)):
+            k = rng.random()
+            if k < 0.3 and parts:
+                parts.append(rng.choice(parts)[:rng.randint(1, 400)])
+            elif k < 0.5:
+                parts.append(bytes([rng.randrange(256)]) * rng.randint(1, 600))
+            else:
+                parts.append(bytes(rng.randrange(256) for _ in range(rng.randint(1, 200))))
+        data = b"".join(parts)
+        assert zlib.decompress(nb.gzip_fast(data), 31) == data
