@@ -320,6 +320,12 @@ def test_fast_deflate_round_trips(tmp_path):
     cases["max_distance"] = (lambda blk: blk + bytes(rng.randrange(256) for _ in range(32768 - len(blk))) + blk * 3)(bytes(rng.randrange(256) for _ in range(300)))
     for n in range(0, 40):
         cases["tiny%d" % n] = bytes(rng.choice(b"abc") for _ in range(n))
+    fib = [1, 1]                                       # Fibonacci literal frequencies: the unlimited Huffman tree is 20 levels deep, the 15-bit limit has to be enforced
+    while sum(fib) + fib[-1] + fib[-2] < 60_000:
+        fib.append(fib[-1] + fib[-2])
+    deep = [sym * 7 % 256 for sym, f in enumerate(fib) for _ in range(f)]
+    rng.shuffle(deep)
+    cases["deep_tree"] = bytes(deep)
     for name, data in cases.items():
         g = nb.gzip_fast(data)
         assert zlib.decompress(g, 31) == data, name
