@@ -25,6 +25,8 @@
 #include <unordered_set>
 #include <vector>
 
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include "host.hpp"
 #include "inflate.hpp"
 #include "deflate_fast.hpp"
@@ -56,12 +58,19 @@ struct RawBuf {
 // holds one UMI at a time, src/parse/sorted_bam_reader.rs:31-107, and its channel 50 groups, src/process/bam.rs:149).
 struct Bgzf {
   FILE* f = nullptr; std::string path; std::vector<u8> cbuf; size_t cpos = 0, cend = 0; bool file_done = false;
+  const u8* map = nullptr; size_t map_size = 0;   // a regular file is mapped: the blocks are inflated straight out of the page cache (fread copied every compressed byte once more, on one thread)
   RawBuf data;   // whole-stream mode (window = everything): kept for callers that want one buffer
-  ~Bgzf() { if (f) fclose(f); }
+  ~Bgzf() { if (map) munmap((void*)map, map_size); if (f) fclose(f); }
+  const u8* cdata() const { return map ? map : cbuf.data(); }
   int open(const std::string& p) {
     path = p; f = fopen(p.c_str(), "rb");
     if (!f) return fail(NB_ERR_IO, "could not open " + p);
     cpos = cend = 0; file_done = false;
+    struct stat st;
+    if (!getenv("NB_BAM_NO_MMAP") && fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+      void* q = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+      if (q != MAP_FAILED) { map = (const u8*)q; map_size = (size_t)st.st_size; madvise(q, map_size, MADV_SEQUENTIAL); cend = map_size; file_done = true; }
+    }
     return NB_OK;
   }
   // Appends the inflated bytes of the next blocks (at least one block, about `target` bytes, everything left when target is
@@ -73,17 +82,17 @@ struct Bgzf {
     for (;;) {
       const size_t avail = cend - cpos;
       if (avail < 18) { if (!refill(18)) { if (avail == 0) break; return fail(NB_ERR_PARSE, "truncated BGZF block at the end of " + path); } continue; }
-      const u8* h = &cbuf[cpos];
+      const u8* const cb = cdata(); const u8* h = cb + cpos;
       if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return fail(NB_ERR_PARSE, "not a BGZF file: " + path);
       // every size field comes from the file: nothing is read or handed to inflate() before it is checked against the
       // block and the bytes that are really there (a damaged BAM must fail with NB_ERR_PARSE, never read out of bounds)
       const size_t xlen = h[10] | (h[11] << 8);
       if (avail < 12 + xlen) { if (!refill(12 + xlen)) return fail(NB_ERR_PARSE, "corrupt BGZF block (extra field runs past the end of the file) in " + path); continue; }
       size_t q = cpos + 12, xend = q + xlen, bsize = 0;
-      while (q + 4 <= xend) { size_t slen = cbuf[q + 2] | (cbuf[q + 3] << 8); if (q + 4 + slen > xend) break; if (cbuf[q] == 'B' && cbuf[q + 1] == 'C' && slen == 2) bsize = (cbuf[q + 4] | (cbuf[q + 5] << 8)) + 1; q += 4 + slen; }
+      while (q + 4 <= xend) { size_t slen = cb[q + 2] | (cb[q + 3] << 8); if (q + 4 + slen > xend) break; if (cb[q] == 'B' && cb[q + 1] == 'C' && slen == 2) bsize = (cb[q + 4] | (cb[q + 5] << 8)) + 1; q += 4 + slen; }
       if (!bsize || 12 + xlen + 8 > bsize) return fail(NB_ERR_PARSE, "corrupt BGZF block in " + path);
       if (avail < bsize) { if (!refill(bsize)) return fail(NB_ERR_PARSE, "corrupt BGZF block (runs past the end of the file) in " + path); continue; }
-      const size_t isize = cbuf[cpos + bsize - 4] | (cbuf[cpos + bsize - 3] << 8) | (cbuf[cpos + bsize - 2] << 16) | ((size_t)cbuf[cpos + bsize - 1] << 24);
+      const size_t isize = cb[cpos + bsize - 4] | (cb[cpos + bsize - 3] << 8) | (cb[cpos + bsize - 2] << 16) | ((size_t)cb[cpos + bsize - 1] << 24);
       if (isize > 65536) return fail(NB_ERR_PARSE, "corrupt BGZF block (ISIZE beyond 64 KiB) in " + path);
       blks.push_back({xend, bsize - (xend - cpos) - 8, utot, isize});
       utot += isize; cpos += bsize;
@@ -95,7 +104,7 @@ struct Bgzf {
     // grow `out` keeping its first `keep` bytes
     if (out.size() < keep + utot) { RawBuf nb2; if (!nb2.alloc(keep + utot + (utot >> 3) + 64)) return fail(NB_ERR_IO, "out of memory inflating " + path); if (keep) memcpy(nb2.data(), out.data(), keep); std::swap(out.p, nb2.p); std::swap(out.n, nb2.n); }
     std::atomic<size_t> next_blk(0); std::atomic<int> bad(0);
-    u8* dst = out.data() + keep; const u8* src = cbuf.data();
+    u8* dst = out.data() + keep; const u8* src = cdata();
     const bool check_crc = !getenv("NB_BAM_NO_CRC");
     auto work = [&]() {
       // inflate.hpp's decoder, one block in one piece into its place in the window (it never writes past the block's
@@ -131,7 +140,7 @@ struct Bgzf {
   }
  public:
   // between windows: drop the consumed compressed bytes
-  void compact() { if (cpos) { memmove(cbuf.data(), cbuf.data() + cpos, cend - cpos); cend -= cpos; cpos = 0; } }
+  void compact() { if (map) return; if (cpos) { memmove(cbuf.data(), cbuf.data() + cpos, cend - cpos); cend -= cpos; cpos = 0; } }
 };
 
 struct Rec {   // one decoded BAM record (views into Bgzf::data stay valid for the run)

@@ -11,8 +11,11 @@ from oracle import bam_ref
 from tests.bamcases import make_bam
 
 
+@pytest.mark.parametrize("no_mmap", [False, True])
 @pytest.mark.parametrize("force_paired", [False, True])
-def test_feeder_groups_match_python_restatement(tmp_path, force_paired):
+def test_feeder_groups_match_python_restatement(tmp_path, monkeypatch, force_paired, no_mmap):
+    if no_mmap:
+        monkeypatch.setenv("NB_BAM_NO_MMAP", "1")      # the read() path kept for inputs that cannot be mapped (pipes)
     L = synth.SynthLibrary(seed=1234, n_fam=20, n_all=5)
     bam = make_bam(str(tmp_path / "t.bam"), L, n_groups=200)
     out = str(tmp_path / "groups.tsv")
