@@ -344,7 +344,7 @@ struct GzParStream : SegStream {
     struct stat st; if (fstat(fd, &st) != 0) return false;
     size = (size_t)st.st_size;
     if (size) { void* q = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0); if (q == MAP_FAILED) return false; map = (const u8*)q; madvise(q, size, MADV_SEQUENTIAL); }
-    size_t cbytes = (size_t)1 << 20;                                                  // compressed bytes per chunk (about 4 MB of text)
+    size_t cbytes = (size_t)2 << 20;                                                  // compressed bytes per chunk: about 8 MB of text = 25 k records, the plain-text parser's granularity (one nb_align_batch call per segment: smaller chunks made the calls, not the inflate, the bound on the box)
     if (const char* e = getenv("NB_GZ_CHUNK_KB")) { const size_t kb = (size_t)strtoull(e, nullptr, 10); if (kb >= 1) cbytes = kb << 10; }
     const int n_segs = 2 * (2 * threads + 2) + 3 + extra + 4;                         // two per chunk in flight (its records, the junction's) + what the consumer holds
     for (int i = 0; i < n_segs; i++) { segs.emplace_back(new Segment()); free_segs.push_back(segs.back().get()); }
