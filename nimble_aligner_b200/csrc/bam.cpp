@@ -578,12 +578,15 @@ struct GroupStreamer {
       parallel_ranges(T, R, [&](size_t ra, size_t rb, int) {
         size_t t = 0; for (int k = 0; k < T; k++) if (R * (size_t)k / T == ra) t = k;   // the slice parallel_ranges gave this thread
         std::vector<Rec>& out = outs[t]; std::vector<Rec> buf, tmp;
+        out.reserve((force_paired ? 1 : 2) * (run[rb] - run[ra]));   // (a dummy mate per unpaired record at most)
         for (size_t r = ra; r < rb; r++) if (!emit_run(r, out, buf, tmp)) { first_empty[t] = r; return; }   // next() returns None on an empty buffer: the stream ends here
       });
       std::vector<Rec>& stream = w.stream; bool cut = false;
-      size_t total = 0; for (int t = 0; t < T; t++) { total += outs[t].size(); if (first_empty[t] != (size_t)-1) break; }
-      stream.reserve(total);
-      for (int t = 0; t < T; t++) { stream.insert(stream.end(), outs[t].begin(), outs[t].end()); std::vector<Rec>().swap(outs[t]); if (first_empty[t] != (size_t)-1) { cut = true; break; } }
+      // the slices' records in order, up to the slice where the stream ends (copied by all threads: tens of millions of records per window)
+      int t_used = 0; std::vector<size_t> at(T + 1, 0);
+      for (int t = 0; t < T; t++) { at[t + 1] = at[t] + outs[t].size(); t_used = t + 1; if (first_empty[t] != (size_t)-1) { cut = true; break; } }
+      stream.resize(at[t_used]);
+      parallel_ranges(std::min(T, t_used), (size_t)t_used, [&](size_t ta, size_t tb, int) { for (size_t t = ta; t < tb; t++) { if (!outs[t].empty()) memcpy((void*)&stream[at[t]], (const void*)outs[t].data(), outs[t].size() * sizeof(Rec)); std::vector<Rec>().swap(outs[t]); } });
       if (cut) { ended = true; w.carry_from = w.len; }   // the reference's reader stops for good at an empty buffer
       const bool final = eof || ended;
       header_done = true; records_seen += all.size();
