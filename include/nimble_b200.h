@@ -109,6 +109,12 @@ void nb_index_free(nb_index*);
 /* on-disk index cache: the flat arrays exactly as they are uploaded (the reference rebuilds its index on every run) */
 int nb_index_save(const nb_index*, const char* path);
 int nb_index_load(const char* path, nb_index** out);
+/* the cache keyed by the library: key = 32 hex digits over the sequence column as the index sees it
+ * (case and non-ACGT folded like DnaString::from_acgt_bytes) and the artefact's format tag.  nb_index_build_cached loads
+ * <cache_dir>/<key>.nbix when it is there and sound, else builds on GPU `device` and writes it (temporary name + rename);
+ * cache_dir NULL: $NB_INDEX_CACHE, and with neither set it is nb_index_build_gpu.  The file drivers and the CLI go through it. */
+int nb_index_cache_key(const nb_library* lib, char out_hex[33]);
+int nb_index_build_cached(const nb_library* lib, const char* cache_dir, int device, int n_threads, nb_index** out);
 /* out[0..7] = n_kmers, n_nodes, n_colours, colour_elems, unitig_bases, table_slots, device_bytes, n_sequences */
 int nb_index_stats(const nb_index*, uint64_t* out8);
 /* canonical text dump (one line per unitig, sorted) used by the parity tests; returns bytes needed */

@@ -138,6 +138,8 @@ _SIGS = {
     "nb_fastq_dump": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_char_p]),
     "nb_gunzip_parallel": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "nb_gzip_fast": (C.c_int, [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "nb_index_cache_key": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "nb_index_build_cached": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "nb_inflate": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "nb_process_fastq_devices": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint32]),
     "nb_process_bam": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]),
@@ -289,6 +291,19 @@ class Index:
 
     def save(self, path):
         _ck(lib().nb_index_save(self.h, str(path).encode()))
+
+    @classmethod
+    def build_cached(cls, library, cache_dir, device=0, threads=1):
+        """<cache_dir>/<key of the library>.nbix when it is there, else the CUDA builder + that file (nb_index_build_cached)."""
+        h = C.c_void_p()
+        _ck(lib().nb_index_build_cached(library.h, str(cache_dir).encode() if cache_dir is not None else None, device, threads, C.byref(h)))
+        return cls(h)
+
+    @staticmethod
+    def cache_key(library):
+        buf = C.create_string_buffer(33)
+        _ck(lib().nb_index_cache_key(library.h, buf))
+        return buf.value.decode()
 
     @classmethod
     def load(cls, path):

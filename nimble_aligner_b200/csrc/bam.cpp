@@ -724,7 +724,7 @@ extern "C" int nb_process_bam(const char* input_file, const char* const* referen
   for (u32 i = 0; i < n_refs && rc == NB_OK; i++) {
     rc = nb_library_load_json(reference_json[i], strand_filter, &libs[i]);
     if (rc == NB_OK && !trims.empty()) { nb_config c; nb_library_get_config(libs[i], &c); c.trim_target_length = trims[i].first; c.trim_strictness = trims[i].second; rc = nb_library_set_config(libs[i], &c); }
-    if (rc == NB_OK) rc = nb_index_build_gpu(libs[i], device, threads, &idx[i]);   // K5: the CUDA builder (same artefact as the host builder)
+    if (rc == NB_OK) rc = nb_index_build_cached(libs[i], nullptr, device, threads, &idx[i]);   // K5: the CUDA builder (same artefact as the host builder), or $NB_INDEX_CACHE
     if (rc == NB_OK) rc = nb_ctx_create(idx[i], libs[i], device, nullptr, &ctx[i]);
     if (rc == NB_OK) rc = nb_ctx_set_option(ctx[i], "agg_slots", 1u << 23);   // a batch of 2^20 pairs can hold that many one-pair scopes, each with its own (scope, callset) row: stay under half full
     if (rc == NB_OK) { outs[i] = fopen(output_paths[i], "wb"); if (!outs[i]) rc = fail(NB_ERR_IO, std::string("could not open output ") + output_paths[i]); }

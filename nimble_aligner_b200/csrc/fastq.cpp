@@ -572,7 +572,7 @@ extern "C" int nb_process_fastq_devices(const char* const* input_files, uint32_t
     const double t0 = now();
     int rc = nb_library_load_json(reference_json[li], strand_filter, &lib);
     const double t1 = now();
-    if (rc == NB_OK) rc = nb_index_build_gpu(lib, devices[0], std::max(1, num_cores), &ix);   // K5: the CUDA builder (same artefact as nb_index_build)
+    if (rc == NB_OK) rc = nb_index_build_cached(lib, nullptr, devices[0], std::max(1, num_cores), &ix);   // K5: the CUDA builder (same artefact as nb_index_build), or $NB_INDEX_CACHE
     const double t2 = now();
     for (u32 d = 0; d < W && rc == NB_OK; d++) { rc = nb_ctx_create(ix, lib, devices[d], nullptr, &ctx[d]); if (rc == NB_OK) rc = nb_ctx_set_option(ctx[d], "max_batch_pairs", BATCH); }
     if (rc == NB_OK && W > 1) {

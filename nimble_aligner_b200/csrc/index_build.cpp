@@ -17,6 +17,7 @@
 #include <thread>
 #include <unordered_map>
 
+#include <unistd.h>
 #include "host.hpp"
 #include "khash.h"
 
@@ -424,3 +425,44 @@ extern "C" int nb_index_load(const char* path, nb_index** out) {
   if (!ok) { delete ix; return fail(NB_ERR_PARSE, std::string("not a nimble_b200 index file (or truncated / damaged): ") + path); }
   *out = ix; return NB_OK;
 }
+
+// ---- index cache keyed by the library's sequences (the reference rebuilds its index on every run,
+// src/reference_library.rs + debruijn_mapping build_index).  The index is a function of the sequence column alone, after
+// DnaString::from_acgt_bytes' folding (case, non-ACGT -> A): the key hashes exactly that, two independent 64-bit sums, plus
+// the artefact's format tag, so a cache written by another layout version is simply not found.
+extern "C" int nb_index_cache_key(const nb_library* lib, char out_hex[33]) {
+  if (!lib || !out_hex) return fail(NB_ERR_INVALID, "null argument");
+  const std::vector<std::string>& col = lib->columns[lib->seq_idx];
+  u64 h1 = 0x243F6A8885A308D3ULL, h2 = 0x13198A2E03707344ULL;
+  auto mix = [&](u64 w) { h1 = (h1 ^ w) * 0x9E3779B97F4A7C15ULL; h1 ^= h1 >> 29; h2 = (h2 + w) * 0xC2B2AE3D27D4EB4FULL; h2 ^= h2 >> 32; };
+  { u64 tag; memcpy(&tag, INDEX_MAGIC, 8); mix(tag); mix((u64)col.size()); }
+  for (const std::string& q : col) {
+    mix((u64)q.size());
+    u64 w = 0; int n = 0;
+    for (size_t i = 0; i < q.size(); i++) { w = (w << 2) | base_code((u8)q[i]); if (++n == 32) { mix(w); w = 0; n = 0; } }
+    if (n) mix(w ^ ((u64)n << 58) ^ 0x8000000000000000ULL);
+  }
+  mix(h1 ^ (h2 >> 7));
+  snprintf(out_hex, 33, "%016llx%016llx", (unsigned long long)h1, (unsigned long long)h2);
+  return NB_OK;
+}
+// The index of `lib`: from <cache_dir>/<key>.nbix when that file is there and sound, else built on GPU `device` and written
+// there (to a temporary name first: a reader never sees half a file).  cache_dir NULL: $NB_INDEX_CACHE; neither: just built.
+// A cache that cannot be written is reported on stderr and otherwise ignored.
+extern "C" int nb_index_build_cached(const nb_library* lib, const char* cache_dir, int device, int n_threads, nb_index** out) {
+  if (!lib || !out) return fail(NB_ERR_INVALID, "null argument");
+  if (!cache_dir || !*cache_dir) cache_dir = getenv("NB_INDEX_CACHE");
+  if (!cache_dir || !*cache_dir) return nb_index_build_gpu(lib, device, n_threads, out);
+  char key[33]; int rc = nb_index_cache_key(lib, key); if (rc) return rc;
+  const std::string path = std::string(cache_dir) + "/" + key + ".nbix";
+  if (nb_index_load(path.c_str(), out) == NB_OK) {
+    if ((*out)->n_sequences == lib->columns[lib->seq_idx].size()) return NB_OK;
+    nb_index_free(*out); *out = nullptr;              // (a key collision would have to get past this and the checksum)
+  }
+  rc = nb_index_build_gpu(lib, device, n_threads, out);
+  if (rc) return rc;
+  const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+  if (nb_index_save(*out, tmp.c_str()) != NB_OK || rename(tmp.c_str(), path.c_str()) != 0) { remove(tmp.c_str()); fprintf(stderr, "nimble_b200: could not write the index cache %s (continuing without it)\n", path.c_str()); }
+  return NB_OK;
+}
+

@@ -106,3 +106,21 @@ def test_gpu_index_big_components_and_save_load(tmp_path):
     assert dev.dump() == orc.Oracle(ocfg, oref).index_dump()
     dev.save(tmp_path / "big.nbidx")
     assert nb.Index.load(tmp_path / "big.nbidx").compare(dev) == 0
+
+
+def test_index_cache_miss_then_hit(tmp_path):
+    """nb_index_build_cached (what the file drivers call): a miss builds on the GPU and leaves <key>.nbix behind, the next
+    call takes that file; both are the host builder's artefact."""
+    _, lib = nb.get_reference_library(os.path.join(G, "libraries", "basic.json"))
+    cache = tmp_path / "cache"; cache.mkdir()
+    a = nb.Index.build_cached(lib, cache, device=0, threads=2)
+    key = nb.Index.cache_key(lib)
+    assert sorted(x.name for x in cache.iterdir()) == [key + ".nbix"]
+    stamp = (cache / (key + ".nbix")).stat().st_mtime_ns
+    b = nb.Index.build_cached(lib, cache, device=0, threads=2)
+    assert (cache / (key + ".nbix")).stat().st_mtime_ns == stamp          # not rebuilt
+    host = nb.build_index(lib, 2)
+    assert a.compare(host) == 0 and b.compare(host) == 0
+    # a cache directory that cannot be written is not an error: the index is built and used
+    c = nb.Index.build_cached(lib, tmp_path / "does" / "not" / "exist", device=0, threads=2)
+    assert c.compare(host) == 0

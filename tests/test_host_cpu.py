@@ -231,3 +231,53 @@ def test_index_compare_and_gpu_builder_fails_loudly_without_a_gpu():
         with pytest.raises(nb.NbError) as e:
             nb.Index.from_sequences(seqs, 1, device=0)
         assert e.value.code == -6
+
+
+def test_index_cache_keyed_by_the_library(tmp_path):
+    """the drivers take the index from $NB_INDEX_CACHE/<key>.nbix when it is there.  The key follows the
+    sequence column as the index sees it (case and non-ACGT folded) and nothing else; a hit needs no GPU; a damaged file is
+    not a hit."""
+    import json
+    base = json.load(open(os.path.join(G, "libraries", "basic.json")))
+
+    def lib_of(obj, name):
+        p = tmp_path / name
+        p.write_text(json.dumps(obj))
+        return nb.get_reference_library(str(p))[1]
+    lib = lib_of(base, "a.json")
+    key = nb.Index.cache_key(lib)
+    assert re.fullmatch(r"[0-9a-f]{32}", key) and key == nb.Index.cache_key(lib_of(base, "b.json"))
+    # same index: case folds like DnaString::from_acgt_bytes (the key sees the sequence column after the library's own
+    # reverse-complement rows were added, so a letter that complements differently is another index)
+    txt = json.dumps(base)
+    seqs = sorted(set(re.findall(r'"([ACGT]{40,})"', txt)), key=len, reverse=True)
+    assert seqs
+    folded = txt.replace(seqs[0], seqs[0].lower(), 1)
+    lf = lib_of(json.loads(folded), "c.json")
+    assert (nb.Index.cache_key(lf) == key) == (nb.build_index(lf, 1).compare(nb.build_index(lib, 1)) == 0)
+    # another index: one base changed
+    s0 = seqs[0]; changed = txt.replace(s0, s0[:10] + ("C" if s0[10] != "C" else "G") + s0[11:], 1)
+    assert nb.Index.cache_key(lib_of(json.loads(changed), "d.json")) != key
+    # a hit: the file written under the key is taken, no device involved
+    cache = tmp_path / "cache"; cache.mkdir()
+    host = nb.build_index(lib, 2)
+    host.save(cache / (key + ".nbix"))
+    hit = nb.Index.build_cached(lib, cache, device=0, threads=2)
+    assert hit.compare(host) == 0 and hit.dump() == host.dump()
+    os.environ["NB_INDEX_CACHE"] = str(cache)
+    try:
+        assert nb.Index.build_cached(lib, None, device=0, threads=2).compare(host) == 0       # the drivers' way: through the environment
+    finally:
+        del os.environ["NB_INDEX_CACHE"]
+    if nb.lib().nb_device_count() == 0:
+        # a miss (another library, or a damaged file) means building, which needs the device — loudly
+        for obj, name in ((json.loads(changed), "e.json"),):
+            with pytest.raises(nb.NbError) as e:
+                nb.Index.build_cached(lib_of(obj, name), cache, device=0)
+            assert e.value.code == -6
+        good = (cache / (key + ".nbix")).read_bytes()
+        (cache / (key + ".nbix")).write_bytes(good[:len(good) // 2])
+        with pytest.raises(nb.NbError) as e:
+            nb.Index.build_cached(lib, cache, device=0)
+        assert e.value.code == -6
+        assert sorted(x.name for x in cache.iterdir()) == [key + ".nbix"]                        # no temporary files left behind
