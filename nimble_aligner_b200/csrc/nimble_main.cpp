@@ -25,6 +25,7 @@ int main(int argc, char** argv) {
     if (a == "-t" || a == "--trim") { trim = val("--trim"); have_trim = true; cur = nullptr; continue; }
     if (a == "-p" || a == "--force_bam_paired") { force_paired = true; cur = nullptr; continue; }
     if (a == "-d" || a == "--devices") { devs = val("--devices"); cur = nullptr; continue; }   // not in cli.yml: which GPUs to use, "0,1,..." (default: NB_DEVICES or 0)
+    if (a == "--index-cache") { const std::string dir = val("--index-cache"); setenv("NB_INDEX_CACHE", dir.c_str(), 1); cur = nullptr; continue; }   // not in cli.yml: keep each library's index in <dir>/<key>.nbix (default: NB_INDEX_CACHE, else rebuilt per run like the reference)
     if (a == "-h" || a == "--help") { printf("nimble 0.8.0 (B200)\nUSAGE: nimble [FLAGS] [OPTIONS] --input <input>... --output <output>... --reference <reference>...\n"); return 0; }
     if (a == "-V" || a == "--version") { printf("nimble 0.8.0\n"); return 0; }
     if (!cur) die("error: Found argument '" + a + "' which wasn't expected, or isn't valid in this context");

@@ -40,6 +40,7 @@ def test_help_and_version():
     (("-r", "a.json", "b.json", "-o", "a.tsv", "b.tsv", "-i", "a.fastq", "-t", "40:0.5"), "number of trim options does not match"),
     (("-r", "lib.json", "-o", "out.tsv", "-i", "a.fastq", "-d", "0,x"), "comma-separated list of GPU ordinals"),
     (("-r", "lib.json", "-o", "out.tsv", "-i", "a.fastq", "-c"), "requires a value"),
+    (("-r", "lib.json", "-o", "out.tsv", "-i", "a.fastq", "--index-cache"), "requires a value"),
     (("-r", "lib.json", "-o", "out.tsv", "-i", "reads.sam"), "Unsupported file format: sam"),
     (("-r", "a.json", "b.json", "-o", "a.tsv", "-i", "a.fastq"), "one output path per reference library"),
     (("stray",), "wasn't expected"),
