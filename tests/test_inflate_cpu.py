@@ -331,6 +331,11 @@ def test_fast_deflate_round_trips(tmp_path):
         assert zlib.decompress(g, 31) == data, name
         assert nb.inflate(g, window=4096 if len(data) else 0, out_cap=len(data) + 64) == data, name
     assert len(nb.gzip_fast(rows)) < len(zlib.compress(rows, 2)) * 1.1              # no worse than the zlib level it replaces
+    # the TSV.gz as the driver writes it: a zlib member (the header) followed by the rows' members, read as ONE gzip stream
+    parts3 = [b"header line\n", rows[:300_000], rows[300_000:]]
+    stream = gzip.compress(parts3[0], 2) + nb.gzip_fast(parts3[1]) + nb.gzip_fast(parts3[2])
+    assert gzip.decompress(stream) == b"".join(parts3)
+    assert nb.gunzip_parallel(stream, 3, 4096, out_cap=len(rows) + 64) == b"".join(parts3)
     for it in range(300):                                                           # structured random inputs: repeats at all distances and lengths
         parts = []
         for _ in range(rng.randint(1, 60)):
